@@ -1,0 +1,151 @@
+/*
+ * patchmatch_b200.h -- C ABI of the B200-native (sm_100a) learned-PatchMatch hot path.
+ *
+ * This is the drop-in boundary: plain device pointers, sizes and a CUDA stream;
+ * no torch types.  The reference (FangjinhuaWang/PatchmatchNet) has no native
+ * layer at all -- its hot path is a chain of ATen calls inside
+ * models/patchmatch.py / models/module.py -- so each entry point below names the
+ * reference Python lines it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all tensors are fp32, dense, in the layout written beside them;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     kernels are enqueued, never synchronised -- the calls are CUDA-graph capturable;
+ *   - return value: 0 on success, negative PMB200_E* on a rejected argument,
+ *     positive cudaError_t if the launch failed.  pmb200_last_error() returns a
+ *     thread-local message for the last non-zero return.  Nothing aborts.
+ *   - re-entrant: no global mutable state; safe to call from one host thread per
+ *     GPU (the reference's nn.DataParallel threading model, train.py:282).
+ *     The caller makes the right device current (cudaSetDevice / torch.cuda.device).
+ */
+#ifndef PATCHMATCH_B200_H_
+#define PATCHMATCH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMB200_ABI_VERSION 1
+
+#define PMB200_EINVAL (-1)       /* bad size / null pointer */
+#define PMB200_EUNSUPPORTED (-2) /* combination the reference raises NotImplementedError for */
+
+#define PMB200_MAX_VIEWS 16
+#define PMB200_MAX_NEIGHBORS 32
+#define PMB200_MAX_HYPOTHESES 256
+
+int pmb200_abi_version(void);
+const char *pmb200_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * Relative projections for every (source view, batch element):
+ *     P = src_proj . inverse(ref_proj);  rt = [P[0,0..2], P[1,0..2], P[2,0..2], P[0..2,3]]
+ * Replaces torch.matmul(src_proj, torch.inverse(ref_proj)) at models/module.py:148-150,
+ * which the reference re-evaluates (with a host sync inside linalg.inv) once per source
+ * view per PatchMatch iteration; here it runs once per stage with no host sync.
+ * The 4x4 inverse is done in fp64 on the device and rounded to fp32.
+ *   ref_proj        [B,4,4], row stride 4, batch stride `ref_batch_stride` floats
+ *   src_projs_host  host array of V device pointers, each [B,4,4] with batch stride `src_batch_stride`
+ *   rt_out          [V,B,12]
+ */
+int pmb200_relative_projection(const float *ref_proj, int64_t ref_batch_stride,
+                               const float *const *src_projs_host, int64_t src_batch_stride,
+                               int V, int B, float *rt_out, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Pack n NCHW feature maps into one channels-last buffer [n,B,H,W,C] (one launch).
+ * The fused kernels read features channels-last so that each bilinear tap is one
+ * contiguous C-vector.  Not needed when the producer already emits channels-last.
+ *   maps_host  host array of n device pointers, each [B,C,H,W] contiguous
+ */
+int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, int W,
+                     float *out_nhwc, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-A: fused homography warp + bilinear gather + group-wise correlation
+ *      (+ view-weighted aggregation).
+ * Replaces, per source view, differentiable_warping (models/module.py:130-181), the
+ * broadcast multiply + mean at models/patchmatch.py:199-203 and -- when view_weights is
+ * given -- the accumulation/normalisation at models/patchmatch.py:192-194,213-217.
+ * The [B,C,D,H,W] warped tensor is never materialised.
+ *   ref_nhwc      [B,H,W,C]
+ *   src_nhwc      [V,B,Hs,Ws,C]
+ *   rt            [V,B,12] from pmb200_relative_projection
+ *   depth         [B,D,H,W]
+ *   view_weights  [B,V,H,W] or NULL
+ *   out           view_weights == NULL : per-view similarity [V,B,G,D,H,W]
+ *                 view_weights != NULL : sum_v(sim_v * w_v) / (1e-5 + sum_v w_v)  [B,G,D,H,W]
+ * Fast path for (C,G) in {(64,8),(32,8),(16,4)}; any other C % G == 0 runs a generic kernel.
+ */
+int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *rt,
+                     const float *depth, const float *view_weights, float *out,
+                     int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * View-weighted aggregation of stored per-view similarities (first iteration on the
+ * coarsest stage, where the weights come from PixelwiseNet run on those similarities):
+ *     out = sum_v(sims[v] * w[:,v]) / (1e-5 + sum_v w[:,v])
+ * Replaces models/patchmatch.py:192-194,213-217.
+ *   sims [V,B,G,D,H,W]   view_weights [B,V,H,W]   out [B,G,D,H,W]
+ */
+int pmb200_aggregate_views(const float *sims, const float *view_weights, float *out,
+                           int V, int B, int G, int D, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-A': reference-feature self-correlation at the learned evaluation neighbours.
+ * Replaces PatchMatch.get_grid(evaluation) (models/patchmatch.py:361-426) and the
+ * grid_sample + multiply + mean of FeatureWeightNet.forward (models/patchmatch.py:613-622).
+ * Neighbour k samples at (x + dx_k + offsets[2k], y + dy_k + offsets[2k+1]) with the
+ * reference's normalise(align_corners=True)/sample(align_corners=False) mismatch and
+ * border padding reproduced.
+ *   offsets  [B,2K,H,W] raw output of eval_conv;  K in {9,17};  dilation = propagation range
+ *   out      [B,G,K,H,W]
+ */
+int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out,
+                       int B, int C, int G, int H, int W, int K, int dilation, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-C: hypothesis initialisation + adaptive propagation + sort, one launch.
+ * Replaces DepthInitialization.forward (models/patchmatch.py:53-94),
+ * PatchMatch.get_grid(propagation) (:331-360,:396-426) and Propagation.forward (:115-124).
+ *   mode 0  random init : `seed_map` is U[0,1) noise [B,48,H,W] (the caller draws it with
+ *                          torch.rand so the generator stream matches the reference); Ns = 48
+ *   mode 1  perturbation: `seed_map` is the current depth [B,1,H,W]; Ns samples at
+ *                          inverse-depth steps (1/dmin - 1/dmax) * interval_scale, clamped
+ *   mode 2  passthrough : Ns == 1, hypotheses = current depth
+ *   offsets [B,2Kp,H,W] raw output of propa_conv, Kp in {0,4,8,16}; with Kp == 0 nothing is
+ *           propagated and the samples keep initialisation order (no sort), as in the reference.
+ *   out     [B,Ns+Kp,H,W]  (ascending along dim 1 when Kp > 0)
+ */
+int pmb200_init_propagate(const float *seed_map, const float *offsets,
+                          const float *depth_min, const float *depth_max, float *out,
+                          int mode, int B, int H, int W, int Ns, int Kp, int dilation,
+                          float interval_scale, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-B: adaptive evaluation tail, one launch.
+ * Replaces depth_weight (models/patchmatch.py:650-669), the feature-weight product and
+ * normalisation (:509-510), SimilarityNet's neighbour gather + weighted sum (:569-577),
+ * softmax (:221) and depth regression (:226-237).
+ *   score0          [B,D,H,W] per-hypothesis score from the 1x1x1 MLP
+ *   depth_sample    [B,D,H,W]
+ *   offsets         [B,2K,H,W] raw output of eval_conv
+ *   feature_weight  [B,K,H,W]
+ *   prob_out        [B,D,H,W]   depth_out [B,H,W]
+ *   is_inverse      stage-1 last-iteration inverse-depth index regression (:227-234)
+ */
+int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *offsets,
+                         const float *feature_weight, const float *depth_min, const float *depth_max,
+                         float *prob_out, float *depth_out,
+                         int B, int D, int H, int W, int K, int dilation,
+                         float interval_scale, int is_inverse, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATCHMATCH_B200_H_ */

@@ -1,0 +1,12 @@
+"""patchmatchnet_b200 -- B200-native (sm_100a) learned-PatchMatch hot path of PatchmatchNet.
+
+Public surface (mirrors the reference's ``models`` package for this path):
+
+    PatchMatch      drop-in for reference models/patchmatch.py:PatchMatch
+    PatchmatchNet   caller-side shell with the reference constructor/forward (models/net.py)
+    ops             tensor-level wrappers over the C ABI (include/patchmatch_b200.h)
+"""
+from .net import PatchmatchNet, load_reference_state  # noqa: F401
+from .patchmatch import PatchMatch  # noqa: F401
+
+__all__ = ["PatchMatch", "PatchmatchNet", "load_reference_state"]

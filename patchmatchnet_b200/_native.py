@@ -1,0 +1,115 @@
+"""ctypes binding of the C ABI in ``include/patchmatch_b200.h`` (libpmb200.so).
+
+The library is built in-tree by ``build_library()`` (called from
+``__graft_entry__.build()``): a single ``nvcc -gencode arch=compute_100a,code=sm_100a``
+invocation, no torch headers.  There is NO fallback: if the shared object is
+missing or a call is made on a non-CUDA tensor the binding raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_void_p
+from typing import Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_REPO_DIR = os.path.dirname(_PKG_DIR)
+LIB_PATH = os.path.join(_PKG_DIR, "libpmb200.so")
+SOURCES = [os.path.join(_PKG_DIR, "csrc", "pm_kernels.cu")]
+HEADERS = [
+    os.path.join(_PKG_DIR, "csrc", "pm_math.cuh"),
+    os.path.join(_REPO_DIR, "include", "patchmatch_b200.h"),
+]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+]
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise NativeLibraryMissing("nvcc not found; cannot build libpmb200.so")
+    return exe
+
+
+def needs_rebuild() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(f) > built for f in SOURCES + HEADERS)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into patchmatchnet_b200/libpmb200.so (in-tree)."""
+    global _lib
+    if not force and not needs_rebuild():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    _lib = None
+    return LIB_PATH
+
+
+_PF = POINTER(c_float)
+_PPF = POINTER(c_void_p)
+
+_SIGNATURES = {
+    "pmb200_abi_version": (c_int, []),
+    "pmb200_last_error": (c_char_p, []),
+    "pmb200_relative_projection": (c_int, [c_void_p, c_int64, _PPF, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "pmb200_pack_nhwc": (c_int, [_PPF, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pmb200_warp_corr": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
+    "pmb200_aggregate_views": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    "pmb200_offset_corr": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+    "pmb200_init_propagate": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
+    "pmb200_adaptive_eval": (c_int, [c_void_p] * 8 + [c_int] * 6 + [c_float, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; raises NativeLibraryMissing when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the B200 path has no CPU or PyTorch fallback)"
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.pmb200_abi_version() != 1:
+            raise RuntimeError("libpmb200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().pmb200_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def pointer_array(ptrs):
+    arr = (c_void_p * len(ptrs))(*ptrs)
+    return ctypes.cast(arr, _PPF), arr  # keep `arr` alive for the duration of the call

@@ -1,0 +1,843 @@
+// pm_kernels.cu -- sm_100a kernels of the learned-PatchMatch hot path + their C ABI.
+//
+// Kernel map (DESIGN.md has the byte/flop budgets):
+//   warp_corr_kernel<C,G,FUSED>   K-A   homography warp + bilinear gather + group-wise correlation
+//                                       (+ view-weighted aggregation)          pmb200_warp_corr
+//   offset_corr_kernel<C,G>       K-A'  same gather/correlate core, coordinates from learned offsets
+//                                                                                pmb200_offset_corr
+//   init_propagate_kernel<NPAD>   K-C   hypothesis init + neighbour gather + register sorting network
+//                                                                                pmb200_init_propagate
+//   adaptive_eval_kernel          K-B   depth/feature weights + neighbour aggregation + softmax + regression
+//                                                                                pmb200_adaptive_eval
+//   aggregate_views_kernel, pack_nhwc_kernel, relative_projection_kernel        small helpers
+//
+// Lane mapping of the gather/correlate core (K-A, K-A'): features are channels-last, each lane
+// owns 8 consecutive channels of one pixel, C/8 lanes share a pixel, a warp covers 32/(C/8)
+// consecutive pixels.  One bilinear tap of one pixel is therefore one contiguous C*4-byte read
+// split over C/8 lanes as 2 x 16-byte loads (a full 128-byte line per pixel at C=32, two at C=64).
+// The per-(pixel, hypothesis) footprint (4 weights + packed texel key) is computed once per warp
+// into shared memory (phase 1) and broadcast to the lanes of the pixel (phase 2), so the
+// projection arithmetic is not repeated C/8 times.  Phase 2 keeps the four tap/reference dot
+// products T[tap][group] in registers and only re-gathers when the footprint key changes:
+// PatchMatch hypotheses of one pixel are sorted and clustered, so consecutive hypotheses mostly
+// land in the same source cell and cost 4 FMAs per group instead of 4 x 32 bytes of L1 traffic.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/patchmatch_b200.h"
+#include "pm_math.cuh"
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+int launch_status(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kChunk = 8;  // hypotheses (or neighbours) handled per warp pass
+
+template <int C, int G>
+struct LaneMap {
+    static_assert(C % 8 == 0 && (32 % (C / 8)) == 0, "C must be 8,16,32,64,128 or 256");
+    static constexpr int CPL = 8;               // channels per lane
+    static constexpr int LPP = C / CPL;         // lanes per pixel
+    static constexpr int PPW = 32 / LPP;        // pixels per warp
+    static constexpr int CPG = C / G;           // channels per group
+    static_assert(CPG == 4 || CPG == 8, "fast path needs 4 or 8 channels per group");
+    static constexpr int GPL = CPL / CPG;       // groups per lane (1 or 2)
+    static constexpr int EPW = PPW * kChunk;    // footprints per warp pass
+};
+
+// ------------------------------------------------------------------------------------------
+// gather/correlate core
+// ------------------------------------------------------------------------------------------
+
+template <int C, int G>
+__device__ __forceinline__ void gather_dot(const float4 *__restrict__ map_lane, int key, int cols,
+                                           const float (&r)[8], float (&T)[4][LaneMap<C, G>::GPL]) {
+    constexpr int V4 = C / 4;  // float4 per texel
+    const int r0 = pm::cell_r0(key), dx = pm::cell_dx(key), dy = pm::cell_dy(key);
+    const float4 *t0 = map_lane + (size_t)r0 * V4;
+    const float4 *t1 = t0 + dx * V4;
+    const float4 *t2 = t0 + (size_t)dy * cols * V4;
+    const float4 *t3 = t2 + dx * V4;
+    const float4 a0 = __ldg(t0), a1 = __ldg(t0 + 1);
+    const float4 b0 = __ldg(t1), b1 = __ldg(t1 + 1);
+    const float4 c0 = __ldg(t2), c1 = __ldg(t2 + 1);
+    const float4 d0 = __ldg(t3), d1 = __ldg(t3 + 1);
+    auto lo = [&](const float4 &q) { return r[0] * q.x + r[1] * q.y + r[2] * q.z + r[3] * q.w; };
+    auto hi = [&](const float4 &q) { return r[4] * q.x + r[5] * q.y + r[6] * q.z + r[7] * q.w; };
+    if constexpr (LaneMap<C, G>::GPL == 1) {
+        T[0][0] = lo(a0) + hi(a1);
+        T[1][0] = lo(b0) + hi(b1);
+        T[2][0] = lo(c0) + hi(c1);
+        T[3][0] = lo(d0) + hi(d1);
+    } else {
+        T[0][0] = lo(a0); T[0][1] = hi(a1);
+        T[1][0] = lo(b0); T[1][1] = hi(b1);
+        T[2][0] = lo(c0); T[2][1] = hi(c1);
+        T[3][0] = lo(d0); T[3][1] = hi(d1);
+    }
+}
+
+template <int C, int G>
+__device__ __forceinline__ void load_reference(const float *__restrict__ ref_nhwc, size_t pixel, int lane_in_pixel,
+                                               float (&r)[8]) {
+    const float4 *rp = reinterpret_cast<const float4 *>(ref_nhwc + pixel * C) + lane_in_pixel * 2;
+    const float4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+    constexpr float s = 1.0f / (float)LaneMap<C, G>::CPG;  // the group mean; exact (power of two)
+    r[0] = q0.x * s; r[1] = q0.y * s; r[2] = q0.z * s; r[3] = q0.w * s;
+    r[4] = q1.x * s; r[5] = q1.y * s; r[6] = q1.z * s; r[7] = q1.w * s;
+}
+
+struct WarpCorrParams {
+    const float *ref, *src, *rt, *depth, *vw;
+    float *out;
+    int V, B, H, W, Hs, Ws, D;
+    float sx, sy;
+};
+
+template <int C, int G, bool FUSED>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const WarpCorrParams p) {
+    using M = LaneMap<C, G>;
+    __shared__ float4 s_w[kWarpsPerBlock][M::EPW];
+    __shared__ int s_key[kWarpsPerBlock][M::EPW];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = p.H * p.W;
+    const int n0 = (blockIdx.x * kWarpsPerBlock + warp) * M::PPW;
+    if (n0 >= HW) return;  // no block-level barrier below, whole warps may leave
+    const int b = blockIdx.z, d0 = blockIdx.y * kChunk;
+    const int pi = lane / M::LPP, li = lane % M::LPP;
+    const int n = n0 + pi;
+    const bool live = n < HW;
+    const int nc = live ? n : HW - 1;
+    const int g0 = li * M::GPL;
+
+    float r[8];
+    load_reference<C, G>(p.ref, (size_t)b * HW + nc, li, r);
+
+    float acc[kChunk][M::GPL];
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i)
+#pragma unroll
+        for (int g = 0; g < M::GPL; ++g) acc[i][g] = 0.0f;
+    float wsum = 1e-5f;  // reference models/patchmatch.py:192
+
+    for (int v = 0; v < p.V; ++v) {
+        float rt[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) rt[i] = __ldg(p.rt + ((size_t)v * p.B + b) * 12 + i);
+
+        // phase 1: one footprint per (pixel, hypothesis) of this warp pass
+        for (int e = lane; e < M::EPW; e += 32) {
+            const int epi = e % M::PPW, edj = e / M::PPW;
+            const int en = n0 + epi, ed = d0 + edj;
+            pm::Cell c;
+            c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
+            c.key = pm::kKeyNone;
+            if (en < HW && ed < p.D) {
+                const float x = (float)(en % p.W), y = (float)(en / p.W);
+                const float dep = __ldg(p.depth + ((size_t)b * p.D + ed) * HW + en);
+                const pm::Ray ray = pm::pixel_ray(rt, x, y);
+                float u, w;
+                pm::project(ray, rt, dep, p.W, p.H, p.sx, p.sy, &u, &w);
+                c = pm::zero_pad_cell(u, w, p.Hs, p.Ws);
+            }
+            s_w[warp][e] = make_float4(c.w00, c.w01, c.w10, c.w11);
+            s_key[warp][e] = c.key;
+        }
+        __syncwarp();
+
+        float wv = 1.0f;
+        if (FUSED) {
+            wv = __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc);
+            wsum += wv;
+        }
+        const float4 *sv =
+            reinterpret_cast<const float4 *>(p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C) + li * 2;
+
+        // phase 2
+        int pkey = pm::kKeyNone;
+        float T[4][M::GPL];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int g = 0; g < M::GPL; ++g) T[t][g] = 0.0f;
+#pragma unroll
+        for (int dj = 0; dj < kChunk; ++dj) {
+            const float4 w = s_w[warp][dj * M::PPW + pi];
+            const int key = s_key[warp][dj * M::PPW + pi];
+            float sim[M::GPL];
+#pragma unroll
+            for (int g = 0; g < M::GPL; ++g) sim[g] = 0.0f;
+            if (key != pm::kKeyNone) {
+                if (key != pkey) {
+                    gather_dot<C, G>(sv, key, p.Ws, r, T);
+                    pkey = key;
+                }
+#pragma unroll
+                for (int g = 0; g < M::GPL; ++g)
+                    sim[g] = w.x * T[0][g] + w.y * T[1][g] + w.z * T[2][g] + w.w * T[3][g];
+            }
+            if (FUSED) {
+#pragma unroll
+                for (int g = 0; g < M::GPL; ++g) acc[dj][g] = fmaf(sim[g], wv, acc[dj][g]);
+            } else if (live && d0 + dj < p.D) {
+#pragma unroll
+                for (int g = 0; g < M::GPL; ++g)
+                    p.out[((((size_t)v * p.B + b) * G + g0 + g) * p.D + d0 + dj) * HW + n] = sim[g];
+            }
+        }
+        __syncwarp();  // the next view overwrites this warp's footprints
+    }
+
+    if (FUSED && live) {
+#pragma unroll
+        for (int dj = 0; dj < kChunk; ++dj) {
+            if (d0 + dj < p.D) {
+#pragma unroll
+                for (int g = 0; g < M::GPL; ++g)
+                    p.out[(((size_t)b * G + g0 + g) * p.D + d0 + dj) * HW + n] = acc[dj][g] / wsum;
+            }
+        }
+    }
+}
+
+// Any C % G == 0: one thread per (batch, hypothesis, pixel), scalar channel loop.  Slow path.
+__global__ void warp_corr_generic_kernel(const WarpCorrParams p, int C, int G) {
+    const int HW = p.H * p.W;
+    const size_t total = (size_t)p.B * p.D * HW;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int n = (int)(idx % HW);
+    const int d = (int)((idx / HW) % p.D);
+    const int b = (int)(idx / ((size_t)HW * p.D));
+    const float x = (float)(n % p.W), y = (float)(n / p.W);
+    const float dep = p.depth[((size_t)b * p.D + d) * HW + n];
+    const float *ref = p.ref + ((size_t)b * HW + n) * C;
+    const int cpg = C / G;
+    const bool fused = p.vw != nullptr;
+    for (int g = 0; g < G; ++g) {
+        float acc = 0.0f, wsum = 1e-5f;
+        for (int v = 0; v < p.V; ++v) {
+            float rt[12];
+            for (int i = 0; i < 12; ++i) rt[i] = p.rt[((size_t)v * p.B + b) * 12 + i];
+            float u, w;
+            pm::project(pm::pixel_ray(rt, x, y), rt, dep, p.W, p.H, p.sx, p.sy, &u, &w);
+            const pm::Cell c = pm::zero_pad_cell(u, w, p.Hs, p.Ws);
+            float sim = 0.0f;
+            if (c.key != pm::kKeyNone) {
+                const float *base = p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C;
+                const float *t0 = base + (size_t)pm::cell_r0(c.key) * C;
+                const float *t1 = t0 + pm::cell_dx(c.key) * C;
+                const float *t2 = t0 + (size_t)pm::cell_dy(c.key) * p.Ws * C;
+                const float *t3 = t2 + pm::cell_dx(c.key) * C;
+                for (int k = g * cpg; k < (g + 1) * cpg; ++k)
+                    sim += ref[k] * (c.w00 * t0[k] + c.w01 * t1[k] + c.w10 * t2[k] + c.w11 * t3[k]);
+                sim /= (float)cpg;
+            }
+            if (fused) {
+                const float wv = p.vw[((size_t)b * p.V + v) * HW + n];
+                acc += sim * wv;
+                wsum += wv;
+            } else {
+                p.out[((((size_t)v * p.B + b) * G + g) * p.D + d) * HW + n] = sim;
+            }
+        }
+        if (fused) p.out[(((size_t)b * G + g) * p.D + d) * HW + n] = acc / wsum;
+    }
+}
+
+struct OffsetCorrParams {
+    const float *ref, *offsets;
+    float *out;
+    int B, H, W, K, dilation;
+};
+
+template <int C, int G>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) offset_corr_kernel(const OffsetCorrParams p) {
+    using M = LaneMap<C, G>;
+    __shared__ float4 s_w[kWarpsPerBlock][M::EPW];
+    __shared__ int s_key[kWarpsPerBlock][M::EPW];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = p.H * p.W;
+    const int n0 = (blockIdx.x * kWarpsPerBlock + warp) * M::PPW;
+    if (n0 >= HW) return;
+    const int b = blockIdx.z, k0 = blockIdx.y * kChunk;
+    const int pi = lane / M::LPP, li = lane % M::LPP;
+    const int n = n0 + pi;
+    const bool live = n < HW;
+    const int nc = live ? n : HW - 1;
+    const int g0 = li * M::GPL;
+
+    float r[8];
+    load_reference<C, G>(p.ref, (size_t)b * HW + nc, li, r);
+
+    for (int e = lane; e < M::EPW; e += 32) {
+        const int epi = e % M::PPW, ekj = e / M::PPW;
+        const int en = n0 + epi, ek = k0 + ekj;
+        pm::Cell c;
+        c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
+        c.key = pm::kKeyNone;
+        if (en < HW && ek < p.K) {
+            int dy = 0, dx = 0;
+            pm::neighbour_offset(true, p.K, p.dilation, ek, &dy, &dx);
+            const float ox = (float)dx + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * ek) * HW + en);
+            const float oy = (float)dy + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * ek + 1) * HW + en);
+            c = pm::border_cell((float)(en % p.W) + ox, (float)(en / p.W) + oy, p.H, p.W);
+        }
+        s_w[warp][e] = make_float4(c.w00, c.w01, c.w10, c.w11);
+        s_key[warp][e] = c.key;
+    }
+    __syncwarp();
+
+    const float4 *sv = reinterpret_cast<const float4 *>(p.ref + (size_t)b * HW * C) + li * 2;
+    int pkey = pm::kKeyNone;
+    float T[4][M::GPL];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int g = 0; g < M::GPL; ++g) T[t][g] = 0.0f;
+#pragma unroll
+    for (int kj = 0; kj < kChunk; ++kj) {
+        const float4 w = s_w[warp][kj * M::PPW + pi];
+        const int key = s_key[warp][kj * M::PPW + pi];
+        if (key == pm::kKeyNone) continue;  // only for k >= K or dead pixels
+        if (key != pkey) {
+            gather_dot<C, G>(sv, key, p.W, r, T);
+            pkey = key;
+        }
+        if (live && k0 + kj < p.K) {
+#pragma unroll
+            for (int g = 0; g < M::GPL; ++g)
+                p.out[(((size_t)b * G + g0 + g) * p.K + k0 + kj) * HW + n] =
+                    w.x * T[0][g] + w.y * T[1][g] + w.z * T[2][g] + w.w * T[3][g];
+        }
+    }
+}
+
+__global__ void offset_corr_generic_kernel(const OffsetCorrParams p, int C, int G) {
+    const int HW = p.H * p.W;
+    const size_t total = (size_t)p.B * p.K * HW;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int n = (int)(idx % HW);
+    const int k = (int)((idx / HW) % p.K);
+    const int b = (int)(idx / ((size_t)HW * p.K));
+    int dy = 0, dx = 0;
+    pm::neighbour_offset(true, p.K, p.dilation, k, &dy, &dx);
+    const float ox = (float)dx + p.offsets[((size_t)b * 2 * p.K + 2 * k) * HW + n];
+    const float oy = (float)dy + p.offsets[((size_t)b * 2 * p.K + 2 * k + 1) * HW + n];
+    const pm::Cell c = pm::border_cell((float)(n % p.W) + ox, (float)(n / p.W) + oy, p.H, p.W);
+    const float *ref = p.ref + ((size_t)b * HW + n) * C;
+    const float *t0 = p.ref + ((size_t)b * HW + pm::cell_r0(c.key)) * C;
+    const float *t1 = t0 + pm::cell_dx(c.key) * C;
+    const float *t2 = t0 + (size_t)pm::cell_dy(c.key) * p.W * C;
+    const float *t3 = t2 + pm::cell_dx(c.key) * C;
+    const int cpg = C / G;
+    for (int g = 0; g < G; ++g) {
+        float sim = 0.0f;
+        for (int q = g * cpg; q < (g + 1) * cpg; ++q)
+            sim += ref[q] * (c.w00 * t0[q] + c.w01 * t1[q] + c.w10 * t2[q] + c.w11 * t3[q]);
+        p.out[(((size_t)b * G + g) * p.K + k) * HW + n] = sim / (float)cpg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+
+__global__ void aggregate_views_kernel(const float *__restrict__ sims, const float *__restrict__ vw,
+                                       float *__restrict__ out, int V, int B, int GD, int HW) {
+    // one thread per (b, g*d, pixel); sims [V,B,GD,HW], vw [B,V,HW]
+    const size_t total = (size_t)B * GD * HW;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int n = (int)(idx % HW);
+        const int b = (int)(idx / ((size_t)GD * HW));
+        float acc = 0.0f, wsum = 1e-5f;
+        for (int v = 0; v < V; ++v) {
+            const float w = __ldg(vw + ((size_t)b * V + v) * HW + n);
+            acc = fmaf(__ldg(sims + (size_t)v * total + idx), w, acc);
+            wsum += w;
+        }
+        out[idx] = acc / wsum;
+    }
+}
+
+struct PtrList {
+    const float *p[PMB200_MAX_VIEWS + 1];
+};
+
+struct PackParams {
+    PtrList maps;
+    float *out;
+    int n, B, C, HW;
+};
+
+__global__ void pack_nhwc_kernel(const PackParams p) {
+    __shared__ float tile[32][33];
+    const int m = blockIdx.z / p.B, b = blockIdx.z % p.B;
+    const float *in = p.maps.p[m] + (size_t)b * p.C * p.HW;
+    float *out = p.out + ((size_t)m * p.B + b) * p.HW * p.C;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, hw = hw0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < p.C && hw < p.HW) ? __ldg(in + (size_t)c * p.HW + hw) : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int hw = hw0 + j, c = c0 + threadIdx.x;
+        if (c < p.C && hw < p.HW) out[(size_t)hw * p.C + c] = tile[threadIdx.x][j];
+    }
+}
+
+struct ProjParams {
+    const float *ref;
+    PtrList src;
+    float *out;
+    long long ref_stride, src_stride;
+    int V, B;
+};
+
+__global__ void relative_projection_kernel(const ProjParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.V * p.B) return;
+    const int v = idx / p.B, b = idx % p.B;
+    double a[4][8];
+    const float *R = p.ref + (size_t)b * p.ref_stride;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            a[i][j] = (double)R[i * 4 + j];
+            a[i][4 + j] = (i == j) ? 1.0 : 0.0;
+        }
+    // Gauss-Jordan with partial pivoting, fp64
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+        double best = fabs(a[col][col]);
+        for (int i = col + 1; i < 4; ++i)
+            if (fabs(a[i][col]) > best) { best = fabs(a[i][col]); piv = i; }
+        if (piv != col)
+            for (int j = 0; j < 8; ++j) { const double t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t; }
+        const double inv = 1.0 / a[col][col];  // singular input -> inf/nan, as torch.inverse would error; caller's contract
+        for (int j = 0; j < 8; ++j) a[col][j] *= inv;
+        for (int i = 0; i < 4; ++i) {
+            if (i == col) continue;
+            const double f = a[i][col];
+            for (int j = 0; j < 8; ++j) a[i][j] -= f * a[col][j];
+        }
+    }
+    const float *S = p.src.p[v] + (size_t)b * p.src_stride;
+    float *o = p.out + ((size_t)v * p.B + b) * 12;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += (double)S[i * 4 + k] * a[k][4 + j];
+            if (j < 3) o[i * 3 + j] = (float)s;
+            else o[9 + i] = (float)s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-C: init + propagate + sort
+// ------------------------------------------------------------------------------------------
+
+struct PropParams {
+    const float *seed, *offsets, *dmin, *dmax;
+    float *out;
+    int mode, B, H, W, Ns, Kp, dilation;
+    float interval_scale;
+};
+
+__device__ __forceinline__ float centre_hypothesis(const PropParams &p, int b, int q, int HW, float inv_min,
+                                                   float inv_max) {
+    if (p.mode == 0) return pm::random_hypothesis(__ldg(p.seed + ((size_t)b * 48 + 24) * HW + q), 24, inv_min, inv_max);
+    const float d = __ldg(p.seed + (size_t)b * HW + q);
+    if (p.mode == 1)
+        return pm::perturbed_hypothesis(d, pm::floor_div2_neg(p.Ns) + p.Ns / 2, inv_min, inv_max, p.interval_scale);
+    return d;
+}
+
+__device__ __forceinline__ float own_hypothesis(const PropParams &p, int b, int n, int k, int HW, float inv_min,
+                                                float inv_max) {
+    if (p.mode == 0) return pm::random_hypothesis(__ldg(p.seed + ((size_t)b * 48 + k) * HW + n), k, inv_min, inv_max);
+    const float d = __ldg(p.seed + (size_t)b * HW + n);
+    if (p.mode == 1) return pm::perturbed_hypothesis(d, pm::floor_div2_neg(p.Ns) + k, inv_min, inv_max, p.interval_scale);
+    return d;
+}
+
+__device__ __forceinline__ float propagated_hypothesis(const PropParams &p, int b, int n, int kk, int HW,
+                                                       float inv_min, float inv_max) {
+    int dy = 0, dx = 0;
+    pm::neighbour_offset(false, p.Kp, p.dilation, kk, &dy, &dx);
+    const float ox = (float)dx + __ldg(p.offsets + ((size_t)b * 2 * p.Kp + 2 * kk) * HW + n);
+    const float oy = (float)dy + __ldg(p.offsets + ((size_t)b * 2 * p.Kp + 2 * kk + 1) * HW + n);
+    const pm::Cell c = pm::border_cell((float)(n % p.W) + ox, (float)(n / p.W) + oy, p.H, p.W);
+    const int r0 = pm::cell_r0(c.key), ddx = pm::cell_dx(c.key), ddy = pm::cell_dy(c.key);
+    float s = centre_hypothesis(p, b, r0, HW, inv_min, inv_max) * c.w00;
+    s = fmaf(centre_hypothesis(p, b, r0 + ddx, HW, inv_min, inv_max), c.w01, s);
+    s = fmaf(centre_hypothesis(p, b, r0 + ddy * p.W, HW, inv_min, inv_max), c.w10, s);
+    s = fmaf(centre_hypothesis(p, b, r0 + ddy * p.W + ddx, HW, inv_min, inv_max), c.w11, s);
+    return s;
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(128) init_propagate_kernel(const PropParams p) {
+    const int HW = p.H * p.W;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (n >= HW) return;
+    const float inv_min = 1.0f / __ldg(p.dmin + b), inv_max = 1.0f / __ldg(p.dmax + b);
+    const int D = p.Ns + p.Kp;
+    float v[NPAD];
+#pragma unroll
+    for (int k = 0; k < NPAD; ++k) {
+        if (k < p.Ns) v[k] = own_hypothesis(p, b, n, k, HW, inv_min, inv_max);
+        else if (k < D) v[k] = propagated_hypothesis(p, b, n, k - p.Ns, HW, inv_min, inv_max);
+        else v[k] = __int_as_float(0x7f800000);  // +inf padding sorts to the end
+    }
+    if (p.Kp > 0) {  // reference sorts only when something was propagated (models/patchmatch.py:497-499)
+#pragma unroll
+        for (int k = 2; k <= NPAD; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int i = 0; i < NPAD; ++i) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const float lo = fminf(v[i], v[l]), hi = fmaxf(v[i], v[l]);
+                        const bool up = (i & k) == 0;
+                        v[i] = up ? lo : hi;
+                        v[l] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NPAD; ++k)
+        if (k < D) p.out[((size_t)b * D + k) * HW + n] = v[k];
+}
+
+// D > 64: write unsorted, then insertion-sort each pixel's column in place.  Slow path.
+__global__ void init_propagate_generic_kernel(const PropParams p) {
+    const int HW = p.H * p.W;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (n >= HW) return;
+    const float inv_min = 1.0f / p.dmin[b], inv_max = 1.0f / p.dmax[b];
+    const int D = p.Ns + p.Kp;
+    float *col = p.out + (size_t)b * D * HW + n;
+    for (int k = 0; k < D; ++k)
+        col[(size_t)k * HW] = k < p.Ns ? own_hypothesis(p, b, n, k, HW, inv_min, inv_max)
+                                       : propagated_hypothesis(p, b, n, k - p.Ns, HW, inv_min, inv_max);
+    if (p.Kp == 0) return;
+    for (int i = 1; i < D; ++i) {
+        const float x = col[(size_t)i * HW];
+        int j = i - 1;
+        while (j >= 0 && col[(size_t)j * HW] > x) {
+            col[(size_t)(j + 1) * HW] = col[(size_t)j * HW];
+            --j;
+        }
+        col[(size_t)(j + 1) * HW] = x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-B: adaptive evaluation tail
+// ------------------------------------------------------------------------------------------
+
+struct EvalParams {
+    const float *score0, *depth, *offsets, *fw, *dmin, *dmax;
+    float *prob, *depth_out;
+    int B, D, H, W, K, dilation, is_inverse;
+    float interval_scale;
+};
+
+// block (TP pixels, DY hypothesis lanes); dynamic smem: float4 cw[K][TP]; int ck[K][TP]; float sc[D][TP]
+__global__ void adaptive_eval_kernel(const EvalParams p) {
+    extern __shared__ float4 smem4[];
+    const int TP = blockDim.x, DY = blockDim.y;
+    float4 *cw = smem4;
+    int *ck = reinterpret_cast<int *>(cw + (size_t)p.K * TP);
+    float *sc = reinterpret_cast<float *>(ck + (size_t)p.K * TP);
+
+    const int tp = threadIdx.x, ty = threadIdx.y;
+    const int HW = p.H * p.W;
+    const int n = blockIdx.x * TP + tp;
+    const int b = blockIdx.y;
+    const bool live = n < HW;
+    const int nc = live ? n : HW - 1;
+    const float inv_min = 1.0f / __ldg(p.dmin + b), inv_max = 1.0f / __ldg(p.dmax + b);
+
+    for (int k = ty; k < p.K; k += DY) {
+        int dy = 0, dx = 0;
+        pm::neighbour_offset(true, p.K, p.dilation, k, &dy, &dx);
+        const float ox = (float)dx + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * k) * HW + nc);
+        const float oy = (float)dy + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * k + 1) * HW + nc);
+        const pm::Cell c = pm::border_cell((float)(nc % p.W) + ox, (float)(nc / p.W) + oy, p.H, p.W);
+        cw[k * TP + tp] = make_float4(c.w00, c.w01, c.w10, c.w11);
+        ck[k * TP + tp] = c.key;
+    }
+    __syncthreads();
+
+    for (int d = ty; d < p.D; d += DY) {
+        const float *dmap = p.depth + ((size_t)b * p.D + d) * HW;
+        const float *smap = p.score0 + ((size_t)b * p.D + d) * HW;
+        const float xc = pm::normalised_inverse_depth(__ldg(dmap + nc), inv_min, inv_max);
+        float num = 0.0f, den = 0.0f;
+        for (int k = 0; k < p.K; ++k) {
+            const float4 w = cw[k * TP + tp];
+            const int key = ck[k * TP + tp];
+            const int r0 = pm::cell_r0(key), ddx = pm::cell_dx(key), ddy = pm::cell_dy(key);
+            const int r1 = r0 + ddx, r2 = r0 + ddy * p.W, r3 = r2 + ddx;
+            float xn = pm::normalised_inverse_depth(__ldg(dmap + r0), inv_min, inv_max) * w.x;
+            xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r1), inv_min, inv_max), w.y, xn);
+            xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r2), inv_min, inv_max), w.z, xn);
+            xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r3), inv_min, inv_max), w.w, xn);
+            float sn = __ldg(smap + r0) * w.x;
+            sn = fmaf(__ldg(smap + r1), w.y, sn);
+            sn = fmaf(__ldg(smap + r2), w.z, sn);
+            sn = fmaf(__ldg(smap + r3), w.w, sn);
+            const float wk = pm::depth_similarity(xc, xn, p.interval_scale) *
+                             __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+            num = fmaf(sn, wk, num);
+            den += wk;
+        }
+        sc[d * TP + tp] = num / den;
+    }
+    __syncthreads();
+
+    float m = -INFINITY;
+    for (int d = 0; d < p.D; ++d) m = fmaxf(m, sc[d * TP + tp]);
+    float sum = 0.0f;
+    for (int d = 0; d < p.D; ++d) sum += expf(sc[d * TP + tp] - m);
+    const float lse = logf(sum);
+    if (live)
+        for (int d = ty; d < p.D; d += DY)
+            p.prob[((size_t)b * p.D + d) * HW + n] = expf(sc[d * TP + tp] - m - lse);
+
+    if (ty == 0 && live) {
+        float out;
+        if (p.is_inverse) {  // reference models/patchmatch.py:227-234
+            float idx = 0.0f;
+            for (int d = 0; d < p.D; ++d) idx = fmaf((float)d, expf(sc[d * TP + tp] - m - lse), idx);
+            const float inv_hi = 1.0f / __ldg(p.depth + ((size_t)b * p.D + (p.D - 1)) * HW + n);
+            const float inv_lo = 1.0f / __ldg(p.depth + ((size_t)b * p.D) * HW + n);
+            out = 1.0f / (inv_lo + idx / (float)(p.D - 1) * (inv_hi - inv_lo));
+        } else {
+            float e = 0.0f;
+            for (int d = 0; d < p.D; ++d)
+                e = fmaf(__ldg(p.depth + ((size_t)b * p.D + d) * HW + n), expf(sc[d * TP + tp] - m - lse), e);
+            out = e;
+        }
+        p.depth_out[(size_t)b * HW + n] = out;
+    }
+}
+
+cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+
+extern "C" {
+
+int pmb200_abi_version(void) { return PMB200_ABI_VERSION; }
+
+const char *pmb200_last_error(void) { return g_err; }
+
+int pmb200_relative_projection(const float *ref_proj, int64_t ref_batch_stride, const float *const *src_projs_host,
+                               int64_t src_batch_stride, int V, int B, float *rt_out, void *stream) {
+    if (!ref_proj || !src_projs_host || !rt_out) return fail(PMB200_EINVAL, "relative_projection: null pointer");
+    if (V < 1 || V > PMB200_MAX_VIEWS || B < 1) return fail(PMB200_EINVAL, "relative_projection: bad V or B");
+    ProjParams p;
+    p.ref = ref_proj;
+    for (int v = 0; v < V; ++v) {
+        if (!src_projs_host[v]) return fail(PMB200_EINVAL, "relative_projection: null source matrix");
+        p.src.p[v] = src_projs_host[v];
+    }
+    p.out = rt_out;
+    p.ref_stride = ref_batch_stride;
+    p.src_stride = src_batch_stride;
+    p.V = V;
+    p.B = B;
+    const int total = V * B;
+    relative_projection_kernel<<<(total + 63) / 64, 64, 0, as_stream(stream)>>>(p);
+    return launch_status("relative_projection");
+}
+
+int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, int W, float *out_nhwc,
+                     void *stream) {
+    if (!maps_host || !out_nhwc) return fail(PMB200_EINVAL, "pack_nhwc: null pointer");
+    if (n < 1 || n > PMB200_MAX_VIEWS + 1 || B < 1 || C < 1 || H < 1 || W < 1)
+        return fail(PMB200_EINVAL, "pack_nhwc: bad size");
+    if ((long long)n * B > 65535) return fail(PMB200_EINVAL, "pack_nhwc: n*B exceeds grid.z");
+    PackParams p;
+    for (int i = 0; i < n; ++i) {
+        if (!maps_host[i]) return fail(PMB200_EINVAL, "pack_nhwc: null map");
+        p.maps.p[i] = maps_host[i];
+    }
+    p.out = out_nhwc;
+    p.n = n;
+    p.B = B;
+    p.C = C;
+    p.HW = H * W;
+    dim3 grid((p.HW + 31) / 32, (C + 31) / 32, n * B);
+    pack_nhwc_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(p);
+    return launch_status("pack_nhwc");
+}
+
+int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth,
+                     const float *view_weights, float *out, int V, int B, int C, int G, int H, int W, int Hs,
+                     int Ws, int D, void *stream) {
+    if (!ref_nhwc || !src_nhwc || !rt || !depth || !out) return fail(PMB200_EINVAL, "warp_corr: null pointer");
+    if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || B > 65535 || H < 1 || W < 1 || Hs < 1 || Ws < 1 || D < 1)
+        return fail(PMB200_EINVAL, "warp_corr: bad size");
+    if (C < 1 || G < 1 || C % G != 0) return fail(PMB200_EINVAL, "warp_corr: C must be a multiple of G");
+    if ((long long)Hs * Ws >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "warp_corr: source map too large");
+    WarpCorrParams p;
+    p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = view_weights; p.out = out;
+    p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
+    // F.grid_sample(align_corners=True) maps the normalised coordinate onto the *source* extent
+    p.sx = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 1.0f;
+    p.sy = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 1.0f;
+    const int HW = H * W;
+    cudaStream_t st = as_stream(stream);
+    const bool fused = view_weights != nullptr;
+    const int nchunk = (D + kChunk - 1) / kChunk;
+    if (nchunk > 65535) return fail(PMB200_EINVAL, "warp_corr: too many hypotheses");
+#define PMB200_LAUNCH_WC(CC, GG)                                                                   \
+    do {                                                                                           \
+        dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
+                  nchunk, B);                                                                      \
+        if (fused) warp_corr_kernel<CC, GG, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(p);        \
+        else warp_corr_kernel<CC, GG, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(p);             \
+    } while (0)
+    if (C == 64 && G == 8) PMB200_LAUNCH_WC(64, 8);
+    else if (C == 32 && G == 8) PMB200_LAUNCH_WC(32, 8);
+    else if (C == 16 && G == 4) PMB200_LAUNCH_WC(16, 4);
+    else {
+        const size_t total = (size_t)B * D * HW;
+        warp_corr_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p, C, G);
+    }
+#undef PMB200_LAUNCH_WC
+    return launch_status("warp_corr");
+}
+
+int pmb200_aggregate_views(const float *sims, const float *view_weights, float *out, int V, int B, int G, int D,
+                           int H, int W, void *stream) {
+    if (!sims || !view_weights || !out) return fail(PMB200_EINVAL, "aggregate_views: null pointer");
+    if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || G < 1 || D < 1 || H < 1 || W < 1)
+        return fail(PMB200_EINVAL, "aggregate_views: bad size");
+    const size_t total = (size_t)B * G * D * H * W;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    aggregate_views_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(sims, view_weights, out, V, B, G * D, H * W);
+    return launch_status("aggregate_views");
+}
+
+int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out, int B, int C, int G, int H, int W,
+                       int K, int dilation, void *stream) {
+    if (!ref_nhwc || !offsets || !out) return fail(PMB200_EINVAL, "offset_corr: null pointer");
+    if (B < 1 || B > 65535 || H < 2 || W < 2) return fail(PMB200_EINVAL, "offset_corr: bad size");
+    if (C < 1 || G < 1 || C % G != 0) return fail(PMB200_EINVAL, "offset_corr: C must be a multiple of G");
+    if (K != 9 && K != 17) return fail(PMB200_EUNSUPPORTED, "offset_corr: evaluate_neighbors must be 9 or 17");
+    if ((long long)H * W >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "offset_corr: map too large");
+    OffsetCorrParams p;
+    p.ref = ref_nhwc; p.offsets = offsets; p.out = out;
+    p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation;
+    const int HW = H * W;
+    cudaStream_t st = as_stream(stream);
+    const int nchunk = (K + kChunk - 1) / kChunk;
+#define PMB200_LAUNCH_OC(CC, GG)                                                                   \
+    do {                                                                                           \
+        dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
+                  nchunk, B);                                                                      \
+        offset_corr_kernel<CC, GG><<<grid, kWarpsPerBlock * 32, 0, st>>>(p);                       \
+    } while (0)
+    if (C == 64 && G == 8) PMB200_LAUNCH_OC(64, 8);
+    else if (C == 32 && G == 8) PMB200_LAUNCH_OC(32, 8);
+    else if (C == 16 && G == 4) PMB200_LAUNCH_OC(16, 4);
+    else {
+        const size_t total = (size_t)B * K * HW;
+        offset_corr_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p, C, G);
+    }
+#undef PMB200_LAUNCH_OC
+    return launch_status("offset_corr");
+}
+
+int pmb200_init_propagate(const float *seed_map, const float *offsets, const float *depth_min,
+                          const float *depth_max, float *out, int mode, int B, int H, int W, int Ns, int Kp,
+                          int dilation, float interval_scale, void *stream) {
+    if (!seed_map || !depth_min || !depth_max || !out) return fail(PMB200_EINVAL, "init_propagate: null pointer");
+    if (B < 1 || B > 65535 || H < 2 || W < 2 || Ns < 1) return fail(PMB200_EINVAL, "init_propagate: bad size");
+    if (mode < 0 || mode > 2) return fail(PMB200_EINVAL, "init_propagate: bad mode");
+    if (mode == 0 && Ns != 48) return fail(PMB200_EINVAL, "init_propagate: random init has 48 samples");
+    if (mode == 2 && Ns != 1) return fail(PMB200_EINVAL, "init_propagate: passthrough needs Ns == 1");
+    if (Kp != 0 && Kp != 4 && Kp != 8 && Kp != 16)
+        return fail(PMB200_EUNSUPPORTED, "init_propagate: propagate_neighbors must be 0, 4, 8 or 16");
+    if (Kp > 0 && !offsets) return fail(PMB200_EINVAL, "init_propagate: offsets missing");
+    if (Ns + Kp > PMB200_MAX_HYPOTHESES) return fail(PMB200_EINVAL, "init_propagate: too many hypotheses");
+    PropParams p;
+    p.seed = seed_map; p.offsets = offsets; p.dmin = depth_min; p.dmax = depth_max; p.out = out;
+    p.mode = mode; p.B = B; p.H = H; p.W = W; p.Ns = Ns; p.Kp = Kp; p.dilation = dilation;
+    p.interval_scale = interval_scale;
+    const int HW = H * W, D = Ns + Kp;
+    cudaStream_t st = as_stream(stream);
+    dim3 grid((HW + 127) / 128, B);
+    if (D <= 8) init_propagate_kernel<8><<<grid, 128, 0, st>>>(p);
+    else if (D <= 16) init_propagate_kernel<16><<<grid, 128, 0, st>>>(p);
+    else if (D <= 32) init_propagate_kernel<32><<<grid, 128, 0, st>>>(p);
+    else if (D <= 64) init_propagate_kernel<64><<<grid, 128, 0, st>>>(p);
+    else init_propagate_generic_kernel<<<grid, 128, 0, st>>>(p);
+    return launch_status("init_propagate");
+}
+
+int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *offsets,
+                         const float *feature_weight, const float *depth_min, const float *depth_max,
+                         float *prob_out, float *depth_out, int B, int D, int H, int W, int K, int dilation,
+                         float interval_scale, int is_inverse, void *stream) {
+    if (!score0 || !depth_sample || !offsets || !feature_weight || !depth_min || !depth_max || !prob_out || !depth_out)
+        return fail(PMB200_EINVAL, "adaptive_eval: null pointer");
+    if (B < 1 || B > 65535 || H < 2 || W < 2 || D < 1 || D > PMB200_MAX_HYPOTHESES)
+        return fail(PMB200_EINVAL, "adaptive_eval: bad size");
+    if (K != 9 && K != 17) return fail(PMB200_EUNSUPPORTED, "adaptive_eval: evaluate_neighbors must be 9 or 17");
+    if (is_inverse && D < 2) return fail(PMB200_EINVAL, "adaptive_eval: inverse regression needs D >= 2");
+    EvalParams p;
+    p.score0 = score0; p.depth = depth_sample; p.offsets = offsets; p.fw = feature_weight;
+    p.dmin = depth_min; p.dmax = depth_max; p.prob = prob_out; p.depth_out = depth_out;
+    p.B = B; p.D = D; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.is_inverse = is_inverse;
+    p.interval_scale = interval_scale;
+    const int HW = H * W;
+    // small maps: fewer pixels per block and more hypothesis lanes, so the grid still covers the SMs
+    int TP = 32, DY = D < 8 ? D : 8;
+    if ((long long)((HW + 31) / 32) * B < 2 * 148) {
+        TP = 8;
+        DY = D < 32 ? D : 32;
+    }
+    const size_t smem = (size_t)K * TP * (sizeof(float4) + sizeof(int)) + (size_t)D * TP * sizeof(float);
+    dim3 grid((HW + TP - 1) / TP, B);
+    adaptive_eval_kernel<<<grid, dim3(TP, DY), smem, as_stream(stream)>>>(p);
+    return launch_status("adaptive_eval");
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+"""Caller-side shell: ``PatchmatchNet`` with the reference constructor / forward
+signatures and parameter names (reference ``models/net.py:125-301``).
+
+Only ``PatchMatch`` (the hot path) is native B200 code.  The dense 2-D convs of
+the feature pyramid and the refinement head stay library ops (cuDNN), as the
+scope table says; they are here because the reference's
+``models/net.py`` does not exist on the GPU box and the end-to-end metric
+(depth-maps/s) is quoted on the full cascade.  When the reference *is*
+importable, ``patchmatchnet_b200.PatchMatch`` drops into its unmodified
+``models/net.py`` instead (tests/test_dropin_reference.py).
+
+The stage module class is a constructor argument so that the oracle
+(``oracle.pm_oracle.PatchMatchOracle``) can be timed/checked behind the very
+same shell by tests and by bench.py's CPU-baseline leg.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple, Type
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+class _ConvBnReLU2d(nn.Module):
+    """conv2d (no bias) + BatchNorm2d + ReLU; children named ``conv`` / ``bn``
+    as in the reference checkpoints (reference models/module.py:11-40)."""
+
+    def __init__(self, cin: int, cout: int, k: int = 3, stride: int = 1, pad: int = 1) -> None:
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=pad, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.relu(self.bn(self.conv(x)), inplace=True)
+
+
+class FeatureNet(nn.Module):
+    """Three-level feature pyramid (reference models/net.py:9-70): 1/8 x 64ch,
+    1/4 x 32ch, 1/2 x 16ch, keyed 3 / 2 / 1."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        spec = [  # (cin, cout, k, stride, pad)
+            (3, 8, 3, 1, 1), (8, 8, 3, 1, 1),
+            (8, 16, 5, 2, 2), (16, 16, 3, 1, 1), (16, 16, 3, 1, 1),
+            (16, 32, 5, 2, 2), (32, 32, 3, 1, 1), (32, 32, 3, 1, 1),
+            (32, 64, 5, 2, 2), (64, 64, 3, 1, 1), (64, 64, 3, 1, 1),
+        ]
+        for i, s in enumerate(spec):
+            setattr(self, f"conv{i}", _ConvBnReLU2d(*s))
+        self.output1 = nn.Conv2d(64, 64, 1, bias=False)
+        self.inner1 = nn.Conv2d(32, 64, 1, bias=True)
+        self.inner2 = nn.Conv2d(16, 64, 1, bias=True)
+        self.output2 = nn.Conv2d(64, 32, 1, bias=False)
+        self.output3 = nn.Conv2d(64, 16, 1, bias=False)
+
+    def _trunk(self, x: Tensor, lo: int, hi: int) -> Tensor:
+        for i in range(lo, hi + 1):
+            x = getattr(self, f"conv{i}")(x)
+        return x
+
+    def forward(self, x: Tensor) -> Dict[int, Tensor]:
+        half = self._trunk(self._trunk(x, 0, 1), 2, 4)
+        quarter = self._trunk(half, 5, 7)
+        eighth = self._trunk(quarter, 8, 10)
+        out: Dict[int, Tensor] = {3: self.output1(eighth)}
+        top = F.interpolate(eighth, scale_factor=2.0, mode="bilinear", align_corners=False) + self.inner1(quarter)
+        out[2] = self.output2(top)
+        top = F.interpolate(top, scale_factor=2.0, mode="bilinear", align_corners=False) + self.inner2(half)
+        out[1] = self.output3(top)
+        return out
+
+
+class Refinement(nn.Module):
+    """Residual depth refinement from 1/2 to full resolution (reference models/net.py:73-122)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.conv0 = _ConvBnReLU2d(3, 8)
+        self.conv1 = _ConvBnReLU2d(1, 8)
+        self.conv2 = _ConvBnReLU2d(8, 8)
+        self.deconv = nn.ConvTranspose2d(8, 8, 3, padding=1, output_padding=1, stride=2, bias=False)
+        self.bn = nn.BatchNorm2d(8)
+        self.conv3 = _ConvBnReLU2d(16, 8)
+        self.res = nn.Conv2d(8, 1, 3, padding=1, bias=False)
+
+    def forward(self, img: Tensor, depth_half: Tensor, depth_min: Tensor, depth_max: Tensor) -> Tensor:
+        B = depth_min.size(0)
+        lo = depth_min.view(B, 1, 1, 1)
+        span = (depth_max - depth_min).view(B, 1, 1, 1)
+        d = (depth_half - lo) / span
+        up = F.relu(self.bn(self.deconv(self.conv2(self.conv1(d)))), inplace=True)
+        res = self.res(self.conv3(torch.cat((up, self.conv0(img)), dim=1)))
+        d = F.interpolate(d, scale_factor=2.0, mode="nearest") + res
+        return d * span + lo
+
+
+def _round_dims_to_8(images: List[Tensor], intrinsics: Tensor) -> Tuple[List[Tensor], Tensor, int, int]:
+    """reference models/net.py:304-318 (mutates ``intrinsics`` in place like the reference)."""
+    H0, W0 = images[0].shape[-2:]
+    for i, im in enumerate(images):
+        h, w = im.shape[-2:]
+        nh, nw = int(round(h / 8)) * 8, int(round(w / 8)) * 8
+        if (nh, nw) != (h, w):
+            intrinsics[:, i, 0] *= nw / w
+            intrinsics[:, i, 1] *= nh / h
+            images[i] = F.interpolate(im, size=[nh, nw], mode="bilinear", align_corners=False)
+    return images, intrinsics, H0, W0
+
+
+class PatchmatchNet(nn.Module):
+    """Coarse-to-fine cascade: features -> PatchMatch on stages 3, 2, 1 -> refinement.
+
+    Constructor and ``forward`` mirror reference models/net.py:128-136 / :176-301;
+    ``patchmatch_cls`` (extra, keyword-only) selects the stage implementation.
+    """
+
+    GROUPS = (4, 8, 8)  # net.py:158
+    FEATURES = (16, 32, 64)  # net.py:153
+
+    def __init__(
+        self,
+        patchmatch_interval_scale: List[float],
+        propagation_range: List[int],
+        patchmatch_iteration: List[int],
+        patchmatch_num_sample: List[int],
+        propagate_neighbors: List[int],
+        evaluate_neighbors: List[int],
+        *,
+        patchmatch_cls: Type[nn.Module] = None,
+    ) -> None:
+        super().__init__()
+        if patchmatch_cls is None:
+            from .patchmatch import PatchMatch as patchmatch_cls  # the B200-native stage
+        self.stages = 4
+        self.feature = FeatureNet()
+        self.patchmatch_num_sample = patchmatch_num_sample
+        self.propagate_neighbors = propagate_neighbors
+        self.evaluate_neighbors = evaluate_neighbors
+        self.G = list(self.GROUPS)
+        for i in range(self.stages - 1):
+            setattr(
+                self,
+                f"patchmatch_{i + 1}",
+                patchmatch_cls(
+                    propagation_out_range=propagation_range[i],
+                    patchmatch_iteration=patchmatch_iteration[i],
+                    patchmatch_num_sample=patchmatch_num_sample[i],
+                    patchmatch_interval_scale=patchmatch_interval_scale[i],
+                    num_feature=self.FEATURES[i],
+                    G=self.G[i],
+                    propagate_neighbors=propagate_neighbors[i],
+                    evaluate_neighbors=evaluate_neighbors[i],
+                    stage=i + 1,
+                ),
+            )
+        self.upsample_net = Refinement()
+        # eval mode: push all views through FeatureNet as one batch (set False to go view by view)
+        self.stack_views = True
+
+    def extract_features(self, images: List[Tensor]) -> List[Dict[int, Tensor]]:
+        """One FeatureNet pass per view (reference net.py:203-208).  In eval mode the
+        views are stacked into one batch (BatchNorm uses running statistics, so the
+        per-sample result is unchanged and the launch count drops N-fold)."""
+        if self.training or not self.stack_views or len({im.shape for im in images}) != 1:
+            return [self.feature(im) for im in images]
+        n, b = len(images), images[0].shape[0]
+        stacked = self.feature(torch.cat(images, dim=0))
+        return [{k: v[i * b:(i + 1) * b] for k, v in stacked.items()} for i in range(n)]
+
+    def forward(
+        self,
+        images: List[Tensor],
+        intrinsics: Tensor,
+        extrinsics: Tensor,
+        depth_min: Tensor,
+        depth_max: Tensor,
+    ) -> Tuple[Tensor, Tensor, Dict[int, List[Tensor]]]:
+        assert len(images) == intrinsics.size(1), "Different number of images and intrinsic matrices"
+        assert len(images) == extrinsics.size(1), "Different number of images and extrinsic matrices"
+        images = list(images)
+        images, intrinsics, H0, W0 = _round_dims_to_8(images, intrinsics)
+        ref_image = images[0]
+        Hr, Wr = ref_image.shape[-2:]
+
+        feats = self.extract_features(images)
+        ref_feat, src_feats = feats[0], feats[1:]
+        depth_min = depth_min.float()
+        depth_max = depth_max.float()
+
+        dev = intrinsics.device
+        depth = torch.empty(0, device=dev)
+        score = torch.empty(0, device=dev)
+        view_weights = torch.empty(0, device=dev)
+        per_stage: Dict[int, List[Tensor]] = {}
+
+        scale = 0.125
+        for stage in (3, 2, 1):
+            K = intrinsics.clone()
+            K[:, :, :2] *= scale
+            proj = extrinsics.clone()
+            proj[:, :, :3, :4] = torch.matmul(K, extrinsics[:, :, :3, :4])
+            projs = torch.unbind(proj, 1)
+            scale *= 2.0
+            depths, score, view_weights = getattr(self, f"patchmatch_{stage}")(
+                ref_feature=ref_feat[stage],
+                src_features=[f[stage] for f in src_feats],
+                ref_proj=projs[0],
+                src_projs=projs[1:],
+                depth_min=depth_min,
+                depth_max=depth_max,
+                depth=depth,
+                view_weights=view_weights,
+            )
+            per_stage[stage] = depths
+            depth = depths[-1].detach()
+            if stage > 1:
+                depth = F.interpolate(depth, scale_factor=2.0, mode="nearest")
+                view_weights = F.interpolate(view_weights, scale_factor=2.0, mode="nearest")
+
+        depth = self.upsample_net(ref_image, depth, depth_min, depth_max)
+        if (Hr, Wr) != (H0, W0):
+            depth = F.interpolate(depth, size=[H0, W0], mode="bilinear", align_corners=False)
+        per_stage[0] = [depth]
+        if self.training:
+            return depth, torch.empty(0, device=dev), per_stage
+
+        # photometric confidence (net.py:289-299): probability mass of the 4 hypotheses around the regressed index
+        D = self.patchmatch_num_sample[0]
+        mass4 = 4 * F.avg_pool3d(F.pad(score.unsqueeze(1), pad=(0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
+        idx = torch.sum(score * torch.arange(D, device=score.device, dtype=torch.float).view(1, D, 1, 1), dim=1)
+        idx = idx.unsqueeze(1).long().clamp(0, D - 1)
+        conf = torch.gather(mass4, 1, idx)
+        conf = F.interpolate(conf, size=[H0, W0], mode="nearest").squeeze(1)
+        return depth, conf, per_stage
+
+
+def load_reference_state(model: nn.Module, state: Dict[str, Tensor]) -> None:
+    """Load a reference checkpoint's ``["model"]`` dict (keys carry the DataParallel
+    ``module.`` prefix, reference eval.py:33-35) and insist every key matches."""
+    clean = {(k[7:] if k.startswith("module.") else k): v for k, v in state.items()}
+    missing, unexpected = model.load_state_dict(clean, strict=False)
+    if missing or unexpected:
+        raise RuntimeError(f"state dict mismatch: missing={missing} unexpected={unexpected}")

@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C ABI (``include/patchmatch_b200.h``).
+
+PyTorch is plumbing here: it owns the device buffers and the CUDA stream.  Each
+wrapper checks dtype / device / layout, allocates the output with the caching
+allocator, and enqueues ONE native kernel on the tensor's current stream via
+ctypes -- capturable in a CUDA graph, no host synchronisation.  A CPU tensor is
+an error (there is no fallback path).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _native
+
+Tensor = torch.Tensor
+
+
+def _require(t: Tensor, name: str, ndim: Optional[int] = None) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: the B200 path needs a CUDA tensor (got {t.device}); there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _rowmajor_4x4(m: Tensor, name: str) -> Tensor:
+    """[B,4,4] with contiguous 4x4 blocks; the batch stride may be anything (torch.unbind views)."""
+    if not m.is_cuda or m.dtype != torch.float32 or m.dim() != 3 or m.shape[1:] != (4, 4):
+        raise RuntimeError(f"{name}: expected a CUDA float32 [B,4,4] tensor, got {m.dtype} {tuple(m.shape)} on {m.device}")
+    if m.stride(1) != 4 or m.stride(2) != 1:
+        m = m.contiguous()
+    return m
+
+
+def relative_projection(ref_proj: Tensor, src_projs: Sequence[Tensor]) -> Tensor:
+    """[V,B,12] rotation/translation of src_proj @ inv(ref_proj); reference module.py:148-150."""
+    B = ref_proj.shape[0]
+    V = len(src_projs)
+    ref = _rowmajor_4x4(ref_proj, "ref_proj")
+    mats = [_rowmajor_4x4(m, "src_proj") for m in src_projs]
+    if any(m.shape[0] != B for m in mats):
+        raise RuntimeError("relative_projection: batch size mismatch")
+    if B > 1 and len({m.stride(0) for m in mats}) != 1:
+        mats = [m.contiguous() for m in mats]
+    out = torch.empty((V, B, 12), dtype=torch.float32, device=ref.device)
+    arr, keep = _native.pointer_array([m.data_ptr() for m in mats])
+    with torch.cuda.device(ref.device):
+        rc = _native.lib().pmb200_relative_projection(
+            ref.data_ptr(), ref.stride(0), arr, mats[0].stride(0), V, B, out.data_ptr(), _stream(ref)
+        )
+    _native.check(rc, "relative_projection")
+    return out
+
+
+def _is_packed_nhwc(maps: Sequence[Tensor]) -> bool:
+    """True when the maps are channels-last and already adjacent in memory (e.g. slices of one
+    stacked channels-last FeatureNet output), so that packing would be a no-op."""
+    first = maps[0]
+    B, C, H, W = first.shape
+    want = (H * W * C, 1, W * C, C)
+    step = B * H * W * C * first.element_size()
+    for i, m in enumerate(maps):
+        if m.shape != first.shape or m.stride() != want or m.data_ptr() != first.data_ptr() + i * step:
+            return False
+    return True
+
+
+def pack_nhwc(maps: Sequence[Tensor]) -> Tensor:
+    """[n,B,H,W,C] channels-last copy of n NCHW maps of equal shape (one launch)."""
+    first = maps[0]
+    B, C, H, W = first.shape
+    if _is_packed_nhwc(maps):
+        return torch.as_strided(first, (len(maps), B, H, W, C), (B * H * W * C, H * W * C, W * C, C, 1))
+    srcs = [_require(m, "feature map", 4) for m in maps]
+    for m in srcs:
+        if m.shape != first.shape:
+            raise RuntimeError("pack_nhwc: maps must share one shape")
+    out = torch.empty((len(srcs), B, H, W, C), dtype=torch.float32, device=first.device)
+    arr, keep = _native.pointer_array([m.data_ptr() for m in srcs])
+    with torch.cuda.device(first.device):
+        rc = _native.lib().pmb200_pack_nhwc(arr, len(srcs), B, C, H, W, out.data_ptr(), _stream(first))
+    _native.check(rc, "pack_nhwc")
+    return out
+
+
+def warp_corr(
+    ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tensor, G: int, view_weights: Optional[Tensor] = None
+) -> Tensor:
+    """K-A.  ref [B,H,W,C], src [V,B,Hs,Ws,C], rt [V,B,12], depth [B,D,H,W].
+
+    Without view weights: per-view similarities [V,B,G,D,H,W].  With view_weights [B,V,H,W]:
+    the weighted average over views [B,G,D,H,W] (reference patchmatch.py:192-217)."""
+    ref = _require(ref_nhwc, "ref_nhwc", 4)
+    src = _require(src_nhwc, "src_nhwc", 5)
+    rt = _require(rt, "rt", 3)
+    depth = _require(depth, "depth", 4)
+    B, H, W, C = ref.shape
+    V, Bs, Hs, Ws, Cs = src.shape
+    D = depth.shape[1]
+    if Bs != B or Cs != C or rt.shape != (V, B, 12) or depth.shape != (B, D, H, W):
+        raise RuntimeError("warp_corr: inconsistent shapes")
+    if view_weights is not None:
+        vw = _require(view_weights, "view_weights", 4)
+        if vw.shape != (B, V, H, W):
+            raise RuntimeError("warp_corr: view_weights must be [B,V,H,W]")
+        out = torch.empty((B, G, D, H, W), dtype=torch.float32, device=ref.device)
+        vw_ptr = vw.data_ptr()
+    else:
+        out = torch.empty((V, B, G, D, H, W), dtype=torch.float32, device=ref.device)
+        vw_ptr = None
+    with torch.cuda.device(ref.device):
+        rc = _native.lib().pmb200_warp_corr(
+            ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), vw_ptr, out.data_ptr(),
+            V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
+        )
+    _native.check(rc, "warp_corr")
+    return out
+
+
+def aggregate_views(sims: Tensor, view_weights: Tensor) -> Tensor:
+    """sum_v sims[v]*w[:,v] / (1e-5 + sum_v w[:,v]) -> [B,G,D,H,W]."""
+    sims = _require(sims, "sims", 6)
+    vw = _require(view_weights, "view_weights", 4)
+    V, B, G, D, H, W = sims.shape
+    if vw.shape != (B, V, H, W):
+        raise RuntimeError("aggregate_views: view_weights must be [B,V,H,W]")
+    out = torch.empty((B, G, D, H, W), dtype=torch.float32, device=sims.device)
+    with torch.cuda.device(sims.device):
+        rc = _native.lib().pmb200_aggregate_views(
+            sims.data_ptr(), vw.data_ptr(), out.data_ptr(), V, B, G, D, H, W, _stream(sims)
+        )
+    _native.check(rc, "aggregate_views")
+    return out
+
+
+def offset_corr(ref_nhwc: Tensor, offsets: Tensor, G: int, K: int, dilation: int) -> Tensor:
+    """K-A'.  ref [B,H,W,C], offsets [B,2K,H,W] -> [B,G,K,H,W]."""
+    ref = _require(ref_nhwc, "ref_nhwc", 4)
+    off = _require(offsets, "offsets", 4)
+    B, H, W, C = ref.shape
+    if off.shape != (B, 2 * K, H, W):
+        raise RuntimeError("offset_corr: offsets must be [B,2K,H,W]")
+    out = torch.empty((B, G, K, H, W), dtype=torch.float32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        rc = _native.lib().pmb200_offset_corr(
+            ref.data_ptr(), off.data_ptr(), out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
+        )
+    _native.check(rc, "offset_corr")
+    return out
+
+
+MODE_RANDOM, MODE_PERTURB, MODE_PASSTHROUGH = 0, 1, 2
+
+
+def init_propagate(
+    seed_map: Tensor,
+    offsets: Optional[Tensor],
+    depth_min: Tensor,
+    depth_max: Tensor,
+    mode: int,
+    Ns: int,
+    Kp: int,
+    dilation: int,
+    interval_scale: float,
+) -> Tensor:
+    """K-C.  seed_map: U[0,1) noise [B,48,H,W] (mode 0) or current depth [B,1,H,W]; -> [B,Ns+Kp,H,W]."""
+    seed = _require(seed_map, "seed_map", 4)
+    B, S, H, W = seed.shape
+    if S != (48 if mode == MODE_RANDOM else 1):
+        raise RuntimeError("init_propagate: seed_map has the wrong number of channels")
+    dmin = _require(depth_min.reshape(-1), "depth_min", 1)
+    dmax = _require(depth_max.reshape(-1), "depth_max", 1)
+    if dmin.numel() != B or dmax.numel() != B:
+        raise RuntimeError("init_propagate: depth_min/max must have B elements")
+    off_ptr = None
+    if Kp > 0:
+        off = _require(offsets, "offsets", 4)
+        if off.shape != (B, 2 * Kp, H, W):
+            raise RuntimeError("init_propagate: offsets must be [B,2Kp,H,W]")
+        off_ptr = off.data_ptr()
+    out = torch.empty((B, Ns + Kp, H, W), dtype=torch.float32, device=seed.device)
+    with torch.cuda.device(seed.device):
+        rc = _native.lib().pmb200_init_propagate(
+            seed.data_ptr(), off_ptr, dmin.data_ptr(), dmax.data_ptr(), out.data_ptr(),
+            mode, B, H, W, Ns, Kp, dilation, float(interval_scale), _stream(seed),
+        )
+    _native.check(rc, "init_propagate")
+    return out
+
+
+def adaptive_eval(
+    score0: Tensor,
+    depth_sample: Tensor,
+    offsets: Tensor,
+    feature_weight: Tensor,
+    depth_min: Tensor,
+    depth_max: Tensor,
+    dilation: int,
+    interval_scale: float,
+    is_inverse: bool,
+):
+    """K-B.  -> (depth [B,H,W], prob [B,D,H,W])."""
+    sc = _require(score0, "score0", 4)
+    ds = _require(depth_sample, "depth_sample", 4)
+    off = _require(offsets, "offsets", 4)
+    fw = _require(feature_weight, "feature_weight", 4)
+    B, D, H, W = sc.shape
+    K = fw.shape[1]
+    if ds.shape != sc.shape or off.shape != (B, 2 * K, H, W) or fw.shape != (B, K, H, W):
+        raise RuntimeError("adaptive_eval: inconsistent shapes")
+    dmin = _require(depth_min.reshape(-1), "depth_min", 1)
+    dmax = _require(depth_max.reshape(-1), "depth_max", 1)
+    prob = torch.empty((B, D, H, W), dtype=torch.float32, device=sc.device)
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=sc.device)
+    with torch.cuda.device(sc.device):
+        rc = _native.lib().pmb200_adaptive_eval(
+            sc.data_ptr(), ds.data_ptr(), off.data_ptr(), fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
+            prob.data_ptr(), depth.data_ptr(), B, D, H, W, K, dilation, float(interval_scale),
+            1 if is_inverse else 0, _stream(sc),
+        )
+    _native.check(rc, "adaptive_eval")
+    return depth, prob

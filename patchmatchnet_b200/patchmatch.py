@@ -1,0 +1,259 @@
+"""B200-native ``PatchMatch``: drop-in for reference ``models/patchmatch.py:242-529``.
+
+Same constructor, same ``forward`` signature and return triple, same parameter /
+buffer names and shapes (the reference checkpoints load with every key matched),
+same error behaviour (``assert`` on view/matrix count mismatch,
+``NotImplementedError`` for neighbour counts the reference does not know).
+
+What runs where (per PatchMatch iteration; DESIGN.md has the byte budgets):
+
+    propa_conv / eval_conv, the three 1x1x1 MLP heads ... cuDNN (library ops, as the scope says)
+    everything else ..................................... five hand-written sm_100a kernels
+        K-C  init_propagate   hypothesis init + neighbour gather + sort          (a8, a9, a7)
+        K-A  warp_corr        warp + bilinear gather + group correlation
+                              + view-weighted aggregation, all views, one launch (a1, a2, a3)
+        K-A' offset_corr      reference self-correlation at learned neighbours   (a11, a7)
+        K-B  adaptive_eval    depth/feature weights + aggregation + softmax
+                              + regression                                       (a10, a6, a5)
+        relative_projection   src_proj . inv(ref_proj), once per stage, no host sync (a1 prologue)
+
+There is no CPU or pure-PyTorch implementation of those kernels here: CPU tensors
+raise.  (The CPU restatement lives in ``oracle/`` and is test infrastructure.)
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+def is_empty(x: Tensor) -> bool:
+    """reference models/module.py:199-200: optional tensors are signalled by numel() == 0."""
+    return x.numel() == 0
+
+
+class _ConvBnReLU3d(nn.Module):
+    """1x1x1 conv3d (no bias) + BatchNorm3d + ReLU; children ``conv`` / ``bn`` (reference module.py:43-72)."""
+
+    def __init__(self, cin: int, cout: int) -> None:
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, 1, stride=1, padding=0, bias=False)
+        self.bn = nn.BatchNorm3d(cout)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.relu(self.bn(self.conv(x)), inplace=True)
+
+
+class _PointwiseHead(nn.Module):
+    """G -> 16 -> 8 -> 1 per-voxel MLP shared by the three learned heads.  ``last`` names the final
+    conv so the state-dict keys match the reference (``conv2`` in PixelwiseNet, ``similarity`` in
+    SimilarityNet / FeatureWeightNet)."""
+
+    def __init__(self, G: int, last: str) -> None:
+        super().__init__()
+        self.conv0 = _ConvBnReLU3d(G, 16)
+        self.conv1 = _ConvBnReLU3d(16, 8)
+        self._last = last
+        setattr(self, last, nn.Conv3d(8, 1, 1, stride=1, padding=0))
+
+    def forward(self, x: Tensor) -> Tensor:
+        """[N,G,D,H,W] -> [N,D,H,W]"""
+        return getattr(self, self._last)(self.conv1(self.conv0(x))).squeeze(1)
+
+
+class PixelwiseNet(_PointwiseHead):
+    """Pixel-wise view weight: max over hypotheses of sigmoid(MLP(similarity)); reference patchmatch.py:672-702."""
+
+    def __init__(self, G: int) -> None:
+        super().__init__(G, "conv2")
+
+    def forward(self, x: Tensor) -> Tensor:
+        return torch.max(torch.sigmoid(super().forward(x)), dim=1)[0].unsqueeze(1)
+
+
+class SimilarityNet(_PointwiseHead):
+    """Per-hypothesis score MLP; the neighbour aggregation that follows it in the reference
+    (patchmatch.py:569-577) is part of kernel K-B."""
+
+    def __init__(self, G: int) -> None:
+        super().__init__(G, "similarity")
+
+
+class FeatureWeightNet(_PointwiseHead):
+    """sigmoid(MLP(self-correlation)); the gather + correlation in front of it (reference
+    patchmatch.py:613-622) is kernel K-A'."""
+
+    def __init__(self, neighbors: int = 9, G: int = 8) -> None:
+        super().__init__(G, "similarity")
+        self.neighbors = neighbors
+        self.G = G
+
+    def forward(self, corr: Tensor) -> Tensor:
+        return torch.sigmoid(super().forward(corr))
+
+
+class Evaluation(nn.Module):
+    """Owner of the two evaluation heads (names as in reference patchmatch.py:132-143)."""
+
+    def __init__(self, G: int = 8) -> None:
+        super().__init__()
+        self.G = G
+        self.pixel_wise_net = PixelwiseNet(G)
+        self.similarity_net = SimilarityNet(G)
+
+
+class PatchMatch(nn.Module):
+    """Learned PatchMatch on one pyramid level; see module docstring."""
+
+    def __init__(
+        self,
+        propagation_out_range: int = 2,
+        patchmatch_iteration: int = 2,
+        patchmatch_num_sample: int = 16,
+        patchmatch_interval_scale: float = 0.025,
+        num_feature: int = 64,
+        G: int = 8,
+        propagate_neighbors: int = 16,
+        evaluate_neighbors: int = 9,
+        stage: int = 3,
+    ) -> None:
+        super().__init__()
+        self.patchmatch_iteration = patchmatch_iteration
+        self.patchmatch_interval_scale = patchmatch_interval_scale
+        self.patchmatch_num_sample = patchmatch_num_sample
+        self.propa_num_feature = num_feature
+        self.G = G
+        self.stage = stage
+        self.dilation = propagation_out_range
+        self.propagate_neighbors = propagate_neighbors
+        self.evaluate_neighbors = evaluate_neighbors
+        # Tests inject a shared U[0,1) draw here when comparing against an oracle on another device;
+        # by default the draw is torch.rand on the compute device, exactly as reference patchmatch.py:61-63.
+        self.rand_source: Optional[Callable] = None
+
+        self.evaluation = Evaluation(G)
+        # zero-initialised offset convs, always defined (reference patchmatch.py:286-311)
+        self.propa_conv = nn.Conv2d(
+            num_feature, max(2 * propagate_neighbors, 1), 3, stride=1,
+            padding=self.dilation, dilation=self.dilation, bias=True,
+        )
+        self.eval_conv = nn.Conv2d(
+            num_feature, 2 * evaluate_neighbors, 3, stride=1,
+            padding=self.dilation, dilation=self.dilation, bias=True,
+        )
+        for conv in (self.propa_conv, self.eval_conv):
+            nn.init.constant_(conv.weight, 0.0)
+            nn.init.constant_(conv.bias, 0.0)
+        self.feature_weight_net = FeatureWeightNet(evaluate_neighbors, G)
+
+    # ------------------------------------------------------------------
+    def _check_neighbour_counts(self) -> None:
+        if self.propagate_neighbors not in (0, 4, 8, 16):
+            raise NotImplementedError  # reference patchmatch.py:359-360
+        if self.evaluate_neighbors not in (9, 17):
+            raise NotImplementedError  # reference patchmatch.py:391-392
+
+    def forward(
+        self,
+        ref_feature: Tensor,
+        src_features: List[Tensor],
+        ref_proj: Tensor,
+        src_projs: List[Tensor],
+        depth_min: Tensor,
+        depth_max: Tensor,
+        depth: Tensor,
+        view_weights: Tensor,
+    ) -> Tuple[List[Tensor], Tensor, Tensor]:
+        self._check_neighbour_counts()
+        assert len(src_features) == len(
+            src_projs
+        ), "Patchmatch Evaluation: Different number of images and projection matrices"
+        if not is_empty(view_weights):
+            assert (
+                len(src_features) == view_weights.size()[1]
+            ), "Patchmatch Evaluation: Different number of images and view weights"
+        if not ref_feature.is_cuda:
+            raise RuntimeError(
+                "patchmatchnet_b200.PatchMatch runs on CUDA (sm_100a) only; there is no CPU fallback "
+                f"(got a tensor on {ref_feature.device})"
+            )
+        if torch.is_grad_enabled() and (
+            ref_feature.requires_grad or any(p.requires_grad for p in self.parameters())
+        ) and self.training:
+            raise NotImplementedError(
+                "training backward of the fused kernels is not built yet (DESIGN.md, 'next'); "
+                "run under torch.no_grad() / eval()"
+            )
+
+        B, C, H, W = ref_feature.shape
+        V = len(src_features)
+        Kp, Ke = self.propagate_neighbors, self.evaluate_neighbors
+        iters = self.patchmatch_iteration
+        depth_min = depth_min.reshape(B).float()
+        depth_max = depth_max.reshape(B).float()
+
+        # learned 2-D offsets (cuDNN)
+        propa_off: Optional[Tensor] = None
+        if Kp > 0 and not (self.stage == 1 and iters == 1):
+            propa_off = self.propa_conv(ref_feature)
+        eval_off = self.eval_conv(ref_feature)
+
+        # channels-last feature pack [1+V,B,H,W,C] (zero-copy if the producer already emitted it)
+        same_size = all(f.shape == ref_feature.shape for f in src_features)
+        if same_size:
+            pack = ops.pack_nhwc([ref_feature] + list(src_features))
+            ref_nhwc, src_nhwc = pack[0], pack[1:]
+        else:
+            ref_nhwc = ops.pack_nhwc([ref_feature])[0]
+            src_nhwc = ops.pack_nhwc(list(src_features))
+        rt = ops.relative_projection(ref_proj, list(src_projs))
+
+        # feature weight of the evaluation neighbours, once per stage (reference patchmatch.py:475)
+        feature_weight = self.feature_weight_net(ops.offset_corr(ref_nhwc, eval_off, self.G, Ke, self.dilation))
+
+        sample = depth
+        prob = torch.empty(0, device=ref_feature.device)
+        outs: List[Tensor] = []
+        for it in range(1, iters + 1):
+            last_of_stage1 = self.stage == 1 and it == iters
+            kp_now = Kp if (Kp > 0 and not last_of_stage1) else 0
+            if is_empty(sample):
+                draw = self.rand_source if self.rand_source is not None else torch.rand
+                seed = draw(size=(B, 48, H, W), device=ref_feature.device)
+                mode, ns = ops.MODE_RANDOM, 48
+            elif self.patchmatch_num_sample == 1:
+                seed, mode, ns = sample.detach(), ops.MODE_PASSTHROUGH, 1
+            else:
+                seed, mode, ns = sample.detach(), ops.MODE_PERTURB, self.patchmatch_num_sample
+            hyp = ops.init_propagate(
+                seed, propa_off if kp_now > 0 else None, depth_min, depth_max,
+                mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale,
+            )  # [B,D,H,W]
+
+            if is_empty(view_weights):
+                sims = ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G)  # [V,B,G,D,H,W]
+                if self.training:
+                    vws = [self.evaluation.pixel_wise_net(sims[v]) for v in range(V)]
+                    view_weights = torch.cat(vws, dim=1)
+                else:  # BatchNorm uses running statistics: all views in one pass
+                    D = hyp.shape[1]
+                    vw = self.evaluation.pixel_wise_net(sims.view(V * B, self.G, D, H, W))  # [V*B,1,H,W]
+                    view_weights = vw.view(V, B, H, W).permute(1, 0, 2, 3).contiguous()
+                similarity = ops.aggregate_views(sims, view_weights)
+            else:
+                similarity = ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights)
+
+            score0 = self.evaluation.similarity_net(similarity)  # [B,D,H,W]
+            new_depth, prob = ops.adaptive_eval(
+                score0, hyp, eval_off, feature_weight, depth_min, depth_max,
+                self.dilation, self.patchmatch_interval_scale, last_of_stage1,
+            )
+            sample = new_depth.unsqueeze(1)
+            outs.append(sample)
+        return outs, prob, view_weights.detach()
