@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- depth-maps/s of the PatchmatchNet cascade with the B200-native PatchMatch hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (one JSON line on rank 0)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1]): 1 reference + 4 source views, 640x512, full 3-stage cascade with
+64/32 -> 16/16 -> 8 hypotheses, one reference view per GPU (weak scaling: N GPUs -> N depth maps per step,
+no collective on the data path).  A "step" is one full forward over one batch of synthetic input.
+
+Numbers on the JSON line
+    value      depth-maps/s, inputs resident in HBM, forward replayed from a CUDA graph, L2 flushed
+               between timed steps, device time by CUDA events, max over ranks
+    e2e        same metric through the public API (DepthEngine.infer_stream): pinned HOST inputs copied
+               to the device and results copied back inside the timed region, every step
+    roofline   the dominant hand-written kernel (fused warp+correlation, all source views per launch):
+               algorithmic bytes per launch / CUDA-event duration of that launch, against the measured
+               HBM copy bandwidth in MEASURED_PEAKS.json
+    cpu_baseline  the oracle (CPU restatement of the reference, bit-identical to it) timed on the host
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from patchmatchnet_b200 import synthetic  # noqa: E402
+
+WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_000007.pt")
+METRIC = "depth-maps/sec (1ref+4src, 640x512)"
+UNIT = "depth-maps/s"
+
+
+def build_net(patchmatch_cls=None):
+    from patchmatchnet_b200.net import PatchmatchNet, load_reference_state
+
+    kw = dict(synthetic.DEFAULT_NET_KWARGS)
+    net = PatchmatchNet(**kw) if patchmatch_cls is None else PatchmatchNet(**kw, patchmatch_cls=patchmatch_cls)
+    if os.path.exists(WEIGHTS):
+        load_reference_state(net, torch.load(WEIGHTS, map_location="cpu"))
+        weights = "reference checkpoint params_000007 (fixture)"
+    else:  # random init; give the zero-initialised offset convs something to do
+        g = torch.Generator().manual_seed(0)
+        for m in (net.patchmatch_1, net.patchmatch_2, net.patchmatch_3):
+            for conv in (m.propa_conv, m.eval_conv):
+                conv.weight.data.normal_(0, 0.05, generator=g)
+        weights = "random init"
+    return net.eval(), weights
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL,
+            )
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference, host cores)
+# ----------------------------------------------------------------------------------------------
+
+
+def cpu_forward_timer(height: int, width: int, n_views: int):
+    from oracle.pm_oracle import PatchMatchOracle  # allowed here: cpu_baseline / --impl reference legs only
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net, _ = build_net(PatchMatchOracle)
+    net.stack_views = False  # the reference runs FeatureNet view by view (net.py:203-208)
+    inp = synthetic.make_inputs(1, n_views, height, width, seed=0)
+
+    def step():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            net([i.clone() for i in inp["images"]], inp["intrinsics"].clone(), inp["extrinsics"].clone(), inp["depth_min"], inp["depth_max"])
+            return time.perf_counter() - t0
+
+    return step, torch.get_num_threads()
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, cores = cpu_forward_timer(args.height, args.width, args.views)
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = sum(times)
+    value = args.steps / total
+    sample = f"{args.steps} full forwards of the workload (1 depth map each) after {args.warmup} warm-up, {cores} torch threads"
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"1ref+{args.views - 1}src {args.width}x{args.height} 3-stage cascade (64/32,16/16,8 hyp), batch 1, host CPU",
+                   "weights": "reference checkpoint (fixture)" if os.path.exists(WEIGHTS) else "random init"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# this repo
+# ----------------------------------------------------------------------------------------------
+
+
+class LaunchCounter:
+    """Counts native (libpmb200.so) kernel launches issued through patchmatchnet_b200.ops."""
+
+    NAMES = ("relative_projection", "pack_nhwc", "warp_corr", "aggregate_views", "offset_corr", "init_propagate", "adaptive_eval")
+
+    def __init__(self):
+        from patchmatchnet_b200 import _native
+
+        self.n = 0
+        self.by_name = {}
+        self._lib = _native.lib()
+        self._orig = {}
+
+    def __enter__(self):
+        for nm in self.NAMES:
+            fn = getattr(self._lib, "pmb200_" + nm)
+            self._orig[nm] = fn
+
+            def wrapped(*a, _fn=fn, _nm=nm):
+                self.n += 1
+                self.by_name[_nm] = self.by_name.get(_nm, 0) + 1
+                return _fn(*a)
+
+            setattr(self._lib, "pmb200_" + nm, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        for nm, fn in self._orig.items():
+            setattr(self._lib, "pmb200_" + nm, fn)
+
+
+def warp_corr_algorithmic_bytes(V, B, C, G, H, W, D):
+    """per source view 4*B*H*W*(2C + D + G*D) bytes; one launch processes V views."""
+    return V * 4 * B * H * W * (2 * C + D + G * D)
+
+
+def warp_corr_minimum_bytes(V, B, C, G, H, W, D):
+    """What the fused launch must actually move: ref once, V source maps, depth, V weights, one output."""
+    return 4 * B * H * W * (C * (1 + V) + D + V + G * D)
+
+
+def time_warp_corr_calls(net, dev_inputs, peak_gbs, flush, iters=20):
+    """Re-run every fused warp+correlation launch of one forward in isolation, L2 flushed before each,
+    CUDA events on the launching (current) stream."""
+    from patchmatchnet_b200 import ops
+
+    calls = []
+    orig = ops.warp_corr
+
+    def spy(ref, src, rt, depth, G, vw=None):
+        calls.append((ref, src, rt, depth, G, vw))
+        return orig(ref, src, rt, depth, G, vw)
+
+    ops.warp_corr = spy
+    try:
+        with torch.no_grad():
+            torch.manual_seed(0)
+            net(*dev_inputs())
+    finally:
+        ops.warp_corr = orig
+    torch.cuda.synchronize()
+    rows = []
+    for (ref, src, rt, depth, G, vw) in calls:
+        B, H, W, C = ref.shape
+        V, D = src.shape[0], depth.shape[1]
+        for _ in range(3):
+            orig(ref, src, rt, depth, G, vw)
+        ts = []
+        for _ in range(iters):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            orig(ref, src, rt, depth, G, vw)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        t = statistics.mean(ts)
+        alg = warp_corr_algorithmic_bytes(V, B, C, G, H, W, D)
+        rows.append({
+            "shape": f"C{C} G{G} D{D} {H}x{W} V{V} B{B}" + ("" if vw is not None else " per-view"),
+            "us": 1e6 * t, "us_min": 1e6 * min(ts), "algorithmic_bytes": alg,
+            "minimum_bytes": warp_corr_minimum_bytes(V, B, C, G, H, W, D),
+            "achieved_gbs": alg / t / 1e9, "frac": alg / t / 1e9 / peak_gbs,
+        })
+    return rows
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--height", type=int, default=512)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--views", type=int, default=5, help="1 reference + (views-1) sources")
+    ap.add_argument("--batch", type=int, default=1, help="reference views per GPU")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-samples", type=int, default=4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    from patchmatchnet_b200.engine import DepthEngine
+
+    B, N, H, W = args.batch, args.views, args.height, args.width
+    net, weights = build_net()
+    eng = DepthEngine(net, B, N, H, W, device=str(dev), use_graph=not args.no_graph)
+
+    host = synthetic.make_inputs(B, N, H, W, seed=rank)
+    host_pinned = dict(
+        images=[im.pin_memory() for im in host["images"]],
+        intrinsics=host["intrinsics"].pin_memory(), extrinsics=host["extrinsics"].pin_memory(),
+        depth_min=host["depth_min"].pin_memory(), depth_max=host["depth_max"].pin_memory(),
+    )
+    d_in = dict(images=[im.to(dev) for im in host["images"]], intrinsics=host["intrinsics"].to(dev),
+                extrinsics=host["extrinsics"].to(dev), depth_min=host["depth_min"].to(dev), depth_max=host["depth_max"].to(dev))
+    for s in (0, 1):
+        eng.set_device_inputs(s, d_in["images"], d_in["intrinsics"], d_in["extrinsics"], d_in["depth_min"], d_in["depth_max"])
+    torch.cuda.synchronize()
+
+    with LaunchCounter() as lc:
+        eng.prepare()  # warm-up forwards + graph capture
+    forwards_counted = 2 * eng._warmup + (2 if eng.use_graph else 0)
+    launches_per_step = lc.n // max(1, forwards_counted)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernel-side throughput: inputs resident in HBM ----------------
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        flush()
+        eng.run_slot(0)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush()
+        starts[i].record(stream)
+        eng.run_slot(0)
+        ends[i].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_seconds = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
+
+    # ---------------- end to end: pinned host in, pinned host out, every step ----------------
+    reqs = [host_pinned] * (args.steps)
+    eng.infer_stream(reqs[: args.warmup])
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(eng.compute_stream):
+        t0.record(eng.compute_stream)
+    eng.copy_stream.wait_stream(eng.compute_stream)
+    h2d, d2h = eng.infer_stream(reqs)
+    with torch.cuda.stream(eng.compute_stream):
+        t1.record(eng.compute_stream)
+    barrier()
+    e2e_seconds = t0.elapsed_time(t1) * 1e-3
+
+    if dist is not None:
+        t = torch.tensor([dev_seconds, e2e_seconds], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_seconds, e2e_seconds = float(t[0]), float(t[1])
+
+    maps = args.steps * B * world
+    value = maps / dev_seconds
+    e2e_value = maps / e2e_seconds
+
+    # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N=1 detail) ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    roofline, detail, cpu_baseline = None, None, None
+    if rank == 0:
+        dev_inputs = lambda: ([im.clone() for im in d_in["images"]], d_in["intrinsics"].clone(), d_in["extrinsics"].clone(),
+                              d_in["depth_min"], d_in["depth_max"])
+        detail = time_warp_corr_calls(net, dev_inputs, peak_gbs, flush)
+        if detail:
+            top = max(detail, key=lambda r: r["us"])
+            traffic = None
+            tfile = os.path.join(REPO, "profiles", "warp_corr_traffic.json")
+            if os.path.exists(tfile):
+                try:
+                    traffic = json.load(open(tfile)).get(top["shape"])
+                except Exception:
+                    traffic = None
+            roofline = {"bound": "hbm", "kernel": "warp_corr_kernel (fused warp+bilinear gather+group correlation+view aggregation)",
+                        "launch": top["shape"], "achieved": top["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+                        "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "us_per_launch": top["us"],
+                        "all_launches_weighted_frac": sum(r["algorithmic_bytes"] for r in detail) / sum(r["us"] * 1e-6 for r in detail) / 1e9 / peak_gbs}
+        if world == 1 and not args.no_cpu_baseline:
+            step, cores = cpu_forward_timer(H, W, N)
+            step()
+            ts = [step() for _ in range(args.cpu_samples)]
+            cpu_baseline = {"value": len(ts) / sum(ts), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{len(ts)} full forwards of the same workload (after 1 warm-up) with the oracle port of the reference, {cores} torch threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"1ref+{N - 1}src {W}x{H} 3-stage cascade (64/32,16/16,8 hyp), batch {B} per GPU (BASELINE.json configs[1])",
+                       "parallelism": f"{world} x (1 process/GPU, reference views sharded by rank, no data-path collective)",
+                       "weights": weights, "cuda_graph": eng.use_graph, "l2": "flushed between timed steps (256 MiB write, outside the events)",
+                       "library_convs": "cuDNN, torch default (TF32 allowed) for FeatureNet/Refinement/1x1x1 heads"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_seconds / args.steps,
+                    "how": "DepthEngine.infer_stream: pinned host inputs -> device (copy stream, overlapped with the previous step's graph) -> graph -> pinned host outputs"},
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "native_kernels_per_step": {k: v // max(1, forwards_counted) for k, v in sorted(lc.by_name.items())},
+            "clocks": clocks,
+            "roofline": roofline, "roofline_detail": detail, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,393 @@
+"""Parity of the CUDA path (called through the C ABI via patchmatchnet_b200.ops) against the oracle
+and against the golden fixtures the unmodified reference produced.  Needs a GPU: run with -m gpu.
+
+Tolerances.  north_star: final depth maps within 1e-3 relative L1 (sum|a-b|/sum|b|).  The kernels
+are fp32 with a different (but equally valid) summation order than ATen, so op-level results agree
+to ~1e-6 relative; the tests assert far tighter than the north_star bound:
+    per-op tensors      max-abs <= 2e-5 * scale
+    depth maps          rel-L1  <= 1e-4   (north_star allows 1e-3)
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pm_oracle
+from patchmatchnet_b200 import PatchMatch, PatchmatchNet, load_reference_state, ops, synthetic
+from tests import pm_cases
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+DEPTH_TOL = 1e-4
+
+
+def maxabs(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# small helpers
+# ------------------------------------------------------------------------------------------------
+
+
+def test_library_loaded_and_no_cpu_fallback():
+    from patchmatchnet_b200 import _native
+
+    assert _native.lib().pmb200_abi_version() == 1
+    mod = PatchMatch(**pm_cases.stage_ctor_kwargs(1)).eval()
+    case = pm_cases.make_stage_inputs(pm_cases.STAGE_CASES["stage1_small"])
+    kw = {k: case[k] for k in ("ref_feature", "src_features", "ref_proj", "src_projs", "depth_min", "depth_max", "depth", "view_weights")}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        with torch.no_grad():
+            mod(**kw)
+
+
+def test_relative_projection_matches_inverse():
+    Kc, Ec = synthetic.make_cameras(3, 5, 512, 640)
+    ref_proj, src_projs = synthetic.stage_projections(Kc, Ec, 2)  # unbind views: batch stride 5*16
+    got = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs]).cpu()
+    ref64 = ref_proj.double()
+    for v, sp in enumerate(src_projs):
+        rel = sp.double() @ torch.linalg.inv(ref64)
+        want = torch.cat([rel[:, :3, :3].reshape(3, 9), rel[:, :3, 3]], dim=1)
+        assert maxabs(got[v], want) <= 1e-6 * float(want.abs().max())
+    # strided inputs straight from torch.unbind on the device
+    proj = torch.stack([ref_proj] + src_projs, dim=1).to(DEV)  # [B,N,4,4]
+    mats = torch.unbind(proj, 1)
+    got2 = ops.relative_projection(mats[0], list(mats[1:])).cpu()
+    assert torch.equal(got, got2)
+
+
+def test_pack_nhwc():
+    maps = [torch.randn(2, 24, 7, 9, device=DEV) for _ in range(3)]
+    got = ops.pack_nhwc(maps)
+    for i, m in enumerate(maps):
+        assert torch.equal(got[i], m.permute(0, 2, 3, 1))
+    # channels-last slices of one stacked tensor are used in place (no copy)
+    stacked = torch.randn(6, 16, 5, 8, device=DEV).contiguous(memory_format=torch.channels_last)
+    views = [stacked[0:2], stacked[2:4], stacked[4:6]]
+    packed = ops.pack_nhwc(views)
+    assert packed.data_ptr() == stacked.data_ptr()
+    for i, m in enumerate(views):
+        assert torch.equal(packed[i], m.permute(0, 2, 3, 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# K-A
+# ------------------------------------------------------------------------------------------------
+
+
+def _warp_case(B, V, C, H, W, D, Hs=None, Ws=None, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    Hs, Ws = Hs or H, Ws or W
+    ref = torch.randn(B, C, H, W, generator=g)
+    srcs = [torch.randn(B, C, Hs, Ws, generator=g) for _ in range(V)]
+    Kc, Ec = synthetic.make_cameras(B, V + 1, H * 8, W * 8)
+    ref_proj, src_projs = synthetic.stage_projections(Kc, Ec, 3)
+    depth = 350.0 + 700.0 * torch.rand(B, D, H, W, generator=g)
+    depth = torch.sort(depth, dim=1)[0]
+    depth[:, 0, : max(1, H // 4)] = -20.0  # some points behind the camera -> must contribute exactly 0
+    vw = torch.rand(B, V, H, W, generator=g)
+    return ref, srcs, ref_proj.contiguous(), [m.contiguous() for m in src_projs], depth, vw
+
+
+def _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G):
+    return torch.stack(
+        [pm_oracle.groupwise_correlation(pm_oracle.homography_warp(s, sp, ref_proj, depth), ref, G) for s, sp in zip(srcs, src_projs)]
+    )
+
+
+@pytest.mark.parametrize(
+    "C,G,H,W,D,B,V",
+    [
+        (64, 8, 13, 21, 64, 2, 3),  # stage-3 shape class, first iteration
+        (64, 8, 16, 20, 32, 1, 4),
+        (32, 8, 19, 27, 16, 2, 2),  # stage 2
+        (16, 4, 22, 35, 8, 2, 4),  # stage 1
+        (16, 4, 9, 11, 5, 1, 1),  # D not a multiple of the chunk, single view
+        (64, 8, 5, 3, 1, 1, 2),  # single hypothesis, tiny map
+        (24, 3, 10, 12, 7, 2, 2),  # generic (slow-path) kernel
+        (32, 4, 10, 12, 9, 1, 2),  # generic: 8 channels per group but not an instantiated pair
+    ],
+)
+def test_warp_corr_matches_oracle(C, G, H, W, D, B, V):
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=C + D)
+    want = _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G)  # [V,B,G,D,H,W]
+    rt = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs])
+    ref_n = nhwc(ref.to(DEV))
+    src_n = torch.stack([nhwc(s.to(DEV)) for s in srcs])
+    got = ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G)
+    scale = float(want.abs().max())
+    assert maxabs(got, want) <= 2e-5 * max(1.0, scale)
+    behind = depth[:, 0, : max(1, H // 4)] < 0
+    assert behind.all() and float(got[:, :, :, 0, : max(1, H // 4)].abs().max()) == 0.0
+    # fused view-weighted aggregation (reference patchmatch.py:192-217)
+    wsum = 1e-5 + vw.sum(1)  # [B,H,W]
+    want_f = (want * vw.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / wsum[:, None, None]
+    got_f = ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV))
+    assert maxabs(got_f, want_f) <= 2e-5 * max(1.0, scale)
+    got_a = ops.aggregate_views(got, vw.to(DEV))
+    assert maxabs(got_a, want_f) <= 2e-5 * max(1.0, scale)
+
+
+def test_warp_corr_source_map_of_other_size():
+    C, G, H, W, D, B, V = 32, 8, 12, 20, 8, 1, 2
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, Hs=9, Ws=14, seed=5)
+    want = _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G)
+    rt = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs])
+    got = ops.warp_corr(nhwc(ref.to(DEV)), torch.stack([nhwc(s.to(DEV)) for s in srcs]), rt, depth.to(DEV), G)
+    assert maxabs(got, want) <= 5e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_warp_corr_rejects_bad_arguments():
+    ref = torch.zeros(1, 4, 4, 16, device=DEV)
+    src = torch.zeros(2, 1, 4, 4, 16, device=DEV)
+    rt = torch.zeros(2, 1, 12, device=DEV)
+    depth = torch.ones(1, 3, 4, 4, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.warp_corr(ref, src, rt, depth, 5)  # 16 % 5 != 0 -> PMB200_EINVAL
+    with pytest.raises(RuntimeError):
+        ops.warp_corr(ref.cpu(), src, rt, depth, 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# K-A'
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("C,G,K,dil,H,W,B", [(64, 8, 9, 2, 13, 21, 2), (32, 8, 9, 4, 19, 27, 1), (16, 4, 9, 6, 22, 35, 2),
+                                             (16, 4, 17, 4, 12, 18, 1), (24, 3, 9, 2, 8, 9, 1)])
+def test_offset_corr_matches_oracle(C, G, K, dil, H, W, B):
+    g = torch.Generator().manual_seed(K + C)
+    ref = torch.randn(B, C, H, W, generator=g)
+    off = torch.randn(B, 2 * K, H, W, generator=g) * 2.5
+    grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("evaluation", K, dil), off.view(B, 2 * K, H * W), H, W)
+    head = pm_oracle._FeatureWeightHead(K, G)
+    want = head.neighbour_correlation(ref, grid)  # [B,G,K,H,W]
+    got = ops.offset_corr(nhwc(ref.to(DEV)), off.to(DEV), G, K, dil)
+    assert maxabs(got, want) <= 2e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_unsupported_neighbour_counts_raise_not_implemented():
+    ref = torch.zeros(1, 4, 4, 16, device=DEV)
+    with pytest.raises(NotImplementedError):
+        ops.offset_corr(ref, torch.zeros(1, 20, 4, 4, device=DEV), 4, 10, 2)
+    with pytest.raises(NotImplementedError):
+        ops.init_propagate(torch.ones(1, 1, 4, 4, device=DEV), torch.zeros(1, 10, 4, 4, device=DEV),
+                           torch.tensor([1.0], device=DEV), torch.tensor([2.0], device=DEV), ops.MODE_PERTURB, 8, 5, 2, 0.1)
+    case = pm_cases.make_stage_inputs(pm_cases.STAGE_CASES["stage3_small"])
+    kw = {k: case[k] for k in ("ref_feature", "src_features", "ref_proj", "src_projs", "depth_min", "depth_max", "depth", "view_weights")}
+    for bad in (dict(propagate_neighbors=5), dict(evaluate_neighbors=10)):
+        with pytest.raises(NotImplementedError):  # reference patchmatch.py:359-360 / :391-392
+            PatchMatch(**bad)(**kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# K-C
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize(
+    "mode,Ns,Kp,dil,H,W,B",
+    [
+        ("random", 48, 16, 2, 13, 21, 2),
+        ("random", 48, 0, 2, 8, 10, 1),
+        ("perturb", 16, 16, 2, 13, 21, 2),
+        ("perturb", 8, 8, 4, 19, 27, 2),
+        ("perturb", 8, 4, 4, 9, 11, 1),
+        ("perturb", 8, 0, 6, 22, 35, 2),
+        ("perturb", 3, 8, 2, 9, 10, 1),  # odd sample count
+        ("perturb", 100, 16, 2, 6, 7, 1),  # > 64 hypotheses: generic path
+        ("pass", 1, 8, 2, 9, 10, 1),
+    ],
+)
+def test_init_propagate_matches_oracle(mode, Ns, Kp, dil, H, W, B):
+    g = torch.Generator().manual_seed(Ns + Kp + H)
+    dmin = torch.full((B,), 425.0) + torch.arange(B) * 3.0
+    dmax = torch.full((B,), 935.0) - torch.arange(B) * 4.0
+    scale = 0.025
+    if mode == "random":
+        u = torch.rand(B, 48, H, W, generator=g)
+        init = pm_oracle.init_hypotheses(dmin, dmax, H, W, scale, 16, torch.empty(0), u.device, lambda size, device: u)
+        seed, m = u, ops.MODE_RANDOM
+    else:
+        depth = 400.0 + 560.0 * torch.rand(B, 1, H, W, generator=g)  # partly outside [dmin,dmax]: exercises the clamp
+        init = pm_oracle.init_hypotheses(dmin, dmax, H, W, scale, Ns, depth, depth.device)
+        seed, m = depth, (ops.MODE_PERTURB if mode == "perturb" else ops.MODE_PASSTHROUGH)
+    off = None
+    want = init
+    if Kp > 0:
+        off = torch.randn(B, 2 * Kp, H, W, generator=g) * 2.0
+        grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("propagation", Kp, dil), off.view(B, 2 * Kp, H * W), H, W)
+        want = pm_oracle.propagate(init, grid)
+    got = ops.init_propagate(seed.to(DEV), None if off is None else off.to(DEV), dmin.to(DEV), dmax.to(DEV), m, Ns, Kp, dil, scale)
+    assert got.shape == want.shape
+    assert pm_cases.rel_l1(got, want) <= 1e-6
+    assert maxabs(got, want) <= 2e-3  # depths are ~400..1000: a few fp32 ulps
+    if Kp > 0:
+        assert bool((got[:, 1:] >= got[:, :-1]).all())  # sorted ascending
+
+
+# ------------------------------------------------------------------------------------------------
+# K-B
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("D,K,dil,H,W,B,inverse", [(64, 9, 2, 13, 21, 2, False), (16, 9, 4, 19, 27, 1, False),
+                                                   (8, 9, 6, 22, 35, 2, True), (8, 17, 4, 40, 64, 5, False), (5, 9, 2, 9, 9, 1, True)])
+def test_adaptive_eval_matches_oracle(D, K, dil, H, W, B, inverse):
+    g = torch.Generator().manual_seed(D + K)
+    dmin = torch.full((B,), 425.0)
+    dmax = torch.full((B,), 935.0)
+    scale = 0.0125
+    depth = 430.0 + 500.0 * torch.rand(B, D, H, W, generator=g)
+    depth = torch.sort(depth, dim=1, descending=inverse)[0]
+    score0 = torch.randn(B, D, H, W, generator=g) * 2.0
+    off = torch.randn(B, 2 * K, H, W, generator=g) * 1.5
+    fw = torch.rand(B, K, H, W, generator=g) + 0.05
+    grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("evaluation", K, dil), off.view(B, 2 * K, H * W), H, W)
+    w = pm_oracle.depth_similarity_weight(depth, dmin, dmax, grid, scale, K) * fw.unsqueeze(1)
+    w = w / torch.sum(w, dim=2).unsqueeze(2)
+    s = torch.sum(pm_oracle._border_sample(score0, grid).view(B, D, K, H, W) * w, dim=2)
+    want_prob = torch.exp(F.log_softmax(s, dim=1))
+    want_depth = pm_oracle._Evaluation.regress(depth, want_prob, inverse)
+    got_depth, got_prob = ops.adaptive_eval(score0.to(DEV), depth.to(DEV), off.to(DEV), fw.to(DEV), dmin.to(DEV), dmax.to(DEV), dil, scale, inverse)
+    assert maxabs(got_prob, want_prob) <= 5e-6
+    assert pm_cases.rel_l1(got_depth, want_depth) <= 1e-6
+    assert maxabs(got_prob.sum(1), torch.ones(B, H, W)) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# whole stages and the whole network against what the unmodified reference produced
+# ------------------------------------------------------------------------------------------------
+
+
+def _stage_module(weights, stage):
+    mod = PatchMatch(**pm_cases.stage_ctor_kwargs(stage))
+    missing, unexpected = mod.load_state_dict(pm_cases.stage_state(weights, stage), strict=True)
+    assert not missing and not unexpected
+    return mod.eval().to(DEV)
+
+
+def _run_stage(weights, spec):
+    case = pm_cases.make_stage_inputs(spec)
+    mod = _stage_module(weights, spec["stage"])
+    if case["rand48"] is not None:
+        mod.rand_source = lambda size, device: case["rand48"].to(device)
+    kw = dict(
+        ref_feature=case["ref_feature"].to(DEV), src_features=[s.to(DEV) for s in case["src_features"]],
+        ref_proj=case["ref_proj"].to(DEV), src_projs=[m.to(DEV) for m in case["src_projs"]],
+        depth_min=case["depth_min"].to(DEV), depth_max=case["depth_max"].to(DEV),
+        depth=case["depth"].to(DEV), view_weights=case["view_weights"].to(DEV),
+    )
+    with torch.no_grad():
+        return case, mod(**kw)
+
+
+@pytest.mark.parametrize("name", list(pm_cases.STAGE_CASES))
+def test_stage_matches_reference_golden(golden_weights, golden_stage_cases, name):
+    gold = golden_stage_cases[name]
+    case, (depths, score, vw) = _run_stage(golden_weights, pm_cases.STAGE_CASES[name])
+    assert pm_cases.checksum(case) == gold["checksum"]
+    assert len(depths) == len(gold["depths"])
+    for x, y in zip(depths, gold["depths"]):
+        assert x.shape == y.shape
+        assert pm_cases.rel_l1(x, y) <= DEPTH_TOL
+    assert score.shape == gold["score"].shape and maxabs(score, gold["score"]) <= 2e-3
+    assert vw.shape == gold["view_weights"].shape and maxabs(vw, gold["view_weights"]) <= 1e-4
+    assert not vw.requires_grad
+
+
+def test_config1_matches_reference_golden(golden_weights, golden_config1):
+    """BASELINE.json configs[0]: 1 ref + 2 src, 160x128 image, single stage, 8 hypotheses."""
+    case, (depths, score, _) = _run_stage(golden_weights, pm_cases.CONFIG1)
+    assert pm_cases.checksum(case) == golden_config1["checksum"]
+    assert pm_cases.rel_l1(depths[-1], golden_config1["depths"][-1]) <= DEPTH_TOL
+    assert maxabs(score, golden_config1["score"]) <= 2e-3
+
+
+def _net(weights, cls=None):
+    net = PatchmatchNet(**pm_cases.NET_KWARGS) if cls is None else PatchmatchNet(**pm_cases.NET_KWARGS, patchmatch_cls=cls)
+    load_reference_state(net, weights)
+    return net.eval().to(DEV)
+
+
+def test_network_matches_reference_golden(golden_weights, golden_net_case):
+    torch.backends.cudnn.allow_tf32 = False  # library convs in full fp32 for the parity run
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = _net(golden_weights)
+    inp = pm_cases.make_net_inputs(pm_cases.NET_CASE)
+    assert pm_cases.checksum(inp) == golden_net_case["checksum"]
+    net.patchmatch_3.rand_source = lambda size, device: inp["rand48"].to(device)
+    with torch.no_grad():
+        depth, conf, per_stage = net(
+            [i.to(DEV) for i in inp["images"]], inp["intrinsics"].to(DEV), inp["extrinsics"].to(DEV),
+            inp["depth_min"].to(DEV), inp["depth_max"].to(DEV),
+        )
+    assert pm_cases.rel_l1(depth, golden_net_case["depth"]) <= DEPTH_TOL
+    for s, ds in golden_net_case["per_stage"].items():
+        for x, y in zip(per_stage[s], ds):
+            assert pm_cases.rel_l1(x, y) <= DEPTH_TOL
+    assert maxabs(conf, golden_net_case["confidence"]) <= 5e-2  # gather at a rounded index: a few pixels may flip bins
+    assert float((conf.cpu() - golden_net_case["confidence"]).abs().mean()) <= 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,n_views", [(1, 512, 640, 5), (2, 256, 320, 3)])
+def test_network_full_size_vs_oracle_on_gpu(golden_weights, B, H, W, n_views):
+    """BASELINE.json configs[1] shape (1 ref + 4 src, 640x512, 64/32/16/16/8 hypotheses): the CUDA path
+    against the oracle run on the same device with the same generator state, plus size-independent
+    properties (probabilities sum to 1, depth inside the range, determinism)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    inp = synthetic.make_inputs(B, n_views, H, W, seed=7)
+    args = lambda: ([i.to(DEV) for i in inp["images"]], inp["intrinsics"].to(DEV), inp["extrinsics"].to(DEV),
+                    inp["depth_min"].to(DEV), inp["depth_max"].to(DEV))
+    mine = _net(golden_weights)
+    orc = _net(golden_weights, pm_oracle.PatchMatchOracle)
+    with torch.no_grad():
+        torch.manual_seed(99)
+        d1, c1, ps1 = mine(*args())
+        torch.manual_seed(99)
+        d2, c2, ps2 = orc(*args())
+        torch.manual_seed(99)
+        d3, _, _ = mine(*args())
+    assert torch.equal(d1, d3), "the CUDA path must be deterministic"
+    assert pm_cases.rel_l1(d1, d2) <= DEPTH_TOL
+    for s in (3, 2, 1):
+        for x, y in zip(ps1[s], ps2[s]):
+            assert pm_cases.rel_l1(x, y) <= DEPTH_TOL
+            assert float(x.min()) >= synthetic.DEPTH_MIN * (1 - 1e-4) and float(x.max()) <= synthetic.DEPTH_MAX * (1 + 1e-4)
+    assert torch.isfinite(d1).all() and torch.isfinite(c1).all()
+
+
+def test_cuda_graph_replay_equals_eager(golden_weights):
+    """The whole stage is capturable: no host sync, no allocation surprises."""
+    spec = pm_cases.STAGE_CASES["stage2_small"]
+    case = pm_cases.make_stage_inputs(spec)
+    mod = _stage_module(golden_weights, 2)
+    kw = dict(
+        ref_feature=case["ref_feature"].to(DEV), src_features=[s.to(DEV) for s in case["src_features"]],
+        ref_proj=case["ref_proj"].to(DEV), src_projs=[m.to(DEV) for m in case["src_projs"]],
+        depth_min=case["depth_min"].to(DEV), depth_max=case["depth_max"].to(DEV),
+        depth=case["depth"].to(DEV), view_weights=case["view_weights"].to(DEV),
+    )
+    with torch.no_grad():
+        eager = mod(**kw)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                mod(**kw)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = mod(**kw)
+        graph.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out[0][-1], eager[0][-1]) and torch.equal(out[1], eager[1])
