@@ -123,10 +123,13 @@ class ClockSampler:
 
 
 def cpu_forward_timer(height: int, width: int, n_views: int):
+    """The oracle port of the reference on the host CPU.  torch's default is one thread per core; on a
+    many-core host the small ops of this network get SLOWER with every core added, so the thread count is
+    calibrated first (one forward per candidate, ascending, stop when it stops paying) and the reference is
+    given its best configuration."""
     from oracle.pm_oracle import PatchMatchOracle  # allowed here: cpu_baseline / --impl reference legs only
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     net, _ = build_net(PatchMatchOracle)
     net.stack_views = False  # the reference runs FeatureNet view by view (net.py:203-208)
     inp = synthetic.make_inputs(1, n_views, height, width, seed=0)
@@ -137,7 +140,20 @@ def cpu_forward_timer(height: int, width: int, n_views: int):
             net([i.clone() for i in inp["images"]], inp["intrinsics"].clone(), inp["extrinsics"].clone(), inp["depth_min"], inp["depth_max"])
             return time.perf_counter() - t0
 
-    return step, torch.get_num_threads()
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    best_t, best_c, tried = None, cands[0], {}
+    for c in cands:
+        torch.set_num_threads(c)
+        step()  # warm-up at this thread count
+        t = step()
+        tried[c] = round(t, 3)
+        if best_t is None or t < best_t:
+            best_t, best_c = t, c
+        elif t > 1.5 * best_t:
+            break
+    torch.set_num_threads(best_c)
+    step.calibration = tried
+    return step, best_c
 
 
 def run_reference_arm(args) -> None:
@@ -150,7 +166,8 @@ def run_reference_arm(args) -> None:
     times = [step() for _ in range(args.steps)]
     total = sum(times)
     value = args.steps / total
-    sample = f"{args.steps} full forwards of the workload (1 depth map each) after {args.warmup} warm-up, {cores} torch threads"
+    sample = (f"{args.steps} full forwards of the workload (1 depth map each) after {args.warmup} warm-up, {cores} torch threads "
+              f"(best of calibration {step.calibration}, host has {os.cpu_count()} cores)")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -173,7 +190,8 @@ def run_reference_arm(args) -> None:
 class LaunchCounter:
     """Counts native (libpmb200.so) kernel launches issued through patchmatchnet_b200.ops."""
 
-    NAMES = ("relative_projection", "pack_nhwc", "warp_corr", "aggregate_views", "offset_corr", "init_propagate", "adaptive_eval")
+    NAMES = ("relative_projection", "pack_nhwc", "warp_corr", "aggregate_views", "offset_corr", "init_propagate", "adaptive_eval",
+             "warp_corr_score", "warp_corr_view_weights", "offset_corr_weight")
 
     def __init__(self):
         from patchmatchnet_b200 import _native
@@ -213,45 +231,56 @@ def warp_corr_minimum_bytes(V, B, C, G, H, W, D):
 
 def time_warp_corr_calls(net, dev_inputs, peak_gbs, flush, iters=20):
     """Re-run every fused warp+correlation launch of one forward in isolation, L2 flushed before each,
-    CUDA events on the launching (current) stream."""
+    CUDA events on the launching (current) stream.  Covers the three entry points that run the K-A core:
+    warp_corr (similarities out), warp_corr_score (SimilarityNet head fused), warp_corr_view_weights
+    (PixelwiseNet fused)."""
     from patchmatchnet_b200 import ops
 
     calls = []
-    orig = ops.warp_corr
+    names = ("warp_corr", "warp_corr_score", "warp_corr_view_weights")
+    origs = {n: getattr(ops, n) for n in names}
 
-    def spy(ref, src, rt, depth, G, vw=None):
-        calls.append((ref, src, rt, depth, G, vw))
-        return orig(ref, src, rt, depth, G, vw)
+    def make_spy(n):
+        def spy(*a, **k):
+            calls.append((n, a, k))
+            return origs[n](*a, **k)
+        return spy
 
-    ops.warp_corr = spy
+    for n in names:
+        setattr(ops, n, make_spy(n))
     try:
         with torch.no_grad():
             torch.manual_seed(0)
             net(*dev_inputs())
     finally:
-        ops.warp_corr = orig
+        for n in names:
+            setattr(ops, n, origs[n])
     torch.cuda.synchronize()
     rows = []
-    for (ref, src, rt, depth, G, vw) in calls:
+    for (n, a, k) in calls:
+        ref, src, depth, G = a[0], a[1], a[3], a[4]
         B, H, W, C = ref.shape
         V, D = src.shape[0], depth.shape[1]
+        fn = origs[n]
         for _ in range(3):
-            orig(ref, src, rt, depth, G, vw)
+            fn(*a, **k)
         ts = []
         for _ in range(iters):
             flush()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            orig(ref, src, rt, depth, G, vw)
-            b.record()
-            b.synchronize()
-            ts.append(a.elapsed_time(b) * 1e-3)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*a, **k)
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
         t = statistics.mean(ts)
         alg = warp_corr_algorithmic_bytes(V, B, C, G, H, W, D)
+        out_floats = {"warp_corr": G * D * (V if (len(a) < 6 or a[5] is None) and "view_weights" not in k else 1),
+                      "warp_corr_score": D, "warp_corr_view_weights": V}[n]
         rows.append({
-            "shape": f"C{C} G{G} D{D} {H}x{W} V{V} B{B}" + ("" if vw is not None else " per-view"),
+            "entry": n, "shape": f"C{C} G{G} D{D} {H}x{W} V{V} B{B}",
             "us": 1e6 * t, "us_min": 1e6 * min(ts), "algorithmic_bytes": alg,
-            "minimum_bytes": warp_corr_minimum_bytes(V, B, C, G, H, W, D),
+            "minimum_bytes": 4 * B * H * W * (C * (1 + V) + D + V + out_floats),
             "achieved_gbs": alg / t / 1e9, "frac": alg / t / 1e9 / peak_gbs,
         })
     return rows
@@ -284,6 +313,7 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True  # as the reference's eval.py:301 does; autotuned during warm-up
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -391,7 +421,7 @@ def main() -> None:
                 except Exception:
                     traffic = None
             roofline = {"bound": "hbm", "kernel": "warp_corr_kernel (fused warp+bilinear gather+group correlation+view aggregation)",
-                        "launch": top["shape"], "achieved": top["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+                        "launch": top["entry"] + " " + top["shape"], "achieved": top["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
                         "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
                         "us_per_launch": top["us"],
                         "all_launches_weighted_frac": sum(r["algorithmic_bytes"] for r in detail) / sum(r["us"] * 1e-6 for r in detail) / 1e9 / peak_gbs}
@@ -400,7 +430,8 @@ def main() -> None:
             step()
             ts = [step() for _ in range(args.cpu_samples)]
             cpu_baseline = {"value": len(ts) / sum(ts), "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{len(ts)} full forwards of the same workload (after 1 warm-up) with the oracle port of the reference, {cores} torch threads"}
+                            "sample": f"{len(ts)} full forwards of the same workload (after 1 warm-up) with the oracle port of the reference, "
+                                      f"{cores} torch threads (best of calibration {step.calibration}, host has {os.cpu_count()} cores)"}
 
     if rank == 0:
         line = {

@@ -110,6 +110,46 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out,
                        int B, int C, int G, int H, int W, int K, int dilation, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Eval-mode fusion of the learned 1x1x1 heads (SURVEY.md 8f "f2").
+ * A head is conv3d(G->16) + BN + ReLU, conv3d(16->8) + BN + ReLU, conv3d(8->1) + bias
+ * (ConvBnReLU3D, models/module.py:43-72).  With BatchNorm in eval mode the BN folds into the
+ * conv; the caller passes the folded weights (HOST pointer, copied into the kernel parameter
+ * block, i.e. constant memory) and the kernels apply the head in their epilogue, so the
+ * [B,G,D,H,W] similarity tensor (62-73 % of K-A's bytes) is never written.
+ * Inference only: training-mode BatchNorm needs batch statistics and keeps the unfused path.
+ */
+typedef struct pmb200_mlp {
+    float w0[16 * 8]; /* [16][G], rows padded to 8 inputs */
+    float b0[16];
+    float w1[8 * 16]; /* [8][16] */
+    float b1[8];
+    float w2[8];
+    float b2;
+} pmb200_mlp;
+
+/* K-A + SimilarityNet head (models/patchmatch.py:547-549,570): weighted view average -> MLP.
+ *   score_out [B,D,H,W];  view_weights [B,V,H,W] required.  (C,G) in {(64,8),(32,8),(16,4)}. */
+int pmb200_warp_corr_score(const float *ref_nhwc, const float *src_nhwc, const float *rt,
+                           const float *depth, const float *view_weights,
+                           const pmb200_mlp *head_host, float *score_out,
+                           int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D,
+                           void *stream);
+
+/* K-A + PixelwiseNet (models/patchmatch.py:690-702): per view, max over hypotheses of
+ * sigmoid(MLP(similarity)).  view_weights_out [B,V,H,W] (zeroed by the call, then atomic max). */
+int pmb200_warp_corr_view_weights(const float *ref_nhwc, const float *src_nhwc, const float *rt,
+                                  const float *depth, const pmb200_mlp *head_host,
+                                  float *view_weights_out,
+                                  int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D,
+                                  void *stream);
+
+/* K-A' + FeatureWeightNet head (models/patchmatch.py:597-601,624): sigmoid(MLP(correlation)).
+ *   weight_out [B,K,H,W] */
+int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets,
+                              const pmb200_mlp *head_host, float *weight_out,
+                              int B, int C, int G, int H, int W, int K, int dilation, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * K-C: hypothesis initialisation + adaptive propagation + sort, one launch.
  * Replaces DepthInitialization.forward (models/patchmatch.py:53-94),
  * PatchMatch.get_grid(propagation) (:331-360,:396-426) and Propagation.forward (:115-124).
@@ -120,10 +160,12 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out,
  *   mode 2  passthrough : Ns == 1, hypotheses = current depth
  *   offsets [B,2Kp,H,W] raw output of propa_conv, Kp in {0,4,8,16}; with Kp == 0 nothing is
  *           propagated and the samples keep initialisation order (no sort), as in the reference.
- *   out     [B,Ns+Kp,H,W]  (ascending along dim 1 when Kp > 0)
+ *   out       [B,Ns+Kp,H,W]  (ascending along dim 1 when Kp > 0)
+ *   xnorm_out [B,Ns+Kp,H,W] or NULL: (1/out - 1/dmax) / (1/dmin - 1/dmax), the normalised inverse
+ *             depth that depth_weight gathers (models/patchmatch.py:655-657), for pmb200_adaptive_eval
  */
 int pmb200_init_propagate(const float *seed_map, const float *offsets,
-                          const float *depth_min, const float *depth_max, float *out,
+                          const float *depth_min, const float *depth_max, float *out, float *xnorm_out,
                           int mode, int B, int H, int W, int Ns, int Kp, int dilation,
                           float interval_scale, void *stream);
 
@@ -134,12 +176,15 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets,
  * softmax (:221) and depth regression (:226-237).
  *   score0          [B,D,H,W] per-hypothesis score from the 1x1x1 MLP
  *   depth_sample    [B,D,H,W]
+ *   xnorm           [B,D,H,W] normalised inverse depth from pmb200_init_propagate, or NULL
+ *                   (then it is recomputed from depth_sample at every tap: same result, slower)
  *   offsets         [B,2K,H,W] raw output of eval_conv
  *   feature_weight  [B,K,H,W]
  *   prob_out        [B,D,H,W]   depth_out [B,H,W]
  *   is_inverse      stage-1 last-iteration inverse-depth index regression (:227-234)
  */
-int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *offsets,
+int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *xnorm,
+                         const float *offsets,
                          const float *feature_weight, const float *depth_min, const float *depth_max,
                          float *prob_out, float *depth_out,
                          int B, int D, int H, int W, int K, int dilation,

@@ -67,6 +67,22 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 _PF = POINTER(c_float)
 _PPF = POINTER(c_void_p)
 
+
+class MlpStruct(ctypes.Structure):
+    """pmb200_mlp (include/patchmatch_b200.h): folded G->16->8->1 head, host memory."""
+
+    _fields_ = [
+        ("w0", c_float * (16 * 8)),
+        ("b0", c_float * 16),
+        ("w1", c_float * (8 * 16)),
+        ("b1", c_float * 8),
+        ("w2", c_float * 8),
+        ("b2", c_float),
+    ]
+
+
+_PMLP = POINTER(MlpStruct)
+
 _SIGNATURES = {
     "pmb200_abi_version": (c_int, []),
     "pmb200_last_error": (c_char_p, []),
@@ -75,8 +91,11 @@ _SIGNATURES = {
     "pmb200_warp_corr": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
     "pmb200_aggregate_views": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "pmb200_offset_corr": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
-    "pmb200_init_propagate": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
-    "pmb200_adaptive_eval": (c_int, [c_void_p] * 8 + [c_int] * 6 + [c_float, c_int, c_void_p]),
+    "pmb200_warp_corr_score": (c_int, [c_void_p] * 5 + [_PMLP, c_void_p] + [c_int] * 9 + [c_void_p]),
+    "pmb200_warp_corr_view_weights": (c_int, [c_void_p] * 4 + [_PMLP, c_void_p] + [c_int] * 9 + [c_void_p]),
+    "pmb200_offset_corr_weight": (c_int, [c_void_p] * 2 + [_PMLP, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "pmb200_init_propagate": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_float, c_void_p]),
+    "pmb200_adaptive_eval": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -103,6 +103,39 @@ __device__ __forceinline__ void load_reference(const float *__restrict__ ref_nhw
     r[4] = q1.x * s; r[5] = q1.y * s; r[6] = q1.z * s; r[7] = q1.w * s;
 }
 
+// Folded (conv3d 1x1x1 + eval-mode BatchNorm) weights of one G -> 16 -> 8 -> 1 head.  Passed by value
+// inside the kernel parameter block, i.e. it lives in the constant bank and every FMA of the epilogue
+// MLP takes its weight as a constant operand (no load instruction).
+struct MlpParams {
+    float w0[16 * 8];  // [16][G padded to 8]
+    float b0[16];
+    float w1[8 * 16];
+    float b1[8];
+    float w2[8];
+    float b2;
+};
+
+template <int G>
+__device__ __forceinline__ float mlp_eval(const MlpParams &m, const float (&x)[G]) {
+    float h0[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float a = m.b0[j];
+#pragma unroll
+        for (int g = 0; g < G; ++g) a = fmaf(m.w0[j * 8 + g], x[g], a);
+        h0[j] = fmaxf(a, 0.0f);
+    }
+    float y = m.b2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float a = m.b1[i];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a = fmaf(m.w1[i * 16 + j], h0[j], a);
+        y = fmaf(m.w2[i], fmaxf(a, 0.0f), y);
+    }
+    return y;
+}
+
 struct WarpCorrParams {
     const float *ref, *src, *rt, *depth, *vw;
     float *out;
@@ -110,11 +143,22 @@ struct WarpCorrParams {
     float sx, sy;
 };
 
-template <int C, int G, bool FUSED>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const WarpCorrParams p) {
+// Epilogue of the fused warp+correlation kernel
+constexpr int kEpiSims = 0;    // per-view similarities                 out [V,B,G,D,H,W]
+constexpr int kEpiAgg = 1;     // view-weighted average                 out [B,G,D,H,W]
+constexpr int kEpiScore = 2;   // view-weighted average -> MLP          out [B,D,H,W]      (SimilarityNet head, eval mode)
+constexpr int kEpiViewW = 3;   // per-view -> MLP -> max_d -> sigmoid   out [B,V,H,W]      (PixelwiseNet, eval mode)
+
+template <int C, int G, int EPI>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const WarpCorrParams p, const MlpParams mlp) {
     using M = LaneMap<C, G>;
+    constexpr bool kWeighted = (EPI == kEpiAgg || EPI == kEpiScore);
+    constexpr bool kHead = (EPI == kEpiScore || EPI == kEpiViewW);
     __shared__ float4 s_w[kWarpsPerBlock][M::EPW];
     __shared__ int s_key[kWarpsPerBlock][M::EPW];
+    // group values of one warp pass, [hypothesis][pixel][group]: the transpose that brings the G
+    // groups of one (pixel, hypothesis) into one thread for the MLP epilogue
+    __shared__ float s_sim[kHead ? kWarpsPerBlock : 1][kHead ? M::EPW * G : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int HW = p.H * p.W;
@@ -163,7 +207,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const Wa
         __syncwarp();
 
         float wv = 1.0f;
-        if (FUSED) {
+        if (kWeighted) {
             wv = __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc);
             wsum += wv;
         }
@@ -193,26 +237,68 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const Wa
                 for (int g = 0; g < M::GPL; ++g)
                     sim[g] = w.x * T[0][g] + w.y * T[1][g] + w.z * T[2][g] + w.w * T[3][g];
             }
-            if (FUSED) {
+            if (kWeighted) {
 #pragma unroll
                 for (int g = 0; g < M::GPL; ++g) acc[dj][g] = fmaf(sim[g], wv, acc[dj][g]);
-            } else if (live && d0 + dj < p.D) {
+            } else if (EPI == kEpiSims) {
+                if (live && d0 + dj < p.D) {
 #pragma unroll
-                for (int g = 0; g < M::GPL; ++g)
-                    p.out[((((size_t)v * p.B + b) * G + g0 + g) * p.D + d0 + dj) * HW + n] = sim[g];
+                    for (int g = 0; g < M::GPL; ++g)
+                        p.out[((((size_t)v * p.B + b) * G + g0 + g) * p.D + d0 + dj) * HW + n] = sim[g];
+                }
+            } else {  // kEpiViewW: stage the per-view similarity for the head
+#pragma unroll
+                for (int g = 0; g < M::GPL; ++g) s_sim[warp][(dj * M::PPW + pi) * G + g0 + g] = sim[g];
             }
         }
-        __syncwarp();  // the next view overwrites this warp's footprints
+        __syncwarp();  // footprints consumed / similarities staged
+
+        if (EPI == kEpiViewW) {
+            // PixelwiseNet (reference models/patchmatch.py:702): sigmoid(MLP(sim)) maximised over hypotheses.
+            // sigmoid is monotonic, so max first, one sigmoid per pixel, then an atomic max across chunks.
+            float best = -INFINITY;
+            for (int e = lane; e < M::EPW; e += 32) {
+                float x[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) x[g] = s_sim[warp][e * G + g];
+                const float y = mlp_eval<G>(mlp, x);
+                if (d0 + e / M::PPW < p.D) best = fmaxf(best, y);
+            }
+#pragma unroll
+            for (int s = M::PPW; s < 32; s <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, s));
+            const int en = n0 + lane;  // lanes 0..PPW-1 own one pixel each
+            if (lane < M::PPW && en < HW) {
+                const float sg = 1.0f / (1.0f + expf(-best));
+                atomicMax(reinterpret_cast<int *>(p.out + ((size_t)b * p.V + v) * HW + en), __float_as_int(sg));
+            }
+            __syncwarp();
+        }
     }
 
-    if (FUSED && live) {
+    if (EPI == kEpiAgg) {
+        if (live) {
 #pragma unroll
-        for (int dj = 0; dj < kChunk; ++dj) {
-            if (d0 + dj < p.D) {
+            for (int dj = 0; dj < kChunk; ++dj) {
+                if (d0 + dj < p.D) {
 #pragma unroll
-                for (int g = 0; g < M::GPL; ++g)
-                    p.out[(((size_t)b * G + g0 + g) * p.D + d0 + dj) * HW + n] = acc[dj][g] / wsum;
+                    for (int g = 0; g < M::GPL; ++g)
+                        p.out[(((size_t)b * G + g0 + g) * p.D + d0 + dj) * HW + n] = acc[dj][g] / wsum;
+                }
             }
+        }
+    } else if (EPI == kEpiScore) {
+#pragma unroll
+        for (int dj = 0; dj < kChunk; ++dj)
+#pragma unroll
+            for (int g = 0; g < M::GPL; ++g) s_sim[warp][(dj * M::PPW + pi) * G + g0 + g] = acc[dj][g] / wsum;
+        __syncwarp();
+        for (int e = lane; e < M::EPW; e += 32) {
+            float x[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) x[g] = s_sim[warp][e * G + g];
+            const float y = mlp_eval<G>(mlp, x);
+            const int en = n0 + e % M::PPW, ed = d0 + e / M::PPW;
+            if (en < HW && ed < p.D) p.out[((size_t)b * p.D + ed) * HW + en] = y;
         }
     }
 }
@@ -268,11 +354,12 @@ struct OffsetCorrParams {
     int B, H, W, K, dilation;
 };
 
-template <int C, int G>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) offset_corr_kernel(const OffsetCorrParams p) {
+template <int C, int G, bool HEAD>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) offset_corr_kernel(const OffsetCorrParams p, const MlpParams mlp) {
     using M = LaneMap<C, G>;
     __shared__ float4 s_w[kWarpsPerBlock][M::EPW];
     __shared__ int s_key[kWarpsPerBlock][M::EPW];
+    __shared__ float s_sim[HEAD ? kWarpsPerBlock : 1][HEAD ? M::EPW * G : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int HW = p.H * p.W;
@@ -317,16 +404,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) offset_corr_kernel(const 
     for (int kj = 0; kj < kChunk; ++kj) {
         const float4 w = s_w[warp][kj * M::PPW + pi];
         const int key = s_key[warp][kj * M::PPW + pi];
-        if (key == pm::kKeyNone) continue;  // only for k >= K or dead pixels
-        if (key != pkey) {
-            gather_dot<C, G>(sv, key, p.W, r, T);
-            pkey = key;
-        }
-        if (live && k0 + kj < p.K) {
+        float sim[M::GPL];
 #pragma unroll
-            for (int g = 0; g < M::GPL; ++g)
-                p.out[(((size_t)b * G + g0 + g) * p.K + k0 + kj) * HW + n] =
-                    w.x * T[0][g] + w.y * T[1][g] + w.z * T[2][g] + w.w * T[3][g];
+        for (int g = 0; g < M::GPL; ++g) sim[g] = 0.0f;
+        if (key != pm::kKeyNone) {  // none only for k >= K or dead pixels
+            if (key != pkey) {
+                gather_dot<C, G>(sv, key, p.W, r, T);
+                pkey = key;
+            }
+#pragma unroll
+            for (int g = 0; g < M::GPL; ++g) sim[g] = w.x * T[0][g] + w.y * T[1][g] + w.z * T[2][g] + w.w * T[3][g];
+        }
+        if (HEAD) {
+#pragma unroll
+            for (int g = 0; g < M::GPL; ++g) s_sim[warp][(kj * M::PPW + pi) * G + g0 + g] = sim[g];
+        } else if (live && k0 + kj < p.K) {
+#pragma unroll
+            for (int g = 0; g < M::GPL; ++g) p.out[(((size_t)b * G + g0 + g) * p.K + k0 + kj) * HW + n] = sim[g];
+        }
+    }
+    if (HEAD) {  // FeatureWeightNet head (reference models/patchmatch.py:624): sigmoid(MLP(correlation)) -> [B,K,H,W]
+        __syncwarp();
+        for (int e = lane; e < M::EPW; e += 32) {
+            float x[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) x[g] = s_sim[warp][e * G + g];
+            const float y = mlp_eval<G>(mlp, x);
+            const int en = n0 + e % M::PPW, ek = k0 + e / M::PPW;
+            if (en < HW && ek < p.K) p.out[((size_t)b * p.K + ek) * HW + en] = 1.0f / (1.0f + expf(-y));
         }
     }
 }
@@ -460,7 +565,7 @@ __global__ void relative_projection_kernel(const ProjParams p) {
 
 struct PropParams {
     const float *seed, *offsets, *dmin, *dmax;
-    float *out;
+    float *out, *xnorm;
     int mode, B, H, W, Ns, Kp, dilation;
     float interval_scale;
 };
@@ -497,42 +602,77 @@ __device__ __forceinline__ float propagated_hypothesis(const PropParams &p, int 
     return s;
 }
 
+// Sorting version (Kp > 0): min(NPAD,32) lanes per pixel, each lane owns hypothesis slot `lane` (and
+// `lane + 32` when NPAD == 64); the ascending sort over the hypothesis axis is a bitonic network run
+// with warp shuffles, so a 64x80 map is 5120 warps of parallel work instead of 5120 serial threads.
 template <int NPAD>
 __global__ void __launch_bounds__(128) init_propagate_kernel(const PropParams p) {
+    constexpr int LPX = NPAD < 32 ? NPAD : 32;  // lanes per pixel
+    constexpr int PPW = 32 / LPX;               // pixels per warp
+    constexpr int VPL = NPAD / LPX;             // values per lane
+    const int HW = p.H * p.W;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int b = blockIdx.y;
+    const int slot = lane % LPX;
+    const int n = warp * PPW + lane / LPX;
+    const bool live = n < HW;
+    const int nc = live ? n : HW - 1;
+    const float inv_min = 1.0f / __ldg(p.dmin + b), inv_max = 1.0f / __ldg(p.dmax + b);
+    const int D = p.Ns + p.Kp;
+    const float kInf = __int_as_float(0x7f800000);
+
+    float v[VPL];
+#pragma unroll
+    for (int r = 0; r < VPL; ++r) {
+        const int k = slot + 32 * r;
+        if (k < p.Ns) v[r] = own_hypothesis(p, b, nc, k, HW, inv_min, inv_max);
+        else if (k < D) v[r] = propagated_hypothesis(p, b, nc, k - p.Ns, HW, inv_min, inv_max);
+        else v[r] = kInf;  // padding sorts to the end
+    }
+#pragma unroll
+    for (int k2 = 2; k2 <= NPAD; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {  // NPAD == 64, final merge: partner lives in the same lane
+                const float lo = fminf(v[0], v[VPL - 1]), hi = fmaxf(v[0], v[VPL - 1]);
+                v[0] = lo;
+                v[VPL - 1] = hi;
+            } else {
+#pragma unroll
+                for (int r = 0; r < VPL; ++r) {
+                    const int idx = slot + 32 * r;
+                    const float other = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = (idx & k2) == 0, lower = (idx & j) == 0;
+                    v[r] = (lower == up) ? fminf(v[r], other) : fmaxf(v[r], other);
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < VPL; ++r) {
+            const int k = slot + 32 * r;
+            if (k < D) {
+                p.out[((size_t)b * D + k) * HW + n] = v[r];
+                if (p.xnorm) p.xnorm[((size_t)b * D + k) * HW + n] = pm::normalised_inverse_depth(v[r], inv_min, inv_max);
+            }
+        }
+    }
+}
+
+// No propagation (Kp == 0): initialisation order is kept (descending depth), nothing to sort.
+__global__ void __launch_bounds__(128) init_only_kernel(const PropParams p) {
     const int HW = p.H * p.W;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (n >= HW) return;
     const float inv_min = 1.0f / __ldg(p.dmin + b), inv_max = 1.0f / __ldg(p.dmax + b);
-    const int D = p.Ns + p.Kp;
-    float v[NPAD];
-#pragma unroll
-    for (int k = 0; k < NPAD; ++k) {
-        if (k < p.Ns) v[k] = own_hypothesis(p, b, n, k, HW, inv_min, inv_max);
-        else if (k < D) v[k] = propagated_hypothesis(p, b, n, k - p.Ns, HW, inv_min, inv_max);
-        else v[k] = __int_as_float(0x7f800000);  // +inf padding sorts to the end
+    for (int k = 0; k < p.Ns; ++k) {
+        const float v = own_hypothesis(p, b, n, k, HW, inv_min, inv_max);
+        p.out[((size_t)b * p.Ns + k) * HW + n] = v;
+        if (p.xnorm) p.xnorm[((size_t)b * p.Ns + k) * HW + n] = pm::normalised_inverse_depth(v, inv_min, inv_max);
     }
-    if (p.Kp > 0) {  // reference sorts only when something was propagated (models/patchmatch.py:497-499)
-#pragma unroll
-        for (int k = 2; k <= NPAD; k <<= 1) {
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-                for (int i = 0; i < NPAD; ++i) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const float lo = fminf(v[i], v[l]), hi = fmaxf(v[i], v[l]);
-                        const bool up = (i & k) == 0;
-                        v[i] = up ? lo : hi;
-                        v[l] = up ? hi : lo;
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NPAD; ++k)
-        if (k < D) p.out[((size_t)b * D + k) * HW + n] = v[k];
 }
 
 // D > 64: write unsorted, then insertion-sort each pixel's column in place.  Slow path.
@@ -547,15 +687,20 @@ __global__ void init_propagate_generic_kernel(const PropParams p) {
     for (int k = 0; k < D; ++k)
         col[(size_t)k * HW] = k < p.Ns ? own_hypothesis(p, b, n, k, HW, inv_min, inv_max)
                                        : propagated_hypothesis(p, b, n, k - p.Ns, HW, inv_min, inv_max);
-    if (p.Kp == 0) return;
-    for (int i = 1; i < D; ++i) {
-        const float x = col[(size_t)i * HW];
-        int j = i - 1;
-        while (j >= 0 && col[(size_t)j * HW] > x) {
-            col[(size_t)(j + 1) * HW] = col[(size_t)j * HW];
-            --j;
+    if (p.Kp > 0) {
+        for (int i = 1; i < D; ++i) {
+            const float x = col[(size_t)i * HW];
+            int j = i - 1;
+            while (j >= 0 && col[(size_t)j * HW] > x) {
+                col[(size_t)(j + 1) * HW] = col[(size_t)j * HW];
+                --j;
+            }
+            col[(size_t)(j + 1) * HW] = x;
         }
-        col[(size_t)(j + 1) * HW] = x;
+    }
+    if (p.xnorm) {
+        float *xc = p.xnorm + (size_t)b * D * HW + n;
+        for (int k = 0; k < D; ++k) xc[(size_t)k * HW] = pm::normalised_inverse_depth(col[(size_t)k * HW], inv_min, inv_max);
     }
 }
 
@@ -564,7 +709,7 @@ __global__ void init_propagate_generic_kernel(const PropParams p) {
 // ------------------------------------------------------------------------------------------
 
 struct EvalParams {
-    const float *score0, *depth, *offsets, *fw, *dmin, *dmax;
+    const float *score0, *depth, *xnorm, *offsets, *fw, *dmin, *dmax;
     float *prob, *depth_out;
     int B, D, H, W, K, dilation, is_inverse;
     float interval_scale;
@@ -598,27 +743,44 @@ __global__ void adaptive_eval_kernel(const EvalParams p) {
     __syncthreads();
 
     for (int d = ty; d < p.D; d += DY) {
-        const float *dmap = p.depth + ((size_t)b * p.D + d) * HW;
         const float *smap = p.score0 + ((size_t)b * p.D + d) * HW;
-        const float xc = pm::normalised_inverse_depth(__ldg(dmap + nc), inv_min, inv_max);
         float num = 0.0f, den = 0.0f;
-        for (int k = 0; k < p.K; ++k) {
-            const float4 w = cw[k * TP + tp];
-            const int key = ck[k * TP + tp];
-            const int r0 = pm::cell_r0(key), ddx = pm::cell_dx(key), ddy = pm::cell_dy(key);
-            const int r1 = r0 + ddx, r2 = r0 + ddy * p.W, r3 = r2 + ddx;
-            float xn = pm::normalised_inverse_depth(__ldg(dmap + r0), inv_min, inv_max) * w.x;
-            xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r1), inv_min, inv_max), w.y, xn);
-            xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r2), inv_min, inv_max), w.z, xn);
-            xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r3), inv_min, inv_max), w.w, xn);
-            float sn = __ldg(smap + r0) * w.x;
-            sn = fmaf(__ldg(smap + r1), w.y, sn);
-            sn = fmaf(__ldg(smap + r2), w.z, sn);
-            sn = fmaf(__ldg(smap + r3), w.w, sn);
-            const float wk = pm::depth_similarity(xc, xn, p.interval_scale) *
-                             __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
-            num = fmaf(sn, wk, num);
-            den += wk;
+        if (p.xnorm) {  // normalised inverse depth precomputed by K-C: 8 loads + 8 FMAs per neighbour
+            const float *xmap = p.xnorm + ((size_t)b * p.D + d) * HW;
+            const float xc = __ldg(xmap + nc);
+            for (int k = 0; k < p.K; ++k) {
+                const float4 w = cw[k * TP + tp];
+                const int key = ck[k * TP + tp];
+                const int r0 = pm::cell_r0(key), ddx = pm::cell_dx(key), ddy = pm::cell_dy(key);
+                const int r1 = r0 + ddx, r2 = r0 + ddy * p.W, r3 = r2 + ddx;
+                const float x0 = __ldg(xmap + r0), x1 = __ldg(xmap + r1), x2 = __ldg(xmap + r2), x3 = __ldg(xmap + r3);
+                const float s0 = __ldg(smap + r0), s1 = __ldg(smap + r1), s2 = __ldg(smap + r2), s3 = __ldg(smap + r3);
+                const float xn = fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, x0 * w.x)));
+                const float sn = fmaf(s3, w.w, fmaf(s2, w.z, fmaf(s1, w.y, s0 * w.x)));
+                const float wk = pm::depth_similarity(xc, xn, p.interval_scale) * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+                num = fmaf(sn, wk, num);
+                den += wk;
+            }
+        } else {
+            const float *dmap = p.depth + ((size_t)b * p.D + d) * HW;
+            const float xc = pm::normalised_inverse_depth(__ldg(dmap + nc), inv_min, inv_max);
+            for (int k = 0; k < p.K; ++k) {
+                const float4 w = cw[k * TP + tp];
+                const int key = ck[k * TP + tp];
+                const int r0 = pm::cell_r0(key), ddx = pm::cell_dx(key), ddy = pm::cell_dy(key);
+                const int r1 = r0 + ddx, r2 = r0 + ddy * p.W, r3 = r2 + ddx;
+                float xn = pm::normalised_inverse_depth(__ldg(dmap + r0), inv_min, inv_max) * w.x;
+                xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r1), inv_min, inv_max), w.y, xn);
+                xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r2), inv_min, inv_max), w.z, xn);
+                xn = fmaf(pm::normalised_inverse_depth(__ldg(dmap + r3), inv_min, inv_max), w.w, xn);
+                float sn = __ldg(smap + r0) * w.x;
+                sn = fmaf(__ldg(smap + r1), w.y, sn);
+                sn = fmaf(__ldg(smap + r2), w.z, sn);
+                sn = fmaf(__ldg(smap + r3), w.w, sn);
+                const float wk = pm::depth_similarity(xc, xn, p.interval_scale) * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+                num = fmaf(sn, wk, num);
+                den += wk;
+            }
         }
         sc[d * TP + tp] = num / den;
     }
@@ -729,8 +891,8 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
     do {                                                                                           \
         dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
                   nchunk, B);                                                                      \
-        if (fused) warp_corr_kernel<CC, GG, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(p);        \
-        else warp_corr_kernel<CC, GG, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(p);             \
+        if (fused) warp_corr_kernel<CC, GG, kEpiAgg><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());   \
+        else warp_corr_kernel<CC, GG, kEpiSims><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());       \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_WC(64, 8);
     else if (C == 32 && G == 8) PMB200_LAUNCH_WC(32, 8);
@@ -741,6 +903,89 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
     }
 #undef PMB200_LAUNCH_WC
     return launch_status("warp_corr");
+}
+
+namespace {
+int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float *src_nhwc, const float *rt,
+                   const float *depth, const float *view_weights, const pmb200_mlp *head_host, float *out, int V, int B,
+                   int C, int G, int H, int W, int Hs, int Ws, int D, void *stream) {
+    if (!ref_nhwc || !src_nhwc || !rt || !depth || !out || !head_host) return fail(PMB200_EINVAL, "warp_corr head: null pointer");
+    if (epi == kEpiScore && !view_weights) return fail(PMB200_EINVAL, "warp_corr_score: view_weights missing");
+    if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || B > 65535 || H < 1 || W < 1 || Hs < 1 || Ws < 1 || D < 1)
+        return fail(PMB200_EINVAL, "warp_corr head: bad size");
+    if ((long long)Hs * Ws >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "warp_corr head: source map too large");
+    static_assert(sizeof(MlpParams) == sizeof(pmb200_mlp), "pmb200_mlp layout");
+    WarpCorrParams p;
+    p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = view_weights; p.out = out;
+    p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
+    p.sx = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 1.0f;
+    p.sy = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 1.0f;
+    MlpParams m;
+    memcpy(&m, head_host, sizeof(m));
+    const int HW = H * W;
+    cudaStream_t st = as_stream(stream);
+    const int nchunk = (D + kChunk - 1) / kChunk;
+    if (nchunk > 65535) return fail(PMB200_EINVAL, "warp_corr head: too many hypotheses");
+    if (epi == kEpiViewW) {  // atomic max target starts at 0 (weights are sigmoids, > 0)
+        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * V * HW * sizeof(float), st);
+        if (e != cudaSuccess) return fail((int)e, "warp_corr_view_weights: memset failed");
+    }
+#define PMB200_LAUNCH_WH(CC, GG)                                                                   \
+    do {                                                                                           \
+        dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
+                  nchunk, B);                                                                      \
+        if (epi == kEpiScore) warp_corr_kernel<CC, GG, kEpiScore><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m); \
+        else warp_corr_kernel<CC, GG, kEpiViewW><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m);      \
+    } while (0)
+    if (C == 64 && G == 8) PMB200_LAUNCH_WH(64, 8);
+    else if (C == 32 && G == 8) PMB200_LAUNCH_WH(32, 8);
+    else if (C == 16 && G == 4) PMB200_LAUNCH_WH(16, 4);
+    else return fail(PMB200_EUNSUPPORTED, "warp_corr head: fused heads exist for (C,G) in {(64,8),(32,8),(16,4)} only");
+#undef PMB200_LAUNCH_WH
+    return launch_status(what);
+}
+}  // namespace
+
+int pmb200_warp_corr_score(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth,
+                           const float *view_weights, const pmb200_mlp *head_host, float *score_out, int V, int B, int C,
+                           int G, int H, int W, int Hs, int Ws, int D, void *stream) {
+    return warp_corr_head("warp_corr_score", kEpiScore, ref_nhwc, src_nhwc, rt, depth, view_weights, head_host, score_out,
+                          V, B, C, G, H, W, Hs, Ws, D, stream);
+}
+
+int pmb200_warp_corr_view_weights(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth,
+                                  const pmb200_mlp *head_host, float *view_weights_out, int V, int B, int C, int G, int H,
+                                  int W, int Hs, int Ws, int D, void *stream) {
+    return warp_corr_head("warp_corr_view_weights", kEpiViewW, ref_nhwc, src_nhwc, rt, depth, nullptr, head_host,
+                          view_weights_out, V, B, C, G, H, W, Hs, Ws, D, stream);
+}
+
+int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets, const pmb200_mlp *head_host, float *weight_out,
+                              int B, int C, int G, int H, int W, int K, int dilation, void *stream) {
+    if (!ref_nhwc || !offsets || !weight_out || !head_host) return fail(PMB200_EINVAL, "offset_corr_weight: null pointer");
+    if (B < 1 || B > 65535 || H < 2 || W < 2) return fail(PMB200_EINVAL, "offset_corr_weight: bad size");
+    if (K != 9 && K != 17) return fail(PMB200_EUNSUPPORTED, "offset_corr_weight: evaluate_neighbors must be 9 or 17");
+    if ((long long)H * W >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "offset_corr_weight: map too large");
+    OffsetCorrParams p;
+    p.ref = ref_nhwc; p.offsets = offsets; p.out = weight_out;
+    p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation;
+    MlpParams m;
+    memcpy(&m, head_host, sizeof(m));
+    const int HW = H * W;
+    cudaStream_t st = as_stream(stream);
+    const int nchunk = (K + kChunk - 1) / kChunk;
+#define PMB200_LAUNCH_OW(CC, GG)                                                                   \
+    do {                                                                                           \
+        dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
+                  nchunk, B);                                                                      \
+        offset_corr_kernel<CC, GG, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m);              \
+    } while (0)
+    if (C == 64 && G == 8) PMB200_LAUNCH_OW(64, 8);
+    else if (C == 32 && G == 8) PMB200_LAUNCH_OW(32, 8);
+    else if (C == 16 && G == 4) PMB200_LAUNCH_OW(16, 4);
+    else return fail(PMB200_EUNSUPPORTED, "offset_corr_weight: fused head exists for (C,G) in {(64,8),(32,8),(16,4)} only");
+#undef PMB200_LAUNCH_OW
+    return launch_status("offset_corr_weight");
 }
 
 int pmb200_aggregate_views(const float *sims, const float *view_weights, float *out, int V, int B, int G, int D,
@@ -772,7 +1017,7 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out, 
     do {                                                                                           \
         dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
                   nchunk, B);                                                                      \
-        offset_corr_kernel<CC, GG><<<grid, kWarpsPerBlock * 32, 0, st>>>(p);                       \
+        offset_corr_kernel<CC, GG, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());                       \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_OC(64, 8);
     else if (C == 32 && G == 8) PMB200_LAUNCH_OC(32, 8);
@@ -786,8 +1031,8 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out, 
 }
 
 int pmb200_init_propagate(const float *seed_map, const float *offsets, const float *depth_min,
-                          const float *depth_max, float *out, int mode, int B, int H, int W, int Ns, int Kp,
-                          int dilation, float interval_scale, void *stream) {
+                          const float *depth_max, float *out, float *xnorm_out, int mode, int B, int H, int W, int Ns,
+                          int Kp, int dilation, float interval_scale, void *stream) {
     if (!seed_map || !depth_min || !depth_max || !out) return fail(PMB200_EINVAL, "init_propagate: null pointer");
     if (B < 1 || B > 65535 || H < 2 || W < 2 || Ns < 1) return fail(PMB200_EINVAL, "init_propagate: bad size");
     if (mode < 0 || mode > 2) return fail(PMB200_EINVAL, "init_propagate: bad mode");
@@ -798,21 +1043,26 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets, const flo
     if (Kp > 0 && !offsets) return fail(PMB200_EINVAL, "init_propagate: offsets missing");
     if (Ns + Kp > PMB200_MAX_HYPOTHESES) return fail(PMB200_EINVAL, "init_propagate: too many hypotheses");
     PropParams p;
-    p.seed = seed_map; p.offsets = offsets; p.dmin = depth_min; p.dmax = depth_max; p.out = out;
+    p.seed = seed_map; p.offsets = offsets; p.dmin = depth_min; p.dmax = depth_max; p.out = out; p.xnorm = xnorm_out;
     p.mode = mode; p.B = B; p.H = H; p.W = W; p.Ns = Ns; p.Kp = Kp; p.dilation = dilation;
     p.interval_scale = interval_scale;
     const int HW = H * W, D = Ns + Kp;
     cudaStream_t st = as_stream(stream);
     dim3 grid((HW + 127) / 128, B);
-    if (D <= 8) init_propagate_kernel<8><<<grid, 128, 0, st>>>(p);
-    else if (D <= 16) init_propagate_kernel<16><<<grid, 128, 0, st>>>(p);
-    else if (D <= 32) init_propagate_kernel<32><<<grid, 128, 0, st>>>(p);
-    else if (D <= 64) init_propagate_kernel<64><<<grid, 128, 0, st>>>(p);
+    auto warp_grid = [&](int lanes_per_pixel) {  // 4 warps per block, 32/lanes_per_pixel pixels per warp
+        const int pix_per_block = 4 * (32 / lanes_per_pixel);
+        return dim3((HW + pix_per_block - 1) / pix_per_block, B);
+    };
+    if (Kp == 0 && D <= 64) init_only_kernel<<<grid, 128, 0, st>>>(p);
+    else if (D <= 8) init_propagate_kernel<8><<<warp_grid(8), 128, 0, st>>>(p);
+    else if (D <= 16) init_propagate_kernel<16><<<warp_grid(16), 128, 0, st>>>(p);
+    else if (D <= 32) init_propagate_kernel<32><<<warp_grid(32), 128, 0, st>>>(p);
+    else if (D <= 64) init_propagate_kernel<64><<<warp_grid(32), 128, 0, st>>>(p);
     else init_propagate_generic_kernel<<<grid, 128, 0, st>>>(p);
     return launch_status("init_propagate");
 }
 
-int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *offsets,
+int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *xnorm, const float *offsets,
                          const float *feature_weight, const float *depth_min, const float *depth_max,
                          float *prob_out, float *depth_out, int B, int D, int H, int W, int K, int dilation,
                          float interval_scale, int is_inverse, void *stream) {
@@ -823,7 +1073,7 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
     if (K != 9 && K != 17) return fail(PMB200_EUNSUPPORTED, "adaptive_eval: evaluate_neighbors must be 9 or 17");
     if (is_inverse && D < 2) return fail(PMB200_EINVAL, "adaptive_eval: inverse regression needs D >= 2");
     EvalParams p;
-    p.score0 = score0; p.depth = depth_sample; p.offsets = offsets; p.fw = feature_weight;
+    p.score0 = score0; p.depth = depth_sample; p.xnorm = xnorm; p.offsets = offsets; p.fw = feature_weight;
     p.dmin = depth_min; p.dmax = depth_max; p.prob = prob_out; p.depth_out = depth_out;
     p.B = B; p.D = D; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.is_inverse = is_inverse;
     p.interval_scale = interval_scale;

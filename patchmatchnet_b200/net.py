@@ -24,17 +24,67 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 
 
+def _fold_bn(weight: Tensor, bn: nn.BatchNorm2d, out_dim: int = 0):
+    """Eval-mode BatchNorm folded into the preceding (bias-free) convolution: returns (weight', bias')."""
+    scale = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+    shape = [1] * weight.dim()
+    shape[out_dim] = -1
+    w = (weight.double() * scale.view(shape)).float()
+    b = (bn.bias.double() - bn.running_mean.double() * scale).float()
+    return w, b
+
+
+class _FoldCache:
+    """Caches derived (folded) weights until any source tensor is modified or moved."""
+
+    def __init__(self) -> None:
+        self._stamp = None
+        self._value = None
+
+    def get(self, tensors, make):
+        stamp = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        if stamp != self._stamp:
+            with torch.no_grad():
+                self._value = make()
+            self._stamp = stamp
+        return self._value
+
+
+_FUSED_CONV_RELU = hasattr(torch, "cudnn_convolution_relu")
+
+
 class _ConvBnReLU2d(nn.Module):
-    """conv2d (no bias) + BatchNorm2d + ReLU; children named ``conv`` / ``bn``
-    as in the reference checkpoints (reference models/module.py:11-40)."""
+    """conv2d (no bias) + BatchNorm2d + ReLU; children named ``conv`` / ``bn`` as in the reference
+    checkpoints (reference models/module.py:11-40).
+
+    Training, or CPU: the three ops as written in the reference.  Eval on CUDA: BatchNorm is folded into
+    the conv weights (cached) and conv + bias + ReLU run as ONE cuDNN call on channels-last data -- the
+    separate cudnn bn_fw_inf kernel alone was 55 % of the forward's GPU time (profiles/r1_launches_v0.md)."""
 
     def __init__(self, cin: int, cout: int, k: int = 3, stride: int = 1, pad: int = 1) -> None:
         super().__init__()
         self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=pad, bias=False)
         self.bn = nn.BatchNorm2d(cout)
+        self._cache = _FoldCache()
+
+    def folded(self):
+        bn = self.bn
+        srcs = [self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def make():
+            w, b = _fold_bn(self.conv.weight, bn)
+            return w.contiguous(memory_format=torch.channels_last), b
+
+        return self._cache.get(srcs, make)
 
     def forward(self, x: Tensor) -> Tensor:
-        return F.relu(self.bn(self.conv(x)), inplace=True)
+        if self.training or not x.is_cuda:
+            return F.relu(self.bn(self.conv(x)), inplace=True)
+        w, b = self.folded()
+        c = self.conv
+        if _FUSED_CONV_RELU:
+            return torch.cudnn_convolution_relu(x, w, b, c.stride, c.padding, c.dilation, 1)
+        return F.relu_(F.conv2d(x, w, b, c.stride, c.padding, c.dilation))
 
 
 class FeatureNet(nn.Module):
@@ -86,13 +136,22 @@ class Refinement(nn.Module):
         self.bn = nn.BatchNorm2d(8)
         self.conv3 = _ConvBnReLU2d(16, 8)
         self.res = nn.Conv2d(8, 1, 3, padding=1, bias=False)
+        self._cache = _FoldCache()
+
+    def _upsample(self, x: Tensor) -> Tensor:
+        if self.training or not x.is_cuda:
+            return F.relu(self.bn(self.deconv(x)), inplace=True)
+        bn = self.bn
+        srcs = [self.deconv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        w, b = self._cache.get(srcs, lambda: _fold_bn(self.deconv.weight, bn, out_dim=1))
+        return F.relu_(F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1))
 
     def forward(self, img: Tensor, depth_half: Tensor, depth_min: Tensor, depth_max: Tensor) -> Tensor:
         B = depth_min.size(0)
         lo = depth_min.view(B, 1, 1, 1)
         span = (depth_max - depth_min).view(B, 1, 1, 1)
         d = (depth_half - lo) / span
-        up = F.relu(self.bn(self.deconv(self.conv2(self.conv1(d)))), inplace=True)
+        up = self._upsample(self.conv2(self.conv1(d)))
         res = self.res(self.conv3(torch.cat((up, self.conv0(img)), dim=1)))
         d = F.interpolate(d, scale_factor=2.0, mode="nearest") + res
         return d * span + lo
@@ -168,7 +227,10 @@ class PatchmatchNet(nn.Module):
         if self.training or not self.stack_views or len({im.shape for im in images}) != 1:
             return [self.feature(im) for im in images]
         n, b = len(images), images[0].shape[0]
-        stacked = self.feature(torch.cat(images, dim=0))
+        x = torch.cat(images, dim=0)
+        if x.is_cuda:  # cuDNN NHWC kernels; the pyramid then comes out channels-last, which is the layout
+            x = x.contiguous(memory_format=torch.channels_last)  # the fused PatchMatch kernels read in place
+        stacked = self.feature(x)
         return [{k: v[i * b:(i + 1) * b] for k, v in stacked.items()} for i in range(n)]
 
     def forward(

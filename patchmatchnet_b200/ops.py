@@ -125,6 +125,70 @@ def warp_corr(
     return out
 
 
+def _warp_args(ref_nhwc, src_nhwc, rt, depth):
+    ref = _require(ref_nhwc, "ref_nhwc", 4)
+    src = _require(src_nhwc, "src_nhwc", 5)
+    rt = _require(rt, "rt", 3)
+    depth = _require(depth, "depth", 4)
+    B, H, W, C = ref.shape
+    V, Bs, Hs, Ws, Cs = src.shape
+    D = depth.shape[1]
+    if Bs != B or Cs != C or rt.shape != (V, B, 12) or depth.shape != (B, D, H, W):
+        raise RuntimeError("warp_corr: inconsistent shapes")
+    return ref, src, rt, depth, (V, B, C, H, W, Hs, Ws, D)
+
+
+def warp_corr_score(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tensor, G: int, view_weights: Tensor,
+                    head: "_native.MlpStruct") -> Tensor:
+    """K-A with the SimilarityNet head fused (eval mode): -> raw score [B,D,H,W]; the similarity
+    tensor is never written.  `head` holds the BN-folded weights (host struct, see PointwiseHead.folded)."""
+    ref, src, rt, depth, (V, B, C, H, W, Hs, Ws, D) = _warp_args(ref_nhwc, src_nhwc, rt, depth)
+    vw = _require(view_weights, "view_weights", 4)
+    if vw.shape != (B, V, H, W):
+        raise RuntimeError("warp_corr_score: view_weights must be [B,V,H,W]")
+    out = torch.empty((B, D, H, W), dtype=torch.float32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        rc = _native.lib().pmb200_warp_corr_score(
+            ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), vw.data_ptr(), head, out.data_ptr(),
+            V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
+        )
+    _native.check(rc, "warp_corr_score")
+    return out
+
+
+def warp_corr_view_weights(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tensor, G: int,
+                           head: "_native.MlpStruct") -> Tensor:
+    """K-A with PixelwiseNet fused (eval mode): -> pixel-wise view weights [B,V,H,W]."""
+    ref, src, rt, depth, (V, B, C, H, W, Hs, Ws, D) = _warp_args(ref_nhwc, src_nhwc, rt, depth)
+    out = torch.empty((B, V, H, W), dtype=torch.float32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        rc = _native.lib().pmb200_warp_corr_view_weights(
+            ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), head, out.data_ptr(),
+            V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
+        )
+    _native.check(rc, "warp_corr_view_weights")
+    return out
+
+
+def offset_corr_weight(ref_nhwc: Tensor, offsets: Tensor, G: int, K: int, dilation: int, head: "_native.MlpStruct") -> Tensor:
+    """K-A' with the FeatureWeightNet head fused (eval mode): -> feature weight [B,K,H,W]."""
+    ref = _require(ref_nhwc, "ref_nhwc", 4)
+    off = _require(offsets, "offsets", 4)
+    B, H, W, C = ref.shape
+    if off.shape != (B, 2 * K, H, W):
+        raise RuntimeError("offset_corr_weight: offsets must be [B,2K,H,W]")
+    out = torch.empty((B, K, H, W), dtype=torch.float32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        rc = _native.lib().pmb200_offset_corr_weight(
+            ref.data_ptr(), off.data_ptr(), head, out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
+        )
+    _native.check(rc, "offset_corr_weight")
+    return out
+
+
+FUSED_HEAD_SHAPES = ((64, 8), (32, 8), (16, 4))
+
+
 def aggregate_views(sims: Tensor, view_weights: Tensor) -> Tensor:
     """sum_v sims[v]*w[:,v] / (1e-5 + sum_v w[:,v]) -> [B,G,D,H,W]."""
     sims = _require(sims, "sims", 6)
@@ -170,8 +234,10 @@ def init_propagate(
     Kp: int,
     dilation: int,
     interval_scale: float,
-) -> Tensor:
-    """K-C.  seed_map: U[0,1) noise [B,48,H,W] (mode 0) or current depth [B,1,H,W]; -> [B,Ns+Kp,H,W]."""
+    with_xnorm: bool = False,
+):
+    """K-C.  seed_map: U[0,1) noise [B,48,H,W] (mode 0) or current depth [B,1,H,W]; -> [B,Ns+Kp,H,W]
+    (and, with_xnorm, the normalised inverse depth of every hypothesis, same shape)."""
     seed = _require(seed_map, "seed_map", 4)
     B, S, H, W = seed.shape
     if S != (48 if mode == MODE_RANDOM else 1):
@@ -187,13 +253,15 @@ def init_propagate(
             raise RuntimeError("init_propagate: offsets must be [B,2Kp,H,W]")
         off_ptr = off.data_ptr()
     out = torch.empty((B, Ns + Kp, H, W), dtype=torch.float32, device=seed.device)
+    xn = torch.empty_like(out) if with_xnorm else None
     with torch.cuda.device(seed.device):
         rc = _native.lib().pmb200_init_propagate(
             seed.data_ptr(), off_ptr, dmin.data_ptr(), dmax.data_ptr(), out.data_ptr(),
+            None if xn is None else xn.data_ptr(),
             mode, B, H, W, Ns, Kp, dilation, float(interval_scale), _stream(seed),
         )
     _native.check(rc, "init_propagate")
-    return out
+    return (out, xn) if with_xnorm else out
 
 
 def adaptive_eval(
@@ -206,8 +274,9 @@ def adaptive_eval(
     dilation: int,
     interval_scale: float,
     is_inverse: bool,
+    xnorm: Optional[Tensor] = None,
 ):
-    """K-B.  -> (depth [B,H,W], prob [B,D,H,W])."""
+    """K-B.  -> (depth [B,H,W], prob [B,D,H,W]).  xnorm: normalised inverse depth from init_propagate."""
     sc = _require(score0, "score0", 4)
     ds = _require(depth_sample, "depth_sample", 4)
     off = _require(offsets, "offsets", 4)
@@ -218,11 +287,17 @@ def adaptive_eval(
         raise RuntimeError("adaptive_eval: inconsistent shapes")
     dmin = _require(depth_min.reshape(-1), "depth_min", 1)
     dmax = _require(depth_max.reshape(-1), "depth_max", 1)
+    xn_ptr = None
+    if xnorm is not None:
+        xn = _require(xnorm, "xnorm", 4)
+        if xn.shape != sc.shape:
+            raise RuntimeError("adaptive_eval: xnorm must match depth_sample")
+        xn_ptr = xn.data_ptr()
     prob = torch.empty((B, D, H, W), dtype=torch.float32, device=sc.device)
     depth = torch.empty((B, H, W), dtype=torch.float32, device=sc.device)
     with torch.cuda.device(sc.device):
         rc = _native.lib().pmb200_adaptive_eval(
-            sc.data_ptr(), ds.data_ptr(), off.data_ptr(), fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
+            sc.data_ptr(), ds.data_ptr(), xn_ptr, off.data_ptr(), fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
             prob.data_ptr(), depth.data_ptr(), B, D, H, W, K, dilation, float(interval_scale),
             1 if is_inverse else 0, _stream(sc),
         )

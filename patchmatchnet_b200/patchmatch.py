@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _native, ops
 
 Tensor = torch.Tensor
 
@@ -65,6 +65,42 @@ class _PointwiseHead(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         """[N,G,D,H,W] -> [N,D,H,W]"""
         return getattr(self, self._last)(self.conv1(self.conv0(x))).squeeze(1)
+
+    def folded(self) -> "_native.MlpStruct":
+        """Eval-mode weights with BatchNorm folded into the convs, as the host struct the fused
+        kernels take (pmb200_mlp).  Cached; recomputed when any parameter/buffer was modified.
+        The fold needs one device->host copy, so the first call must happen outside graph capture
+        (DepthEngine warms up before capturing)."""
+        tensors = list(self.parameters()) + list(self.buffers())
+        stamp = tuple((t.data_ptr(), t._version) for t in tensors)
+        if getattr(self, "_fold_stamp", None) == stamp:
+            return self._fold_cache
+        with torch.no_grad():
+            def fold(block):
+                w = block.conv.weight.double().flatten(1)  # [out,in]
+                bn = block.bn
+                scale = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+                return (w * scale[:, None]).float().cpu(), (bn.bias.double() - bn.running_mean.double() * scale).float().cpu()
+
+            w0, b0 = fold(self.conv0)
+            w1, b1 = fold(self.conv1)
+            last = getattr(self, self._last)
+            w2 = last.weight.detach().flatten().float().cpu()
+            b2 = float(last.bias.detach().float().cpu())
+        G = w0.shape[1]
+        if G > 8 or w0.shape[0] != 16 or w1.shape != (8, 16):
+            raise NotImplementedError("fused heads support G <= 8")
+        m = _native.MlpStruct()
+        pad = torch.zeros(16, 8)
+        pad[:, :G] = w0
+        m.w0[:] = pad.flatten().tolist()
+        m.b0[:] = b0.tolist()
+        m.w1[:] = w1.flatten().tolist()
+        m.b1[:] = b1.tolist()
+        m.w2[:] = w2.tolist()
+        m.b2 = b2
+        self._fold_stamp, self._fold_cache = stamp, m
+        return m
 
 
 class PixelwiseNet(_PointwiseHead):
@@ -136,6 +172,9 @@ class PatchMatch(nn.Module):
         # Tests inject a shared U[0,1) draw here when comparing against an oracle on another device;
         # by default the draw is torch.rand on the compute device, exactly as reference patchmatch.py:61-63.
         self.rand_source: Optional[Callable] = None
+        # eval mode: apply the 1x1x1 heads in the kernels' epilogues (BatchNorm folded); set False to
+        # run them as cuDNN ops on materialised similarity tensors (the training path always does)
+        self.fuse_heads = True
 
         self.evaluation = Evaluation(G)
         # zero-initialised offset convs, always defined (reference patchmatch.py:286-311)
@@ -214,8 +253,12 @@ class PatchMatch(nn.Module):
             src_nhwc = ops.pack_nhwc(list(src_features))
         rt = ops.relative_projection(ref_proj, list(src_projs))
 
+        fused = (not self.training) and self.fuse_heads and (C, self.G) in ops.FUSED_HEAD_SHAPES
         # feature weight of the evaluation neighbours, once per stage (reference patchmatch.py:475)
-        feature_weight = self.feature_weight_net(ops.offset_corr(ref_nhwc, eval_off, self.G, Ke, self.dilation))
+        if fused:
+            feature_weight = ops.offset_corr_weight(ref_nhwc, eval_off, self.G, Ke, self.dilation, self.feature_weight_net.folded())
+        else:
+            feature_weight = self.feature_weight_net(ops.offset_corr(ref_nhwc, eval_off, self.G, Ke, self.dilation))
 
         sample = depth
         prob = torch.empty(0, device=ref_feature.device)
@@ -231,12 +274,20 @@ class PatchMatch(nn.Module):
                 seed, mode, ns = sample.detach(), ops.MODE_PASSTHROUGH, 1
             else:
                 seed, mode, ns = sample.detach(), ops.MODE_PERTURB, self.patchmatch_num_sample
-            hyp = ops.init_propagate(
+            hyp, xnorm = ops.init_propagate(
                 seed, propa_off if kp_now > 0 else None, depth_min, depth_max,
-                mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale,
-            )  # [B,D,H,W]
+                mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale, with_xnorm=True,
+            )  # [B,D,H,W] hypotheses and their normalised inverse depth
 
-            if is_empty(view_weights):
+            if fused:
+                if is_empty(view_weights):  # PixelwiseNet in the epilogue; similarities are recomputed below
+                    view_weights = ops.warp_corr_view_weights(
+                        ref_nhwc, src_nhwc, rt, hyp, self.G, self.evaluation.pixel_wise_net.folded()
+                    )
+                score0 = ops.warp_corr_score(
+                    ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights, self.evaluation.similarity_net.folded()
+                )
+            elif is_empty(view_weights):
                 sims = ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G)  # [V,B,G,D,H,W]
                 if self.training:
                     vws = [self.evaluation.pixel_wise_net(sims[v]) for v in range(V)]
@@ -245,14 +296,12 @@ class PatchMatch(nn.Module):
                     D = hyp.shape[1]
                     vw = self.evaluation.pixel_wise_net(sims.view(V * B, self.G, D, H, W))  # [V*B,1,H,W]
                     view_weights = vw.view(V, B, H, W).permute(1, 0, 2, 3).contiguous()
-                similarity = ops.aggregate_views(sims, view_weights)
+                score0 = self.evaluation.similarity_net(ops.aggregate_views(sims, view_weights))  # [B,D,H,W]
             else:
-                similarity = ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights)
-
-            score0 = self.evaluation.similarity_net(similarity)  # [B,D,H,W]
+                score0 = self.evaluation.similarity_net(ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights))
             new_depth, prob = ops.adaptive_eval(
                 score0, hyp, eval_off, feature_weight, depth_min, depth_max,
-                self.dilation, self.patchmatch_interval_scale, last_of_stage1,
+                self.dilation, self.patchmatch_interval_scale, last_of_stage1, xnorm=xnorm,
             )
             sample = new_depth.unsqueeze(1)
             outs.append(sample)

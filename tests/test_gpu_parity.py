@@ -23,6 +23,22 @@ DEV = "cuda:0"
 DEPTH_TOL = 1e-4
 
 
+@pytest.fixture(autouse=True)
+def _full_fp32_library_ops():
+    """Parity runs compare against fp32 CPU results of the reference: keep the cuDNN/cuBLAS library ops
+    (offset convs, 1x1x1 heads, FeatureNet) in full fp32 -- torch would otherwise use TF32 for them --
+    and deterministic (ConvTranspose2d's dgrad algorithms are not, by default)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic,
+           torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    yield
+    (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic,
+     torch.backends.cudnn.benchmark) = old
+
+
 def maxabs(a, b):
     return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
 
@@ -226,8 +242,12 @@ def test_init_propagate_matches_oracle(mode, Ns, Kp, dil, H, W, B):
         off = torch.randn(B, 2 * Kp, H, W, generator=g) * 2.0
         grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("propagation", Kp, dil), off.view(B, 2 * Kp, H * W), H, W)
         want = pm_oracle.propagate(init, grid)
-    got = ops.init_propagate(seed.to(DEV), None if off is None else off.to(DEV), dmin.to(DEV), dmax.to(DEV), m, Ns, Kp, dil, scale)
+    got, got_x = ops.init_propagate(seed.to(DEV), None if off is None else off.to(DEV), dmin.to(DEV), dmax.to(DEV), m, Ns, Kp, dil,
+                                    scale, with_xnorm=True)
     assert got.shape == want.shape
+    inv_min, inv_max = (1.0 / dmin).view(B, 1, 1, 1), (1.0 / dmax).view(B, 1, 1, 1)
+    want_x = (1.0 / want - inv_max) / (inv_min - inv_max)  # reference patchmatch.py:655-657
+    assert maxabs(got_x, want_x) <= 5e-6
     assert pm_cases.rel_l1(got, want) <= 1e-6
     assert maxabs(got, want) <= 2e-3  # depths are ~400..1000: a few fp32 ulps
     if Kp > 0:
@@ -257,10 +277,88 @@ def test_adaptive_eval_matches_oracle(D, K, dil, H, W, B, inverse):
     s = torch.sum(pm_oracle._border_sample(score0, grid).view(B, D, K, H, W) * w, dim=2)
     want_prob = torch.exp(F.log_softmax(s, dim=1))
     want_depth = pm_oracle._Evaluation.regress(depth, want_prob, inverse)
-    got_depth, got_prob = ops.adaptive_eval(score0.to(DEV), depth.to(DEV), off.to(DEV), fw.to(DEV), dmin.to(DEV), dmax.to(DEV), dil, scale, inverse)
-    assert maxabs(got_prob, want_prob) <= 5e-6
-    assert pm_cases.rel_l1(got_depth, want_depth) <= 1e-6
-    assert maxabs(got_prob.sum(1), torch.ones(B, H, W)) <= 1e-5
+    inv_min, inv_max = (1.0 / dmin).view(B, 1, 1, 1), (1.0 / dmax).view(B, 1, 1, 1)
+    xnorm = (1.0 / depth - inv_max) / (inv_min - inv_max)
+    for xn in (None, xnorm.to(DEV)):  # recomputed per tap, or precomputed by K-C
+        got_depth, got_prob = ops.adaptive_eval(score0.to(DEV), depth.to(DEV), off.to(DEV), fw.to(DEV), dmin.to(DEV), dmax.to(DEV),
+                                                dil, scale, inverse, xnorm=xn)
+        assert maxabs(got_prob, want_prob) <= 5e-6
+        assert pm_cases.rel_l1(got_depth, want_depth) <= 1e-6
+        assert maxabs(got_prob.sum(1), torch.ones(B, H, W)) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# eval-mode fused heads (f2): kernel epilogue MLP vs the cuDNN heads on materialised similarities
+# ------------------------------------------------------------------------------------------------
+
+
+def _random_head(cls, G, seed):
+    torch.manual_seed(seed)
+    head = cls(G) if cls is not None else None
+    for m in head.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):  # non-trivial running statistics and affine terms
+            m.running_mean.normal_(0, 0.3)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    return head.eval()
+
+
+@pytest.mark.parametrize("C,G,H,W,D,B,V", [(64, 8, 13, 21, 64, 2, 3), (32, 8, 19, 27, 16, 1, 2), (16, 4, 22, 35, 8, 2, 4), (16, 4, 9, 11, 5, 1, 1)])
+def test_fused_heads_match_unfused(C, G, H, W, D, B, V):
+    from patchmatchnet_b200.patchmatch import FeatureWeightNet, PixelwiseNet, SimilarityNet
+
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=C + D + 1)
+    rt = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs])
+    ref_n = nhwc(ref.to(DEV))
+    src_n = torch.stack([nhwc(s.to(DEV)) for s in srcs])
+    depth_d, vw_d = depth.to(DEV), vw.to(DEV)
+    with torch.no_grad():
+        # SimilarityNet head
+        sim_head = _random_head(SimilarityNet, G, 1).to(DEV)
+        want = sim_head(ops.warp_corr(ref_n, src_n, rt, depth_d, G, vw_d))
+        got = ops.warp_corr_score(ref_n, src_n, rt, depth_d, G, vw_d, sim_head.folded())
+        assert maxabs(got, want) <= 2e-5 * max(1.0, float(want.abs().max()))
+        # PixelwiseNet
+        pw = _random_head(PixelwiseNet, G, 2).to(DEV)
+        sims = ops.warp_corr(ref_n, src_n, rt, depth_d, G)
+        want_vw = torch.cat([pw(sims[v]) for v in range(V)], dim=1)
+        got_vw = ops.warp_corr_view_weights(ref_n, src_n, rt, depth_d, G, pw.folded())
+        assert maxabs(got_vw, want_vw) <= 1e-5
+        # FeatureWeightNet head
+        K, dil = 9, 2
+        off = torch.randn(B, 2 * K, H, W, device=DEV) * 2.0
+        fw = _random_head(lambda g: FeatureWeightNet(K, g), G, 3).to(DEV)
+        want_fw = fw(ops.offset_corr(ref_n, off, G, K, dil))
+        got_fw = ops.offset_corr_weight(ref_n, off, G, K, dil, fw.folded())
+        assert maxabs(got_fw, want_fw) <= 1e-5
+        # the fold cache follows parameter updates
+        sim_head.similarity.bias.data.add_(1.0)
+        got2 = ops.warp_corr_score(ref_n, src_n, rt, depth_d, G, vw_d, sim_head.folded())
+        assert maxabs(got2, want + 1.0) <= 2e-5 * max(1.0, float(want.abs().max()) + 1.0)
+
+
+@pytest.mark.parametrize("name", list(pm_cases.STAGE_CASES))
+def test_stage_fused_equals_unfused(golden_weights, name):
+    spec = pm_cases.STAGE_CASES[name]
+    case = pm_cases.make_stage_inputs(spec)
+    outs = []
+    for fuse in (True, False):
+        mod = _stage_module(golden_weights, spec["stage"])
+        mod.fuse_heads = fuse
+        if case["rand48"] is not None:
+            mod.rand_source = lambda size, device: case["rand48"].to(device)
+        kw = dict(
+            ref_feature=case["ref_feature"].to(DEV), src_features=[s.to(DEV) for s in case["src_features"]],
+            ref_proj=case["ref_proj"].to(DEV), src_projs=[m.to(DEV) for m in case["src_projs"]],
+            depth_min=case["depth_min"].to(DEV), depth_max=case["depth_max"].to(DEV),
+            depth=case["depth"].to(DEV), view_weights=case["view_weights"].to(DEV),
+        )
+        with torch.no_grad():
+            outs.append(mod(**kw))
+    for x, y in zip(outs[0][0], outs[1][0]):
+        assert pm_cases.rel_l1(x, y) <= 1e-5
+    assert maxabs(outs[0][1], outs[1][1]) <= 1e-4 and maxabs(outs[0][2], outs[1][2]) <= 1e-5
 
 
 # ------------------------------------------------------------------------------------------------
@@ -356,8 +454,11 @@ def test_network_full_size_vs_oracle_on_gpu(golden_weights, B, H, W, n_views):
         torch.manual_seed(99)
         d2, c2, ps2 = orc(*args())
         torch.manual_seed(99)
-        d3, _, _ = mine(*args())
-    assert torch.equal(d1, d3), "the CUDA path must be deterministic"
+        d3, _, ps3 = mine(*args())
+    for s in (3, 2, 1):  # the native kernels have no atomics on float data: bit-exact run to run
+        for x, y in zip(ps1[s], ps3[s]):
+            assert torch.equal(x, y), f"stage {s} is not deterministic"
+    assert torch.equal(d1, d3), "the whole forward must be deterministic (cudnn.deterministic is set)"
     assert pm_cases.rel_l1(d1, d2) <= DEPTH_TOL
     for s in (3, 2, 1):
         for x, y in zip(ps1[s], ps2[s]):
