@@ -151,6 +151,8 @@ class Refinement(nn.Module):
         lo = depth_min.view(B, 1, 1, 1)
         span = (depth_max - depth_min).view(B, 1, 1, 1)
         d = (depth_half - lo) / span
+        if img.is_cuda and not self.training:
+            img = img.contiguous(memory_format=torch.channels_last)
         up = self._upsample(self.conv2(self.conv1(d)))
         res = self.res(self.conv3(torch.cat((up, self.conv0(img)), dim=1)))
         d = F.interpolate(d, scale_factor=2.0, mode="nearest") + res

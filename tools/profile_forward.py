@@ -18,6 +18,7 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
 dev = "cuda:0"
+torch.backends.cudnn.benchmark = True
 net, _ = bench.build_net()
 net = net.to(dev)
 inp = synthetic.make_inputs(a.batch, a.views, a.height, a.width, seed=0)
