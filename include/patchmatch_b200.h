@@ -136,12 +136,20 @@ int pmb200_warp_corr_score(const float *ref_nhwc, const float *src_nhwc, const f
                            void *stream);
 
 /* K-A + PixelwiseNet (models/patchmatch.py:690-702): per view, max over hypotheses of
- * sigmoid(MLP(similarity)).  view_weights_out [B,V,H,W] (zeroed by the call, then atomic max). */
+ * sigmoid(MLP(similarity)).  view_weights_out [B,V,H,W] (zeroed by the call, then atomic max).
+ * sims_out: NULL, or [V,B,G,D,H,W] to also keep the per-view similarities so that the weighted
+ * aggregation that follows (pmb200_aggregate_views_score) does not have to recompute them. */
 int pmb200_warp_corr_view_weights(const float *ref_nhwc, const float *src_nhwc, const float *rt,
                                   const float *depth, const pmb200_mlp *head_host,
-                                  float *view_weights_out,
+                                  float *view_weights_out, float *sims_out,
                                   int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D,
                                   void *stream);
+
+/* View-weighted aggregation of stored per-view similarities + SimilarityNet head:
+ *   score_out [B,D,H,W] = MLP( sum_v sims[v]*w[:,v] / (1e-5 + sum_v w[:,v]) ).  G in {4,8}. */
+int pmb200_aggregate_views_score(const float *sims, const float *view_weights,
+                                 const pmb200_mlp *head_host, float *score_out,
+                                 int V, int B, int G, int D, int H, int W, void *stream);
 
 /* K-A' + FeatureWeightNet head (models/patchmatch.py:597-601,624): sigmoid(MLP(correlation)).
  *   weight_out [B,K,H,W] */

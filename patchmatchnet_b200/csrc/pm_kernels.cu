@@ -23,6 +23,7 @@
 // land in the same source cell and cost 4 FMAs per group instead of 4 x 32 bytes of L1 traffic.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/patchmatch_b200.h"
@@ -301,6 +302,255 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const Wa
             if (en < HW && ed < p.D) p.out[((size_t)b * p.D + ed) * HW + en] = y;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-A, second generation: footprint compaction.
+//
+// The first-generation kernel above re-gathers whenever ANY pixel of the warp changes source cell and
+// runs the blend once per lane-group.  Measured on the 640x512 cascade only 19-31 % of the (pixel,
+// hypothesis, view) footprints differ from the previous hypothesis of the same pixel, but with 8-16
+// pixels per warp "any pixel changed" is true 70 % of the time, so the reuse did not turn into saved
+// issue slots.  Here each warp pass is split differently:
+//   phase 1  (one footprint per lane)   projection + footprint; "new cell" flags are compacted with a
+//            ballot/popc prefix into a dense list of UNIQUE cells; every footprint learns the slot of its
+//            cell through a shuffle prefix-max along the hypothesis axis;
+//   phase 2a (C/8 lanes per unique cell) gather the 4 taps, dot with the pixel's reference vector
+//            (staged in shared memory), store T[tap][group] of that slot in shared memory;
+//   phase 2b (one footprint per lane)   sim[g] = sum_t w_t * T[slot][t][g]; accumulate over views.
+// Gather work is now proportional to the number of unique cells, the blend runs on all 32 lanes for 32
+// different footprints, and the G group values of a footprint end up in one thread, which is exactly
+// what the MLP epilogue needs (no transpose).
+// ------------------------------------------------------------------------------------------
+constexpr int kWarps2 = 4;
+
+template <int C, int G, int EPI>
+__global__ void __launch_bounds__(kWarps2 * 32) warp_corr2_kernel(const WarpCorrParams p, const MlpParams mlp,
+                                                                  float *__restrict__ sims_out) {
+    using M = LaneMap<C, G>;
+    constexpr int NE = M::EPW / 32;    // footprints per lane (1, 2, 4)
+    constexpr int RPK = 32 / M::PPW;   // hypothesis rows covered by one k (8, 4, 2)
+    constexpr int TS = 4 * G + 4;      // floats per slot in s_T (padded: conflict-free LDS.128 across slots)
+    constexpr bool kWeighted = (EPI == kEpiAgg || EPI == kEpiScore);
+    __shared__ __align__(16) float s_ref[kWarps2][M::PPW * C];
+    __shared__ int2 s_u[kWarps2][M::EPW];
+    __shared__ __align__(16) float s_T[kWarps2][M::EPW * TS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = p.H * p.W;
+    const int n0 = (blockIdx.x * kWarps2 + warp) * M::PPW;
+    if (n0 >= HW) return;  // warp-level barriers only below
+    const int b = blockIdx.z, d0 = blockIdx.y * kChunk;
+    const unsigned full = 0xffffffffu;
+
+    // reference vectors of this warp's pixels -> shared memory, pre-scaled by 1/(C/G) (exact)
+    {
+        constexpr int V4 = C / 4;
+        constexpr float sc = 1.0f / (float)M::CPG;
+        const float4 *rp = reinterpret_cast<const float4 *>(p.ref + (size_t)b * HW * C);
+#pragma unroll
+        for (int i = lane; i < M::PPW * V4; i += 32) {
+            const int px = i / V4;
+            const int nn = min(n0 + px, HW - 1);
+            float4 q = __ldg(rp + (size_t)nn * V4 + (i % V4));
+            q.x *= sc; q.y *= sc; q.z *= sc; q.w *= sc;
+            reinterpret_cast<float4 *>(s_ref[warp])[i] = q;
+        }
+    }
+
+    const int pi = lane % M::PPW;          // pixel of all of this lane's footprints
+    const int row0 = lane / M::PPW;        // hypothesis row of footprint k is row0 + k * RPK
+    const int n = n0 + pi;
+    const bool live = n < HW;
+    const int nc = live ? n : HW - 1;
+    const float px_x = (float)(nc % p.W), px_y = (float)(nc / p.W);
+    float dep[NE];
+    bool ev[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int d = d0 + row0 + k * RPK;
+        ev[k] = live && d < p.D;
+        dep[k] = ev[k] ? __ldg(p.depth + ((size_t)b * p.D + d) * HW + n) : 1.0f;
+    }
+    float acc[NE][G];
+#pragma unroll
+    for (int k = 0; k < NE; ++k)
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[k][g] = 0.0f;
+    float wsum = 1e-5f;  // reference models/patchmatch.py:192
+    const int li = lane % M::LPP, grp = lane / M::LPP;
+    __syncwarp();
+
+    for (int v = 0; v < p.V; ++v) {
+        float rt[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) rt[i] = __ldg(p.rt + ((size_t)v * p.B + b) * 12 + i);
+        const pm::Ray ray = pm::pixel_ray(rt, px_x, px_y);
+
+        // ---- phase 1 ----
+        float4 w[NE];
+        int key[NE], slot[NE];
+        int nu = 0;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            pm::Cell c;
+            c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
+            c.key = pm::kKeyNone;
+            if (ev[k]) {
+                float uu, vv;
+                pm::project(ray, rt, dep[k], p.W, p.H, p.sx, p.sy, &uu, &vv);
+                c = pm::zero_pad_cell(uu, vv, p.Hs, p.Ws);
+            }
+            w[k] = make_float4(c.w00, c.w01, c.w10, c.w11);
+            key[k] = c.key;
+            // key of the previous hypothesis row of the same pixel
+            int pk = __shfl_up_sync(full, key[k], M::PPW);
+            if (k > 0) {
+                const int ck = __shfl_sync(full, key[k > 0 ? k - 1 : 0], 32 - M::PPW + pi);
+                if (lane < M::PPW) pk = ck;
+            } else if (lane < M::PPW) {
+                pk = pm::kKeyNone;
+            }
+            const bool isnew = key[k] != pm::kKeyNone && key[k] != pk;
+            const unsigned m = __ballot_sync(full, isnew);
+            int sl = isnew ? nu + __popc(m & ((1u << lane) - 1u)) : -1;
+            if (isnew) s_u[warp][sl] = make_int2(key[k], pi);
+            nu += __popc(m);
+            // slot of the latest new cell at or before this row (prefix max along rows)
+#pragma unroll
+            for (int off = M::PPW; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(full, sl, off);
+                if (lane >= off) sl = max(sl, t);
+            }
+            if (k > 0) {
+                const int cs = __shfl_sync(full, slot[k > 0 ? k - 1 : 0], 32 - M::PPW + pi);
+                sl = max(sl, cs);
+            }
+            slot[k] = sl;
+        }
+        __syncwarp();
+
+        float wv = 1.0f;
+        if (kWeighted) {
+            wv = __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc);
+            wsum += wv;
+        }
+
+        // ---- phase 2a: one unique cell per lane group ----
+        const float4 *sv =
+            reinterpret_cast<const float4 *>(p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C) + li * 2;
+        for (int base = 0; base < nu; base += M::PPW) {
+            const int s = base + grp;
+            if (s < nu) {
+                const int2 u = s_u[warp][s];
+                float r[8];
+                const float4 *rr = reinterpret_cast<const float4 *>(s_ref[warp] + u.y * C) + li * 2;
+                const float4 r0 = rr[0], r1 = rr[1];
+                r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
+                r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                float T[4][M::GPL];
+                gather_dot<C, G>(sv, u.x, p.Ws, r, T);
+                float *tp = s_T[warp] + s * TS + li * M::GPL;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if constexpr (M::GPL == 1) tp[t * G] = T[t][0];
+                    else *reinterpret_cast<float2 *>(tp + t * G) = make_float2(T[t][0], T[t][1]);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2b: one footprint per lane ----
+        float best = -INFINITY;  // kEpiViewW only
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            float sim[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) sim[g] = 0.0f;
+            if (key[k] != pm::kKeyNone) {
+                const float4 *tp = reinterpret_cast<const float4 *>(s_T[warp] + slot[k] * TS);
+#pragma unroll
+                for (int q = 0; q < G / 4; ++q) {
+                    const float4 t0 = tp[q], t1 = tp[G / 4 + q], t2 = tp[2 * (G / 4) + q], t3 = tp[3 * (G / 4) + q];
+                    sim[4 * q + 0] = w[k].x * t0.x + w[k].y * t1.x + w[k].z * t2.x + w[k].w * t3.x;
+                    sim[4 * q + 1] = w[k].x * t0.y + w[k].y * t1.y + w[k].z * t2.y + w[k].w * t3.y;
+                    sim[4 * q + 2] = w[k].x * t0.z + w[k].y * t1.z + w[k].z * t2.z + w[k].w * t3.z;
+                    sim[4 * q + 3] = w[k].x * t0.w + w[k].y * t1.w + w[k].z * t2.w + w[k].w * t3.w;
+                }
+            }
+            if (kWeighted) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[k][g] = fmaf(sim[g], wv, acc[k][g]);
+            } else {
+                const int d = d0 + row0 + k * RPK;
+                if ((EPI == kEpiSims || sims_out != nullptr) && ev[k]) {
+                    float *o = (EPI == kEpiSims ? p.out : sims_out) + ((((size_t)v * p.B + b) * G) * p.D + d) * HW + n;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = sim[g];
+                }
+                if (EPI == kEpiViewW && ev[k]) best = fmaxf(best, mlp_eval<G>(mlp, sim));
+            }
+        }
+        if (EPI == kEpiViewW) {
+            // PixelwiseNet (reference models/patchmatch.py:702): max over hypotheses of sigmoid(MLP(sim)); sigmoid is
+            // monotonic -> max first, one sigmoid per pixel, atomic max across hypothesis chunks
+#pragma unroll
+            for (int off = M::PPW; off < 32; off <<= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
+            if (lane < M::PPW && live && best > -INFINITY) {
+                const float sg = 1.0f / (1.0f + expf(-best));
+                atomicMax(reinterpret_cast<int *>(p.out + ((size_t)b * p.V + v) * HW + n), __float_as_int(sg));
+            }
+        }
+        __syncwarp();  // s_u / s_T are rewritten by the next view
+    }
+
+    if (EPI == kEpiAgg) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const int d = d0 + row0 + k * RPK;
+            if (ev[k]) {
+                float *o = p.out + (((size_t)b * G) * p.D + d) * HW + n;
+#pragma unroll
+                for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = acc[k][g] / wsum;
+            }
+        }
+    } else if (EPI == kEpiScore) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const int d = d0 + row0 + k * RPK;
+            float x[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) x[g] = acc[k][g] / wsum;
+            const float y = mlp_eval<G>(mlp, x);
+            if (ev[k]) p.out[((size_t)b * p.D + d) * HW + n] = y;
+        }
+    }
+}
+
+// sum_v sims[v]*w_v / (1e-5 + sum_v w_v) -> SimilarityNet head -> score [B,D,H,W]   (first stage-3 iteration, eval)
+template <int G>
+__global__ void aggregate_score_kernel(const float *__restrict__ sims, const float *__restrict__ vw,
+                                       float *__restrict__ score, const MlpParams mlp, int V, int B, int D, int HW) {
+    const size_t total = (size_t)B * D * HW;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int n = (int)(idx % HW);
+    const int d = (int)((idx / HW) % D);
+    const int b = (int)(idx / ((size_t)HW * D));
+    float x[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) x[g] = 0.0f;
+    float wsum = 1e-5f;
+    for (int v = 0; v < V; ++v) {
+        const float w = __ldg(vw + ((size_t)b * V + v) * HW + n);
+        wsum += w;
+        const float *sp = sims + ((((size_t)v * B + b) * G) * D + d) * HW + n;
+#pragma unroll
+        for (int g = 0; g < G; ++g) x[g] = fmaf(__ldg(sp + (size_t)g * D * HW), w, x[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) x[g] = x[g] / wsum;
+    score[idx] = mlp_eval<G>(mlp, x);
 }
 
 // Any C % G == 0: one thread per (batch, hypothesis, pixel), scalar channel loop.  Slow path.
@@ -715,13 +965,14 @@ struct EvalParams {
     float interval_scale;
 };
 
-// block (TP pixels, DY hypothesis lanes); dynamic smem: float4 cw[K][TP]; int ck[K][TP]; float sc[D][TP]
+// block (TP pixels, DY hypothesis lanes); dynamic smem: float4 cw[K][TP]; int ck[K][TP]; float sc[D][TP]; float pr[D][TP]
 __global__ void adaptive_eval_kernel(const EvalParams p) {
     extern __shared__ float4 smem4[];
     const int TP = blockDim.x, DY = blockDim.y;
     float4 *cw = smem4;
     int *ck = reinterpret_cast<int *>(cw + (size_t)p.K * TP);
     float *sc = reinterpret_cast<float *>(ck + (size_t)p.K * TP);
+    float *pr = sc + (size_t)p.D * TP;
 
     const int tp = threadIdx.x, ty = threadIdx.y;
     const int HW = p.H * p.W;
@@ -730,6 +981,7 @@ __global__ void adaptive_eval_kernel(const EvalParams p) {
     const bool live = n < HW;
     const int nc = live ? n : HW - 1;
     const float inv_min = 1.0f / __ldg(p.dmin + b), inv_max = 1.0f / __ldg(p.dmax + b);
+    const float inv_interval = 1.0f / p.interval_scale;
 
     for (int k = ty; k < p.K; k += DY) {
         int dy = 0, dx = 0;
@@ -757,7 +1009,11 @@ __global__ void adaptive_eval_kernel(const EvalParams p) {
                 const float s0 = __ldg(smap + r0), s1 = __ldg(smap + r1), s2 = __ldg(smap + r2), s3 = __ldg(smap + r3);
                 const float xn = fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, x0 * w.x)));
                 const float sn = fmaf(s3, w.w, fmaf(s2, w.z, fmaf(s1, w.y, s0 * w.x)));
-                const float wk = pm::depth_similarity(xc, xn, p.interval_scale) * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+                // sigmoid(4 - 2*clamp(|dx|/interval, 0, 4)) with the fast exponential / reciprocal
+                // (argument in [-4, 4]: relative error ~1e-7, far below the parity tolerance)
+                const float t = fminf(fabsf(xn - xc) * inv_interval, 4.0f);
+                const float sg = __fdividef(1.0f, 1.0f + __expf(2.0f * t - 4.0f));
+                const float wk = sg * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
                 num = fmaf(sn, wk, num);
                 den += wk;
             }
@@ -786,27 +1042,33 @@ __global__ void adaptive_eval_kernel(const EvalParams p) {
     }
     __syncthreads();
 
+    // softmax over the hypotheses of this pixel: one exponential per (pixel, hypothesis) thread
     float m = -INFINITY;
     for (int d = 0; d < p.D; ++d) m = fmaxf(m, sc[d * TP + tp]);
+    for (int d = ty; d < p.D; d += DY) pr[d * TP + tp] = expf(sc[d * TP + tp] - m);
+    __syncthreads();
     float sum = 0.0f;
-    for (int d = 0; d < p.D; ++d) sum += expf(sc[d * TP + tp] - m);
+    for (int d = 0; d < p.D; ++d) sum += pr[d * TP + tp];
     const float lse = logf(sum);
-    if (live)
-        for (int d = ty; d < p.D; d += DY)
-            p.prob[((size_t)b * p.D + d) * HW + n] = expf(sc[d * TP + tp] - m - lse);
+    __syncthreads();  // everybody has read the un-normalised values
+    for (int d = ty; d < p.D; d += DY) {
+        const float q = expf(sc[d * TP + tp] - m - lse);  // exp(log_softmax), as the reference writes it
+        pr[d * TP + tp] = q;
+        if (live) p.prob[((size_t)b * p.D + d) * HW + n] = q;
+    }
+    __syncthreads();
 
     if (ty == 0 && live) {
         float out;
         if (p.is_inverse) {  // reference models/patchmatch.py:227-234
             float idx = 0.0f;
-            for (int d = 0; d < p.D; ++d) idx = fmaf((float)d, expf(sc[d * TP + tp] - m - lse), idx);
+            for (int d = 0; d < p.D; ++d) idx = fmaf((float)d, pr[d * TP + tp], idx);
             const float inv_hi = 1.0f / __ldg(p.depth + ((size_t)b * p.D + (p.D - 1)) * HW + n);
             const float inv_lo = 1.0f / __ldg(p.depth + ((size_t)b * p.D) * HW + n);
             out = 1.0f / (inv_lo + idx / (float)(p.D - 1) * (inv_hi - inv_lo));
         } else {
             float e = 0.0f;
-            for (int d = 0; d < p.D; ++d)
-                e = fmaf(__ldg(p.depth + ((size_t)b * p.D + d) * HW + n), expf(sc[d * TP + tp] - m - lse), e);
+            for (int d = 0; d < p.D; ++d) e = fmaf(__ldg(p.depth + ((size_t)b * p.D + d) * HW + n), pr[d * TP + tp], e);
             out = e;
         }
         p.depth_out[(size_t)b * HW + n] = out;
@@ -814,6 +1076,12 @@ __global__ void adaptive_eval_kernel(const EvalParams p) {
 }
 
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// PMB200_WARP_CORR_V1=1 selects the first-generation K-A kernel (kept for A/B measurements)
+bool use_v1() {
+    const char *e = getenv("PMB200_WARP_CORR_V1");  // read per call so tests/benchmarks can toggle it
+    return e && e[0] == '1';
+}
 
 }  // namespace
 
@@ -889,10 +1157,16 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
     if (nchunk > 65535) return fail(PMB200_EINVAL, "warp_corr: too many hypotheses");
 #define PMB200_LAUNCH_WC(CC, GG)                                                                   \
     do {                                                                                           \
-        dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
-                  nchunk, B);                                                                      \
-        if (fused) warp_corr_kernel<CC, GG, kEpiAgg><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());   \
-        else warp_corr_kernel<CC, GG, kEpiSims><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());       \
+        if (use_v1()) {                                                                            \
+            dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
+                      nchunk, B);                                                                  \
+            if (fused) warp_corr_kernel<CC, GG, kEpiAgg><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());   \
+            else warp_corr_kernel<CC, GG, kEpiSims><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());       \
+        } else {                                                                                   \
+            dim3 grid((HW + kWarps2 * LaneMap<CC, GG>::PPW - 1) / (kWarps2 * LaneMap<CC, GG>::PPW), nchunk, B);   \
+            if (fused) warp_corr2_kernel<CC, GG, kEpiAgg><<<grid, kWarps2 * 32, 0, st>>>(p, MlpParams(), nullptr); \
+            else warp_corr2_kernel<CC, GG, kEpiSims><<<grid, kWarps2 * 32, 0, st>>>(p, MlpParams(), nullptr);     \
+        }                                                                                          \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_WC(64, 8);
     else if (C == 32 && G == 8) PMB200_LAUNCH_WC(32, 8);
@@ -907,8 +1181,8 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
 
 namespace {
 int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float *src_nhwc, const float *rt,
-                   const float *depth, const float *view_weights, const pmb200_mlp *head_host, float *out, int V, int B,
-                   int C, int G, int H, int W, int Hs, int Ws, int D, void *stream) {
+                   const float *depth, const float *view_weights, const pmb200_mlp *head_host, float *out,
+                   float *sims_out, int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D, void *stream) {
     if (!ref_nhwc || !src_nhwc || !rt || !depth || !out || !head_host) return fail(PMB200_EINVAL, "warp_corr head: null pointer");
     if (epi == kEpiScore && !view_weights) return fail(PMB200_EINVAL, "warp_corr_score: view_weights missing");
     if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || B > 65535 || H < 1 || W < 1 || Hs < 1 || Ws < 1 || D < 1)
@@ -932,10 +1206,16 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
     }
 #define PMB200_LAUNCH_WH(CC, GG)                                                                   \
     do {                                                                                           \
-        dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
-                  nchunk, B);                                                                      \
-        if (epi == kEpiScore) warp_corr_kernel<CC, GG, kEpiScore><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m); \
-        else warp_corr_kernel<CC, GG, kEpiViewW><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m);      \
+        if (use_v1() && sims_out == nullptr) {                                                     \
+            dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
+                      nchunk, B);                                                                  \
+            if (epi == kEpiScore) warp_corr_kernel<CC, GG, kEpiScore><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m); \
+            else warp_corr_kernel<CC, GG, kEpiViewW><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m);  \
+        } else {                                                                                   \
+            dim3 grid((HW + kWarps2 * LaneMap<CC, GG>::PPW - 1) / (kWarps2 * LaneMap<CC, GG>::PPW), nchunk, B);   \
+            if (epi == kEpiScore) warp_corr2_kernel<CC, GG, kEpiScore><<<grid, kWarps2 * 32, 0, st>>>(p, m, nullptr); \
+            else warp_corr2_kernel<CC, GG, kEpiViewW><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);             \
+        }                                                                                          \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_WH(64, 8);
     else if (C == 32 && G == 8) PMB200_LAUNCH_WH(32, 8);
@@ -950,14 +1230,29 @@ int pmb200_warp_corr_score(const float *ref_nhwc, const float *src_nhwc, const f
                            const float *view_weights, const pmb200_mlp *head_host, float *score_out, int V, int B, int C,
                            int G, int H, int W, int Hs, int Ws, int D, void *stream) {
     return warp_corr_head("warp_corr_score", kEpiScore, ref_nhwc, src_nhwc, rt, depth, view_weights, head_host, score_out,
-                          V, B, C, G, H, W, Hs, Ws, D, stream);
+                          nullptr, V, B, C, G, H, W, Hs, Ws, D, stream);
 }
 
 int pmb200_warp_corr_view_weights(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth,
-                                  const pmb200_mlp *head_host, float *view_weights_out, int V, int B, int C, int G, int H,
-                                  int W, int Hs, int Ws, int D, void *stream) {
+                                  const pmb200_mlp *head_host, float *view_weights_out, float *sims_out, int V, int B,
+                                  int C, int G, int H, int W, int Hs, int Ws, int D, void *stream) {
     return warp_corr_head("warp_corr_view_weights", kEpiViewW, ref_nhwc, src_nhwc, rt, depth, nullptr, head_host,
-                          view_weights_out, V, B, C, G, H, W, Hs, Ws, D, stream);
+                          view_weights_out, sims_out, V, B, C, G, H, W, Hs, Ws, D, stream);
+}
+
+int pmb200_aggregate_views_score(const float *sims, const float *view_weights, const pmb200_mlp *head_host,
+                                 float *score_out, int V, int B, int G, int D, int H, int W, void *stream) {
+    if (!sims || !view_weights || !head_host || !score_out) return fail(PMB200_EINVAL, "aggregate_views_score: null pointer");
+    if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || D < 1 || H < 1 || W < 1)
+        return fail(PMB200_EINVAL, "aggregate_views_score: bad size");
+    MlpParams m;
+    memcpy(&m, head_host, sizeof(m));
+    const size_t total = (size_t)B * D * H * W;
+    const unsigned blocks = (unsigned)((total + 127) / 128);
+    if (G == 8) aggregate_score_kernel<8><<<blocks, 128, 0, as_stream(stream)>>>(sims, view_weights, score_out, m, V, B, D, H * W);
+    else if (G == 4) aggregate_score_kernel<4><<<blocks, 128, 0, as_stream(stream)>>>(sims, view_weights, score_out, m, V, B, D, H * W);
+    else return fail(PMB200_EUNSUPPORTED, "aggregate_views_score: G must be 4 or 8");
+    return launch_status("aggregate_views_score");
 }
 
 int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets, const pmb200_mlp *head_host, float *weight_out,
@@ -1084,7 +1379,12 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
         TP = 8;
         DY = D < 32 ? D : 32;
     }
-    const size_t smem = (size_t)K * TP * (sizeof(float4) + sizeof(int)) + (size_t)D * TP * sizeof(float);
+    auto smem_for = [&](int tp) { return (size_t)K * tp * (sizeof(float4) + sizeof(int)) + 2 * (size_t)D * tp * sizeof(float); };
+    if (smem_for(TP) > 48 * 1024) {  // many hypotheses: fewer pixels per block keeps the tile under the default 48 KB
+        TP = 8;
+        DY = D < 32 ? D : 32;
+    }
+    const size_t smem = smem_for(TP);
     dim3 grid((HW + TP - 1) / TP, B);
     adaptive_eval_kernel<<<grid, dim3(TP, DY), smem, as_stream(stream)>>>(p);
     return launch_status("adaptive_eval");

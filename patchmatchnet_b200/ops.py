@@ -157,16 +157,34 @@ def warp_corr_score(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tenso
 
 
 def warp_corr_view_weights(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tensor, G: int,
-                           head: "_native.MlpStruct") -> Tensor:
-    """K-A with PixelwiseNet fused (eval mode): -> pixel-wise view weights [B,V,H,W]."""
+                           head: "_native.MlpStruct", keep_sims: bool = False):
+    """K-A with PixelwiseNet fused (eval mode): -> pixel-wise view weights [B,V,H,W]
+    (and, keep_sims, the per-view similarities [V,B,G,D,H,W] for aggregate_views_score)."""
     ref, src, rt, depth, (V, B, C, H, W, Hs, Ws, D) = _warp_args(ref_nhwc, src_nhwc, rt, depth)
     out = torch.empty((B, V, H, W), dtype=torch.float32, device=ref.device)
+    sims = torch.empty((V, B, G, D, H, W), dtype=torch.float32, device=ref.device) if keep_sims else None
     with torch.cuda.device(ref.device):
         rc = _native.lib().pmb200_warp_corr_view_weights(
             ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), head, out.data_ptr(),
-            V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
+            None if sims is None else sims.data_ptr(), V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
         )
     _native.check(rc, "warp_corr_view_weights")
+    return (out, sims) if keep_sims else out
+
+
+def aggregate_views_score(sims: Tensor, view_weights: Tensor, head: "_native.MlpStruct") -> Tensor:
+    """MLP(sum_v sims[v]*w[:,v] / (1e-5 + sum_v w[:,v])) -> raw score [B,D,H,W]."""
+    sims = _require(sims, "sims", 6)
+    vw = _require(view_weights, "view_weights", 4)
+    V, B, G, D, H, W = sims.shape
+    if vw.shape != (B, V, H, W):
+        raise RuntimeError("aggregate_views_score: view_weights must be [B,V,H,W]")
+    out = torch.empty((B, D, H, W), dtype=torch.float32, device=sims.device)
+    with torch.cuda.device(sims.device):
+        rc = _native.lib().pmb200_aggregate_views_score(
+            sims.data_ptr(), vw.data_ptr(), head, out.data_ptr(), V, B, G, D, H, W, _stream(sims)
+        )
+    _native.check(rc, "aggregate_views_score")
     return out
 
 

@@ -280,13 +280,17 @@ class PatchMatch(nn.Module):
             )  # [B,D,H,W] hypotheses and their normalised inverse depth
 
             if fused:
-                if is_empty(view_weights):  # PixelwiseNet in the epilogue; similarities are recomputed below
-                    view_weights = ops.warp_corr_view_weights(
-                        ref_nhwc, src_nhwc, rt, hyp, self.G, self.evaluation.pixel_wise_net.folded()
+                if is_empty(view_weights):
+                    # first iteration on the coarsest stage: PixelwiseNet in the K-A epilogue; the per-view
+                    # similarities are kept (L2-resident) and aggregated + scored by a light second kernel
+                    view_weights, sims = ops.warp_corr_view_weights(
+                        ref_nhwc, src_nhwc, rt, hyp, self.G, self.evaluation.pixel_wise_net.folded(), keep_sims=True
                     )
-                score0 = ops.warp_corr_score(
-                    ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights, self.evaluation.similarity_net.folded()
-                )
+                    score0 = ops.aggregate_views_score(sims, view_weights, self.evaluation.similarity_net.folded())
+                else:
+                    score0 = ops.warp_corr_score(
+                        ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights, self.evaluation.similarity_net.folded()
+                    )
             elif is_empty(view_weights):
                 sims = ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G)  # [V,B,G,D,H,W]
                 if self.training:

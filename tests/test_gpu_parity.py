@@ -152,6 +152,21 @@ def test_warp_corr_matches_oracle(C, G, H, W, D, B, V):
     assert maxabs(got_a, want_f) <= 2e-5 * max(1.0, scale)
 
 
+def test_warp_corr_generations_agree(monkeypatch):
+    """The first-generation kernel (PMB200_WARP_CORR_V1=1, kept for A/B measurements) and the compaction
+    kernel are two schedules of the same arithmetic."""
+    for (C, G, H, W, D, B, V) in [(64, 8, 13, 21, 20, 2, 3), (32, 8, 19, 27, 16, 1, 2), (16, 4, 22, 35, 8, 2, 4)]:
+        ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=77)
+        rt = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs])
+        ref_n, src_n = nhwc(ref.to(DEV)), torch.stack([nhwc(s.to(DEV)) for s in srcs])
+        outs = {}
+        for gen in ("0", "1"):
+            monkeypatch.setenv("PMB200_WARP_CORR_V1", gen)
+            outs[gen] = (ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G), ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV)))
+        for a, b in zip(outs["0"], outs["1"]):
+            assert maxabs(a, b) <= 1e-5 * max(1.0, float(a.abs().max()))
+
+
 def test_warp_corr_source_map_of_other_size():
     C, G, H, W, D, B, V = 32, 8, 12, 20, 8, 1, 2
     ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, Hs=9, Ws=14, seed=5)
@@ -325,6 +340,11 @@ def test_fused_heads_match_unfused(C, G, H, W, D, B, V):
         want_vw = torch.cat([pw(sims[v]) for v in range(V)], dim=1)
         got_vw = ops.warp_corr_view_weights(ref_n, src_n, rt, depth_d, G, pw.folded())
         assert maxabs(got_vw, want_vw) <= 1e-5
+        got_vw2, kept = ops.warp_corr_view_weights(ref_n, src_n, rt, depth_d, G, pw.folded(), keep_sims=True)
+        assert torch.equal(got_vw2, got_vw) and maxabs(kept, sims) <= 1e-6 * max(1.0, float(sims.abs().max()))
+        want_sc = sim_head(ops.aggregate_views(sims, want_vw))
+        got_sc = ops.aggregate_views_score(kept, got_vw2, sim_head.folded())
+        assert maxabs(got_sc, want_sc) <= 2e-5 * max(1.0, float(want_sc.abs().max()))
         # FeatureWeightNet head
         K, dil = 9, 2
         off = torch.randn(B, 2 * K, H, W, device=DEV) * 2.0
@@ -333,7 +353,7 @@ def test_fused_heads_match_unfused(C, G, H, W, D, B, V):
         got_fw = ops.offset_corr_weight(ref_n, off, G, K, dil, fw.folded())
         assert maxabs(got_fw, want_fw) <= 1e-5
         # the fold cache follows parameter updates
-        sim_head.similarity.bias.data.add_(1.0)
+        sim_head.similarity.bias.add_(1.0)  # in place under no_grad: bumps the version the fold cache watches
         got2 = ops.warp_corr_score(ref_n, src_n, rt, depth_d, G, vw_d, sim_head.folded())
         assert maxabs(got2, want + 1.0) <= 2e-5 * max(1.0, float(want.abs().max()) + 1.0)
 
