@@ -66,6 +66,15 @@ int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, 
                      float *out_nhwc, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Caller-side helper (feature pyramid top-down path, models/net.py:60-66): channels-last
+ *     out = bilinear_upsample_x2(x) + y      x [N,h,w,C], y/out [N,2h,2w,C], C % 4 == 0
+ * same sampling as F.interpolate(scale_factor=2, mode="bilinear", align_corners=False).
+ * Replaces ATen's channels-last bilinear kernel + a separate add (12 % of the forward before).
+ */
+int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, float *out_nhwc,
+                               int N, int h, int w, int C, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * K-A: fused homography warp + bilinear gather + group-wise correlation
  *      (+ view-weighted aggregation).
  * Replaces, per source view, differentiable_warping (models/module.py:130-181), the

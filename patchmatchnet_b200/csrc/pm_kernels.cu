@@ -762,6 +762,35 @@ __global__ void pack_nhwc_kernel(const PackParams p) {
     }
 }
 
+// out[n,oy,ox,:] = bilinear_up2(x)[n,oy,ox,:] + y[n,oy,ox,:], channels-last, float4 over channels.
+// Same sampling as F.interpolate(scale_factor=2, mode="bilinear", align_corners=False).
+__global__ void upsample2x_add_nhwc_kernel(const float4 *__restrict__ x, const float4 *__restrict__ y,
+                                           float4 *__restrict__ out, int N, int h, int w, int C4) {
+    const int H = 2 * h, W = 2 * w;
+    const size_t total = (size_t)N * H * W * C4;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % C4);
+    const int ox = (int)((idx / C4) % W);
+    const int oy = (int)((idx / ((size_t)C4 * W)) % H);
+    const int n = (int)(idx / ((size_t)C4 * W * H));
+    const float sy = fmaxf(0.5f * ((float)oy + 0.5f) - 0.5f, 0.0f), sx = fmaxf(0.5f * ((float)ox + 0.5f) - 0.5f, 0.0f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const float4 *b = x + (size_t)n * h * w * C4 + c;
+    const float4 a00 = __ldg(b + ((size_t)y0 * w + x0) * C4), a01 = __ldg(b + ((size_t)y0 * w + x1) * C4);
+    const float4 a10 = __ldg(b + ((size_t)y1 * w + x0) * C4), a11 = __ldg(b + ((size_t)y1 * w + x1) * C4);
+    const float4 r = __ldg(y + idx);
+    float4 o;
+    o.x = hy * (hx * a00.x + lx * a01.x) + ly * (hx * a10.x + lx * a11.x) + r.x;
+    o.y = hy * (hx * a00.y + lx * a01.y) + ly * (hx * a10.y + lx * a11.y) + r.y;
+    o.z = hy * (hx * a00.z + lx * a01.z) + ly * (hx * a10.z + lx * a11.z) + r.z;
+    o.w = hy * (hx * a00.w + lx * a01.w) + ly * (hx * a10.w + lx * a11.w) + r.w;
+    out[idx] = o;
+}
+
 struct ProjParams {
     const float *ref;
     PtrList src;
@@ -1134,6 +1163,17 @@ int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, 
     dim3 grid((p.HW + 31) / 32, (C + 31) / 32, n * B);
     pack_nhwc_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(p);
     return launch_status("pack_nhwc");
+}
+
+int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, float *out_nhwc, int N, int h, int w, int C,
+                               void *stream) {
+    if (!x_nhwc || !y_nhwc || !out_nhwc) return fail(PMB200_EINVAL, "upsample2x_add_nhwc: null pointer");
+    if (N < 1 || h < 1 || w < 1 || C < 4 || C % 4 != 0) return fail(PMB200_EINVAL, "upsample2x_add_nhwc: bad size (C % 4 == 0)");
+    const size_t total = (size_t)N * 2 * h * 2 * w * (C / 4);
+    upsample2x_add_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(x_nhwc), reinterpret_cast<const float4 *>(y_nhwc),
+        reinterpret_cast<float4 *>(out_nhwc), N, h, w, C / 4);
+    return launch_status("upsample2x_add_nhwc");
 }
 
 int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth,

@@ -117,11 +117,20 @@ class FeatureNet(nn.Module):
         quarter = self._trunk(half, 5, 7)
         eighth = self._trunk(quarter, 8, 10)
         out: Dict[int, Tensor] = {3: self.output1(eighth)}
-        top = F.interpolate(eighth, scale_factor=2.0, mode="bilinear", align_corners=False) + self.inner1(quarter)
+        top = self._top_down(eighth, self.inner1(quarter))
         out[2] = self.output2(top)
-        top = F.interpolate(top, scale_factor=2.0, mode="bilinear", align_corners=False) + self.inner2(half)
+        top = self._top_down(top, self.inner2(half))
         out[1] = self.output3(top)
         return out
+
+    def _top_down(self, coarse: Tensor, lateral: Tensor) -> Tensor:
+        """bilinear x2 upsample + lateral add (reference net.py:60-66); one native launch on CUDA in eval mode
+        (ATen's channels-last bilinear kernel was the single largest launch of the forward)."""
+        if coarse.is_cuda and not self.training and not torch.is_grad_enabled():
+            from . import ops
+
+            return ops.upsample2x_add(coarse, lateral)
+        return F.interpolate(coarse, scale_factor=2.0, mode="bilinear", align_corners=False) + lateral
 
 
 class Refinement(nn.Module):
@@ -229,7 +238,12 @@ class PatchmatchNet(nn.Module):
         if self.training or not self.stack_views or len({im.shape for im in images}) != 1:
             return [self.feature(im) for im in images]
         n, b = len(images), images[0].shape[0]
-        x = torch.cat(images, dim=0)
+        first = images[0]
+        step = first.numel() * first.element_size()
+        if all(im.is_contiguous() and im.data_ptr() == first.data_ptr() + i * step for i, im in enumerate(images)):
+            x = torch.as_strided(first, (n * b,) + tuple(first.shape[1:]), first.stride())  # views of one buffer: no copy
+        else:
+            x = torch.cat(images, dim=0)
         if x.is_cuda:  # cuDNN NHWC kernels; the pyramid then comes out channels-last, which is the layout
             x = x.contiguous(memory_format=torch.channels_last)  # the fused PatchMatch kernels read in place
         stacked = self.feature(x)

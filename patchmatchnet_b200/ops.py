@@ -91,6 +91,25 @@ def pack_nhwc(maps: Sequence[Tensor]) -> Tensor:
     return out
 
 
+def upsample2x_add(x: Tensor, y: Tensor) -> Tensor:
+    """bilinear x2 upsample of `x` plus `y`, both channels-last 4-D CUDA tensors (logical NCHW)."""
+    N, C, h, w = x.shape
+    if y.shape != (N, C, 2 * h, 2 * w):
+        raise RuntimeError("upsample2x_add: y must be [N,C,2h,2w]")
+    for t, nm in ((x, "x"), (y, "y")):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"upsample2x_add: {nm} must be a CUDA float32 tensor (no CPU fallback)")
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    if not y.is_contiguous(memory_format=torch.channels_last):
+        y = y.contiguous(memory_format=torch.channels_last)
+    out = torch.empty_like(y, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = _native.lib().pmb200_upsample2x_add_nhwc(x.data_ptr(), y.data_ptr(), out.data_ptr(), N, h, w, C, _stream(x))
+    _native.check(rc, "upsample2x_add_nhwc")
+    return out
+
+
 def warp_corr(
     ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tensor, G: int, view_weights: Optional[Tensor] = None
 ) -> Tensor:

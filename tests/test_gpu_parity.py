@@ -94,6 +94,17 @@ def test_pack_nhwc():
         assert torch.equal(packed[i], m.permute(0, 2, 3, 1))
 
 
+def test_upsample2x_add_matches_interpolate():
+    for (N, C, h, w) in [(5, 64, 8, 10), (2, 32, 7, 9), (1, 16, 1, 3)]:
+        x = torch.randn(N, C, h, w, device=DEV).contiguous(memory_format=torch.channels_last)
+        y = torch.randn(N, C, 2 * h, 2 * w, device=DEV).contiguous(memory_format=torch.channels_last)
+        want = F.interpolate(x, scale_factor=2.0, mode="bilinear", align_corners=False) + y
+        got = ops.upsample2x_add(x, y)
+        assert got.shape == want.shape and maxabs(got, want) <= 1e-5
+        got2 = ops.upsample2x_add(x.contiguous(), y.contiguous())  # NCHW inputs are converted
+        assert maxabs(got2, want) <= 1e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # K-A
 # ------------------------------------------------------------------------------------------------
