@@ -324,23 +324,27 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const Wa
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps2 = 4;
 
-template <int C, int G, int EPI>
+// DC = hypothesis rows per warp pass (PPW * DC must be a multiple of 32), U2A = unique cells gathered per
+// lane group and phase-2a iteration (2 doubles the loads in flight per warp).
+template <int C, int G, int EPI, int DC, int U2A>
 __global__ void __launch_bounds__(kWarps2 * 32) warp_corr2_kernel(const WarpCorrParams p, const MlpParams mlp,
                                                                   float *__restrict__ sims_out) {
     using M = LaneMap<C, G>;
-    constexpr int NE = M::EPW / 32;    // footprints per lane (1, 2, 4)
+    constexpr int EPW = M::PPW * DC;   // footprints per warp pass
+    static_assert(EPW % 32 == 0, "PPW * DC must be a multiple of the warp size");
+    constexpr int NE = EPW / 32;       // footprints per lane (1, 2, 4)
     constexpr int RPK = 32 / M::PPW;   // hypothesis rows covered by one k (8, 4, 2)
     constexpr int TS = 4 * G + 4;      // floats per slot in s_T (padded: conflict-free LDS.128 across slots)
     constexpr bool kWeighted = (EPI == kEpiAgg || EPI == kEpiScore);
     __shared__ __align__(16) float s_ref[kWarps2][M::PPW * C];
-    __shared__ int2 s_u[kWarps2][M::EPW];
-    __shared__ __align__(16) float s_T[kWarps2][M::EPW * TS];
+    __shared__ int2 s_u[kWarps2][EPW];
+    __shared__ __align__(16) float s_T[kWarps2][EPW * TS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int HW = p.H * p.W;
     const int n0 = (blockIdx.x * kWarps2 + warp) * M::PPW;
     if (n0 >= HW) return;  // warp-level barriers only below
-    const int b = blockIdx.z, d0 = blockIdx.y * kChunk;
+    const int b = blockIdx.z, d0 = blockIdx.y * DC;
     const unsigned full = 0xffffffffu;
 
     // reference vectors of this warp's pixels -> shared memory, pre-scaled by 1/(C/G) (exact)
@@ -439,22 +443,36 @@ __global__ void __launch_bounds__(kWarps2 * 32) warp_corr2_kernel(const WarpCorr
         // ---- phase 2a: one unique cell per lane group ----
         const float4 *sv =
             reinterpret_cast<const float4 *>(p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C) + li * 2;
-        for (int base = 0; base < nu; base += M::PPW) {
-            const int s = base + grp;
-            if (s < nu) {
-                const int2 u = s_u[warp][s];
-                float r[8];
-                const float4 *rr = reinterpret_cast<const float4 *>(s_ref[warp] + u.y * C) + li * 2;
-                const float4 r0 = rr[0], r1 = rr[1];
-                r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
-                r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-                float T[4][M::GPL];
-                gather_dot<C, G>(sv, u.x, p.Ws, r, T);
-                float *tp = s_T[warp] + s * TS + li * M::GPL;
+        for (int base = 0; base < nu; base += M::PPW * U2A) {
+            int2 u[U2A];
+            bool on[U2A];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if constexpr (M::GPL == 1) tp[t * G] = T[t][0];
-                    else *reinterpret_cast<float2 *>(tp + t * G) = make_float2(T[t][0], T[t][1]);
+            for (int j = 0; j < U2A; ++j) {
+                const int s = base + j * M::PPW + grp;
+                on[j] = s < nu;
+                u[j] = on[j] ? s_u[warp][s] : make_int2(0, 0);
+            }
+            float T[U2A][4][M::GPL];
+#pragma unroll
+            for (int j = 0; j < U2A; ++j) {
+                if (on[j]) {
+                    float r[8];
+                    const float4 *rr = reinterpret_cast<const float4 *>(s_ref[warp] + u[j].y * C) + li * 2;
+                    const float4 r0 = rr[0], r1 = rr[1];
+                    r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
+                    r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                    gather_dot<C, G>(sv, u[j].x, p.Ws, r, T[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U2A; ++j) {
+                if (on[j]) {
+                    float *tp = s_T[warp] + (base + j * M::PPW + grp) * TS + li * M::GPL;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if constexpr (M::GPL == 1) tp[t * G] = T[j][t][0];
+                        else *reinterpret_cast<float2 *>(tp + t * G) = make_float2(T[j][t][0], T[j][t][1]);
+                    }
                 }
             }
         }
@@ -1107,9 +1125,47 @@ __global__ void adaptive_eval_kernel(const EvalParams p) {
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // PMB200_WARP_CORR_V1=1 selects the first-generation K-A kernel (kept for A/B measurements)
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
 bool use_v1() {
     const char *e = getenv("PMB200_WARP_CORR_V1");  // read per call so tests/benchmarks can toggle it
     return e && e[0] == '1';
+}
+
+template <int C, int G, int EPI, int DC, int U2A>
+void launch_wc2(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    const int HW = p.H * p.W;
+    constexpr int pix_per_block = kWarps2 * LaneMap<C, G>::PPW;
+    dim3 grid((HW + pix_per_block - 1) / pix_per_block, (p.D + DC - 1) / DC, p.B);
+    warp_corr2_kernel<C, G, EPI, DC, U2A><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+}
+
+// Second-generation K-A launch.  Rows per warp pass (DC) and gather unroll (U2A) default to the values
+// measured best on B200 (profiles/); PMB200_KA_DC / PMB200_KA_U2A override them for the score epilogue
+// only (tuning sweeps, tools/kbench.py).
+template <int C, int G, int EPI>
+void launch_wc2_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    constexpr int PPW = LaneMap<C, G>::PPW;
+    if constexpr (EPI == kEpiScore) {
+        const int dc = env_int("PMB200_KA_DC", 0), u2 = env_int("PMB200_KA_U2A", 0);
+        if (dc != 0 || u2 != 0) {
+            const int d = dc ? dc : 8, u = u2 ? u2 : 1;
+#define PMB200_TRY(DD, UU)                                                       \
+    if (d == DD && u == UU) {                                                    \
+        if constexpr ((PPW * DD) % 32 == 0 && PPW * DD * (4 * G + 4) * 4 * kWarps2 <= 40 * 1024) { \
+            launch_wc2<C, G, EPI, DD, UU>(p, m, sims_out, st);                   \
+            return;                                                              \
+        }                                                                        \
+    }
+            PMB200_TRY(2, 1) PMB200_TRY(2, 2) PMB200_TRY(4, 1) PMB200_TRY(4, 2)
+            PMB200_TRY(8, 1) PMB200_TRY(8, 2) PMB200_TRY(16, 1) PMB200_TRY(16, 2)
+#undef PMB200_TRY
+        }
+    }
+    launch_wc2<C, G, EPI, 8, 1>(p, m, sims_out, st);
 }
 
 }  // namespace
@@ -1203,9 +1259,8 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
             if (fused) warp_corr_kernel<CC, GG, kEpiAgg><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());   \
             else warp_corr_kernel<CC, GG, kEpiSims><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());       \
         } else {                                                                                   \
-            dim3 grid((HW + kWarps2 * LaneMap<CC, GG>::PPW - 1) / (kWarps2 * LaneMap<CC, GG>::PPW), nchunk, B);   \
-            if (fused) warp_corr2_kernel<CC, GG, kEpiAgg><<<grid, kWarps2 * 32, 0, st>>>(p, MlpParams(), nullptr); \
-            else warp_corr2_kernel<CC, GG, kEpiSims><<<grid, kWarps2 * 32, 0, st>>>(p, MlpParams(), nullptr);     \
+            if (fused) launch_wc2_auto<CC, GG, kEpiAgg>(p, MlpParams(), nullptr, st);                 \
+            else launch_wc2_auto<CC, GG, kEpiSims>(p, MlpParams(), nullptr, st);                      \
         }                                                                                          \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_WC(64, 8);
@@ -1252,9 +1307,8 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
             if (epi == kEpiScore) warp_corr_kernel<CC, GG, kEpiScore><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m); \
             else warp_corr_kernel<CC, GG, kEpiViewW><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m);  \
         } else {                                                                                   \
-            dim3 grid((HW + kWarps2 * LaneMap<CC, GG>::PPW - 1) / (kWarps2 * LaneMap<CC, GG>::PPW), nchunk, B);   \
-            if (epi == kEpiScore) warp_corr2_kernel<CC, GG, kEpiScore><<<grid, kWarps2 * 32, 0, st>>>(p, m, nullptr); \
-            else warp_corr2_kernel<CC, GG, kEpiViewW><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);             \
+            if (epi == kEpiScore) launch_wc2_auto<CC, GG, kEpiScore>(p, m, nullptr, st);              \
+            else launch_wc2_auto<CC, GG, kEpiViewW>(p, m, sims_out, st);                              \
         }                                                                                          \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_WH(64, 8);

@@ -228,6 +228,7 @@ class PatchmatchNet(nn.Module):
                 ),
             )
         self.upsample_net = Refinement()
+        self.register_buffer("_stage_scales", torch.tensor([0.125, 0.25, 0.5]).view(3, 1, 1, 1, 1), persistent=False)
         # eval mode: push all views through FeatureNet as one batch (set False to go view by view)
         self.stack_views = True
 
@@ -275,12 +276,21 @@ class PatchmatchNet(nn.Module):
         view_weights = torch.empty(0, device=dev)
         per_stage: Dict[int, List[Tensor]] = {}
 
+        all_proj = None
+        if intrinsics.is_cuda:  # the three stages' projection matrices in one batch (5 launches instead of 15)
+            K3 = intrinsics.unsqueeze(0).repeat(3, 1, 1, 1, 1)
+            K3[:, :, :, :2] *= self._stage_scales
+            all_proj = extrinsics.unsqueeze(0).repeat(3, 1, 1, 1, 1)
+            all_proj[:, :, :, :3, :4] = torch.matmul(K3, extrinsics[:, :, :3, :4])
         scale = 0.125
         for stage in (3, 2, 1):
-            K = intrinsics.clone()
-            K[:, :, :2] *= scale
-            proj = extrinsics.clone()
-            proj[:, :, :3, :4] = torch.matmul(K, extrinsics[:, :, :3, :4])
+            if all_proj is not None:
+                proj = all_proj[3 - stage]
+            else:  # reference order of operations (net.py:226-231), kept bit-exact on the CPU
+                K = intrinsics.clone()
+                K[:, :, :2] *= scale
+                proj = extrinsics.clone()
+                proj[:, :, :3, :4] = torch.matmul(K, extrinsics[:, :, :3, :4])
             projs = torch.unbind(proj, 1)
             scale *= 2.0
             depths, score, view_weights = getattr(self, f"patchmatch_{stage}")(
