@@ -168,6 +168,20 @@ class Refinement(nn.Module):
         return d * span + lo
 
 
+def _adjacent_views(tensors) -> bool:
+    """True when the tensors are equally shaped contiguous views laid out back to back in ONE storage
+    (e.g. slices of a stacked buffer), so that they can be re-viewed as one batch without a copy."""
+    first = tensors[0]
+    if not first.is_contiguous():
+        return False
+    store = first.untyped_storage().data_ptr()
+    for i, t in enumerate(tensors):
+        if (t.shape != first.shape or not t.is_contiguous() or t.untyped_storage().data_ptr() != store
+                or t.storage_offset() != first.storage_offset() + i * first.numel()):
+            return False
+    return True
+
+
 def _round_dims_to_8(images: List[Tensor], intrinsics: Tensor) -> Tuple[List[Tensor], Tensor, int, int]:
     """reference models/net.py:304-318 (mutates ``intrinsics`` in place like the reference)."""
     H0, W0 = images[0].shape[-2:]
@@ -240,8 +254,7 @@ class PatchmatchNet(nn.Module):
             return [self.feature(im) for im in images]
         n, b = len(images), images[0].shape[0]
         first = images[0]
-        step = first.numel() * first.element_size()
-        if all(im.is_contiguous() and im.data_ptr() == first.data_ptr() + i * step for i, im in enumerate(images)):
+        if _adjacent_views(images):
             x = torch.as_strided(first, (n * b,) + tuple(first.shape[1:]), first.stride())  # views of one buffer: no copy
         else:
             x = torch.cat(images, dim=0)

@@ -61,14 +61,15 @@ def relative_projection(ref_proj: Tensor, src_projs: Sequence[Tensor]) -> Tensor
 
 
 def _is_packed_nhwc(maps: Sequence[Tensor]) -> bool:
-    """True when the maps are channels-last and already adjacent in memory (e.g. slices of one
+    """True when the maps are channels-last views laid out back to back in ONE storage (e.g. slices of one
     stacked channels-last FeatureNet output), so that packing would be a no-op."""
     first = maps[0]
     B, C, H, W = first.shape
     want = (H * W * C, 1, W * C, C)
-    step = B * H * W * C * first.element_size()
+    store = first.untyped_storage().data_ptr()
     for i, m in enumerate(maps):
-        if m.shape != first.shape or m.stride() != want or m.data_ptr() != first.data_ptr() + i * step:
+        if (m.shape != first.shape or m.stride() != want or m.untyped_storage().data_ptr() != store
+                or m.storage_offset() != first.storage_offset() + i * first.numel()):
             return False
     return True
 

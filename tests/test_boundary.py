@@ -85,3 +85,28 @@ def test_drops_into_unmodified_reference_net(reference_models, golden_weights, m
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
         # FeatureNet (reference code) runs; the first PatchMatch call refuses the CPU tensors
         net(inp["images"], inp["intrinsics"], inp["extrinsics"], inp["depth_min"], inp["depth_max"])
+
+
+def test_zero_copy_view_detection_needs_one_storage():
+    """Back-to-back addresses are not enough (the caching allocator can place separate tensors adjacently):
+    the zero-copy re-view is only taken for views of ONE storage."""
+    from patchmatchnet_b200 import ops
+    from patchmatchnet_b200.net import _adjacent_views
+
+    stacked = torch.arange(3 * 2 * 4 * 5 * 6, dtype=torch.float32).view(6, 4, 5, 6)
+    views = [stacked[0:2], stacked[2:4], stacked[4:6]]
+    assert _adjacent_views(views)
+    assert not _adjacent_views([v.clone() for v in views])
+    assert not _adjacent_views([views[0], views[2], views[1]])
+    net = PatchmatchNet(**pm_cases.NET_KWARGS, patchmatch_cls=pm_oracle.PatchMatchOracle).eval()
+    imgs = torch.rand(3, 1, 3, 16, 24)
+    with torch.no_grad():
+        a = net.extract_features([imgs[0], imgs[1], imgs[2]])           # views of one buffer
+        b = net.extract_features([imgs[i].clone() for i in range(3)])   # separate tensors -> torch.cat
+    for fa, fb in zip(a, b):
+        for k in fa:
+            assert torch.equal(fa[k], fb[k])
+    cl = stacked.contiguous(memory_format=torch.channels_last)
+    assert ops._is_packed_nhwc([cl[0:2], cl[2:4], cl[4:6]])
+    assert not ops._is_packed_nhwc([cl[0:2].clone(memory_format=torch.channels_last), cl[2:4], cl[4:6]])
+    assert not ops._is_packed_nhwc(views)
