@@ -229,16 +229,72 @@ def warp_corr_minimum_bytes(V, B, C, G, H, W, D):
     return 4 * B * H * W * (C * (1 + V) + D + V + G * D)
 
 
-def time_warp_corr_calls(net, dev_inputs, peak_gbs, flush, iters=20):
-    """Re-run every fused warp+correlation launch of one forward in isolation, L2 flushed before each,
-    CUDA events on the launching (current) stream.  Covers the three entry points that run the K-A core:
-    warp_corr (similarities out), warp_corr_score (SimilarityNet head fused), warp_corr_view_weights
-    (PixelwiseNet fused)."""
+KA_ENTRIES = ("warp_corr", "warp_corr_score", "warp_corr_view_weights")
+
+
+def _ka_row(n, a, k, times_s, peak_gbs):
+    ref, src, depth, G = a[0], a[1], a[3], a[4]
+    B, H, W, C = ref.shape
+    V, D = src.shape[0], depth.shape[1]
+    t = statistics.mean(times_s)
+    alg = warp_corr_algorithmic_bytes(V, B, C, G, H, W, D)
+    per_view_out = n == "warp_corr" and (len(a) < 6 or a[5] is None) and k.get("view_weights") is None
+    keeps_sims = n == "warp_corr_view_weights" and (k.get("keep_sims") or (len(a) > 6 and a[6]))
+    out_floats = {"warp_corr": G * D * (V if per_view_out else 1), "warp_corr_score": D,
+                  "warp_corr_view_weights": V + (G * D * V if keeps_sims else 0)}[n]
+    return {"entry": n, "shape": f"C{C} G{G} D{D} {H}x{W} V{V} B{B}", "us": 1e6 * t, "us_min": 1e6 * min(times_s),
+            "algorithmic_bytes": alg, "minimum_bytes": 4 * B * H * W * (C * (1 + V) + D + V + out_floats),
+            "achieved_gbs": alg / t / 1e9, "frac": alg / t / 1e9 / peak_gbs}
+
+
+def time_warp_corr_in_step(net, dev_inputs, peak_gbs, flush, steps=10, warmup=3):
+    """Launch durations of the fused warp+correlation kernel measured LIVE inside timed steps: eager forwards
+    (no graph, so events can bracket a launch), L2 flushed between steps -- not between kernels, the producer
+    kernels of the same step leave their outputs in L2 exactly as in production -- one CUDA-event pair per K-A
+    launch on the launching stream.  Covers warp_corr / warp_corr_score / warp_corr_view_weights."""
+    from patchmatchnet_b200 import ops
+
+    origs = {n: getattr(ops, n) for n in KA_ENTRIES}
+    record = []  # (name, args, kwargs, start_event, end_event) per launch of the current step
+
+    def make_spy(n):
+        def spy(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = origs[n](*a, **k)
+            e1.record()
+            record.append((n, a, k, e0, e1))
+            return out
+        return spy
+
+    for n in KA_ENTRIES:
+        setattr(ops, n, make_spy(n))
+    per_call = []
+    try:
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                record.clear()
+                flush()
+                torch.manual_seed(0)
+                net(*dev_inputs())
+                torch.cuda.synchronize()
+                if it >= warmup:
+                    for i, (n, a, k, e0, e1) in enumerate(record):
+                        if len(per_call) <= i:
+                            per_call.append((n, a, k, []))
+                        per_call[i][3].append(e0.elapsed_time(e1) * 1e-3)
+    finally:
+        for n in KA_ENTRIES:
+            setattr(ops, n, origs[n])
+    return [_ka_row(n, a, k, ts, peak_gbs) for (n, a, k, ts) in per_call]
+
+
+def time_warp_corr_isolated(net, dev_inputs, peak_gbs, flush, iters=10):
+    """The same launches re-run one at a time with L2 flushed before EACH launch (cold inputs from HBM)."""
     from patchmatchnet_b200 import ops
 
     calls = []
-    names = ("warp_corr", "warp_corr_score", "warp_corr_view_weights")
-    origs = {n: getattr(ops, n) for n in names}
+    origs = {n: getattr(ops, n) for n in KA_ENTRIES}
 
     def make_spy(n):
         def spy(*a, **k):
@@ -246,23 +302,20 @@ def time_warp_corr_calls(net, dev_inputs, peak_gbs, flush, iters=20):
             return origs[n](*a, **k)
         return spy
 
-    for n in names:
+    for n in KA_ENTRIES:
         setattr(ops, n, make_spy(n))
     try:
         with torch.no_grad():
             torch.manual_seed(0)
             net(*dev_inputs())
     finally:
-        for n in names:
+        for n in KA_ENTRIES:
             setattr(ops, n, origs[n])
     torch.cuda.synchronize()
     rows = []
     for (n, a, k) in calls:
-        ref, src, depth, G = a[0], a[1], a[3], a[4]
-        B, H, W, C = ref.shape
-        V, D = src.shape[0], depth.shape[1]
         fn = origs[n]
-        for _ in range(3):
+        for _ in range(2):
             fn(*a, **k)
         ts = []
         for _ in range(iters):
@@ -273,16 +326,7 @@ def time_warp_corr_calls(net, dev_inputs, peak_gbs, flush, iters=20):
             e1.record()
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)
-        t = statistics.mean(ts)
-        alg = warp_corr_algorithmic_bytes(V, B, C, G, H, W, D)
-        out_floats = {"warp_corr": G * D * (V if (len(a) < 6 or a[5] is None) and "view_weights" not in k else 1),
-                      "warp_corr_score": D, "warp_corr_view_weights": V}[n]
-        rows.append({
-            "entry": n, "shape": f"C{C} G{G} D{D} {H}x{W} V{V} B{B}",
-            "us": 1e6 * t, "us_min": 1e6 * min(ts), "algorithmic_bytes": alg,
-            "minimum_bytes": 4 * B * H * W * (C * (1 + V) + D + V + out_floats),
-            "achieved_gbs": alg / t / 1e9, "frac": alg / t / 1e9 / peak_gbs,
-        })
+        rows.append(_ka_row(n, a, k, ts, peak_gbs))
     return rows
 
 
@@ -406,24 +450,26 @@ def main() -> None:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    roofline, detail, cpu_baseline = None, None, None
+    roofline, detail, detail_cold, cpu_baseline = None, None, None, None
     if rank == 0:
         dev_inputs = lambda: ([im.clone() for im in d_in["images"]], d_in["intrinsics"].clone(), d_in["extrinsics"].clone(),
                               d_in["depth_min"], d_in["depth_max"])
-        detail = time_warp_corr_calls(net, dev_inputs, peak_gbs, flush)
+        detail = time_warp_corr_in_step(net, dev_inputs, peak_gbs, flush, steps=max(5, args.steps // 2))
+        detail_cold = time_warp_corr_isolated(net, dev_inputs, peak_gbs, flush)
         if detail:
             top = max(detail, key=lambda r: r["us"])
             traffic = None
             tfile = os.path.join(REPO, "profiles", "warp_corr_traffic.json")
             if os.path.exists(tfile):
                 try:
-                    traffic = json.load(open(tfile)).get(top["shape"])
+                    traffic = json.load(open(tfile)).get(top["entry"] + " " + top["shape"])
                 except Exception:
                     traffic = None
             roofline = {"bound": "hbm", "kernel": "warp_corr_kernel (fused warp+bilinear gather+group correlation+view aggregation)",
                         "launch": top["entry"] + " " + top["shape"], "achieved": top["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
                         "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
                         "us_per_launch": top["us"],
+                        "how": "CUDA-event pair around each launch inside timed eager steps (L2 flushed between steps)",
                         "all_launches_weighted_frac": sum(r["algorithmic_bytes"] for r in detail) / sum(r["us"] * 1e-6 for r in detail) / 1e9 / peak_gbs}
         if world == 1 and not args.no_cpu_baseline:
             step, cores = cpu_forward_timer(H, W, N)
@@ -448,7 +494,8 @@ def main() -> None:
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "native_kernels_per_step": {k: v // max(1, forwards_counted) for k, v in sorted(lc.by_name.items())},
             "clocks": clocks,
-            "roofline": roofline, "roofline_detail": detail, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_detail": detail, "roofline_detail_cold_isolated": detail_cold if rank == 0 else None,
+            "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
