@@ -545,6 +545,235 @@ __global__ void __launch_bounds__(kWarps2 * 32) warp_corr2_kernel(const WarpCorr
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K-A, third generation.  Same three phases as the second, with the profile-driven changes
+// (profiles/r1_run3_ncu.md: phase 1 was 30 % of the issued instructions, the gather loop took 41 % of
+// the stall samples):
+//   * unique cells are numbered PER PIXEL in "layers" (slot = layer * PPW + pixel) straight from the
+//     ballot mask with one popc -- no shuffle prefix scan; every lane group then gathers the cells of
+//     its OWN pixel, so the reference vector stays in registers (no shared-memory copy of it);
+//   * the gather loop is software pipelined two deep: the taps of layer j+1 are in flight while layer j
+//     is being dotted with the reference vector;
+//   * projection with MUFU.RCP instead of two IEEE divisions, footprint routine with an interior fast path.
+// ------------------------------------------------------------------------------------------
+template <int PPW>
+__device__ __forceinline__ unsigned pixel_lane_mask(int pixel) {
+    constexpr unsigned base = PPW == 4 ? 0x11111111u : (PPW == 8 ? 0x01010101u : 0x00010001u);
+    return base << pixel;
+}
+
+template <int C, int G>
+__device__ __forceinline__ void load_taps(const float4 *__restrict__ map_lane, int key, int cols, float4 (&t)[8]) {
+    constexpr int V4 = C / 4;
+    const int r0 = pm::cell_r0(key), dx = pm::cell_dx(key), dy = pm::cell_dy(key);
+    const float4 *t0 = map_lane + (size_t)r0 * V4;
+    const float4 *t1 = t0 + dx * V4;
+    const float4 *t2 = t0 + (size_t)dy * cols * V4;
+    const float4 *t3 = t2 + dx * V4;
+    t[0] = __ldg(t0); t[1] = __ldg(t0 + 1);
+    t[2] = __ldg(t1); t[3] = __ldg(t1 + 1);
+    t[4] = __ldg(t2); t[5] = __ldg(t2 + 1);
+    t[6] = __ldg(t3); t[7] = __ldg(t3 + 1);
+}
+
+template <int C, int G>
+__device__ __forceinline__ void dot_store(const float4 (&t)[8], const float (&r)[8], float *__restrict__ tp) {
+    using M = LaneMap<C, G>;
+    auto lo = [&](const float4 &q) { return r[0] * q.x + r[1] * q.y + r[2] * q.z + r[3] * q.w; };
+    auto hi = [&](const float4 &q) { return r[4] * q.x + r[5] * q.y + r[6] * q.z + r[7] * q.w; };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if constexpr (M::GPL == 1) tp[k * G] = lo(t[2 * k]) + hi(t[2 * k + 1]);
+        else *reinterpret_cast<float2 *>(tp + k * G) = make_float2(lo(t[2 * k]), hi(t[2 * k + 1]));
+    }
+}
+
+template <int C, int G, int EPI, int DC, int PIPE>
+__global__ void __launch_bounds__(kWarps2 * 32, PIPE ? 4 : 6) warp_corr3_kernel(const WarpCorrParams p, const MlpParams mlp,
+                                                                  float *__restrict__ sims_out) {
+    using M = LaneMap<C, G>;
+    constexpr int EPW = M::PPW * DC;   // footprints per warp pass
+    static_assert(EPW % 32 == 0, "PPW * DC must be a multiple of the warp size");
+    constexpr int NE = EPW / 32;       // footprints per lane
+    constexpr int RPK = 32 / M::PPW;   // hypothesis rows covered by one k
+    constexpr int TS = 4 * G + 4;      // floats per slot in s_T
+    constexpr bool kWeighted = (EPI == kEpiAgg || EPI == kEpiScore);
+    __shared__ int s_key[kWarps2][EPW];
+    __shared__ __align__(16) float s_T[kWarps2][EPW * TS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = p.H * p.W;
+    const int n0 = (blockIdx.x * kWarps2 + warp) * M::PPW;
+    if (n0 >= HW) return;  // warp-level barriers only below
+    const int b = blockIdx.z, d0 = blockIdx.y * DC;
+    const unsigned full = 0xffffffffu;
+
+    // gather mapping: lane group `grp` works on pixel n0+grp, lane `li` of the group owns channels 8*li..8*li+7
+    const int li = lane % M::LPP, grp = lane / M::LPP;
+    float r[8];
+    load_reference<C, G>(p.ref, (size_t)b * HW + min(n0 + grp, HW - 1), li, r);
+    const unsigned gmask = pixel_lane_mask<M::PPW>(grp);
+
+    // footprint mapping: all footprints of a lane belong to pixel n0+pi, rows row0 + k*RPK
+    const int pi = lane % M::PPW, row0 = lane / M::PPW;
+    const unsigned fmask = pixel_lane_mask<M::PPW>(pi);
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    const int n = n0 + pi;
+    const bool live = n < HW;
+    const int nc = live ? n : HW - 1;
+    const float px_x = (float)(nc % p.W), px_y = (float)(nc / p.W);
+    float dep[NE];
+    bool ev[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int d = d0 + row0 + k * RPK;
+        ev[k] = live && d < p.D;
+        dep[k] = ev[k] ? __ldg(p.depth + ((size_t)b * p.D + d) * HW + n) : 1.0f;
+    }
+    float acc[NE][G];
+#pragma unroll
+    for (int k = 0; k < NE; ++k)
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[k][g] = 0.0f;
+    float wsum = 1e-5f;  // reference models/patchmatch.py:192
+
+    for (int v = 0; v < p.V; ++v) {
+        float rt[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) rt[i] = __ldg(p.rt + ((size_t)v * p.B + b) * 12 + i);
+        const pm::Ray ray = pm::pixel_ray(rt, px_x, px_y);
+
+        // ---- phase 1: footprints, per-pixel layered numbering of the unique cells ----
+        float4 w[NE];
+        int key[NE], slot[NE];
+        int mine_before = 0;   // unique cells of my footprint pixel found in earlier k
+        int cg = 0;            // unique cells of my gather pixel
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            pm::Cell c;
+            c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
+            c.key = pm::kKeyNone;
+            if (ev[k]) {
+                float uu, vv;
+                pm::project_fast(ray, rt, dep[k], p.W, p.H, p.sx, p.sy, &uu, &vv);
+                c = pm::zero_pad_cell_fast(uu, vv, p.Hs, p.Ws);
+            }
+            w[k] = make_float4(c.w00, c.w01, c.w10, c.w11);
+            key[k] = c.key;
+            int pk = __shfl_up_sync(full, key[k], M::PPW);  // previous hypothesis row, same pixel
+            if (k > 0) {
+                const int ck = __shfl_sync(full, key[k > 0 ? k - 1 : 0], 32 - M::PPW + pi);
+                if (lane < M::PPW) pk = ck;
+            } else if (lane < M::PPW) {
+                pk = pm::kKeyNone;
+            }
+            const bool isnew = key[k] != pm::kKeyNone && key[k] != pk;
+            const unsigned m = __ballot_sync(full, isnew);
+            const int c_incl = mine_before + __popc(m & fmask & le_mask);  // unique cells of my pixel up to my row
+            slot[k] = (c_incl - 1) * M::PPW + pi;                          // >= 0 whenever key != none
+            if (isnew) s_key[warp][slot[k]] = key[k];
+            mine_before += __popc(m & fmask);
+            cg += __popc(m & gmask);
+        }
+        __syncwarp();
+
+        float wv = 1.0f;
+        if (kWeighted) {
+            wv = __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc);
+            wsum += wv;
+        }
+
+        // ---- phase 2a: gather layer by layer, two layers in flight ----
+        const float4 *sv =
+            reinterpret_cast<const float4 *>(p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C) + li * 2;
+        const int maxc = __reduce_max_sync(full, cg);
+        if constexpr (PIPE) {
+            float4 ta[8], tb[8];
+            float *tbase = s_T[warp] + grp * TS + li * M::GPL;
+            if (cg > 0) load_taps<C, G>(sv, s_key[warp][grp], p.Ws, ta);
+            for (int j = 0; j < maxc; j += 2) {
+                if (j + 1 < cg) load_taps<C, G>(sv, s_key[warp][(j + 1) * M::PPW + grp], p.Ws, tb);
+                if (j < cg) dot_store<C, G>(ta, r, tbase + j * M::PPW * TS);
+                if (j + 2 < cg) load_taps<C, G>(sv, s_key[warp][(j + 2) * M::PPW + grp], p.Ws, ta);
+                if (j + 1 < cg) dot_store<C, G>(tb, r, tbase + (j + 1) * M::PPW * TS);
+            }
+        } else {
+            float *tbase = s_T[warp] + grp * TS + li * M::GPL;
+            for (int j = 0; j < maxc; ++j) {
+                if (j < cg) {
+                    float4 ta[8];
+                    load_taps<C, G>(sv, s_key[warp][j * M::PPW + grp], p.Ws, ta);
+                    dot_store<C, G>(ta, r, tbase + j * M::PPW * TS);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2b: one footprint per lane ----
+        float best = -INFINITY;  // kEpiViewW only
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            float sim[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) sim[g] = 0.0f;
+            if (key[k] != pm::kKeyNone) {
+                const float4 *tp = reinterpret_cast<const float4 *>(s_T[warp] + slot[k] * TS);
+#pragma unroll
+                for (int q = 0; q < G / 4; ++q) {
+                    const float4 t0 = tp[q], t1 = tp[G / 4 + q], t2 = tp[2 * (G / 4) + q], t3 = tp[3 * (G / 4) + q];
+                    sim[4 * q + 0] = w[k].x * t0.x + w[k].y * t1.x + w[k].z * t2.x + w[k].w * t3.x;
+                    sim[4 * q + 1] = w[k].x * t0.y + w[k].y * t1.y + w[k].z * t2.y + w[k].w * t3.y;
+                    sim[4 * q + 2] = w[k].x * t0.z + w[k].y * t1.z + w[k].z * t2.z + w[k].w * t3.z;
+                    sim[4 * q + 3] = w[k].x * t0.w + w[k].y * t1.w + w[k].z * t2.w + w[k].w * t3.w;
+                }
+            }
+            if (kWeighted) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[k][g] = fmaf(sim[g], wv, acc[k][g]);
+            } else {
+                const int d = d0 + row0 + k * RPK;
+                if ((EPI == kEpiSims || sims_out != nullptr) && ev[k]) {
+                    float *o = (EPI == kEpiSims ? p.out : sims_out) + ((((size_t)v * p.B + b) * G) * p.D + d) * HW + n;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = sim[g];
+                }
+                if (EPI == kEpiViewW && ev[k]) best = fmaxf(best, mlp_eval<G>(mlp, sim));
+            }
+        }
+        if (EPI == kEpiViewW) {
+#pragma unroll
+            for (int off = M::PPW; off < 32; off <<= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
+            if (lane < M::PPW && live && best > -INFINITY) {
+                const float sg = 1.0f / (1.0f + expf(-best));
+                atomicMax(reinterpret_cast<int *>(p.out + ((size_t)b * p.V + v) * HW + n), __float_as_int(sg));
+            }
+        }
+        __syncwarp();  // s_key / s_T are rewritten by the next view
+    }
+
+    if (EPI == kEpiAgg) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const int d = d0 + row0 + k * RPK;
+            if (ev[k]) {
+                float *o = p.out + (((size_t)b * G) * p.D + d) * HW + n;
+#pragma unroll
+                for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = acc[k][g] / wsum;
+            }
+        }
+    } else if (EPI == kEpiScore) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const int d = d0 + row0 + k * RPK;
+            float x[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) x[g] = acc[k][g] / wsum;
+            const float y = mlp_eval<G>(mlp, x);
+            if (ev[k]) p.out[((size_t)b * p.D + d) * HW + n] = y;
+        }
+    }
+}
+
 // sum_v sims[v]*w_v / (1e-5 + sum_v w_v) -> SimilarityNet head -> score [B,D,H,W]   (first stage-3 iteration, eval)
 template <int G>
 __global__ void aggregate_score_kernel(const float *__restrict__ sims, const float *__restrict__ vw,
@@ -1146,8 +1375,42 @@ void launch_wc2(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
 // Second-generation K-A launch.  Rows per warp pass (DC) and gather unroll (U2A) default to the values
 // measured best on B200 (profiles/); PMB200_KA_DC / PMB200_KA_U2A override them for the score epilogue
 // only (tuning sweeps, tools/kbench.py).
+template <int C, int G, int EPI, int DC>
+void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    const int HW = p.H * p.W;
+    constexpr int pix_per_block = kWarps2 * LaneMap<C, G>::PPW;
+    dim3 grid((HW + pix_per_block - 1) / pix_per_block, (p.D + DC - 1) / DC, p.B);
+    if (env_int("PMB200_KA_PIPE", 0)) warp_corr3_kernel<C, G, EPI, DC, 1><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+    else warp_corr3_kernel<C, G, EPI, DC, 0><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+}
+
+// Third-generation launch: rows per warp pass chosen per lane map (more rows = more reuse along the
+// hypothesis axis, fewer = less shared memory / registers per warp); PMB200_KA_DC overrides (score epilogue).
+template <int C, int G, int EPI>
+void launch_wc3_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    constexpr int PPW = LaneMap<C, G>::PPW;
+    constexpr int kDefault = PPW == 4 ? 16 : (PPW == 8 ? 8 : 4);
+    if constexpr (EPI == kEpiScore) {
+        const int d = env_int("PMB200_KA_DC", 0);
+#define PMB200_TRY3(DD)                                                                                  \
+    if (d == DD) {                                                                                       \
+        if constexpr ((PPW * DD) % 32 == 0 && PPW * DD * (4 * G + 4) * 4 * kWarps2 <= 40 * 1024) {       \
+            launch_wc3<C, G, EPI, DD>(p, m, sims_out, st);                                               \
+            return;                                                                                      \
+        }                                                                                                \
+    }
+        PMB200_TRY3(2) PMB200_TRY3(4) PMB200_TRY3(8) PMB200_TRY3(16)
+#undef PMB200_TRY3
+    }
+    launch_wc3<C, G, EPI, (EPI == kEpiScore ? kDefault : (PPW == 4 ? 8 : kDefault))>(p, m, sims_out, st);
+}
+
 template <int C, int G, int EPI>
 void launch_wc2_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    if (env_int("PMB200_KA_GEN", 3) == 3) {
+        launch_wc3_auto<C, G, EPI>(p, m, sims_out, st);
+        return;
+    }
     constexpr int PPW = LaneMap<C, G>::PPW;
     if constexpr (EPI == kEpiScore) {
         const int dc = env_int("PMB200_KA_DC", 0), u2 = env_int("PMB200_KA_U2A", 0);

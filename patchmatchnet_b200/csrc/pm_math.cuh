@@ -118,6 +118,43 @@ PM_HD void project(const Ray &r, const float *rt, float d, int W, int H, float s
     *v = (Y / Z) * sy;
 }
 
+#if defined(__CUDACC__)
+// Device-only variants used by the third-generation K-A kernel: division by MUFU.RCP (<= 2 ulp, i.e.
+// < 2e-4 px at 640 px -- far below the fp32 noise of the reference's own normalise/un-normalise round
+// trip) and a footprint routine with a branch-free interior fast path.
+__device__ __forceinline__ void project_fast(const Ray &r, const float *rt, float d, int W, int H, float sx, float sy,
+                                             float *u, float *v) {
+    float X = fmaf(r.ax, d, rt[9]);
+    float Y = fmaf(r.ay, d, rt[10]);
+    float Z = fmaf(r.az, d, rt[11]);
+    if (Z <= 1e-3f) {
+        X = (float)W;
+        Y = (float)H;
+        Z = 1.0f;
+    }
+    const float iz = __fdividef(1.0f, Z);
+    *u = X * iz * sx;
+    *v = Y * iz * sy;
+}
+
+__device__ __forceinline__ Cell zero_pad_cell_fast(float u, float v, int rows, int cols) {
+    const float xf = floorf(u), yf = floorf(v);
+    const float fx = u - xf, fy = v - yf;
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    // interior: all four taps inside.  (NaN / huge coordinates fail the comparisons and take the general path.)
+    if (xf >= 0.0f && xf < (float)(cols - 1) && yf >= 0.0f && yf < (float)(rows - 1)) {
+        Cell c;
+        c.w00 = gx * gy;
+        c.w01 = fx * gy;
+        c.w10 = gx * fy;
+        c.w11 = fx * fy;
+        c.key = ((int)yf * cols + (int)xf) | (1 << kKeyDxShift) | (1 << kKeyDyShift);
+        return c;
+    }
+    return zero_pad_cell(u, v, rows, cols);
+}
+#endif
+
 // Fixed neighbour offset (dy, dx) tables, reference models/patchmatch.py:331-392.
 // Returns false for the counts the reference raises NotImplementedError on.
 PM_HD bool neighbour_offset(bool evaluation, int count, int dilation, int k, int *dy, int *dx) {

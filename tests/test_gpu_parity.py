@@ -164,18 +164,29 @@ def test_warp_corr_matches_oracle(C, G, H, W, D, B, V):
 
 
 def test_warp_corr_generations_agree(monkeypatch):
-    """The first-generation kernel (PMB200_WARP_CORR_V1=1, kept for A/B measurements) and the compaction
-    kernel are two schedules of the same arithmetic."""
+    """The kernel generations kept for A/B measurements (first: PMB200_WARP_CORR_V1=1, second: PMB200_KA_GEN=2,
+    third: default, with/without the two-deep gather pipeline) are schedules of the same arithmetic; the third
+    uses a reciprocal instead of two divisions in the projection, hence the 1e-4 (not 1e-6) agreement bound."""
+    from patchmatchnet_b200.patchmatch import SimilarityNet
+
+    variants = [dict(PMB200_WARP_CORR_V1="1"), dict(PMB200_KA_GEN="2"), dict(PMB200_KA_GEN="3", PMB200_KA_PIPE="0"),
+                dict(PMB200_KA_GEN="3", PMB200_KA_PIPE="1"), dict(PMB200_KA_GEN="3", PMB200_KA_DC="8", PMB200_KA_PIPE="1")]
     for (C, G, H, W, D, B, V) in [(64, 8, 13, 21, 20, 2, 3), (32, 8, 19, 27, 16, 1, 2), (16, 4, 22, 35, 8, 2, 4)]:
         ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=77)
         rt = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs])
         ref_n, src_n = nhwc(ref.to(DEV)), torch.stack([nhwc(s.to(DEV)) for s in srcs])
-        outs = {}
-        for gen in ("0", "1"):
-            monkeypatch.setenv("PMB200_WARP_CORR_V1", gen)
-            outs[gen] = (ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G), ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV)))
-        for a, b in zip(outs["0"], outs["1"]):
-            assert maxabs(a, b) <= 1e-5 * max(1.0, float(a.abs().max()))
+        head = _random_head(SimilarityNet, G, 5).to(DEV)
+        outs = []
+        for env in variants:
+            for k in ("PMB200_WARP_CORR_V1", "PMB200_KA_GEN", "PMB200_KA_PIPE", "PMB200_KA_DC"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            outs.append((ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G), ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV)),
+                         ops.warp_corr_score(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV), head.folded())))
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert maxabs(a, b) <= 1e-4 * max(1.0, float(a.abs().max()))
 
 
 def test_warp_corr_source_map_of_other_size():
