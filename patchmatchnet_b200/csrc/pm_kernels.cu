@@ -1380,7 +1380,10 @@ void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
     const int HW = p.H * p.W;
     constexpr int pix_per_block = kWarps2 * LaneMap<C, G>::PPW;
     dim3 grid((HW + pix_per_block - 1) / pix_per_block, (p.D + DC - 1) / DC, p.B);
-    if (env_int("PMB200_KA_PIPE", 0)) warp_corr3_kernel<C, G, EPI, DC, 1><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+    // measured on B200 (profiles/r1_run5_kbench.json): the two-deep gather pipeline pays at 8 pixels per warp
+    // (C = 32), is neutral at 4 and loses to the higher occupancy of the plain loop at 16
+    constexpr int kPipeDefault = LaneMap<C, G>::PPW == 8 ? 1 : 0;
+    if (env_int("PMB200_KA_PIPE", kPipeDefault)) warp_corr3_kernel<C, G, EPI, DC, 1><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
     else warp_corr3_kernel<C, G, EPI, DC, 0><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
 }
 
