@@ -207,6 +207,54 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
                          int B, int D, int H, int W, int K, int dilation,
                          float interval_scale, int is_inverse, void *stream);
 
+/* ====================================================================================
+ * Backward entry points (training configuration).  Which gradients exist follows the
+ * reference's graph: the warp grid is built under no_grad
+ * (models/module.py:147), depth_weight and the incoming depth are detached
+ * (models/patchmatch.py:74,85,503,506,669), FeatureWeightNet sees a detached reference
+ * feature (:475).  All d_* outputs have the shape of the tensor they differentiate.
+ * ==================================================================================== */
+
+/* K-A backward: gradients w.r.t. the reference feature and the source features.
+ *   grad_out  view_weights == NULL: [V,B,G,D,H,W] (per-view similarities)
+ *             view_weights != NULL: [B,G,D,H,W]   (weighted average; the weights get no gradient here,
+ *                                                  they arrive detached on every iteration that uses this mode)
+ *   d_ref_nhwc [B,H,W,C]   d_src_nhwc [V,B,Hs,Ws,C] (zeroed by the call, then 128-bit vector atomics) */
+int pmb200_warp_corr_backward(const float *ref_nhwc, const float *src_nhwc, const float *rt,
+                              const float *depth, const float *view_weights, const float *grad_out,
+                              float *d_ref_nhwc, float *d_src_nhwc,
+                              int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D,
+                              void *stream);
+
+/* aggregate_views backward: d_sims [V,B,G,D,H,W], d_view_weights [B,V,H,W]. */
+int pmb200_aggregate_views_backward(const float *sims, const float *view_weights, const float *grad_out,
+                                    float *d_sims, float *d_view_weights,
+                                    int V, int B, int G, int D, int H, int W, void *stream);
+
+/* K-A' backward: gradient of the self-correlation [B,G,K,H,W] w.r.t. the raw evaluation offsets [B,2K,H,W]. */
+int pmb200_offset_corr_backward(const float *ref_nhwc, const float *offsets, const float *grad_out,
+                                float *d_offsets, int B, int C, int G, int H, int W, int K, int dilation,
+                                void *stream);
+
+/* K-C backward: gradient of the sorted hypotheses [B,Ns+Kp,H,W] w.r.t. the raw propagation offsets [B,2Kp,H,W]. */
+int pmb200_init_propagate_backward(const float *seed_map, const float *offsets,
+                                   const float *depth_min, const float *depth_max,
+                                   const float *grad_out, float *d_offsets,
+                                   int mode, int B, int H, int W, int Ns, int Kp, int dilation,
+                                   float interval_scale, void *stream);
+
+/* K-B backward.  prob is the forward's probability output; grad_depth [B,H,W] and/or grad_prob [B,D,H,W]
+ * (either may be NULL).  d_score0 [B,D,H,W] (zeroed by the call, atomics), d_depth_sample [B,D,H,W],
+ * d_offsets [B,2K,H,W], d_feature_weight [B,K,H,W]. */
+int pmb200_adaptive_eval_backward(const float *score0, const float *depth_sample, const float *xnorm,
+                                  const float *offsets, const float *feature_weight,
+                                  const float *depth_min, const float *depth_max, const float *prob,
+                                  const float *grad_depth, const float *grad_prob,
+                                  float *d_score0, float *d_depth_sample, float *d_offsets,
+                                  float *d_feature_weight,
+                                  int B, int D, int H, int W, int K, int dilation,
+                                  float interval_scale, int is_inverse, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ from typing import Optional
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libpmb200.so")
-SOURCES = [os.path.join(_PKG_DIR, "csrc", "pm_kernels.cu")]
+SOURCES = [os.path.join(_PKG_DIR, "csrc", "pm_kernels.cu"), os.path.join(_PKG_DIR, "csrc", "pm_backward.cu")]
 HEADERS = [
     os.path.join(_PKG_DIR, "csrc", "pm_math.cuh"),
     os.path.join(_REPO_DIR, "include", "patchmatch_b200.h"),
@@ -98,6 +98,11 @@ _SIGNATURES = {
     "pmb200_offset_corr_weight": (c_int, [c_void_p] * 2 + [_PMLP, c_void_p] + [c_int] * 7 + [c_void_p]),
     "pmb200_init_propagate": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_float, c_void_p]),
     "pmb200_adaptive_eval": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_int, c_void_p]),
+    "pmb200_warp_corr_backward": (c_int, [c_void_p] * 8 + [c_int] * 9 + [c_void_p]),
+    "pmb200_aggregate_views_backward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "pmb200_offset_corr_backward": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "pmb200_init_propagate_backward": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_float, c_void_p]),
+    "pmb200_adaptive_eval_backward": (c_int, [c_void_p] * 14 + [c_int] * 6 + [c_float, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

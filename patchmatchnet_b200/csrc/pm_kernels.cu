@@ -1442,6 +1442,10 @@ void launch_wc2_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_ou
 
 extern "C" {
 
+// shared with pm_backward.cu (not part of the public header)
+int pmb200_internal_fail(int code, const char *msg) { return fail(code, msg); }
+int pmb200_internal_launch_status(const char *what) { return launch_status(what); }
+
 int pmb200_abi_version(void) { return PMB200_ABI_VERSION; }
 
 const char *pmb200_last_error(void) { return g_err; }

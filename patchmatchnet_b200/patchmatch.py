@@ -222,13 +222,12 @@ class PatchMatch(nn.Module):
                 "patchmatchnet_b200.PatchMatch runs on CUDA (sm_100a) only; there is no CPU fallback "
                 f"(got a tensor on {ref_feature.device})"
             )
-        if torch.is_grad_enabled() and (
-            ref_feature.requires_grad or any(p.requires_grad for p in self.parameters())
-        ) and self.training:
-            raise NotImplementedError(
-                "training backward of the fused kernels is not built yet (DESIGN.md, 'next'); "
-                "run under torch.no_grad() / eval()"
-            )
+        # autograd is needed when anything upstream or any parameter can receive a gradient
+        need_grad = torch.is_grad_enabled() and (
+            ref_feature.requires_grad
+            or any(f.requires_grad for f in src_features)
+            or any(p.requires_grad for p in self.parameters())
+        )
 
         B, C, H, W = ref_feature.shape
         V = len(src_features)
@@ -245,18 +244,29 @@ class PatchMatch(nn.Module):
 
         # channels-last feature pack [1+V,B,H,W,C] (zero-copy if the producer already emitted it)
         same_size = all(f.shape == ref_feature.shape for f in src_features)
-        if same_size:
+        if need_grad:
+            from . import autograd as ag  # training configuration: native forward + native backward kernels
+
+            if not same_size:
+                raise NotImplementedError("training with source maps of a different size than the reference map")
+            pack = ag.PackNHWC.apply(ref_feature, *src_features)
+            ref_nhwc, src_nhwc = pack[0], pack[1:]
+        elif same_size:
             pack = ops.pack_nhwc([ref_feature] + list(src_features))
             ref_nhwc, src_nhwc = pack[0], pack[1:]
         else:
             ref_nhwc = ops.pack_nhwc([ref_feature])[0]
             src_nhwc = ops.pack_nhwc(list(src_features))
-        rt = ops.relative_projection(ref_proj, list(src_projs))
+        with torch.no_grad():
+            rt = ops.relative_projection(ref_proj, list(src_projs))
 
-        fused = (not self.training) and self.fuse_heads and (C, self.G) in ops.FUSED_HEAD_SHAPES
+        # eval-mode fusion of the heads has no backward: it is used only when nothing needs a gradient
+        fused = (not self.training) and (not need_grad) and self.fuse_heads and (C, self.G) in ops.FUSED_HEAD_SHAPES
         # feature weight of the evaluation neighbours, once per stage (reference patchmatch.py:475)
         if fused:
             feature_weight = ops.offset_corr_weight(ref_nhwc, eval_off, self.G, Ke, self.dilation, self.feature_weight_net.folded())
+        elif need_grad:
+            feature_weight = self.feature_weight_net(ag.OffsetCorr.apply(ref_nhwc.detach(), eval_off, self.G, Ke, self.dilation))
         else:
             feature_weight = self.feature_weight_net(ops.offset_corr(ref_nhwc, eval_off, self.G, Ke, self.dilation))
 
@@ -274,10 +284,15 @@ class PatchMatch(nn.Module):
                 seed, mode, ns = sample.detach(), ops.MODE_PASSTHROUGH, 1
             else:
                 seed, mode, ns = sample.detach(), ops.MODE_PERTURB, self.patchmatch_num_sample
-            hyp, xnorm = ops.init_propagate(
-                seed, propa_off if kp_now > 0 else None, depth_min, depth_max,
-                mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale, with_xnorm=True,
-            )  # [B,D,H,W] hypotheses and their normalised inverse depth
+            if need_grad and kp_now > 0:
+                hyp, xnorm = ag.InitPropagate.apply(
+                    seed, propa_off, depth_min, depth_max, mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale
+                )
+            else:
+                hyp, xnorm = ops.init_propagate(
+                    seed, propa_off if kp_now > 0 else None, depth_min, depth_max,
+                    mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale, with_xnorm=True,
+                )  # [B,D,H,W] hypotheses and their normalised inverse depth
 
             if fused:
                 if is_empty(view_weights):
@@ -291,6 +306,17 @@ class PatchMatch(nn.Module):
                     score0 = ops.warp_corr_score(
                         ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights, self.evaluation.similarity_net.folded()
                     )
+            elif need_grad:
+                if is_empty(view_weights):
+                    sims = ag.WarpCorr.apply(ref_nhwc, src_nhwc, rt, hyp, None, self.G)  # [V,B,G,D,H,W]
+                    if self.training:
+                        view_weights = torch.cat([self.evaluation.pixel_wise_net(sims[v]) for v in range(V)], dim=1)
+                    else:
+                        vw = self.evaluation.pixel_wise_net(sims.reshape(V * B, self.G, hyp.shape[1], H, W))
+                        view_weights = vw.view(V, B, H, W).permute(1, 0, 2, 3).contiguous()
+                    score0 = self.evaluation.similarity_net(ag.AggregateViews.apply(sims, view_weights))
+                else:
+                    score0 = self.evaluation.similarity_net(ag.WarpCorr.apply(ref_nhwc, src_nhwc, rt, hyp, view_weights, self.G))
             elif is_empty(view_weights):
                 sims = ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G)  # [V,B,G,D,H,W]
                 if self.training:
@@ -303,10 +329,16 @@ class PatchMatch(nn.Module):
                 score0 = self.evaluation.similarity_net(ops.aggregate_views(sims, view_weights))  # [B,D,H,W]
             else:
                 score0 = self.evaluation.similarity_net(ops.warp_corr(ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights))
-            new_depth, prob = ops.adaptive_eval(
-                score0, hyp, eval_off, feature_weight, depth_min, depth_max,
-                self.dilation, self.patchmatch_interval_scale, last_of_stage1, xnorm=xnorm,
-            )
+            if need_grad:
+                new_depth, prob = ag.AdaptiveEval.apply(
+                    score0, hyp, xnorm, eval_off, feature_weight, depth_min, depth_max,
+                    self.dilation, self.patchmatch_interval_scale, last_of_stage1,
+                )
+            else:
+                new_depth, prob = ops.adaptive_eval(
+                    score0, hyp, eval_off, feature_weight, depth_min, depth_max,
+                    self.dilation, self.patchmatch_interval_scale, last_of_stage1, xnorm=xnorm,
+                )
             sample = new_depth.unsqueeze(1)
             outs.append(sample)
         return outs, prob, view_weights.detach()
