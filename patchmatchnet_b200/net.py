@@ -339,6 +339,17 @@ class PatchmatchNet(nn.Module):
         return depth, conf, per_stage
 
 
+def patchmatchnet_loss(depth_patchmatch: Dict[int, List[Tensor]], depth_gt: List[Tensor], mask: List[Tensor]) -> Tensor:
+    """Sum over the 4 pyramid levels and every PatchMatch iteration of the masked smooth-L1 depth error
+    (reference models/net.py:321-342).  depth_gt / mask are per-level lists, finest first."""
+    loss = 0
+    for level in range(4):
+        gt = depth_gt[level][mask[level]]
+        for depth in depth_patchmatch[level]:
+            loss = loss + F.smooth_l1_loss(depth[mask[level]], gt, reduction="mean")
+    return loss
+
+
 def load_reference_state(model: nn.Module, state: Dict[str, Tensor]) -> None:
     """Load a reference checkpoint's ``["model"]`` dict (keys carry the DataParallel
     ``module.`` prefix, reference eval.py:33-35) and insist every key matches."""
