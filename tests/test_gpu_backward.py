@@ -37,6 +37,25 @@ def nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 
 
+def compare_param_grads(mine, want, rtol, atol_of_global):
+    """Per-parameter comparison with an absolute floor tied to the largest gradient of the model: parameters in
+    front of a train-mode BatchNorm have (analytically) zero gradient along some directions, what is left of
+    them is rounding noise of either implementation and must not be compared relatively."""
+    assert set(mine) == set(want)
+    glob = max(float(w.abs().max()) for w in want.values() if w is not None)
+    bad = []
+    for k, w in want.items():
+        if w is None:  # parameters the reference graph never reaches (SURVEY.md 3.4)
+            assert mine[k] is None or float(mine[k].abs().max()) == 0.0, k
+            continue
+        assert mine[k] is not None, k
+        err = float((mine[k].double() - w.double()).abs().max())
+        lim = rtol * float(w.abs().max()) + atol_of_global * glob
+        if err > lim:
+            bad.append((k, err, float(w.abs().max())))
+    assert not bad, f"global grad scale {glob:.3e}; offenders (name, max err, tensor scale): {bad[:8]}"
+
+
 def _warp_case(B, V, C, H, W, D, seed):
     g = torch.Generator().manual_seed(seed)
     ref = torch.randn(B, C, H, W, generator=g)
@@ -224,13 +243,7 @@ def test_stage_training_gradients_match_oracle(golden_weights, name):
     close(grm, gro, 2e-3)
     for a, b in zip(gsm, gso):
         close(a, b, 2e-3)
-    assert set(pmine) == set(po)
-    for k in po:
-        if po[k] is None:  # parameters the reference graph never reaches
-            assert pmine[k] is None or float(pmine[k].abs().max()) == 0.0, k
-        else:
-            assert pmine[k] is not None, k
-            close(pmine[k], po[k], 5e-3)
+    compare_param_grads(pmine, po, rtol=5e-3, atol_of_global=1e-4)
 
 
 def test_network_training_step_matches_oracle(golden_weights):
@@ -265,12 +278,5 @@ def test_network_training_step_matches_oracle(golden_weights):
     assert abs(lm - lo) <= 2e-4 * abs(lo)
     never = sorted(k for k, v in go.items() if v is None)
     assert any("patchmatch_1.propa_conv" in k for k in never) and any("patchmatch_2.evaluation.pixel_wise_net" in k for k in never)
-    worst = 0.0
-    for k, want in go.items():
-        if want is None:
-            assert gm[k] is None or float(gm[k].abs().max()) == 0.0, k
-            continue
-        assert gm[k] is not None, k
-        scale = max(1e-9, float(want.abs().max()))
-        worst = max(worst, float((gm[k] - want).abs().max()) / scale)
-    assert worst <= 2e-2, worst  # gradients flow through ~40 conv/BN layers computed by different libraries on CPU and GPU
+    # gradients flow through ~40 conv/BN layers computed by different libraries on CPU and GPU
+    compare_param_grads(gm, go, rtol=2e-2, atol_of_global=2e-3)
