@@ -333,6 +333,12 @@ def time_warp_corr_isolated(net, dev_inputs, peak_gbs, flush, iters=10):
     return rows
 
 
+def _recorded(stream):
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return ev
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,6 +351,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=1, help="reference views per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=3, help="independent requests in flight per GPU (each its own stream + CUDA graph)")
     ap.add_argument("--cpu-samples", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -373,7 +380,7 @@ def main() -> None:
 
     B, N, H, W = args.batch, args.views, args.height, args.width
     net, weights = build_net()
-    eng = DepthEngine(net, B, N, H, W, device=str(dev), use_graph=not args.no_graph)
+    eng = DepthEngine(net, B, N, H, W, device=str(dev), use_graph=not args.no_graph, n_slots=args.slots)
 
     host = synthetic.make_inputs(B, N, H, W, seed=rank)
     host_pinned = dict(
@@ -383,13 +390,13 @@ def main() -> None:
     )
     d_in = dict(images=[im.to(dev) for im in host["images"]], intrinsics=host["intrinsics"].to(dev),
                 extrinsics=host["extrinsics"].to(dev), depth_min=host["depth_min"].to(dev), depth_max=host["depth_max"].to(dev))
-    for s in (0, 1):
+    for s in range(eng.n_slots):
         eng.set_device_inputs(s, d_in["images"], d_in["intrinsics"], d_in["extrinsics"], d_in["depth_min"], d_in["depth_max"])
     torch.cuda.synchronize()
 
     with LaunchCounter() as lc:
         eng.prepare()  # warm-up forwards + graph capture
-    forwards_counted = 2 * eng._warmup + (2 if eng.use_graph else 0)
+    forwards_counted = eng.n_slots * (eng._warmup + (1 if eng.use_graph else 0))
     launches_per_step = lc.n // max(1, forwards_counted)
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -403,36 +410,39 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---------------- kernel-side throughput: inputs resident in HBM ----------------
+    # K steps run as rounds of up to `slots` concurrent forwards (one per slot stream); L2 is flushed before every
+    # round, outside the event pair that times the round.
     stream = torch.cuda.current_stream()
-    for _ in range(args.warmup):
+    S = eng.n_slots
+    rounds = [min(S, args.steps - r) for r in range(0, args.steps, S)]
+    for _ in range(max(1, (args.warmup + S - 1) // S)):
         flush()
-        eng.run_slot(0)
+        eng.run_round(S, _recorded(stream), torch.cuda.Event())
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for i in range(args.steps):
+    starts = [torch.cuda.Event(enable_timing=True) for _ in rounds]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in rounds]
+    for i, n_now in enumerate(rounds):
         flush()
         starts[i].record(stream)
-        eng.run_slot(0)
-        ends[i].record(stream)
+        eng.run_round(n_now, starts[i], ends[i])
     barrier()
     clocks = sampler.stop()
     dev_seconds = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
 
     # ---------------- end to end: pinned host in, pinned host out, every step ----------------
     reqs = [host_pinned] * (args.steps)
-    eng.infer_stream(reqs[: args.warmup])
+    eng.infer_stream(reqs[: max(args.warmup, eng.n_slots)])
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(eng.compute_stream):
-        t0.record(eng.compute_stream)
-    eng.copy_stream.wait_stream(eng.compute_stream)
-    h2d, d2h = eng.infer_stream(reqs)
-    with torch.cuda.stream(eng.compute_stream):
-        t1.record(eng.compute_stream)
+    t0.record(stream)
+    eng.copy_stream.wait_event(t0)
+    for sl in eng._slots:
+        sl["stream"].wait_event(t0)
+    h2d, d2h = eng.infer_stream(reqs)  # returns after every slot stream has drained
+    t1.record(stream)
     barrier()
     e2e_seconds = t0.elapsed_time(t1) * 1e-3
 
@@ -489,11 +499,13 @@ def main() -> None:
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"1ref+{N - 1}src {W}x{H} 3-stage cascade (64/32,16/16,8 hyp), batch {B} per GPU (BASELINE.json configs[1])",
                        "parallelism": f"{world} x (1 process/GPU, reference views sharded by rank, no data-path collective)",
-                       "weights": weights, "cuda_graph": eng.use_graph, "l2": "flushed between timed steps (256 MiB write, outside the events)",
+                       "weights": weights, "cuda_graph": eng.use_graph, "requests_in_flight": eng.n_slots,
+                       "l2": "flushed before every timed round of <= requests_in_flight concurrent steps (256 MiB write, outside the events)",
                        "library_convs": "cuDNN, torch default (TF32 allowed) for FeatureNet/Refinement/1x1x1 heads"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_seconds / args.steps,
-                    "how": "DepthEngine.infer_stream: pinned host inputs -> device (copy stream, overlapped with the previous step's graph) -> graph -> pinned host outputs"},
+                    "how": "DepthEngine.infer_stream: pinned host inputs -> device (copy stream) -> CUDA graph on the request's slot stream -> pinned host outputs; "
+                           "requests_in_flight independent requests overlap"},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "native_kernels_per_step": {k: v // max(1, forwards_counted) for k, v in sorted(lc.by_name.items())},
             "clocks": clocks,

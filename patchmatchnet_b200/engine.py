@@ -2,9 +2,10 @@
 
 ``DepthEngine`` owns static device buffers for one input shape, captures the whole
 ``PatchmatchNet.forward`` (cuDNN feature pyramid, the native PatchMatch kernels, refinement) into ONE
-CUDA graph -- the cascade is ~300 short kernels, so at 640x512 launch latency, not bandwidth, is the
-enemy -- and moves data with pinned-memory async copies on a side stream so the
-next request's host->device copy overlaps the current request's compute.
+CUDA graph per slot -- the cascade is ~120 short kernels, so at 640x512 launch latency, not bandwidth,
+is the enemy -- runs independent requests concurrently on per-slot streams (most
+kernels of one request launch fewer CTAs than the 148 SMs hold) and moves data with pinned-memory
+async copies on a copy stream so uploads overlap compute.
 
     eng = DepthEngine(net, batch=1, n_views=5, height=512, width=640, device="cuda:0")
     depth, confidence = eng.infer(images, intrinsics, extrinsics, depth_min, depth_max)   # host in, host out
@@ -31,6 +32,7 @@ class DepthEngine:
         device: str = "cuda:0",
         use_graph: bool = True,
         warmup: int = 3,
+        n_slots: int = 3,
     ) -> None:
         if not torch.cuda.is_available():
             raise RuntimeError("DepthEngine needs a CUDA device (B200); there is no CPU fallback")
@@ -39,9 +41,12 @@ class DepthEngine:
         self.shape = (batch, n_views, height, width)
         B, N, H, W = self.shape
         dev = self.device
-        # static device inputs (two sets: the copy stream fills one while the graph reads the other)
+        # One slot = static device inputs + its own compute stream + its own captured graph + pinned host outputs.
+        # Several slots let independent requests overlap on the GPU: most kernels of a 640x512 forward launch far
+        # fewer CTAs than 148 SMs hold, so one request alone cannot fill the machine.
+        self.n_slots = max(1, int(n_slots))
         self._slots = []
-        for _ in range(2):
+        for _ in range(self.n_slots):
             self._slots.append(
                 dict(
                     images=torch.zeros(N, B, 3, H, W, device=dev),
@@ -49,17 +54,16 @@ class DepthEngine:
                     extrinsics=torch.zeros(B, N, 4, 4, device=dev),
                     depth_min=torch.ones(B, device=dev),
                     depth_max=torch.full((B,), 2.0, device=dev),
+                    stream=torch.cuda.Stream(device=dev),
+                    host_depth=torch.empty(B, 1, H, W).pin_memory(),
+                    host_conf=torch.empty(B, H, W).pin_memory(),
+                    graph=None,
+                    outs=None,
                 )
             )
-        self._host_out = dict(
-            depth=torch.empty(B, 1, H, W).pin_memory(),
-            confidence=torch.empty(B, H, W).pin_memory(),
-        )
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.compute_stream = torch.cuda.Stream(device=dev)
+        self.compute_stream = self._slots[0]["stream"]
         self.use_graph = use_graph
-        self._graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]
-        self._outs: List[Optional[Tuple[Tensor, Tensor]]] = [None, None]
         self._warmup = warmup
         self._ready = False
 
@@ -80,19 +84,20 @@ class DepthEngine:
         s["depth_max"].copy_(depth_max.reshape(-1))
 
     def prepare(self) -> None:
-        """Warm up (cuDNN autotune, allocator) and capture one graph per slot.  Slots must hold valid cameras."""
-        with torch.no_grad():
-            with torch.cuda.device(self.device), torch.cuda.stream(self.compute_stream):
-                for slot in self._slots:
+        """Warm up (cuDNN autotune, allocator, BatchNorm/head folding) and capture one graph per slot.
+        Slots must hold valid cameras."""
+        with torch.no_grad(), torch.cuda.device(self.device):
+            for slot in self._slots:
+                with torch.cuda.stream(slot["stream"]):
                     for _ in range(self._warmup):
                         self._forward(slot)
-                self.compute_stream.synchronize()
-                if self.use_graph:
-                    for i, slot in enumerate(self._slots):
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, stream=self.compute_stream):
-                            self._outs[i] = self._forward(slot)
-                        self._graphs[i] = g
+                slot["stream"].synchronize()
+            if self.use_graph:
+                for slot in self._slots:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=slot["stream"]):
+                        slot["outs"] = self._forward(slot)
+                    slot["graph"] = g
         torch.cuda.synchronize(self.device)
         self._ready = True
 
@@ -100,11 +105,24 @@ class DepthEngine:
         """One forward on the inputs currently in the slot, enqueued on the CURRENT stream."""
         if not self._ready:
             self.prepare()
+        slot = self._slots[slot_idx]
         if self.use_graph:
-            self._graphs[slot_idx].replay()
-            return self._outs[slot_idx]
+            slot["graph"].replay()
+            return slot["outs"]
         with torch.no_grad():
-            return self._forward(self._slots[slot_idx])
+            return self._forward(slot)
+
+    def run_round(self, n: int, start: torch.cuda.Event, done: torch.cuda.Event) -> None:
+        """`n` (<= n_slots) forwards concurrently, one per slot stream, fenced by `start` (already recorded on the
+        current stream) and `done` (recorded on the current stream once every slot has finished)."""
+        cur = torch.cuda.current_stream(self.device)
+        for i in range(n):
+            st = self._slots[i]["stream"]
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                self.run_slot(i)
+            cur.wait_stream(st)
+        done.record(cur)
 
     # ------------------------------------------------------------------
     def upload(self, slot_idx: int, host: Dict[str, object], stream: torch.cuda.Stream) -> int:
@@ -121,54 +139,64 @@ class DepthEngine:
                 n += src.numel() * src.element_size()
         return n
 
+    def _first_use(self, host: Dict[str, object]) -> None:
+        for i in range(self.n_slots):
+            self.upload(i, host, self._slots[i]["stream"])
+            self._slots[i]["stream"].synchronize()
+        self.prepare()
+
     def infer(self, images: Sequence[Tensor], intrinsics: Tensor, extrinsics: Tensor, depth_min: Tensor, depth_max: Tensor):
         """Host tensors in, host (pinned) tensors out; one request, synchronous."""
         host = dict(images=list(images), intrinsics=intrinsics, extrinsics=extrinsics,
                     depth_min=depth_min.float(), depth_max=depth_max.float())
         if not self._ready:
-            self.upload(0, host, self.compute_stream)
-            self.upload(1, host, self.compute_stream)
-            self.compute_stream.synchronize()
-            self.prepare()
-        with torch.cuda.device(self.device), torch.cuda.stream(self.compute_stream):
-            self.upload(0, host, self.compute_stream)
+            self._first_use(host)
+        slot = self._slots[0]
+        with torch.cuda.device(self.device), torch.cuda.stream(slot["stream"]):
+            self.upload(0, host, slot["stream"])
             depth, conf = self.run_slot(0)
-            self._host_out["depth"].copy_(depth, non_blocking=True)
-            self._host_out["confidence"].copy_(conf, non_blocking=True)
-        self.compute_stream.synchronize()
-        return self._host_out["depth"], self._host_out["confidence"]
+            slot["host_depth"].copy_(depth, non_blocking=True)
+            slot["host_conf"].copy_(conf, non_blocking=True)
+        slot["stream"].synchronize()
+        return slot["host_depth"], slot["host_conf"]
 
     def infer_stream(self, requests: Sequence[Dict[str, object]], on_result=None) -> Tuple[int, int]:
-        """Pipelined serving loop over pinned-host requests: request i+1 uploads on the copy stream while
-        request i computes; every result is read back to pinned host memory.  Returns (h2d_bytes, d2h_bytes)
-        per request."""
+        """Pipelined serving loop over pinned-host requests.  Request i goes to slot i % n_slots: its inputs are
+        uploaded on the copy stream while earlier requests compute on their own slot streams, its graph is replayed
+        on the slot stream, and its results are read back to that slot's pinned host buffers.  Every request pays its
+        host->device and device->host copies.  Returns (h2d_bytes, d2h_bytes) per request."""
         if not self._ready:
-            self.upload(0, requests[0], self.compute_stream)
-            self.upload(1, requests[0], self.compute_stream)
-            self.compute_stream.synchronize()
-            self.prepare()
+            self._first_use(requests[0])
+        S = self.n_slots
         h2d = d2h = 0
-        uploaded = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        uploaded = [torch.cuda.Event() for _ in range(S)]
+        drained = [None] * S  # recorded on the slot stream once its inputs were consumed AND its outputs copied out
         with torch.cuda.device(self.device):
-            h2d = self.upload(0, requests[0], self.copy_stream)
-            uploaded[0].record(self.copy_stream)
-            for i in range(len(requests)):
-                cur, nxt = i % 2, (i + 1) % 2
-                if i + 1 < len(requests):
-                    if i >= 1:
-                        self.copy_stream.wait_event(consumed[nxt])  # slot nxt was read by request i-1
-                    self.upload(nxt, requests[i + 1], self.copy_stream)
-                    uploaded[nxt].record(self.copy_stream)
-                with torch.cuda.stream(self.compute_stream):
-                    self.compute_stream.wait_event(uploaded[cur])
-                    depth, conf = self.run_slot(cur)
-                    consumed[cur].record(self.compute_stream)
-                    self._host_out["depth"].copy_(depth, non_blocking=True)
-                    self._host_out["confidence"].copy_(conf, non_blocking=True)
+            for i, req in enumerate(requests):
+                k = i % S
+                slot = self._slots[k]
+                if drained[k] is not None:
+                    self.copy_stream.wait_event(drained[k])  # the slot's previous request is completely done
+                    if on_result is not None:
+                        drained[k].synchronize()
+                        on_result(i - S, slot["host_depth"], slot["host_conf"])
+                h2d = self.upload(k, req, self.copy_stream)
+                uploaded[k].record(self.copy_stream)
+                st = slot["stream"]
+                with torch.cuda.stream(st):
+                    st.wait_event(uploaded[k])
+                    depth, conf = self.run_slot(k)
+                    slot["host_depth"].copy_(depth, non_blocking=True)
+                    slot["host_conf"].copy_(conf, non_blocking=True)
                     d2h = depth.numel() * 4 + conf.numel() * 4
-                if on_result is not None:
-                    self.compute_stream.synchronize()
-                    on_result(i, self._host_out["depth"], self._host_out["confidence"])
-            self.compute_stream.synchronize()
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    drained[k] = ev
+            for k in range(S):
+                self._slots[k]["stream"].synchronize()
+            if on_result is not None:
+                first = max(0, len(requests) - S)
+                for i in range(first, len(requests)):
+                    k = i % S
+                    on_result(i, self._slots[k]["host_depth"], self._slots[k]["host_conf"])
         return h2d, d2h

@@ -534,3 +534,30 @@ def test_cuda_graph_replay_equals_eager(golden_weights):
         graph.replay()
         torch.cuda.synchronize()
     assert torch.equal(out[0][-1], eager[0][-1]) and torch.equal(out[1], eager[1])
+
+
+def test_depth_engine_matches_direct_forward(golden_weights):
+    """The public serving call (pinned host in -> CUDA graph on a slot stream -> pinned host out), single request and
+    pipelined over several slots, returns what a direct forward returns."""
+    from patchmatchnet_b200.engine import DepthEngine
+
+    B, N, H, W = 1, 3, 64, 80
+    net = _net(golden_weights)
+    inp = synthetic.make_inputs(B, N, H, W, seed=3)
+    fixed = torch.rand(B, 48, H // 8, W // 8, device=DEV)
+    net.patchmatch_3.rand_source = lambda size, device: fixed  # the stochastic init is pinned so runs are comparable
+    with torch.no_grad():
+        want_d, want_c, _ = net([i.to(DEV) for i in inp["images"]], inp["intrinsics"].to(DEV), inp["extrinsics"].to(DEV),
+                                inp["depth_min"].to(DEV), inp["depth_max"].to(DEV))
+    eng = DepthEngine(net, B, N, H, W, device=DEV, n_slots=3)
+    d, c = eng.infer(inp["images"], inp["intrinsics"], inp["extrinsics"], inp["depth_min"], inp["depth_max"])
+    assert pm_cases.rel_l1(d, want_d) <= 1e-6 and maxabs(c, want_c) <= 1e-5
+    host = dict(images=[i.pin_memory() for i in inp["images"]], intrinsics=inp["intrinsics"].pin_memory(),
+                extrinsics=inp["extrinsics"].pin_memory(), depth_min=inp["depth_min"].pin_memory(), depth_max=inp["depth_max"].pin_memory())
+    seen = {}
+    h2d, d2h = eng.infer_stream([host] * 7, on_result=lambda i, dd, cc: seen.__setitem__(i, (dd.clone(), cc.clone())))
+    assert sorted(seen) == list(range(7))
+    assert h2d == sum(i.numel() * 4 for i in inp["images"]) + 4 * (inp["intrinsics"].numel() + inp["extrinsics"].numel() + 2 * B)
+    assert d2h == 4 * (want_d.numel() + want_c.numel())
+    for i in range(7):
+        assert pm_cases.rel_l1(seen[i][0], want_d) <= 1e-6 and maxabs(seen[i][1], want_c) <= 1e-5
