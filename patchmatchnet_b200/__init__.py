@@ -6,6 +6,7 @@ Public surface (mirrors the reference's ``models`` package for this path):
     PatchmatchNet   caller-side shell with the reference constructor/forward (models/net.py)
     ops             tensor-level wrappers over the C ABI (include/patchmatch_b200.h)
 """
+from . import distributed, engine, ops, synthetic  # noqa: F401
 from .net import PatchmatchNet, load_reference_state, patchmatchnet_loss  # noqa: F401
 from .patchmatch import PatchMatch  # noqa: F401
 

@@ -1242,7 +1242,10 @@ struct EvalParams {
 };
 
 // block (TP pixels, DY hypothesis lanes); dynamic smem: float4 cw[K][TP]; int ck[K][TP]; float sc[D][TP]; float pr[D][TP]
-__global__ void adaptive_eval_kernel(const EvalParams p) {
+// KT = number of evaluation neighbours (9 or 17) as a compile-time constant: the neighbour loop is fully unrolled
+// so that the 8 gathers of every neighbour are issued back to back instead of one neighbour at a time.
+template <int KT>
+__global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) {
     extern __shared__ float4 smem4[];
     const int TP = blockDim.x, DY = blockDim.y;
     float4 *cw = smem4;
@@ -1276,7 +1279,8 @@ __global__ void adaptive_eval_kernel(const EvalParams p) {
         if (p.xnorm) {  // normalised inverse depth precomputed by K-C: 8 loads + 8 FMAs per neighbour
             const float *xmap = p.xnorm + ((size_t)b * p.D + d) * HW;
             const float xc = __ldg(xmap + nc);
-            for (int k = 0; k < p.K; ++k) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
                 const float4 w = cw[k * TP + tp];
                 const int key = ck[k * TP + tp];
                 const int r0 = pm::cell_r0(key), ddx = pm::cell_dx(key), ddy = pm::cell_dy(key);
@@ -1750,7 +1754,8 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
     }
     const size_t smem = smem_for(TP);
     dim3 grid((HW + TP - 1) / TP, B);
-    adaptive_eval_kernel<<<grid, dim3(TP, DY), smem, as_stream(stream)>>>(p);
+    if (K == 9) adaptive_eval_kernel<9><<<grid, dim3(TP, DY), smem, as_stream(stream)>>>(p);
+    else adaptive_eval_kernel<17><<<grid, dim3(TP, DY), smem, as_stream(stream)>>>(p);
     return launch_status("adaptive_eval");
 }
 
