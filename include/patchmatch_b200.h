@@ -67,11 +67,12 @@ int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, 
 
 /* ------------------------------------------------------------------------------------
  * Caller-side helper (feature pyramid top-down path, models/net.py:60-66): channels-last
- *     out = bilinear_upsample_x2(x) + y      x [N,h,w,C], y/out [N,2h,2w,C], C % 4 == 0
+ *     out = bilinear_upsample_x2(x) + y (+ bias[c])     x [N,h,w,C], y/out [N,2h,2w,C], C % 4 == 0
  * same sampling as F.interpolate(scale_factor=2, mode="bilinear", align_corners=False).
- * Replaces ATen's channels-last bilinear kernel + a separate add (12 % of the forward before).
+ * bias: NULL, or the [C] bias of the lateral 1x1 conv that produced y (so that conv can run bias-free).
+ * Replaces ATen's channels-last bilinear kernel + separate bias/add passes (12 % + 4 % of the forward before).
  */
-int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, float *out_nhwc,
+int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const float *bias, float *out_nhwc,
                                int N, int h, int w, int C, void *stream);
 
 /* ------------------------------------------------------------------------------------

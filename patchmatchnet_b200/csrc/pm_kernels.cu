@@ -588,8 +588,8 @@ __device__ __forceinline__ void dot_store(const float4 (&t)[8], const float (&r)
     }
 }
 
-template <int C, int G, int EPI, int DC, int PIPE>
-__global__ void __launch_bounds__(kWarps2 * 32, PIPE ? 4 : 6) warp_corr3_kernel(const WarpCorrParams p, const MlpParams mlp,
+template <int C, int G, int EPI, int DC, int PIPE, int MINB>
+__global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const WarpCorrParams p, const MlpParams mlp,
                                                                   float *__restrict__ sims_out) {
     using M = LaneMap<C, G>;
     constexpr int EPW = M::PPW * DC;   // footprints per warp pass
@@ -642,6 +642,8 @@ __global__ void __launch_bounds__(kWarps2 * 32, PIPE ? 4 : 6) warp_corr3_kernel(
 #pragma unroll
         for (int i = 0; i < 12; ++i) rt[i] = __ldg(p.rt + ((size_t)v * p.B + b) * 12 + i);
         const pm::Ray ray = pm::pixel_ray(rt, px_x, px_y);
+        // issued here so that its latency hides behind phase 1 (it was 10 % of the stall samples right before its use)
+        const float wv = kWeighted ? __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc) : 1.0f;
 
         // ---- phase 1: footprints, per-pixel layered numbering of the unique cells ----
         float4 w[NE];
@@ -676,12 +678,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, PIPE ? 4 : 6) warp_corr3_kernel(
             cg += __popc(m & gmask);
         }
         __syncwarp();
-
-        float wv = 1.0f;
-        if (kWeighted) {
-            wv = __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc);
-            wsum += wv;
-        }
+        if (kWeighted) wsum += wv;
 
         // ---- phase 2a: gather layer by layer, two layers in flight ----
         const float4 *sv =
@@ -1012,7 +1009,8 @@ __global__ void pack_nhwc_kernel(const PackParams p) {
 // out[n,oy,ox,:] = bilinear_up2(x)[n,oy,ox,:] + y[n,oy,ox,:], channels-last, float4 over channels.
 // Same sampling as F.interpolate(scale_factor=2, mode="bilinear", align_corners=False).
 __global__ void upsample2x_add_nhwc_kernel(const float4 *__restrict__ x, const float4 *__restrict__ y,
-                                           float4 *__restrict__ out, int N, int h, int w, int C4) {
+                                           const float4 *__restrict__ bias, float4 *__restrict__ out, int N, int h,
+                                           int w, int C4) {
     const int H = 2 * h, W = 2 * w;
     const size_t total = (size_t)N * H * W * C4;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1029,7 +1027,11 @@ __global__ void upsample2x_add_nhwc_kernel(const float4 *__restrict__ x, const f
     const float4 *b = x + (size_t)n * h * w * C4 + c;
     const float4 a00 = __ldg(b + ((size_t)y0 * w + x0) * C4), a01 = __ldg(b + ((size_t)y0 * w + x1) * C4);
     const float4 a10 = __ldg(b + ((size_t)y1 * w + x0) * C4), a11 = __ldg(b + ((size_t)y1 * w + x1) * C4);
-    const float4 r = __ldg(y + idx);
+    float4 r = __ldg(y + idx);
+    if (bias) {  // per-channel bias of the lateral 1x1 conv, folded in here instead of a separate elementwise pass
+        const float4 bb = __ldg(bias + c);
+        r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+    }
     float4 o;
     o.x = hy * (hx * a00.x + lx * a01.x) + ly * (hx * a10.x + lx * a11.x) + r.x;
     o.y = hy * (hx * a00.y + lx * a01.y) + ly * (hx * a10.y + lx * a11.y) + r.y;
@@ -1387,8 +1389,15 @@ void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
     // measured on B200 (profiles/r1_run5_kbench.json): the two-deep gather pipeline pays at 8 pixels per warp
     // (C = 32), is neutral at 4 and loses to the higher occupancy of the plain loop at 16
     constexpr int kPipeDefault = LaneMap<C, G>::PPW == 8 ? 1 : 0;
-    if (env_int("PMB200_KA_PIPE", kPipeDefault)) warp_corr3_kernel<C, G, EPI, DC, 1><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
-    else warp_corr3_kernel<C, G, EPI, DC, 0><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+    const int pipe = env_int("PMB200_KA_PIPE", kPipeDefault);
+    if constexpr (EPI == kEpiScore) {  // occupancy variant for tuning sweeps: 8 resident CTAs (<= 64 registers)
+        if (!pipe && env_int("PMB200_KA_MINB", 6) == 8) {
+            warp_corr3_kernel<C, G, EPI, DC, 0, 8><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+            return;
+        }
+    }
+    if (pipe) warp_corr3_kernel<C, G, EPI, DC, 1, 4><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+    else warp_corr3_kernel<C, G, EPI, DC, 0, 6><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
 }
 
 // Third-generation launch: rows per warp pass chosen per lane map (more rows = more reuse along the
@@ -1495,14 +1504,14 @@ int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, 
     return launch_status("pack_nhwc");
 }
 
-int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, float *out_nhwc, int N, int h, int w, int C,
-                               void *stream) {
+int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const float *bias, float *out_nhwc, int N, int h,
+                               int w, int C, void *stream) {
     if (!x_nhwc || !y_nhwc || !out_nhwc) return fail(PMB200_EINVAL, "upsample2x_add_nhwc: null pointer");
     if (N < 1 || h < 1 || w < 1 || C < 4 || C % 4 != 0) return fail(PMB200_EINVAL, "upsample2x_add_nhwc: bad size (C % 4 == 0)");
     const size_t total = (size_t)N * 2 * h * 2 * w * (C / 4);
     upsample2x_add_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4 *>(x_nhwc), reinterpret_cast<const float4 *>(y_nhwc),
-        reinterpret_cast<float4 *>(out_nhwc), N, h, w, C / 4);
+        reinterpret_cast<const float4 *>(bias), reinterpret_cast<float4 *>(out_nhwc), N, h, w, C / 4);
     return launch_status("upsample2x_add_nhwc");
 }
 

@@ -117,20 +117,22 @@ class FeatureNet(nn.Module):
         quarter = self._trunk(half, 5, 7)
         eighth = self._trunk(quarter, 8, 10)
         out: Dict[int, Tensor] = {3: self.output1(eighth)}
-        top = self._top_down(eighth, self.inner1(quarter))
+        top = self._top_down(eighth, self.inner1, quarter)
         out[2] = self.output2(top)
-        top = self._top_down(top, self.inner2(half))
+        top = self._top_down(top, self.inner2, half)
         out[1] = self.output3(top)
         return out
 
-    def _top_down(self, coarse: Tensor, lateral: Tensor) -> Tensor:
-        """bilinear x2 upsample + lateral add (reference net.py:60-66); one native launch on CUDA in eval mode
-        (ATen's channels-last bilinear kernel was the single largest launch of the forward)."""
+    def _top_down(self, coarse: Tensor, lateral_conv: nn.Conv2d, fine: Tensor) -> Tensor:
+        """bilinear x2 upsample + lateral 1x1 conv (reference net.py:60-66).  On CUDA in eval mode the upsample, the
+        add and the lateral conv's bias are ONE native launch (ATen's channels-last bilinear kernel was the single
+        largest launch of the forward, the bias add another full pass over the largest tensor)."""
         if coarse.is_cuda and not self.training and not torch.is_grad_enabled():
             from . import ops
 
-            return ops.upsample2x_add(coarse, lateral)
-        return F.interpolate(coarse, scale_factor=2.0, mode="bilinear", align_corners=False) + lateral
+            lateral = F.conv2d(fine, lateral_conv.weight, None)
+            return ops.upsample2x_add(coarse, lateral, lateral_conv.bias)
+        return F.interpolate(coarse, scale_factor=2.0, mode="bilinear", align_corners=False) + lateral_conv(fine)
 
 
 class Refinement(nn.Module):

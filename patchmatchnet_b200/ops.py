@@ -92,8 +92,8 @@ def pack_nhwc(maps: Sequence[Tensor]) -> Tensor:
     return out
 
 
-def upsample2x_add(x: Tensor, y: Tensor) -> Tensor:
-    """bilinear x2 upsample of `x` plus `y`, both channels-last 4-D CUDA tensors (logical NCHW)."""
+def upsample2x_add(x: Tensor, y: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """bilinear x2 upsample of `x` plus `y` (plus a per-channel `bias`), channels-last 4-D CUDA tensors (logical NCHW)."""
     N, C, h, w = x.shape
     if y.shape != (N, C, 2 * h, 2 * w):
         raise RuntimeError("upsample2x_add: y must be [N,C,2h,2w]")
@@ -104,9 +104,15 @@ def upsample2x_add(x: Tensor, y: Tensor) -> Tensor:
         x = x.contiguous(memory_format=torch.channels_last)
     if not y.is_contiguous(memory_format=torch.channels_last):
         y = y.contiguous(memory_format=torch.channels_last)
+    b_ptr = None
+    if bias is not None:
+        bias = _require(bias, "bias", 1)
+        if bias.numel() != C:
+            raise RuntimeError("upsample2x_add: bias must have C elements")
+        b_ptr = bias.data_ptr()
     out = torch.empty_like(y, memory_format=torch.channels_last)
     with torch.cuda.device(x.device):
-        rc = _native.lib().pmb200_upsample2x_add_nhwc(x.data_ptr(), y.data_ptr(), out.data_ptr(), N, h, w, C, _stream(x))
+        rc = _native.lib().pmb200_upsample2x_add_nhwc(x.data_ptr(), y.data_ptr(), b_ptr, out.data_ptr(), N, h, w, C, _stream(x))
     _native.check(rc, "upsample2x_add_nhwc")
     return out
 

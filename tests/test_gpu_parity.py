@@ -103,6 +103,8 @@ def test_upsample2x_add_matches_interpolate():
         assert got.shape == want.shape and maxabs(got, want) <= 1e-5
         got2 = ops.upsample2x_add(x.contiguous(), y.contiguous())  # NCHW inputs are converted
         assert maxabs(got2, want) <= 1e-5
+        bias = torch.randn(C, device=DEV)
+        assert maxabs(ops.upsample2x_add(x, y, bias), want + bias.view(1, C, 1, 1)) <= 1e-5
 
 
 # ------------------------------------------------------------------------------------------------

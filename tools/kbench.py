@@ -69,7 +69,8 @@ def timeit(fn, iters=12):
 
 out = {"shape": f"{W}x{H}", "rows": []}
 variants = ([dict(PMB200_WARP_CORR_V1="1"), dict(PMB200_KA_GEN="2")]
-            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE=str(pp)) for d, pp in itertools.product((0, 2, 4, 8, 16), (0, 1))])
+            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE=str(pp)) for d, pp in itertools.product((0, 4, 8, 16), (0, 1))]
+            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE="0", PMB200_KA_MINB="8") for d in (0, 4, 8, 16)])
 for (n, a, k) in calls:
     desc = n
     if n.startswith("warp_corr"):
