@@ -75,6 +75,12 @@ int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, 
 int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const float *bias, float *out_nhwc,
                                int N, int h, int w, int C, void *stream);
 
+/* Caller-side helper (models/net.py:289-299): photometric confidence = probability mass of the four
+ * hypotheses around the regressed hypothesis index, nearest-resized to [H_out, W_out].
+ *   prob [B,D,h,w] (the last PatchMatch stage's probabilities)   confidence_out [B,H_out,W_out] */
+int pmb200_photometric_confidence(const float *prob, float *confidence_out,
+                                  int B, int D, int h, int w, int H_out, int W_out, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * K-A: fused homography warp + bilinear gather + group-wise correlation
  *      (+ view-weighted aggregation).

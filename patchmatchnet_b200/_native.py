@@ -88,6 +88,7 @@ _SIGNATURES = {
     "pmb200_last_error": (c_char_p, []),
     "pmb200_relative_projection": (c_int, [c_void_p, c_int64, _PPF, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "pmb200_pack_nhwc": (c_int, [_PPF, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pmb200_photometric_confidence": (c_int, [c_void_p] * 2 + [c_int] * 6 + [c_void_p]),
     "pmb200_upsample2x_add_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "pmb200_warp_corr": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
     "pmb200_aggregate_views": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),

@@ -1040,6 +1040,32 @@ __global__ void upsample2x_add_nhwc_kernel(const float4 *__restrict__ x, const f
     out[idx] = o;
 }
 
+// Photometric confidence (caller side, reference models/net.py:289-299): probability mass of the four
+// hypotheses around the regressed index, nearest-upsampled to the output size -- one launch instead of
+// pad + avg_pool3d + mul + arange + mul + sum + long + clamp + gather + interpolate.
+__global__ void photometric_confidence_kernel(const float *__restrict__ prob, float *__restrict__ out, int B, int D,
+                                              int h, int w, int H, int W) {
+    const size_t total = (size_t)B * H * W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int X = (int)(idx % W), Y = (int)((idx / W) % H), b = (int)(idx / ((size_t)W * H));
+    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+    const int y = min((int)floorf((float)Y * sy), h - 1), x = min((int)floorf((float)X * sx), w - 1);
+    const float *pp = prob + (size_t)b * D * h * w + (size_t)y * w + x;
+    const size_t plane = (size_t)h * w;
+    float e = 0.0f;
+    for (int d = 0; d < D; ++d) e += __ldg(pp + d * plane) * (float)d;
+    int k = (int)e;  // .long(): truncation
+    k = max(0, min(k, D - 1));
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = -1; j <= 2; ++j) {
+        const int d = k + j;
+        sum += (d >= 0 && d < D) ? __ldg(pp + d * plane) : 0.0f;
+    }
+    out[idx] = 4.0f * (sum * 0.25f);
+}
+
 struct ProjParams {
     const float *ref;
     PtrList src;
@@ -1502,6 +1528,16 @@ int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, 
     dim3 grid((p.HW + 31) / 32, (C + 31) / 32, n * B);
     pack_nhwc_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(p);
     return launch_status("pack_nhwc");
+}
+
+int pmb200_photometric_confidence(const float *prob, float *confidence_out, int B, int D, int h, int w, int H_out,
+                                  int W_out, void *stream) {
+    if (!prob || !confidence_out) return fail(PMB200_EINVAL, "photometric_confidence: null pointer");
+    if (B < 1 || D < 1 || h < 1 || w < 1 || H_out < 1 || W_out < 1) return fail(PMB200_EINVAL, "photometric_confidence: bad size");
+    const size_t total = (size_t)B * H_out * W_out;
+    photometric_confidence_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(prob, confidence_out, B, D, h, w,
+                                                                                                H_out, W_out);
+    return launch_status("photometric_confidence");
 }
 
 int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const float *bias, float *out_nhwc, int N, int h,

@@ -332,6 +332,10 @@ class PatchmatchNet(nn.Module):
             return depth, torch.empty(0, device=dev), per_stage
 
         # photometric confidence (net.py:289-299): probability mass of the 4 hypotheses around the regressed index
+        if score.is_cuda and not torch.is_grad_enabled() and score.shape[1] == self.patchmatch_num_sample[0]:
+            from . import ops
+
+            return depth, ops.photometric_confidence(score, H0, W0), per_stage
         D = self.patchmatch_num_sample[0]
         mass4 = 4 * F.avg_pool3d(F.pad(score.unsqueeze(1), pad=(0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
         idx = torch.sum(score * torch.arange(D, device=score.device, dtype=torch.float).view(1, D, 1, 1), dim=1)

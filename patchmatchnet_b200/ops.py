@@ -92,6 +92,17 @@ def pack_nhwc(maps: Sequence[Tensor]) -> Tensor:
     return out
 
 
+def photometric_confidence(prob: Tensor, out_h: int, out_w: int) -> Tensor:
+    """[B,D,h,w] probabilities -> [B,out_h,out_w] confidence (reference net.py:289-299)."""
+    pr = _require(prob, "prob", 4)
+    B, D, h, w = pr.shape
+    out = torch.empty((B, out_h, out_w), dtype=torch.float32, device=pr.device)
+    with torch.cuda.device(pr.device):
+        rc = _native.lib().pmb200_photometric_confidence(pr.data_ptr(), out.data_ptr(), B, D, h, w, out_h, out_w, _stream(pr))
+    _native.check(rc, "photometric_confidence")
+    return out
+
+
 def upsample2x_add(x: Tensor, y: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     """bilinear x2 upsample of `x` plus `y` (plus a per-channel `bias`), channels-last 4-D CUDA tensors (logical NCHW)."""
     N, C, h, w = x.shape

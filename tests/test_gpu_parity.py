@@ -94,6 +94,20 @@ def test_pack_nhwc():
         assert torch.equal(packed[i], m.permute(0, 2, 3, 1))
 
 
+def test_photometric_confidence_matches_reference_ops():
+    g = torch.Generator().manual_seed(4)
+    for (B, D, h, w, H0, W0) in [(2, 8, 16, 20, 32, 40), (1, 8, 9, 7, 17, 15), (1, 5, 6, 6, 6, 6)]:
+        score = torch.softmax(torch.randn(B, D, h, w, generator=g) * 2.0, dim=1)
+        sum4 = 4 * F.avg_pool3d(F.pad(score.unsqueeze(1), pad=(0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
+        idx = torch.sum(score * torch.arange(D, dtype=torch.float).view(1, D, 1, 1), dim=1).unsqueeze(1).long().clamp(0, D - 1)
+        want = F.interpolate(torch.gather(sum4, 1, idx), size=[H0, W0], mode="nearest").squeeze(1)
+        got = ops.photometric_confidence(score.to(DEV), H0, W0)
+        assert got.shape == want.shape
+        # the regressed index is truncated to an integer: a pixel whose expectation sits on an integer may flip bins
+        bad = (got.cpu() - want).abs() > 1e-5
+        assert float(bad.float().mean()) <= 0.002
+
+
 def test_upsample2x_add_matches_interpolate():
     for (N, C, h, w) in [(5, 64, 8, 10), (2, 32, 7, 9), (1, 16, 1, 3)]:
         x = torch.randn(N, C, h, w, device=DEV).contiguous(memory_format=torch.channels_last)
