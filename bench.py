@@ -351,6 +351,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=1, help="reference views per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tf32", action="store_true", help="run the library convolutions in full fp32 instead of torch's default TF32")
     ap.add_argument("--slots", type=int, default=3, help="independent requests in flight per GPU (each its own stream + CUDA graph)")
     ap.add_argument("--cpu-samples", type=int, default=4)
     args = ap.parse_args()
@@ -368,6 +369,9 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True  # as the reference's eval.py:301 does; autotuned during warm-up
+    if args.no_tf32:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -507,7 +511,9 @@ def main() -> None:
                        "parallelism": f"{world} x (1 process/GPU, reference views sharded by rank, no data-path collective)",
                        "weights": weights, "cuda_graph": eng.use_graph, "requests_in_flight": eng.n_slots,
                        "l2": "flushed before every timed round of <= requests_in_flight concurrent steps (256 MiB write, outside the events)",
-                       "library_convs": "cuDNN, torch default (TF32 allowed) for FeatureNet/Refinement/1x1x1 heads"},
+                       "library_convs": ("cuDNN, full fp32 (--no-tf32)" if args.no_tf32 else
+                                         "cuDNN under torch's default flags (TF32 allowed, as the unmodified reference would run on this GPU) for "
+                                         "FeatureNet/Refinement/offset convs; every hand-written kernel is full fp32")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_seconds / args.steps,
                     "how": "DepthEngine.infer_stream: pinned host inputs -> device (copy stream) -> CUDA graph on the request's slot stream -> pinned host outputs; "

@@ -1,26 +1,23 @@
-// pm_kernels.cu -- sm_100a kernels of the learned-PatchMatch hot path + their C ABI.
+// pm_kernels.cu -- sm_100a forward kernels of the learned-PatchMatch hot path + their C ABI
+// (backward kernels: pm_backward.cu; per-element formulas shared with the CPU formula tests: pm_math.cuh).
 //
-// Kernel map (DESIGN.md has the byte/flop budgets):
-//   warp_corr_kernel<C,G,FUSED>   K-A   homography warp + bilinear gather + group-wise correlation
-//                                       (+ view-weighted aggregation)          pmb200_warp_corr
-//   offset_corr_kernel<C,G>       K-A'  same gather/correlate core, coordinates from learned offsets
-//                                                                                pmb200_offset_corr
-//   init_propagate_kernel<NPAD>   K-C   hypothesis init + neighbour gather + register sorting network
-//                                                                                pmb200_init_propagate
-//   adaptive_eval_kernel          K-B   depth/feature weights + neighbour aggregation + softmax + regression
-//                                                                                pmb200_adaptive_eval
-//   aggregate_views_kernel, pack_nhwc_kernel, relative_projection_kernel        small helpers
+// Kernel map (DESIGN.md has the byte/flop budgets and the measured numbers):
+//   warp_corr3_kernel<C,G,EPI,DC,PIPE,MINB>  K-A, third generation (default): homography warp + bilinear gather +
+//                                  group-wise correlation + view-weighted aggregation + (eval) 1x1x1 head epilogue
+//                                  pmb200_warp_corr / _score / _view_weights
+//   warp_corr2_kernel, warp_corr_kernel      K-A generations 2 and 1, kept selectable (PMB200_KA_GEN=2,
+//                                  PMB200_WARP_CORR_V1=1) for A/B measurements; warp_corr_generic_kernel: any C % G == 0
+//   aggregate_views_kernel / aggregate_score_kernel   weighted view average of stored similarities (+ head)
+//   offset_corr_kernel<C,G,HEAD>   K-A': reference self-correlation at the learned evaluation neighbours (+ head)
+//   init_propagate_kernel<NPAD>    K-C: hypothesis init + neighbour gather + warp-shuffle bitonic sort
+//   adaptive_eval_kernel<K>        K-B: depth/feature weights + neighbour aggregation + softmax + regression
+//   relative_projection_kernel, pack_nhwc_kernel, upsample2x_add_nhwc_kernel, photometric_confidence_kernel   helpers
 //
-// Lane mapping of the gather/correlate core (K-A, K-A'): features are channels-last, each lane
-// owns 8 consecutive channels of one pixel, C/8 lanes share a pixel, a warp covers 32/(C/8)
-// consecutive pixels.  One bilinear tap of one pixel is therefore one contiguous C*4-byte read
-// split over C/8 lanes as 2 x 16-byte loads (a full 128-byte line per pixel at C=32, two at C=64).
-// The per-(pixel, hypothesis) footprint (4 weights + packed texel key) is computed once per warp
-// into shared memory (phase 1) and broadcast to the lanes of the pixel (phase 2), so the
-// projection arithmetic is not repeated C/8 times.  Phase 2 keeps the four tap/reference dot
-// products T[tap][group] in registers and only re-gathers when the footprint key changes:
-// PatchMatch hypotheses of one pixel are sorted and clustered, so consecutive hypotheses mostly
-// land in the same source cell and cost 4 FMAs per group instead of 4 x 32 bytes of L1 traffic.
+// Lane mapping of the gather (K-A, K-A'): features are channels-last, each lane owns 8 consecutive channels of one
+// pixel, C/8 lanes share a pixel, a warp covers 32/(C/8) consecutive pixels.  One bilinear tap of one pixel is one
+// contiguous C*4-byte read split over C/8 lanes as 2 x 16-byte loads (a full 128-byte line per pixel at C=32, two at
+// C=64).  PatchMatch hypotheses of one pixel are sorted and clustered, so consecutive hypotheses mostly land in the
+// same source cell; every generation of K-A exploits that differently (see the comments above each kernel).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -577,3 +577,49 @@ def test_depth_engine_matches_direct_forward(golden_weights):
     assert d2h == 4 * (want_d.numel() + want_c.numel())
     for i in range(7):
         assert pm_cases.rel_l1(seen[i][0], want_d) <= 1e-6 and maxabs(seen[i][1], want_c) <= 1e-5
+
+
+def test_reentrant_from_two_host_threads(golden_weights):
+    """nn.DataParallel (reference eval.py:33, train.py:282) calls replicas from one Python thread per GPU; the C ABI
+    holds no global mutable state, so concurrent calls from several host threads (here: two threads, two streams,
+    one GPU) give the same results as serial calls."""
+    import threading
+
+    specs = [pm_cases.STAGE_CASES["stage2_small"], pm_cases.STAGE_CASES["stage1_small"]]
+    mods, kws, want = [], [], []
+    for spec in specs:
+        case = pm_cases.make_stage_inputs(spec)
+        mod = _stage_module(golden_weights, spec["stage"])
+        kw = dict(
+            ref_feature=case["ref_feature"].to(DEV), src_features=[s.to(DEV) for s in case["src_features"]],
+            ref_proj=case["ref_proj"].to(DEV), src_projs=[m.to(DEV) for m in case["src_projs"]],
+            depth_min=case["depth_min"].to(DEV), depth_max=case["depth_max"].to(DEV),
+            depth=case["depth"].to(DEV), view_weights=case["view_weights"].to(DEV),
+        )
+        with torch.no_grad():
+            want.append(mod(**kw)[0][-1].clone())
+        mods.append(mod)
+        kws.append(kw)
+    torch.cuda.synchronize()
+    results, errors = [[], []], []
+
+    def work(i):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.no_grad(), torch.cuda.stream(stream):
+                for _ in range(20):
+                    results[i].append(mods[i](**kws[i])[0][-1])
+            stream.synchronize()
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for i in range(2):
+        assert len(results[i]) == 20
+        for r in results[i]:
+            assert torch.equal(r, want[i])
