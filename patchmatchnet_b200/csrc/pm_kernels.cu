@@ -101,37 +101,70 @@ __device__ __forceinline__ void load_reference(const float *__restrict__ ref_nhw
     r[4] = q1.x * s; r[5] = q1.y * s; r[6] = q1.z * s; r[7] = q1.w * s;
 }
 
-// Folded (conv3d 1x1x1 + eval-mode BatchNorm) weights of one G -> 16 -> 8 -> 1 head.  Passed by value
-// inside the kernel parameter block, i.e. it lives in the constant bank and every FMA of the epilogue
-// MLP takes its weight as a constant operand (no load instruction).
-struct MlpParams {
-    float w0[16 * 8];  // [16][G padded to 8]
+// Packed fp32x2 FMA (Blackwell: SASS FFMA2): two IEEE fp32 fused multiply-adds per issued instruction.  The K-A
+// kernels are bound by issue slots, not by the fp32 pipe, so halving the FFMA count of the head MLP, the blend and
+// the gather dot products buys back issue bandwidth at unchanged numerics.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    ra = *reinterpret_cast<const unsigned long long *>(&a);
+    rb = *reinterpret_cast<const unsigned long long *>(&b);
+    rc = *reinterpret_cast<const unsigned long long *>(&c);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// Folded (conv3d 1x1x1 + eval-mode BatchNorm) weights of one G -> 16 -> 8 -> 1 head in the layout the device code
+// wants: input-major ("transposed") so that the weights of two adjacent outputs are one 64-bit constant operand.
+// Passed by value inside the kernel parameter block, i.e. it lives in the constant bank.
+struct alignas(16) MlpParams {
+    float w0t[8][16];  // [input g (padded to 8)][output j]
     float b0[16];
-    float w1[8 * 16];
+    float w1t[16][8];  // [input j][output i]
     float b1[8];
     float w2[8];
     float b2;
 };
 
+// public layout (pmb200_mlp: output-major, as the convolutions store them) -> device layout
+inline MlpParams to_device_layout(const pmb200_mlp *h) {
+    static_assert(sizeof(MlpParams) >= sizeof(pmb200_mlp), "pmb200_mlp layout");
+    MlpParams m;
+    for (int j = 0; j < 16; ++j)
+        for (int g = 0; g < 8; ++g) m.w0t[g][j] = h->w0[j * 8 + g];
+    for (int j = 0; j < 16; ++j) m.b0[j] = h->b0[j];
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 16; ++j) m.w1t[j][i] = h->w1[i * 16 + j];
+    for (int i = 0; i < 8; ++i) { m.b1[i] = h->b1[i]; m.w2[i] = h->w2[i]; }
+    m.b2 = h->b2;
+    return m;
+}
+
 template <int G>
 __device__ __forceinline__ float mlp_eval(const MlpParams &m, const float (&x)[G]) {
-    float h0[16];
+    float2 h0[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) h0[q] = make_float2(m.b0[2 * q], m.b0[2 * q + 1]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float2 xx = make_float2(x[g], x[g]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h0[q] = ffma2(make_float2(m.w0t[g][2 * q], m.w0t[g][2 * q + 1]), xx, h0[q]);
+    }
+    float2 h1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h1[q] = make_float2(m.b1[2 * q], m.b1[2 * q + 1]);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        float a = m.b0[j];
+        const float hj = fmaxf((j & 1) ? h0[j >> 1].y : h0[j >> 1].x, 0.0f);
+        const float2 hh = make_float2(hj, hj);
 #pragma unroll
-        for (int g = 0; g < G; ++g) a = fmaf(m.w0[j * 8 + g], x[g], a);
-        h0[j] = fmaxf(a, 0.0f);
+        for (int q = 0; q < 4; ++q) h1[q] = ffma2(make_float2(m.w1t[j][2 * q], m.w1t[j][2 * q + 1]), hh, h1[q]);
     }
-    float y = m.b2;
+    float2 acc = make_float2(m.b2, 0.0f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float a = m.b1[i];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a = fmaf(m.w1[i * 16 + j], h0[j], a);
-        y = fmaf(m.w2[i], fmaxf(a, 0.0f), y);
-    }
-    return y;
+    for (int q = 0; q < 4; ++q)
+        acc = ffma2(make_float2(m.w2[2 * q], m.w2[2 * q + 1]), make_float2(fmaxf(h1[q].x, 0.0f), fmaxf(h1[q].y, 0.0f)), acc);
+    return acc.x + acc.y;
 }
 
 struct WarpCorrParams {
@@ -576,12 +609,20 @@ __device__ __forceinline__ void load_taps(const float4 *__restrict__ map_lane, i
 template <int C, int G>
 __device__ __forceinline__ void dot_store(const float4 (&t)[8], const float (&r)[8], float *__restrict__ tp) {
     using M = LaneMap<C, G>;
-    auto lo = [&](const float4 &q) { return r[0] * q.x + r[1] * q.y + r[2] * q.z + r[3] * q.w; };
-    auto hi = [&](const float4 &q) { return r[4] * q.x + r[5] * q.y + r[6] * q.z + r[7] * q.w; };
+    const float2 r01 = make_float2(r[0], r[1]), r23 = make_float2(r[2], r[3]);
+    const float2 r45 = make_float2(r[4], r[5]), r67 = make_float2(r[6], r[7]);
+    const float2 zero = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if constexpr (M::GPL == 1) tp[k * G] = lo(t[2 * k]) + hi(t[2 * k + 1]);
-        else *reinterpret_cast<float2 *>(tp + k * G) = make_float2(lo(t[2 * k]), hi(t[2 * k + 1]));
+        const float4 a = t[2 * k], bq = t[2 * k + 1];
+        const float2 lo = ffma2(r23, make_float2(a.z, a.w), ffma2(r01, make_float2(a.x, a.y), zero));
+        if constexpr (M::GPL == 1) {
+            const float2 s = ffma2(r67, make_float2(bq.z, bq.w), ffma2(r45, make_float2(bq.x, bq.y), lo));
+            tp[k * G] = s.x + s.y;
+        } else {
+            const float2 hi = ffma2(r67, make_float2(bq.z, bq.w), ffma2(r45, make_float2(bq.x, bq.y), zero));
+            *reinterpret_cast<float2 *>(tp + k * G) = make_float2(lo.x + lo.y, hi.x + hi.y);
+        }
     }
 }
 
@@ -712,18 +753,27 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
             for (int g = 0; g < G; ++g) sim[g] = 0.0f;
             if (key[k] != pm::kKeyNone) {
                 const float4 *tp = reinterpret_cast<const float4 *>(s_T[warp] + slot[k] * TS);
+                const float2 wx = make_float2(w[k].x, w[k].x), wy = make_float2(w[k].y, w[k].y);
+                const float2 wz = make_float2(w[k].z, w[k].z), ww = make_float2(w[k].w, w[k].w);
+                const float2 zero = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int q = 0; q < G / 4; ++q) {
                     const float4 t0 = tp[q], t1 = tp[G / 4 + q], t2 = tp[2 * (G / 4) + q], t3 = tp[3 * (G / 4) + q];
-                    sim[4 * q + 0] = w[k].x * t0.x + w[k].y * t1.x + w[k].z * t2.x + w[k].w * t3.x;
-                    sim[4 * q + 1] = w[k].x * t0.y + w[k].y * t1.y + w[k].z * t2.y + w[k].w * t3.y;
-                    sim[4 * q + 2] = w[k].x * t0.z + w[k].y * t1.z + w[k].z * t2.z + w[k].w * t3.z;
-                    sim[4 * q + 3] = w[k].x * t0.w + w[k].y * t1.w + w[k].z * t2.w + w[k].w * t3.w;
+                    const float2 lo = ffma2(ww, make_float2(t3.x, t3.y), ffma2(wz, make_float2(t2.x, t2.y),
+                                      ffma2(wy, make_float2(t1.x, t1.y), ffma2(wx, make_float2(t0.x, t0.y), zero))));
+                    const float2 hi = ffma2(ww, make_float2(t3.z, t3.w), ffma2(wz, make_float2(t2.z, t2.w),
+                                      ffma2(wy, make_float2(t1.z, t1.w), ffma2(wx, make_float2(t0.z, t0.w), zero))));
+                    sim[4 * q + 0] = lo.x; sim[4 * q + 1] = lo.y; sim[4 * q + 2] = hi.x; sim[4 * q + 3] = hi.y;
                 }
             }
             if (kWeighted) {
+                const float2 wv2 = make_float2(wv, wv);
 #pragma unroll
-                for (int g = 0; g < G; ++g) acc[k][g] = fmaf(sim[g], wv, acc[k][g]);
+                for (int g = 0; g < G; g += 2) {
+                    const float2 a2 = ffma2(make_float2(sim[g], sim[g + 1]), wv2, make_float2(acc[k][g], acc[k][g + 1]));
+                    acc[k][g] = a2.x;
+                    acc[k][g + 1] = a2.y;
+                }
             } else {
                 const int d = d0 + row0 + k * RPK;
                 if ((EPI == kEpiSims || sims_out != nullptr) && ev[k]) {
@@ -1599,14 +1649,12 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
     if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || B > 65535 || H < 1 || W < 1 || Hs < 1 || Ws < 1 || D < 1)
         return fail(PMB200_EINVAL, "warp_corr head: bad size");
     if ((long long)Hs * Ws >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "warp_corr head: source map too large");
-    static_assert(sizeof(MlpParams) == sizeof(pmb200_mlp), "pmb200_mlp layout");
     WarpCorrParams p;
     p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = view_weights; p.out = out;
     p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
     p.sx = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 1.0f;
     p.sy = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 1.0f;
-    MlpParams m;
-    memcpy(&m, head_host, sizeof(m));
+    const MlpParams m = to_device_layout(head_host);
     const int HW = H * W;
     cudaStream_t st = as_stream(stream);
     const int nchunk = (D + kChunk - 1) / kChunk;
@@ -1655,8 +1703,7 @@ int pmb200_aggregate_views_score(const float *sims, const float *view_weights, c
     if (!sims || !view_weights || !head_host || !score_out) return fail(PMB200_EINVAL, "aggregate_views_score: null pointer");
     if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || D < 1 || H < 1 || W < 1)
         return fail(PMB200_EINVAL, "aggregate_views_score: bad size");
-    MlpParams m;
-    memcpy(&m, head_host, sizeof(m));
+    const MlpParams m = to_device_layout(head_host);
     const size_t total = (size_t)B * D * H * W;
     const unsigned blocks = (unsigned)((total + 127) / 128);
     if (G == 8) aggregate_score_kernel<8><<<blocks, 128, 0, as_stream(stream)>>>(sims, view_weights, score_out, m, V, B, D, H * W);
@@ -1674,8 +1721,7 @@ int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets, const
     OffsetCorrParams p;
     p.ref = ref_nhwc; p.offsets = offsets; p.out = weight_out;
     p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation;
-    MlpParams m;
-    memcpy(&m, head_host, sizeof(m));
+    const MlpParams m = to_device_layout(head_host);
     const int HW = H * W;
     cudaStream_t st = as_stream(stream);
     const int nchunk = (K + kChunk - 1) / kChunk;
