@@ -147,9 +147,12 @@ typedef struct pmb200_mlp {
  *   score_out [B,D,H,W];  view_weights [B,V,H,W] required.  (C,G) in {(64,8),(32,8),(16,4)}. */
 int pmb200_warp_corr_score(const float *ref_nhwc, const float *src_nhwc, const float *rt,
                            const float *depth, const float *view_weights,
-                           const pmb200_mlp *head_host, float *score_out,
+                           const pmb200_mlp *head_host, float *score_out, int score_stride,
                            int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D,
                            void *stream);
+/* score_stride: element stride of score_out.  1 = dense [B,D,H,W]; 2 = write the .y lanes of an interleaved
+ * (xnorm, score) buffer [B,D,H,W,2] whose .x lanes pmb200_init_propagate filled (xnorm_stride = 2), which
+ * pmb200_adaptive_eval then gathers with ONE 8-byte load per tap (xnorm_score argument). */
 
 /* K-A + PixelwiseNet (models/patchmatch.py:690-702): per view, max over hypotheses of
  * sigmoid(MLP(similarity)).  view_weights_out [B,V,H,W] (zeroed by the call, then atomic max).
@@ -164,7 +167,7 @@ int pmb200_warp_corr_view_weights(const float *ref_nhwc, const float *src_nhwc, 
 /* View-weighted aggregation of stored per-view similarities + SimilarityNet head:
  *   score_out [B,D,H,W] = MLP( sum_v sims[v]*w[:,v] / (1e-5 + sum_v w[:,v]) ).  G in {4,8}. */
 int pmb200_aggregate_views_score(const float *sims, const float *view_weights,
-                                 const pmb200_mlp *head_host, float *score_out,
+                                 const pmb200_mlp *head_host, float *score_out, int score_stride,
                                  int V, int B, int G, int D, int H, int W, void *stream);
 
 /* K-A' + FeatureWeightNet head (models/patchmatch.py:597-601,624): sigmoid(MLP(correlation)).
@@ -190,7 +193,7 @@ int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets,
  */
 int pmb200_init_propagate(const float *seed_map, const float *offsets,
                           const float *depth_min, const float *depth_max, float *out, float *xnorm_out,
-                          int mode, int B, int H, int W, int Ns, int Kp, int dilation,
+                          int xnorm_stride, int mode, int B, int H, int W, int Ns, int Kp, int dilation,
                           float interval_scale, void *stream);
 
 /* ------------------------------------------------------------------------------------
@@ -208,6 +211,7 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets,
  *   is_inverse      stage-1 last-iteration inverse-depth index regression (:227-234)
  */
 int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *xnorm,
+                         const float *xnorm_score, /* NULL, or interleaved [B,D,H,W,2] replacing score0 + xnorm */
                          const float *offsets,
                          const float *feature_weight, const float *depth_min, const float *depth_max,
                          float *prob_out, float *depth_out,

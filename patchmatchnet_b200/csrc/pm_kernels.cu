@@ -172,6 +172,7 @@ struct WarpCorrParams {
     float *out;
     int V, B, H, W, Hs, Ws, D;
     float sx, sy;
+    int ostride = 1;  // element stride of the score epilogue's output (2: the .y lane of an (xnorm, score) buffer)
 };
 
 // Epilogue of the fused warp+correlation kernel
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const Wa
             for (int g = 0; g < G; ++g) x[g] = s_sim[warp][e * G + g];
             const float y = mlp_eval<G>(mlp, x);
             const int en = n0 + e % M::PPW, ed = d0 + e / M::PPW;
-            if (en < HW && ed < p.D) p.out[((size_t)b * p.D + ed) * HW + en] = y;
+            if (en < HW && ed < p.D) p.out[(((size_t)b * p.D + ed) * HW + en) * p.ostride] = y;
         }
     }
 }
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(kWarps2 * 32) warp_corr2_kernel(const WarpCorr
 #pragma unroll
             for (int g = 0; g < G; ++g) x[g] = acc[k][g] / wsum;
             const float y = mlp_eval<G>(mlp, x);
-            if (ev[k]) p.out[((size_t)b * p.D + d) * HW + n] = y;
+            if (ev[k]) p.out[(((size_t)b * p.D + d) * HW + n) * p.ostride] = y;
         }
     }
 }
@@ -813,7 +814,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
 #pragma unroll
             for (int g = 0; g < G; ++g) x[g] = acc[k][g] / wsum;
             const float y = mlp_eval<G>(mlp, x);
-            if (ev[k]) p.out[((size_t)b * p.D + d) * HW + n] = y;
+            if (ev[k]) p.out[(((size_t)b * p.D + d) * HW + n) * p.ostride] = y;
         }
     }
 }
@@ -821,7 +822,8 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
 // sum_v sims[v]*w_v / (1e-5 + sum_v w_v) -> SimilarityNet head -> score [B,D,H,W]   (first stage-3 iteration, eval)
 template <int G>
 __global__ void aggregate_score_kernel(const float *__restrict__ sims, const float *__restrict__ vw,
-                                       float *__restrict__ score, const MlpParams mlp, int V, int B, int D, int HW) {
+                                       float *__restrict__ score, const MlpParams mlp, int V, int B, int D, int HW,
+                                       int ostride) {
     const size_t total = (size_t)B * D * HW;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -841,7 +843,7 @@ __global__ void aggregate_score_kernel(const float *__restrict__ sims, const flo
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) x[g] = x[g] / wsum;
-    score[idx] = mlp_eval<G>(mlp, x);
+    score[idx * ostride] = mlp_eval<G>(mlp, x);
 }
 
 // Any C % G == 0: one thread per (batch, hypothesis, pixel), scalar channel loop.  Slow path.
@@ -1167,6 +1169,7 @@ __global__ void relative_projection_kernel(const ProjParams p) {
 struct PropParams {
     const float *seed, *offsets, *dmin, *dmax;
     float *out, *xnorm;
+    int xstride;  // element stride of xnorm (2 when it is the .x lane of an interleaved (xnorm, score) buffer)
     int mode, B, H, W, Ns, Kp, dilation;
     float interval_scale;
 };
@@ -1256,7 +1259,7 @@ __global__ void __launch_bounds__(128) init_propagate_kernel(const PropParams p)
             const int k = slot + 32 * r;
             if (k < D) {
                 p.out[((size_t)b * D + k) * HW + n] = v[r];
-                if (p.xnorm) p.xnorm[((size_t)b * D + k) * HW + n] = pm::normalised_inverse_depth(v[r], inv_min, inv_max);
+                if (p.xnorm) p.xnorm[(((size_t)b * D + k) * HW + n) * p.xstride] = pm::normalised_inverse_depth(v[r], inv_min, inv_max);
             }
         }
     }
@@ -1272,7 +1275,7 @@ __global__ void __launch_bounds__(128) init_only_kernel(const PropParams p) {
     for (int k = 0; k < p.Ns; ++k) {
         const float v = own_hypothesis(p, b, n, k, HW, inv_min, inv_max);
         p.out[((size_t)b * p.Ns + k) * HW + n] = v;
-        if (p.xnorm) p.xnorm[((size_t)b * p.Ns + k) * HW + n] = pm::normalised_inverse_depth(v, inv_min, inv_max);
+        if (p.xnorm) p.xnorm[(((size_t)b * p.Ns + k) * HW + n) * p.xstride] = pm::normalised_inverse_depth(v, inv_min, inv_max);
     }
 }
 
@@ -1300,8 +1303,7 @@ __global__ void init_propagate_generic_kernel(const PropParams p) {
         }
     }
     if (p.xnorm) {
-        float *xc = p.xnorm + (size_t)b * D * HW + n;
-        for (int k = 0; k < D; ++k) xc[(size_t)k * HW] = pm::normalised_inverse_depth(col[(size_t)k * HW], inv_min, inv_max);
+        for (int k = 0; k < D; ++k) p.xnorm[(((size_t)b * D + k) * HW + n) * p.xstride] = pm::normalised_inverse_depth(col[(size_t)k * HW], inv_min, inv_max);
     }
 }
 
@@ -1311,6 +1313,7 @@ __global__ void init_propagate_generic_kernel(const PropParams p) {
 
 struct EvalParams {
     const float *score0, *depth, *xnorm, *offsets, *fw, *dmin, *dmax;
+    const float2 *xs;  // optional interleaved (xnorm, score0): one 8-byte gather per tap instead of two 4-byte ones
     float *prob, *depth_out;
     int B, D, H, W, K, dilation, is_inverse;
     float interval_scale;
@@ -1351,7 +1354,25 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
     for (int d = ty; d < p.D; d += DY) {
         const float *smap = p.score0 + ((size_t)b * p.D + d) * HW;
         float num = 0.0f, den = 0.0f;
-        if (p.xnorm) {  // normalised inverse depth precomputed by K-C: 8 loads + 8 FMAs per neighbour
+        if (p.xs) {
+            const float2 *xsm = p.xs + ((size_t)b * p.D + d) * HW;
+            const float xc = __ldg(xsm + nc).x;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                const float4 w = cw[k * TP + tp];
+                const int key = ck[k * TP + tp];
+                const int r0 = pm::cell_r0(key), ddx = pm::cell_dx(key), ddy = pm::cell_dy(key);
+                const float2 *q0 = xsm + r0, *q2 = q0 + ddy * p.W;
+                const float2 v0 = __ldg(q0), v1 = __ldg(q0 + ddx), v2 = __ldg(q2), v3 = __ldg(q2 + ddx);
+                const float2 acc = ffma2(v3, make_float2(w.w, w.w), ffma2(v2, make_float2(w.z, w.z),
+                                   ffma2(v1, make_float2(w.y, w.y), make_float2(v0.x * w.x, v0.y * w.x))));
+                const float t = fminf(fabsf(acc.x - xc) * inv_interval, 4.0f);
+                const float sg = __fdividef(1.0f, 1.0f + __expf(2.0f * t - 4.0f));
+                const float wk = sg * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+                num = fmaf(acc.y, wk, num);
+                den += wk;
+            }
+        } else if (p.xnorm) {  // normalised inverse depth precomputed by K-C: 8 loads + 8 FMAs per neighbour
             const float *xmap = p.xnorm + ((size_t)b * p.D + d) * HW;
             const float xc = __ldg(xmap + nc);
 #pragma unroll
@@ -1643,7 +1664,8 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
 namespace {
 int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float *src_nhwc, const float *rt,
                    const float *depth, const float *view_weights, const pmb200_mlp *head_host, float *out,
-                   float *sims_out, int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D, void *stream) {
+                   float *sims_out, int out_stride, int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D,
+                   void *stream) {
     if (!ref_nhwc || !src_nhwc || !rt || !depth || !out || !head_host) return fail(PMB200_EINVAL, "warp_corr head: null pointer");
     if (epi == kEpiScore && !view_weights) return fail(PMB200_EINVAL, "warp_corr_score: view_weights missing");
     if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || B > 65535 || H < 1 || W < 1 || Hs < 1 || Ws < 1 || D < 1)
@@ -1654,6 +1676,7 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
     p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
     p.sx = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 1.0f;
     p.sy = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 1.0f;
+    p.ostride = out_stride < 1 ? 1 : out_stride;
     const MlpParams m = to_device_layout(head_host);
     const int HW = H * W;
     cudaStream_t st = as_stream(stream);
@@ -1685,29 +1708,31 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
 }  // namespace
 
 int pmb200_warp_corr_score(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth,
-                           const float *view_weights, const pmb200_mlp *head_host, float *score_out, int V, int B, int C,
-                           int G, int H, int W, int Hs, int Ws, int D, void *stream) {
+                           const float *view_weights, const pmb200_mlp *head_host, float *score_out, int score_stride,
+                           int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D, void *stream) {
     return warp_corr_head("warp_corr_score", kEpiScore, ref_nhwc, src_nhwc, rt, depth, view_weights, head_host, score_out,
-                          nullptr, V, B, C, G, H, W, Hs, Ws, D, stream);
+                          nullptr, score_stride, V, B, C, G, H, W, Hs, Ws, D, stream);
 }
 
 int pmb200_warp_corr_view_weights(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth,
                                   const pmb200_mlp *head_host, float *view_weights_out, float *sims_out, int V, int B,
                                   int C, int G, int H, int W, int Hs, int Ws, int D, void *stream) {
     return warp_corr_head("warp_corr_view_weights", kEpiViewW, ref_nhwc, src_nhwc, rt, depth, nullptr, head_host,
-                          view_weights_out, sims_out, V, B, C, G, H, W, Hs, Ws, D, stream);
+                          view_weights_out, sims_out, 1, V, B, C, G, H, W, Hs, Ws, D, stream);
 }
 
 int pmb200_aggregate_views_score(const float *sims, const float *view_weights, const pmb200_mlp *head_host,
-                                 float *score_out, int V, int B, int G, int D, int H, int W, void *stream) {
+                                 float *score_out, int score_stride, int V, int B, int G, int D, int H, int W,
+                                 void *stream) {
     if (!sims || !view_weights || !head_host || !score_out) return fail(PMB200_EINVAL, "aggregate_views_score: null pointer");
     if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || D < 1 || H < 1 || W < 1)
         return fail(PMB200_EINVAL, "aggregate_views_score: bad size");
     const MlpParams m = to_device_layout(head_host);
     const size_t total = (size_t)B * D * H * W;
     const unsigned blocks = (unsigned)((total + 127) / 128);
-    if (G == 8) aggregate_score_kernel<8><<<blocks, 128, 0, as_stream(stream)>>>(sims, view_weights, score_out, m, V, B, D, H * W);
-    else if (G == 4) aggregate_score_kernel<4><<<blocks, 128, 0, as_stream(stream)>>>(sims, view_weights, score_out, m, V, B, D, H * W);
+    const int os = score_stride < 1 ? 1 : score_stride;
+    if (G == 8) aggregate_score_kernel<8><<<blocks, 128, 0, as_stream(stream)>>>(sims, view_weights, score_out, m, V, B, D, H * W, os);
+    else if (G == 4) aggregate_score_kernel<4><<<blocks, 128, 0, as_stream(stream)>>>(sims, view_weights, score_out, m, V, B, D, H * W, os);
     else return fail(PMB200_EUNSUPPORTED, "aggregate_views_score: G must be 4 or 8");
     return launch_status("aggregate_views_score");
 }
@@ -1782,8 +1807,8 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out, 
 }
 
 int pmb200_init_propagate(const float *seed_map, const float *offsets, const float *depth_min,
-                          const float *depth_max, float *out, float *xnorm_out, int mode, int B, int H, int W, int Ns,
-                          int Kp, int dilation, float interval_scale, void *stream) {
+                          const float *depth_max, float *out, float *xnorm_out, int xnorm_stride, int mode, int B, int H,
+                          int W, int Ns, int Kp, int dilation, float interval_scale, void *stream) {
     if (!seed_map || !depth_min || !depth_max || !out) return fail(PMB200_EINVAL, "init_propagate: null pointer");
     if (B < 1 || B > 65535 || H < 2 || W < 2 || Ns < 1) return fail(PMB200_EINVAL, "init_propagate: bad size");
     if (mode < 0 || mode > 2) return fail(PMB200_EINVAL, "init_propagate: bad mode");
@@ -1795,6 +1820,7 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets, const flo
     if (Ns + Kp > PMB200_MAX_HYPOTHESES) return fail(PMB200_EINVAL, "init_propagate: too many hypotheses");
     PropParams p;
     p.seed = seed_map; p.offsets = offsets; p.dmin = depth_min; p.dmax = depth_max; p.out = out; p.xnorm = xnorm_out;
+    p.xstride = xnorm_stride < 1 ? 1 : xnorm_stride;
     p.mode = mode; p.B = B; p.H = H; p.W = W; p.Ns = Ns; p.Kp = Kp; p.dilation = dilation;
     p.interval_scale = interval_scale;
     const int HW = H * W, D = Ns + Kp;
@@ -1813,11 +1839,12 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets, const flo
     return launch_status("init_propagate");
 }
 
-int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *xnorm, const float *offsets,
-                         const float *feature_weight, const float *depth_min, const float *depth_max,
-                         float *prob_out, float *depth_out, int B, int D, int H, int W, int K, int dilation,
-                         float interval_scale, int is_inverse, void *stream) {
-    if (!score0 || !depth_sample || !offsets || !feature_weight || !depth_min || !depth_max || !prob_out || !depth_out)
+int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *xnorm, const float *xnorm_score,
+                         const float *offsets, const float *feature_weight, const float *depth_min,
+                         const float *depth_max, float *prob_out, float *depth_out, int B, int D, int H, int W, int K,
+                         int dilation, float interval_scale, int is_inverse, void *stream) {
+    if ((!score0 && !xnorm_score) || !depth_sample || !offsets || !feature_weight || !depth_min || !depth_max || !prob_out ||
+        !depth_out)
         return fail(PMB200_EINVAL, "adaptive_eval: null pointer");
     if (B < 1 || B > 65535 || H < 2 || W < 2 || D < 1 || D > PMB200_MAX_HYPOTHESES)
         return fail(PMB200_EINVAL, "adaptive_eval: bad size");
@@ -1825,6 +1852,7 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
     if (is_inverse && D < 2) return fail(PMB200_EINVAL, "adaptive_eval: inverse regression needs D >= 2");
     EvalParams p;
     p.score0 = score0; p.depth = depth_sample; p.xnorm = xnorm; p.offsets = offsets; p.fw = feature_weight;
+    p.xs = reinterpret_cast<const float2 *>(xnorm_score);
     p.dmin = depth_min; p.dmax = depth_max; p.prob = prob_out; p.depth_out = depth_out;
     p.B = B; p.D = D; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.is_inverse = is_inverse;
     p.interval_scale = interval_scale;

@@ -175,18 +175,27 @@ def _warp_args(ref_nhwc, src_nhwc, rt, depth):
     return ref, src, rt, depth, (V, B, C, H, W, Hs, Ws, D)
 
 
+def _score_target(xs: Optional[Tensor], B: int, D: int, H: int, W: int, device):
+    if xs is None:
+        out = torch.empty((B, D, H, W), dtype=torch.float32, device=device)
+        return out, out.data_ptr(), 1
+    if xs.shape != (B, D, H, W, 2) or not xs.is_contiguous() or xs.dtype != torch.float32 or xs.device != device:
+        raise RuntimeError("xs must be a contiguous float32 [B,D,H,W,2] buffer on the same device")
+    return xs, xs.data_ptr() + 4, 2  # the .y lanes
+
+
 def warp_corr_score(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tensor, G: int, view_weights: Tensor,
-                    head: "_native.MlpStruct") -> Tensor:
+                    head: "_native.MlpStruct", xs: Optional[Tensor] = None) -> Tensor:
     """K-A with the SimilarityNet head fused (eval mode): -> raw score [B,D,H,W]; the similarity
     tensor is never written.  `head` holds the BN-folded weights (host struct, see PointwiseHead.folded)."""
     ref, src, rt, depth, (V, B, C, H, W, Hs, Ws, D) = _warp_args(ref_nhwc, src_nhwc, rt, depth)
     vw = _require(view_weights, "view_weights", 4)
     if vw.shape != (B, V, H, W):
         raise RuntimeError("warp_corr_score: view_weights must be [B,V,H,W]")
-    out = torch.empty((B, D, H, W), dtype=torch.float32, device=ref.device)
+    out, out_ptr, stride = _score_target(xs, B, D, H, W, ref.device)
     with torch.cuda.device(ref.device):
         rc = _native.lib().pmb200_warp_corr_score(
-            ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), vw.data_ptr(), head, out.data_ptr(),
+            ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), vw.data_ptr(), head, out_ptr, stride,
             V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
         )
     _native.check(rc, "warp_corr_score")
@@ -209,17 +218,17 @@ def warp_corr_view_weights(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth
     return (out, sims) if keep_sims else out
 
 
-def aggregate_views_score(sims: Tensor, view_weights: Tensor, head: "_native.MlpStruct") -> Tensor:
+def aggregate_views_score(sims: Tensor, view_weights: Tensor, head: "_native.MlpStruct", xs: Optional[Tensor] = None) -> Tensor:
     """MLP(sum_v sims[v]*w[:,v] / (1e-5 + sum_v w[:,v])) -> raw score [B,D,H,W]."""
     sims = _require(sims, "sims", 6)
     vw = _require(view_weights, "view_weights", 4)
     V, B, G, D, H, W = sims.shape
     if vw.shape != (B, V, H, W):
         raise RuntimeError("aggregate_views_score: view_weights must be [B,V,H,W]")
-    out = torch.empty((B, D, H, W), dtype=torch.float32, device=sims.device)
+    out, out_ptr, stride = _score_target(xs, B, D, H, W, sims.device)
     with torch.cuda.device(sims.device):
         rc = _native.lib().pmb200_aggregate_views_score(
-            sims.data_ptr(), vw.data_ptr(), head, out.data_ptr(), V, B, G, D, H, W, _stream(sims)
+            sims.data_ptr(), vw.data_ptr(), head, out_ptr, stride, V, B, G, D, H, W, _stream(sims)
         )
     _native.check(rc, "aggregate_views_score")
     return out
@@ -279,6 +288,12 @@ def offset_corr(ref_nhwc: Tensor, offsets: Tensor, G: int, K: int, dilation: int
 MODE_RANDOM, MODE_PERTURB, MODE_PASSTHROUGH = 0, 1, 2
 
 
+def alloc_xs(B: int, D: int, H: int, W: int, device) -> Tensor:
+    """Interleaved (normalised inverse depth, raw score) buffer [B,D,H,W,2]: K-C fills the .x lanes, the K-A score
+    epilogue the .y lanes, K-B then gathers both with one 8-byte load per tap."""
+    return torch.empty((B, D, H, W, 2), dtype=torch.float32, device=device)
+
+
 def init_propagate(
     seed_map: Tensor,
     offsets: Optional[Tensor],
@@ -290,9 +305,11 @@ def init_propagate(
     dilation: int,
     interval_scale: float,
     with_xnorm: bool = False,
+    xs: Optional[Tensor] = None,
 ):
     """K-C.  seed_map: U[0,1) noise [B,48,H,W] (mode 0) or current depth [B,1,H,W]; -> [B,Ns+Kp,H,W]
-    (and, with_xnorm, the normalised inverse depth of every hypothesis, same shape)."""
+    (and, with_xnorm, the normalised inverse depth of every hypothesis, same shape).  With `xs` (an interleaved
+    (xnorm, score) buffer [B,Ns+Kp,H,W,2] from alloc_xs) the normalised inverse depth goes into its .x lanes."""
     seed = _require(seed_map, "seed_map", 4)
     B, S, H, W = seed.shape
     if S != (48 if mode == MODE_RANDOM else 1):
@@ -308,14 +325,21 @@ def init_propagate(
             raise RuntimeError("init_propagate: offsets must be [B,2Kp,H,W]")
         off_ptr = off.data_ptr()
     out = torch.empty((B, Ns + Kp, H, W), dtype=torch.float32, device=seed.device)
-    xn = torch.empty_like(out) if with_xnorm else None
+    if xs is not None:
+        if xs.shape != (B, Ns + Kp, H, W, 2) or not xs.is_contiguous() or xs.dtype != torch.float32 or not xs.is_cuda:
+            raise RuntimeError("init_propagate: xs must be a contiguous CUDA float32 [B,Ns+Kp,H,W,2] buffer")
+        xn, xn_ptr, xstride = None, xs.data_ptr(), 2
+    else:
+        xn = torch.empty_like(out) if with_xnorm else None
+        xn_ptr, xstride = (None if xn is None else xn.data_ptr()), 1
     with torch.cuda.device(seed.device):
         rc = _native.lib().pmb200_init_propagate(
-            seed.data_ptr(), off_ptr, dmin.data_ptr(), dmax.data_ptr(), out.data_ptr(),
-            None if xn is None else xn.data_ptr(),
+            seed.data_ptr(), off_ptr, dmin.data_ptr(), dmax.data_ptr(), out.data_ptr(), xn_ptr, xstride,
             mode, B, H, W, Ns, Kp, dilation, float(interval_scale), _stream(seed),
         )
     _native.check(rc, "init_propagate")
+    if xs is not None:
+        return out
     return (out, xn) if with_xnorm else out
 
 
@@ -330,9 +354,17 @@ def adaptive_eval(
     interval_scale: float,
     is_inverse: bool,
     xnorm: Optional[Tensor] = None,
+    xs: Optional[Tensor] = None,
 ):
-    """K-B.  -> (depth [B,H,W], prob [B,D,H,W]).  xnorm: normalised inverse depth from init_propagate."""
-    sc = _require(score0, "score0", 4)
+    """K-B.  -> (depth [B,H,W], prob [B,D,H,W]).  xnorm: normalised inverse depth from init_propagate.
+    With `xs` (interleaved (xnorm, score) buffer) `score0` is ignored and may be None."""
+    if xs is not None:
+        if xs.dim() != 5 or xs.shape[-1] != 2 or not xs.is_contiguous() or not xs.is_cuda or xs.dtype != torch.float32:
+            raise RuntimeError("adaptive_eval: xs must be a contiguous CUDA float32 [B,D,H,W,2] buffer")
+        score0 = xs[..., 1]  # shape carrier only; never made contiguous below
+        sc = score0
+    else:
+        sc = _require(score0, "score0", 4)
     ds = _require(depth_sample, "depth_sample", 4)
     off = _require(offsets, "offsets", 4)
     fw = _require(feature_weight, "feature_weight", 4)
@@ -352,7 +384,7 @@ def adaptive_eval(
     depth = torch.empty((B, H, W), dtype=torch.float32, device=sc.device)
     with torch.cuda.device(sc.device):
         rc = _native.lib().pmb200_adaptive_eval(
-            sc.data_ptr(), ds.data_ptr(), xn_ptr, off.data_ptr(), fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
+            None if xs is not None else sc.data_ptr(), ds.data_ptr(), xn_ptr, None if xs is None else xs.data_ptr(), off.data_ptr(), fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
             prob.data_ptr(), depth.data_ptr(), B, D, H, W, K, dilation, float(interval_scale),
             1 if is_inverse else 0, _stream(sc),
         )

@@ -284,7 +284,15 @@ class PatchMatch(nn.Module):
                 seed, mode, ns = sample.detach(), ops.MODE_PASSTHROUGH, 1
             else:
                 seed, mode, ns = sample.detach(), ops.MODE_PERTURB, self.patchmatch_num_sample
-            if need_grad and kp_now > 0:
+            xs = None
+            if fused:  # (xnorm, score) interleaved: K-C writes .x, the K-A epilogue .y, K-B gathers both at once
+                xs = ops.alloc_xs(B, ns + kp_now, H, W, ref_feature.device)
+                hyp = ops.init_propagate(
+                    seed, propa_off if kp_now > 0 else None, depth_min, depth_max,
+                    mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale, xs=xs,
+                )
+                xnorm = None
+            elif need_grad and kp_now > 0:
                 hyp, xnorm = ag.InitPropagate.apply(
                     seed, propa_off, depth_min, depth_max, mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale
                 )
@@ -301,11 +309,12 @@ class PatchMatch(nn.Module):
                     view_weights, sims = ops.warp_corr_view_weights(
                         ref_nhwc, src_nhwc, rt, hyp, self.G, self.evaluation.pixel_wise_net.folded(), keep_sims=True
                     )
-                    score0 = ops.aggregate_views_score(sims, view_weights, self.evaluation.similarity_net.folded())
+                    ops.aggregate_views_score(sims, view_weights, self.evaluation.similarity_net.folded(), xs=xs)
                 else:
-                    score0 = ops.warp_corr_score(
-                        ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights, self.evaluation.similarity_net.folded()
+                    ops.warp_corr_score(
+                        ref_nhwc, src_nhwc, rt, hyp, self.G, view_weights, self.evaluation.similarity_net.folded(), xs=xs
                     )
+                score0 = None
             elif need_grad:
                 if is_empty(view_weights):
                     sims = ag.WarpCorr.apply(ref_nhwc, src_nhwc, rt, hyp, None, self.G)  # [V,B,G,D,H,W]
@@ -337,7 +346,7 @@ class PatchMatch(nn.Module):
             else:
                 new_depth, prob = ops.adaptive_eval(
                     score0, hyp, eval_off, feature_weight, depth_min, depth_max,
-                    self.dilation, self.patchmatch_interval_scale, last_of_stage1, xnorm=xnorm,
+                    self.dilation, self.patchmatch_interval_scale, last_of_stage1, xnorm=xnorm, xs=xs,
                 )
             sample = new_depth.unsqueeze(1)
             outs.append(sample)

@@ -303,6 +303,9 @@ def test_init_propagate_matches_oracle(mode, Ns, Kp, dil, H, W, B):
     assert maxabs(got_x, want_x) <= 5e-6
     assert pm_cases.rel_l1(got, want) <= 1e-6
     assert maxabs(got, want) <= 2e-3  # depths are ~400..1000: a few fp32 ulps
+    xs = ops.alloc_xs(B, Ns + Kp, H, W, DEV).fill_(-7.0)
+    got2 = ops.init_propagate(seed.to(DEV), None if off is None else off.to(DEV), dmin.to(DEV), dmax.to(DEV), m, Ns, Kp, dil, scale, xs=xs)
+    assert torch.equal(got2, got) and torch.equal(xs[..., 0], got_x) and bool((xs[..., 1] == -7.0).all())
     if Kp > 0:
         assert bool((got[:, 1:] >= got[:, :-1]).all())  # sorted ascending
 
@@ -332,9 +335,10 @@ def test_adaptive_eval_matches_oracle(D, K, dil, H, W, B, inverse):
     want_depth = pm_oracle._Evaluation.regress(depth, want_prob, inverse)
     inv_min, inv_max = (1.0 / dmin).view(B, 1, 1, 1), (1.0 / dmax).view(B, 1, 1, 1)
     xnorm = (1.0 / depth - inv_max) / (inv_min - inv_max)
-    for xn in (None, xnorm.to(DEV)):  # recomputed per tap, or precomputed by K-C
-        got_depth, got_prob = ops.adaptive_eval(score0.to(DEV), depth.to(DEV), off.to(DEV), fw.to(DEV), dmin.to(DEV), dmax.to(DEV),
-                                                dil, scale, inverse, xnorm=xn)
+    xs = torch.stack([xnorm, score0], dim=-1).contiguous().to(DEV)
+    for xn, inter in ((None, None), (xnorm.to(DEV), None), (None, xs)):  # recomputed per tap / precomputed by K-C / interleaved
+        got_depth, got_prob = ops.adaptive_eval(None if inter is not None else score0.to(DEV), depth.to(DEV), off.to(DEV), fw.to(DEV),
+                                                dmin.to(DEV), dmax.to(DEV), dil, scale, inverse, xnorm=xn, xs=inter)
         assert maxabs(got_prob, want_prob) <= 5e-6
         assert pm_cases.rel_l1(got_depth, want_depth) <= 1e-6
         assert maxabs(got_prob.sum(1), torch.ones(B, H, W)) <= 1e-5
@@ -372,6 +376,9 @@ def test_fused_heads_match_unfused(C, G, H, W, D, B, V):
         want = sim_head(ops.warp_corr(ref_n, src_n, rt, depth_d, G, vw_d))
         got = ops.warp_corr_score(ref_n, src_n, rt, depth_d, G, vw_d, sim_head.folded())
         assert maxabs(got, want) <= 2e-5 * max(1.0, float(want.abs().max()))
+        xs = ops.alloc_xs(B, D, H, W, DEV).fill_(3.0)
+        ops.warp_corr_score(ref_n, src_n, rt, depth_d, G, vw_d, sim_head.folded(), xs=xs)
+        assert torch.equal(xs[..., 1], got) and bool((xs[..., 0] == 3.0).all())
         # PixelwiseNet
         pw = _random_head(PixelwiseNet, G, 2).to(DEV)
         sims = ops.warp_corr(ref_n, src_n, rt, depth_d, G)
@@ -383,6 +390,9 @@ def test_fused_heads_match_unfused(C, G, H, W, D, B, V):
         want_sc = sim_head(ops.aggregate_views(sims, want_vw))
         got_sc = ops.aggregate_views_score(kept, got_vw2, sim_head.folded())
         assert maxabs(got_sc, want_sc) <= 2e-5 * max(1.0, float(want_sc.abs().max()))
+        xs2 = ops.alloc_xs(B, D, H, W, DEV).fill_(3.0)
+        ops.aggregate_views_score(kept, got_vw2, sim_head.folded(), xs=xs2)
+        assert torch.equal(xs2[..., 1], got_sc) and bool((xs2[..., 0] == 3.0).all())
         # FeatureWeightNet head
         K, dil = 9, 2
         off = torch.randn(B, 2 * K, H, W, device=DEV) * 2.0

@@ -77,7 +77,7 @@ for (n, a, k) in calls:
         ref, src, depth = a[0], a[1], a[3]
         desc += f" C{ref.shape[3]} D{depth.shape[1]} {ref.shape[1]}x{ref.shape[2]} V{src.shape[0]}"
     elif n == "adaptive_eval":
-        desc += f" D{a[0].shape[1]} {a[0].shape[2]}x{a[0].shape[3]}"
+        desc += f" D{a[1].shape[1]} {a[1].shape[2]}x{a[1].shape[3]}"
     elif n == "init_propagate":
         desc += f" Ns{a[5]} Kp{a[6]} {a[0].shape[2]}x{a[0].shape[3]}"
     elif n == "offset_corr_weight":
