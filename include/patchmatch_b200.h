@@ -122,8 +122,10 @@ int pmb200_aggregate_views(const float *sims, const float *view_weights, float *
  *   offsets  [B,2K,H,W] raw output of eval_conv;  K in {9,17};  dilation = propagation range
  *   out      [B,G,K,H,W]
  */
-int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out,
+int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, int offsets_channels_last, float *out,
                        int B, int C, int G, int H, int W, int K, int dilation, void *stream);
+/* offsets_channels_last (here and below): 0 = planar [B,2K,H,W]; 1 = channels-last [B,H,W,2K], i.e. the memory a
+ * conv2d on channels-last input produces -- consumed in place, no re-layout copy. */
 
 /* ------------------------------------------------------------------------------------
  * Eval-mode fusion of the learned 1x1x1 heads (SURVEY.md 8f "f2").
@@ -172,7 +174,7 @@ int pmb200_aggregate_views_score(const float *sims, const float *view_weights,
 
 /* K-A' + FeatureWeightNet head (models/patchmatch.py:597-601,624): sigmoid(MLP(correlation)).
  *   weight_out [B,K,H,W] */
-int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets,
+int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets, int offsets_channels_last,
                               const pmb200_mlp *head_host, float *weight_out,
                               int B, int C, int G, int H, int W, int K, int dilation, void *stream);
 
@@ -191,7 +193,7 @@ int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets,
  *   xnorm_out [B,Ns+Kp,H,W] or NULL: (1/out - 1/dmax) / (1/dmin - 1/dmax), the normalised inverse
  *             depth that depth_weight gathers (models/patchmatch.py:655-657), for pmb200_adaptive_eval
  */
-int pmb200_init_propagate(const float *seed_map, const float *offsets,
+int pmb200_init_propagate(const float *seed_map, const float *offsets, int offsets_channels_last,
                           const float *depth_min, const float *depth_max, float *out, float *xnorm_out,
                           int xnorm_stride, int mode, int B, int H, int W, int Ns, int Kp, int dilation,
                           float interval_scale, void *stream);
@@ -212,7 +214,7 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets,
  */
 int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *xnorm,
                          const float *xnorm_score, /* NULL, or interleaved [B,D,H,W,2] replacing score0 + xnorm */
-                         const float *offsets,
+                         const float *offsets, int offsets_channels_last,
                          const float *feature_weight, const float *depth_min, const float *depth_max,
                          float *prob_out, float *depth_out,
                          int B, int D, int H, int W, int K, int dilation,

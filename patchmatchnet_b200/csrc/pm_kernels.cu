@@ -44,6 +44,15 @@ int launch_status(const char *what) {
     return 0;
 }
 
+// Learned 2-D offset (x, y) of neighbour k at pixel n.  The offset convs' output is consumed in place in either
+// layout: planar [B,2K,H,W] (NCHW-contiguous) or channels-last [B,H,W,2K] (what cuDNN emits for a channels-last
+// input; then (x, y) is one aligned 8-byte load).
+__device__ __forceinline__ float2 load_offset(const float *__restrict__ off, int nhwc, int b, int k, int n, int K, int HW) {
+    if (nhwc) return __ldg(reinterpret_cast<const float2 *>(off + ((size_t)b * HW + n) * 2 * K) + k);
+    const float *q = off + ((size_t)b * 2 * K + 2 * k) * HW + n;
+    return make_float2(__ldg(q), __ldg(q + HW));
+}
+
 constexpr int kWarpsPerBlock = 8;
 constexpr int kChunk = 8;  // hypotheses (or neighbours) handled per warp pass
 
@@ -895,6 +904,7 @@ struct OffsetCorrParams {
     const float *ref, *offsets;
     float *out;
     int B, H, W, K, dilation;
+    int off_nhwc = 0;
 };
 
 template <int C, int G, bool HEAD>
@@ -927,8 +937,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) offset_corr_kernel(const 
         if (en < HW && ek < p.K) {
             int dy = 0, dx = 0;
             pm::neighbour_offset(true, p.K, p.dilation, ek, &dy, &dx);
-            const float ox = (float)dx + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * ek) * HW + en);
-            const float oy = (float)dy + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * ek + 1) * HW + en);
+            const float2 lo = load_offset(p.offsets, p.off_nhwc, b, ek, en, p.K, HW);
+            const float ox = (float)dx + lo.x, oy = (float)dy + lo.y;
             c = pm::border_cell((float)(en % p.W) + ox, (float)(en / p.W) + oy, p.H, p.W);
         }
         s_w[warp][e] = make_float4(c.w00, c.w01, c.w10, c.w11);
@@ -989,8 +999,8 @@ __global__ void offset_corr_generic_kernel(const OffsetCorrParams p, int C, int 
     const int b = (int)(idx / ((size_t)HW * p.K));
     int dy = 0, dx = 0;
     pm::neighbour_offset(true, p.K, p.dilation, k, &dy, &dx);
-    const float ox = (float)dx + p.offsets[((size_t)b * 2 * p.K + 2 * k) * HW + n];
-    const float oy = (float)dy + p.offsets[((size_t)b * 2 * p.K + 2 * k + 1) * HW + n];
+    const float2 lo = load_offset(p.offsets, p.off_nhwc, b, k, n, p.K, HW);
+    const float ox = (float)dx + lo.x, oy = (float)dy + lo.y;
     const pm::Cell c = pm::border_cell((float)(n % p.W) + ox, (float)(n / p.W) + oy, p.H, p.W);
     const float *ref = p.ref + ((size_t)b * HW + n) * C;
     const float *t0 = p.ref + ((size_t)b * HW + pm::cell_r0(c.key)) * C;
@@ -1170,6 +1180,7 @@ struct PropParams {
     const float *seed, *offsets, *dmin, *dmax;
     float *out, *xnorm;
     int xstride;  // element stride of xnorm (2 when it is the .x lane of an interleaved (xnorm, score) buffer)
+    int off_nhwc;
     int mode, B, H, W, Ns, Kp, dilation;
     float interval_scale;
 };
@@ -1195,8 +1206,8 @@ __device__ __forceinline__ float propagated_hypothesis(const PropParams &p, int 
                                                        float inv_min, float inv_max) {
     int dy = 0, dx = 0;
     pm::neighbour_offset(false, p.Kp, p.dilation, kk, &dy, &dx);
-    const float ox = (float)dx + __ldg(p.offsets + ((size_t)b * 2 * p.Kp + 2 * kk) * HW + n);
-    const float oy = (float)dy + __ldg(p.offsets + ((size_t)b * 2 * p.Kp + 2 * kk + 1) * HW + n);
+    const float2 lo = load_offset(p.offsets, p.off_nhwc, b, kk, n, p.Kp, HW);
+    const float ox = (float)dx + lo.x, oy = (float)dy + lo.y;
     const pm::Cell c = pm::border_cell((float)(n % p.W) + ox, (float)(n / p.W) + oy, p.H, p.W);
     const int r0 = pm::cell_r0(c.key), ddx = pm::cell_dx(c.key), ddy = pm::cell_dy(c.key);
     float s = centre_hypothesis(p, b, r0, HW, inv_min, inv_max) * c.w00;
@@ -1314,6 +1325,7 @@ __global__ void init_propagate_generic_kernel(const PropParams p) {
 struct EvalParams {
     const float *score0, *depth, *xnorm, *offsets, *fw, *dmin, *dmax;
     const float2 *xs;  // optional interleaved (xnorm, score0): one 8-byte gather per tap instead of two 4-byte ones
+    int off_nhwc;
     float *prob, *depth_out;
     int B, D, H, W, K, dilation, is_inverse;
     float interval_scale;
@@ -1343,8 +1355,8 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
     for (int k = ty; k < p.K; k += DY) {
         int dy = 0, dx = 0;
         pm::neighbour_offset(true, p.K, p.dilation, k, &dy, &dx);
-        const float ox = (float)dx + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * k) * HW + nc);
-        const float oy = (float)dy + __ldg(p.offsets + ((size_t)b * 2 * p.K + 2 * k + 1) * HW + nc);
+        const float2 lo = load_offset(p.offsets, p.off_nhwc, b, k, nc, p.K, HW);
+        const float ox = (float)dx + lo.x, oy = (float)dy + lo.y;
         const pm::Cell c = pm::border_cell((float)(nc % p.W) + ox, (float)(nc / p.W) + oy, p.H, p.W);
         cw[k * TP + tp] = make_float4(c.w00, c.w01, c.w10, c.w11);
         ck[k * TP + tp] = c.key;
@@ -1737,15 +1749,16 @@ int pmb200_aggregate_views_score(const float *sims, const float *view_weights, c
     return launch_status("aggregate_views_score");
 }
 
-int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets, const pmb200_mlp *head_host, float *weight_out,
-                              int B, int C, int G, int H, int W, int K, int dilation, void *stream) {
+int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets, int offsets_channels_last,
+                              const pmb200_mlp *head_host, float *weight_out, int B, int C, int G, int H, int W, int K,
+                              int dilation, void *stream) {
     if (!ref_nhwc || !offsets || !weight_out || !head_host) return fail(PMB200_EINVAL, "offset_corr_weight: null pointer");
     if (B < 1 || B > 65535 || H < 2 || W < 2) return fail(PMB200_EINVAL, "offset_corr_weight: bad size");
     if (K != 9 && K != 17) return fail(PMB200_EUNSUPPORTED, "offset_corr_weight: evaluate_neighbors must be 9 or 17");
     if ((long long)H * W >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "offset_corr_weight: map too large");
     OffsetCorrParams p;
     p.ref = ref_nhwc; p.offsets = offsets; p.out = weight_out;
-    p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation;
+    p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.off_nhwc = offsets_channels_last ? 1 : 0;
     const MlpParams m = to_device_layout(head_host);
     const int HW = H * W;
     cudaStream_t st = as_stream(stream);
@@ -1776,8 +1789,8 @@ int pmb200_aggregate_views(const float *sims, const float *view_weights, float *
     return launch_status("aggregate_views");
 }
 
-int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out, int B, int C, int G, int H, int W,
-                       int K, int dilation, void *stream) {
+int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, int offsets_channels_last, float *out, int B, int C,
+                       int G, int H, int W, int K, int dilation, void *stream) {
     if (!ref_nhwc || !offsets || !out) return fail(PMB200_EINVAL, "offset_corr: null pointer");
     if (B < 1 || B > 65535 || H < 2 || W < 2) return fail(PMB200_EINVAL, "offset_corr: bad size");
     if (C < 1 || G < 1 || C % G != 0) return fail(PMB200_EINVAL, "offset_corr: C must be a multiple of G");
@@ -1785,7 +1798,7 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out, 
     if ((long long)H * W >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "offset_corr: map too large");
     OffsetCorrParams p;
     p.ref = ref_nhwc; p.offsets = offsets; p.out = out;
-    p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation;
+    p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.off_nhwc = offsets_channels_last ? 1 : 0;
     const int HW = H * W;
     cudaStream_t st = as_stream(stream);
     const int nchunk = (K + kChunk - 1) / kChunk;
@@ -1806,7 +1819,7 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, float *out, 
     return launch_status("offset_corr");
 }
 
-int pmb200_init_propagate(const float *seed_map, const float *offsets, const float *depth_min,
+int pmb200_init_propagate(const float *seed_map, const float *offsets, int offsets_channels_last, const float *depth_min,
                           const float *depth_max, float *out, float *xnorm_out, int xnorm_stride, int mode, int B, int H,
                           int W, int Ns, int Kp, int dilation, float interval_scale, void *stream) {
     if (!seed_map || !depth_min || !depth_max || !out) return fail(PMB200_EINVAL, "init_propagate: null pointer");
@@ -1821,6 +1834,7 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets, const flo
     PropParams p;
     p.seed = seed_map; p.offsets = offsets; p.dmin = depth_min; p.dmax = depth_max; p.out = out; p.xnorm = xnorm_out;
     p.xstride = xnorm_stride < 1 ? 1 : xnorm_stride;
+    p.off_nhwc = offsets_channels_last ? 1 : 0;
     p.mode = mode; p.B = B; p.H = H; p.W = W; p.Ns = Ns; p.Kp = Kp; p.dilation = dilation;
     p.interval_scale = interval_scale;
     const int HW = H * W, D = Ns + Kp;
@@ -1840,7 +1854,7 @@ int pmb200_init_propagate(const float *seed_map, const float *offsets, const flo
 }
 
 int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const float *xnorm, const float *xnorm_score,
-                         const float *offsets, const float *feature_weight, const float *depth_min,
+                         const float *offsets, int offsets_channels_last, const float *feature_weight, const float *depth_min,
                          const float *depth_max, float *prob_out, float *depth_out, int B, int D, int H, int W, int K,
                          int dilation, float interval_scale, int is_inverse, void *stream) {
     if ((!score0 && !xnorm_score) || !depth_sample || !offsets || !feature_weight || !depth_min || !depth_max || !prob_out ||
@@ -1853,6 +1867,7 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
     EvalParams p;
     p.score0 = score0; p.depth = depth_sample; p.xnorm = xnorm; p.offsets = offsets; p.fw = feature_weight;
     p.xs = reinterpret_cast<const float2 *>(xnorm_score);
+    p.off_nhwc = offsets_channels_last ? 1 : 0;
     p.dmin = depth_min; p.dmax = depth_max; p.prob = prob_out; p.depth_out = depth_out;
     p.B = B; p.D = D; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.is_inverse = is_inverse;
     p.interval_scale = interval_scale;

@@ -27,6 +27,20 @@ def _require(t: Tensor, name: str, ndim: Optional[int] = None) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _offsets_arg(off: Tensor, shape, name: str):
+    """(tensor, channels_last flag) for a raw offset-conv output: planar NCHW memory or channels-last memory are both
+    consumed in place; anything else is made NCHW-contiguous."""
+    if not off.is_cuda or off.dtype != torch.float32:
+        raise RuntimeError(f"{name}: offsets must be a CUDA float32 tensor (got {off.dtype} on {off.device}); there is no CPU fallback")
+    if tuple(off.shape) != tuple(shape):
+        raise RuntimeError(f"{name}: offsets must be {tuple(shape)}, got {tuple(off.shape)}")
+    if off.is_contiguous():
+        return off, 0
+    if off.is_contiguous(memory_format=torch.channels_last):
+        return off, 1
+    return off.contiguous(), 0
+
+
 def _stream(t: Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -237,14 +251,12 @@ def aggregate_views_score(sims: Tensor, view_weights: Tensor, head: "_native.Mlp
 def offset_corr_weight(ref_nhwc: Tensor, offsets: Tensor, G: int, K: int, dilation: int, head: "_native.MlpStruct") -> Tensor:
     """K-A' with the FeatureWeightNet head fused (eval mode): -> feature weight [B,K,H,W]."""
     ref = _require(ref_nhwc, "ref_nhwc", 4)
-    off = _require(offsets, "offsets", 4)
     B, H, W, C = ref.shape
-    if off.shape != (B, 2 * K, H, W):
-        raise RuntimeError("offset_corr_weight: offsets must be [B,2K,H,W]")
+    off, off_cl = _offsets_arg(offsets, (B, 2 * K, H, W), "offset_corr_weight")
     out = torch.empty((B, K, H, W), dtype=torch.float32, device=ref.device)
     with torch.cuda.device(ref.device):
         rc = _native.lib().pmb200_offset_corr_weight(
-            ref.data_ptr(), off.data_ptr(), head, out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
+            ref.data_ptr(), off.data_ptr(), off_cl, head, out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
         )
     _native.check(rc, "offset_corr_weight")
     return out
@@ -272,14 +284,12 @@ def aggregate_views(sims: Tensor, view_weights: Tensor) -> Tensor:
 def offset_corr(ref_nhwc: Tensor, offsets: Tensor, G: int, K: int, dilation: int) -> Tensor:
     """K-A'.  ref [B,H,W,C], offsets [B,2K,H,W] -> [B,G,K,H,W]."""
     ref = _require(ref_nhwc, "ref_nhwc", 4)
-    off = _require(offsets, "offsets", 4)
     B, H, W, C = ref.shape
-    if off.shape != (B, 2 * K, H, W):
-        raise RuntimeError("offset_corr: offsets must be [B,2K,H,W]")
+    off, off_cl = _offsets_arg(offsets, (B, 2 * K, H, W), "offset_corr")
     out = torch.empty((B, G, K, H, W), dtype=torch.float32, device=ref.device)
     with torch.cuda.device(ref.device):
         rc = _native.lib().pmb200_offset_corr(
-            ref.data_ptr(), off.data_ptr(), out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
+            ref.data_ptr(), off.data_ptr(), off_cl, out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
         )
     _native.check(rc, "offset_corr")
     return out
@@ -318,11 +328,9 @@ def init_propagate(
     dmax = _require(depth_max.reshape(-1), "depth_max", 1)
     if dmin.numel() != B or dmax.numel() != B:
         raise RuntimeError("init_propagate: depth_min/max must have B elements")
-    off_ptr = None
+    off_ptr, off_cl = None, 0
     if Kp > 0:
-        off = _require(offsets, "offsets", 4)
-        if off.shape != (B, 2 * Kp, H, W):
-            raise RuntimeError("init_propagate: offsets must be [B,2Kp,H,W]")
+        off, off_cl = _offsets_arg(offsets, (B, 2 * Kp, H, W), "init_propagate")
         off_ptr = off.data_ptr()
     out = torch.empty((B, Ns + Kp, H, W), dtype=torch.float32, device=seed.device)
     if xs is not None:
@@ -334,7 +342,7 @@ def init_propagate(
         xn_ptr, xstride = (None if xn is None else xn.data_ptr()), 1
     with torch.cuda.device(seed.device):
         rc = _native.lib().pmb200_init_propagate(
-            seed.data_ptr(), off_ptr, dmin.data_ptr(), dmax.data_ptr(), out.data_ptr(), xn_ptr, xstride,
+            seed.data_ptr(), off_ptr, off_cl, dmin.data_ptr(), dmax.data_ptr(), out.data_ptr(), xn_ptr, xstride,
             mode, B, H, W, Ns, Kp, dilation, float(interval_scale), _stream(seed),
         )
     _native.check(rc, "init_propagate")
@@ -366,11 +374,11 @@ def adaptive_eval(
     else:
         sc = _require(score0, "score0", 4)
     ds = _require(depth_sample, "depth_sample", 4)
-    off = _require(offsets, "offsets", 4)
     fw = _require(feature_weight, "feature_weight", 4)
     B, D, H, W = sc.shape
     K = fw.shape[1]
-    if ds.shape != sc.shape or off.shape != (B, 2 * K, H, W) or fw.shape != (B, K, H, W):
+    off, off_cl = _offsets_arg(offsets, (B, 2 * K, H, W), "adaptive_eval")
+    if ds.shape != sc.shape or fw.shape != (B, K, H, W):
         raise RuntimeError("adaptive_eval: inconsistent shapes")
     dmin = _require(depth_min.reshape(-1), "depth_min", 1)
     dmax = _require(depth_max.reshape(-1), "depth_max", 1)
@@ -384,7 +392,7 @@ def adaptive_eval(
     depth = torch.empty((B, H, W), dtype=torch.float32, device=sc.device)
     with torch.cuda.device(sc.device):
         rc = _native.lib().pmb200_adaptive_eval(
-            None if xs is not None else sc.data_ptr(), ds.data_ptr(), xn_ptr, None if xs is None else xs.data_ptr(), off.data_ptr(), fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
+            None if xs is not None else sc.data_ptr(), ds.data_ptr(), xn_ptr, None if xs is None else xs.data_ptr(), off.data_ptr(), off_cl, fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
             prob.data_ptr(), depth.data_ptr(), B, D, H, W, K, dilation, float(interval_scale),
             1 if is_inverse else 0, _stream(sc),
         )

@@ -50,10 +50,10 @@ def test_abi_version_and_errors_without_gpu(lib):
     assert lib.pmb200_warp_corr(one, one, one, one, None, one, 1, 1, 16, 5, 4, 4, 4, 4, 1, None) == -1
     assert lib.pmb200_warp_corr(one, one, one, one, None, one, 99, 1, 16, 4, 4, 4, 4, 4, 1, None) == -1
     # neighbour counts the reference raises NotImplementedError for -> PMB200_EUNSUPPORTED
-    assert lib.pmb200_offset_corr(one, one, one, 1, 16, 4, 4, 4, 10, 2, None) == -2
-    assert lib.pmb200_init_propagate(one, one, one, one, one, None, 1, 1, 1, 4, 4, 8, 5, 2, 0.1, None) == -2
-    assert lib.pmb200_adaptive_eval(one, one, None, None, one, one, one, one, one, one, 1, 8, 4, 4, 11, 2, 0.1, 0, None) == -2
-    assert lib.pmb200_init_propagate(one, one, one, one, one, None, 1, 0, 1, 4, 4, 16, 8, 2, 0.1, None) == -1  # random init has 48
+    assert lib.pmb200_offset_corr(one, one, 0, one, 1, 16, 4, 4, 4, 10, 2, None) == -2
+    assert lib.pmb200_init_propagate(one, one, 0, one, one, one, None, 1, 1, 1, 4, 4, 8, 5, 2, 0.1, None) == -2
+    assert lib.pmb200_adaptive_eval(one, one, None, None, one, 0, one, one, one, one, one, 1, 8, 4, 4, 11, 2, 0.1, 0, None) == -2
+    assert lib.pmb200_init_propagate(one, one, 0, one, one, one, None, 1, 0, 1, 4, 4, 16, 8, 2, 0.1, None) == -1  # random init has 48
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

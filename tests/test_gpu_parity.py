@@ -241,6 +241,9 @@ def test_offset_corr_matches_oracle(C, G, K, dil, H, W, B):
     want = head.neighbour_correlation(ref, grid)  # [B,G,K,H,W]
     got = ops.offset_corr(nhwc(ref.to(DEV)), off.to(DEV), G, K, dil)
     assert maxabs(got, want) <= 2e-5 * max(1.0, float(want.abs().max()))
+    # the same offsets in channels-last memory (what a conv on channels-last input emits) are consumed in place
+    got_cl = ops.offset_corr(nhwc(ref.to(DEV)), off.to(DEV).contiguous(memory_format=torch.channels_last), G, K, dil)
+    assert torch.equal(got_cl, got)
 
 
 def test_unsupported_neighbour_counts_raise_not_implemented():
@@ -304,7 +307,8 @@ def test_init_propagate_matches_oracle(mode, Ns, Kp, dil, H, W, B):
     assert pm_cases.rel_l1(got, want) <= 1e-6
     assert maxabs(got, want) <= 2e-3  # depths are ~400..1000: a few fp32 ulps
     xs = ops.alloc_xs(B, Ns + Kp, H, W, DEV).fill_(-7.0)
-    got2 = ops.init_propagate(seed.to(DEV), None if off is None else off.to(DEV), dmin.to(DEV), dmax.to(DEV), m, Ns, Kp, dil, scale, xs=xs)
+    off_cl = None if off is None else off.to(DEV).contiguous(memory_format=torch.channels_last)  # consumed in place
+    got2 = ops.init_propagate(seed.to(DEV), off_cl, dmin.to(DEV), dmax.to(DEV), m, Ns, Kp, dil, scale, xs=xs)
     assert torch.equal(got2, got) and torch.equal(xs[..., 0], got_x) and bool((xs[..., 1] == -7.0).all())
     if Kp > 0:
         assert bool((got[:, 1:] >= got[:, :-1]).all())  # sorted ascending
@@ -336,8 +340,9 @@ def test_adaptive_eval_matches_oracle(D, K, dil, H, W, B, inverse):
     inv_min, inv_max = (1.0 / dmin).view(B, 1, 1, 1), (1.0 / dmax).view(B, 1, 1, 1)
     xnorm = (1.0 / depth - inv_max) / (inv_min - inv_max)
     xs = torch.stack([xnorm, score0], dim=-1).contiguous().to(DEV)
-    for xn, inter in ((None, None), (xnorm.to(DEV), None), (None, xs)):  # recomputed per tap / precomputed by K-C / interleaved
-        got_depth, got_prob = ops.adaptive_eval(None if inter is not None else score0.to(DEV), depth.to(DEV), off.to(DEV), fw.to(DEV),
+    off_variants = [off.to(DEV), off.to(DEV).contiguous(memory_format=torch.channels_last), off.to(DEV)]
+    for (xn, inter), off_d in zip(((None, None), (xnorm.to(DEV), None), (None, xs)), off_variants):  # recomputed per tap / precomputed by K-C / interleaved
+        got_depth, got_prob = ops.adaptive_eval(None if inter is not None else score0.to(DEV), depth.to(DEV), off_d, fw.to(DEV),
                                                 dmin.to(DEV), dmax.to(DEV), dil, scale, inverse, xnorm=xn, xs=inter)
         assert maxabs(got_prob, want_prob) <= 5e-6
         assert pm_cases.rel_l1(got_depth, want_depth) <= 1e-6
