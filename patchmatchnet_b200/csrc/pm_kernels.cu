@@ -19,6 +19,7 @@
 // C=64).  PatchMatch hypotheses of one pixel are sorted and clustered, so consecutive hypotheses mostly land in the
 // same source cell; every generation of K-A exploits that differently (see the comments above each kernel).
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -53,6 +54,17 @@ __device__ __forceinline__ float2 load_offset(const float *__restrict__ off, int
     return make_float2(__ldg(q), __ldg(q + HW));
 }
 
+// One 256-bit read-only global load (sm_100: SASS LDG.E.ENL2.256): a lane's 8 channels of a texel in ONE request.
+// The gather is bound by L1 data-pipe wavefronts; two LDG.128 at a 32-byte lane stride each touch every 128-byte
+// line of the texel, one LDG.256 touches it once.  The address must be 32-byte aligned (checked by the C entry points).
+__device__ __forceinline__ void ldg256(const float4 *__restrict__ p, float4 &lo, float4 &hi) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+        : "l"(p));
+}
+
+inline bool misaligned32(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) != 0; }
+
 constexpr int kWarpsPerBlock = 8;
 constexpr int kChunk = 8;  // hypotheses (or neighbours) handled per warp pass
 
@@ -81,10 +93,11 @@ __device__ __forceinline__ void gather_dot(const float4 *__restrict__ map_lane, 
     const float4 *t1 = t0 + dx * V4;
     const float4 *t2 = t0 + (size_t)dy * cols * V4;
     const float4 *t3 = t2 + dx * V4;
-    const float4 a0 = __ldg(t0), a1 = __ldg(t0 + 1);
-    const float4 b0 = __ldg(t1), b1 = __ldg(t1 + 1);
-    const float4 c0 = __ldg(t2), c1 = __ldg(t2 + 1);
-    const float4 d0 = __ldg(t3), d1 = __ldg(t3 + 1);
+    float4 a0, a1, b0, b1, c0, c1, d0, d1;
+    ldg256(t0, a0, a1);
+    ldg256(t1, b0, b1);
+    ldg256(t2, c0, c1);
+    ldg256(t3, d0, d1);
     auto lo = [&](const float4 &q) { return r[0] * q.x + r[1] * q.y + r[2] * q.z + r[3] * q.w; };
     auto hi = [&](const float4 &q) { return r[4] * q.x + r[5] * q.y + r[6] * q.z + r[7] * q.w; };
     if constexpr (LaneMap<C, G>::GPL == 1) {
@@ -104,7 +117,8 @@ template <int C, int G>
 __device__ __forceinline__ void load_reference(const float *__restrict__ ref_nhwc, size_t pixel, int lane_in_pixel,
                                                float (&r)[8]) {
     const float4 *rp = reinterpret_cast<const float4 *>(ref_nhwc + pixel * C) + lane_in_pixel * 2;
-    const float4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+    float4 q0, q1;
+    ldg256(rp, q0, q1);
     constexpr float s = 1.0f / (float)LaneMap<C, G>::CPG;  // the group mean; exact (power of two)
     r[0] = q0.x * s; r[1] = q0.y * s; r[2] = q0.z * s; r[3] = q0.w * s;
     r[4] = q1.x * s; r[5] = q1.y * s; r[6] = q1.z * s; r[7] = q1.w * s;
@@ -610,10 +624,10 @@ __device__ __forceinline__ void load_taps(const float4 *__restrict__ map_lane, i
     const float4 *t1 = t0 + dx * V4;
     const float4 *t2 = t0 + (size_t)dy * cols * V4;
     const float4 *t3 = t2 + dx * V4;
-    t[0] = __ldg(t0); t[1] = __ldg(t0 + 1);
-    t[2] = __ldg(t1); t[3] = __ldg(t1 + 1);
-    t[4] = __ldg(t2); t[5] = __ldg(t2 + 1);
-    t[6] = __ldg(t3); t[7] = __ldg(t3 + 1);
+    ldg256(t0, t[0], t[1]);
+    ldg256(t1, t[2], t[3]);
+    ldg256(t2, t[4], t[5]);
+    ldg256(t3, t[6], t[7]);
 }
 
 template <int C, int G>
@@ -1639,6 +1653,8 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
         return fail(PMB200_EINVAL, "warp_corr: bad size");
     if (C < 1 || G < 1 || C % G != 0) return fail(PMB200_EINVAL, "warp_corr: C must be a multiple of G");
     if ((long long)Hs * Ws >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "warp_corr: source map too large");
+    if (C % 8 == 0 && (misaligned32(ref_nhwc) || misaligned32(src_nhwc)))
+        return fail(PMB200_EINVAL, "warp_corr: feature packs must be 32-byte aligned (256-bit loads)");
     WarpCorrParams p;
     p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = view_weights; p.out = out;
     p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
@@ -1683,6 +1699,8 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
     if (V < 1 || V > PMB200_MAX_VIEWS || B < 1 || B > 65535 || H < 1 || W < 1 || Hs < 1 || Ws < 1 || D < 1)
         return fail(PMB200_EINVAL, "warp_corr head: bad size");
     if ((long long)Hs * Ws >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "warp_corr head: source map too large");
+    if (misaligned32(ref_nhwc) || misaligned32(src_nhwc))
+        return fail(PMB200_EINVAL, "warp_corr head: feature packs must be 32-byte aligned (256-bit loads)");
     WarpCorrParams p;
     p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = view_weights; p.out = out;
     p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
@@ -1756,6 +1774,7 @@ int pmb200_offset_corr_weight(const float *ref_nhwc, const float *offsets, int o
     if (B < 1 || B > 65535 || H < 2 || W < 2) return fail(PMB200_EINVAL, "offset_corr_weight: bad size");
     if (K != 9 && K != 17) return fail(PMB200_EUNSUPPORTED, "offset_corr_weight: evaluate_neighbors must be 9 or 17");
     if ((long long)H * W >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "offset_corr_weight: map too large");
+    if (misaligned32(ref_nhwc)) return fail(PMB200_EINVAL, "offset_corr_weight: feature pack must be 32-byte aligned (256-bit loads)");
     OffsetCorrParams p;
     p.ref = ref_nhwc; p.offsets = offsets; p.out = weight_out;
     p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.off_nhwc = offsets_channels_last ? 1 : 0;
@@ -1796,6 +1815,7 @@ int pmb200_offset_corr(const float *ref_nhwc, const float *offsets, int offsets_
     if (C < 1 || G < 1 || C % G != 0) return fail(PMB200_EINVAL, "offset_corr: C must be a multiple of G");
     if (K != 9 && K != 17) return fail(PMB200_EUNSUPPORTED, "offset_corr: evaluate_neighbors must be 9 or 17");
     if ((long long)H * W >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "offset_corr: map too large");
+    if (C % 8 == 0 && misaligned32(ref_nhwc)) return fail(PMB200_EINVAL, "offset_corr: feature pack must be 32-byte aligned (256-bit loads)");
     OffsetCorrParams p;
     p.ref = ref_nhwc; p.offsets = offsets; p.out = out;
     p.B = B; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.off_nhwc = offsets_channels_last ? 1 : 0;

@@ -81,6 +81,8 @@ def _is_packed_nhwc(maps: Sequence[Tensor]) -> bool:
     B, C, H, W = first.shape
     want = (H * W * C, 1, W * C, C)
     store = first.untyped_storage().data_ptr()
+    if first.dtype != torch.float32 or first.data_ptr() % 32 != 0:  # the kernels read a lane's 8 channels with one 256-bit load
+        return False
     for i, m in enumerate(maps):
         if (m.shape != first.shape or m.stride() != want or m.untyped_storage().data_ptr() != store
                 or m.storage_offset() != first.storage_offset() + i * first.numel()):
