@@ -17,6 +17,8 @@ Numbers on the JSON line
                algorithmic bytes per launch / CUDA-event duration of that launch, against the measured
                HBM copy bandwidth in MEASURED_PEAKS.json
     cpu_baseline  the oracle (CPU restatement of the reference, bit-identical to it) timed on the host
+    gpu_eager_reference  the same oracle in eager PyTorch on the GPU, issuing the reference's own op sequence
+               (what the unmodified reference would do on this B200; SURVEY.md 8d "honest bar")
 """
 from __future__ import annotations
 
@@ -154,6 +156,39 @@ def cpu_forward_timer(height: int, width: int, n_views: int):
     torch.set_num_threads(best_c)
     step.calibration = tried
     return step, best_c
+
+
+def gpu_eager_reference(height: int, width: int, n_views: int, device, warmup: int = 3, iters: int = 10):
+    """The reference's algorithm as the reference would run it on THIS GPU: the oracle port (bit-identical to the
+    reference on CPU) in eager PyTorch, the caller-side shell issuing the reference's own op sequence (conv, BatchNorm,
+    ReLU separately, view by view; no folding, no stacking), cudnn.benchmark on as in eval.py:301, TF32 as torch's
+    defaults leave it.  A reported baseline (SURVEY.md 8d "honest bar"), never part of the product path."""
+    from oracle.pm_oracle import PatchMatchOracle  # allowed here: baseline legs only
+    import patchmatchnet_b200.net as net_mod
+
+    net, _ = build_net(PatchMatchOracle)
+    net = net.to(device).eval()
+    net.stack_views = False
+    inp = synthetic.make_inputs(1, n_views, height, width, seed=0)
+    imgs = [i.to(device) for i in inp["images"]]
+    K, E = inp["intrinsics"].to(device), inp["extrinsics"].to(device)
+    dmin, dmax = inp["depth_min"].to(device), inp["depth_max"].to(device)
+    net_mod.LIBRARY_FAST_PATH = False
+    try:
+        with torch.no_grad():
+            for _ in range(warmup):
+                net([i.clone() for i in imgs], K.clone(), E.clone(), dmin, dmax)
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                net([i.clone() for i in imgs], K.clone(), E.clone(), dmin, dmax)
+            torch.cuda.synchronize(device)
+            dt = time.perf_counter() - t0
+    finally:
+        net_mod.LIBRARY_FAST_PATH = True
+    return {"value": iters / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / iters, "kind": "port",
+            "how": f"oracle port of the reference in eager PyTorch on the same GPU, reference op sequence, inputs resident, "
+                   f"{warmup} warm-up + {iters} timed forwards, synchronize-bracketed wall clock, cudnn.benchmark=True"}
 
 
 def run_reference_arm(args) -> None:
@@ -351,6 +386,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=1, help="reference views per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch reference timing on the GPU")
     ap.add_argument("--no-tf32", action="store_true", help="run the library convolutions in full fp32 instead of torch's default TF32")
     ap.add_argument("--slots", type=int, default=3, help="independent requests in flight per GPU (each its own stream + CUDA graph)")
     ap.add_argument("--cpu-samples", type=int, default=4)
@@ -467,7 +503,7 @@ def main() -> None:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    roofline, detail, detail_cold, cpu_baseline = None, None, None, None
+    roofline, detail, detail_cold, cpu_baseline, gpu_eager = None, None, None, None, None
     if rank == 0:
         dev_inputs = lambda: ([im.clone() for im in d_in["images"]], d_in["intrinsics"].clone(), d_in["extrinsics"].clone(),
                               d_in["depth_min"], d_in["depth_max"])
@@ -494,6 +530,8 @@ def main() -> None:
                                "(L2 flushed between steps, GPU parked so the host's enqueue latency is not measured); "
                                "algorithmic bytes = V * 4*B*H*W*(2C + D + G*D) per launch (SURVEY.md 8d)",
                         "best_launch_frac": max(r["frac"] for r in detail), "worst_launch_frac": min(r["frac"] for r in detail)}
+        if world == 1 and not args.no_gpu_baseline:
+            gpu_eager = gpu_eager_reference(H, W, N, dev)
         if world == 1 and not args.no_cpu_baseline:
             step, cores = cpu_forward_timer(H, W, N)
             step()
@@ -523,6 +561,7 @@ def main() -> None:
             "clocks": clocks,
             "roofline": roofline, "roofline_detail": detail, "roofline_detail_cold_isolated": detail_cold if rank == 0 else None,
             "cpu_baseline": cpu_baseline,
+            "gpu_eager_reference": gpu_eager,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

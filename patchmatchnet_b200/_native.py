@@ -28,7 +28,12 @@ NVCC_FLAGS = [
     "--shared", "-Xcompiler", "-fPIC",
 ]
 
+# TorchScript-facing shim: TORCH_LIBRARY(pmb200) over the same C ABI (csrc/torch_binding.cpp), host C++ only
+TORCH_LIB_PATH = os.path.join(_PKG_DIR, "libpmb200_torch.so")
+TORCH_SOURCE = os.path.join(_PKG_DIR, "csrc", "torch_binding.cpp")
+
 _lib: Optional[ctypes.CDLL] = None
+_torch_ops_loaded = False
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -107,6 +112,48 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def build_torch_library(force: bool = False) -> str:
+    """Compile csrc/torch_binding.cpp (g++, torch headers) into patchmatchnet_b200/libpmb200_torch.so.  It links
+    against libpmb200.so (rpath $ORIGIN), so build_library() must have run."""
+    deps = [TORCH_SOURCE, HEADERS[1]]
+    if not force and os.path.exists(TORCH_LIB_PATH) and all(os.path.getmtime(TORCH_LIB_PATH) >= os.path.getmtime(f) for f in deps):
+        return TORCH_LIB_PATH
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing("build libpmb200.so first (build_library())")
+    import torch
+
+    tdir = os.path.dirname(os.path.abspath(torch.__file__))
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = [
+        shutil.which("g++") or "g++", "-O2", "-std=c++17", "-shared", "-fPIC",
+        f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+        f"-I{tdir}/include", f"-I{tdir}/include/torch/csrc/api/include", f"-I{cuda_home}/include",
+        TORCH_SOURCE, "-o", TORCH_LIB_PATH,
+        f"-L{tdir}/lib", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+        f"-L{_PKG_DIR}", "-lpmb200", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tdir}/lib",
+    ]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed on torch_binding.cpp:\n" + res.stdout + res.stderr)
+    return TORCH_LIB_PATH
+
+
+def load_torch_ops() -> None:
+    """Register `torch.ops.pmb200.*` (needed before a PatchMatch is scripted, and before torch.jit.load of a scripted
+    model that contains it).  Raises NativeLibraryMissing when the shim has not been built."""
+    global _torch_ops_loaded
+    if _torch_ops_loaded:
+        return
+    if not os.path.exists(TORCH_LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{TORCH_LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`"
+        )
+    import torch
+
+    torch.ops.load_library(TORCH_LIB_PATH)
+    _torch_ops_loaded = True
 
 
 def lib() -> ctypes.CDLL:

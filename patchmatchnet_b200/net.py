@@ -34,6 +34,17 @@ def _fold_bn(weight: Tensor, bn: nn.BatchNorm2d, out_dim: int = 0):
     return w, b
 
 
+# The caller-side shell (FeatureNet, Refinement, stage glue) has CUDA eval fast paths: BatchNorm folded into cuDNN
+# conv+bias+ReLU calls on channels-last data, views stacked into one batch, batched projection matrices, native
+# upsample+add and confidence tail.  Setting this False makes the shell issue the reference's own op sequence
+# (bench.py uses that, with the oracle stage module, to time "the reference in eager PyTorch on this GPU").
+LIBRARY_FAST_PATH = True
+
+
+def _fast(x: Tensor) -> bool:
+    return LIBRARY_FAST_PATH and x.is_cuda
+
+
 class _FoldCache:
     """Caches derived (folded) weights until any source tensor is modified or moved."""
 
@@ -78,7 +89,7 @@ class _ConvBnReLU2d(nn.Module):
         return self._cache.get(srcs, make)
 
     def forward(self, x: Tensor) -> Tensor:
-        if self.training or not x.is_cuda:
+        if self.training or not _fast(x):
             return F.relu(self.bn(self.conv(x)), inplace=True)
         w, b = self.folded()
         c = self.conv
@@ -127,7 +138,7 @@ class FeatureNet(nn.Module):
         """bilinear x2 upsample + lateral 1x1 conv (reference net.py:60-66).  On CUDA in eval mode the upsample, the
         add and the lateral conv's bias are ONE native launch (ATen's channels-last bilinear kernel was the single
         largest launch of the forward, the bias add another full pass over the largest tensor)."""
-        if coarse.is_cuda and not self.training and not torch.is_grad_enabled():
+        if _fast(coarse) and not self.training and not torch.is_grad_enabled():
             from . import ops
 
             lateral = F.conv2d(fine, lateral_conv.weight, None)
@@ -150,7 +161,7 @@ class Refinement(nn.Module):
         self._cache = _FoldCache()
 
     def _upsample(self, x: Tensor) -> Tensor:
-        if self.training or not x.is_cuda:
+        if self.training or not _fast(x):
             return F.relu(self.bn(self.deconv(x)), inplace=True)
         bn = self.bn
         srcs = [self.deconv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
@@ -162,7 +173,7 @@ class Refinement(nn.Module):
         lo = depth_min.view(B, 1, 1, 1)
         span = (depth_max - depth_min).view(B, 1, 1, 1)
         d = (depth_half - lo) / span
-        if img.is_cuda and not self.training:
+        if _fast(img) and not self.training:
             img = img.contiguous(memory_format=torch.channels_last)
         up = self._upsample(self.conv2(self.conv1(d)))
         res = self.res(self.conv3(torch.cat((up, self.conv0(img)), dim=1)))
@@ -260,7 +271,7 @@ class PatchmatchNet(nn.Module):
             x = torch.as_strided(first, (n * b,) + tuple(first.shape[1:]), first.stride())  # views of one buffer: no copy
         else:
             x = torch.cat(images, dim=0)
-        if x.is_cuda:  # cuDNN NHWC kernels; the pyramid then comes out channels-last, which is the layout
+        if _fast(x):  # cuDNN NHWC kernels; the pyramid then comes out channels-last, which is the layout
             x = x.contiguous(memory_format=torch.channels_last)  # the fused PatchMatch kernels read in place
         stacked = self.feature(x)
         return [{k: v[i * b:(i + 1) * b] for k, v in stacked.items()} for i in range(n)]
@@ -292,7 +303,7 @@ class PatchmatchNet(nn.Module):
         per_stage: Dict[int, List[Tensor]] = {}
 
         all_proj = None
-        if intrinsics.is_cuda:  # the three stages' projection matrices in one batch (5 launches instead of 15)
+        if _fast(intrinsics):  # the three stages' projection matrices in one batch (5 launches instead of 15)
             K3 = intrinsics.unsqueeze(0).repeat(3, 1, 1, 1, 1)
             K3[:, :, :, :2] *= self._stage_scales
             all_proj = extrinsics.unsqueeze(0).repeat(3, 1, 1, 1, 1)
@@ -332,7 +343,7 @@ class PatchmatchNet(nn.Module):
             return depth, torch.empty(0, device=dev), per_stage
 
         # photometric confidence (net.py:289-299): probability mass of the 4 hypotheses around the regressed index
-        if score.is_cuda and not torch.is_grad_enabled() and score.shape[1] == self.patchmatch_num_sample[0]:
+        if _fast(score) and not torch.is_grad_enabled() and score.shape[1] == self.patchmatch_num_sample[0]:
             from . import ops
 
             return depth, ops.photometric_confidence(score, H0, W0), per_stage

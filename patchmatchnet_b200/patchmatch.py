@@ -22,6 +22,7 @@ raise.  (The CPU restatement lives in ``oracle/`` and is test infrastructure.)
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, List, Optional, Tuple
 
 import torch
@@ -31,6 +32,15 @@ import torch.nn.functional as F
 from . import _native, ops
 
 Tensor = torch.Tensor
+
+
+_FOLD_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_HEAD_FLOATS = 16 * 8 + 16 + 8 * 16 + 8 + 8 + 1  # sizeof(pmb200_mlp) / 4
+
+
+def _refresh_after_load(module, incompatible_keys) -> None:
+    if not module.training:
+        module.refresh_script_heads()
 
 
 def is_empty(x: Tensor) -> bool:
@@ -62,9 +72,14 @@ class _PointwiseHead(nn.Module):
         self._last = last
         setattr(self, last, nn.Conv3d(8, 1, 1, stride=1, padding=0))
 
-    def forward(self, x: Tensor) -> Tensor:
-        """[N,G,D,H,W] -> [N,D,H,W]"""
-        return getattr(self, self._last)(self.conv1(self.conv0(x))).squeeze(1)
+    # forward lives in the subclasses with the last conv named literally, so that the module tree scripts
+    # (TorchScript has no dynamic getattr): [N,G,D,H,W] -> [N,D,H,W]
+
+    def folded_tensor(self) -> Tensor:
+        """The same folded head as a flat CPU float32 tensor (the memory image of pmb200_mlp): what the
+        `torch.ops.pmb200.*` operators take, because a TorchScript graph cannot hold a ctypes struct."""
+        m = self.folded()
+        return torch.frombuffer(bytearray(bytes(m)), dtype=torch.float32).clone()
 
     def folded(self) -> "_native.MlpStruct":
         """Eval-mode weights with BatchNorm folded into the convs, as the host struct the fused
@@ -73,8 +88,9 @@ class _PointwiseHead(nn.Module):
         (DepthEngine warms up before capturing)."""
         tensors = list(self.parameters()) + list(self.buffers())
         stamp = tuple((t.data_ptr(), t._version) for t in tensors)
-        if getattr(self, "_fold_stamp", None) == stamp:
-            return self._fold_cache
+        cached = _FOLD_CACHE.get(self)  # kept off the module: TorchScript would try to type a ctypes attribute
+        if cached is not None and cached[0] == stamp:
+            return cached[1]
         with torch.no_grad():
             def fold(block):
                 w = block.conv.weight.double().flatten(1)  # [out,in]
@@ -99,7 +115,7 @@ class _PointwiseHead(nn.Module):
         m.b1[:] = b1.tolist()
         m.w2[:] = w2.tolist()
         m.b2 = b2
-        self._fold_stamp, self._fold_cache = stamp, m
+        _FOLD_CACHE[self] = (stamp, m)
         return m
 
 
@@ -110,7 +126,8 @@ class PixelwiseNet(_PointwiseHead):
         super().__init__(G, "conv2")
 
     def forward(self, x: Tensor) -> Tensor:
-        return torch.max(torch.sigmoid(super().forward(x)), dim=1)[0].unsqueeze(1)
+        y = self.conv2(self.conv1(self.conv0(x))).squeeze(1)
+        return torch.max(torch.sigmoid(y), dim=1)[0].unsqueeze(1)
 
 
 class SimilarityNet(_PointwiseHead):
@@ -119,6 +136,9 @@ class SimilarityNet(_PointwiseHead):
 
     def __init__(self, G: int) -> None:
         super().__init__(G, "similarity")
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.similarity(self.conv1(self.conv0(x))).squeeze(1)
 
 
 class FeatureWeightNet(_PointwiseHead):
@@ -131,7 +151,7 @@ class FeatureWeightNet(_PointwiseHead):
         self.G = G
 
     def forward(self, corr: Tensor) -> Tensor:
-        return torch.sigmoid(super().forward(corr))
+        return torch.sigmoid(self.similarity(self.conv1(self.conv0(corr))).squeeze(1))
 
 
 class Evaluation(nn.Module):
@@ -171,7 +191,7 @@ class PatchMatch(nn.Module):
         self.evaluate_neighbors = evaluate_neighbors
         # Tests inject a shared U[0,1) draw here when comparing against an oracle on another device;
         # by default the draw is torch.rand on the compute device, exactly as reference patchmatch.py:61-63.
-        self.rand_source: Optional[Callable] = None
+        self.rand_source = None  # Optional[Callable]
         # eval mode: apply the 1x1x1 heads in the kernels' epilogues (BatchNorm folded); set False to
         # run them as cuDNN ops on materialised similarity tensors (the training path always does)
         self.fuse_heads = True
@@ -190,8 +210,28 @@ class PatchMatch(nn.Module):
             nn.init.constant_(conv.weight, 0.0)
             nn.init.constant_(conv.bias, 0.0)
         self.feature_weight_net = FeatureWeightNet(evaluate_neighbors, G)
+        # Folded heads as plain CPU tensors for the TorchScript path (not buffers: the state dict must keep exactly
+        # the reference's keys).  Refreshed on eval() / load_state_dict, i.e. before the reference scripts the model
+        # (train.py:50-55: child_model.eval(); torch.jit.script(child_model)).
+        self._head_fw = torch.zeros(_HEAD_FLOATS)
+        self._head_pw = torch.zeros(_HEAD_FLOATS)
+        self._head_sim = torch.zeros(_HEAD_FLOATS)
+        self.register_load_state_dict_post_hook(_refresh_after_load)
 
     # ------------------------------------------------------------------
+    def refresh_script_heads(self) -> None:
+        """Re-fold BatchNorm into the three heads for the scripted forward (call after changing weights in eval mode)."""
+        if self.G <= 8:
+            self._head_fw = self.feature_weight_net.folded_tensor()
+            self._head_pw = self.evaluation.pixel_wise_net.folded_tensor()
+            self._head_sim = self.evaluation.similarity_net.folded_tensor()
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        if not mode:
+            self.refresh_script_heads()
+        return self
+
     def _check_neighbour_counts(self) -> None:
         if self.propagate_neighbors not in (0, 4, 8, 16):
             raise NotImplementedError  # reference patchmatch.py:359-360
@@ -199,6 +239,112 @@ class PatchMatch(nn.Module):
             raise NotImplementedError  # reference patchmatch.py:391-392
 
     def forward(
+        self,
+        ref_feature: Tensor,
+        src_features: List[Tensor],
+        ref_proj: Tensor,
+        src_projs: List[Tensor],
+        depth_min: Tensor,
+        depth_max: Tensor,
+        depth: Tensor,
+        view_weights: Tensor,
+    ) -> Tuple[List[Tensor], Tensor, Tensor]:
+        if torch.jit.is_scripting():
+            return self._forward_script(
+                ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max, depth, view_weights
+            )
+        else:
+            return self._forward_eager(
+                ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max, depth, view_weights
+            )
+
+    def _forward_script(
+        self,
+        ref_feature: Tensor,
+        src_features: List[Tensor],
+        ref_proj: Tensor,
+        src_projs: List[Tensor],
+        depth_min: Tensor,
+        depth_max: Tensor,
+        depth: Tensor,
+        view_weights: Tensor,
+    ) -> Tuple[List[Tensor], Tensor, Tensor]:
+        """The eval-mode cascade written in the TorchScript subset over `torch.ops.pmb200.*` (csrc/torch_binding.cpp):
+        what runs inside a scripted model (reference train.py:53, eval.py:38).  Same kernels, same order as the fused
+        branch of `_forward_eager`.  Inference only: scripting exports a deployment artefact in the reference too."""
+        if self.training:
+            raise RuntimeError("a scripted patchmatchnet_b200.PatchMatch is inference-only; call eval() before torch.jit.script")
+        if self.propagate_neighbors != 0 and self.propagate_neighbors != 4 and self.propagate_neighbors != 8 and self.propagate_neighbors != 16:
+            raise NotImplementedError
+        if self.evaluate_neighbors != 9 and self.evaluate_neighbors != 17:
+            raise NotImplementedError
+        assert len(src_features) == len(
+            src_projs
+        ), "Patchmatch Evaluation: Different number of images and projection matrices"
+        if view_weights.numel() != 0:
+            assert (
+                len(src_features) == view_weights.size(1)
+            ), "Patchmatch Evaluation: Different number of images and view weights"
+        B, H, W = ref_feature.size(0), ref_feature.size(2), ref_feature.size(3)
+        Kp, Ke, iters = self.propagate_neighbors, self.evaluate_neighbors, self.patchmatch_iteration
+        dmin = depth_min.reshape(B).float()
+        dmax = depth_max.reshape(B).float()
+
+        propa_off: Optional[Tensor] = None
+        if Kp > 0 and not (self.stage == 1 and iters == 1):
+            propa_off = self.propa_conv(ref_feature)
+        eval_off = self.eval_conv(ref_feature)
+
+        same_size = True
+        for f in src_features:
+            if f.size(2) != H or f.size(3) != W:
+                same_size = False
+        if same_size:
+            pack = torch.ops.pmb200.pack_nhwc([ref_feature] + src_features)
+            ref_nhwc = pack[0]
+            src_nhwc = pack[1:]
+        else:
+            ref_nhwc = torch.ops.pmb200.pack_nhwc([ref_feature])[0]
+            src_nhwc = torch.ops.pmb200.pack_nhwc(src_features)
+        rt = torch.ops.pmb200.relative_projection(ref_proj, src_projs)
+        feature_weight = torch.ops.pmb200.offset_corr_weight(ref_nhwc, eval_off, self._head_fw, self.G, Ke, self.dilation)
+
+        sample = depth
+        vw = view_weights
+        prob = torch.empty(0, device=ref_feature.device)
+        outs: List[Tensor] = []
+        for it in range(1, iters + 1):
+            last_of_stage1 = self.stage == 1 and it == iters
+            kp_now = 0
+            if Kp > 0 and not last_of_stage1:
+                kp_now = Kp
+            if sample.numel() == 0:
+                seed = torch.rand([B, 48, H, W], device=ref_feature.device)
+                mode, ns = 0, 48
+            elif self.patchmatch_num_sample == 1:
+                seed, mode, ns = sample, 2, 1
+            else:
+                seed, mode, ns = sample, 1, self.patchmatch_num_sample
+            off_now: Optional[Tensor] = None
+            if kp_now > 0:
+                off_now = propa_off
+            hyp, xs = torch.ops.pmb200.init_propagate(
+                seed, off_now, dmin, dmax, mode, ns, kp_now, self.dilation, self.patchmatch_interval_scale
+            )
+            if vw.numel() == 0:
+                vw, sims = torch.ops.pmb200.warp_corr_view_weights(ref_nhwc, src_nhwc, rt, hyp, self._head_pw, self.G)
+                torch.ops.pmb200.aggregate_views_score_(sims, vw, self._head_sim, xs)
+            else:
+                torch.ops.pmb200.warp_corr_score_(ref_nhwc, src_nhwc, rt, hyp, vw, self._head_sim, self.G, xs)
+            new_depth, prob = torch.ops.pmb200.adaptive_eval(
+                xs, hyp, eval_off, feature_weight, dmin, dmax, self.dilation, self.patchmatch_interval_scale, last_of_stage1
+            )
+            sample = new_depth.unsqueeze(1)
+            outs.append(sample)
+        return outs, prob, vw.detach()
+
+    @torch.jit.unused
+    def _forward_eager(
         self,
         ref_feature: Tensor,
         src_features: List[Tensor],

@@ -14,6 +14,7 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 REFERENCE = "/root/reference"
 
 warnings.filterwarnings("ignore", message="torch.meshgrid")
+warnings.filterwarnings("ignore", message=".*torch.jit.*is deprecated.*")
 
 
 def pytest_configure(config):
