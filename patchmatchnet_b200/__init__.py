@@ -6,8 +6,15 @@ Public surface (mirrors the reference's ``models`` package for this path):
     PatchmatchNet   caller-side shell with the reference constructor/forward (models/net.py)
     ops             tensor-level wrappers over the C ABI (include/patchmatch_b200.h)
 """
-from . import distributed, engine, ops, synthetic  # noqa: F401
+import os as _os
+
+from . import _native, distributed, engine, ops, synthetic  # noqa: F401
 from .net import PatchmatchNet, load_reference_state, patchmatchnet_loss  # noqa: F401
 from .patchmatch import PatchMatch  # noqa: F401
+
+# torch.ops.pmb200.* (TorchScript-facing registration of the same C ABI): registered on import when the shim is built,
+# so that `torch.jit.script(model)` / `torch.jit.load(path)` work after a plain `import patchmatchnet_b200`.
+if _os.path.exists(_native.TORCH_LIB_PATH):
+    _native.load_torch_ops()
 
 __all__ = ["PatchMatch", "PatchmatchNet", "load_reference_state", "patchmatchnet_loss"]
