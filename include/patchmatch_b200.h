@@ -75,6 +75,33 @@ int pmb200_pack_nhwc(const float *const *maps_host, int n, int B, int C, int H, 
 int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const float *bias, float *out_nhwc,
                                int N, int h, int w, int C, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Channels-last 2-D convolution for the small learned convs of the model (1..64 channels), tensor cores
+ * (TF32 implicit GEMM), bias + ReLU fused:
+ *     y[n,oy,ox,yco+co] = act(bias[co] + sum_{ky,kx,ci} x[n, oy*S-pad+ky*dil, ox*S-pad+kx*dil, ci] * w[co,ci,ky,kx])
+ * Replaces, on the hot path, the offset convs propa_conv / eval_conv (models/patchmatch.py:288-311, called at
+ * :486 and :498: nn.Conv2d 3x3, dilation = padding = propagation range) and, either side of it (SURVEY.md 8f rows
+ * f1 / f3), ConvBnReLU (models/module.py:11-40, BatchNorm folded by the caller) and the plain convs of FeatureNet
+ * (models/net.py:9-70) and Refinement (models/net.py:73-122, including its ConvTranspose2d: transposed2x = 1 runs the
+ * equivalent stride-1 conv over the virtually zero-stuffed input, caller passes the flipped filter and pad = KS-1-pad_t).
+ *   x            [N,H,W,Cin]      (16-byte aligned when Cin % 4 == 0)
+ *   filter_frag  the filter in tensor-core fragment order, pmb200_conv2d_filter_floats(Cin,Cout,KS) floats:
+ *                [tap = ky*KS+kx][ks = 0..ceil8(Cin')/8)[nt = 0..NT)[lane = 0..32)[2] with
+ *                (b0, b1) = (w[nt*8 + lane/4][ks*8 + lane%4][ky][kx], w[nt*8 + lane/4][ks*8 + lane%4 + 4][ky][kx]),
+ *                zero where the channel index is outside the filter; Cin' = Cin rounded up to 8/16/32/64,
+ *                NT = ceil(Cout/8) rounded up to 1,2,3,4 or 8
+ *   bias         [Cout] or NULL
+ *   y            [N,Ho,Wo,y_channel_stride], written at channels y_channel_offset .. +Cout (stride 0 = Cout: dense)
+ *   precision    1: operands rounded to TF32 (the library's behaviour under torch.backends.cudnn.allow_tf32, torch's
+ *                default); 3: error-compensated 3xTF32, fp32-accurate
+ *   rows_per_warp 0 = choose (tile = 16 columns x 4*rows_per_warp rows per 4-warp CTA); 1, 2 or 4 to force
+ */
+int pmb200_conv2d_filter_floats(int Cin, int Cout, int KS);
+int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bias, float *y,
+                       int N, int H, int W, int Cin, int Cout, int KS, int stride, int pad, int dil,
+                       int relu, int precision, int transposed2x, int y_channel_stride, int y_channel_offset,
+                       int rows_per_warp, void *stream);
+
 /* Caller-side helper (models/net.py:289-299): photometric confidence = probability mass of the four
  * hypotheses around the regressed hypothesis index, nearest-resized to [H_out, W_out].
  *   prob [B,D,h,w] (the last PatchMatch stage's probabilities)   confidence_out [B,H_out,W_out] */

@@ -331,6 +331,38 @@ Tensor photometric_confidence(const Tensor &prob, int64_t out_h, int64_t out_w) 
     return out;
 }
 
+// reference patchmatch.py:288-311 (propa_conv / eval_conv) -- the channels-last tensor-core conv of csrc/pm_conv.cu.
+// x: logical [N,Cin,H,W] (made channels-last if it is not); filter_frag: the fragment-ordered filter
+// (patchmatchnet_b200.ops.pack_conv_filter), moved to x's device when the scripted module holds it on the CPU;
+// -> logical [N,cout,Ho,Wo] in channels-last memory, which the fused kernels consume in place.
+Tensor conv2d_nhwc(const Tensor &x, const Tensor &filter_frag, const c10::optional<Tensor> &bias, int64_t cout, int64_t ks,
+                   int64_t stride, int64_t pad, int64_t dil, bool relu, int64_t precision) {
+    TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kFloat && x.dim() == 4,
+                "conv2d_nhwc: x must be a 4-D CUDA float32 tensor; there is no CPU fallback");
+    const Tensor xc = x.contiguous(at::MemoryFormat::ChannelsLast);
+    const int64_t N = xc.size(0), cin = xc.size(1), H = xc.size(2), W = xc.size(3);
+    const int want = pmb200_conv2d_filter_floats((int)cin, (int)cout, (int)ks);
+    TORCH_CHECK(want > 0 && filter_frag.scalar_type() == at::kFloat && filter_frag.numel() == want,
+                "conv2d_nhwc: filter must be ", want, " float32 values in fragment order (pack_conv_filter)");
+    c10::cuda::CUDAGuard guard(xc.device());
+    const Tensor frag = filter_frag.to(xc.device()).contiguous();
+    Tensor b;
+    const float *b_ptr = nullptr;
+    if (bias.has_value() && bias->defined()) {
+        b = bias->to(xc.device(), at::kFloat).contiguous();
+        TORCH_CHECK(b.numel() == cout, "conv2d_nhwc: bias must have Cout elements");
+        b_ptr = b.data_ptr<float>();
+    }
+    const int64_t Ho = (H + 2 * pad - dil * (ks - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
+    TORCH_CHECK(Ho >= 1 && Wo >= 1, "conv2d_nhwc: empty output");
+    Tensor out = at::empty({N, cout, Ho, Wo}, xc.options().memory_format(at::MemoryFormat::ChannelsLast));
+    check(pmb200_conv2d_nhwc(xc.data_ptr<float>(), frag.data_ptr<float>(), b_ptr, out.data_ptr<float>(), (int)N, (int)H, (int)W,
+                             (int)cin, (int)cout, (int)ks, (int)stride, (int)pad, (int)dil, relu ? 1 : 0, (int)precision, 0, 0, 0,
+                             0, stream_of(xc)),
+          "conv2d_nhwc");
+    return out;
+}
+
 int64_t abi_version() { return pmb200_abi_version(); }
 
 }  // namespace
@@ -350,6 +382,7 @@ TORCH_LIBRARY(pmb200, m) {
     m.def("adaptive_eval(Tensor xs, Tensor depth_sample, Tensor offsets, Tensor feature_weight, Tensor depth_min, Tensor depth_max, int dilation, float interval_scale, bool is_inverse) -> (Tensor, Tensor)");
     m.def("adaptive_eval_planar(Tensor score0, Tensor xnorm, Tensor depth_sample, Tensor offsets, Tensor feature_weight, Tensor depth_min, Tensor depth_max, int dilation, float interval_scale, bool is_inverse) -> (Tensor, Tensor)");
     m.def("photometric_confidence(Tensor prob, int out_h, int out_w) -> Tensor");
+    m.def("conv2d_nhwc(Tensor x, Tensor filter_frag, Tensor? bias, int cout, int ks, int stride, int pad, int dil, bool relu, int precision) -> Tensor");
 }
 
 // CUDA is the only backend: a CPU tensor reaches no kernel and the dispatcher raises, there is no fallback.
@@ -368,4 +401,5 @@ TORCH_LIBRARY_IMPL(pmb200, CUDA, m) {
     m.impl("adaptive_eval", &adaptive_eval);
     m.impl("adaptive_eval_planar", &adaptive_eval_planar);
     m.impl("photometric_confidence", &photometric_confidence);
+    m.impl("conv2d_nhwc", &conv2d_nhwc);
 }

@@ -46,22 +46,48 @@ def _fast(x: Tensor) -> bool:
 
 
 class _FoldCache:
-    """Caches derived (folded) weights until any source tensor is modified or moved."""
+    """Caches derived (folded / packed) weights until any source tensor is modified or moved.  The (stamp, value)
+    pair is one attribute, read and written whole: module replicas (nn.DataParallel threads) may share a cache object,
+    and then at worst recompute -- a caller never gets another device's value."""
 
     def __init__(self) -> None:
-        self._stamp = None
-        self._value = None
+        self._entry = (None, None)
 
     def get(self, tensors, make):
         stamp = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
-        if stamp != self._stamp:
+        have, value = self._entry
+        if stamp != have:
             with torch.no_grad():
-                self._value = make()
-            self._stamp = stamp
-        return self._value
+                value = make()
+            self._entry = (stamp, value)
+        return value
 
 
 _FUSED_CONV_RELU = hasattr(torch, "cudnn_convolution_relu")
+
+def _native_convs(x: Tensor) -> bool:
+    """Eval mode on CUDA: every conv of the shell (FeatureNet, Refinement) runs through the native channels-last
+    tensor-core conv (csrc/pm_conv.cu, ops.conv2d_nhwc) instead of cuDNN, unless ops.NATIVE_CONVS is False
+    (PMB200_NATIVE_CONVS=0), which keeps the folded cuDNN calls -- bench.py uses that for an A/B line."""
+    from . import ops
+
+    return ops.NATIVE_CONVS and _fast(x) and not torch.is_grad_enabled()
+
+
+class _PackedConv:
+    """Fragment-ordered filter (+ bias) of a plain nn.Conv2d, cached until the weights change or move."""
+
+    def __init__(self) -> None:
+        self._cache = _FoldCache()
+
+    def __call__(self, conv: nn.Conv2d, x: Tensor, relu: bool = False, with_bias: bool = True) -> Tensor:
+        from . import ops
+
+        srcs = [conv.weight] + ([conv.bias] if conv.bias is not None else [])
+        frag, bias = self._cache.get(
+            srcs, lambda: (ops.pack_conv_filter(conv.weight), None if conv.bias is None else conv.bias.detach().clone()))
+        return ops.conv2d_nhwc(x, frag, bias if with_bias else None, conv.out_channels, conv.kernel_size[0], conv.stride[0],
+                               conv.padding[0], conv.dilation[0], relu=relu)
 
 
 class _ConvBnReLU2d(nn.Module):
@@ -77,6 +103,28 @@ class _ConvBnReLU2d(nn.Module):
         self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=pad, bias=False)
         self.bn = nn.BatchNorm2d(cout)
         self._cache = _FoldCache()
+        self._frag_cache = _FoldCache()
+
+    def folded_frag(self):
+        """(fragment-ordered folded filter, folded bias) for the native conv."""
+        from . import ops
+
+        bn = self.bn
+        srcs = [self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def make():
+            w, b = _fold_bn(self.conv.weight, bn)
+            return ops.pack_conv_filter(w), b.contiguous()
+
+        return self._frag_cache.get(srcs, make)
+
+    def native(self, x: Tensor, out: Tensor = None, out_channel_offset: int = 0) -> Tensor:
+        from . import ops
+
+        frag, b = self.folded_frag()
+        c = self.conv
+        return ops.conv2d_nhwc(x, frag, b, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
+                               relu=True, out=out, out_channel_offset=out_channel_offset)
 
     def folded(self):
         bn = self.bn
@@ -91,6 +139,8 @@ class _ConvBnReLU2d(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         if self.training or not _fast(x):
             return F.relu(self.bn(self.conv(x)), inplace=True)
+        if _native_convs(x):
+            return self.native(x)
         w, b = self.folded()
         c = self.conv
         if _FUSED_CONV_RELU:
@@ -117,6 +167,13 @@ class FeatureNet(nn.Module):
         self.inner2 = nn.Conv2d(16, 64, 1, bias=True)
         self.output2 = nn.Conv2d(64, 32, 1, bias=False)
         self.output3 = nn.Conv2d(64, 16, 1, bias=False)
+        self._packed = {n: _PackedConv() for n in ("output1", "inner1", "inner2", "output2", "output3")}
+
+    def _plain(self, name: str, x: Tensor) -> Tensor:
+        """One of the bias-free / lateral 1x1 convs: native in eval mode on CUDA, else the module itself."""
+        if not self.training and _native_convs(x):
+            return self._packed[name](getattr(self, name), x)
+        return getattr(self, name)(x)
 
     def _trunk(self, x: Tensor, lo: int, hi: int) -> Tensor:
         for i in range(lo, hi + 1):
@@ -127,21 +184,25 @@ class FeatureNet(nn.Module):
         half = self._trunk(self._trunk(x, 0, 1), 2, 4)
         quarter = self._trunk(half, 5, 7)
         eighth = self._trunk(quarter, 8, 10)
-        out: Dict[int, Tensor] = {3: self.output1(eighth)}
-        top = self._top_down(eighth, self.inner1, quarter)
-        out[2] = self.output2(top)
-        top = self._top_down(top, self.inner2, half)
-        out[1] = self.output3(top)
+        out: Dict[int, Tensor] = {3: self._plain("output1", eighth)}
+        top = self._top_down(eighth, "inner1", quarter)
+        out[2] = self._plain("output2", top)
+        top = self._top_down(top, "inner2", half)
+        out[1] = self._plain("output3", top)
         return out
 
-    def _top_down(self, coarse: Tensor, lateral_conv: nn.Conv2d, fine: Tensor) -> Tensor:
+    def _top_down(self, coarse: Tensor, lateral_name: str, fine: Tensor) -> Tensor:
         """bilinear x2 upsample + lateral 1x1 conv (reference net.py:60-66).  On CUDA in eval mode the upsample, the
         add and the lateral conv's bias are ONE native launch (ATen's channels-last bilinear kernel was the single
         largest launch of the forward, the bias add another full pass over the largest tensor)."""
+        lateral_conv = getattr(self, lateral_name)
         if _fast(coarse) and not self.training and not torch.is_grad_enabled():
             from . import ops
 
-            lateral = F.conv2d(fine, lateral_conv.weight, None)
+            if _native_convs(fine):
+                lateral = self._packed[lateral_name](lateral_conv, fine, with_bias=False)
+            else:
+                lateral = F.conv2d(fine, lateral_conv.weight, None)
             return ops.upsample2x_add(coarse, lateral, lateral_conv.bias)
         return F.interpolate(coarse, scale_factor=2.0, mode="bilinear", align_corners=False) + lateral_conv(fine)
 
@@ -159,6 +220,29 @@ class Refinement(nn.Module):
         self.conv3 = _ConvBnReLU2d(16, 8)
         self.res = nn.Conv2d(8, 1, 3, padding=1, bias=False)
         self._cache = _FoldCache()
+        self._deconv_frag = _FoldCache()
+        self._res_packed = _PackedConv()
+
+    def _native_tail(self, img: Tensor, d: Tensor) -> Tensor:
+        """conv1 -> conv2 -> transposed conv (BatchNorm folded, ReLU) and conv0(img) written straight into the two
+        halves of one 16-channel buffer (no torch.cat), -> conv3 -> res: six native launches."""
+        from . import ops
+
+        bn = self.bn
+        srcs = [self.deconv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def make():
+            w, b = _fold_bn(self.deconv.weight, bn, out_dim=1)
+            return ops.pack_conv_filter(w, transposed=True), b.contiguous()
+
+        frag, b = self._deconv_frag.get(srcs, make)
+        low = self.conv2.native(self.conv1.native(d))
+        N, _, h, w = low.shape
+        both = torch.empty((N, 16, 2 * h, 2 * w), dtype=torch.float32, device=low.device, memory_format=torch.channels_last)
+        # ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1) == stride-1 conv (pad 3-1-1 = 1) over the zero-stuffed input
+        ops.conv2d_nhwc(low, frag, b, 8, 3, 1, 1, 1, relu=True, transposed2x=True, out=both, out_channel_offset=0)
+        self.conv0.native(img, out=both, out_channel_offset=8)
+        return self._res_packed(self.res, self.conv3.native(both))
 
     def _upsample(self, x: Tensor) -> Tensor:
         if self.training or not _fast(x):
@@ -175,8 +259,11 @@ class Refinement(nn.Module):
         d = (depth_half - lo) / span
         if _fast(img) and not self.training:
             img = img.contiguous(memory_format=torch.channels_last)
-        up = self._upsample(self.conv2(self.conv1(d)))
-        res = self.res(self.conv3(torch.cat((up, self.conv0(img)), dim=1)))
+        if not self.training and _native_convs(img) and img.shape[-2:] == (2 * d.shape[-2], 2 * d.shape[-1]):
+            res = self._native_tail(img, d)
+        else:
+            up = self._upsample(self.conv2(self.conv1(d)))
+            res = self.res(self.conv3(torch.cat((up, self.conv0(img)), dim=1)))
         d = F.interpolate(d, scale_factor=2.0, mode="nearest") + res
         return d * span + lo
 

@@ -8,6 +8,7 @@ an error (there is no fallback path).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -141,6 +142,89 @@ def upsample2x_add(x: Tensor, y: Tensor, bias: Optional[Tensor] = None) -> Tenso
     with torch.cuda.device(x.device):
         rc = _native.lib().pmb200_upsample2x_add_nhwc(x.data_ptr(), y.data_ptr(), b_ptr, out.data_ptr(), N, h, w, C, _stream(x))
     _native.check(rc, "upsample2x_add_nhwc")
+    return out
+
+
+# The small learned convs (offset convs of the hot path, FeatureNet, Refinement) run through csrc/pm_conv.cu in eval
+# mode.  False (or PMB200_NATIVE_CONVS=0) hands them back to cuDNN -- kept only for A/B measurements.
+NATIVE_CONVS = os.environ.get("PMB200_NATIVE_CONVS", "1") != "0"
+
+
+def _round_kcin(cin: int) -> int:
+    return 8 if cin <= 8 else (16 if cin <= 16 else (32 if cin <= 32 else 64))
+
+
+def _round_nt(cout: int) -> int:
+    nt = (cout + 7) // 8
+    return nt if nt <= 4 else 8
+
+
+def pack_conv_filter(weight: Tensor, transposed: bool = False) -> Tensor:
+    """Conv filter [Cout,Cin,KS,KS] -> the tensor-core fragment order `pmb200_conv2d_nhwc` reads
+    (include/patchmatch_b200.h): [tap][k-slice][n-tile][lane][2] with lane = 4*g + t holding
+    (w[nt*8+g][ks*8+t], w[nt*8+g][ks*8+t+4]) of that tap, zero padded.  `transposed`: `weight` is a
+    ConvTranspose2d filter [Cin,Cout,KS,KS]; the equivalent direct filter is its spatial flip with the
+    channel axes swapped.  Pure layout work on the weight's own device (host logic, CPU-testable)."""
+    if weight.dim() != 4 or weight.shape[2] != weight.shape[3]:
+        raise RuntimeError(f"pack_conv_filter: expected [Cout,Cin,KS,KS], got {tuple(weight.shape)}")
+    w = weight.detach().float()
+    if transposed:
+        w = w.flip(2, 3).permute(1, 0, 2, 3)
+    cout, cin, ks, _ = w.shape
+    if not (1 <= cin <= 64 and 1 <= cout <= 64):
+        raise RuntimeError("pack_conv_filter: 1 <= Cin, Cout <= 64")
+    kc, nt = _round_kcin(cin), _round_nt(cout)
+    wp = torch.zeros((ks * ks, kc, nt * 8), dtype=torch.float32, device=w.device)
+    wp[:, :cin, :cout] = w.permute(2, 3, 1, 0).reshape(ks * ks, cin, cout)
+    # k = ks8*8 + half*4 + t ; n = j*8 + g  ->  [tap][ks8][j][g][t][half]
+    frag = wp.view(ks * ks, kc // 8, 2, 4, nt, 8).permute(0, 1, 4, 5, 3, 2).contiguous()
+    return frag.view(-1)
+
+
+def conv_precision() -> int:
+    """1 (TF32 operands) when the library would use TF32 for convolutions (torch.backends.cudnn.allow_tf32, torch's
+    default), else 3 (3xTF32, fp32-accurate): the native convs honour the same switch as the cuDNN ones they replace."""
+    return 1 if torch.backends.cudnn.allow_tf32 else 3
+
+
+def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: int, ks: int, stride: int = 1, pad: int = 0,
+                dil: int = 1, relu: bool = False, transposed2x: bool = False, out: Optional[Tensor] = None,
+                out_channel_offset: int = 0, precision: Optional[int] = None, rows_per_warp: int = 0) -> Tensor:
+    """Channels-last convolution on the tensor cores (csrc/pm_conv.cu).  `x` is a logical-NCHW CUDA tensor in
+    channels-last memory (made so if not); returns a logical-NCHW channels-last tensor [N,cout,Ho,Wo], or writes the
+    channels out_channel_offset..+cout of `out` (a wider channels-last tensor: concat fusion) and returns `out`."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
+        raise RuntimeError(f"conv2d_nhwc: x must be a 4-D CUDA float32 tensor (got {x.dtype} {tuple(x.shape)} on {x.device}); no CPU fallback")
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    N, cin, H, W = x.shape
+    want = _native.lib().pmb200_conv2d_filter_floats(cin, cout, ks)
+    if want <= 0 or filter_frag.numel() != want or filter_frag.dtype != torch.float32 or filter_frag.device != x.device:
+        raise RuntimeError(f"conv2d_nhwc: filter must be {want} float32 values on {x.device} in fragment order (pack_conv_filter)")
+    Hv, Wv = (2 * H, 2 * W) if transposed2x else (H, W)
+    Ho = (Hv + 2 * pad - dil * (ks - 1) - 1) // stride + 1
+    Wo = (Wv + 2 * pad - dil * (ks - 1) - 1) // stride + 1
+    if out is None:
+        out = torch.empty((N, cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        ycs, yco = cout, 0
+    else:
+        if (out.dim() != 4 or out.shape[0] != N or out.shape[2:] != (Ho, Wo) or out.dtype != torch.float32 or out.device != x.device
+                or not out.is_contiguous(memory_format=torch.channels_last)):
+            raise RuntimeError("conv2d_nhwc: `out` must be a channels-last CUDA float32 [N,C,Ho,Wo] tensor")
+        ycs, yco = out.shape[1], out_channel_offset
+    b_ptr = None
+    if bias is not None:
+        bias = _require(bias, "bias", 1)
+        if bias.numel() != cout:
+            raise RuntimeError("conv2d_nhwc: bias must have Cout elements")
+        b_ptr = bias.data_ptr()
+    prec = conv_precision() if precision is None else precision
+    with torch.cuda.device(x.device):
+        rc = _native.lib().pmb200_conv2d_nhwc(
+            x.data_ptr(), filter_frag.data_ptr(), b_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride, pad, dil,
+            1 if relu else 0, prec, 1 if transposed2x else 0, ycs, yco, rows_per_warp, _stream(x),
+        )
+    _native.check(rc, "conv2d_nhwc")
     return out
 
 

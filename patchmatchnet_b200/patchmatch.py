@@ -43,6 +43,23 @@ def _refresh_after_load(module, incompatible_keys) -> None:
         module.refresh_script_heads()
 
 
+def _offset_conv(conv: nn.Conv2d, x: Tensor, native: bool) -> Tensor:
+    """propa_conv / eval_conv (reference patchmatch.py:288-311, called at :486 / :498).  `native`: the channels-last
+    tensor-core conv of csrc/pm_conv.cu (its channels-last output is what the fused kernels consume in place); the
+    fragment-ordered filter is cached off the module (TorchScript would try to type the attribute)."""
+    if not native:
+        return conv(x)
+    srcs = (conv.weight, conv.bias)
+    stamp = tuple((t.data_ptr(), t._version, t.device) for t in srcs)
+    cached = _FOLD_CACHE.get(conv)
+    if cached is None or cached[0] != stamp:
+        with torch.no_grad():
+            cached = (stamp, (ops.pack_conv_filter(conv.weight), conv.bias.detach().clone()))
+        _FOLD_CACHE[conv] = cached
+    frag, bias = cached[1]
+    return ops.conv2d_nhwc(x, frag, bias, conv.out_channels, conv.kernel_size[0], 1, conv.padding[0], conv.dilation[0])
+
+
 def is_empty(x: Tensor) -> bool:
     """reference models/module.py:199-200: optional tensors are signalled by numel() == 0."""
     return x.numel() == 0
@@ -216,6 +233,12 @@ class PatchMatch(nn.Module):
         self._head_fw = torch.zeros(_HEAD_FLOATS)
         self._head_pw = torch.zeros(_HEAD_FLOATS)
         self._head_sim = torch.zeros(_HEAD_FLOATS)
+        # The offset convs' filters in tensor-core fragment order, and the conv precision (1 = TF32 operands, 3 = 3xTF32),
+        # for the scripted forward: like everything in a scripted artefact they are frozen when it is made, i.e. the
+        # precision is what torch.backends.cudnn.allow_tf32 selects at eval() / load_state_dict time.
+        self._off_propa_frag = torch.zeros(1)
+        self._off_eval_frag = torch.zeros(1)
+        self._conv_precision = 3
         self.register_load_state_dict_post_hook(_refresh_after_load)
 
     # ------------------------------------------------------------------
@@ -225,6 +248,10 @@ class PatchMatch(nn.Module):
             self._head_fw = self.feature_weight_net.folded_tensor()
             self._head_pw = self.evaluation.pixel_wise_net.folded_tensor()
             self._head_sim = self.evaluation.similarity_net.folded_tensor()
+        with torch.no_grad():
+            self._off_propa_frag = ops.pack_conv_filter(self.propa_conv.weight).cpu()
+            self._off_eval_frag = ops.pack_conv_filter(self.eval_conv.weight).cpu()
+        self._conv_precision = ops.conv_precision()
 
     def train(self, mode: bool = True):
         super().train(mode)
@@ -292,8 +319,12 @@ class PatchMatch(nn.Module):
 
         propa_off: Optional[Tensor] = None
         if Kp > 0 and not (self.stage == 1 and iters == 1):
-            propa_off = self.propa_conv(ref_feature)
-        eval_off = self.eval_conv(ref_feature)
+            propa_off = torch.ops.pmb200.conv2d_nhwc(
+                ref_feature, self._off_propa_frag, self.propa_conv.bias, 2 * Kp, 3, 1, self.dilation, self.dilation, False,
+                self._conv_precision)
+        eval_off = torch.ops.pmb200.conv2d_nhwc(
+            ref_feature, self._off_eval_frag, self.eval_conv.bias, 2 * Ke, 3, 1, self.dilation, self.dilation, False,
+            self._conv_precision)
 
         same_size = True
         for f in src_features:
@@ -382,11 +413,12 @@ class PatchMatch(nn.Module):
         depth_min = depth_min.reshape(B).float()
         depth_max = depth_max.reshape(B).float()
 
-        # learned 2-D offsets (cuDNN)
+        # learned 2-D offsets: native channels-last tensor-core conv (inference), cuDNN + autograd (training)
+        native_conv = ops.NATIVE_CONVS and not need_grad and not torch.is_grad_enabled()
         propa_off: Optional[Tensor] = None
         if Kp > 0 and not (self.stage == 1 and iters == 1):
-            propa_off = self.propa_conv(ref_feature)
-        eval_off = self.eval_conv(ref_feature)
+            propa_off = _offset_conv(self.propa_conv, ref_feature, native_conv)
+        eval_off = _offset_conv(self.eval_conv, ref_feature, native_conv)
 
         # channels-last feature pack [1+V,B,H,W,C] (zero-copy if the producer already emitted it)
         same_size = all(f.shape == ref_feature.shape for f in src_features)

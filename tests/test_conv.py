@@ -1,0 +1,221 @@
+"""Native channels-last tensor-core conv (csrc/pm_conv.cu, ops.conv2d_nhwc): the offset convs of the hot path
+(reference models/patchmatch.py:288-311) and the FeatureNet / Refinement convs either side of it (models/net.py:9-122).
+
+CPU part: the host-side filter packing and the kernel's index math (staging, fragment addresses, lane <-> element
+mapping, epilogue ownership, zero-stuffed transposed form) through the lane-level emulator in tests/conv_emulator.py,
+against torch's conv2d / conv_transpose2d.  GPU part (-m gpu): the kernel itself against cuDNN in full fp32 for
+every layer shape of the network plus ragged sizes, channel slices and forced tile heights.
+Tolerances: precision 3 (3xTF32) is fp32-accurate -> 2e-5 of the output scale; precision 1 (TF32 operands, the
+library's default behaviour) -> 3e-3 of the output scale (10-bit mantissas, K <= 1600 products)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from patchmatchnet_b200 import _native, ops
+from tests.conv_emulator import emulate_conv, pixel_stride
+
+# (cin, cout, ks, stride, pad, dil, relu): every conv shape of the model
+LAYERS = {
+    "feature.conv0": (3, 8, 3, 1, 1, 1, True),
+    "feature.conv1": (8, 8, 3, 1, 1, 1, True),
+    "feature.conv2": (8, 16, 5, 2, 2, 1, True),
+    "feature.conv3": (16, 16, 3, 1, 1, 1, True),
+    "feature.conv5": (16, 32, 5, 2, 2, 1, True),
+    "feature.conv6": (32, 32, 3, 1, 1, 1, True),
+    "feature.conv8": (32, 64, 5, 2, 2, 1, True),
+    "feature.conv9": (64, 64, 3, 1, 1, 1, True),
+    "feature.output1": (64, 64, 1, 1, 0, 1, False),
+    "feature.inner1": (32, 64, 1, 1, 0, 1, False),
+    "feature.inner2": (16, 64, 1, 1, 0, 1, False),
+    "feature.output2": (64, 32, 1, 1, 0, 1, False),
+    "feature.output3": (64, 16, 1, 1, 0, 1, False),
+    "refine.conv1": (1, 8, 3, 1, 1, 1, True),
+    "refine.conv3": (16, 8, 3, 1, 1, 1, True),
+    "refine.res": (8, 1, 3, 1, 1, 1, False),
+    "stage3.propa_conv": (64, 32, 3, 1, 2, 2, False),
+    "stage3.eval_conv": (64, 18, 3, 1, 2, 2, False),
+    "stage2.propa_conv": (32, 16, 3, 1, 4, 4, False),
+    "stage2.eval_conv": (32, 18, 3, 1, 4, 4, False),
+    "stage1.eval_conv": (16, 18, 3, 1, 6, 6, False),
+    "stage1.propa_conv": (16, 1, 3, 1, 6, 6, False),
+}
+
+
+def _ref_conv(x, w, b, S, pad, dil, relu):
+    y = F.conv2d(x, w, b, stride=S, padding=pad, dilation=dil)
+    return y.relu() if relu else y
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU: packing + index math
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", ["feature.conv0", "feature.conv2", "feature.conv9", "refine.res", "stage2.eval_conv", "stage1.eval_conv",
+                                  "feature.inner2", "refine.conv1"])
+def test_emulated_kernel_matches_conv2d(name):
+    cin, cout, ks, S, pad, dil, relu = LAYERS[name]
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    H, W = (7, 19) if cin >= 32 else (11, 21)
+    x = torch.randn(1, cin, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, ks, ks, generator=g).double()
+    b = torch.randn(cout, generator=g).double()
+    frag = ops.pack_conv_filter(w.float())
+    assert frag.numel() == _native.lib().pmb200_conv2d_filter_floats(cin, cout, ks)
+    want = _ref_conv(x, w, b, S, pad, dil, relu).permute(0, 2, 3, 1).numpy()
+    for mt in (1, 4):
+        got = emulate_conv(x.permute(0, 2, 3, 1).numpy(), frag.numpy(), b.numpy(), cout, ks, S, pad, dil, relu, False, mt)
+        assert got.shape == want.shape
+        assert not np.isnan(got).any(), "an output element was never written"
+        assert np.abs(got - want).max() < 1e-9
+        assert emulate_conv.last_banks_ok, "A-fragment loads of a warp must hit 32 distinct banks"
+
+
+def test_emulated_transposed_form_matches_conv_transpose2d():
+    """ConvTranspose2d(8, 8, 3, stride=2, padding=1, output_padding=1) (reference net.py:89) == stride-1 conv with the
+    flipped filter and pad 1 over the zero-stuffed input; written into channels 0..7 of a 16-channel buffer."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 8, 6, 9, generator=g, dtype=torch.float64)
+    wt = torch.randn(8, 8, 3, 3, generator=g).double()
+    b = torch.randn(8, generator=g).double()
+    want = F.conv_transpose2d(x, wt, b, stride=2, padding=1, output_padding=1).relu().permute(0, 2, 3, 1).numpy()
+    frag = ops.pack_conv_filter(wt.float(), transposed=True)
+    y = np.full((2, 12, 18, 16), np.nan)
+    got = emulate_conv(x.permute(0, 2, 3, 1).numpy(), frag.numpy(), b.numpy(), 8, 3, 1, 1, 1, True, True, 4, ycs=16, yco=0, y=y)
+    assert np.abs(got[..., :8] - want).max() < 1e-9
+    assert np.isnan(got[..., 8:]).all(), "channels outside the slice must not be touched"
+
+
+def test_pixel_stride_rule():
+    for kc in (8, 16, 32, 64):
+        for S in (1, 2):
+            ps = pixel_stride(kc, S)
+            assert ps >= kc and ps % 2 == 0 and (S * ps) % 32 in (4, 12, 20, 28)
+
+
+def test_conv_entry_rejects_bad_arguments_without_gpu():
+    lib = _native.lib()
+    one = ctypes.c_void_p(64)
+    ok_tail = (1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 1, 0, 0, 0, 0, None)
+    assert lib.pmb200_conv2d_nhwc(None, one, None, one, *ok_tail) == -1
+    assert b"null pointer" in lib.pmb200_last_error()
+    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 65, 8, 3, 1, 1, 1, 0, 1, 0, 0, 0, 0, None) == -1  # Cin > 64
+    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 3, 1, 1, 0, 1, 0, 0, 0, 0, None) == -1   # stride 3
+    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 2, 0, 0, 0, 0, None) == -1   # precision 2
+    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 1, 0, 12, 8, 0, None) == -1  # slice outside
+    assert lib.pmb200_conv2d_filter_floats(64, 64, 3) == 9 * 8 * 8 * 64
+    assert lib.pmb200_conv2d_filter_floats(3, 18, 3) == 9 * 1 * 3 * 64
+    assert lib.pmb200_conv2d_filter_floats(0, 8, 3) == -1
+
+
+def test_conv_wrapper_has_no_cpu_fallback():
+    x = torch.zeros(1, 8, 4, 4)
+    frag = ops.pack_conv_filter(torch.zeros(8, 8, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.conv2d_nhwc(x, frag, None, 8, 3, 1, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU: the kernel against cuDNN in full fp32
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.fixture()
+def fp32_library():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _scaled_err(got, want):
+    return float((got - want).abs().max() / want.abs().max().clamp_min(1e-6))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(LAYERS))
+def test_gpu_conv_matches_cudnn_fp32(name, fp32_library):
+    cin, cout, ks, S, pad, dil, relu = LAYERS[name]
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    # ragged map: neither dimension a multiple of the 16 x (4*MT) tile; two images
+    N, H, W = 2, 37, 53
+    x = torch.randn(N, cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    want = _ref_conv(x, w, b, S, pad, dil, relu)
+    frag = ops.pack_conv_filter(w)
+    for prec, tol in ((3, 2e-5), (1, 3e-3)):
+        for mt in (0, 1, 2, 4):
+            got = ops.conv2d_nhwc(x, frag, b, cout, ks, S, pad, dil, relu=relu, precision=prec, rows_per_warp=mt)
+            assert got.shape == want.shape
+            err = _scaled_err(got, want)
+            assert err <= tol, f"{name} precision {prec} rows_per_warp {mt}: scaled max err {err:.3e}"
+    torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+def test_gpu_conv_full_size_layers(fp32_library):
+    """The three heaviest shapes at their BASELINE config-2 sizes (5 stacked views of 640x512)."""
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(11)
+    for name, (H, W) in (("feature.conv1", (512, 640)), ("feature.conv5", (256, 320)), ("feature.conv9", (64, 80))):
+        cin, cout, ks, S, pad, dil, relu = LAYERS[name]
+        x = torch.randn(5, cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
+        b = torch.randn(cout, generator=g).to(dev)
+        want = _ref_conv(x, w, b, S, pad, dil, relu)
+        got = ops.conv2d_nhwc(x, ops.pack_conv_filter(w), b, cout, ks, S, pad, dil, relu=relu, precision=3)
+        assert _scaled_err(got, want) <= 2e-5, name
+
+
+@pytest.mark.gpu
+def test_gpu_transposed_conv_and_channel_slices(fp32_library):
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(5)
+    low = torch.randn(2, 8, 19, 27, generator=g).to(dev)
+    img = torch.randn(2, 3, 38, 54, generator=g).to(dev)
+    wt = (torch.randn(8, 8, 3, 3, generator=g) / 8).to(dev)
+    bt = torch.randn(8, generator=g).to(dev)
+    w0 = (torch.randn(8, 3, 3, 3, generator=g) / 5).to(dev)
+    b0 = torch.randn(8, generator=g).to(dev)
+    want = torch.cat((F.conv_transpose2d(low, wt, bt, stride=2, padding=1, output_padding=1).relu(),
+                      F.conv2d(img, w0, b0, padding=1).relu()), dim=1)
+    both = torch.full((2, 16, 38, 54), float("nan"), device=dev).contiguous(memory_format=torch.channels_last)
+    ops.conv2d_nhwc(low, ops.pack_conv_filter(wt, transposed=True), bt, 8, 3, 1, 1, 1, relu=True, transposed2x=True,
+                    out=both, out_channel_offset=0, precision=3)
+    assert torch.isnan(both[:, 8:]).all(), "the other half of the buffer must be untouched"
+    ops.conv2d_nhwc(img, ops.pack_conv_filter(w0), b0, 8, 3, 1, 1, 1, relu=True, out=both, out_channel_offset=8, precision=3)
+    assert _scaled_err(both, want) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_gpu_net_native_convs_match_library_convs(fp32_library, golden_weights):
+    """Whole network, eval mode: native convs (3xTF32) vs the folded cuDNN convs in fp32 -- same depth map."""
+    from patchmatchnet_b200 import synthetic
+    from patchmatchnet_b200.net import PatchmatchNet, load_reference_state
+
+    dev = "cuda:0"
+    net = PatchmatchNet(**synthetic.DEFAULT_NET_KWARGS)
+    load_reference_state(net, golden_weights)
+    net = net.eval().to(dev)
+    inp = synthetic.make_inputs(1, 3, 128, 160, seed=3)
+    args = lambda: ([i.to(dev) for i in inp["images"]], inp["intrinsics"].to(dev), inp["extrinsics"].to(dev),
+                    inp["depth_min"].to(dev), inp["depth_max"].to(dev))
+    outs = {}
+    old = ops.NATIVE_CONVS
+    try:
+        for flag in (True, False):
+            ops.NATIVE_CONVS = flag
+            torch.manual_seed(0)
+            with torch.no_grad():
+                depth, conf, _ = net(*args())
+            outs[flag] = (depth, conf)
+    finally:
+        ops.NATIVE_CONVS = old
+    rel = float((outs[True][0] - outs[False][0]).abs().sum() / outs[False][0].abs().sum())
+    assert rel <= 1e-4, rel

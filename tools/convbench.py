@@ -1,0 +1,111 @@
+"""Per-layer micro-benchmark of the native channels-last tensor-core conv (csrc/pm_conv.cu) against the cuDNN call it
+replaces, at the sizes of one 640x512 1+4-view forward (5 stacked views through FeatureNet, 1 view through the rest).
+
+    python tools/convbench.py > gpurun_out/convbench.json
+
+cold = L2 flushed before each launch (CUDA events on the launching stream), warm = 10 back-to-back launches.
+GB/s = (input + output activation bytes) / cold time: the traffic a perfectly fused layer must move.
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from patchmatchnet_b200 import ops  # noqa: E402
+
+dev = "cuda:0"
+torch.backends.cudnn.benchmark = True
+H, W = int(os.environ.get("CB_H", 512)), int(os.environ.get("CB_W", 640))
+# name: (N, cin, cout, ks, stride, pad, dil, relu, h, w)
+LAYERS = [
+    ("feature.conv0", 5, 3, 8, 3, 1, 1, 1, True, H, W),
+    ("feature.conv1", 5, 8, 8, 3, 1, 1, 1, True, H, W),
+    ("feature.conv2", 5, 8, 16, 5, 2, 2, 1, True, H, W),
+    ("feature.conv3/4", 5, 16, 16, 3, 1, 1, 1, True, H // 2, W // 2),
+    ("feature.conv5", 5, 16, 32, 5, 2, 2, 1, True, H // 2, W // 2),
+    ("feature.conv6/7", 5, 32, 32, 3, 1, 1, 1, True, H // 4, W // 4),
+    ("feature.conv8", 5, 32, 64, 5, 2, 2, 1, True, H // 4, W // 4),
+    ("feature.conv9/10", 5, 64, 64, 3, 1, 1, 1, True, H // 8, W // 8),
+    ("feature.output1", 5, 64, 64, 1, 1, 0, 1, False, H // 8, W // 8),
+    ("feature.inner1", 5, 32, 64, 1, 1, 0, 1, False, H // 4, W // 4),
+    ("feature.output2", 5, 64, 32, 1, 1, 0, 1, False, H // 4, W // 4),
+    ("feature.inner2", 5, 16, 64, 1, 1, 0, 1, False, H // 2, W // 2),
+    ("feature.output3", 5, 64, 16, 1, 1, 0, 1, False, H // 2, W // 2),
+    ("stage3.propa_conv", 1, 64, 32, 3, 1, 2, 2, False, H // 8, W // 8),
+    ("stage3.eval_conv", 1, 64, 18, 3, 1, 2, 2, False, H // 8, W // 8),
+    ("stage2.propa_conv", 1, 32, 16, 3, 1, 4, 4, False, H // 4, W // 4),
+    ("stage2.eval_conv", 1, 32, 18, 3, 1, 4, 4, False, H // 4, W // 4),
+    ("stage1.eval_conv", 1, 16, 18, 3, 1, 6, 6, False, H // 2, W // 2),
+    ("refine.conv1", 1, 1, 8, 3, 1, 1, 1, True, H // 2, W // 2),
+    ("refine.conv2", 1, 8, 8, 3, 1, 1, 1, True, H // 2, W // 2),
+    ("refine.conv0", 1, 3, 8, 3, 1, 1, 1, True, H, W),
+    ("refine.conv3", 1, 16, 8, 3, 1, 1, 1, True, H, W),
+    ("refine.res", 1, 8, 1, 3, 1, 1, 1, False, H, W),
+]
+flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    cold = []
+    for _ in range(iters):
+        flush_buf.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        cold.append(a.elapsed_time(b) * 1e3)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(2_000_000)
+    a.record()
+    for _ in range(10):
+        fn()
+    b.record()
+    b.synchronize()
+    return sum(cold) / len(cold), min(cold), a.elapsed_time(b) * 1e2
+
+
+rows = []
+g = torch.Generator().manual_seed(0)
+for (name, N, cin, cout, ks, S, pad, dil, relu, h, w) in LAYERS:
+    x = torch.randn(N, cin, h, w, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
+    wcl = wt.contiguous(memory_format=torch.channels_last)
+    b = torch.randn(cout, generator=g).to(dev)
+    frag = ops.pack_conv_filter(wt)
+    ho = (h + 2 * pad - dil * (ks - 1) - 1) // S + 1
+    wo = (w + 2 * pad - dil * (ks - 1) - 1) // S + 1
+    act_bytes = 4 * N * (h * w * cin + ho * wo * cout)
+    flops = 2.0 * N * ho * wo * cout * cin * ks * ks
+    row = {"layer": name, "shape": f"N{N} {cin}->{cout} k{ks} s{S} d{dil} {h}x{w}", "activation_mb": act_bytes / 1e6, "gflop": flops / 1e9}
+    torch.backends.cudnn.allow_tf32 = True
+    if relu and dil == 1:
+        lib = lambda: torch.cudnn_convolution_relu(x, wcl, b, (S, S), (pad, pad), (dil, dil), 1)
+    else:
+        lib = lambda: F.conv2d(x, wcl, b, S, pad, dil)
+    c, cmin, wm = timeit(lib)
+    row["cudnn_tf32_us"] = {"cold": round(c, 1), "cold_min": round(cmin, 1), "warm": round(wm, 1)}
+    best = None
+    for prec in (1, 3):
+        for mt in (0, 1, 2, 4):
+            fn = lambda: ops.conv2d_nhwc(x, frag, b, cout, ks, S, pad, dil, relu=relu, precision=prec, rows_per_warp=mt)
+            try:
+                c, cmin, wm = timeit(fn)
+            except Exception as e:  # noqa: BLE001
+                row[f"native_p{prec}_mt{mt}_us"] = f"ERR {e}"
+                continue
+            row[f"native_p{prec}_mt{mt}_us"] = {"cold": round(c, 1), "cold_min": round(cmin, 1), "warm": round(wm, 1)}
+            if prec == 1 and mt == 0:
+                row["native_tf32_gbs"] = round(act_bytes / (c * 1e-6) / 1e9, 1)
+                row["native_tf32_tflops"] = round(flops / (c * 1e-6) / 1e12, 2)
+                row["speedup_vs_cudnn_cold"] = round(row["cudnn_tf32_us"]["cold"] / c, 2)
+    rows.append(row)
+tot_lib = sum(r["cudnn_tf32_us"]["cold"] for r in rows)
+tot_nat = sum(r["native_p1_mt0_us"]["cold"] for r in rows if isinstance(r.get("native_p1_mt0_us"), dict))
+print(json.dumps({"gpu": torch.cuda.get_device_name(0), "size": [H, W], "sum_cold_us": {"cudnn_tf32": round(tot_lib, 1), "native_tf32": round(tot_nat, 1)},
+                  "layers": rows}, indent=1))
