@@ -85,18 +85,22 @@ int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const f
  * (models/net.py:9-70) and Refinement (models/net.py:73-122, including its ConvTranspose2d: transposed2x = 1 runs the
  * equivalent stride-1 conv over the virtually zero-stuffed input, caller passes the flipped filter and pad = KS-1-pad_t).
  *   x            [N,H,W,Cin]      (16-byte aligned when Cin % 4 == 0)
- *   filter_frag  the filter in tensor-core fragment order, pmb200_conv2d_filter_floats(Cin,Cout,KS) floats:
- *                [tap = ky*KS+kx][ks = 0..ceil8(Cin')/8)[nt = 0..NT)[lane = 0..32)[2] with
- *                (b0, b1) = (w[nt*8 + lane/4][ks*8 + lane%4][ky][kx], w[nt*8 + lane/4][ks*8 + lane%4 + 4][ky][kx]),
- *                zero where the channel index is outside the filter; Cin' = Cin rounded up to 8/16/32/64,
- *                NT = ceil(Cout/8) rounded up to 1,2,3,4 or 8
+ *   filter_frag  the filter in tensor-core fragment order for the chosen precision,
+ *                pmb200_conv2d_filter_floats(Cin,Cout,KS,precision) floats, 16-byte aligned:
+ *                [tap = ky*KS+kx][ks = 0..Cin'/8)[nt = 0..NT)[lane = 0..32)[2 or 4], lane = 4*g + t holding
+ *                (b0, b1) = (w[nt*8+g][ks*8+2t][ky][kx], w[nt*8+g][ks*8+2t+1][ky][kx]) -- the MMA's k slots (t, t+4)
+ *                are mapped to the adjacent channels (2t, 2t+1) -- zero where an index is outside the filter;
+ *                Cin' = Cin rounded up to 8/16/32/64, NT = ceil(Cout/8) rounded up to 1,2,3,4 or 8.
+ *                precision 1: the two values rounded to TF32 (nearest, ties away from zero);
+ *                precision 3: four values (b0_hi, b1_hi, b0_lo, b1_lo), hi = tf32(w), lo = tf32(w - hi)
  *   bias         [Cout] or NULL
  *   y            [N,Ho,Wo,y_channel_stride], written at channels y_channel_offset .. +Cout (stride 0 = Cout: dense)
- *   precision    1: operands rounded to TF32 (the library's behaviour under torch.backends.cudnn.allow_tf32, torch's
- *                default); 3: error-compensated 3xTF32, fp32-accurate
+ *   precision    1: TF32 operands (the library's behaviour under torch.backends.cudnn.allow_tf32, torch's default:
+ *                filter rounded by the host, activations truncated by the tensor core as for tcgen05 kind::tf32);
+ *                3: error-compensated 3xTF32, fp32-accurate
  *   rows_per_warp 0 = choose (tile = 16 columns x 4*rows_per_warp rows per 4-warp CTA); 1, 2 or 4 to force
  */
-int pmb200_conv2d_filter_floats(int Cin, int Cout, int KS);
+int pmb200_conv2d_filter_floats(int Cin, int Cout, int KS, int precision);
 int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bias, float *y,
                        int N, int H, int W, int Cin, int Cout, int KS, int stride, int pad, int dil,
                        int relu, int precision, int transposed2x, int y_channel_stride, int y_channel_offset,

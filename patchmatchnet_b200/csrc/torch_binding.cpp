@@ -341,9 +341,9 @@ Tensor conv2d_nhwc(const Tensor &x, const Tensor &filter_frag, const c10::option
                 "conv2d_nhwc: x must be a 4-D CUDA float32 tensor; there is no CPU fallback");
     const Tensor xc = x.contiguous(at::MemoryFormat::ChannelsLast);
     const int64_t N = xc.size(0), cin = xc.size(1), H = xc.size(2), W = xc.size(3);
-    const int want = pmb200_conv2d_filter_floats((int)cin, (int)cout, (int)ks);
+    const int want = pmb200_conv2d_filter_floats((int)cin, (int)cout, (int)ks, (int)precision);
     TORCH_CHECK(want > 0 && filter_frag.scalar_type() == at::kFloat && filter_frag.numel() == want,
-                "conv2d_nhwc: filter must be ", want, " float32 values in fragment order (pack_conv_filter)");
+                "conv2d_nhwc: filter must be ", want, " float32 values in fragment order for this precision (pack_conv_filter)");
     c10::cuda::CUDAGuard guard(xc.device());
     const Tensor frag = filter_frag.to(xc.device()).contiguous();
     Tensor b;

@@ -53,8 +53,8 @@ class _FoldCache:
     def __init__(self) -> None:
         self._entry = (None, None)
 
-    def get(self, tensors, make):
-        stamp = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+    def get(self, tensors, make, key=None):
+        stamp = (key,) + tuple((t.data_ptr(), t._version, t.device) for t in tensors)
         have, value = self._entry
         if stamp != have:
             with torch.no_grad():
@@ -84,8 +84,9 @@ class _PackedConv:
         from . import ops
 
         srcs = [conv.weight] + ([conv.bias] if conv.bias is not None else [])
+        prec = ops.conv_precision()
         frag, bias = self._cache.get(
-            srcs, lambda: (ops.pack_conv_filter(conv.weight), None if conv.bias is None else conv.bias.detach().clone()))
+            srcs, lambda: (ops.pack_conv_filter(conv.weight, prec), None if conv.bias is None else conv.bias.detach().clone()), key=prec)
         return ops.conv2d_nhwc(x, frag, bias if with_bias else None, conv.out_channels, conv.kernel_size[0], conv.stride[0],
                                conv.padding[0], conv.dilation[0], relu=relu)
 
@@ -112,11 +113,13 @@ class _ConvBnReLU2d(nn.Module):
         bn = self.bn
         srcs = [self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
 
+        prec = ops.conv_precision()
+
         def make():
             w, b = _fold_bn(self.conv.weight, bn)
-            return ops.pack_conv_filter(w), b.contiguous()
+            return ops.pack_conv_filter(w, prec), b.contiguous()
 
-        return self._frag_cache.get(srcs, make)
+        return self._frag_cache.get(srcs, make, key=prec)
 
     def native(self, x: Tensor, out: Tensor = None, out_channel_offset: int = 0) -> Tensor:
         from . import ops
@@ -231,11 +234,13 @@ class Refinement(nn.Module):
         bn = self.bn
         srcs = [self.deconv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
 
+        prec = ops.conv_precision()
+
         def make():
             w, b = _fold_bn(self.deconv.weight, bn, out_dim=1)
-            return ops.pack_conv_filter(w, transposed=True), b.contiguous()
+            return ops.pack_conv_filter(w, prec, transposed=True), b.contiguous()
 
-        frag, b = self._deconv_frag.get(srcs, make)
+        frag, b = self._deconv_frag.get(srcs, make, key=prec)
         low = self.conv2.native(self.conv1.native(d))
         N, _, h, w = low.shape
         both = torch.empty((N, 16, 2 * h, 2 * w), dtype=torch.float32, device=low.device, memory_format=torch.channels_last)

@@ -159,14 +159,25 @@ def _round_nt(cout: int) -> int:
     return nt if nt <= 4 else 8
 
 
-def pack_conv_filter(weight: Tensor, transposed: bool = False) -> Tensor:
-    """Conv filter [Cout,Cin,KS,KS] -> the tensor-core fragment order `pmb200_conv2d_nhwc` reads
-    (include/patchmatch_b200.h): [tap][k-slice][n-tile][lane][2] with lane = 4*g + t holding
-    (w[nt*8+g][ks*8+t], w[nt*8+g][ks*8+t+4]) of that tap, zero padded.  `transposed`: `weight` is a
-    ConvTranspose2d filter [Cin,Cout,KS,KS]; the equivalent direct filter is its spatial flip with the
-    channel axes swapped.  Pure layout work on the weight's own device (host logic, CPU-testable)."""
+def _tf32_round(x: Tensor) -> Tensor:
+    """fp32 -> nearest TF32 value (10-bit mantissa), ties away from zero -- the arithmetic of PTX cvt.rna.tf32.f32 for
+    finite inputs: add half an ulp to the magnitude bits, clear the 13 low bits."""
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_conv_filter(weight: Tensor, precision: int, transposed: bool = False) -> Tensor:
+    """Conv filter [Cout,Cin,KS,KS] -> the tensor-core fragment order `pmb200_conv2d_nhwc` reads for `precision`
+    (include/patchmatch_b200.h): [tap][k-slice][n-tile][lane][2 or 4] with lane = 4*g + t holding the weights of
+    output channel nt*8+g for the adjacent input channels ks*8+2t, ks*8+2t+1 of that tap (the MMA's k slots t, t+4),
+    zero padded.  precision 1: values rounded to TF32; precision 3: (b0_hi, b1_hi, b0_lo, b1_lo) with
+    hi = tf32(w), lo = tf32(w - hi).  `transposed`: `weight` is a ConvTranspose2d filter [Cin,Cout,KS,KS]; the
+    equivalent direct filter is its spatial flip with the channel axes swapped.  Pure layout/rounding work on the
+    weight's own device (host logic, CPU-testable)."""
     if weight.dim() != 4 or weight.shape[2] != weight.shape[3]:
         raise RuntimeError(f"pack_conv_filter: expected [Cout,Cin,KS,KS], got {tuple(weight.shape)}")
+    if precision not in (1, 3):
+        raise RuntimeError("pack_conv_filter: precision must be 1 (TF32) or 3 (3xTF32)")
     w = weight.detach().float()
     if transposed:
         w = w.flip(2, 3).permute(1, 0, 2, 3)
@@ -176,9 +187,13 @@ def pack_conv_filter(weight: Tensor, transposed: bool = False) -> Tensor:
     kc, nt = _round_kcin(cin), _round_nt(cout)
     wp = torch.zeros((ks * ks, kc, nt * 8), dtype=torch.float32, device=w.device)
     wp[:, :cin, :cout] = w.permute(2, 3, 1, 0).reshape(ks * ks, cin, cout)
-    # k = ks8*8 + half*4 + t ; n = j*8 + g  ->  [tap][ks8][j][g][t][half]
-    frag = wp.view(ks * ks, kc // 8, 2, 4, nt, 8).permute(0, 1, 4, 5, 3, 2).contiguous()
-    return frag.view(-1)
+    # channel = ks8*8 + 2*t + half ; n = j*8 + g  ->  [tap][ks8][j][g][t][half]
+    frag = wp.view(ks * ks, kc // 8, 4, 2, nt, 8).permute(0, 1, 4, 5, 2, 3).contiguous()
+    hi = _tf32_round(frag)
+    if precision == 1:
+        return hi.view(-1)
+    lo = _tf32_round(frag - hi)
+    return torch.cat((hi, lo), dim=-1).contiguous().view(-1)
 
 
 def conv_precision() -> int:
@@ -198,9 +213,11 @@ def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: in
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     N, cin, H, W = x.shape
-    want = _native.lib().pmb200_conv2d_filter_floats(cin, cout, ks)
+    prec = conv_precision() if precision is None else precision
+    want = _native.lib().pmb200_conv2d_filter_floats(cin, cout, ks, prec)
     if want <= 0 or filter_frag.numel() != want or filter_frag.dtype != torch.float32 or filter_frag.device != x.device:
-        raise RuntimeError(f"conv2d_nhwc: filter must be {want} float32 values on {x.device} in fragment order (pack_conv_filter)")
+        raise RuntimeError(f"conv2d_nhwc: filter must be {want} float32 values on {x.device} in fragment order for precision {prec} "
+                           "(pack_conv_filter)")
     Hv, Wv = (2 * H, 2 * W) if transposed2x else (H, W)
     Ho = (Hv + 2 * pad - dil * (ks - 1) - 1) // stride + 1
     Wo = (Wv + 2 * pad - dil * (ks - 1) - 1) // stride + 1
@@ -218,7 +235,6 @@ def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: in
         if bias.numel() != cout:
             raise RuntimeError("conv2d_nhwc: bias must have Cout elements")
         b_ptr = bias.data_ptr()
-    prec = conv_precision() if precision is None else precision
     with torch.cuda.device(x.device):
         rc = _native.lib().pmb200_conv2d_nhwc(
             x.data_ptr(), filter_frag.data_ptr(), b_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride, pad, dil,

@@ -50,11 +50,12 @@ def _offset_conv(conv: nn.Conv2d, x: Tensor, native: bool) -> Tensor:
     if not native:
         return conv(x)
     srcs = (conv.weight, conv.bias)
-    stamp = tuple((t.data_ptr(), t._version, t.device) for t in srcs)
+    prec = ops.conv_precision()
+    stamp = (prec,) + tuple((t.data_ptr(), t._version, t.device) for t in srcs)
     cached = _FOLD_CACHE.get(conv)
     if cached is None or cached[0] != stamp:
         with torch.no_grad():
-            cached = (stamp, (ops.pack_conv_filter(conv.weight), conv.bias.detach().clone()))
+            cached = (stamp, (ops.pack_conv_filter(conv.weight, prec), conv.bias.detach().clone()))
         _FOLD_CACHE[conv] = cached
     frag, bias = cached[1]
     return ops.conv2d_nhwc(x, frag, bias, conv.out_channels, conv.kernel_size[0], 1, conv.padding[0], conv.dilation[0])
@@ -248,10 +249,10 @@ class PatchMatch(nn.Module):
             self._head_fw = self.feature_weight_net.folded_tensor()
             self._head_pw = self.evaluation.pixel_wise_net.folded_tensor()
             self._head_sim = self.evaluation.similarity_net.folded_tensor()
-        with torch.no_grad():
-            self._off_propa_frag = ops.pack_conv_filter(self.propa_conv.weight).cpu()
-            self._off_eval_frag = ops.pack_conv_filter(self.eval_conv.weight).cpu()
         self._conv_precision = ops.conv_precision()
+        with torch.no_grad():
+            self._off_propa_frag = ops.pack_conv_filter(self.propa_conv.weight, self._conv_precision).cpu()
+            self._off_eval_frag = ops.pack_conv_filter(self.eval_conv.weight, self._conv_precision).cpu()
 
     def train(self, mode: bool = True):
         super().train(mode)

@@ -1,7 +1,7 @@
 """Lane-level CPU emulation of csrc/pm_conv.cu (test infrastructure only).
 
 Mirrors the kernel step by step -- halo staging with the bank-conflict-free pixel stride, zero padding / zero
-stuffing, A-fragment addresses, host-packed B fragments, the m16n8k8 lane <-> matrix-element mapping of
+stuffing, 64-bit A-fragment addresses (k slots t, t+4 <- channels 2t, 2t+1), host-packed B fragments, the m16n8k8 lane <-> matrix-element mapping of
 `mma.sync` and the epilogue's (pixel, channel) ownership -- in exact fp32/fp64 arithmetic, so that the CPU build
 box can check the index math and the host-side filter packing against torch's conv2d without a GPU.
 """
@@ -21,8 +21,8 @@ def round_nt(cout: int) -> int:
 
 def pixel_stride(kcin: int, S: int) -> int:
     ps = kcin
-    while (S * ps) % 32 not in (4, 12, 20, 28):
-        ps += 2
+    while (S * ps) % 32 not in (8, 24):
+        ps += 4
     return ps
 
 
@@ -51,7 +51,9 @@ def emulate_conv(x_nhwc: np.ndarray, frag: np.ndarray, bias, cout: int, ks: int,
     ycs = ycs or cout
     if y is None:
         y = np.full((N, Ho, Wo, ycs), np.nan, dtype=np.float64)
-    frag = np.asarray(frag, dtype=np.float64).reshape(ks * ks, KK, nt, 32, 2)
+    frag = np.asarray(frag, dtype=np.float64).reshape(ks * ks, KK, nt, 32, -1)
+    if frag.shape[-1] == 4:  # 3xTF32 packing (b0_hi, b1_hi, b0_lo, b1_lo): hi + lo restores the weight to ~2^-22
+        frag = frag[..., :2] + frag[..., 2:]
     lanes = np.arange(32)
     g, t = lanes >> 2, lanes & 3
     banks_ok = True
@@ -80,14 +82,16 @@ def emulate_conv(x_nhwc: np.ndarray, frag: np.ndarray, bias, cout: int, ks: int,
                                 tap = ky * ks + kx
                                 for kk in range(KK):
                                     base = ((orow * S + ky * dil) * rw + kx * dil) * ps + kk * 8
-                                    i0 = base + g * S * ps + t
+                                    i0 = base + g * S * ps + 2 * t   # 64-bit load: channels 2t, 2t+1 of pixel g
                                     i1 = i0 + 8 * S * ps
-                                    banks_ok = banks_ok and len(set((i0 % 32).tolist())) == 32
+                                    for half in (slice(0, 16), slice(16, 32)):  # a 64-bit shared load is served per half-warp
+                                        words = np.concatenate((i0[half], i0[half] + 1)) % 32
+                                        banks_ok = banks_ok and len(set(words.tolist())) == 32
                                     A = np.zeros((16, 8))
-                                    A[g, t] = s_in[i0]
+                                    A[g, t] = s_in[i0]          # k slot t   <- channel 2t
                                     A[g + 8, t] = s_in[i1]
-                                    A[g, t + 4] = s_in[i0 + 4]
-                                    A[g + 8, t + 4] = s_in[i1 + 4]
+                                    A[g, t + 4] = s_in[i0 + 1]  # k slot t+4 <- channel 2t+1
+                                    A[g + 8, t + 4] = s_in[i1 + 1]
                                     for j in range(nt):
                                         Bm = np.zeros((8, 8))
                                         Bm[t, g] = frag[tap, kk, j, :, 0]

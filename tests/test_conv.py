@@ -63,15 +63,17 @@ def test_emulated_kernel_matches_conv2d(name):
     x = torch.randn(1, cin, H, W, generator=g, dtype=torch.float64)
     w = torch.randn(cout, cin, ks, ks, generator=g).double()
     b = torch.randn(cout, generator=g).double()
-    frag = ops.pack_conv_filter(w.float())
-    assert frag.numel() == _native.lib().pmb200_conv2d_filter_floats(cin, cout, ks)
-    want = _ref_conv(x, w, b, S, pad, dil, relu).permute(0, 2, 3, 1).numpy()
-    for mt in (1, 4):
-        got = emulate_conv(x.permute(0, 2, 3, 1).numpy(), frag.numpy(), b.numpy(), cout, ks, S, pad, dil, relu, False, mt)
-        assert got.shape == want.shape
-        assert not np.isnan(got).any(), "an output element was never written"
-        assert np.abs(got - want).max() < 1e-9
-        assert emulate_conv.last_banks_ok, "A-fragment loads of a warp must hit 32 distinct banks"
+    want = _ref_conv(x, w.float().double(), b, S, pad, dil, relu).permute(0, 2, 3, 1).numpy()
+    scale = np.abs(want).max()
+    for prec, tol in ((3, 2e-6), (1, 2e-3)):  # hi+lo restores the fp32 weight to 2^-22; TF32 weights carry 2^-11
+        frag = ops.pack_conv_filter(w.float(), prec)
+        assert frag.numel() == _native.lib().pmb200_conv2d_filter_floats(cin, cout, ks, prec)
+        for mt in (1, 4):
+            got = emulate_conv(x.permute(0, 2, 3, 1).numpy(), frag.numpy(), b.numpy(), cout, ks, S, pad, dil, relu, False, mt)
+            assert got.shape == want.shape
+            assert not np.isnan(got).any(), "an output element was never written"
+            assert np.abs(got - want).max() <= tol * scale
+            assert emulate_conv.last_banks_ok, "the 64-bit A-fragment loads of each half-warp must hit 32 distinct banks"
 
 
 def test_emulated_transposed_form_matches_conv_transpose2d():
@@ -82,10 +84,11 @@ def test_emulated_transposed_form_matches_conv_transpose2d():
     wt = torch.randn(8, 8, 3, 3, generator=g).double()
     b = torch.randn(8, generator=g).double()
     want = F.conv_transpose2d(x, wt, b, stride=2, padding=1, output_padding=1).relu().permute(0, 2, 3, 1).numpy()
-    frag = ops.pack_conv_filter(wt.float(), transposed=True)
+    want = F.conv_transpose2d(x, wt.float().double(), b, stride=2, padding=1, output_padding=1).relu().permute(0, 2, 3, 1).numpy()
+    frag = ops.pack_conv_filter(wt.float(), 3, transposed=True)
     y = np.full((2, 12, 18, 16), np.nan)
     got = emulate_conv(x.permute(0, 2, 3, 1).numpy(), frag.numpy(), b.numpy(), 8, 3, 1, 1, 1, True, True, 4, ycs=16, yco=0, y=y)
-    assert np.abs(got[..., :8] - want).max() < 1e-9
+    assert np.abs(got[..., :8] - want).max() <= 2e-6 * np.abs(want).max()
     assert np.isnan(got[..., 8:]).all(), "channels outside the slice must not be touched"
 
 
@@ -93,7 +96,23 @@ def test_pixel_stride_rule():
     for kc in (8, 16, 32, 64):
         for S in (1, 2):
             ps = pixel_stride(kc, S)
-            assert ps >= kc and ps % 2 == 0 and (S * ps) % 32 in (4, 12, 20, 28)
+            assert ps >= kc and ps % 4 == 0 and (S * ps) % 32 in (8, 24)
+
+
+def test_tf32_rounding_matches_cvt_rna():
+    """The host-side TF32 rounding of the filter: nearest 10-bit mantissa, ties away from zero."""
+    x = torch.tensor([1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -11 + 2.0 ** -20, 1.0 + 2.0 ** -12, -(1.0 + 2.0 ** -11), 3.0e-5, -7.25, 0.0])
+    r = ops._tf32_round(x)
+    want = torch.tensor([1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -10, 1.0, -(1.0 + 2.0 ** -10), 0.0, -7.25, 0.0])
+    want[5] = r[5]
+    assert torch.equal(r, want)
+    assert (r.view(torch.int32) & 0x1FFF).eq(0).all()
+    assert ((r - x).abs() <= x.abs() * 2.0 ** -11).all()
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(1000, generator=g)
+    hi = ops._tf32_round(w)
+    lo = ops._tf32_round(w - hi)
+    assert ((hi + lo - w).abs() <= w.abs() * 2.0 ** -21).all()
 
 
 def test_conv_entry_rejects_bad_arguments_without_gpu():
@@ -106,16 +125,17 @@ def test_conv_entry_rejects_bad_arguments_without_gpu():
     assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 3, 1, 1, 0, 1, 0, 0, 0, 0, None) == -1   # stride 3
     assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 2, 0, 0, 0, 0, None) == -1   # precision 2
     assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 1, 0, 12, 8, 0, None) == -1  # slice outside
-    assert lib.pmb200_conv2d_filter_floats(64, 64, 3) == 9 * 8 * 8 * 64
-    assert lib.pmb200_conv2d_filter_floats(3, 18, 3) == 9 * 1 * 3 * 64
-    assert lib.pmb200_conv2d_filter_floats(0, 8, 3) == -1
+    assert lib.pmb200_conv2d_filter_floats(64, 64, 3, 1) == 9 * 8 * 8 * 64
+    assert lib.pmb200_conv2d_filter_floats(3, 18, 3, 3) == 9 * 1 * 3 * 128
+    assert lib.pmb200_conv2d_filter_floats(0, 8, 3, 1) == -1
+    assert lib.pmb200_conv2d_filter_floats(8, 8, 3, 2) == -1
 
 
 def test_conv_wrapper_has_no_cpu_fallback():
     x = torch.zeros(1, 8, 4, 4)
-    frag = ops.pack_conv_filter(torch.zeros(8, 8, 3, 3))
+    frag = ops.pack_conv_filter(torch.zeros(8, 8, 3, 3), 1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        ops.conv2d_nhwc(x, frag, None, 8, 3, 1, 1)
+        ops.conv2d_nhwc(x, frag, None, 8, 3, 1, 1, precision=1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -148,8 +168,8 @@ def test_gpu_conv_matches_cudnn_fp32(name, fp32_library):
     w = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
     b = torch.randn(cout, generator=g).to(dev)
     want = _ref_conv(x, w, b, S, pad, dil, relu)
-    frag = ops.pack_conv_filter(w)
     for prec, tol in ((3, 2e-5), (1, 3e-3)):
+        frag = ops.pack_conv_filter(w, prec)
         for mt in (0, 1, 2, 4):
             got = ops.conv2d_nhwc(x, frag, b, cout, ks, S, pad, dil, relu=relu, precision=prec, rows_per_warp=mt)
             assert got.shape == want.shape
@@ -169,7 +189,7 @@ def test_gpu_conv_full_size_layers(fp32_library):
         w = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
         b = torch.randn(cout, generator=g).to(dev)
         want = _ref_conv(x, w, b, S, pad, dil, relu)
-        got = ops.conv2d_nhwc(x, ops.pack_conv_filter(w), b, cout, ks, S, pad, dil, relu=relu, precision=3)
+        got = ops.conv2d_nhwc(x, ops.pack_conv_filter(w, 3), b, cout, ks, S, pad, dil, relu=relu, precision=3)
         assert _scaled_err(got, want) <= 2e-5, name
 
 
@@ -186,10 +206,10 @@ def test_gpu_transposed_conv_and_channel_slices(fp32_library):
     want = torch.cat((F.conv_transpose2d(low, wt, bt, stride=2, padding=1, output_padding=1).relu(),
                       F.conv2d(img, w0, b0, padding=1).relu()), dim=1)
     both = torch.full((2, 16, 38, 54), float("nan"), device=dev).contiguous(memory_format=torch.channels_last)
-    ops.conv2d_nhwc(low, ops.pack_conv_filter(wt, transposed=True), bt, 8, 3, 1, 1, 1, relu=True, transposed2x=True,
+    ops.conv2d_nhwc(low, ops.pack_conv_filter(wt, 3, transposed=True), bt, 8, 3, 1, 1, 1, relu=True, transposed2x=True,
                     out=both, out_channel_offset=0, precision=3)
     assert torch.isnan(both[:, 8:]).all(), "the other half of the buffer must be untouched"
-    ops.conv2d_nhwc(img, ops.pack_conv_filter(w0), b0, 8, 3, 1, 1, 1, relu=True, out=both, out_channel_offset=8, precision=3)
+    ops.conv2d_nhwc(img, ops.pack_conv_filter(w0, 3), b0, 8, 3, 1, 1, 1, relu=True, out=both, out_channel_offset=8, precision=3)
     assert _scaled_err(both, want) <= 2e-5
 
 

@@ -77,7 +77,8 @@ for (name, N, cin, cout, ks, S, pad, dil, relu, h, w) in LAYERS:
     wt = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
     wcl = wt.contiguous(memory_format=torch.channels_last)
     b = torch.randn(cout, generator=g).to(dev)
-    frag = ops.pack_conv_filter(wt)
+    frags = {1: ops.pack_conv_filter(wt, 1), 3: ops.pack_conv_filter(wt, 3)}
+    frag = frags[1]
     ho = (h + 2 * pad - dil * (ks - 1) - 1) // S + 1
     wo = (w + 2 * pad - dil * (ks - 1) - 1) // S + 1
     act_bytes = 4 * N * (h * w * cin + ho * wo * cout)
@@ -92,8 +93,8 @@ for (name, N, cin, cout, ks, S, pad, dil, relu, h, w) in LAYERS:
     row["cudnn_tf32_us"] = {"cold": round(c, 1), "cold_min": round(cmin, 1), "warm": round(wm, 1)}
     best = None
     for prec in (1, 3):
-        for mt in (0, 1, 2, 4):
-            fn = lambda: ops.conv2d_nhwc(x, frag, b, cout, ks, S, pad, dil, relu=relu, precision=prec, rows_per_warp=mt)
+        for mt in ((0, 1, 2, 4, -1) if prec == 1 else (0,)):
+            fn = lambda: ops.conv2d_nhwc(x, frags[prec], b, cout, ks, S, pad, dil, relu=relu, precision=prec, rows_per_warp=mt)
             try:
                 c, cmin, wm = timeit(fn)
             except Exception as e:  # noqa: BLE001
