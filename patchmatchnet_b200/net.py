@@ -74,6 +74,12 @@ def _native_convs(x: Tensor) -> bool:
     return ops.NATIVE_CONVS and _fast(x) and not torch.is_grad_enabled()
 
 
+def ops_prefers(conv: nn.Conv2d) -> bool:
+    from . import ops
+
+    return ops.conv_prefers_native(conv.in_channels, conv.out_channels, conv.kernel_size[0])
+
+
 class _PackedConv:
     """Fragment-ordered filter (+ bias) of a plain nn.Conv2d, cached until the weights change or move."""
 
@@ -142,7 +148,8 @@ class _ConvBnReLU2d(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         if self.training or not _fast(x):
             return F.relu(self.bn(self.conv(x)), inplace=True)
-        if _native_convs(x):
+        c = self.conv
+        if _native_convs(x) and ops_prefers(c):
             return self.native(x)
         w, b = self.folded()
         c = self.conv

@@ -148,6 +148,17 @@ def upsample2x_add(x: Tensor, y: Tensor, bias: Optional[Tensor] = None) -> Tenso
 # The small learned convs (offset convs of the hot path, FeatureNet, Refinement) run through csrc/pm_conv.cu in eval
 # mode.  False (or PMB200_NATIVE_CONVS=0) hands them back to cuDNN -- kept only for A/B measurements.
 NATIVE_CONVS = os.environ.get("PMB200_NATIVE_CONVS", "1") != "0"
+NATIVE_CONVS_ALL = os.environ.get("PMB200_NATIVE_CONVS", "1") == "all"  # A/B aid: native even where the library is faster
+
+
+def conv_prefers_native(cin: int, cout: int, ks: int) -> bool:
+    """Which implementation runs a small conv in eval mode.  Measured per layer on B200 (profiles/r1_run17_convbench.json,
+    tools/convbench.py): the native channels-last kernel wins on the memory-bound layers -- every 1x1 conv and every
+    layer with at most 3200 multiply-adds per output pixel (full-resolution 3->8 / 8->8 / 8->16 convs, the refinement
+    head, the stage-1 offset conv: 1.2-3.7x faster than the library) -- while the FLOP-heavy 16..64-channel 3x3 / 5x5
+    layers stay with cuDNN, whose tcgen05 implicit-GEMM kernels reach 100-150 TFLOP/s there against ~50 for the
+    legacy mma.sync path this kernel issues (measured peak of that path: ~245 TFLOP/s TF32)."""
+    return NATIVE_CONVS and (NATIVE_CONVS_ALL or ks == 1 or cin * cout * ks * ks <= 3200)
 
 
 def _round_kcin(cin: int) -> int:

@@ -47,7 +47,7 @@ def _offset_conv(conv: nn.Conv2d, x: Tensor, native: bool) -> Tensor:
     """propa_conv / eval_conv (reference patchmatch.py:288-311, called at :486 / :498).  `native`: the channels-last
     tensor-core conv of csrc/pm_conv.cu (its channels-last output is what the fused kernels consume in place); the
     fragment-ordered filter is cached off the module (TorchScript would try to type the attribute)."""
-    if not native:
+    if not native or not ops.conv_prefers_native(conv.in_channels, conv.out_channels, conv.kernel_size[0]):
         return conv(x)
     srcs = (conv.weight, conv.bias)
     prec = ops.conv_precision()
@@ -240,6 +240,8 @@ class PatchMatch(nn.Module):
         self._off_propa_frag = torch.zeros(1)
         self._off_eval_frag = torch.zeros(1)
         self._conv_precision = 3
+        self._native_propa = False  # ops.conv_prefers_native(...) for the two offset convs, frozen likewise
+        self._native_eval = False
         self.register_load_state_dict_post_hook(_refresh_after_load)
 
     # ------------------------------------------------------------------
@@ -250,6 +252,8 @@ class PatchMatch(nn.Module):
             self._head_pw = self.evaluation.pixel_wise_net.folded_tensor()
             self._head_sim = self.evaluation.similarity_net.folded_tensor()
         self._conv_precision = ops.conv_precision()
+        self._native_propa = ops.conv_prefers_native(self.propa_conv.in_channels, self.propa_conv.out_channels, 3)
+        self._native_eval = ops.conv_prefers_native(self.eval_conv.in_channels, self.eval_conv.out_channels, 3)
         with torch.no_grad():
             self._off_propa_frag = ops.pack_conv_filter(self.propa_conv.weight, self._conv_precision).cpu()
             self._off_eval_frag = ops.pack_conv_filter(self.eval_conv.weight, self._conv_precision).cpu()
@@ -320,12 +324,18 @@ class PatchMatch(nn.Module):
 
         propa_off: Optional[Tensor] = None
         if Kp > 0 and not (self.stage == 1 and iters == 1):
-            propa_off = torch.ops.pmb200.conv2d_nhwc(
-                ref_feature, self._off_propa_frag, self.propa_conv.bias, 2 * Kp, 3, 1, self.dilation, self.dilation, False,
+            if self._native_propa:
+                propa_off = torch.ops.pmb200.conv2d_nhwc(
+                    ref_feature, self._off_propa_frag, self.propa_conv.bias, 2 * Kp, 3, 1, self.dilation, self.dilation, False,
+                    self._conv_precision)
+            else:
+                propa_off = self.propa_conv(ref_feature)
+        if self._native_eval:
+            eval_off = torch.ops.pmb200.conv2d_nhwc(
+                ref_feature, self._off_eval_frag, self.eval_conv.bias, 2 * Ke, 3, 1, self.dilation, self.dilation, False,
                 self._conv_precision)
-        eval_off = torch.ops.pmb200.conv2d_nhwc(
-            ref_feature, self._off_eval_frag, self.eval_conv.bias, 2 * Ke, 3, 1, self.dilation, self.dilation, False,
-            self._conv_precision)
+        else:
+            eval_off = self.eval_conv(ref_feature)
 
         same_size = True
         for f in src_features:

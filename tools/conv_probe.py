@@ -10,6 +10,8 @@ from patchmatchnet_b200 import ops  # noqa: E402
 dev = "cuda:0"
 LAYERS = [  # N, cin, cout, ks, S, pad, dil, h, w
     ("conv1", 5, 8, 8, 3, 1, 1, 1, 512, 640),
+    ("conv3", 5, 16, 16, 3, 1, 1, 1, 256, 320),
+    ("conv6", 5, 32, 32, 3, 1, 1, 1, 128, 160),
     ("conv5", 5, 16, 32, 5, 2, 2, 1, 256, 320),
     ("conv8", 5, 32, 64, 5, 2, 2, 1, 128, 160),
     ("conv9", 5, 64, 64, 3, 1, 1, 1, 64, 80),
