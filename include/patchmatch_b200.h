@@ -94,6 +94,9 @@ int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const f
  *                precision 1: the two values rounded to TF32 (nearest, ties away from zero);
  *                precision 3: four values (b0_hi, b1_hi, b0_lo, b1_lo), hi = tf32(w), lo = tf32(w - hi)
  *   bias         [Cout] or NULL
+ *   add_up2x     NULL, or a coarser map [N,Ho/2,Wo/2,Cout] whose bilinear x2 upsample (F.interpolate scale_factor=2,
+ *                align_corners=False) is added before the activation: the top-down step of the feature pyramid
+ *                (models/net.py:60-66) fused into the lateral conv's epilogue (Ho, Wo, Cout even)
  *   y            [N,Ho,Wo,y_channel_stride], written at channels y_channel_offset .. +Cout (stride 0 = Cout: dense)
  *   precision    1: TF32 operands (the library's behaviour under torch.backends.cudnn.allow_tf32, torch's default:
  *                filter rounded by the host, activations truncated by the tensor core as for tcgen05 kind::tf32);
@@ -101,7 +104,7 @@ int pmb200_upsample2x_add_nhwc(const float *x_nhwc, const float *y_nhwc, const f
  *   rows_per_warp 0 = choose (tile = 16 columns x 4*rows_per_warp rows per 4-warp CTA); 1, 2 or 4 to force
  */
 int pmb200_conv2d_filter_floats(int Cin, int Cout, int KS, int precision);
-int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bias, float *y,
+int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bias, const float *add_up2x, float *y,
                        int N, int H, int W, int Cin, int Cout, int KS, int stride, int pad, int dil,
                        int relu, int precision, int transposed2x, int y_channel_stride, int y_channel_offset,
                        int rows_per_warp, void *stream);

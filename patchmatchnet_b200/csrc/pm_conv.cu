@@ -47,6 +47,7 @@ struct ConvParams {
     const float *x;      // [N,H,W,Cin]
     const float *wf;     // fragment-ordered filter [taps][KCIN/8][NT][32][2 (TF32) or 4 (3xTF32: b0h,b1h,b0l,b1l)]
     const float *bias;   // [Cout] or null
+    const float *up;     // optional [N,Ho/2,Wo/2,Cout]: its bilinear x2 upsample is added in the epilogue
     float *y;            // [N,Ho,Wo,ycs] written at channel offset yco
     int N, H, W, Cin, Ho, Wo, Cout;
     int KS, S, pad, dil, relu;
@@ -310,6 +311,20 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
                     const int ox = ox0 + g + 8 * h;
                     if (ox >= p.Wo) continue;
                     float v0 = acc[m][j][2 * h] + bi0, v1 = acc[m][j][2 * h + 1] + bi1;
+                    if (p.up) {  // + bilinear x2 upsample of the coarser map (F.interpolate, align_corners=False); Cout even
+                        const int hc = p.Ho >> 1, wc = p.Wo >> 1;
+                        const float sy = fmaxf(0.5f * ((float)oy + 0.5f) - 0.5f, 0.0f), sx = fmaxf(0.5f * ((float)ox + 0.5f) - 0.5f, 0.0f);
+                        const int y0 = (int)sy, x0 = (int)sx;
+                        const int y1 = min(y0 + 1, hc - 1), x1 = min(x0 + 1, wc - 1);
+                        const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.0f - ly, hx = 1.0f - lx;
+                        const float *ub = p.up + (size_t)n * hc * wc * p.Cout + co;
+                        const float2 a00 = __ldg(reinterpret_cast<const float2 *>(ub + ((size_t)y0 * wc + x0) * p.Cout));
+                        const float2 a01 = __ldg(reinterpret_cast<const float2 *>(ub + ((size_t)y0 * wc + x1) * p.Cout));
+                        const float2 a10 = __ldg(reinterpret_cast<const float2 *>(ub + ((size_t)y1 * wc + x0) * p.Cout));
+                        const float2 a11 = __ldg(reinterpret_cast<const float2 *>(ub + ((size_t)y1 * wc + x1) * p.Cout));
+                        v0 += hy * (hx * a00.x + lx * a01.x) + ly * (hx * a10.x + lx * a11.x);
+                        v1 += hy * (hx * a00.y + lx * a01.y) + ly * (hx * a10.y + lx * a11.y);
+                    }
                     if (p.relu) {
                         v0 = fmaxf(v0, 0.f);
                         v1 = fmaxf(v1, 0.f);
@@ -442,8 +457,8 @@ int pmb200_conv2d_filter_floats(int Cin, int Cout, int KS, int precision) {
     return KS * KS * (round_kcin(Cin) / 8) * round_nt(Cout) * 32 * (precision == 1 ? 2 : 4);
 }
 
-int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bias, float *y, int N, int H, int W,
-                       int Cin, int Cout, int KS, int stride, int pad, int dil, int relu, int precision,
+int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bias, const float *add_up2x, float *y, int N,
+                       int H, int W, int Cin, int Cout, int KS, int stride, int pad, int dil, int relu, int precision,
                        int transposed2x, int y_channel_stride, int y_channel_offset, int rows_per_warp, void *stream) {
     if (!x || !filter_frag || !y) return conv_fail(PMB200_EINVAL, "conv2d_nhwc: null pointer");
     if (N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || Cin > 64 || Cout > 64)
@@ -465,8 +480,13 @@ int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bi
     if (((ycs | y_channel_offset) & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 7u))
         return conv_fail(PMB200_EINVAL, "conv2d_nhwc: y must be 8-byte aligned");
 
+    if (add_up2x) {
+        if ((Ho & 1) || (Wo & 1) || (Cout & 1)) return conv_fail(PMB200_EINVAL, "conv2d_nhwc: add_up2x needs even Ho, Wo and Cout");
+        if (reinterpret_cast<uintptr_t>(add_up2x) & 7u) return conv_fail(PMB200_EINVAL, "conv2d_nhwc: add_up2x must be 8-byte aligned");
+    }
     const int kcin = round_kcin(Cin), nt = round_nt(Cout);
     ConvParams p;
+    p.up = add_up2x;
     p.x = x; p.wf = filter_frag; p.bias = bias; p.y = y;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
     p.KS = KS; p.S = stride; p.pad = pad; p.dil = dil; p.relu = relu ? 1 : 0;

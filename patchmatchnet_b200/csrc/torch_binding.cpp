@@ -356,7 +356,7 @@ Tensor conv2d_nhwc(const Tensor &x, const Tensor &filter_frag, const c10::option
     const int64_t Ho = (H + 2 * pad - dil * (ks - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
     TORCH_CHECK(Ho >= 1 && Wo >= 1, "conv2d_nhwc: empty output");
     Tensor out = at::empty({N, cout, Ho, Wo}, xc.options().memory_format(at::MemoryFormat::ChannelsLast));
-    check(pmb200_conv2d_nhwc(xc.data_ptr<float>(), frag.data_ptr<float>(), b_ptr, out.data_ptr<float>(), (int)N, (int)H, (int)W,
+    check(pmb200_conv2d_nhwc(xc.data_ptr<float>(), frag.data_ptr<float>(), b_ptr, nullptr, out.data_ptr<float>(), (int)N, (int)H, (int)W,
                              (int)cin, (int)cout, (int)ks, (int)stride, (int)pad, (int)dil, relu ? 1 : 0, (int)precision, 0, 0, 0,
                              0, stream_of(xc)),
           "conv2d_nhwc");

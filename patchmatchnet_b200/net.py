@@ -178,6 +178,8 @@ class FeatureNet(nn.Module):
         self.output2 = nn.Conv2d(64, 32, 1, bias=False)
         self.output3 = nn.Conv2d(64, 16, 1, bias=False)
         self._packed = {n: _PackedConv() for n in ("output1", "inner1", "inner2", "output2", "output3")}
+        self._composed_cache = _FoldCache()
+        self.fuse_top_down = True  # eval mode on CUDA: composed 1x1 heads (see composed_heads); False = layer by layer
 
     def _plain(self, name: str, x: Tensor) -> Tensor:
         """One of the bias-free / lateral 1x1 convs: native in eval mode on CUDA, else the module itself."""
@@ -190,10 +192,50 @@ class FeatureNet(nn.Module):
             x = getattr(self, f"conv{i}")(x)
         return x
 
+    def composed_heads(self) -> Dict[str, Tensor]:
+        """The top-down path with its 1x1 convs composed.  Every op between the trunk and the three outputs is linear
+        (1x1 convs, bilinear upsampling, additions) and 1x1 convs commute with the upsampling, so with
+        W2 = output2, W3 = output3, (Wi1, bi1) = inner1, (Wi2, bi2) = inner2 (reference net.py:52-66):
+            out2 = W2 top2            = up(W2 eighth) + (W2 Wi1) quarter + W2 bi1
+            t    = W3 top2            = up(W3 eighth) + (W3 Wi1) quarter + W3 bi1
+            out1 = W3 (up(top2) + Wi2 half + bi2) = up(t) + (W3 Wi2) half + W3 bi2
+        and the 64-channel maps top2 (26 MB at 640x512 x 5 views) and top1 (105 MB, written once and read twice) never
+        exist.  Products in fp64, rounded once.  Pure tensor algebra: CPU-testable."""
+        f = lambda conv: conv.weight.detach().double().flatten(1)
+        W2, W3, Wi1, Wi2 = f(self.output2), f(self.output3), f(self.inner1), f(self.inner2)
+        bi1, bi2 = self.inner1.bias.detach().double(), self.inner2.bias.detach().double()
+        as4 = lambda m: m.float().reshape(m.shape[0], m.shape[1], 1, 1).contiguous()
+        return {"u_o": as4(W2), "u_t": as4(W3), "l2_o": as4(W2 @ Wi1), "l2_t": as4(W3 @ Wi1), "l1": as4(W3 @ Wi2),
+                "c2_o": (W2 @ bi1).float(), "c2_t": (W3 @ bi1).float(), "c1": (W3 @ bi2).float()}
+
+    def _fused_top_down(self, eighth: Tensor, quarter: Tensor, half: Tensor) -> Dict[int, Tensor]:
+        """Eval mode on CUDA: six native launches (1x1 convs, the upsample+add fused into the lateral conv's epilogue)."""
+        from . import ops
+
+        srcs = [self.output2.weight, self.output3.weight, self.inner1.weight, self.inner1.bias, self.inner2.weight, self.inner2.bias]
+        prec = ops.conv_precision()
+
+        def make():
+            h = self.composed_heads()
+            packed = {k: ops.pack_conv_filter(v, prec) for k, v in h.items() if v.dim() == 4}
+            packed.update({k: v.contiguous() for k, v in h.items() if v.dim() == 1})
+            return packed
+
+        w = self._composed_cache.get(srcs, make, key=prec)
+        out: Dict[int, Tensor] = {3: self._plain("output1", eighth)}
+        u_o = ops.conv2d_nhwc(eighth, w["u_o"], None, 32, 1)
+        u_t = ops.conv2d_nhwc(eighth, w["u_t"], None, 16, 1)
+        out[2] = ops.conv2d_nhwc(quarter, w["l2_o"], w["c2_o"], 32, 1, add_up2x=u_o)
+        t = ops.conv2d_nhwc(quarter, w["l2_t"], w["c2_t"], 16, 1, add_up2x=u_t)
+        out[1] = ops.conv2d_nhwc(half, w["l1"], w["c1"], 16, 1, add_up2x=t)
+        return out
+
     def forward(self, x: Tensor) -> Dict[int, Tensor]:
         half = self._trunk(self._trunk(x, 0, 1), 2, 4)
         quarter = self._trunk(half, 5, 7)
         eighth = self._trunk(quarter, 8, 10)
+        if not self.training and _native_convs(x) and self.fuse_top_down:
+            return self._fused_top_down(eighth, quarter, half)
         out: Dict[int, Tensor] = {3: self._plain("output1", eighth)}
         top = self._top_down(eighth, "inner1", quarter)
         out[2] = self._plain("output2", top)

@@ -215,16 +215,24 @@ def conv_precision() -> int:
 
 def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: int, ks: int, stride: int = 1, pad: int = 0,
                 dil: int = 1, relu: bool = False, transposed2x: bool = False, out: Optional[Tensor] = None,
-                out_channel_offset: int = 0, precision: Optional[int] = None, rows_per_warp: int = 0) -> Tensor:
+                out_channel_offset: int = 0, precision: Optional[int] = None, rows_per_warp: int = 0,
+                add_up2x: Optional[Tensor] = None) -> Tensor:
     """Channels-last convolution on the tensor cores (csrc/pm_conv.cu).  `x` is a logical-NCHW CUDA tensor in
     channels-last memory (made so if not); returns a logical-NCHW channels-last tensor [N,cout,Ho,Wo], or writes the
-    channels out_channel_offset..+cout of `out` (a wider channels-last tensor: concat fusion) and returns `out`."""
+    channels out_channel_offset..+cout of `out` (a wider channels-last tensor: concat fusion) and returns `out`.
+    `add_up2x`: a coarser channels-last map [N,cout,Ho/2,Wo/2] whose bilinear x2 upsample is added in the epilogue."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
         raise RuntimeError(f"conv2d_nhwc: x must be a 4-D CUDA float32 tensor (got {x.dtype} {tuple(x.shape)} on {x.device}); no CPU fallback")
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     N, cin, H, W = x.shape
     prec = conv_precision() if precision is None else precision
+    up_ptr = None
+    if add_up2x is not None:
+        if (not add_up2x.is_cuda or add_up2x.dtype != torch.float32 or add_up2x.dim() != 4
+                or not add_up2x.is_contiguous(memory_format=torch.channels_last)):
+            raise RuntimeError("conv2d_nhwc: add_up2x must be a channels-last CUDA float32 tensor")
+        up_ptr = add_up2x.data_ptr()
     want = _native.lib().pmb200_conv2d_filter_floats(cin, cout, ks, prec)
     if want <= 0 or filter_frag.numel() != want or filter_frag.dtype != torch.float32 or filter_frag.device != x.device:
         raise RuntimeError(f"conv2d_nhwc: filter must be {want} float32 values on {x.device} in fragment order for precision {prec} "
@@ -232,6 +240,8 @@ def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: in
     Hv, Wv = (2 * H, 2 * W) if transposed2x else (H, W)
     Ho = (Hv + 2 * pad - dil * (ks - 1) - 1) // stride + 1
     Wo = (Wv + 2 * pad - dil * (ks - 1) - 1) // stride + 1
+    if add_up2x is not None and tuple(add_up2x.shape) != (N, cout, Ho // 2, Wo // 2):
+        raise RuntimeError(f"conv2d_nhwc: add_up2x must be [N,cout,Ho/2,Wo/2] = {(N, cout, Ho // 2, Wo // 2)}, got {tuple(add_up2x.shape)}")
     if out is None:
         out = torch.empty((N, cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
         ycs, yco = cout, 0
@@ -248,7 +258,7 @@ def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: in
         b_ptr = bias.data_ptr()
     with torch.cuda.device(x.device):
         rc = _native.lib().pmb200_conv2d_nhwc(
-            x.data_ptr(), filter_frag.data_ptr(), b_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride, pad, dil,
+            x.data_ptr(), filter_frag.data_ptr(), b_ptr, up_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride, pad, dil,
             1 if relu else 0, prec, 1 if transposed2x else 0, ycs, yco, rows_per_warp, _stream(x),
         )
     _native.check(rc, "conv2d_nhwc")

@@ -110,3 +110,30 @@ def test_zero_copy_view_detection_needs_one_storage():
     assert ops._is_packed_nhwc([cl[0:2], cl[2:4], cl[4:6]])
     assert not ops._is_packed_nhwc([cl[0:2].clone(memory_format=torch.channels_last), cl[2:4], cl[4:6]])
     assert not ops._is_packed_nhwc(views)
+
+
+def test_composed_feature_heads_equal_the_layerwise_top_down():
+    """FeatureNet's eval fast path composes the linear top-down ops (reference net.py:52-66); the composed weights
+    must reproduce the layer-by-layer outputs (pure tensor algebra, checked here in fp64 on the CPU)."""
+    import torch
+    import torch.nn.functional as F
+
+    from patchmatchnet_b200.net import FeatureNet
+
+    torch.manual_seed(0)
+    net = FeatureNet().double().eval()
+    x = torch.randn(2, 3, 32, 48, dtype=torch.float64)
+    with torch.no_grad():
+        want = net(x)
+        half = net._trunk(net._trunk(x, 0, 1), 2, 4)
+        quarter = net._trunk(half, 5, 7)
+        eighth = net._trunk(quarter, 8, 10)
+        h = {k: v.double() for k, v in net.composed_heads().items()}
+        up = lambda t: F.interpolate(t, scale_factor=2.0, mode="bilinear", align_corners=False)
+        out2 = up(F.conv2d(eighth, h["u_o"])) + F.conv2d(quarter, h["l2_o"], h["c2_o"])
+        t = up(F.conv2d(eighth, h["u_t"])) + F.conv2d(quarter, h["l2_t"], h["c2_t"])
+        out1 = up(t) + F.conv2d(half, h["l1"], h["c1"])
+    # composed weights are rounded to fp32 once: agreement to fp32 resolution of the output scale
+    for got, ref in ((out2, want[2]), (out1, want[1])):
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max() / ref.abs().max()) < 5e-6

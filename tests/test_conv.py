@@ -119,12 +119,13 @@ def test_conv_entry_rejects_bad_arguments_without_gpu():
     lib = _native.lib()
     one = ctypes.c_void_p(64)
     ok_tail = (1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 1, 0, 0, 0, 0, None)
-    assert lib.pmb200_conv2d_nhwc(None, one, None, one, *ok_tail) == -1
+    assert lib.pmb200_conv2d_nhwc(None, one, None, None, one, *ok_tail) == -1
     assert b"null pointer" in lib.pmb200_last_error()
-    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 65, 8, 3, 1, 1, 1, 0, 1, 0, 0, 0, 0, None) == -1  # Cin > 64
-    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 3, 1, 1, 0, 1, 0, 0, 0, 0, None) == -1   # stride 3
-    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 2, 0, 0, 0, 0, None) == -1   # precision 2
-    assert lib.pmb200_conv2d_nhwc(one, one, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 1, 0, 12, 8, 0, None) == -1  # slice outside
+    assert lib.pmb200_conv2d_nhwc(one, one, None, None, one, 1, 8, 8, 65, 8, 3, 1, 1, 1, 0, 1, 0, 0, 0, 0, None) == -1  # Cin > 64
+    assert lib.pmb200_conv2d_nhwc(one, one, None, None, one, 1, 8, 8, 8, 8, 3, 3, 1, 1, 0, 1, 0, 0, 0, 0, None) == -1   # stride 3
+    assert lib.pmb200_conv2d_nhwc(one, one, None, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 2, 0, 0, 0, 0, None) == -1   # precision 2
+    assert lib.pmb200_conv2d_nhwc(one, one, None, None, one, 1, 8, 8, 8, 8, 3, 1, 1, 1, 0, 1, 0, 12, 8, 0, None) == -1  # slice outside
+    assert lib.pmb200_conv2d_nhwc(one, one, None, one, one, 1, 7, 8, 8, 8, 1, 1, 0, 1, 0, 1, 0, 0, 0, 0, None) == -1  # add_up2x: odd Ho
     assert lib.pmb200_conv2d_filter_floats(64, 64, 3, 1) == 9 * 8 * 8 * 64
     assert lib.pmb200_conv2d_filter_floats(3, 18, 3, 3) == 9 * 1 * 3 * 128
     assert lib.pmb200_conv2d_filter_floats(0, 8, 3, 1) == -1
@@ -239,3 +240,20 @@ def test_gpu_net_native_convs_match_library_convs(fp32_library, golden_weights):
         ops.NATIVE_CONVS = old
     rel = float((outs[True][0] - outs[False][0]).abs().sum() / outs[False][0].abs().sum())
     assert rel <= 1e-4, rel
+
+
+@pytest.mark.gpu
+def test_gpu_conv_with_fused_upsample_add(fp32_library):
+    """Lateral 1x1 conv + bias + bilinear x2 upsample of the coarser map in one launch (reference net.py:60-66)."""
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(9)
+    for cin, cout, (h, w) in ((32, 32, (19, 27)), (16, 16, (32, 40)), (32, 16, (8, 8))):
+        fine = torch.randn(2, cin, 2 * h, 2 * w, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        coarse = torch.randn(2, cout, h, w, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        wt = (torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).to(dev)
+        b = torch.randn(cout, generator=g).to(dev)
+        want = F.interpolate(coarse, scale_factor=2.0, mode="bilinear", align_corners=False) + F.conv2d(fine, wt, b)
+        got = ops.conv2d_nhwc(fine, ops.pack_conv_filter(wt, 3), b, cout, 1, precision=3, add_up2x=coarse)
+        assert _scaled_err(got, want) <= 2e-5
+    with pytest.raises(RuntimeError, match="add_up2x"):
+        ops.conv2d_nhwc(fine, ops.pack_conv_filter(wt, 3), b, cout, 1, precision=3, add_up2x=coarse[:, :, :-1])
