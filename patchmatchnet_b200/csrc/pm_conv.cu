@@ -62,6 +62,7 @@ struct ConvParams {
     int cpp, cpp_shift;  // cp.async chunks per pixel (Cin/4 16-byte chunks, or Cin 4-byte chunks), log2 or -1
     int row_chunks, tile_chunks;        // chunks per region row / per halo tile
     unsigned magic_row, magic_cpp;      // floor(2^32 / d) + 1: idx / d == umulhi(idx, magic) for idx * d < 2^32
+    int step_r[2], step_c[2];           // (128 or 256) / row_chunks and % row_chunks: per-iteration advance of a thread
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float f) {
@@ -101,10 +102,11 @@ __device__ __forceinline__ void stage_tile(const ConvParams &p, int tile, float 
     const int ix0 = tx * 16 * p.S - p.pad, iy0 = ty * rows_per_tile * p.S - p.pad;
     const unsigned Hv = STUFF ? 2 * p.H : p.H, Wv = STUFF ? 2 * p.W : p.W;
     const float *img = p.x + (size_t)n * p.H * p.W * p.Cin;
+    // this thread's first chunk, then THREADS chunks further each iteration: (row, chunk-in-row) advance by a constant
+    int r = (int)__umulhi(threadIdx.x, p.magic_row);
+    int c = (int)threadIdx.x - r * p.row_chunks;
 #pragma unroll 2
     for (int idx = threadIdx.x; idx < p.tile_chunks; idx += THREADS) {
-        const int r = (int)__umulhi((unsigned)idx, p.magic_row);
-        const int c = idx - r * p.row_chunks;
         const int rx = p.cpp_shift >= 0 ? (c >> p.cpp_shift) : (int)__umulhi((unsigned)c, p.magic_cpp);
         const int v = c - rx * p.cpp;
         int iy = iy0 + r, ix = ix0 + rx;
@@ -118,6 +120,12 @@ __device__ __forceinline__ void stage_tile(const ConvParams &p, int tile, float 
         const int soff = (r * p.rw + rx) * p.ps;
         if (VEC) cp_async<16>(buf + soff + v * 4, img + goff + v * 4, inside);  // ps % 4 == 0: 16-byte aligned
         else cp_async<4>(buf + soff + v, img + goff + v, inside);
+        r += p.step_r[THREADS / 256];
+        c += p.step_c[THREADS / 256];
+        if (c >= p.row_chunks) {
+            c -= p.row_chunks;
+            ++r;
+        }
     }
 }
 
@@ -144,6 +152,9 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
     constexpr int KK = KCIN / 8;
     constexpr int ROWS = 4 * MT;
     constexpr int THREADS = 128 * NSPLIT;
+    // WREG kernels serve 3x3 / stride 1 / dilation 1 only: the halo row is 18 pixels and the pixel stride is known at
+    // compile time, so every A-fragment address is the lane's base plus an immediate offset
+    constexpr int kPsW = KCIN == 8 ? 8 : 24, kRwW = 18;
     const int warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int nbase = (threadIdx.x >> 7) * NT;  // first output-channel tile of this warp group
 
@@ -176,6 +187,14 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
         }
     }
 
+    // this lane's two output channels of every n-tile and their bias, fixed for the lifetime of the CTA
+    float bi0[NT], bi1[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int co = (nbase + j) * 8 + 2 * t;
+        bi0[j] = (p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+        bi1[j] = (p.bias && co + 1 < p.Cout) ? __ldg(p.bias + co + 1) : 0.f;
+    }
     const int arow = g * p.S * p.ps + 2 * t;  // lane part of the A-fragment address: channels 2t, 2t+1 of pixel g
     const int astep8 = 8 * p.S * p.ps;    // 8 output pixels further right
     const bool vec2 = ((p.ycs | p.yco) & 1) == 0;
@@ -207,9 +226,9 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
         auto mma_step = [&](const float *ap0, const uint32_t (&bh)[NT][2], const uint32_t (&bl)[NT][2]) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-                const float *ap = ap0 + m * p.S * p.rw * p.ps;
+                const float *ap = ap0 + (WREG ? m * kRwW * kPsW : m * p.S * p.rw * p.ps);
                 const float2 lo = *reinterpret_cast<const float2 *>(ap);           // pixel g:   k slots t, t+4
-                const float2 hi = *reinterpret_cast<const float2 *>(ap + astep8);  // pixel g+8
+                const float2 hi = *reinterpret_cast<const float2 *>(ap + (WREG ? 8 * kPsW : astep8));  // pixel g+8
                 uint32_t ah[4];
                 if constexpr (PREC == 1) {  // the tensor core ignores the low 13 mantissa bits
                     ah[0] = __float_as_uint(lo.x); ah[1] = __float_as_uint(hi.x);
@@ -233,7 +252,8 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
             }
         };
 
-        const float *abase = cur + (warp * MT * p.S) * p.rw * p.ps + arow;
+        const float *abase = WREG ? cur + (warp * MT) * (kRwW * kPsW) + g * kPsW + 2 * t
+                                  : cur + (warp * MT * p.S) * p.rw * p.ps + arow;
         if constexpr (WREG) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
                             bh[j][0] = wh[q][0]; bh[j][1] = wh[q][1];
                             bl[j][0] = wlo[(PREC == 3) ? q : 0][0]; bl[j][1] = wlo[(PREC == 3) ? q : 0][1];
                         }
-                        mma_step(abase + (ky * p.dil * p.rw + kx * p.dil) * p.ps + kk * 8, bh, bl);
+                        mma_step(abase + (ky * kRwW + kx) * kPsW + kk * 8, bh, bl);
                     }
         } else {
             // filter fragments streamed through L1, one (tap, k-slice) ahead of the MMAs that use them
@@ -295,22 +315,23 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
         const int n = tile / per_img, tt = tile - n * per_img;
         const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
         const int ox0 = tx * 16, oy0 = ty * ROWS;
+        const int oyw = oy0 + warp * MT;
+        float *const dst0 = p.y + (((size_t)n * p.Ho + oyw) * p.Wo + ox0 + g) * p.ycs + p.yco + nbase * 8 + 2 * t;
+        const int row_step = p.Wo * p.ycs, half_step = 8 * p.ycs;
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-            const int oy = oy0 + warp * MT + m;
+            const int oy = oyw + m;
             if (oy >= p.Ho) continue;
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int co = (nbase + j) * 8 + 2 * t;
                 if (co >= p.Cout) continue;
                 const bool pair = co + 1 < p.Cout;
-                const float bi0 = p.bias ? __ldg(p.bias + co) : 0.f;
-                const float bi1 = (p.bias && pair) ? __ldg(p.bias + co + 1) : 0.f;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int ox = ox0 + g + 8 * h;
                     if (ox >= p.Wo) continue;
-                    float v0 = acc[m][j][2 * h] + bi0, v1 = acc[m][j][2 * h + 1] + bi1;
+                    float v0 = acc[m][j][2 * h] + bi0[j], v1 = acc[m][j][2 * h + 1] + bi1[j];
                     if (p.up) {  // + bilinear x2 upsample of the coarser map (F.interpolate, align_corners=False); Cout even
                         const int hc = p.Ho >> 1, wc = p.Wo >> 1;
                         const float sy = fmaxf(0.5f * ((float)oy + 0.5f) - 0.5f, 0.0f), sx = fmaxf(0.5f * ((float)ox + 0.5f) - 0.5f, 0.0f);
@@ -329,7 +350,7 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvP
                         v0 = fmaxf(v0, 0.f);
                         v1 = fmaxf(v1, 0.f);
                     }
-                    float *dst = p.y + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ycs + p.yco + co;
+                    float *dst = dst0 + (m * row_step + h * half_step + j * 8);
                     if (pair && vec2) {
                         *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
                     } else {
@@ -408,7 +429,7 @@ template <int KCIN, int NT, int MT, int NSPLIT>
 int launch_prec(const ConvParams &p, const LaunchPlan &plan, int prec, cudaStream_t st) {
     constexpr bool kCanHold = NSPLIT == 1 && (KCIN / 8) * NT <= 2;  // <= 18 fragments of a 3x3 filter in registers
     if constexpr (kCanHold) {
-        if (p.KS == 3)
+        if (p.KS == 3 && p.S == 1 && p.dil == 1)  // the register-resident form hard-codes the 18-pixel halo row
             return prec == 1 ? launch_conv<KCIN, NT, MT, 1, true, 1>(p, plan, st) : launch_conv<KCIN, NT, MT, 3, true, 1>(p, plan, st);
     }
     return prec == 1 ? launch_conv<KCIN, NT, MT, 1, false, NSPLIT>(p, plan, st) : launch_conv<KCIN, NT, MT, 3, false, NSPLIT>(p, plan, st);
@@ -558,6 +579,10 @@ int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bi
     p.tile_chunks = p.rh * p.row_chunks;
     p.magic_row = (unsigned)((1ull << 32) / (unsigned)p.row_chunks + 1ull);
     p.magic_cpp = (unsigned)((1ull << 32) / (unsigned)p.cpp + 1ull);
+    for (int i = 0; i < 2; ++i) {
+        p.step_r[i] = (128 << i) / p.row_chunks;
+        p.step_c[i] = (128 << i) % p.row_chunks;
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (kcin) {
         case 8: return launch_shape<8>(p, plan, ntw, nsplit, mt, precision, st);

@@ -1892,16 +1892,25 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
     p.B = B; p.D = D; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.is_inverse = is_inverse;
     p.interval_scale = interval_scale;
     const int HW = H * W;
-    // small maps: fewer pixels per block and more hypothesis lanes, so the grid still covers the SMs
-    int TP = 32, DY = D < 8 ? D : 8;
+    // Block shape from the B200 sweep (profiles/r1_run20_kbench_eval.json): large maps want 32 pixels x few hypothesis
+    // lanes (each thread then walks D/DY hypotheses with the footprints it already decoded), small maps 16 pixels x 16
+    // lanes so that the grid still covers the SMs.
+    int TP = 32, DY = D <= 16 ? (D < 4 ? D : 4) : 8;
     if ((long long)((HW + 31) / 32) * B < 2 * 148) {
-        TP = 8;
-        DY = D < 32 ? D : 32;
+        TP = 16;
+        DY = D < 16 ? D : 16;
     }
     auto smem_for = [&](int tp) { return (size_t)K * tp * (sizeof(float4) + sizeof(int)) + 2 * (size_t)D * tp * sizeof(float); };
     if (smem_for(TP) > 48 * 1024) {  // many hypotheses: fewer pixels per block keeps the tile under the default 48 KB
         TP = 8;
         DY = D < 32 ? D : 32;
+    }
+    {   // measurement aid (tools/kbench.py): PMB200_KB_TP / PMB200_KB_DY override the block shape
+        const int etp = env_int("PMB200_KB_TP", 0), edy = env_int("PMB200_KB_DY", 0);
+        if (etp > 0 && edy > 0 && etp * edy <= 256 && smem_for(etp) <= 48 * 1024) {
+            TP = etp;
+            DY = edy < D ? edy : D;
+        }
     }
     const size_t smem = smem_for(TP);
     dim3 grid((HW + TP - 1) / TP, B);

@@ -83,7 +83,13 @@ for (n, a, k) in calls:
     elif n == "offset_corr_weight":
         desc += f" C{a[0].shape[3]} {a[0].shape[1]}x{a[0].shape[2]}"
     row = {"call": desc, "default_us": timeit(lambda: origs[n](*a, **k))}
-    if n == "warp_corr_score":
+    if n == "adaptive_eval" and os.environ.get("KB_SWEEP_EVAL", "1") == "1":
+        for tp, dy in ((32, 8), (32, 4), (16, 16), (16, 8), (8, 32), (8, 16), (64, 4), (32, 2)):
+            os.environ["PMB200_KB_TP"], os.environ["PMB200_KB_DY"] = str(tp), str(dy)
+            row[f"TP={tp},DY={dy}"] = timeit(lambda: origs[n](*a, **k))
+            os.environ.pop("PMB200_KB_TP", None)
+            os.environ.pop("PMB200_KB_DY", None)
+    if n == "warp_corr_score" and os.environ.get("KB_SWEEP_KA", "1") == "1":
         for v in variants:
             for kk, vv in v.items():
                 os.environ[kk] = vv
