@@ -311,9 +311,10 @@ def time_warp_corr_in_step(net, dev_inputs, peak_gbs, flush, steps=10, warmup=3)
             for it in range(warmup + steps):
                 record.clear()
                 flush()
-                # eager Python enqueues slower than the GPU drains: park the GPU (~3 ms) so the whole step is
-                # queued before it starts, otherwise an event pair would also time the host's enqueue latency
-                torch.cuda._sleep(6_000_000)
+                # eager Python enqueues slower than the GPU drains (an eager forward is ~90 launches through Python, a few
+                # ms of host time, for < 1.5 ms of device time): park the GPU (~12 ms) so the whole step is queued before
+                # it starts, otherwise an event pair would also time the host's enqueue latency
+                torch.cuda._sleep(24_000_000)
                 torch.manual_seed(0)
                 net(*dev_inputs())
                 torch.cuda.synchronize()
