@@ -109,6 +109,26 @@ int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bi
                        int relu, int precision, int transposed2x, int y_channel_stride, int y_channel_offset,
                        int rows_per_warp, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Geometric-consistency filtering of one reference depth map against V source depth maps, one launch
+ * (SURVEY.md 8f row f4).  Replaces reproject_with_depth (eval.py:86-146), check_geometric_consistency (eval.py:149-190)
+ * and the per-reference-view accumulation of filter_depth (eval.py:220, :226-256): numpy + cv2.remap on one CPU thread.
+ *   ref_depth [H,W], confidence [H,W], src_depths [V,Hs,Ws]   float32
+ *   cams [V,60] float64 (device): per source view, row-major, composed exactly as the reference composes them in float32
+ *       and then widened:  inv(K_ref) (9) | (E_src . inv(E_ref))[:3,:4] (12) | K_src (9) | inv(K_src) (9) |
+ *       (E_ref . inv(E_src))[:3,:4] (12) | K_ref (9)        (eval.py:116-139)
+ *   geo_mask_sum_out [H,W] int32: source views consistent with the pixel (dist < geo_pixel_thres and relative depth
+ *       difference < geo_depth_thres, eval.py:180-187); photo_mask_out / final_mask_out [H,W] uint8 (0/1):
+ *       confidence > photo_thres, and that AND geo_mask_sum >= geo_mask_thres (eval.py:220, :254-255);
+ *   depth_avg_out [H,W] float64: (sum of the consistent reprojected depths + ref_depth) / (geo_mask_sum + 1) (eval.py:252).
+ * The source-depth sample reproduces cv2.remap(INTER_LINEAR, constant border 0): coordinates rounded to 1/32 pixel,
+ * float32 weights, no fused multiply-add. */
+int pmb200_geometric_filter(const float *ref_depth, const float *confidence, const float *src_depths,
+                            const double *cams, int V, int H, int W, int Hs, int Ws, double geo_pixel_thres,
+                            float geo_depth_thres, float photo_thres, int geo_mask_thres, int *geo_mask_sum_out,
+                            unsigned char *photo_mask_out, unsigned char *final_mask_out, double *depth_avg_out,
+                            void *stream);
+
 /* Caller-side helper (models/net.py:289-299): photometric confidence = probability mass of the four
  * hypotheses around the regressed hypothesis index, nearest-resized to [H_out, W_out].
  *   prob [B,D,h,w] (the last PatchMatch stage's probabilities)   confidence_out [B,H_out,W_out] */

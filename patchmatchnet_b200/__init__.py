@@ -14,7 +14,9 @@ from .patchmatch import PatchMatch  # noqa: F401
 
 # torch.ops.pmb200.* (TorchScript-facing registration of the same C ABI): registered on import when the shim is built,
 # so that `torch.jit.script(model)` / `torch.jit.load(path)` work after a plain `import patchmatchnet_b200`.
-if _os.path.exists(_native.TORCH_LIB_PATH):
+# Not when libpmb200.so is older than its sources: loading the shim would map the stale library into the process and the
+# rebuild that build() is about to do could no longer be loaded under the same path.
+if _os.path.exists(_native.TORCH_LIB_PATH) and not _native.needs_rebuild():
     _native.load_torch_ops()
 
 __all__ = ["PatchMatch", "PatchmatchNet", "load_reference_state", "patchmatchnet_loss"]

@@ -521,3 +521,50 @@ def adaptive_eval(
         )
     _native.check(rc, "adaptive_eval")
     return depth, prob
+
+
+def compose_filter_cameras(ref_K, ref_E, src_Ks, src_Es) -> Tensor:
+    """[V,60] float64 (CPU): the camera matrices `pmb200_geometric_filter` takes, composed the way the reference composes
+    them -- numpy float32 inverses and products (eval.py:116-139) -- and then widened to float64 without rounding."""
+    import numpy as np
+
+    f32 = lambda m: np.asarray(m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else m, dtype=np.float32)
+    Kr, Er = f32(ref_K), f32(ref_E)
+    rows = []
+    for K, E in zip(src_Ks, src_Es):
+        Ks, Es = f32(K), f32(E)
+        t1 = np.matmul(Es, np.linalg.inv(Er))
+        t2 = np.matmul(Er, np.linalg.inv(Es))
+        rows.append(np.concatenate([np.linalg.inv(Kr).ravel(), t1[:3, :4].ravel(), Ks.ravel(), np.linalg.inv(Ks).ravel(),
+                                    t2[:3, :4].ravel(), Kr.ravel()]).astype(np.float64))
+    return torch.from_numpy(np.stack(rows))
+
+
+def geometric_filter(ref_depth: Tensor, confidence: Tensor, src_depths: Tensor, cams: Tensor, geo_pixel_thres: float = 1.0,
+                     geo_depth_thres: float = 0.01, photo_thres: float = 0.8, geo_mask_thres: int = 3):
+    """Geometric-consistency filtering of one reference view against V source views in one launch (reference
+    eval.py:86-190, :220-256).  ref_depth / confidence [H,W], src_depths [V,Hs,Ws] CUDA float32; cams [V,60] float64 from
+    compose_filter_cameras (moved to the device here).  -> (photo_mask bool [H,W], geo_mask_sum int32 [H,W],
+    final_mask bool [H,W], depth_averaged float64 [H,W])."""
+    ref = _require(ref_depth, "ref_depth", 2)
+    conf = _require(confidence, "confidence", 2)
+    src = _require(src_depths, "src_depths", 3)
+    H, W = ref.shape
+    V, Hs, Ws = src.shape
+    if conf.shape != (H, W):
+        raise RuntimeError("geometric_filter: confidence must match ref_depth")
+    if cams.shape != (V, 60) or cams.dtype != torch.float64:
+        raise RuntimeError("geometric_filter: cams must be a [V,60] float64 tensor (compose_filter_cameras)")
+    cams = cams.to(ref.device).contiguous()
+    mask_sum = torch.empty((H, W), dtype=torch.int32, device=ref.device)
+    photo = torch.empty((H, W), dtype=torch.uint8, device=ref.device)
+    final = torch.empty((H, W), dtype=torch.uint8, device=ref.device)
+    avg = torch.empty((H, W), dtype=torch.float64, device=ref.device)
+    with torch.cuda.device(ref.device):
+        rc = _native.lib().pmb200_geometric_filter(
+            ref.data_ptr(), conf.data_ptr(), src.data_ptr(), cams.data_ptr(), V, H, W, Hs, Ws, float(geo_pixel_thres),
+            float(geo_depth_thres), float(photo_thres), int(geo_mask_thres), mask_sum.data_ptr(), photo.data_ptr(),
+            final.data_ptr(), avg.data_ptr(), _stream(ref),
+        )
+    _native.check(rc, "geometric_filter")
+    return photo.bool(), mask_sum, final.bool(), avg

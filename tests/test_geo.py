@@ -1,0 +1,141 @@
+"""Geometric-consistency filtering (reference eval.py:86-190, :220-256).
+
+CPU: the oracle (oracle/geo_oracle.py) is pinned bit for bit against (a) cv2.remap for its restatement of the bilinear
+sampler, (b) the reference's own source text executed in the build container, (c) the committed reference-generated fixture.
+GPU (-m gpu): the one-launch kernel, through the C ABI, against the oracle and the fixture.  The masks are thresholded
+quantities: a pixel whose distance / relative depth difference lies within rounding of its threshold may legitimately flip
+(the kernel's float64 dot products are fused multiply-adds, BLAS's are not), so the bound is a fraction of pixels:
+<= 1e-4 of the pixels per mask, and the averaged depth must agree to 1e-6 relative wherever the masks agree."""
+import os
+from typing import Tuple
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geo_oracle as go
+from tests import geo_cases
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geo_case.npz")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    z = np.load(GOLDEN)
+    return {k: z[k] for k in z.files}
+
+
+def test_remap_restatement_is_bit_exact_against_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    img = rng.uniform(400, 900, size=(61, 83)).astype(np.float32)
+    H, W = img.shape
+    mx = rng.uniform(-5, W + 5, size=(H, W)).astype(np.float32)
+    my = rng.uniform(-5, H + 5, size=(H, W)).astype(np.float32)
+    mx[0, :8] = [np.nan, np.inf, -np.inf, 1e9, -1e9, 40000.3, -40000.7, 0.015625]
+    my[0, :8] = [1, 2, 3, 4, 5, 6, 7, 0.984375]
+    mx[1, :4] = [-1.0, -0.5, W - 1, W - 0.5]  # footprints straddling the border
+    my[1, :4] = [0.25, H - 1, H - 0.5, -0.99]
+    want = cv2.remap(img, mx, my, interpolation=cv2.INTER_LINEAR)
+    assert np.array_equal(want, go.remap_linear(img, mx, my))
+
+
+def test_oracle_is_bit_identical_to_the_reference_source():
+    cv2 = pytest.importorskip("cv2")
+    path = "/root/reference/eval.py"
+    if not os.path.exists(path):
+        pytest.skip("/root/reference not present (GPU box): the oracle is pinned by the golden fixture instead")
+    src = open(path).read()
+    ns = {"np": np, "cv2": cv2, "Tuple": Tuple}
+    exec(src[src.index("def reproject_with_depth("):src.index("def filter_depth(")], ns)  # eval.py:86-190, unmodified
+    sc = geo_cases.make_scene(seed=3, H=72, W=100, n_src=3)
+    for d, k, e in zip(sc["src_depths"], sc["src_Ks"], sc["src_Es"]):
+        rm, rd = ns["check_geometric_consistency"](sc["ref_depth"], sc["ref_K"], sc["ref_E"], d, k, e, 1.0, 0.01)
+        om, od = go.check_geometric_consistency(sc["ref_depth"], sc["ref_K"], sc["ref_E"], d, k, e, 1.0, 0.01)
+        assert np.array_equal(rm, om) and np.array_equal(rd, od)
+        assert 0.05 < rm.mean() < 0.95, "the scene must exercise both outcomes"
+        r3 = ns["reproject_with_depth"](sc["ref_depth"], sc["ref_K"], sc["ref_E"], d, k, e)
+        o3 = go.reproject_with_depth(sc["ref_depth"], sc["ref_K"], sc["ref_E"], d, k, e)
+        assert all(np.array_equal(a, b) for a, b in zip(r3, o3))
+
+
+def test_oracle_reproduces_the_reference_fixture(golden):
+    sc = geo_cases.make_scene(seed=0)
+    assert np.array_equal(sc["ref_depth"], golden["ref_depth"]) and np.array_equal(np.stack(sc["src_depths"]), golden["src_depths"])
+    photo, msum, final, avg = go.fuse_reference_view(
+        golden["ref_depth"], golden["ref_K"], golden["ref_E"], list(golden["src_depths"]), list(golden["src_Ks"]),
+        list(golden["src_Es"]), golden["confidence"])
+    assert np.array_equal(photo, golden["photo_mask"]) and np.array_equal(msum, golden["geo_mask_sum"])
+    assert np.array_equal(final, golden["final_mask"]) and np.array_equal(avg, golden["depth_est_averaged"])
+    assert avg.dtype == np.float64 and set(np.unique(msum)) == {0, 1, 2, 3, 4}
+
+
+def test_camera_composition_matches_numpy_float32(golden):
+    from patchmatchnet_b200 import ops
+
+    cams = ops.compose_filter_cameras(golden["ref_K"], golden["ref_E"], list(golden["src_Ks"]), list(golden["src_Es"]))
+    assert cams.shape == (4, 60) and cams.dtype == torch.float64
+    t1 = np.matmul(golden["src_Es"][2], np.linalg.inv(golden["ref_E"]))
+    assert np.array_equal(cams[2, 9:21].numpy().reshape(3, 4), t1[:3].astype(np.float64))
+    assert np.array_equal(cams[2, :9].numpy().reshape(3, 3), np.linalg.inv(golden["ref_K"]).astype(np.float64))
+
+
+def test_geometric_filter_rejects_bad_arguments_without_gpu():
+    from patchmatchnet_b200 import _native, ops
+
+    lib = _native.lib()
+    assert lib.pmb200_geometric_filter(None, None, None, None, 1, 4, 4, 4, 4, 1.0, 0.01, 0.8, 3, None, None, None, None, None) == -1
+    assert b"null pointer" in lib.pmb200_last_error()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.geometric_filter(torch.zeros(4, 4), torch.zeros(4, 4), torch.zeros(1, 4, 4), torch.zeros(1, 60, dtype=torch.float64))
+
+
+def _run_gpu(sc):
+    from patchmatchnet_b200 import ops
+
+    dev = "cuda:0"
+    cams = ops.compose_filter_cameras(sc["ref_K"], sc["ref_E"], list(sc["src_Ks"]), list(sc["src_Es"]))
+    out = ops.geometric_filter(torch.from_numpy(sc["ref_depth"]).to(dev), torch.from_numpy(sc["confidence"]).to(dev),
+                               torch.from_numpy(np.stack(list(sc["src_depths"]))).to(dev), cams)
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in out]
+
+
+def _compare(got, want):
+    photo, msum, final, avg = got
+    wphoto, wsum, wfinal, wavg = want
+    n = wsum.size
+    assert np.array_equal(photo, wphoto)
+    flipped = msum != wsum
+    assert flipped.sum() <= max(1, int(1e-4 * n)), f"{flipped.sum()} of {n} pixels disagree on the geometric mask count"
+    assert (final != wfinal).sum() <= max(1, int(1e-4 * n))
+    same = ~flipped
+    rel = np.abs(avg[same] - wavg[same]) / np.abs(wavg[same])
+    assert avg.dtype == np.float64 and rel.max() <= 1e-6, rel.max()
+
+
+@pytest.mark.gpu
+def test_gpu_filter_matches_the_reference_fixture(golden):
+    sc = dict(ref_depth=golden["ref_depth"], ref_K=golden["ref_K"], ref_E=golden["ref_E"], src_depths=golden["src_depths"],
+              src_Ks=golden["src_Ks"], src_Es=golden["src_Es"], confidence=golden["confidence"])
+    _compare(_run_gpu(sc), (golden["photo_mask"], golden["geo_mask_sum"], golden["final_mask"], golden["depth_est_averaged"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,n_src,seed", [(72, 100, 3, 3), (33, 47, 1, 5), (512, 640, 4, 7)])
+def test_gpu_filter_matches_the_oracle(H, W, n_src, seed):
+    sc = geo_cases.make_scene(seed=seed, H=H, W=W, n_src=n_src)
+    if H * W < 8000:  # degenerate inputs: zero depth, NaN confidence
+        sc["ref_depth"][0, :5] = 0.0
+        sc["confidence"][1, :3] = np.nan
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = go.fuse_reference_view(sc["ref_depth"], sc["ref_K"], sc["ref_E"], sc["src_depths"], sc["src_Ks"], sc["src_Es"], sc["confidence"])
+    got = _run_gpu(sc)
+    finite = np.isfinite(want[3])
+    got[3] = np.where(finite, got[3], 0.0)
+    want = (want[0], want[1], want[2], np.where(finite, want[3], 0.0) + (~finite) * 0.0)
+    # pixels with a zero / non-finite reference depth: masks must still agree, the averaged depth is not compared
+    got[3][~finite] = 1.0
+    w3 = want[3].copy()
+    w3[~finite] = 1.0
+    _compare(got, (want[0], want[1], want[2], w3))
