@@ -20,12 +20,13 @@ LIB_PATH = os.path.join(_PKG_DIR, "libpmb200.so")
 SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in ("pm_kernels.cu", "pm_backward.cu", "pm_conv.cu", "pm_geo.cu")]
 HEADERS = [
     os.path.join(_PKG_DIR, "csrc", "pm_math.cuh"),
+    os.path.join(_PKG_DIR, "csrc", "pm_geo_math.cuh"),
     os.path.join(_REPO_DIR, "include", "patchmatch_b200.h"),
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
+    "--shared", "-Xcompiler", "-fPIC", "--threads", "0",
 ]
 
 # TorchScript-facing shim: TORCH_LIBRARY(pmb200) over the same C ABI (csrc/torch_binding.cpp), host C++ only
@@ -120,7 +121,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 def build_torch_library(force: bool = False) -> str:
     """Compile csrc/torch_binding.cpp (g++, torch headers) into patchmatchnet_b200/libpmb200_torch.so.  It links
     against libpmb200.so (rpath $ORIGIN), so build_library() must have run."""
-    deps = [TORCH_SOURCE, HEADERS[1]]
+    deps = [TORCH_SOURCE, HEADERS[-1]]
     if not force and os.path.exists(TORCH_LIB_PATH) and all(os.path.getmtime(TORCH_LIB_PATH) >= os.path.getmtime(f) for f in deps):
         return TORCH_LIB_PATH
     if not os.path.exists(LIB_PATH):

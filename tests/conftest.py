@@ -66,9 +66,9 @@ def reference_models():
 def hostmath():
     """pm_math.cuh compiled for the host (test infrastructure, see tests/hostmath.cpp)."""
     src = os.path.join(REPO, "tests", "hostmath.cpp")
-    hdr = os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_math.cuh")
+    hdrs = [os.path.join(REPO, "patchmatchnet_b200", "csrc", h) for h in ("pm_math.cuh", "pm_geo_math.cuh")]
     out = os.path.join(REPO, "tests", "_hostmath.so")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.run(
             ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", out, "-x", "c++", src],
             check=True,

@@ -3,6 +3,7 @@
 // build box (no GPU) check the per-element arithmetic the kernels inline against the oracle.
 // It is never loaded by the product package.
 #include "../patchmatchnet_b200/csrc/pm_math.cuh"
+#include "../patchmatchnet_b200/csrc/pm_geo_math.cuh"
 
 extern "C" {
 
@@ -63,6 +64,24 @@ float hm_depth_similarity(float xc, float xn, float scale) { return pm::depth_si
 
 float hm_normalised_inverse_depth(float d, float inv_min, float inv_max) {
     return pm::normalised_inverse_depth(d, inv_min, inv_max);
+}
+
+// geometric-consistency filter, pixel by pixel with the kernel's own per-pixel function (pm_geo_math.cuh)
+void hm_geometric_filter(const float *ref_depth, const float *confidence, const float *src_depths, const double *cams, int V,
+                         int H, int W, int Hs, int Ws, double pixel_thres, float depth_thres, float photo_thres, int mask_thres,
+                         int *mask_sum, unsigned char *photo_mask, unsigned char *final_mask, double *depth_avg) {
+    for (int n = 0; n < H * W; ++n) {
+        const pmgeo::PixelResult r = pmgeo::filter_pixel(cams, src_depths, V, Hs, Ws, n % W, n / W, ref_depth[n], confidence[n],
+                                                         pixel_thres, depth_thres, photo_thres, mask_thres);
+        mask_sum[n] = r.count;
+        photo_mask[n] = r.photo ? 1 : 0;
+        final_mask[n] = r.final ? 1 : 0;
+        depth_avg[n] = r.depth_avg;
+    }
+}
+
+void hm_remap_linear(const float *src, int rows, int cols, const float *mx, const float *my, int n, float *out) {
+    for (int i = 0; i < n; ++i) out[i] = pmgeo::remap_linear(src, rows, cols, mx[i], my[i]);
 }
 
 }  // extern "C"

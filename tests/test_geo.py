@@ -90,6 +90,79 @@ def test_geometric_filter_rejects_bad_arguments_without_gpu():
         ops.geometric_filter(torch.zeros(4, 4), torch.zeros(4, 4), torch.zeros(1, 4, 4), torch.zeros(1, 60, dtype=torch.float64))
 
 
+def _run_host(hostmath, sc):
+    """The kernel's own per-pixel function (csrc/pm_geo_math.cuh) compiled for the host, pixel by pixel."""
+    import ctypes
+
+    from patchmatchnet_b200 import ops
+
+    cams = ops.compose_filter_cameras(sc["ref_K"], sc["ref_E"], list(sc["src_Ks"]), list(sc["src_Es"])).numpy()
+    ref = np.ascontiguousarray(sc["ref_depth"], dtype=np.float32)
+    conf = np.ascontiguousarray(sc["confidence"], dtype=np.float32)
+    src = np.ascontiguousarray(np.stack(list(sc["src_depths"])), dtype=np.float32)
+    H, W = ref.shape
+    V, Hs, Ws = src.shape
+    msum = np.empty((H, W), np.int32)
+    photo = np.empty((H, W), np.uint8)
+    final = np.empty((H, W), np.uint8)
+    avg = np.empty((H, W), np.float64)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    fn = hostmath.hm_geometric_filter
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_double, ctypes.c_float, ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 4
+    fn(ptr(ref), ptr(conf), ptr(src), ptr(cams), V, H, W, Hs, Ws, 1.0, 0.01, 0.8, 3, ptr(msum), ptr(photo), ptr(final), ptr(avg))
+    return [photo.astype(bool), msum, final.astype(bool), avg]
+
+
+def test_kernel_remap_function_is_bit_exact_against_cv2(hostmath):
+    """pmgeo::remap_linear (the function the kernel inlines) against cv2.remap, including non-finite / huge coordinates."""
+    import ctypes
+
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    img = rng.uniform(400, 900, size=(37, 53)).astype(np.float32)
+    H, W = img.shape
+    mx = rng.uniform(-4, W + 4, size=(H, W)).astype(np.float32)
+    my = rng.uniform(-4, H + 4, size=(H, W)).astype(np.float32)
+    mx[0, :8] = [np.nan, np.inf, -np.inf, 1e9, -1e9, 40000.3, -40000.7, 0.015625]
+    my[0, :8] = [1, 2, 3, 4, 5, 6, 7, 0.984375]
+    mx[1, :4] = [-1.0, -0.5, W - 1, W - 0.5]
+    my[1, :4] = [0.25, H - 1, H - 0.5, -0.99]
+    want = cv2.remap(img, mx, my, interpolation=cv2.INTER_LINEAR)
+    got = np.empty_like(want)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    fn = hostmath.hm_remap_linear
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    fn(ptr(img), H, W, ptr(mx), ptr(my), H * W, ptr(got))
+    assert np.array_equal(want, got)
+
+
+def test_kernel_pixel_function_matches_the_reference_fixture(hostmath, golden):
+    sc = dict(ref_depth=golden["ref_depth"], ref_K=golden["ref_K"], ref_E=golden["ref_E"], src_depths=golden["src_depths"],
+              src_Ks=golden["src_Ks"], src_Es=golden["src_Es"], confidence=golden["confidence"])
+    _compare(_run_host(hostmath, sc), (golden["photo_mask"], golden["geo_mask_sum"], golden["final_mask"], golden["depth_est_averaged"]))
+
+
+@pytest.mark.parametrize("H,W,n_src,seed", [(72, 100, 3, 3), (33, 47, 1, 5)])
+def test_kernel_pixel_function_matches_the_oracle(hostmath, H, W, n_src, seed):
+    sc, want = _oracle_case(H, W, n_src, seed)
+    got = _run_host(hostmath, sc)
+    got[3][~np.isfinite(want[3])] = 1.0
+    w3 = np.where(np.isfinite(want[3]), want[3], 1.0)
+    _compare(got, (want[0], want[1], want[2], w3))
+
+
+def _oracle_case(H, W, n_src, seed):
+    sc = geo_cases.make_scene(seed=seed, H=H, W=W, n_src=n_src)
+    if H * W < 8000:  # degenerate inputs: zero depth, NaN confidence
+        sc["ref_depth"][0, :5] = 0.0
+        sc["confidence"][1, :3] = np.nan
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = go.fuse_reference_view(sc["ref_depth"], sc["ref_K"], sc["ref_E"], sc["src_depths"], sc["src_Ks"], sc["src_Es"], sc["confidence"])
+    return sc, want
+
+
 def _run_gpu(sc):
     from patchmatchnet_b200 import ops
 
@@ -110,8 +183,8 @@ def _compare(got, want):
     assert flipped.sum() <= max(1, int(1e-4 * n)), f"{flipped.sum()} of {n} pixels disagree on the geometric mask count"
     assert (final != wfinal).sum() <= max(1, int(1e-4 * n))
     same = ~flipped
-    rel = np.abs(avg[same] - wavg[same]) / np.abs(wavg[same])
-    assert avg.dtype == np.float64 and rel.max() <= 1e-6, rel.max()
+    err = np.abs(avg[same] - wavg[same])
+    assert avg.dtype == np.float64 and np.all(err <= 1e-6 * np.abs(wavg[same])), err.max()  # (0 vs 0 passes; NaN fails)
 
 
 @pytest.mark.gpu
@@ -124,18 +197,9 @@ def test_gpu_filter_matches_the_reference_fixture(golden):
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,n_src,seed", [(72, 100, 3, 3), (33, 47, 1, 5), (512, 640, 4, 7)])
 def test_gpu_filter_matches_the_oracle(H, W, n_src, seed):
-    sc = geo_cases.make_scene(seed=seed, H=H, W=W, n_src=n_src)
-    if H * W < 8000:  # degenerate inputs: zero depth, NaN confidence
-        sc["ref_depth"][0, :5] = 0.0
-        sc["confidence"][1, :3] = np.nan
-    with np.errstate(divide="ignore", invalid="ignore"):
-        want = go.fuse_reference_view(sc["ref_depth"], sc["ref_K"], sc["ref_E"], sc["src_depths"], sc["src_Ks"], sc["src_Es"], sc["confidence"])
+    sc, want = _oracle_case(H, W, n_src, seed)
     got = _run_gpu(sc)
-    finite = np.isfinite(want[3])
-    got[3] = np.where(finite, got[3], 0.0)
-    want = (want[0], want[1], want[2], np.where(finite, want[3], 0.0) + (~finite) * 0.0)
     # pixels with a zero / non-finite reference depth: masks must still agree, the averaged depth is not compared
-    got[3][~finite] = 1.0
-    w3 = want[3].copy()
-    w3[~finite] = 1.0
+    got[3][~np.isfinite(want[3])] = 1.0
+    w3 = np.where(np.isfinite(want[3]), want[3], 1.0)
     _compare(got, (want[0], want[1], want[2], w3))
