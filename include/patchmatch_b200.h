@@ -33,6 +33,8 @@ extern "C" {
 
 #define PMB200_EINVAL (-1)       /* bad size / null pointer */
 #define PMB200_EUNSUPPORTED (-2) /* combination the reference raises NotImplementedError for */
+#define PMB200_EIO (-3)          /* map files: open / read / write failed (message carries strerror and the path) */
+#define PMB200_EFORMAT (-4)      /* map files: not a PFM file / malformed header / payload does not match the header */
 
 #define PMB200_MAX_VIEWS 16
 #define PMB200_MAX_NEIGHBORS 32
@@ -128,6 +130,34 @@ int pmb200_geometric_filter(const float *ref_depth, const float *confidence, con
                             float geo_depth_thres, float photo_thres, int geo_mask_thres, int *geo_mask_sum_out,
                             unsigned char *photo_mask_out, unsigned char *final_mask_out, double *depth_avg_out,
                             void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Depth / confidence map files either side of the path: PFM and COLMAP .bin, read straight into /
+ * written straight from caller-owned host buffers (pinned, so the next step is one cudaMemcpyAsync).  Host code, no
+ * stream.  Replaces reference datasets/data_io.py read_pfm :257-288, save_pfm :291-322, read_bin :165-191,
+ * save_bin :194-223 -- identical bytes on disk, identical values in memory.  In-memory layout is [H,W,C] row-major, top
+ * row first (what read_pfm / read_bin return); the PFM bottom-up row order and the planar [C][H][W] payload of .bin are
+ * handled inside the I/O.  Messages of PMB200_EFORMAT are the reference's exception texts ("Not a PFM file.",
+ * "Malformed PFM header.", numpy's "cannot reshape array of size N into shape (..)"). */
+#define PMB200_MAP_PFM 1
+#define PMB200_MAP_COLMAP_BIN 2
+
+typedef struct {
+    int format;             /* PMB200_MAP_* */
+    int width, height, channels;
+    int big_endian;         /* PFM: non-negative scale line (data_io.py:275-279); .bin: 0 */
+    double scale;           /* PFM: |scale line| (data_io.py:277); .bin: 1 */
+    int64_t data_offset;    /* first payload byte */
+    int64_t payload_floats; /* whole float32 items after the header (np.fromfile) */
+} pmb200_map_info;
+
+/* Parse the header only (to size the destination buffer). */
+int pmb200_map_probe(const char *path, int format, pmb200_map_info *info);
+/* Read the whole map into out_host[H*W*C]; `info_out` may be NULL.  capacity_floats < H*W*C -> PMB200_EINVAL. */
+int pmb200_map_read(const char *path, int format, float *out_host, int64_t capacity_floats, pmb200_map_info *info_out);
+/* Write data_host[H,W,C] (C = 1 or 3).  PFM: the scale line is printf("%f", -scale) -- the reference negates the scale on a
+ * little-endian host (data_io.py:315-318); .bin ignores `scale`. */
+int pmb200_map_write(const char *path, int format, const float *data_host, int height, int width, int channels, double scale);
 
 /* Caller-side helper (models/net.py:289-299): photometric confidence = probability mass of the four
  * hypotheses around the regressed hypothesis index, nearest-resized to [H_out, W_out].

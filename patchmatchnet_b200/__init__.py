@@ -8,7 +8,7 @@ Public surface (mirrors the reference's ``models`` package for this path):
 """
 import os as _os
 
-from . import _native, distributed, engine, ops, synthetic  # noqa: F401
+from . import _native, data_io, distributed, engine, ops, synthetic  # noqa: F401
 from .net import PatchmatchNet, load_reference_state, patchmatchnet_loss  # noqa: F401
 from .patchmatch import PatchMatch  # noqa: F401
 

@@ -17,7 +17,7 @@ from typing import Optional
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libpmb200.so")
-SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in ("pm_kernels.cu", "pm_backward.cu", "pm_conv.cu", "pm_geo.cu")]
+SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in ("pm_kernels.cu", "pm_backward.cu", "pm_conv.cu", "pm_geo.cu", "pm_mapio.cpp")]
 HEADERS = [
     os.path.join(_PKG_DIR, "csrc", "pm_math.cuh"),
     os.path.join(_PKG_DIR, "csrc", "pm_geo_math.cuh"),
@@ -89,6 +89,18 @@ class MlpStruct(ctypes.Structure):
 
 _PMLP = POINTER(MlpStruct)
 
+
+class MapInfo(ctypes.Structure):
+    """pmb200_map_info (include/patchmatch_b200.h)."""
+
+    _fields_ = [
+        ("format", c_int), ("width", c_int), ("height", c_int), ("channels", c_int), ("big_endian", c_int),
+        ("scale", c_double), ("data_offset", c_int64), ("payload_floats", c_int64),
+    ]
+
+
+_PMAP = POINTER(MapInfo)
+
 _SIGNATURES = {
     "pmb200_abi_version": (c_int, []),
     "pmb200_last_error": (c_char_p, []),
@@ -99,6 +111,9 @@ _SIGNATURES = {
     "pmb200_conv2d_filter_floats": (c_int, [c_int] * 4),
     "pmb200_conv2d_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 15 + [c_void_p]),
     "pmb200_geometric_filter": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_double, c_float, c_float, c_int] + [c_void_p] * 5),
+    "pmb200_map_probe": (c_int, [c_char_p, c_int, _PMAP]),
+    "pmb200_map_read": (c_int, [c_char_p, c_int, c_void_p, c_int64, _PMAP]),
+    "pmb200_map_write": (c_int, [c_char_p, c_int, c_void_p, c_int, c_int, c_int, c_double]),
     "pmb200_warp_corr": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
     "pmb200_aggregate_views": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "pmb200_offset_corr": (c_int, [c_void_p] * 2 + [c_int, c_void_p] + [c_int] * 7 + [c_void_p]),
