@@ -819,6 +819,9 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
         __syncwarp();  // s_key / s_T are rewritten by the next view
     }
 
+    // One IEEE division per thread, then multiplies: the NE*G divisions that stood here were 13 instructions each
+    // (221 of this kernel's 1608 SASS instructions at C32 D16, tools/sass_lines.py); a * (1/b) is within 1.5 ulp of a / b.
+    const float inv_wsum = 1.0f / wsum;
     if (EPI == kEpiAgg) {
 #pragma unroll
         for (int k = 0; k < NE; ++k) {
@@ -826,7 +829,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
             if (ev[k]) {
                 float *o = p.out + (((size_t)b * G) * p.D + d) * HW + n;
 #pragma unroll
-                for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = acc[k][g] / wsum;
+                for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = acc[k][g] * inv_wsum;
             }
         }
     } else if (EPI == kEpiScore) {
@@ -835,7 +838,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
             const int d = d0 + row0 + k * RPK;
             float x[G];
 #pragma unroll
-            for (int g = 0; g < G; ++g) x[g] = acc[k][g] / wsum;
+            for (int g = 0; g < G; ++g) x[g] = acc[k][g] * inv_wsum;
             const float y = mlp_eval<G>(mlp, x);
             if (ev[k]) p.out[(((size_t)b * p.D + d) * HW + n) * p.ostride] = y;
         }
@@ -864,8 +867,9 @@ __global__ void aggregate_score_kernel(const float *__restrict__ sims, const flo
 #pragma unroll
         for (int g = 0; g < G; ++g) x[g] = fmaf(__ldg(sp + (size_t)g * D * HW), w, x[g]);
     }
+    const float inv_wsum = 1.0f / wsum;
 #pragma unroll
-    for (int g = 0; g < G; ++g) x[g] = x[g] / wsum;
+    for (int g = 0; g < G; ++g) x[g] *= inv_wsum;
     score[idx * ostride] = mlp_eval<G>(mlp, x);
 }
 
@@ -1345,7 +1349,8 @@ struct EvalParams {
     float interval_scale;
 };
 
-// block (TP pixels, DY hypothesis lanes); dynamic smem: float4 cw[K][TP]; int ck[K][TP]; float sc[D][TP]; float pr[D][TP]
+// block (TP pixels, DY hypothesis lanes); dynamic smem: float4 cw[K][TP]; int ck[K][TP]; float sc[D][TP]; float pr[D][TP];
+// float cf[K][TP]
 // KT = number of evaluation neighbours (9 or 17) as a compile-time constant: the neighbour loop is fully unrolled
 // so that the 8 gathers of every neighbour are issued back to back instead of one neighbour at a time.
 template <int KT>
@@ -1356,6 +1361,7 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
     int *ck = reinterpret_cast<int *>(cw + (size_t)p.K * TP);
     float *sc = reinterpret_cast<float *>(ck + (size_t)p.K * TP);
     float *pr = sc + (size_t)p.D * TP;
+    float *cf = pr + (size_t)p.D * TP;  // feature weight of (neighbour, pixel): independent of the hypothesis, read D times
 
     const int tp = threadIdx.x, ty = threadIdx.y;
     const int HW = p.H * p.W;
@@ -1374,6 +1380,7 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
         const pm::Cell c = pm::border_cell((float)(nc % p.W) + ox, (float)(nc / p.W) + oy, p.H, p.W);
         cw[k * TP + tp] = make_float4(c.w00, c.w01, c.w10, c.w11);
         ck[k * TP + tp] = c.key;
+        cf[k * TP + tp] = __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
     }
     __syncthreads();
 
@@ -1394,7 +1401,7 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
                                    ffma2(v1, make_float2(w.y, w.y), make_float2(v0.x * w.x, v0.y * w.x))));
                 const float t = fminf(fabsf(acc.x - xc) * inv_interval, 4.0f);
                 const float sg = __fdividef(1.0f, 1.0f + __expf(2.0f * t - 4.0f));
-                const float wk = sg * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+                const float wk = sg * cf[k * TP + tp];
                 num = fmaf(acc.y, wk, num);
                 den += wk;
             }
@@ -1415,7 +1422,7 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
                 // (argument in [-4, 4]: relative error ~1e-7, far below the parity tolerance)
                 const float t = fminf(fabsf(xn - xc) * inv_interval, 4.0f);
                 const float sg = __fdividef(1.0f, 1.0f + __expf(2.0f * t - 4.0f));
-                const float wk = sg * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+                const float wk = sg * cf[k * TP + tp];
                 num = fmaf(sn, wk, num);
                 den += wk;
             }
@@ -1435,7 +1442,7 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
                 sn = fmaf(__ldg(smap + r1), w.y, sn);
                 sn = fmaf(__ldg(smap + r2), w.z, sn);
                 sn = fmaf(__ldg(smap + r3), w.w, sn);
-                const float wk = pm::depth_similarity(xc, xn, p.interval_scale) * __ldg(p.fw + ((size_t)b * p.K + k) * HW + nc);
+                const float wk = pm::depth_similarity(xc, xn, p.interval_scale) * cf[k * TP + tp];
                 num = fmaf(sn, wk, num);
                 den += wk;
             }
@@ -1900,7 +1907,7 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
         TP = 16;
         DY = D < 16 ? D : 16;
     }
-    auto smem_for = [&](int tp) { return (size_t)K * tp * (sizeof(float4) + sizeof(int)) + 2 * (size_t)D * tp * sizeof(float); };
+    auto smem_for = [&](int tp) { return (size_t)K * tp * (sizeof(float4) + sizeof(int) + sizeof(float)) + 2 * (size_t)D * tp * sizeof(float); };
     if (smem_for(TP) > 48 * 1024) {  // many hypotheses: fewer pixels per block keeps the tile under the default 48 KB
         TP = 8;
         DY = D < 32 ? D : 32;
