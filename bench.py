@@ -67,56 +67,135 @@ def build_net(patchmatch_cls=None):
 
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons DURING the timed region.
 
-    def __init__(self, gpu_index: int):
+    The timed region of the default run is ~20 ms, far shorter than the start-up of an `nvidia-smi -lms` process, so the
+    primary sampler is an NVML thread (pynvml / nvidia-ml-py: one clock + one reasons query every ~2 ms, GIL released
+    inside the library calls); `nvidia-smi -lms 20`, started BEFORE the warm-up so that it is already printing, is the
+    fallback when NVML cannot be loaded.  Only samples taken between mark_begin() and mark_end() are reported; when the
+    window caught none (nvidia-smi fallback on a very short run) the samples of the warm-up just before it are used and
+    the line says so."""
+
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_index: int, device_uuid: str = ""):
         self.gpu = gpu_index
+        self.uuid = device_uuid
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []  # (perf_counter, sm_mhz, reasons tuple)   [NVML thread]
+        self.max_mhz = None
+        self._stop = False
+        self.t_begin = self.t_end = None
+        self.wall_begin = self.wall_end = None
+
+    # ---- NVML thread -------------------------------------------------------------------------------------------
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        if self.uuid:
+            for cand in (self.uuid, "GPU-" + self.uuid):
+                for arg in (cand, cand.encode()):  # str or bytes, depending on the nvidia-ml-py version
+                    try:
+                        return pynvml, pynvml.nvmlDeviceGetHandleByUUID(arg)
+                    except Exception:  # noqa: BLE001
+                        continue
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _run_nvml(self, nv, h):
+        bits = ((nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((time.perf_counter(), mhz, tuple(n for b, n in bits if mask & b)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run_nvml, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL,
             )
-        except Exception:
+        except Exception:  # noqa: BLE001
             self.proc = None
 
+    def mark_begin(self):
+        self.t_begin, self.wall_begin = time.perf_counter(), time.time()
+
+    def mark_end(self):
+        self.t_end, self.wall_end = time.perf_counter(), time.time()
+
+    # ---- results -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def _summary(rows, max_mhz, how, window):
+        """rows: (sm_mhz, reasons tuple)"""
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": max_mhz, "reasons": ["no samples"], "how": how}
+        reasons = sorted({r for _, rs in rows for r in rs})
+        return {"sm_mhz": statistics.median(m for m, _ in rows), "sm_max_mhz": max_mhz, "reasons": reasons, "samples": len(rows),
+                "how": how, "window": window}
+
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            lo = self.t_begin if self.t_begin is not None else -1.0
+            hi = self.t_end if self.t_end is not None else float("inf")
+            inside = [(m, r) for t, m, r in self.samples if lo <= t <= hi]
+            if inside:
+                return self._summary(inside, self.max_mhz, "NVML thread, 2 ms period", "timed region")
+            return self._summary([(m, r) for _, m, r in self.samples], self.max_mhz, "NVML thread, 2 ms period", "warm-up + timed region")
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
-        except Exception:
+        except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows, mx = [], []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
+                    stamp = time.mktime(time.strptime(f[0].split(".")[0], "%Y/%m/%d %H:%M:%S")) + float("0." + f[0].split(".")[1])
+                    mhz = float(f[1])
                     mx.append(float(f[2]))
-                except ValueError:
+                except (ValueError, IndexError):
                     continue
-                for nm, val in zip(names, f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
+                rows.append((stamp, mhz, tuple(nm for nm, val in zip(self.NAMES, f[5:9]) if val.lower().startswith("active"))))
         finally:
             try:
                 os.unlink(self.path)
             except OSError:
                 pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        top = max(mx) if mx else None
+        if self.wall_begin is not None and self.wall_end is not None:
+            inside = [(m, r) for t, m, r in rows if self.wall_begin - 0.02 <= t <= self.wall_end + 0.02]
+            if inside:
+                return self._summary(inside, top, "nvidia-smi -lms 20", "timed region")
+        return self._summary([(m, r) for _, m, r in rows], top, "nvidia-smi -lms 20", "warm-up + timed region")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -457,12 +536,17 @@ def main() -> None:
     stream = torch.cuda.current_stream()
     S = eng.n_slots
     rounds = [min(S, args.steps - r) for r in range(0, args.steps, S)]
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:  # noqa: BLE001
+        uuid = ""
+    sampler = ClockSampler(local, uuid)
+    sampler.start()  # before the warm-up: the sampler is already running when the timed region starts
     for _ in range(max(1, (args.warmup + S - 1) // S)):
         flush()
         eng.run_round(S, _recorded(stream), torch.cuda.Event())
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_begin()
     starts = [torch.cuda.Event(enable_timing=True) for _ in rounds]
     ends = [torch.cuda.Event(enable_timing=True) for _ in rounds]
     for i, n_now in enumerate(rounds):
@@ -470,6 +554,7 @@ def main() -> None:
         starts[i].record(stream)
         eng.run_round(n_now, starts[i], ends[i])
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     dev_seconds = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
 

@@ -18,7 +18,9 @@
 // contiguous C*4-byte read split over C/8 lanes as 2 x 16-byte loads (a full 128-byte line per pixel at C=32, two at
 // C=64).  PatchMatch hypotheses of one pixel are sorted and clustered, so consecutive hypotheses mostly land in the
 // same source cell; every generation of K-A exploits that differently (see the comments above each kernel).
+#if !defined(PM_EMU)  // host emulation build (tests/warp_emu.h) brings its own CUDA vocabulary
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -36,6 +38,7 @@ int fail(int code, const char *msg) {
     return code;
 }
 
+#if !defined(PM_EMU)
 int launch_status(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -44,6 +47,7 @@ int launch_status(const char *what) {
     }
     return 0;
 }
+#endif
 
 // Learned 2-D offset (x, y) of neighbour k at pixel n.  The offset convs' output is consumed in place in either
 // layout: planar [B,2K,H,W] (NCHW-contiguous) or channels-last [B,H,W,2K] (what cuDNN emits for a channels-last
@@ -58,9 +62,15 @@ __device__ __forceinline__ float2 load_offset(const float *__restrict__ off, int
 // The gather is bound by L1 data-pipe wavefronts; two LDG.128 at a 32-byte lane stride each touch every 128-byte
 // line of the texel, one LDG.256 touches it once.  The address must be 32-byte aligned (checked by the C entry points).
 __device__ __forceinline__ void ldg256(const float4 *__restrict__ p, float4 &lo, float4 &hi) {
+#if defined(PM_EMU)
+    assert((reinterpret_cast<uintptr_t>(p) & 31u) == 0);  // what ld.global.nc.v8.f32 requires
+    lo = p[0];
+    hi = p[1];
+#else
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
         : "l"(p));
+#endif
 }
 
 inline bool misaligned32(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) != 0; }
@@ -128,12 +138,16 @@ __device__ __forceinline__ void load_reference(const float *__restrict__ ref_nhw
 // kernels are bound by issue slots, not by the fp32 pipe, so halving the FFMA count of the head MLP, the blend and
 // the gather dot products buys back issue bandwidth at unchanged numerics.
 __device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+#if defined(PM_EMU)
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
     unsigned long long ra, rb, rc, rd;
     ra = *reinterpret_cast<const unsigned long long *>(&a);
     rb = *reinterpret_cast<const unsigned long long *>(&b);
     rc = *reinterpret_cast<const unsigned long long *>(&c);
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2 *>(&rd);
+#endif
 }
 
 // Folded (conv3d 1x1x1 + eval-mode BatchNorm) weights of one G -> 16 -> 8 -> 1 head in the layout the device code
@@ -1355,7 +1369,11 @@ struct EvalParams {
 // so that the 8 gathers of every neighbour are issued back to back instead of one neighbour at a time.
 template <int KT>
 __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) {
+#if defined(PM_EMU)
+    float4 *smem4 = static_cast<float4 *>(emu::dyn_smem());
+#else
     extern __shared__ float4 smem4[];
+#endif
     const int TP = blockDim.x, DY = blockDim.y;
     float4 *cw = smem4;
     int *ck = reinterpret_cast<int *>(cw + (size_t)p.K * TP);
@@ -1484,6 +1502,9 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
     }
 }
 
+#if defined(PM_EMU)
+}  // namespace  (the emulation build stops here: launchers and the C ABI below need the CUDA runtime)
+#else
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // PMB200_WARP_CORR_V1=1 selects the first-generation K-A kernel (kept for A/B measurements)
@@ -1520,6 +1541,15 @@ void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
     if constexpr (EPI == kEpiScore) {  // occupancy variant for tuning sweeps: 8 resident CTAs (<= 64 registers)
         if (!pipe && env_int("PMB200_KA_MINB", 6) == 8) {
             warp_corr3_kernel<C, G, EPI, DC, 0, 8><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+            return;
+        }
+    }
+    if constexpr (EPI == kEpiScore && LaneMap<C, G>::PPW == 8) {
+        // sweep candidate (PMB200_KA_MINB=5): the pipelined stage-2 kernel holds 128 registers -> 4 resident CTAs per SM,
+        // 592 on the chip, and its 1280-CTA grid at 128x160 is 2.16 waves; capped at 96 registers (276 bytes of spills)
+        // 5 CTAs fit (shared memory allows exactly 5) -> 1.73 waves.  Not the default until measured.
+        if (pipe && env_int("PMB200_KA_MINB", 4) == 5) {
+            warp_corr3_kernel<C, G, EPI, DC, 1, 5><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
             return;
         }
     }
@@ -1927,3 +1957,4 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
 }
 
 }  // extern "C"
+#endif  // !PM_EMU

@@ -118,7 +118,7 @@ PM_HD void project(const Ray &r, const float *rt, float d, int W, int H, float s
     *v = (Y / Z) * sy;
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(PM_EMU)
 // Device-only variants used by the third-generation K-A kernel: division by MUFU.RCP (<= 2 ulp, i.e.
 // < 2e-4 px at 640 px -- far below the fp32 noise of the reference's own normalise/un-normalise round
 // trip) and a footprint routine with a branch-free interior fast path.

@@ -1,0 +1,295 @@
+"""The CUDA kernels' own source, executed on the CPU by the lockstep warp emulator (tests/warp_emu.h), against the oracle.
+
+pm_kernels.cu is compiled by g++ with -DPM_EMU (tests/emu_kernels.cpp); every CUDA thread of a block is a fiber, warp
+collectives and barriers synchronise them.  This checks, without a GPU, what the GPU parity tests check on the box -- lane
+mappings, the per-pixel layered cell numbering, shuffles, shared-memory plumbing, epilogues -- at small sizes, and for MORE
+launch configurations (rows per warp pass, gather pipelining) than the GPU suite sweeps.  Numerics: the emulated build
+computes in the same fp32 operation order except for FMA contraction and the fast reciprocal/exponential intrinsics, so the
+GPU tests' tolerances apply unchanged.  TEST INFRASTRUCTURE: nothing here is on the product path."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pm_oracle
+from patchmatchnet_b200 import _native, synthetic
+from tests import pm_cases
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def emu():
+    src = os.path.join(REPO, "tests", "emu_kernels.cpp")
+    deps = [src, os.path.join(REPO, "tests", "warp_emu.h"), os.path.join(REPO, "include", "patchmatch_b200.h")]
+    deps += [os.path.join(REPO, "patchmatchnet_b200", "csrc", f) for f in ("pm_kernels.cu", "pm_math.cuh")]
+    out = os.path.join(REPO, "tests", "_emu_kernels.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")  # vector_types.h only
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", f"-I{cuda_inc}", "-o", out, src], check=True, cwd=os.path.join(REPO, "tests"))
+    lib = ctypes.CDLL(out)
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.emu_warp_corr3.argtypes = [P] * 5 + [ctypes.POINTER(_native.MlpStruct), P, P] + [I] * 13
+    lib.emu_warp_corr3.restype = I
+    lib.emu_adaptive_eval.argtypes = [P] * 5 + [I] + [P] * 5 + [I] * 6 + [ctypes.c_float, I, I, I]
+    lib.emu_adaptive_eval.restype = I
+    lib.emu_init_propagate.argtypes = [P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, ctypes.c_float]
+    lib.emu_init_propagate.restype = I
+    lib.emu_offset_corr.argtypes = [P, P, I, ctypes.POINTER(_native.MlpStruct), P] + [I] * 7
+    lib.emu_offset_corr.restype = I
+    return lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _aligned(t):
+    """contiguous float32 copy whose storage is 32-byte aligned (what the 256-bit gather loads require)"""
+    buf = torch.empty(t.numel() + 8, dtype=torch.float32)
+    shift = (-buf.data_ptr() // 4) % 8
+    out = buf[shift:shift + t.numel()].view(t.shape)
+    out.copy_(t)
+    assert out.data_ptr() % 32 == 0
+    return out
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def maxabs(a, b):
+    return float((a.double() - b.double()).abs().max())
+
+
+def _warp_case(B, V, C, H, W, D, Hs=None, Ws=None, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    Hs, Ws = Hs or H, Ws or W
+    ref = torch.randn(B, C, H, W, generator=g)
+    srcs = [torch.randn(B, C, Hs, Ws, generator=g) for _ in range(V)]
+    Kc, Ec = synthetic.make_cameras(B, V + 1, H * 8, W * 8)
+    ref_proj, src_projs = synthetic.stage_projections(Kc, Ec, 3)
+    depth = 350.0 + 700.0 * torch.rand(B, D, H, W, generator=g)
+    depth = torch.sort(depth, dim=1)[0]
+    depth[:, 0, : max(1, H // 4)] = -20.0  # behind the camera -> exactly 0
+    vw = torch.rand(B, V, H, W, generator=g)
+    return ref, srcs, ref_proj.contiguous(), [m.contiguous() for m in src_projs], depth, vw
+
+
+def _rt(ref_proj, src_projs):
+    """what pmb200_relative_projection computes: src . inverse(ref) in float64, [V,B,12] float32"""
+    inv = torch.linalg.inv(ref_proj.double())
+    rows = []
+    for sp in src_projs:
+        rel = sp.double() @ inv
+        rows.append(torch.cat([rel[:, :3, :3].reshape(-1, 9), rel[:, :3, 3]], dim=1))
+    return torch.stack(rows).float().contiguous()
+
+
+def _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G):
+    return torch.stack([pm_oracle.groupwise_correlation(pm_oracle.homography_warp(s, sp, ref_proj, depth), ref, G)
+                        for s, sp in zip(srcs, src_projs)])
+
+
+def _run_ka(emu, ref, srcs, rt, depth, G, epi, dc, pipe, vw=None, head=None, keep_sims=False, ostride=1):
+    B, C, H, W = ref.shape
+    V, D = len(srcs), depth.shape[1]
+    Hs, Ws = srcs[0].shape[-2:]
+    ref_n = _aligned(nhwc(ref))
+    src_n = _aligned(torch.stack([nhwc(s) for s in srcs]))
+    shape = {0: (V, B, G, D, H, W), 1: (B, G, D, H, W), 2: (B, D, H, W, ostride), 3: (B, V, H, W)}[epi]
+    out = torch.zeros(shape) if epi == 3 else torch.full(shape, -77.0)
+    sims = torch.full((V, B, G, D, H, W), -77.0) if keep_sims else None
+    depth_c, vw_c = depth.contiguous(), None if vw is None else vw.contiguous()
+    out_ptr = out.data_ptr() + 4 * (ostride - 1)  # ostride 2: the .y lane of an interleaved (xnorm, score) buffer
+    rc = emu.emu_warp_corr3(_ptr(ref_n), _ptr(src_n), _ptr(rt), _ptr(depth_c), _ptr(vw_c), head, out_ptr, _ptr(sims), ostride,
+                            V, B, C, G, H, W, Hs, Ws, D, epi, dc, pipe)
+    assert rc == 0, rc
+    return (out, sims) if keep_sims else out
+
+
+KA_SHAPES = [
+    (64, 8, 9, 13, 20, 1, 2),  # stage-3 shape class; D not a multiple of the rows per pass
+    (32, 8, 10, 11, 16, 2, 2),  # stage 2, batch 2
+    (16, 4, 7, 19, 8, 1, 3),  # stage 1: 16 pixels per warp, ragged pixel count
+    (16, 4, 5, 6, 5, 1, 1),  # single view, odd hypothesis count
+    (64, 8, 3, 3, 1, 1, 2),  # single hypothesis, tiny map
+]
+
+
+def _configs(C):
+    ppw = 32 // (C // 8)
+    return [(dc, pipe) for dc in (4, 8, 16) for pipe in (0, 1) if (ppw * dc) % 32 == 0]
+
+
+@pytest.mark.parametrize("C,G,H,W,D,B,V", KA_SHAPES)
+def test_emulated_warp_corr_matches_oracle(emu, C, G, H, W, D, B, V):
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=C + D)
+    want = _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G)
+    rt = _rt(ref_proj, src_projs)
+    scale = max(1.0, float(want.abs().max()))
+    wsum = 1e-5 + vw.sum(1)
+    want_f = (want * vw.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / wsum[:, None, None]
+    for dc, pipe in _configs(C):
+        got = _run_ka(emu, ref, srcs, rt, depth, G, 0, dc, pipe)
+        assert maxabs(got, want) <= 2e-5 * scale, (dc, pipe)
+        assert float(got[:, :, :, 0, : max(1, H // 4)].abs().max()) == 0.0
+        got_f = _run_ka(emu, ref, srcs, rt, depth, G, 1, dc, pipe, vw=vw)
+        assert maxabs(got_f, want_f) <= 2e-5 * scale, (dc, pipe)
+
+
+def test_emulated_warp_corr_source_map_of_other_size(emu):
+    C, G, H, W, D, B, V = 32, 8, 12, 20, 8, 1, 2
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, Hs=9, Ws=14, seed=5)
+    want = _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G)
+    got = _run_ka(emu, ref, srcs, _rt(ref_proj, src_projs), depth, G, 0, 8, 1)
+    assert maxabs(got, want) <= 5e-5 * max(1.0, float(want.abs().max()))
+
+
+def _random_head(cls, G, seed):
+    torch.manual_seed(seed)
+    head = cls(G)
+    for m in head.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.running_mean.normal_(0, 0.3)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    return head.eval()
+
+
+@pytest.mark.parametrize("C,G,H,W,D,B,V", KA_SHAPES[:4])
+def test_emulated_fused_heads_match_unfused(emu, C, G, H, W, D, B, V):
+    from patchmatchnet_b200.patchmatch import PixelwiseNet, SimilarityNet
+
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=C + D + 1)
+    rt = _rt(ref_proj, src_projs)
+    sims = _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G)
+    wsum = 1e-5 + vw.sum(1)
+    agg = (sims * vw.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / wsum[:, None, None]
+    with torch.no_grad():
+        sim_head = _random_head(SimilarityNet, G, 1)
+        want = sim_head(agg)
+        pw = _random_head(PixelwiseNet, G, 2)
+        want_vw = torch.cat([pw(sims[v]) for v in range(V)], dim=1)
+    for dc, pipe in _configs(C):
+        got = _run_ka(emu, ref, srcs, rt, depth, G, 2, dc, pipe, vw=vw, head=sim_head.folded())
+        assert maxabs(got[..., 0], want) <= 2e-5 * max(1.0, float(want.abs().max())), (dc, pipe)
+        got_vw, kept = _run_ka(emu, ref, srcs, rt, depth, G, 3, dc, pipe, head=pw.folded(), keep_sims=True)
+        assert maxabs(got_vw, want_vw) <= 1e-5, (dc, pipe)
+        assert maxabs(kept, sims) <= 2e-5 * max(1.0, float(sims.abs().max()))
+    # the score epilogue writing the .y lane of an interleaved (xnorm, score) buffer
+    dc, pipe = _configs(C)[0]
+    xs = _run_ka(emu, ref, srcs, rt, depth, G, 2, dc, pipe, vw=vw, head=sim_head.folded(), ostride=2)
+    assert bool((xs[..., 0] == -77.0).all()) and maxabs(xs[..., 1], want) <= 2e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("D,K,dil,H,W,B,inverse,TP,DY", [(16, 9, 4, 11, 13, 1, False, 32, 4), (8, 9, 6, 9, 14, 2, True, 16, 8),
+                                                         (8, 17, 4, 12, 16, 1, False, 16, 16), (5, 9, 2, 7, 7, 1, True, 8, 32),
+                                                         (40, 9, 2, 6, 9, 1, False, 32, 8)])
+def test_emulated_adaptive_eval_matches_oracle(emu, D, K, dil, H, W, B, inverse, TP, DY):
+    g = torch.Generator().manual_seed(D + K)
+    dmin, dmax = torch.full((B,), 425.0), torch.full((B,), 935.0)
+    scale = 0.0125
+    depth = torch.sort(430.0 + 500.0 * torch.rand(B, D, H, W, generator=g), dim=1, descending=inverse)[0].contiguous()
+    score0 = (torch.randn(B, D, H, W, generator=g) * 2.0).contiguous()
+    off = (torch.randn(B, 2 * K, H, W, generator=g) * 1.5).contiguous()
+    fw = (torch.rand(B, K, H, W, generator=g) + 0.05).contiguous()
+    grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("evaluation", K, dil), off.view(B, 2 * K, H * W), H, W)
+    w = pm_oracle.depth_similarity_weight(depth, dmin, dmax, grid, scale, K) * fw.unsqueeze(1)
+    w = w / torch.sum(w, dim=2).unsqueeze(2)
+    s = torch.sum(pm_oracle._border_sample(score0, grid).view(B, D, K, H, W) * w, dim=2)
+    want_prob = torch.exp(F.log_softmax(s, dim=1))
+    want_depth = pm_oracle._Evaluation.regress(depth, want_prob, inverse)
+    inv_min, inv_max = (1.0 / dmin).view(B, 1, 1, 1), (1.0 / dmax).view(B, 1, 1, 1)
+    xnorm = ((1.0 / depth - inv_max) / (inv_min - inv_max)).contiguous()
+    xs = torch.stack([xnorm, score0], dim=-1).contiguous()
+    off_cl = off.permute(0, 2, 3, 1).contiguous()  # channels-last memory
+    for sc, xn, inter, o, cl in ((score0, None, None, off, 0), (score0, xnorm, None, off_cl, 1), (None, None, xs, off, 0)):
+        prob, dep = torch.full((B, D, H, W), -1.0), torch.full((B, H, W), -1.0)
+        rc = emu.emu_adaptive_eval(_ptr(sc), _ptr(depth), _ptr(xn), _ptr(inter), _ptr(o), cl, _ptr(fw), _ptr(dmin), _ptr(dmax),
+                                   _ptr(prob), _ptr(dep), B, D, H, W, K, dil, scale, 1 if inverse else 0, TP, DY)
+        assert rc == 0
+        assert maxabs(prob, want_prob) <= 5e-6
+        assert pm_cases.rel_l1(dep, want_depth) <= 1e-6
+        assert maxabs(prob.sum(1), torch.ones(B, H, W)) <= 1e-5
+
+
+MODE_RANDOM, MODE_PERTURB, MODE_PASSTHROUGH = 0, 1, 2  # patchmatchnet_b200.ops.MODE_*
+
+
+@pytest.mark.parametrize(
+    "mode,Ns,Kp,dil,H,W,B",
+    [
+        ("random", 48, 16, 2, 9, 13, 1),  # 64 hypotheses: two per lane
+        ("random", 48, 0, 2, 8, 10, 1),
+        ("perturb", 16, 16, 2, 11, 9, 2),
+        ("perturb", 8, 8, 4, 13, 17, 1),
+        ("perturb", 8, 4, 4, 9, 11, 1),
+        ("perturb", 8, 0, 6, 12, 15, 2),
+        ("perturb", 3, 8, 2, 9, 10, 1),  # odd sample count
+        ("perturb", 100, 16, 2, 6, 7, 1),  # > 64 hypotheses: generic path
+        ("pass", 1, 8, 2, 9, 10, 1),
+    ],
+)
+def test_emulated_init_propagate_matches_oracle(emu, mode, Ns, Kp, dil, H, W, B):
+    g = torch.Generator().manual_seed(Ns + Kp + H)
+    dmin = torch.full((B,), 425.0) + torch.arange(B) * 3.0
+    dmax = torch.full((B,), 935.0) - torch.arange(B) * 4.0
+    scale = 0.025
+    if mode == "random":
+        u = torch.rand(B, 48, H, W, generator=g)
+        init = pm_oracle.init_hypotheses(dmin, dmax, H, W, scale, 16, torch.empty(0), u.device, lambda size, device: u)
+        seed, m = u, MODE_RANDOM
+    else:
+        depth = 400.0 + 560.0 * torch.rand(B, 1, H, W, generator=g)
+        init = pm_oracle.init_hypotheses(dmin, dmax, H, W, scale, Ns, depth, depth.device)
+        seed, m = depth, (MODE_PERTURB if mode == "perturb" else MODE_PASSTHROUGH)
+    off, want = None, init
+    if Kp > 0:
+        off = (torch.randn(B, 2 * Kp, H, W, generator=g) * 2.0).contiguous()
+        grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("propagation", Kp, dil), off.view(B, 2 * Kp, H * W), H, W)
+        want = pm_oracle.propagate(init, grid)
+    D = Ns + Kp
+    inv_min, inv_max = (1.0 / dmin).view(B, 1, 1, 1), (1.0 / dmax).view(B, 1, 1, 1)
+    want_x = (1.0 / want - inv_max) / (inv_min - inv_max)
+    seed = seed.contiguous()
+    for cl in (0, 1):
+        o = off if (off is None or not cl) else off.permute(0, 2, 3, 1).contiguous()
+        got = torch.full((B, D, H, W), -1.0)
+        xs = torch.full((B, D, H, W, 2), -7.0)  # xnorm goes to the .x lane of the interleaved buffer
+        rc = emu.emu_init_propagate(_ptr(seed), _ptr(o), cl, _ptr(dmin), _ptr(dmax), _ptr(got), _ptr(xs), 2, m, B, H, W, Ns, Kp, dil, scale)
+        assert rc == 0
+        assert got.shape == want.shape and pm_cases.rel_l1(got, want) <= 1e-6 and maxabs(got, want) <= 2e-3
+        assert maxabs(xs[..., 0], want_x) <= 5e-6 and bool((xs[..., 1] == -7.0).all())
+        if Kp > 0:
+            assert bool((got[:, 1:] >= got[:, :-1]).all())  # sorted ascending
+
+
+@pytest.mark.parametrize("C,G,K,dil,H,W,B", [(64, 8, 9, 2, 9, 13, 1), (32, 8, 9, 4, 11, 14, 2), (16, 4, 9, 6, 13, 19, 1), (16, 4, 17, 4, 12, 18, 1)])
+def test_emulated_offset_corr_matches_oracle(emu, C, G, K, dil, H, W, B):
+    from patchmatchnet_b200.patchmatch import FeatureWeightNet
+
+    g = torch.Generator().manual_seed(K + C)
+    ref = torch.randn(B, C, H, W, generator=g)
+    off = (torch.randn(B, 2 * K, H, W, generator=g) * 2.5).contiguous()
+    grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("evaluation", K, dil), off.view(B, 2 * K, H * W), H, W)
+    want = pm_oracle._FeatureWeightHead(K, G).neighbour_correlation(ref, grid)  # [B,G,K,H,W]
+    ref_n = _aligned(nhwc(ref))
+    got = torch.full((B, G, K, H, W), -1.0)
+    assert emu.emu_offset_corr(_ptr(ref_n), _ptr(off), 0, None, _ptr(got), B, C, G, H, W, K, dil) == 0
+    assert maxabs(got, want) <= 2e-5 * max(1.0, float(want.abs().max()))
+    got_cl = torch.full((B, G, K, H, W), -1.0)
+    off_cl = off.permute(0, 2, 3, 1).contiguous()
+    assert emu.emu_offset_corr(_ptr(ref_n), _ptr(off_cl), 1, None, _ptr(got_cl), B, C, G, H, W, K, dil) == 0
+    assert torch.equal(got_cl, got)
+    with torch.no_grad():
+        fw = _random_head(lambda gg: FeatureWeightNet(K, gg), G, 3)
+        want_fw = fw(want)
+    got_fw = torch.full((B, K, H, W), -1.0)
+    assert emu.emu_offset_corr(_ptr(ref_n), _ptr(off), 0, fw.folded(), _ptr(got_fw), B, C, G, H, W, K, dil) == 0
+    assert maxabs(got_fw, want_fw) <= 1e-5

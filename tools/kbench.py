@@ -70,7 +70,9 @@ def timeit(fn, iters=12):
 out = {"shape": f"{W}x{H}", "rows": []}
 variants = ([dict(PMB200_WARP_CORR_V1="1"), dict(PMB200_KA_GEN="2")]
             + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE=str(pp)) for d, pp in itertools.product((0, 4, 8, 16), (0, 1))]
-            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE="0", PMB200_KA_MINB="8") for d in (0, 4, 8, 16)])
+            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE="0", PMB200_KA_MINB="8") for d in (0, 4, 8, 16)]
+            # C32 only (8 pixels per warp): pipelined gather capped at 96 registers -> 5 resident CTAs instead of 4
+            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE="1", PMB200_KA_MINB="5") for d in (0, 8, 16)])
 for (n, a, k) in calls:
     desc = n
     if n.startswith("warp_corr"):
