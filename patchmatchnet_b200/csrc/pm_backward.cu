@@ -9,7 +9,9 @@
 //     learned evaluation offsets (through the score gather only) and the feature weight;
 //   * FeatureWeightNet sees a detached reference feature (:475): K-A' differentiates w.r.t. the offsets only.
 // Layouts and argument meaning follow the forward entry points (include/patchmatch_b200.h).
+#if !defined(PM_EMU)  // host emulation build (tests/warp_emu.h) brings its own CUDA vocabulary
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 
 #include "../../include/patchmatch_b200.h"
@@ -20,7 +22,9 @@ extern "C" int pmb200_internal_launch_status(const char *what);
 
 namespace {
 
+#if !defined(PM_EMU)
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // bilinear footprints with the quantities a backward pass needs
@@ -485,6 +489,7 @@ __global__ void adaptive_eval_backward_kernel(const EvalBwdParams p) {
 
 }  // namespace
 
+#if !defined(PM_EMU)  // the emulation build stops here: the launchers below need the CUDA runtime
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -604,3 +609,4 @@ int pmb200_adaptive_eval_backward(const float *score0, const float *depth_sample
 }
 
 }  // extern "C"
+#endif  // !PM_EMU

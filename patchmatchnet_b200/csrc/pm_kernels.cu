@@ -1563,8 +1563,8 @@ template <int C, int G, int EPI>
 void launch_wc3_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
     constexpr int PPW = LaneMap<C, G>::PPW;
     constexpr int kDefault = PPW == 4 ? 16 : (PPW == 8 ? 8 : 4);
-    if constexpr (EPI == kEpiScore) {
-        const int d = env_int("PMB200_KA_DC", 0);
+    if constexpr (EPI == kEpiScore || EPI == kEpiViewW) {  // tuning sweeps (tools/kbench.py); unset = the measured defaults below
+        const int d = env_int(EPI == kEpiScore ? "PMB200_KA_DC" : "PMB200_KA_DC_VW", 0);
 #define PMB200_TRY3(DD)                                                                                  \
     if (d == DD) {                                                                                       \
         if constexpr ((PPW * DD) % 32 == 0 && PPW * DD * (4 * G + 4) * 4 * kWarps2 <= 40 * 1024) {       \

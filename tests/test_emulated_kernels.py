@@ -24,13 +24,13 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="session")
 def emu():
-    src = os.path.join(REPO, "tests", "emu_kernels.cpp")
-    deps = [src, os.path.join(REPO, "tests", "warp_emu.h"), os.path.join(REPO, "include", "patchmatch_b200.h")]
-    deps += [os.path.join(REPO, "patchmatchnet_b200", "csrc", f) for f in ("pm_kernels.cu", "pm_math.cuh")]
+    srcs = [os.path.join(REPO, "tests", f) for f in ("emu_kernels.cpp", "emu_backward.cpp")]
+    deps = srcs + [os.path.join(REPO, "tests", "warp_emu.h"), os.path.join(REPO, "include", "patchmatch_b200.h")]
+    deps += [os.path.join(REPO, "patchmatchnet_b200", "csrc", f) for f in ("pm_kernels.cu", "pm_backward.cu", "pm_math.cuh")]
     out = os.path.join(REPO, "tests", "_emu_kernels.so")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")  # vector_types.h only
-        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", f"-I{cuda_inc}", "-o", out, src], check=True, cwd=os.path.join(REPO, "tests"))
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", f"-I{cuda_inc}", "-o", out] + srcs, check=True, cwd=os.path.join(REPO, "tests"))
     lib = ctypes.CDLL(out)
     P, I = ctypes.c_void_p, ctypes.c_int
     lib.emu_warp_corr3.argtypes = [P] * 5 + [ctypes.POINTER(_native.MlpStruct), P, P] + [I] * 13
@@ -41,6 +41,15 @@ def emu():
     lib.emu_init_propagate.restype = I
     lib.emu_offset_corr.argtypes = [P, P, I, ctypes.POINTER(_native.MlpStruct), P] + [I] * 7
     lib.emu_offset_corr.restype = I
+    F32 = ctypes.c_float
+    lib.emu_warp_corr_backward.argtypes = [P] * 8 + [I] * 9
+    lib.emu_aggregate_views_backward.argtypes = [P] * 5 + [I] * 6
+    lib.emu_offset_corr_backward.argtypes = [P] * 4 + [I] * 7
+    lib.emu_init_propagate_backward.argtypes = [P] * 6 + [I] * 7 + [F32]
+    lib.emu_adaptive_eval_backward.argtypes = [P] * 14 + [I] * 6 + [F32, I]
+    for fn in ("emu_warp_corr_backward", "emu_aggregate_views_backward", "emu_offset_corr_backward", "emu_init_propagate_backward",
+               "emu_adaptive_eval_backward"):
+        getattr(lib, fn).restype = I
     return lib
 
 
@@ -293,3 +302,130 @@ def test_emulated_offset_corr_matches_oracle(emu, C, G, K, dil, H, W, B):
     got_fw = torch.full((B, K, H, W), -1.0)
     assert emu.emu_offset_corr(_ptr(ref_n), _ptr(off), 0, fw.folded(), _ptr(got_fw), B, C, G, H, W, K, dil) == 0
     assert maxabs(got_fw, want_fw) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# backward kernels (pm_backward.cu) against torch autograd on the oracle -- the CPU twin of tests/test_gpu_backward.py
+# ------------------------------------------------------------------------------------------------
+
+
+def close(got, want, tol=2e-5):
+    got, want = got.detach().double(), want.detach().double()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = max(1e-12, float(want.abs().max()))
+    err = float((got - want).abs().max())
+    assert err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("C,G,H,W,D,B,V", [(64, 8, 7, 9, 6, 1, 2), (32, 8, 9, 10, 8, 2, 2), (16, 4, 9, 14, 5, 1, 3)])
+def test_emulated_warp_corr_backward(emu, C, G, H, W, D, B, V):
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=C + D)
+    rt = _rt(ref_proj, src_projs)
+    ref_n, src_n = _aligned(nhwc(ref)), _aligned(torch.stack([nhwc(s) for s in srcs]))
+    depth_c, vw_c = depth.contiguous(), vw.contiguous()
+    for weighted in (False, True):
+        r = ref.clone().requires_grad_(True)
+        ss = [s.clone().requires_grad_(True) for s in srcs]
+        sims = torch.stack([pm_oracle.groupwise_correlation(pm_oracle.homography_warp(s, sp, ref_proj, depth), r, G) for s, sp in zip(ss, src_projs)])
+        if weighted:  # view weights detached, as on every iteration that uses the fused average
+            gw = torch.randn(B, G, D, H, W, generator=torch.Generator().manual_seed(2))
+            wsum = 1e-5 + vw.sum(1)
+            out = (sims * vw.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / wsum[:, None, None]
+        else:
+            gw = torch.randn(V, B, G, D, H, W, generator=torch.Generator().manual_seed(1))
+            out = sims
+        (out * gw).sum().backward()
+        d_ref = _aligned(torch.full((B, H, W, C), -3.0))
+        d_src = _aligned(torch.full((V, B, H, W, C), -3.0))
+        rc = emu.emu_warp_corr_backward(_ptr(ref_n), _ptr(src_n), _ptr(rt), _ptr(depth_c), _ptr(vw_c) if weighted else None, _ptr(gw.contiguous()),
+                                        _ptr(d_ref), _ptr(d_src), V, B, C, G, H, W, H, W, D)
+        assert rc == 0
+        close(d_ref.permute(0, 3, 1, 2), r.grad)
+        for v in range(V):
+            close(d_src[v].permute(0, 3, 1, 2), ss[v].grad)
+
+
+def test_emulated_aggregate_views_backward(emu):
+    g = torch.Generator().manual_seed(3)
+    V, B, G, D, H, W = 3, 2, 8, 6, 5, 7
+    sims = torch.randn(V, B, G, D, H, W, generator=g)
+    vw = torch.rand(B, V, H, W, generator=g)
+    gw = torch.randn(B, G, D, H, W, generator=g)
+    s1, w1 = sims.clone().requires_grad_(True), vw.clone().requires_grad_(True)
+    agg = (s1 * w1.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / (1e-5 + w1.sum(1))[:, None, None]
+    (agg * gw).sum().backward()
+    d_s, d_w = torch.full_like(sims, -3.0), torch.full_like(vw, -3.0)
+    assert emu.emu_aggregate_views_backward(_ptr(sims), _ptr(vw), _ptr(gw), _ptr(d_s), _ptr(d_w), V, B, G, D, H, W) == 0
+    close(d_s, s1.grad)
+    close(d_w, w1.grad)
+
+
+@pytest.mark.parametrize("C,G,K,dil,H,W,B", [(64, 8, 9, 2, 9, 13, 1), (32, 8, 9, 4, 11, 14, 1), (16, 4, 17, 4, 12, 16, 1)])
+def test_emulated_offset_corr_backward(emu, C, G, K, dil, H, W, B):
+    g = torch.Generator().manual_seed(K + C)
+    ref = torch.randn(B, C, H, W, generator=g)
+    off = (torch.randn(B, 2 * K, H, W, generator=g) * 2.5).contiguous()
+    gw = torch.randn(B, G, K, H, W, generator=g)
+    o1 = off.clone().requires_grad_(True)
+    grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("evaluation", K, dil), o1.view(B, 2 * K, H * W), H, W)
+    corr = pm_oracle._FeatureWeightHead(K, G).neighbour_correlation(ref, grid)
+    (corr * gw).sum().backward()
+    d_off = torch.full_like(off, -3.0)
+    assert emu.emu_offset_corr_backward(_ptr(_aligned(nhwc(ref))), _ptr(off), _ptr(gw), _ptr(d_off), B, C, G, H, W, K, dil) == 0
+    close(d_off, o1.grad, 5e-5)
+
+
+@pytest.mark.parametrize("mode,Ns,Kp,dil,H,W,B", [("random", 48, 16, 2, 9, 13, 1), ("perturb", 16, 16, 2, 9, 13, 1), ("perturb", 8, 8, 4, 11, 14, 2), ("perturb", 8, 4, 4, 7, 9, 1)])
+def test_emulated_init_propagate_backward(emu, mode, Ns, Kp, dil, H, W, B):
+    g = torch.Generator().manual_seed(Ns + Kp)
+    dmin, dmax = torch.full((B,), 425.0), torch.full((B,), 935.0)
+    scale = 0.025
+    off = (torch.randn(B, 2 * Kp, H, W, generator=g) * 2.0).contiguous()
+    gw = torch.randn(B, Ns + Kp, H, W, generator=g)
+    o1 = off.clone().requires_grad_(True)
+    if mode == "random":
+        u = torch.rand(B, 48, H, W, generator=g)
+        init = pm_oracle.init_hypotheses(dmin, dmax, H, W, scale, 16, torch.empty(0), u.device, lambda size, device: u)
+        seed, m = u, MODE_RANDOM
+    else:
+        depth = 430.0 + 500.0 * torch.rand(B, 1, H, W, generator=g)
+        init = pm_oracle.init_hypotheses(dmin, dmax, H, W, scale, Ns, depth, depth.device)
+        seed, m = depth, MODE_PERTURB
+    grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("propagation", Kp, dil), o1.view(B, 2 * Kp, H * W), H, W)
+    (pm_oracle.propagate(init, grid) * gw).sum().backward()
+    d_off = torch.full_like(off, -3.0)
+    rc = emu.emu_init_propagate_backward(_ptr(seed.contiguous()), _ptr(off), _ptr(dmin), _ptr(dmax), _ptr(gw), _ptr(d_off), m, B, H, W, Ns, Kp, dil, scale)
+    assert rc == 0
+    close(d_off, o1.grad, 1e-4)
+
+
+@pytest.mark.parametrize("D,K,dil,H,W,B,inverse", [(16, 9, 2, 9, 13, 1, False), (8, 9, 6, 11, 14, 1, True), (8, 17, 4, 10, 12, 1, False)])
+def test_emulated_adaptive_eval_backward(emu, D, K, dil, H, W, B, inverse):
+    g = torch.Generator().manual_seed(D + K)
+    dmin, dmax = torch.full((B,), 425.0), torch.full((B,), 935.0)
+    scale = 0.0125
+    depth = torch.sort(430.0 + 500.0 * torch.rand(B, D, H, W, generator=g), dim=1, descending=inverse)[0].contiguous()
+    score0 = (torch.randn(B, D, H, W, generator=g) * 2.0).contiguous()
+    off = (torch.randn(B, 2 * K, H, W, generator=g) * 1.5).contiguous()
+    fw = (torch.rand(B, K, H, W, generator=g) + 0.05).contiguous()
+    gdepth = torch.randn(B, H, W, generator=g)
+    gprob = torch.randn(B, D, H, W, generator=g)
+    inv_min, inv_max = (1.0 / dmin).view(B, 1, 1, 1), (1.0 / dmax).view(B, 1, 1, 1)
+    xnorm = ((1.0 / depth - inv_max) / (inv_min - inv_max)).contiguous()
+    for use_prob in (False, True):
+        s1, d1, o1, f1 = [t.clone().requires_grad_(True) for t in (score0, depth, off, fw)]
+        grid = pm_oracle.sampling_grid(pm_oracle.neighbour_table("evaluation", K, dil), o1.view(B, 2 * K, H * W), H, W)
+        w = pm_oracle.depth_similarity_weight(d1.detach(), dmin, dmax, grid.detach(), scale, K) * f1.unsqueeze(1)
+        w = w / torch.sum(w, dim=2).unsqueeze(2)
+        s = torch.sum(pm_oracle._border_sample(s1, grid).view(B, D, K, H, W) * w, dim=2)
+        prob = torch.exp(F.log_softmax(s, dim=1))
+        out = pm_oracle._Evaluation.regress(d1, prob, inverse)
+        ((out * gdepth).sum() + ((prob * gprob).sum() if use_prob else 0.0)).backward()
+        d_s, d_d, d_o, d_f = [torch.full_like(t, -3.0) for t in (score0, depth, off, fw)]
+        prob_c = prob.detach().contiguous()
+        rc = emu.emu_adaptive_eval_backward(_ptr(score0), _ptr(depth), _ptr(xnorm), _ptr(off), _ptr(fw), _ptr(dmin), _ptr(dmax), _ptr(prob_c),
+                                            _ptr(gdepth), _ptr(gprob) if use_prob else None, _ptr(d_s), _ptr(d_d), _ptr(d_o), _ptr(d_f),
+                                            B, D, H, W, K, dil, scale, 1 if inverse else 0)
+        assert rc == 0
+        for got, want, tol in zip((d_s, d_d, d_o, d_f), (s1.grad, d1.grad, o1.grad, f1.grad), (5e-5, 5e-5, 2e-4, 1e-4)):
+            close(got, want, tol)

@@ -283,5 +283,17 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline int atomicMax(int *p, int v) { const int o = *p; *p = std::max(o, v); return o; }
 inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
 inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
+inline float4 atomicAdd(float4 *p, float4 v) {  // sm_90+ 128-bit vector atomic (needs a 16-byte aligned address)
+    assert((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+    const float4 o = *p;
+    p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+    return o;
+}
+inline float2 atomicAdd(float2 *p, float2 v) {
+    assert((reinterpret_cast<uintptr_t>(p) & 7u) == 0);
+    const float2 o = *p;
+    p->x += v.x; p->y += v.y;
+    return o;
+}
 using std::max;
 using std::min;

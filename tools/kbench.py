@@ -91,6 +91,12 @@ for (n, a, k) in calls:
             row[f"TP={tp},DY={dy}"] = timeit(lambda: origs[n](*a, **k))
             os.environ.pop("PMB200_KB_TP", None)
             os.environ.pop("PMB200_KB_DY", None)
+    if n == "warp_corr_view_weights" and os.environ.get("KB_SWEEP_KA", "1") == "1":
+        for dc, pp in itertools.product((8, 16), (0, 1)):  # rows per warp pass / gather pipeline of the view-weights epilogue
+            os.environ["PMB200_KA_DC_VW"], os.environ["PMB200_KA_PIPE"] = str(dc), str(pp)
+            row[f"DC_VW={dc},PIPE={pp}"] = timeit(lambda: origs[n](*a, **k))
+            os.environ.pop("PMB200_KA_DC_VW", None)
+            os.environ.pop("PMB200_KA_PIPE", None)
     if n == "warp_corr_score" and os.environ.get("KB_SWEEP_KA", "1") == "1":
         for v in variants:
             for kk, vv in v.items():
