@@ -630,18 +630,27 @@ __device__ __forceinline__ unsigned pixel_lane_mask(int pixel) {
     return base << pixel;
 }
 
+// The four taps of one unique cell for this lane: 4 x LDG.256.  Addresses are formed from ONE 64-bit base (the feature
+// pack, a kernel parameter = uniform register) and 32-bit float4 indices: `lane_idx` (view / batch / lane offset, computed
+// once per view) + the texel offsets decoded from the key.  The first version added 64-bit pointers per tap; under the
+// 128-register cap of the pipelined variant ptxas rematerialised the 64-bit view base and the row stride inside the
+// gather loop (~35 of the ~95 instructions per lane and layer, tools/sass_lines.py); with 32-bit indices it is ~13.
+// The C entry points reject packs with more than 2^31 float4 elements.
 template <int C, int G>
-__device__ __forceinline__ void load_taps(const float4 *__restrict__ map_lane, int key, int cols, float4 (&t)[8]) {
-    constexpr int V4 = C / 4;
-    const int r0 = pm::cell_r0(key), dx = pm::cell_dx(key), dy = pm::cell_dy(key);
-    const float4 *t0 = map_lane + (size_t)r0 * V4;
-    const float4 *t1 = t0 + dx * V4;
-    const float4 *t2 = t0 + (size_t)dy * cols * V4;
-    const float4 *t3 = t2 + dx * V4;
-    ldg256(t0, t[0], t[1]);
-    ldg256(t1, t[2], t[3]);
-    ldg256(t2, t[4], t[5]);
-    ldg256(t3, t[6], t[7]);
+__device__ __forceinline__ void load_taps(const float4 *__restrict__ pack, unsigned lane_idx, int key, unsigned row_stride,
+                                          float4 (&t)[8]) {
+    constexpr unsigned V4 = C / 4;  // float4 per texel (4, 8 or 16)
+    constexpr int kLog2V4 = V4 == 4 ? 2 : (V4 == 8 ? 3 : 4);
+    static_assert(V4 == 4 || V4 == 8 || V4 == 16, "load_taps: C must be 16, 32 or 64");
+    const unsigned ukey = (unsigned)key;
+    const unsigned ox = (ukey >> (pm::kKeyDxShift - kLog2V4)) & V4;            // dx ? V4 : 0
+    const unsigned oy = ((ukey >> pm::kKeyDyShift) & 1u) * row_stride;         // dy ? cols * V4 : 0
+    const unsigned i0 = lane_idx + (ukey & (unsigned)pm::kKeyIndexMask) * V4;
+    const unsigned i2 = i0 + oy;
+    ldg256(pack + i0, t[0], t[1]);
+    ldg256(pack + (i0 + ox), t[2], t[3]);
+    ldg256(pack + i2, t[4], t[5]);
+    ldg256(pack + (i2 + ox), t[6], t[7]);
 }
 
 template <int C, int G>
@@ -757,17 +766,18 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
         if (kWeighted) wsum += wv;
 
         // ---- phase 2a: gather layer by layer, two layers in flight ----
-        const float4 *sv =
-            reinterpret_cast<const float4 *>(p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C) + li * 2;
+        const float4 *pack = reinterpret_cast<const float4 *>(p.src);
+        const unsigned row_stride = (unsigned)p.Ws * (C / 4);
+        const unsigned sv = (unsigned)(v * p.B + b) * ((unsigned)p.Hs * row_stride) + li * 2;  // float4 index of this lane's channels
         const int maxc = __reduce_max_sync(full, cg);
         if constexpr (PIPE) {
             float4 ta[8], tb[8];
             float *tbase = s_T[warp] + grp * TS + li * M::GPL;
-            if (cg > 0) load_taps<C, G>(sv, s_key[warp][grp], p.Ws, ta);
+            if (cg > 0) load_taps<C, G>(pack, sv, s_key[warp][grp], row_stride, ta);
             for (int j = 0; j < maxc; j += 2) {
-                if (j + 1 < cg) load_taps<C, G>(sv, s_key[warp][(j + 1) * M::PPW + grp], p.Ws, tb);
+                if (j + 1 < cg) load_taps<C, G>(pack, sv, s_key[warp][(j + 1) * M::PPW + grp], row_stride, tb);
                 if (j < cg) dot_store<C, G>(ta, r, tbase + j * M::PPW * TS);
-                if (j + 2 < cg) load_taps<C, G>(sv, s_key[warp][(j + 2) * M::PPW + grp], p.Ws, ta);
+                if (j + 2 < cg) load_taps<C, G>(pack, sv, s_key[warp][(j + 2) * M::PPW + grp], row_stride, ta);
                 if (j + 1 < cg) dot_store<C, G>(tb, r, tbase + (j + 1) * M::PPW * TS);
             }
         } else {
@@ -775,7 +785,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, MINB) warp_corr3_kernel(const Wa
             for (int j = 0; j < maxc; ++j) {
                 if (j < cg) {
                     float4 ta[8];
-                    load_taps<C, G>(sv, s_key[warp][j * M::PPW + grp], p.Ws, ta);
+                    load_taps<C, G>(pack, sv, s_key[warp][j * M::PPW + grp], row_stride, ta);
                     dot_store<C, G>(ta, r, tbase + j * M::PPW * TS);
                 }
             }
@@ -1692,6 +1702,7 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
     if ((long long)Hs * Ws >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "warp_corr: source map too large");
     if (C % 8 == 0 && (misaligned32(ref_nhwc) || misaligned32(src_nhwc)))
         return fail(PMB200_EINVAL, "warp_corr: feature packs must be 32-byte aligned (256-bit loads)");
+    if ((long long)V * B * Hs * Ws * C / 4 >= (1LL << 31)) return fail(PMB200_EINVAL, "warp_corr: source pack too large (32-bit tap indices)");
     WarpCorrParams p;
     p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = view_weights; p.out = out;
     p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
@@ -1738,6 +1749,7 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
     if ((long long)Hs * Ws >= (1LL << pm::kKeyDxShift)) return fail(PMB200_EINVAL, "warp_corr head: source map too large");
     if (misaligned32(ref_nhwc) || misaligned32(src_nhwc))
         return fail(PMB200_EINVAL, "warp_corr head: feature packs must be 32-byte aligned (256-bit loads)");
+    if ((long long)V * B * Hs * Ws * C / 4 >= (1LL << 31)) return fail(PMB200_EINVAL, "warp_corr head: source pack too large (32-bit tap indices)");
     WarpCorrParams p;
     p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = view_weights; p.out = out;
     p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
