@@ -1564,7 +1564,14 @@ void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
         }
     }
     if (pipe) warp_corr3_kernel<C, G, EPI, DC, 1, 4><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
-    else warp_corr3_kernel<C, G, EPI, DC, 0, 6><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+    else {
+        // shared memory per CTA (s_T + s_key) decides how many CTAs fit; asking ptxas for more than that only caps the
+        // registers for nothing
+        constexpr int kSmem = kWarps2 * LaneMap<C, G>::PPW * DC * ((4 * G + 4) * 4 + 4);
+        constexpr int kFit = (227 * 1024) / (kSmem + 1024);
+        constexpr int kMinB = kFit >= 6 ? 6 : (kFit >= 5 ? 5 : 4);
+        warp_corr3_kernel<C, G, EPI, DC, 0, kMinB><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
+    }
 }
 
 // Third-generation launch: rows per warp pass chosen per lane map (more rows = more reuse along the
