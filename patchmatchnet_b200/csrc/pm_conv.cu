@@ -31,7 +31,9 @@
 //
 // tcgen05/TMEM is deliberately not used here: with N <= 64 and K <= 64 per tap the operands are far below the
 // 128xNx8 UMMA tile economy, and the layers are bound by activation traffic, not by MMA issue.
+#if !defined(PM_EMU)  // host emulation build (tests/warp_emu.h) brings its own CUDA vocabulary
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 
@@ -65,6 +67,22 @@ struct ConvParams {
     int step_r[2], step_c[2];           // (128 or 256) / row_chunks and % row_chunks: per-iteration advance of a thread
 };
 
+#if defined(PM_EMU)
+// Host emulation (tests/warp_emu.h): the PTX below restated in C++ -- cvt.rna (nearest, ties away from zero, 10-bit
+// mantissa), the m16n8k8 TF32 MMA as a warp collective with the hardware's fragment layout (operands truncated to TF32 as
+// the tensor core does), cp.async as an immediate copy / zero fill.
+__device__ __forceinline__ uint32_t to_tf32(float f) { return emu::cvt_rna_tf32(f); }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { emu::mma_m16n8k8_tf32(d, a, b0, b1); }
+template <int BYTES>
+__device__ __forceinline__ void cp_async(float *smem_dst, const float *gmem_src, bool valid) {
+    assert((reinterpret_cast<uintptr_t>(smem_dst) % BYTES) == 0 && (!valid || (reinterpret_cast<uintptr_t>(gmem_src) % BYTES) == 0));
+    if (valid) memcpy(smem_dst, gmem_src, BYTES);
+    else memset(smem_dst, 0, BYTES);
+}
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ uint32_t to_tf32(float f) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
@@ -88,6 +106,7 @@ __device__ __forceinline__ void cp_async(float *smem_dst, const float *gmem_src,
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 // Stage the halo tile of output tile `tile` into `buf` ([rh][rw][ps]): the CTA's threads stride over the
 // tile's copy chunks (16-byte channel vectors when VEC, else single floats: Cin % 4 != 0).  Out-of-image pixels and
@@ -148,7 +167,11 @@ __device__ __forceinline__ void stage_any(const ConvParams &p, int tile, float *
 // few pixels and many channels get twice the warps per tile without staging the halo twice.
 template <int KCIN, int NT, int MT, int PREC, bool WREG, int NSPLIT>
 __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvParams p) {
+#if defined(PM_EMU)
+    float *s_in = static_cast<float *>(emu::dyn_smem());
+#else
     extern __shared__ __align__(16) float s_in[];
+#endif
     constexpr int KK = KCIN / 8;
     constexpr int ROWS = 4 * MT;
     constexpr int THREADS = 128 * NSPLIT;
@@ -415,7 +438,12 @@ int launch_conv(const ConvParams &p, const LaunchPlan &plan, cudaStream_t st) {
             if (dev >= 0 && dev < 64) granted[dev] = (int)plan.smem;
         }
     }
+#if defined(PM_EMU)
+    (void)st;
+    emu::launch(dim3((unsigned)plan.ctas), dim3(128 * NSPLIT), plan.smem, [&] { kern(p); });
+#else
     kern<<<(unsigned)plan.ctas, 128 * NSPLIT, plan.smem, st>>>(p);
+#endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         char msg[200];

@@ -47,6 +47,8 @@
 
 namespace emu {
 
+constexpr int kSlotWords = 4;  // 64-bit operand words a lane can post per collective (the MMA posts its A and B fragments at once)
+
 struct Fiber {
     ucontext_t ctx;
     std::vector<char> stack;
@@ -59,7 +61,7 @@ struct Fiber {
 
 struct Block {
     std::vector<Fiber> fibers;
-    std::vector<uint64_t> slot[2];  // [generation parity][linear thread id]
+    std::vector<uint64_t> slot[2];  // [generation parity][linear thread id * kSlotWords + word]
     dim3 block_dim{1, 1, 1}, grid_dim{1, 1, 1};
     uint3 block_idx{0, 0, 0};
     ucontext_t sched;
@@ -101,8 +103,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
     b.grid_dim = grid;
     b.body = &body;
     b.fibers.resize((size_t)nthreads);
-    b.slot[0].assign((size_t)nthreads, 0);
-    b.slot[1].assign((size_t)nthreads, 0);
+    b.slot[0].assign((size_t)nthreads * kSlotWords, 0);
+    b.slot[1].assign((size_t)nthreads * kSlotWords, 0);
     for (auto &f : b.fibers) f.stack.resize(256 * 1024);
     blk() = &b;
     for (unsigned bz = 0; bz < grid.z; ++bz)
@@ -142,16 +144,18 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
 inline int lane_id() { return cur()->linear & 31; }
 inline int warp_base() { return cur()->linear & ~31; }
 
-// Arrive at a warp collective with operand `v`; returns once every live lane named in `mask` has arrived.
-// `out[l]` then holds lane l's operand (only meaningful for lanes in the mask that are alive).
-inline void warp_exchange(unsigned mask, uint64_t v, uint64_t (&out)[32]) {
+// Arrive at a warp collective with NW operand words; returns once every live lane named in `mask` has arrived.
+// `out[w][l]` then holds word w of lane l (only meaningful for lanes in the mask that are alive).
+template <int NW>
+inline void warp_exchange_n(unsigned mask, const uint64_t (&v)[NW], uint64_t (&out)[NW][32]) {
+    static_assert(NW >= 1 && NW <= kSlotWords, "too many operand words");
     Block *b = blk();
     Fiber *me = cur();
     const int base = warp_base();
     const int nthreads = (int)b->fibers.size();
     assert((mask >> lane_id()) & 1u);  // the calling lane must be named in the mask
     const unsigned long long g = ++me->warp_gen;
-    b->slot[g & 1][(size_t)me->linear] = v;
+    for (int w = 0; w < NW; ++w) b->slot[g & 1][(size_t)me->linear * kSlotWords + w] = v[w];
     for (;;) {
         bool all = true;
         for (int l = 0; l < 32; ++l) {
@@ -162,7 +166,15 @@ inline void warp_exchange(unsigned mask, uint64_t v, uint64_t (&out)[32]) {
         if (all) break;
         yield();
     }
-    for (int l = 0; l < 32; ++l) out[l] = (base + l < nthreads) ? b->slot[g & 1][(size_t)(base + l)] : 0;
+    for (int w = 0; w < NW; ++w)
+        for (int l = 0; l < 32; ++l) out[w][l] = (base + l < nthreads) ? b->slot[g & 1][(size_t)(base + l) * kSlotWords + w] : 0;
+}
+
+inline void warp_exchange(unsigned mask, uint64_t v, uint64_t (&out)[32]) {
+    const uint64_t in[1] = {v};
+    uint64_t all[1][32];
+    warp_exchange_n<1>(mask, in, all);
+    for (int l = 0; l < 32; ++l) out[l] = all[0][l];
 }
 
 inline void block_barrier() {
@@ -295,5 +307,54 @@ inline float2 atomicAdd(float2 *p, float2 v) {
     p->x += v.x; p->y += v.y;
     return o;
 }
+inline unsigned __float_as_uint(float f) { return emu::from_bits<unsigned>(emu::bits_of(f)); }
+inline float __uint_as_float(unsigned u) { return emu::from_bits<float>(emu::bits_of(u)); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 using std::max;
 using std::min;
+
+// ---- the slice of the CUDA runtime API the launch-planning host code touches (pm_conv.cu) ---------------------------
+// (types and enumerators come from the toolkit's driver_types.h, which vector_types.h includes; only the calls are stubbed)
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetDevice(int *dev) { *dev = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }  // plan as for a B200
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
+namespace emu {
+
+// cvt.rna.tf32.f32: round to nearest, ties away from zero, keep 10 mantissa bits
+inline uint32_t cvt_rna_tf32(float f) {
+    uint32_t u = from_bits<uint32_t>(bits_of(f));
+    if ((u & 0x7f800000u) == 0x7f800000u) return u;  // inf / nan pass through
+    return (u + 0x1000u) & 0xffffe000u;
+}
+
+// mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 as a warp collective.  Fragments (PTX ISA): g = lane / 4, t = lane % 4;
+// A 16x8: a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  B 8x8: b0 (k = t, n = g)  b1 (k = t+4, n = g);
+// C/D 16x8: c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1).  Operands are read as TF32 (low 13 mantissa bits ignored).
+inline void mma_m16n8k8_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    uint64_t x[3][32];
+    const uint64_t mine[3] = {((uint64_t)a[1] << 32) | a[0], ((uint64_t)a[3] << 32) | a[2], ((uint64_t)b1 << 32) | b0};
+    warp_exchange_n<3>(0xffffffffu, mine, x);
+    auto tf = [](uint32_t u) { return from_bits<float>(bits_of((uint32_t)(u & 0xffffe000u))); };
+    const int lane = lane_id(), g = lane >> 2, t = lane & 3;
+    auto A = [&](int row, int k) {  // row 0..15, k 0..7
+        const int src = (row & 7) * 4 + (k & 3);
+        const uint64_t w = x[k >> 2][src];
+        return tf((row >> 3) ? (uint32_t)(w >> 32) : (uint32_t)w);
+    };
+    auto B = [&](int k, int n) {
+        const uint64_t w = x[2][n * 4 + (k & 3)];
+        return tf((k >> 2) ? (uint32_t)(w >> 32) : (uint32_t)w);
+    };
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + ((i >> 1) ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = d[i];
+        for (int k = 0; k < 8; ++k) acc = fmaf(A(row, k), B(k, col), acc);
+        d[i] = acc;
+    }
+}
+
+}  // namespace emu
