@@ -139,4 +139,71 @@ int emu_offset_corr(const float *ref_nhwc, const float *offsets, int offsets_cha
     return -2;
 }
 
+// ---- helper kernels ---------------------------------------------------------------------------------------------------
+int emu_relative_projection(const float *ref_proj, long long ref_batch_stride, const float *const *src_projs, long long src_batch_stride,
+                            int V, int B, float *rt_out) {
+    ProjParams p;
+    p.ref = ref_proj;
+    for (int v = 0; v < V; ++v) p.src.p[v] = src_projs[v];
+    p.out = rt_out; p.ref_stride = ref_batch_stride; p.src_stride = src_batch_stride; p.V = V; p.B = B;
+    emu::launch(dim3((V * B + 63) / 64), dim3(64), 0, [&] { relative_projection_kernel(p); });
+    return 0;
+}
+
+int emu_pack_nhwc(const float *const *maps, int n, int B, int C, int H, int W, float *out_nhwc) {
+    PackParams p;
+    for (int i = 0; i < n; ++i) p.maps.p[i] = maps[i];
+    p.out = out_nhwc; p.n = n; p.B = B; p.C = C; p.HW = H * W;
+    emu::launch(dim3((p.HW + 31) / 32, (C + 31) / 32, n * B), dim3(32, 8), 0, [&] { pack_nhwc_kernel(p); });
+    return 0;
+}
+
+int emu_photometric_confidence(const float *prob, float *out, int B, int D, int h, int w, int H_out, int W_out) {
+    const size_t total = (size_t)B * H_out * W_out;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [&] { photometric_confidence_kernel(prob, out, B, D, h, w, H_out, W_out); });
+    return 0;
+}
+
+int emu_upsample2x_add_nhwc(const float *x, const float *y, const float *bias, float *out, int N, int h, int w, int C) {
+    const size_t total = (size_t)N * 2 * h * 2 * w * (C / 4);
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [&] {
+        upsample2x_add_nhwc_kernel(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(bias),
+                                   reinterpret_cast<float4 *>(out), N, h, w, C / 4);
+    });
+    return 0;
+}
+
+int emu_aggregate_views(const float *sims, const float *vw, float *out, int V, int B, int G, int D, int H, int W) {
+    const size_t total = (size_t)B * G * D * H * W;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 7) blocks = 7;  // fewer CTAs than elements: exercises the grid-stride loop
+    emu::launch(dim3((unsigned)blocks), dim3(256), 0, [&] { aggregate_views_kernel(sims, vw, out, V, B, G * D, H * W); });
+    return 0;
+}
+
+int emu_aggregate_views_score(const float *sims, const float *vw, const pmb200_mlp *head, float *score, int stride, int V, int B, int G,
+                              int D, int H, int W) {
+    const MlpParams m = to_device_layout(head);
+    const size_t total = (size_t)B * D * H * W;
+    const unsigned blocks = (unsigned)((total + 127) / 128);
+    const int os = stride < 1 ? 1 : stride;
+    if (G == 8) emu::launch(dim3(blocks), dim3(128), 0, [&] { aggregate_score_kernel<8>(sims, vw, score, m, V, B, D, H * W, os); });
+    else if (G == 4) emu::launch(dim3(blocks), dim3(128), 0, [&] { aggregate_score_kernel<4>(sims, vw, score, m, V, B, D, H * W, os); });
+    else return -2;
+    return 0;
+}
+
+// generic (any C % G == 0) slow-path K-A: one thread per (batch, hypothesis, pixel)
+int emu_warp_corr_generic(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth, const float *vw, float *out,
+                          int V, int B, int C, int G, int H, int W, int Hs, int Ws, int D) {
+    WarpCorrParams p;
+    p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = vw; p.out = out;
+    p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
+    p.sx = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 1.0f;
+    p.sy = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 1.0f;
+    const size_t total = (size_t)B * D * H * W;
+    emu::launch(dim3((unsigned)((total + 127) / 128)), dim3(128), 0, [&] { warp_corr_generic_kernel(p, C, G); });
+    return 0;
+}
+
 }  // extern "C"

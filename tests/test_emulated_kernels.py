@@ -42,6 +42,17 @@ def emu():
     lib.emu_offset_corr.argtypes = [P, P, I, ctypes.POINTER(_native.MlpStruct), P] + [I] * 7
     lib.emu_offset_corr.restype = I
     F32 = ctypes.c_float
+    LL = ctypes.c_longlong
+    lib.emu_relative_projection.argtypes = [P, LL, P, LL, I, I, P]
+    lib.emu_pack_nhwc.argtypes = [P, I, I, I, I, I, P]
+    lib.emu_photometric_confidence.argtypes = [P, P] + [I] * 6
+    lib.emu_upsample2x_add_nhwc.argtypes = [P] * 4 + [I] * 4
+    lib.emu_aggregate_views.argtypes = [P] * 3 + [I] * 6
+    lib.emu_aggregate_views_score.argtypes = [P, P, ctypes.POINTER(_native.MlpStruct), P] + [I] * 7
+    lib.emu_warp_corr_generic.argtypes = [P] * 6 + [I] * 9
+    for fn in ("emu_relative_projection", "emu_pack_nhwc", "emu_photometric_confidence", "emu_upsample2x_add_nhwc", "emu_aggregate_views",
+               "emu_aggregate_views_score", "emu_warp_corr_generic"):
+        getattr(lib, fn).restype = I
     lib.emu_warp_corr_backward.argtypes = [P] * 8 + [I] * 9
     lib.emu_aggregate_views_backward.argtypes = [P] * 5 + [I] * 6
     lib.emu_offset_corr_backward.argtypes = [P] * 4 + [I] * 7
@@ -429,3 +440,91 @@ def test_emulated_adaptive_eval_backward(emu, D, K, dil, H, W, B, inverse):
         assert rc == 0
         for got, want, tol in zip((d_s, d_d, d_o, d_f), (s1.grad, d1.grad, o1.grad, f1.grad), (5e-5, 5e-5, 2e-4, 1e-4)):
             close(got, want, tol)
+
+
+# ------------------------------------------------------------------------------------------------
+# helper kernels
+# ------------------------------------------------------------------------------------------------
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def test_emulated_relative_projection_matches_inverse(emu):
+    Kc, Ec = synthetic.make_cameras(3, 5, 512, 640)
+    ref_proj, src_projs = synthetic.stage_projections(Kc, Ec, 2)  # views unbound from [B,N,4,4]: batch stride 5*16
+    rt = torch.full((len(src_projs), 3, 12), -1.0)
+    assert emu.emu_relative_projection(_ptr(ref_proj), ref_proj.stride(0), _ptr_array(src_projs), src_projs[0].stride(0), len(src_projs), 3, _ptr(rt)) == 0
+    want = _rt(ref_proj, src_projs)
+    for v in range(len(src_projs)):
+        assert maxabs(rt[v], want[v]) <= 1e-6 * float(want[v].abs().max())
+
+
+def test_emulated_pack_nhwc(emu):
+    maps = [torch.randn(2, 24, 7, 9) for _ in range(3)]
+    out = torch.full((3, 2, 7, 9, 24), -1.0)
+    assert emu.emu_pack_nhwc(_ptr_array(maps), 3, 2, 24, 7, 9, _ptr(out)) == 0
+    for i, m in enumerate(maps):
+        assert torch.equal(out[i], m.permute(0, 2, 3, 1))
+
+
+def test_emulated_photometric_confidence(emu):
+    g = torch.Generator().manual_seed(4)
+    for (B, D, h, w, H0, W0) in [(2, 8, 16, 20, 32, 40), (1, 8, 9, 7, 17, 15), (1, 5, 6, 6, 6, 6)]:
+        score = torch.softmax(torch.randn(B, D, h, w, generator=g) * 2.0, dim=1).contiguous()
+        sum4 = 4 * F.avg_pool3d(F.pad(score.unsqueeze(1), pad=(0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
+        idx = torch.sum(score * torch.arange(D, dtype=torch.float).view(1, D, 1, 1), dim=1).unsqueeze(1).long().clamp(0, D - 1)
+        want = F.interpolate(torch.gather(sum4, 1, idx), size=[H0, W0], mode="nearest").squeeze(1)
+        got = torch.full((B, H0, W0), -1.0)
+        assert emu.emu_photometric_confidence(_ptr(score), _ptr(got), B, D, h, w, H0, W0) == 0
+        bad = (got - want).abs() > 1e-5  # a pixel whose expectation sits on an integer may flip bins
+        assert float(bad.float().mean()) <= 0.002
+
+
+def test_emulated_upsample2x_add(emu):
+    for (N, C, h, w) in [(2, 32, 7, 9), (1, 16, 1, 3)]:
+        x = torch.randn(N, C, h, w)
+        y = torch.randn(N, C, 2 * h, 2 * w)
+        bias = torch.randn(C)
+        want = F.interpolate(x, scale_factor=2.0, mode="bilinear", align_corners=False) + y + bias.view(1, C, 1, 1)
+        out = torch.full((N, 2 * h, 2 * w, C), -1.0)
+        assert emu.emu_upsample2x_add_nhwc(_ptr(_aligned(nhwc(x))), _ptr(_aligned(nhwc(y))), _ptr(_aligned(bias)), _ptr(out), N, h, w, C) == 0
+        assert maxabs(out.permute(0, 3, 1, 2), want) <= 1e-5
+
+
+def test_emulated_aggregate_views_and_score(emu):
+    from patchmatchnet_b200.patchmatch import SimilarityNet
+
+    g = torch.Generator().manual_seed(8)
+    V, B, G, D, H, W = 3, 2, 8, 6, 5, 7
+    sims = torch.randn(V, B, G, D, H, W, generator=g)
+    vw = torch.rand(B, V, H, W, generator=g)
+    want = (sims * vw.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / (1e-5 + vw.sum(1))[:, None, None]
+    got = torch.full((B, G, D, H, W), -1.0)
+    assert emu.emu_aggregate_views(_ptr(sims), _ptr(vw), _ptr(got), V, B, G, D, H, W) == 0
+    assert maxabs(got, want) <= 2e-6 * float(want.abs().max())
+    with torch.no_grad():
+        head = _random_head(SimilarityNet, G, 1)
+        want_s = head(want)
+    xs = torch.full((B, D, H, W, 2), -7.0)
+    assert emu.emu_aggregate_views_score(_ptr(sims), _ptr(vw), head.folded(), xs.data_ptr() + 4, 2, V, B, G, D, H, W) == 0
+    assert bool((xs[..., 0] == -7.0).all()) and maxabs(xs[..., 1], want_s) <= 2e-5 * max(1.0, float(want_s.abs().max()))
+
+
+@pytest.mark.parametrize("C,G", [(24, 3), (32, 4)])
+def test_emulated_generic_warp_corr(emu, C, G):
+    B, V, H, W, D = 1, 2, 10, 12, 7
+    ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=C)
+    want = _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G)
+    rt = _rt(ref_proj, src_projs)
+    ref_n, src_n = nhwc(ref), torch.stack([nhwc(s) for s in srcs]).contiguous()
+    got = torch.full((V, B, G, D, H, W), -1.0)
+    assert emu.emu_warp_corr_generic(_ptr(ref_n), _ptr(src_n), _ptr(rt), _ptr(depth.contiguous()), None, _ptr(got), V, B, C, G, H, W, H, W, D) == 0
+    assert maxabs(got, want) <= 2e-5 * max(1.0, float(want.abs().max()))
+    wsum = 1e-5 + vw.sum(1)
+    want_f = (want * vw.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / wsum[:, None, None]
+    got_f = torch.full((B, G, D, H, W), -1.0)
+    assert emu.emu_warp_corr_generic(_ptr(ref_n), _ptr(src_n), _ptr(rt), _ptr(depth.contiguous()), _ptr(vw.contiguous()), _ptr(got_f), V, B, C, G, H, W, H, W, D) == 0
+    assert maxabs(got_f, want_f) <= 2e-5 * max(1.0, float(want.abs().max()))
