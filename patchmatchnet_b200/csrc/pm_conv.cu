@@ -148,15 +148,70 @@ __device__ __forceinline__ void stage_tile(const ConvParams &p, int tile, float 
     }
 }
 
+// The same copy with a FIXED column per thread, for halo rows of at most THREADS chunks (every layer the policy runs
+// natively except the 64-channel ones): thread -> (first row r0, chunk-in-row c) once, then it walks down the rows in steps
+// of THREADS / row_chunks.  Everything that depends on the column -- the pixel, the channel vector, the x bounds test, the
+// zero-stuffing parity, the shared and global column offsets -- leaves the loop; per chunk there remain the row bounds test,
+// one multiply-add for the global row and the copy (~8 instructions instead of ~22: staging was ~45 % of the issued
+// instructions of the 8-channel full-resolution layers, tools/sass_lines.py on profiles/r1_run23_ncu.md's kernels).
+template <bool VEC, bool STUFF, int THREADS>
+__device__ __forceinline__ void stage_tile_cols(const ConvParams &p, int tile, float *buf, int rows_per_tile) {
+    const int rows_per_iter = p.step_r[THREADS / 256];  // THREADS / row_chunks >= 1
+    const int r0 = (int)__umulhi(threadIdx.x, p.magic_row);
+    if (r0 >= rows_per_iter) return;  // the remainder threads of the last partial row group have no column
+    const int per_img = p.tiles_x * p.tiles_y;
+    const int n = tile / per_img, tt = tile - n * per_img;
+    const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+    const int ix0 = tx * 16 * p.S - p.pad, iy0 = ty * rows_per_tile * p.S - p.pad;
+    const unsigned Hv = STUFF ? 2 * p.H : p.H, Wv = STUFF ? 2 * p.W : p.W;
+    const float *img = p.x + (size_t)n * p.H * p.W * p.Cin;
+    const int c = (int)threadIdx.x - r0 * p.row_chunks;
+    const int rx = p.cpp_shift >= 0 ? (c >> p.cpp_shift) : (int)__umulhi((unsigned)c, p.magic_cpp);
+    const int v = (c - rx * p.cpp) * (VEC ? 4 : 1);  // first channel of this thread's chunk
+    int ix = ix0 + rx;
+    bool in_x = (unsigned)ix < Wv;
+    if (STUFF) {
+        in_x = in_x && (ix & 1) == 0;
+        ix >>= 1;
+    }
+    const unsigned gcol = in_x ? (unsigned)(ix * p.Cin + v) : 0u;
+    const unsigned grow = (unsigned)(p.W * p.Cin);
+    float *dst = buf + (r0 * p.rw + rx) * p.ps + v;
+    const int dstep = rows_per_iter * p.rw * p.ps;
+#pragma unroll 2
+    for (int r = r0; r < p.rh; r += rows_per_iter, dst += dstep) {
+        int iy = iy0 + r;
+        bool inside = in_x && (unsigned)iy < Hv;
+        if (STUFF) {
+            inside = inside && (iy & 1) == 0;
+            iy >>= 1;
+        }
+        const unsigned goff = inside ? (unsigned)iy * grow + gcol : 0u;
+        if (VEC) cp_async<16>(dst, img + goff, inside);
+        else cp_async<4>(dst, img + goff, inside);
+    }
+}
+
+// Not inlined: one copy of the eight staging variants per kernel instead of three (prologue, prefetch, single-buffer
+// path), and their address arithmetic does not inflate the register allocation of the MMA loop (the planner counts on
+// <= ~100 registers for 5 resident CTAs; inlined, the 8-channel register-filter kernel went from 96 to 118).
 template <int THREADS>
-__device__ __forceinline__ void stage_any(const ConvParams &p, int tile, float *buf, int rows_per_tile) {
+__device__ __noinline__ void stage_any(const ConvParams &p, int tile, float *buf, int rows_per_tile) {
+    const bool cols = p.step_r[THREADS / 256] >= 1;  // a halo row has at most THREADS chunks
     if (p.stuff) {
-        if ((p.Cin & 3) == 0) stage_tile<true, true, THREADS>(p, tile, buf, rows_per_tile);
-        else stage_tile<false, true, THREADS>(p, tile, buf, rows_per_tile);
+        if ((p.Cin & 3) == 0) {
+            if (cols) stage_tile_cols<true, true, THREADS>(p, tile, buf, rows_per_tile);
+            else stage_tile<true, true, THREADS>(p, tile, buf, rows_per_tile);
+        } else {
+            if (cols) stage_tile_cols<false, true, THREADS>(p, tile, buf, rows_per_tile);
+            else stage_tile<false, true, THREADS>(p, tile, buf, rows_per_tile);
+        }
     } else if ((p.Cin & 3) == 0) {
-        stage_tile<true, false, THREADS>(p, tile, buf, rows_per_tile);
+        if (cols) stage_tile_cols<true, false, THREADS>(p, tile, buf, rows_per_tile);
+        else stage_tile<true, false, THREADS>(p, tile, buf, rows_per_tile);
     } else {
-        stage_tile<false, false, THREADS>(p, tile, buf, rows_per_tile);
+        if (cols) stage_tile_cols<false, false, THREADS>(p, tile, buf, rows_per_tile);
+        else stage_tile<false, false, THREADS>(p, tile, buf, rows_per_tile);
     }
 }
 

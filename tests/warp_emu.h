@@ -34,6 +34,7 @@
 #undef __device__
 #undef __host__
 #undef __forceinline__
+#undef __noinline__
 #undef __shared__
 #undef __launch_bounds__
 #undef __align__
@@ -41,6 +42,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
