@@ -194,7 +194,9 @@ __device__ __forceinline__ void stage_tile_cols(const ConvParams &p, int tile, f
 
 // Not inlined: one copy of the eight staging variants per kernel instead of three (prologue, prefetch, single-buffer
 // path), and their address arithmetic does not inflate the register allocation of the MMA loop (the planner counts on
-// <= ~100 registers for 5 resident CTAs; inlined, the 8-channel register-filter kernel went from 96 to 118).
+// <= ~100 registers for 5 resident CTAs; inlined, the 8-channel register-filter kernel went from 96 to 118).  The kernel
+// takes its parameter block as __grid_constant__, so the reference handed to this function points into the parameter
+// space itself and no per-thread stack copy of the 176-byte block is made.
 template <int THREADS>
 __device__ __noinline__ void stage_any(const ConvParams &p, int tile, float *buf, int rows_per_tile) {
     const bool cols = p.step_r[THREADS / 256] >= 1;  // a halo row has at most THREADS chunks
@@ -221,7 +223,7 @@ __device__ __noinline__ void stage_any(const ConvParams &p, int tile, float *buf
 // groups per CTA that share one halo tile and split the output channels (NSPLIT * NT tiles in all): the layers with
 // few pixels and many channels get twice the warps per tile without staging the halo twice.
 template <int KCIN, int NT, int MT, int PREC, bool WREG, int NSPLIT>
-__global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const __grid_constant__ ConvParams p) {
 #if defined(PM_EMU)
     float *s_in = static_cast<float *>(emu::dyn_smem());
 #else

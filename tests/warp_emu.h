@@ -35,6 +35,7 @@
 #undef __host__
 #undef __forceinline__
 #undef __noinline__
+#undef __grid_constant__
 #undef __shared__
 #undef __launch_bounds__
 #undef __align__
@@ -43,6 +44,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __noinline__
+#define __grid_constant__
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
