@@ -464,7 +464,9 @@ struct DeviceInfo {
 // SM count of the current device (cached per device; benign race: every writer stores the same value)
 int sm_count(int dev) {
     static DeviceInfo info[64];
+#if !defined(PM_EMU)  // (the emulation build re-reads its pretend SM count every call)
     if (dev >= 0 && dev < 64 && info[dev].sms > 0) return info[dev].sms;
+#endif
     int n = 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
     if (dev >= 0 && dev < 64) info[dev].sms = n;

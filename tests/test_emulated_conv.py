@@ -82,6 +82,22 @@ def test_emulated_source_matches_conv2d(emu_conv, name):
             assert err <= tol, f"{name} precision {prec} rows_per_warp {mt}: scaled max err {err:.3e}"
 
 
+@pytest.mark.parametrize("name", ["feature.conv0", "feature.conv1", "feature.conv2", "feature.conv3", "feature.conv9", "stage1.eval_conv"])
+def test_emulated_persistent_double_buffered_path(emu_conv, name, monkeypatch):
+    """On a pretend 1-SM device the planner gives the same small map several tiles per CTA and two halo buffers: the
+    persistent loop with the next tile's prefetch in flight (what every full-size layer runs on the B200)."""
+    monkeypatch.setenv("PM_EMU_SMS", "1")
+    cin, cout, ks, S, pad, dil, relu = LAYERS[name]
+    g = torch.Generator().manual_seed(sum(map(ord, name)) + 1)
+    N, H, W = 2, 29, 37
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    b = torch.randn(cout, generator=g)
+    want = _ref_conv(x, w, b, S, pad, dil, relu)
+    got = _run(emu_conv, x, ops.pack_conv_filter(w, 3), b, cout, ks, S, pad, dil, relu=relu, prec=3, mt=0)
+    assert _scaled_err(got, want) <= 2e-5
+
+
 def test_emulated_transposed_conv_and_channel_slices(emu_conv):
     g = torch.Generator().manual_seed(5)
     low = torch.randn(2, 8, 11, 19, generator=g)
