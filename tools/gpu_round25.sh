@@ -15,6 +15,7 @@ echo "bench exit $? at $(( $(date +%s) - t0 )) s" >> gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 timeout 600 python tools/kbench.py > gpurun_out/kbench.json 2> gpurun_out/kbench.err          # full K-A / K-B sweeps
 timeout 600 python tools/convbench.py > gpurun_out/convbench.json 2> gpurun_out/convbench.err  # per-layer native vs cuDNN
+PMB200_CONV_T=1 timeout 600 python tools/convbench.py > gpurun_out/convbench_transposed.json 2> gpurun_out/convbench_transposed.err
 timeout 120 python tools/geobench.py > gpurun_out/geobench.json 2> gpurun_out/geobench.err
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches.csv python tools/profile_forward.py > gpurun_out/launches.log 2>&1
