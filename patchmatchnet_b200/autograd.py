@@ -57,7 +57,7 @@ class WarpCorr(torch.autograd.Function):
         D = depth.shape[1]
         d_ref = torch.empty_like(ref)
         d_src = torch.empty_like(src)
-        with torch.cuda.device(ref.device):
+        with ops._device_guard(ref):
             rc = _native.lib().pmb200_warp_corr_backward(
                 ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), _ptr(vw), g.data_ptr(),
                 d_ref.data_ptr(), d_src.data_ptr(), V, B, C, ctx.G, H, W, Hs, Ws, D, ops._stream(ref),
@@ -81,7 +81,7 @@ class AggregateViews(torch.autograd.Function):
         V, B, G, D, H, W = sims.shape
         d_sims = torch.empty_like(sims)
         d_vw = torch.empty_like(vw)
-        with torch.cuda.device(sims.device):
+        with ops._device_guard(sims):
             rc = _native.lib().pmb200_aggregate_views_backward(
                 sims.data_ptr(), vw.data_ptr(), g.data_ptr(), d_sims.data_ptr(), d_vw.data_ptr(), V, B, G, D, H, W,
                 ops._stream(sims),
@@ -106,7 +106,7 @@ class OffsetCorr(torch.autograd.Function):
         g = g.contiguous()
         B, H, W, C = ref.shape
         d_off = torch.empty_like(off)
-        with torch.cuda.device(ref.device):
+        with ops._device_guard(ref):
             rc = _native.lib().pmb200_offset_corr_backward(
                 ref.data_ptr(), off.data_ptr(), g.data_ptr(), d_off.data_ptr(), B, C, G, H, W, K, dilation, ops._stream(ref)
             )
@@ -134,7 +134,7 @@ class InitPropagate(torch.autograd.Function):
         g = g_hyp.contiguous()
         B, _, H, W = seed.shape
         d_off = torch.empty_like(off)
-        with torch.cuda.device(seed.device):
+        with ops._device_guard(seed):
             rc = _native.lib().pmb200_init_propagate_backward(
                 seed.data_ptr(), off.data_ptr(), dmin.data_ptr(), dmax.data_ptr(), g.data_ptr(), d_off.data_ptr(),
                 mode, B, H, W, Ns, Kp, dilation, scale, ops._stream(seed),
@@ -170,7 +170,7 @@ class AdaptiveEval(torch.autograd.Function):
         d_hyp = torch.empty_like(hyp)
         d_off = torch.empty_like(off)
         d_fw = torch.empty_like(fw)
-        with torch.cuda.device(score0.device):
+        with ops._device_guard(score0):
             rc = _native.lib().pmb200_adaptive_eval_backward(
                 score0.data_ptr(), hyp.data_ptr(), xnorm.data_ptr(), off.data_ptr(), fw.data_ptr(), dmin.data_ptr(),
                 dmax.data_ptr(), prob.data_ptr(), _ptr(g_depth), _ptr(g_prob), d_score0.data_ptr(), d_hyp.data_ptr(),

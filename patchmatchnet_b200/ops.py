@@ -18,8 +18,19 @@ from . import _native
 Tensor = torch.Tensor
 
 
+def _on_device(t: Tensor) -> bool:
+    """The one place that decides whether a tensor may be handed to the native library.  (tests/emu_backend.py replaces
+    this, `_device_guard` and `_stream` to run the wrappers against the CPU-emulated kernels; the product has no such path.)"""
+    return t.is_cuda
+
+
+def _device_guard(t: Tensor):
+    """Context that makes `t`'s GPU current for the duration of a native call."""
+    return torch.cuda.device(t.device)
+
+
 def _require(t: Tensor, name: str, ndim: Optional[int] = None) -> Tensor:
-    if not t.is_cuda:
+    if not _on_device(t):
         raise RuntimeError(f"{name}: the B200 path needs a CUDA tensor (got {t.device}); there is no CPU fallback")
     if t.dtype != torch.float32:
         raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
@@ -31,7 +42,7 @@ def _require(t: Tensor, name: str, ndim: Optional[int] = None) -> Tensor:
 def _offsets_arg(off: Tensor, shape, name: str):
     """(tensor, channels_last flag) for a raw offset-conv output: planar NCHW memory or channels-last memory are both
     consumed in place; anything else is made NCHW-contiguous."""
-    if not off.is_cuda or off.dtype != torch.float32:
+    if not _on_device(off) or off.dtype != torch.float32:
         raise RuntimeError(f"{name}: offsets must be a CUDA float32 tensor (got {off.dtype} on {off.device}); there is no CPU fallback")
     if tuple(off.shape) != tuple(shape):
         raise RuntimeError(f"{name}: offsets must be {tuple(shape)}, got {tuple(off.shape)}")
@@ -48,7 +59,7 @@ def _stream(t: Tensor) -> int:
 
 def _rowmajor_4x4(m: Tensor, name: str) -> Tensor:
     """[B,4,4] with contiguous 4x4 blocks; the batch stride may be anything (torch.unbind views)."""
-    if not m.is_cuda or m.dtype != torch.float32 or m.dim() != 3 or m.shape[1:] != (4, 4):
+    if not _on_device(m) or m.dtype != torch.float32 or m.dim() != 3 or m.shape[1:] != (4, 4):
         raise RuntimeError(f"{name}: expected a CUDA float32 [B,4,4] tensor, got {m.dtype} {tuple(m.shape)} on {m.device}")
     if m.stride(1) != 4 or m.stride(2) != 1:
         m = m.contiguous()
@@ -67,7 +78,7 @@ def relative_projection(ref_proj: Tensor, src_projs: Sequence[Tensor]) -> Tensor
         mats = [m.contiguous() for m in mats]
     out = torch.empty((V, B, 12), dtype=torch.float32, device=ref.device)
     arr, keep = _native.pointer_array([m.data_ptr() for m in mats])
-    with torch.cuda.device(ref.device):
+    with _device_guard(ref):
         rc = _native.lib().pmb200_relative_projection(
             ref.data_ptr(), ref.stride(0), arr, mats[0].stride(0), V, B, out.data_ptr(), _stream(ref)
         )
@@ -103,7 +114,7 @@ def pack_nhwc(maps: Sequence[Tensor]) -> Tensor:
             raise RuntimeError("pack_nhwc: maps must share one shape")
     out = torch.empty((len(srcs), B, H, W, C), dtype=torch.float32, device=first.device)
     arr, keep = _native.pointer_array([m.data_ptr() for m in srcs])
-    with torch.cuda.device(first.device):
+    with _device_guard(first):
         rc = _native.lib().pmb200_pack_nhwc(arr, len(srcs), B, C, H, W, out.data_ptr(), _stream(first))
     _native.check(rc, "pack_nhwc")
     return out
@@ -114,7 +125,7 @@ def photometric_confidence(prob: Tensor, out_h: int, out_w: int) -> Tensor:
     pr = _require(prob, "prob", 4)
     B, D, h, w = pr.shape
     out = torch.empty((B, out_h, out_w), dtype=torch.float32, device=pr.device)
-    with torch.cuda.device(pr.device):
+    with _device_guard(pr):
         rc = _native.lib().pmb200_photometric_confidence(pr.data_ptr(), out.data_ptr(), B, D, h, w, out_h, out_w, _stream(pr))
     _native.check(rc, "photometric_confidence")
     return out
@@ -126,7 +137,7 @@ def upsample2x_add(x: Tensor, y: Tensor, bias: Optional[Tensor] = None) -> Tenso
     if y.shape != (N, C, 2 * h, 2 * w):
         raise RuntimeError("upsample2x_add: y must be [N,C,2h,2w]")
     for t, nm in ((x, "x"), (y, "y")):
-        if not t.is_cuda or t.dtype != torch.float32:
+        if not _on_device(t) or t.dtype != torch.float32:
             raise RuntimeError(f"upsample2x_add: {nm} must be a CUDA float32 tensor (no CPU fallback)")
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
@@ -139,7 +150,7 @@ def upsample2x_add(x: Tensor, y: Tensor, bias: Optional[Tensor] = None) -> Tenso
             raise RuntimeError("upsample2x_add: bias must have C elements")
         b_ptr = bias.data_ptr()
     out = torch.empty_like(y, memory_format=torch.channels_last)
-    with torch.cuda.device(x.device):
+    with _device_guard(x):
         rc = _native.lib().pmb200_upsample2x_add_nhwc(x.data_ptr(), y.data_ptr(), b_ptr, out.data_ptr(), N, h, w, C, _stream(x))
     _native.check(rc, "upsample2x_add_nhwc")
     return out
@@ -221,7 +232,7 @@ def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: in
     channels-last memory (made so if not); returns a logical-NCHW channels-last tensor [N,cout,Ho,Wo], or writes the
     channels out_channel_offset..+cout of `out` (a wider channels-last tensor: concat fusion) and returns `out`.
     `add_up2x`: a coarser channels-last map [N,cout,Ho/2,Wo/2] whose bilinear x2 upsample is added in the epilogue."""
-    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
+    if not _on_device(x) or x.dtype != torch.float32 or x.dim() != 4:
         raise RuntimeError(f"conv2d_nhwc: x must be a 4-D CUDA float32 tensor (got {x.dtype} {tuple(x.shape)} on {x.device}); no CPU fallback")
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
@@ -229,7 +240,7 @@ def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: in
     prec = conv_precision() if precision is None else precision
     up_ptr = None
     if add_up2x is not None:
-        if (not add_up2x.is_cuda or add_up2x.dtype != torch.float32 or add_up2x.dim() != 4
+        if (not _on_device(add_up2x) or add_up2x.dtype != torch.float32 or add_up2x.dim() != 4
                 or not add_up2x.is_contiguous(memory_format=torch.channels_last)):
             raise RuntimeError("conv2d_nhwc: add_up2x must be a channels-last CUDA float32 tensor")
         up_ptr = add_up2x.data_ptr()
@@ -256,7 +267,7 @@ def conv2d_nhwc(x: Tensor, filter_frag: Tensor, bias: Optional[Tensor], cout: in
         if bias.numel() != cout:
             raise RuntimeError("conv2d_nhwc: bias must have Cout elements")
         b_ptr = bias.data_ptr()
-    with torch.cuda.device(x.device):
+    with _device_guard(x):
         rc = _native.lib().pmb200_conv2d_nhwc(
             x.data_ptr(), filter_frag.data_ptr(), b_ptr, up_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride, pad, dil,
             1 if relu else 0, prec, 1 if transposed2x else 0, ycs, yco, rows_per_warp, _stream(x),
@@ -290,7 +301,7 @@ def warp_corr(
     else:
         out = torch.empty((V, B, G, D, H, W), dtype=torch.float32, device=ref.device)
         vw_ptr = None
-    with torch.cuda.device(ref.device):
+    with _device_guard(ref):
         rc = _native.lib().pmb200_warp_corr(
             ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), vw_ptr, out.data_ptr(),
             V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
@@ -330,7 +341,7 @@ def warp_corr_score(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth: Tenso
     if vw.shape != (B, V, H, W):
         raise RuntimeError("warp_corr_score: view_weights must be [B,V,H,W]")
     out, out_ptr, stride = _score_target(xs, B, D, H, W, ref.device)
-    with torch.cuda.device(ref.device):
+    with _device_guard(ref):
         rc = _native.lib().pmb200_warp_corr_score(
             ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), vw.data_ptr(), head, out_ptr, stride,
             V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
@@ -346,7 +357,7 @@ def warp_corr_view_weights(ref_nhwc: Tensor, src_nhwc: Tensor, rt: Tensor, depth
     ref, src, rt, depth, (V, B, C, H, W, Hs, Ws, D) = _warp_args(ref_nhwc, src_nhwc, rt, depth)
     out = torch.empty((B, V, H, W), dtype=torch.float32, device=ref.device)
     sims = torch.empty((V, B, G, D, H, W), dtype=torch.float32, device=ref.device) if keep_sims else None
-    with torch.cuda.device(ref.device):
+    with _device_guard(ref):
         rc = _native.lib().pmb200_warp_corr_view_weights(
             ref.data_ptr(), src.data_ptr(), rt.data_ptr(), depth.data_ptr(), head, out.data_ptr(),
             None if sims is None else sims.data_ptr(), V, B, C, G, H, W, Hs, Ws, D, _stream(ref),
@@ -363,7 +374,7 @@ def aggregate_views_score(sims: Tensor, view_weights: Tensor, head: "_native.Mlp
     if vw.shape != (B, V, H, W):
         raise RuntimeError("aggregate_views_score: view_weights must be [B,V,H,W]")
     out, out_ptr, stride = _score_target(xs, B, D, H, W, sims.device)
-    with torch.cuda.device(sims.device):
+    with _device_guard(sims):
         rc = _native.lib().pmb200_aggregate_views_score(
             sims.data_ptr(), vw.data_ptr(), head, out_ptr, stride, V, B, G, D, H, W, _stream(sims)
         )
@@ -377,7 +388,7 @@ def offset_corr_weight(ref_nhwc: Tensor, offsets: Tensor, G: int, K: int, dilati
     B, H, W, C = ref.shape
     off, off_cl = _offsets_arg(offsets, (B, 2 * K, H, W), "offset_corr_weight")
     out = torch.empty((B, K, H, W), dtype=torch.float32, device=ref.device)
-    with torch.cuda.device(ref.device):
+    with _device_guard(ref):
         rc = _native.lib().pmb200_offset_corr_weight(
             ref.data_ptr(), off.data_ptr(), off_cl, head, out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
         )
@@ -396,7 +407,7 @@ def aggregate_views(sims: Tensor, view_weights: Tensor) -> Tensor:
     if vw.shape != (B, V, H, W):
         raise RuntimeError("aggregate_views: view_weights must be [B,V,H,W]")
     out = torch.empty((B, G, D, H, W), dtype=torch.float32, device=sims.device)
-    with torch.cuda.device(sims.device):
+    with _device_guard(sims):
         rc = _native.lib().pmb200_aggregate_views(
             sims.data_ptr(), vw.data_ptr(), out.data_ptr(), V, B, G, D, H, W, _stream(sims)
         )
@@ -410,7 +421,7 @@ def offset_corr(ref_nhwc: Tensor, offsets: Tensor, G: int, K: int, dilation: int
     B, H, W, C = ref.shape
     off, off_cl = _offsets_arg(offsets, (B, 2 * K, H, W), "offset_corr")
     out = torch.empty((B, G, K, H, W), dtype=torch.float32, device=ref.device)
-    with torch.cuda.device(ref.device):
+    with _device_guard(ref):
         rc = _native.lib().pmb200_offset_corr(
             ref.data_ptr(), off.data_ptr(), off_cl, out.data_ptr(), B, C, G, H, W, K, dilation, _stream(ref)
         )
@@ -457,13 +468,13 @@ def init_propagate(
         off_ptr = off.data_ptr()
     out = torch.empty((B, Ns + Kp, H, W), dtype=torch.float32, device=seed.device)
     if xs is not None:
-        if xs.shape != (B, Ns + Kp, H, W, 2) or not xs.is_contiguous() or xs.dtype != torch.float32 or not xs.is_cuda:
+        if xs.shape != (B, Ns + Kp, H, W, 2) or not xs.is_contiguous() or xs.dtype != torch.float32 or not _on_device(xs):
             raise RuntimeError("init_propagate: xs must be a contiguous CUDA float32 [B,Ns+Kp,H,W,2] buffer")
         xn, xn_ptr, xstride = None, xs.data_ptr(), 2
     else:
         xn = torch.empty_like(out) if with_xnorm else None
         xn_ptr, xstride = (None if xn is None else xn.data_ptr()), 1
-    with torch.cuda.device(seed.device):
+    with _device_guard(seed):
         rc = _native.lib().pmb200_init_propagate(
             seed.data_ptr(), off_ptr, off_cl, dmin.data_ptr(), dmax.data_ptr(), out.data_ptr(), xn_ptr, xstride,
             mode, B, H, W, Ns, Kp, dilation, float(interval_scale), _stream(seed),
@@ -490,7 +501,7 @@ def adaptive_eval(
     """K-B.  -> (depth [B,H,W], prob [B,D,H,W]).  xnorm: normalised inverse depth from init_propagate.
     With `xs` (interleaved (xnorm, score) buffer) `score0` is ignored and may be None."""
     if xs is not None:
-        if xs.dim() != 5 or xs.shape[-1] != 2 or not xs.is_contiguous() or not xs.is_cuda or xs.dtype != torch.float32:
+        if xs.dim() != 5 or xs.shape[-1] != 2 or not xs.is_contiguous() or not _on_device(xs) or xs.dtype != torch.float32:
             raise RuntimeError("adaptive_eval: xs must be a contiguous CUDA float32 [B,D,H,W,2] buffer")
         score0 = xs[..., 1]  # shape carrier only; never made contiguous below
         sc = score0
@@ -513,7 +524,7 @@ def adaptive_eval(
         xn_ptr = xn.data_ptr()
     prob = torch.empty((B, D, H, W), dtype=torch.float32, device=sc.device)
     depth = torch.empty((B, H, W), dtype=torch.float32, device=sc.device)
-    with torch.cuda.device(sc.device):
+    with _device_guard(sc):
         rc = _native.lib().pmb200_adaptive_eval(
             None if xs is not None else sc.data_ptr(), ds.data_ptr(), xn_ptr, None if xs is None else xs.data_ptr(), off.data_ptr(), off_cl, fw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
             prob.data_ptr(), depth.data_ptr(), B, D, H, W, K, dilation, float(interval_scale),
@@ -560,7 +571,7 @@ def geometric_filter(ref_depth: Tensor, confidence: Tensor, src_depths: Tensor, 
     photo = torch.empty((H, W), dtype=torch.uint8, device=ref.device)
     final = torch.empty((H, W), dtype=torch.uint8, device=ref.device)
     avg = torch.empty((H, W), dtype=torch.float64, device=ref.device)
-    with torch.cuda.device(ref.device):
+    with _device_guard(ref):
         rc = _native.lib().pmb200_geometric_filter(
             ref.data_ptr(), conf.data_ptr(), src.data_ptr(), cams.data_ptr(), V, H, W, Hs, Ws, float(geo_pixel_thres),
             float(geo_depth_thres), float(photo_thres), int(geo_mask_thres), mask_sum.data_ptr(), photo.data_ptr(),

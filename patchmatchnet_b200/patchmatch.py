@@ -405,7 +405,7 @@ class PatchMatch(nn.Module):
             assert (
                 len(src_features) == view_weights.size()[1]
             ), "Patchmatch Evaluation: Different number of images and view weights"
-        if not ref_feature.is_cuda:
+        if not ops._on_device(ref_feature):
             raise RuntimeError(
                 "patchmatchnet_b200.PatchMatch runs on CUDA (sm_100a) only; there is no CPU fallback "
                 f"(got a tensor on {ref_feature.device})"

@@ -1,0 +1,103 @@
+"""Whole PatchMatch stages on the CPU box: the package's REAL host code (ops wrappers + PatchMatch._forward_eager, the
+orchestration that otherwise only ever runs on the GPU) driving the CPU-emulated kernels through tests/emu_backend.py,
+against the oracle and the reference-generated golden outputs -- the CPU twin of the GPU stage tests.  Tolerance as there:
+depth rel-L1 <= 1e-4 (north_star allows 1e-3)."""
+import pytest
+import torch
+
+from oracle import pm_oracle
+from patchmatchnet_b200 import PatchMatch, ops
+from tests import emu_backend, pm_cases
+from tests.test_emulated_conv import emu_conv  # noqa: F401  (fixtures)
+from tests.test_emulated_kernels import emu  # noqa: F401
+
+NAMES = ("ref_feature", "src_features", "ref_proj", "src_projs", "depth_min", "depth_max", "depth", "view_weights")
+
+
+def _aligned_like(t):
+    """contiguous copy whose storage is 32-byte aligned (the feature packs are read with 256-bit loads)"""
+    buf = torch.empty(t.numel() + 8, dtype=t.dtype)
+    shift = (-buf.data_ptr() // t.element_size()) % 8
+    out = buf[shift:shift + t.numel()].view(t.shape)
+    out.copy_(t)
+    return out
+
+
+@pytest.fixture()
+def backend(monkeypatch, emu, emu_conv):  # noqa: F811
+    real_pack = ops.pack_nhwc
+    facade = emu_backend.install(monkeypatch, emu, emu_conv)
+    # torch's CPU allocator gives 64-byte alignment, but be explicit about the contract of the gather loads
+    monkeypatch.setattr(ops, "pack_nhwc", lambda maps: _aligned_like(real_pack(maps)))
+    return facade
+
+
+@pytest.mark.parametrize("name", list(pm_cases.STAGE_CASES))
+@pytest.mark.parametrize("fused", [True, False])
+def test_native_stage_on_emulated_kernels_matches_oracle(backend, golden_weights, name, fused):
+    spec = pm_cases.STAGE_CASES[name]
+    stage = spec["stage"]
+    case = pm_cases.make_stage_inputs(spec)
+    state = pm_cases.stage_state(golden_weights, stage)
+    mine = PatchMatch(**pm_cases.stage_ctor_kwargs(stage))
+    mine.load_state_dict(state, strict=True)
+    mine = mine.eval()
+    mine.fuse_heads = fused
+    orc = pm_oracle.PatchMatchOracle(**pm_cases.stage_ctor_kwargs(stage))
+    orc.load_state_dict(state, strict=True)
+    orc.eval()
+    kw = {k: case[k] for k in NAMES}
+    u = torch.rand(kw["ref_feature"].shape[0], 48, *kw["ref_feature"].shape[2:], generator=torch.Generator().manual_seed(3))
+    mine.rand_source = lambda size, device: u  # one shared draw for the random initialisation
+    orc.rand_source = lambda size, device: u
+    with torch.no_grad():
+        want = orc(**kw)
+        got = mine(**kw)
+    assert len(got[0]) == len(want[0])
+    for a, b in zip(got[0], want[0]):
+        assert a.shape == b.shape and pm_cases.rel_l1(a, b) <= 1e-4
+    assert float((got[2] - want[2]).abs().max()) <= 1e-4  # view weights
+    # probabilities: a hypothesis that sits on a bilinear cell boundary moves a little probability mass at single pixels
+    # (the GPU stage tests bound the maximum by 2e-3 against the golden outputs; the emulated build differs from the GPU
+    # in the last bits -- exact division instead of the fast reciprocal -- so bound the mean tightly and the maximum loosely)
+    dp = (got[1] - want[1]).abs()
+    assert float((got[1].sum(1) - 1.0).abs().max()) <= 1e-5 and float(dp.mean()) <= 2e-5 and float(dp.max()) <= 5e-3
+
+
+def test_native_network_on_emulated_kernels_matches_oracle(backend, golden_weights, monkeypatch):
+    """The whole cascade -- FeatureNet (native channels-last convs with folded BatchNorm, composed top-down heads, fused
+    upsample-add), three PatchMatch stages, Refinement, photometric confidence -- through the package's inference fast path
+    (the code that otherwise needs the GPU), every hand-written kernel emulated, against the oracle network on the CPU."""
+    from patchmatchnet_b200 import net as native_net, synthetic
+    from patchmatchnet_b200.net import PatchmatchNet, load_reference_state
+
+    monkeypatch.setattr(native_net, "_fast", lambda x: True)
+    monkeypatch.setattr(native_net, "_FUSED_CONV_RELU", False)  # the FLOP-bound layers stay library convs: plain conv2d + relu here
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)  # native convs in the fp32-accurate 3xTF32 mode
+    kw = dict(synthetic.DEFAULT_NET_KWARGS)
+    mine = PatchmatchNet(**kw)
+    load_reference_state(mine, golden_weights)
+    mine = mine.eval()
+    orc = PatchmatchNet(**kw, patchmatch_cls=pm_oracle.PatchMatchOracle)
+    load_reference_state(orc, golden_weights)
+    orc = orc.eval()
+    inp = synthetic.make_inputs(1, 3, 48, 64, seed=5)
+    u = torch.rand(1, 48, 6, 8, generator=torch.Generator().manual_seed(9))
+    for net in (mine, orc):
+        net.patchmatch_3.rand_source = lambda size, device: u
+    args = lambda: (list(inp["images"]), inp["intrinsics"].clone(), inp["extrinsics"], inp["depth_min"], inp["depth_max"])
+    with torch.no_grad():
+        monkeypatch.setattr(native_net, "_fast", lambda x: False)  # the oracle network: plain torch ops
+        want_depth, want_conf, _ = orc(*args())
+        monkeypatch.setattr(native_net, "_fast", lambda x: True)
+        got_depth, got_conf, stages = mine(*args())
+    assert got_depth.shape == want_depth.shape and pm_cases.rel_l1(got_depth, want_depth) <= 2e-4
+    assert float(((got_conf - want_conf).abs() > 1e-3).float().mean()) <= 0.01  # the regressed index truncates to an integer
+    assert sorted(stages) == [0, 1, 2, 3]
+    n = backend.calls
+    # the launches of one fused inference forward (DESIGN.md "Launches per forward"): 3 projections, 3 K-A'+head, 5 K-C,
+    # 1 K-A view weights, 1 aggregate+head, 4 K-A+head, 5 K-B, the native convs, the confidence tail
+    assert n.get("pmb200_relative_projection") == 3 and n.get("pmb200_offset_corr_weight") == 3 and n.get("pmb200_init_propagate") == 5
+    assert n.get("pmb200_warp_corr_view_weights") == 1 and n.get("pmb200_aggregate_views_score") == 1
+    assert n.get("pmb200_warp_corr_score") == 4 and n.get("pmb200_adaptive_eval") == 5 and n.get("pmb200_photometric_confidence") == 1
+    assert n.get("pmb200_conv2d_nhwc", 0) >= 12, n
