@@ -414,6 +414,7 @@ class PatchmatchNet(nn.Module):
             x = torch.cat(images, dim=0)
         if _fast(x):  # cuDNN NHWC kernels; the pyramid then comes out channels-last, which is the layout
             x = x.contiguous(memory_format=torch.channels_last)  # the fused PatchMatch kernels read in place
+            self._ref_image_cl = x[:b]  # the reference view, already channels-last: Refinement reads it without a second conversion
         stacked = self.feature(x)
         return [{k: v[i * b:(i + 1) * b] for k, v in stacked.items()} for i in range(n)]
 
@@ -432,8 +433,12 @@ class PatchmatchNet(nn.Module):
         ref_image = images[0]
         Hr, Wr = ref_image.shape[-2:]
 
+        self._ref_image_cl = None
         feats = self.extract_features(images)
         ref_feat, src_feats = feats[0], feats[1:]
+        if self._ref_image_cl is not None:  # same values as ref_image, channels-last memory (eval fast path only)
+            ref_image = self._ref_image_cl
+            self._ref_image_cl = None
         depth_min = depth_min.float()
         depth_max = depth_max.float()
 
