@@ -9,7 +9,7 @@ reference feature (patchmatch.py:475).  The 1x1x1 heads stay ordinary torch modu
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import torch
 

@@ -14,7 +14,7 @@ There is no CPU path: construction fails without CUDA.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import torch
 

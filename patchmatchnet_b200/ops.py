@@ -9,7 +9,7 @@ an error (there is no fallback path).
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

@@ -8,8 +8,6 @@ configurations mirror the defaults of the launchers in csrc/pm_kernels.cu."""
 import contextlib
 import ctypes
 
-import torch
-
 from patchmatchnet_b200 import _native, ops
 
 

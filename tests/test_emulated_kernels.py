@@ -10,7 +10,6 @@ import ctypes
 import os
 import subprocess
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
