@@ -87,6 +87,24 @@ class EmulatedLibrary:
         return self.emu.emu_adaptive_eval(score0, depth, xnorm, xs, off, off_cl, fw, dmin, dmax, prob, depth_out, B, D, H, W, K,
                                           dilation, scale, is_inverse, 16, min(D, 16))
 
+    # ---- backward kernels (training configuration; patchmatchnet_b200/autograd.py) ----
+    def pmb200_warp_corr_backward(self, ref, src, rt, depth, vw, g, d_ref, d_src, V, B, C, G, H, W, Hs, Ws, D, stream):
+        return self.emu.emu_warp_corr_backward(ref, src, rt, depth, vw, g, d_ref, d_src, V, B, C, G, H, W, Hs, Ws, D)
+
+    def pmb200_aggregate_views_backward(self, sims, vw, g, d_sims, d_vw, V, B, G, D, H, W, stream):
+        return self.emu.emu_aggregate_views_backward(sims, vw, g, d_sims, d_vw, V, B, G, D, H, W)
+
+    def pmb200_offset_corr_backward(self, ref, off, g, d_off, B, C, G, H, W, K, dilation, stream):
+        return self.emu.emu_offset_corr_backward(ref, off, g, d_off, B, C, G, H, W, K, dilation)
+
+    def pmb200_init_propagate_backward(self, seed, off, dmin, dmax, g, d_off, mode, B, H, W, Ns, Kp, dilation, scale, stream):
+        return self.emu.emu_init_propagate_backward(seed, off, dmin, dmax, g, d_off, mode, B, H, W, Ns, Kp, dilation, scale)
+
+    def pmb200_adaptive_eval_backward(self, score0, hyp, xnorm, off, fw, dmin, dmax, prob, g_depth, g_prob, d_score0, d_hyp, d_off, d_fw,
+                                      B, D, H, W, K, dilation, scale, inverse, stream):
+        return self.emu.emu_adaptive_eval_backward(score0, hyp, xnorm, off, fw, dmin, dmax, prob, g_depth, g_prob, d_score0, d_hyp, d_off,
+                                                   d_fw, B, D, H, W, K, dilation, scale, inverse)
+
     def pmb200_conv2d_filter_floats(self, cin, cout, ks, prec):
         return self.conv.emu_conv2d_filter_floats(cin, cout, ks, prec)
 

@@ -101,3 +101,68 @@ def test_native_network_on_emulated_kernels_matches_oracle(backend, golden_weigh
     assert n.get("pmb200_warp_corr_view_weights") == 1 and n.get("pmb200_aggregate_views_score") == 1
     assert n.get("pmb200_warp_corr_score") == 4 and n.get("pmb200_adaptive_eval") == 5 and n.get("pmb200_photometric_confidence") == 1
     assert n.get("pmb200_conv2d_nhwc", 0) >= 12, n
+
+
+# ------------------------------------------------------------------------------------------------
+# training configuration: native forward + native backward kernels behind patchmatchnet_b200.autograd, on the CPU box
+# ------------------------------------------------------------------------------------------------
+
+
+def _close(got, want, tol):
+    got, want = got.detach().double(), want.detach().double()
+    scale = max(1e-12, float(want.abs().max()))
+    err = float((got - want).abs().max())
+    assert got.shape == want.shape and err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e}"
+
+
+def _compare_param_grads(mine, want, rtol, atol_of_global):
+    assert set(mine) == set(want)
+    glob = max(float(w.abs().max()) for w in want.values() if w is not None)
+    bad = []
+    for k, w in want.items():
+        if w is None:  # parameters the reference graph never reaches
+            assert mine[k] is None or float(mine[k].abs().max()) == 0.0, k
+            continue
+        assert mine[k] is not None, k
+        err = float((mine[k].double() - w.double()).abs().max())
+        if err > rtol * float(w.abs().max()) + atol_of_global * glob:
+            bad.append((k, err, float(w.abs().max())))
+    assert not bad, f"global grad scale {glob:.3e}; offenders: {bad[:8]}"
+
+
+@pytest.mark.parametrize("name", list(pm_cases.STAGE_CASES))
+def test_native_stage_training_gradients_on_emulated_kernels(backend, golden_weights, name):
+    """train() mode, loss = sum of smooth-L1 of every iteration's depth (reference net.py:336-342): parameter and
+    input-feature gradients of the native path (autograd bridges over the emulated backward kernels) against torch autograd
+    on the oracle -- the CPU twin of tests/test_gpu_backward.py::test_stage_training_gradients_match_oracle."""
+    import torch.nn.functional as F
+
+    spec = pm_cases.STAGE_CASES[name]
+    case = pm_cases.make_stage_inputs(spec)
+    state = pm_cases.stage_state(golden_weights, spec["stage"])
+    target = 500.0 + 300.0 * torch.rand(case["ref_feature"].shape[0], 1, *case["ref_feature"].shape[2:], generator=torch.Generator().manual_seed(9))
+
+    def run(mod):
+        mod.load_state_dict(state, strict=True)
+        mod = mod.train()
+        if case["rand48"] is not None:
+            mod.rand_source = lambda size, device: case["rand48"]
+        ref = case["ref_feature"].detach().clone().requires_grad_(True)
+        srcs = [s.detach().clone().requires_grad_(True) for s in case["src_features"]]
+        depths, score, vw = mod(ref_feature=ref, src_features=srcs, ref_proj=case["ref_proj"], src_projs=list(case["src_projs"]),
+                                depth_min=case["depth_min"], depth_max=case["depth_max"], depth=case["depth"], view_weights=case["view_weights"])
+        loss = sum(F.smooth_l1_loss(d, target, reduction="mean") for d in depths)
+        loss.backward()
+        grads = {k: (p.grad.detach() if p.grad is not None else None) for k, p in mod.named_parameters()}
+        return loss.item(), [d.detach() for d in depths], ref.grad, [s.grad for s in srcs], grads
+
+    lo, do, gro, gso, po = run(pm_oracle.PatchMatchOracle(**pm_cases.stage_ctor_kwargs(spec["stage"])))
+    lm, dm, grm, gsm, pmine = run(PatchMatch(**pm_cases.stage_ctor_kwargs(spec["stage"])))
+    for a, b in zip(dm, do):
+        assert pm_cases.rel_l1(a, b) <= 1e-4
+    assert abs(lm - lo) <= 1e-4 * abs(lo)
+    _close(grm, gro, 2e-3)
+    for a, b in zip(gsm, gso):
+        _close(a, b, 2e-3)
+    _compare_param_grads(pmine, po, rtol=5e-3, atol_of_global=1e-4)
+    assert backend.calls.get("pmb200_warp_corr_backward", 0) >= 1 and backend.calls.get("pmb200_adaptive_eval_backward", 0) >= 1
