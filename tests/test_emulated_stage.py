@@ -166,3 +166,37 @@ def test_native_stage_training_gradients_on_emulated_kernels(backend, golden_wei
         _close(a, b, 2e-3)
     _compare_param_grads(pmine, po, rtol=5e-3, atol_of_global=1e-4)
     assert backend.calls.get("pmb200_warp_corr_backward", 0) >= 1 and backend.calls.get("pmb200_adaptive_eval_backward", 0) >= 1
+
+
+def test_native_network_training_step_on_emulated_kernels(backend, golden_weights):
+    """BASELINE.json configs[4] in miniature on the CPU box: full cascade in train() mode, reference loss (net.py:321-342),
+    backward; every parameter gradient of the native path against torch autograd on the oracle behind the same shell."""
+    from patchmatchnet_b200 import PatchmatchNet, load_reference_state, patchmatchnet_loss, synthetic
+
+    spec = dict(B=1, n_views=3, H=48, W=64, seed=41)
+    inp = synthetic.make_inputs(spec["B"], spec["n_views"], spec["H"], spec["W"], seed=spec["seed"])
+    g = torch.Generator().manual_seed(5)
+    rand48 = torch.rand(spec["B"], 48, spec["H"] // 8, spec["W"] // 8, generator=g)
+    gts, masks = [], []
+    for lvl in range(4):
+        h, w = spec["H"] >> lvl, spec["W"] >> lvl
+        gts.append(500.0 + 350.0 * torch.rand(spec["B"], 1, h, w, generator=g))
+        masks.append(torch.rand(spec["B"], 1, h, w, generator=g) > 0.2)
+
+    def run(cls):
+        net = PatchmatchNet(**pm_cases.NET_KWARGS) if cls is None else PatchmatchNet(**pm_cases.NET_KWARGS, patchmatch_cls=cls)
+        load_reference_state(net, golden_weights)
+        net = net.train()
+        net.patchmatch_3.rand_source = lambda size, device: rand48
+        depth, conf, per_stage = net(list(inp["images"]), inp["intrinsics"].clone(), inp["extrinsics"], inp["depth_min"], inp["depth_max"])
+        assert conf.numel() == 0  # train mode returns an empty confidence (net.py:286-287)
+        loss = patchmatchnet_loss(per_stage, gts, masks)
+        loss.backward()
+        return loss.item(), {k: (p.grad.detach() if p.grad is not None else None) for k, p in net.named_parameters()}
+
+    lo, go = run(pm_oracle.PatchMatchOracle)
+    lm, gm = run(None)
+    assert abs(lm - lo) <= 2e-4 * abs(lo)
+    never = sorted(k for k, v in go.items() if v is None)
+    assert any("patchmatch_1.propa_conv" in k for k in never) and any("patchmatch_2.evaluation.pixel_wise_net" in k for k in never)
+    _compare_param_grads(gm, go, rtol=2e-2, atol_of_global=2e-3)
