@@ -12,6 +12,11 @@ tail -4 gpurun_out/pytest_gpu.log | cut -c1-200
 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit $? at $(( $(date +%s) - t0 )) s" >> gpurun_out/bench.err
+# requests coalesced into one batch vs independent slots (run 9, older kernels: batch 8 gave 1,058 maps/s against 871 with 3 slots)
+for cfg in "2 2" "4 1" "4 2" "8 1"; do
+  set -- $cfg
+  timeout 200 python bench.py --batch $1 --slots $2 --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_b$1_s$2.json 2> gpurun_out/bench_b$1_s$2.err
+done
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 timeout 600 python tools/kbench.py > gpurun_out/kbench.json 2> gpurun_out/kbench.err          # full K-A / K-B sweeps
 timeout 600 python tools/convbench.py > gpurun_out/convbench.json 2> gpurun_out/convbench.err  # per-layer native vs cuDNN
@@ -28,6 +33,10 @@ try:
     b=json.load(open("gpurun_out/bench.json"))
     print('value',round(b['value'],1),'e2e',round(b['e2e']['value'],1),'ms',round(b['ms_per_step'],3),'roofline frac',round(b['roofline']['frac'],3),'clocks',b['clocks'])
 except Exception as e: print('bench ERR',e)
+for tag in ("b2_s2","b4_s1","b4_s2","b8_s1"):
+    try:
+        b=json.load(open(f"gpurun_out/bench_{tag}.json")); print('  batch/slots',tag,'value',round(b['value'],1),'e2e',round(b['e2e']['value'],1))
+    except Exception as e: print('  ',tag,'ERR',e)
 try:
     for r in json.load(open("gpurun_out/kbench.json"))['rows']:
         best=min(((v[0],k) for k,v in r.items() if isinstance(v,list)),default=None)
