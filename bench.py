@@ -37,7 +37,14 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-from patchmatchnet_b200 import synthetic  # noqa: E402
+
+def _synthetic():
+    """patchmatchnet_b200.synthetic, imported lazily: `--impl reference` sets PMB200_SKIP_TORCH_OPS first so that the
+    reference process maps none of the repo's native libraries."""
+    from patchmatchnet_b200 import synthetic
+
+    return synthetic
+
 
 WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_000007.pt")
 METRIC = "depth-maps/sec (1ref+4src, 640x512)"
@@ -47,6 +54,7 @@ UNIT = "depth-maps/s"
 def build_net(patchmatch_cls=None):
     from patchmatchnet_b200.net import PatchmatchNet, load_reference_state
 
+    synthetic = _synthetic()
     kw = dict(synthetic.DEFAULT_NET_KWARGS)
     net = PatchmatchNet(**kw) if patchmatch_cls is None else PatchmatchNet(**kw, patchmatch_cls=patchmatch_cls)
     if os.path.exists(WEIGHTS):
@@ -213,7 +221,7 @@ def cpu_forward_timer(height: int, width: int, n_views: int):
     cores = os.cpu_count() or 1
     net, _ = build_net(PatchMatchOracle)
     net.stack_views = False  # the reference runs FeatureNet view by view (net.py:203-208)
-    inp = synthetic.make_inputs(1, n_views, height, width, seed=0)
+    inp = _synthetic().make_inputs(1, n_views, height, width, seed=0)
 
     def step():
         with torch.no_grad():
@@ -248,7 +256,7 @@ def gpu_eager_reference(height: int, width: int, n_views: int, device, warmup: i
     net, _ = build_net(PatchMatchOracle)
     net = net.to(device).eval()
     net.stack_views = False
-    inp = synthetic.make_inputs(1, n_views, height, width, seed=0)
+    inp = _synthetic().make_inputs(1, n_views, height, width, seed=0)
     imgs = [i.to(device) for i in inp["images"]]
     K, E = inp["intrinsics"].to(device), inp["extrinsics"].to(device)
     dmin, dmax = inp["depth_min"].to(device), inp["depth_max"].to(device)
@@ -274,6 +282,7 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["PMB200_SKIP_TORCH_OPS"] = "1"  # this process must not map libpmb200*.so (nothing here calls them)
     step, cores = cpu_forward_timer(args.height, args.width, args.views)
     for _ in range(args.warmup):
         step()
@@ -287,8 +296,9 @@ def run_reference_arm(args) -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"1ref+{args.views - 1}src {args.width}x{args.height} 3-stage cascade (64/32,16/16,8 hyp), batch 1, host CPU",
-                   "weights": "reference checkpoint (fixture)" if os.path.exists(WEIGHTS) else "random init"},
+        "config": {"workload": workload_label(1, args.views, args.height, args.width),
+                   "where": "host CPU, one process on rank 0 whatever --gpus says: for N GPUs compare against N x this value",
+                   "weights": "reference checkpoint params_000007 (fixture)" if os.path.exists(WEIGHTS) else "random init"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -455,6 +465,157 @@ def _recorded(stream):
     return ev
 
 
+def workload_label(B, N, H, W) -> str:
+    base = f"1ref+{N - 1}src {W}x{H} 3-stage cascade (64/32,16/16,8 hyp), batch {B} per GPU"
+    if (N, H, W) == (5, 512, 640):
+        tag = "BASELINE.json configs[1]" if B == 1 else f"BASELINE.json configs[3]'s reference views, {B} on one GPU"
+    elif (N, H, W) == (5, 1184, 1600) and B == 1:
+        tag = "BASELINE.json configs[2]"
+    else:
+        tag = "custom size"
+    return f"{base} ({tag})"
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pin this process (and therefore its pinned-host allocations, first-touch) to the CPUs NVML reports as local to the
+    rank's GPU.  SCALE_r01: e2e efficiency at 8 GPUs was 0.93 with eight unbound processes pushing pinned H2D copies across
+    both NUMA nodes.  Best effort: returns what it did for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and w * 64 + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"bound": False, "why": "NVML affinity set is empty or outside this process's cpuset"}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "cpus": f"{allowed[0]}-{allowed[-1]} ({len(allowed)})", "how": "nvmlDeviceGetCpuAffinity -> sched_setaffinity before pinned allocations"}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": repr(e)[:120]}
+
+
+class Workload:
+    """One (batch, views, size) problem on this rank: engine, resident device inputs, pinned host inputs."""
+
+    def __init__(self, net, B, N, H, W, dev, slots, rank, use_graph=True):
+        from patchmatchnet_b200.engine import DepthEngine
+
+        synthetic = _synthetic()
+        self.shape = (B, N, H, W)
+        self.eng = DepthEngine(net, B, N, H, W, device=str(dev), use_graph=use_graph, n_slots=slots)
+        host = synthetic.make_inputs(B, N, H, W, seed=rank)
+        self.host_pinned = dict(
+            images=[im.pin_memory() for im in host["images"]],
+            intrinsics=host["intrinsics"].pin_memory(), extrinsics=host["extrinsics"].pin_memory(),
+            depth_min=host["depth_min"].pin_memory(), depth_max=host["depth_max"].pin_memory(),
+        )
+        self.d_in = dict(images=[im.to(dev) for im in host["images"]], intrinsics=host["intrinsics"].to(dev),
+                         extrinsics=host["extrinsics"].to(dev), depth_min=host["depth_min"].to(dev), depth_max=host["depth_max"].to(dev))
+        for s in range(self.eng.n_slots):
+            self.eng.set_device_inputs(s, self.d_in["images"], self.d_in["intrinsics"], self.d_in["extrinsics"],
+                                       self.d_in["depth_min"], self.d_in["depth_max"])
+        torch.cuda.synchronize()
+
+    def dev_inputs(self):
+        d = self.d_in
+        return ([im.clone() for im in d["images"]], d["intrinsics"].clone(), d["extrinsics"].clone(), d["depth_min"], d["depth_max"])
+
+
+def time_resident(wl, steps, flush, stream, barrier):
+    """K steps with inputs resident in HBM: rounds of up to `slots` concurrent graph replays, L2 flushed before every
+    round outside the event pair that times it.  Returns the summed device seconds."""
+    eng = wl.eng
+    S = eng.n_slots
+    rounds = [min(S, steps - r) for r in range(0, steps, S)]
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in rounds]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in rounds]
+    for i, n_now in enumerate(rounds):
+        flush()
+        starts[i].record(stream)
+        eng.run_round(n_now, starts[i], ends[i])
+    barrier()
+    return sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
+
+
+def time_e2e(wl, steps, stream, barrier):
+    """K requests through the public API: pinned host in -> device -> graph -> pinned host out, every request."""
+    eng = wl.eng
+    reqs = [wl.host_pinned] * steps
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    eng.copy_stream.wait_event(t0)
+    for sl in eng._slots:
+        sl["stream"].wait_event(t0)
+    h2d, d2h = eng.infer_stream(reqs)  # returns after every slot stream has drained
+    t1.record(stream)
+    barrier()
+    return t0.elapsed_time(t1) * 1e-3, h2d, d2h
+
+
+def single_request_latency(wl, flush, stream, iters=10):
+    """One request alone on the GPU: device time of one graph replay (inputs resident, L2 flushed) and the wall-clock of
+    the synchronous public call (pinned host in -> pinned host out)."""
+    eng = wl.eng
+    dev_ms, wall_ms = [], []
+    for _ in range(iters):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.run_slot(0)
+        e1.record(stream)
+        e1.synchronize()
+        dev_ms.append(e0.elapsed_time(e1))
+    h = wl.host_pinned
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        eng.infer(h["images"], h["intrinsics"], h["extrinsics"], h["depth_min"], h["depth_max"])
+        wall_ms.append(1e3 * (time.perf_counter() - t0))
+    return {"device_ms": statistics.median(dev_ms), "device_ms_min": min(dev_ms), "host_to_host_ms": statistics.median(wall_ms),
+            "how": f"median of {iters}: one CUDA-graph replay alone on the GPU, L2 flushed, CUDA events; and DepthEngine.infer wall clock"}
+
+
+def ka_roofline(net, wl, peak_gbs, peak_src, flush, steps):
+    detail = time_warp_corr_in_step(net, wl.dev_inputs, peak_gbs, flush, steps=steps)
+    if not detail:
+        return None, detail
+    n_l = len(detail)
+    alg_mean = sum(r["algorithmic_bytes"] for r in detail) / n_l
+    us_mean = sum(r["us"] for r in detail) / n_l
+    traffic, traffic_src = None, None
+    tfile = os.path.join(REPO, "profiles", TRAFFIC_FILE)
+    if os.path.exists(tfile):
+        try:
+            t = json.load(open(tfile))
+            traffic, traffic_src = t.get("mean_dram_bytes_per_launch"), f"profiles/{TRAFFIC_FILE} ({t.get('capture', 'ncu --set full')})"
+        except Exception:  # noqa: BLE001
+            traffic = None
+    achieved = alg_mean / (us_mean * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"fused warp + bilinear gather + group correlation + view aggregation + head (K-A), {n_l} launches per step",
+                "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
+                "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_mean, "us_per_launch": us_mean,
+                "how": "mean over the kernel's launches of one step; each launch timed by a CUDA-event pair inside timed eager steps "
+                       "(L2 flushed between steps, GPU parked so the host's enqueue latency is not measured); "
+                       "algorithmic bytes = V * 4*B*H*W*(2C + D + G*D) per launch (SURVEY.md 8d)",
+                "best_launch_frac": max(r["frac"] for r in detail), "worst_launch_frac": min(r["frac"] for r in detail)}
+    return roofline, detail
+
+
+TRAFFIC_FILE = "r2_warp_corr_traffic.json"  # written from this round's ncu --set full capture (tools/summarize_ncu.py)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -468,9 +629,11 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch reference timing on the GPU")
-    ap.add_argument("--no-tf32", action="store_true", help="run the library convolutions in full fp32 instead of torch's default TF32")
+    ap.add_argument("--no-tf32", action="store_true", help="run every convolution in full fp32 (3xTF32 native, fp32 cuDNN) instead of torch's default TF32")
     ap.add_argument("--slots", type=int, default=3, help="independent requests in flight per GPU (each its own stream + CUDA graph)")
     ap.add_argument("--cpu-samples", type=int, default=4)
+    ap.add_argument("--repeats", type=int, default=5, help="the K-step timed region is repeated this many times; the line reports the median")
+    ap.add_argument("--no-sub", action="store_true", help="skip the fp32 / 1600x1184 / batch-8 sub-records (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -483,6 +646,7 @@ def main() -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local)  # before any pinned allocation
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True  # as the reference's eval.py:301 does; autotuned during warm-up
@@ -497,23 +661,10 @@ def main() -> None:
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
 
-    from patchmatchnet_b200.engine import DepthEngine
-
     B, N, H, W = args.batch, args.views, args.height, args.width
     net, weights = build_net()
-    eng = DepthEngine(net, B, N, H, W, device=str(dev), use_graph=not args.no_graph, n_slots=args.slots)
-
-    host = synthetic.make_inputs(B, N, H, W, seed=rank)
-    host_pinned = dict(
-        images=[im.pin_memory() for im in host["images"]],
-        intrinsics=host["intrinsics"].pin_memory(), extrinsics=host["extrinsics"].pin_memory(),
-        depth_min=host["depth_min"].pin_memory(), depth_max=host["depth_max"].pin_memory(),
-    )
-    d_in = dict(images=[im.to(dev) for im in host["images"]], intrinsics=host["intrinsics"].to(dev),
-                extrinsics=host["extrinsics"].to(dev), depth_min=host["depth_min"].to(dev), depth_max=host["depth_max"].to(dev))
-    for s in range(eng.n_slots):
-        eng.set_device_inputs(s, d_in["images"], d_in["intrinsics"], d_in["extrinsics"], d_in["depth_min"], d_in["depth_max"])
-    torch.cuda.synchronize()
+    wl = Workload(net, B, N, H, W, dev, args.slots, rank, use_graph=not args.no_graph)
+    eng = wl.eng
 
     with LaunchCounter() as lc:
         eng.prepare()  # warm-up forwards + graph capture
@@ -530,12 +681,16 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(vals):
+        if dist is None:
+            return list(vals)
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
     # ---------------- kernel-side throughput: inputs resident in HBM ----------------
-    # K steps run as rounds of up to `slots` concurrent forwards (one per slot stream); L2 is flushed before every
-    # round, outside the event pair that times the round.
     stream = torch.cuda.current_stream()
     S = eng.n_slots
-    rounds = [min(S, args.steps - r) for r in range(0, args.steps, S)]
     try:
         uuid = str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:  # noqa: BLE001
@@ -547,76 +702,78 @@ def main() -> None:
         eng.run_round(S, _recorded(stream), torch.cuda.Event())
     barrier()
     sampler.mark_begin()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in rounds]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in rounds]
-    for i, n_now in enumerate(rounds):
-        flush()
-        starts[i].record(stream)
-        eng.run_round(n_now, starts[i], ends[i])
-    barrier()
+    dev_runs = [time_resident(wl, args.steps, flush, stream, barrier) for _ in range(max(1, args.repeats))]
     sampler.mark_end()
     clocks = sampler.stop()
-    dev_seconds = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
+    dev_runs = reduce_max(dev_runs)  # per repeat: the slowest rank
+    dev_seconds = statistics.median(dev_runs)
 
     # ---------------- end to end: pinned host in, pinned host out, every step ----------------
-    reqs = [host_pinned] * (args.steps)
-    eng.infer_stream(reqs[: max(args.warmup, eng.n_slots)])
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record(stream)
-    eng.copy_stream.wait_event(t0)
-    for sl in eng._slots:
-        sl["stream"].wait_event(t0)
-    h2d, d2h = eng.infer_stream(reqs)  # returns after every slot stream has drained
-    t1.record(stream)
-    barrier()
-    e2e_seconds = t0.elapsed_time(t1) * 1e-3
-
-    if dist is not None:
-        t = torch.tensor([dev_seconds, e2e_seconds], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_seconds, e2e_seconds = float(t[0]), float(t[1])
+    eng.infer_stream([wl.host_pinned] * max(args.warmup, eng.n_slots))
+    e2e_runs, h2d, d2h = [], 0, 0
+    for _ in range(max(1, args.repeats)):
+        t, h2d, d2h = time_e2e(wl, args.steps, stream, barrier)
+        e2e_runs.append(t)
+    e2e_runs = reduce_max(e2e_runs)
+    e2e_seconds = statistics.median(e2e_runs)
 
     maps = args.steps * B * world
     value = maps / dev_seconds
     e2e_value = maps / e2e_seconds
 
-    # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N=1 detail) ----------------
+    # ---------------- roofline of the dominant kernel + baselines + sub-records (rank 0) ----------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-    except Exception:
+    except Exception:  # noqa: BLE001
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    roofline, detail, detail_cold, cpu_baseline, gpu_eager = None, None, None, None, None
+    roofline, detail, detail_cold, cpu_baseline, gpu_eager, latency, sub = None, None, None, None, None, None, {}
     if rank == 0:
-        dev_inputs = lambda: ([im.clone() for im in d_in["images"]], d_in["intrinsics"].clone(), d_in["extrinsics"].clone(),
-                              d_in["depth_min"], d_in["depth_max"])
-        detail = time_warp_corr_in_step(net, dev_inputs, peak_gbs, flush, steps=max(5, args.steps // 2))
-        detail_cold = time_warp_corr_isolated(net, dev_inputs, peak_gbs, flush)
-        if detail:
-            # the dominant hand-written kernel is the fused warp+correlation kernel: average over its launches of one step
-            n_l = len(detail)
-            alg_mean = sum(r["algorithmic_bytes"] for r in detail) / n_l
-            us_mean = sum(r["us"] for r in detail) / n_l
-            traffic = None
-            tfile = os.path.join(REPO, "profiles", "warp_corr_traffic.json")
-            if os.path.exists(tfile):
-                try:
-                    traffic = json.load(open(tfile)).get("mean_dram_bytes_per_launch")
-                except Exception:
-                    traffic = None
-            achieved = alg_mean / (us_mean * 1e-6) / 1e9
-            roofline = {"bound": "hbm", "kernel": "warp_corr3_kernel (fused warp + bilinear gather + group correlation + view aggregation + head), "
-                                                  f"{n_l} launches per step",
-                        "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_mean, "us_per_launch": us_mean,
-                        "how": "mean over the kernel's launches of one step; each launch timed by a CUDA-event pair inside timed eager steps "
-                               "(L2 flushed between steps, GPU parked so the host's enqueue latency is not measured); "
-                               "algorithmic bytes = V * 4*B*H*W*(2C + D + G*D) per launch (SURVEY.md 8d)",
-                        "best_launch_frac": max(r["frac"] for r in detail), "worst_launch_frac": min(r["frac"] for r in detail)}
+        roofline, detail = ka_roofline(net, wl, peak_gbs, peak_src, flush, steps=max(5, args.steps // 2))
+        detail_cold = time_warp_corr_isolated(net, wl.dev_inputs, peak_gbs, flush)
+        latency = single_request_latency(wl, flush, stream)
+    if world == 1 and not args.no_sub:
+        # (1) the same workload with every convolution in full fp32 (native 3xTF32, cuDNN fp32): own net so that the
+        #     precision-keyed weight caches captured by the TF32 graphs above are not evicted
+        if not args.no_tf32:
+            old = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                net32, _ = build_net()
+                wl32 = Workload(net32, B, N, H, W, dev, args.slots, rank, use_graph=not args.no_graph)
+                wl32.eng.prepare()
+                runs = [time_resident(wl32, args.steps, flush, stream, barrier) for _ in range(3)]
+                sub["value_fp32"] = {"value": args.steps * B / statistics.median(runs), "unit": UNIT,
+                                     "ms_per_step": 1e3 * statistics.median(runs) / args.steps,
+                                     "how": "same workload, cudnn.allow_tf32=False: native convs 3xTF32 (fp32-accurate), library convs fp32; median of 3"}
+                del wl32, net32
+            finally:
+                torch.backends.cudnn.allow_tf32 = old
+        # (2) BASELINE config 3 (DTU full size) and 8 reference views on one GPU: value, e2e and the K-A roofline there
+        for key, (b2, h2, w2, s2, st2) in {"cfg3_1600x1184": (1, 1184, 1600, 2, 10), "batch8_640x512": (8, 512, 640, 1, 5)}.items():
+            if (b2, h2, w2) == (B, H, W):
+                continue
+            try:
+                w2l = Workload(net, b2, N, h2, w2, dev, s2, rank, use_graph=not args.no_graph)
+                w2l.eng.prepare()
+                for _ in range(2):
+                    time_resident(w2l, s2, flush, stream, barrier)
+                runs = [time_resident(w2l, st2, flush, stream, barrier) for _ in range(3)]
+                w2l.eng.infer_stream([w2l.host_pinned] * max(3, s2))
+                e_runs = [time_e2e(w2l, st2, stream, barrier)[0] for _ in range(3)]
+                rl, det = ka_roofline(net, w2l, peak_gbs, peak_src, flush, steps=5)
+                sub[key] = {"workload": workload_label(b2, N, h2, w2), "value": st2 * b2 / statistics.median(runs), "unit": UNIT,
+                            "ms_per_step": 1e3 * statistics.median(runs) / st2, "e2e_value": st2 * b2 / statistics.median(e_runs),
+                            "requests_in_flight": s2, "steps": st2, "repeats": 3,
+                            "roofline": None if rl is None else {k: rl[k] for k in ("achieved", "peak", "frac", "us_per_launch", "algorithmic_bytes_per_launch", "best_launch_frac", "worst_launch_frac")},
+                            "roofline_detail": None if det is None else [{k: r[k] for k in ("shape", "us", "frac")} for r in det]}
+                del w2l
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                sub[key] = {"error": repr(e)[:300]}
+    if rank == 0:
         if world == 1 and not args.no_gpu_baseline:
             gpu_eager = gpu_eager_reference(H, W, N, dev)
         if world == 1 and not args.no_cpu_baseline:
@@ -628,28 +785,38 @@ def main() -> None:
                                       f"{cores} torch threads (best of calibration {step.calibration}, host has {os.cpu_count()} cores)"}
 
     if rank == 0:
+        tf32 = not args.no_tf32
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"1ref+{N - 1}src {W}x{H} 3-stage cascade (64/32,16/16,8 hyp), batch {B} per GPU (BASELINE.json configs[1])",
+            "dtype": "f32 kernels + tf32-operand convs (torch default cudnn.allow_tf32)" if tf32 else "f32 (convs 3xTF32-compensated / cuDNN fp32)",
+            "data": "synthetic",
+            "repeats": {"n": len(dev_runs), "statistic": "median", "value_min": maps / max(dev_runs), "value_max": maps / min(dev_runs),
+                        "e2e_min": maps / max(e2e_runs), "e2e_max": maps / min(e2e_runs),
+                        "ms_per_step_all": [round(1e3 * t / args.steps, 4) for t in dev_runs]},
+            "config": {"workload": workload_label(B, N, H, W),
                        "parallelism": f"{world} x (1 process/GPU, reference views sharded by rank, no data-path collective)",
                        "weights": weights, "cuda_graph": eng.use_graph, "requests_in_flight": eng.n_slots,
                        "l2": "flushed before every timed round of <= requests_in_flight concurrent steps (256 MiB write, outside the events)",
-                       "library_convs": ("cuDNN, full fp32 (--no-tf32)" if args.no_tf32 else
-                                         "cuDNN under torch's default flags (TF32 allowed, as the unmodified reference would run on this GPU) for "
-                                         "FeatureNet/Refinement/offset convs; every hand-written kernel is full fp32")},
+                       "convs": ("every conv fp32-accurate: native kernels 3xTF32, cuDNN fp32 (--no-tf32)" if not tf32 else
+                                 "native channels-last tensor-core convs (TF32 operands, fp32 accumulate) for FeatureNet's memory-bound layers, "
+                                 "its top-down path, Refinement and the stage-1 offset conv; cuDNN (TF32 allowed, torch's default) for the "
+                                 "FLOP-bound FeatureNet layers and the stage-2/3 offset convs; every PatchMatch kernel is full fp32. "
+                                 "Parity of THIS mode: tests/test_gpu_bench_mode.py"),
+                       "numa": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_seconds / args.steps,
                     "how": "DepthEngine.infer_stream: pinned host inputs -> device (copy stream) -> CUDA graph on the request's slot stream -> pinned host outputs; "
                            "requests_in_flight independent requests overlap"},
+            "latency_single_request": latency,
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "native_kernels_per_step": {k: v // max(1, forwards_counted) for k, v in sorted(lc.by_name.items())},
             "clocks": clocks,
-            "roofline": roofline, "roofline_detail": detail, "roofline_detail_cold_isolated": detail_cold if rank == 0 else None,
+            "roofline": roofline, "roofline_detail": detail, "roofline_detail_cold_isolated": detail_cold,
             "cpu_baseline": cpu_baseline,
             "gpu_eager_reference": gpu_eager,
         }
+        line.update(sub)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

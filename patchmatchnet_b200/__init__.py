@@ -16,7 +16,9 @@ from .patchmatch import PatchMatch  # noqa: F401
 # so that `torch.jit.script(model)` / `torch.jit.load(path)` work after a plain `import patchmatchnet_b200`.
 # Not when libpmb200.so is older than its sources: loading the shim would map the stale library into the process and the
 # rebuild that build() is about to do could no longer be loaded under the same path.
-if _os.path.exists(_native.TORCH_LIB_PATH) and not _native.needs_rebuild():
+# PMB200_SKIP_TORCH_OPS=1: a process that must not map the native libraries at all (bench.py --impl reference).
+if (_os.environ.get("PMB200_SKIP_TORCH_OPS") != "1" and _os.path.exists(_native.TORCH_LIB_PATH)
+        and not _native.needs_rebuild()):
     _native.load_torch_ops()
 
 __all__ = ["PatchMatch", "PatchmatchNet", "load_reference_state", "patchmatchnet_loss"]

@@ -42,7 +42,10 @@ LIBRARY_FAST_PATH = True
 
 
 def _fast(x: Tensor) -> bool:
-    return LIBRARY_FAST_PATH and x.is_cuda
+    """Inference fast paths (BatchNorm folded into constant weights, cuDNN fused conv+ReLU, native convs) have no
+    derivative: they are taken only when autograd is off.  In eval() with grad enabled -- frozen-BN fine-tuning,
+    gradient analysis -- the shell issues the reference's own differentiable op sequence, as the reference does."""
+    return LIBRARY_FAST_PATH and x.is_cuda and not torch.is_grad_enabled()
 
 
 class _FoldCache:
