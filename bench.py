@@ -248,8 +248,9 @@ def cpu_forward_timer(height: int, width: int, n_views: int):
 def gpu_eager_reference(height: int, width: int, n_views: int, device, warmup: int = 3, iters: int = 10):
     """The reference's algorithm as the reference would run it on THIS GPU: the oracle port (bit-identical to the
     reference on CPU) in eager PyTorch, the caller-side shell issuing the reference's own op sequence (conv, BatchNorm,
-    ReLU separately, view by view; no folding, no stacking), cudnn.benchmark on as in eval.py:301, TF32 as torch's
-    defaults leave it.  A reported baseline (SURVEY.md 8d "honest bar"), never part of the product path."""
+    ReLU separately, view by view; no folding, no stacking), cudnn.benchmark on as in eval.py:301, the TF32 switch as the
+    caller left it (bench.py's default: off, i.e. the library convolutions in fp32 -- the configuration whose depth maps
+    match the timed ones).  A reported baseline (SURVEY.md 8d "honest bar"), never part of the product path."""
     from oracle.pm_oracle import PatchMatchOracle  # allowed here: baseline legs only
     import patchmatchnet_b200.net as net_mod
 
@@ -275,7 +276,8 @@ def gpu_eager_reference(height: int, width: int, n_views: int, device, warmup: i
         net_mod.LIBRARY_FAST_PATH = True
     return {"value": iters / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / iters, "kind": "port",
             "how": f"oracle port of the reference in eager PyTorch on the same GPU, reference op sequence, inputs resident, "
-                   f"{warmup} warm-up + {iters} timed forwards, synchronize-bracketed wall clock, cudnn.benchmark=True"}
+                   f"{warmup} warm-up + {iters} timed forwards, synchronize-bracketed wall clock, cudnn.benchmark=True, "
+                   f"cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}"}
 
 
 def run_reference_arm(args) -> None:
@@ -629,7 +631,9 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch reference timing on the GPU")
-    ap.add_argument("--no-tf32", action="store_true", help="run every convolution in full fp32 (3xTF32 native, fp32 cuDNN) instead of torch's default TF32")
+    ap.add_argument("--tf32", action="store_true", help="time torch's default flags instead (TF32 operands in the convolutions): faster, but the "
+                    "depth maps are 2.6e-3..3.3e-3 off the fp32 reference, outside north_star's 1e-3 (tests/test_gpu_bench_mode.py)")
+    ap.add_argument("--no-tf32", action="store_true", help="accepted for compatibility: fp32-accurate convolutions are the default")
     ap.add_argument("--slots", type=int, default=3, help="independent requests in flight per GPU (each its own stream + CUDA graph)")
     ap.add_argument("--cpu-samples", type=int, default=4)
     ap.add_argument("--repeats", type=int, default=5, help="the K-step timed region is repeated this many times; the line reports the median")
@@ -650,6 +654,9 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True  # as the reference's eval.py:301 does; autotuned during warm-up
+    # Default: every convolution fp32-accurate (native 3xTF32 split on the tensor cores) -- the configuration the parity tests
+    # hold to north_star's 1e-3 (observed ~1e-5).  --tf32 leaves torch's default (TF32 operands).
+    args.no_tf32 = not args.tf32
     if args.no_tf32:
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -735,20 +742,24 @@ def main() -> None:
         detail_cold = time_warp_corr_isolated(net, wl.dev_inputs, peak_gbs, flush)
         latency = single_request_latency(wl, flush, stream)
     if world == 1 and not args.no_sub:
-        # (1) the same workload with every convolution in full fp32 (native 3xTF32, cuDNN fp32): own net so that the
-        #     precision-keyed weight caches captured by the TF32 graphs above are not evicted
-        if not args.no_tf32:
+        # (1) the same workload under torch's default flags (TF32 operands in the convs), as round 1 timed it: own net so that
+        #     the precision-keyed weight caches captured by the graphs above are not evicted.  Reported, not the headline:
+        #     its depth maps are outside the 1e-3 parity bound.
+        if args.no_tf32:
             old = torch.backends.cudnn.allow_tf32
-            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = True
             try:
-                net32, _ = build_net()
-                wl32 = Workload(net32, B, N, H, W, dev, args.slots, rank, use_graph=not args.no_graph)
-                wl32.eng.prepare()
-                runs = [time_resident(wl32, args.steps, flush, stream, barrier) for _ in range(3)]
-                sub["value_fp32"] = {"value": args.steps * B / statistics.median(runs), "unit": UNIT,
+                net_t, _ = build_net()
+                wl_t = Workload(net_t, B, N, H, W, dev, args.slots, rank, use_graph=not args.no_graph)
+                wl_t.eng.prepare()
+                runs = [time_resident(wl_t, args.steps, flush, stream, barrier) for _ in range(3)]
+                sub["value_tf32"] = {"value": args.steps * B / statistics.median(runs), "unit": UNIT,
                                      "ms_per_step": 1e3 * statistics.median(runs) / args.steps,
-                                     "how": "same workload, cudnn.allow_tf32=False: native convs 3xTF32 (fp32-accurate), library convs fp32; median of 3"}
-                del wl32, net32
+                                     "parity": "OUTSIDE the bound: depth rel-L1 vs the fp32 oracle 2.6e-3 (cfg 2) / 3.3e-3 (cfg 3) / 3.1e-3 (B=8), "
+                                               "north_star allows 1e-3 (tests/test_gpu_bench_mode.py, profiles/r2_run1_bench_mode_parity.json)",
+                                     "how": "same workload, torch default cudnn.allow_tf32=True: native convs with TF32 operands on the memory-bound "
+                                            "layers, cuDNN TF32 on the FLOP-bound ones; median of 3"}
+                del wl_t, net_t
             finally:
                 torch.backends.cudnn.allow_tf32 = old
         # (2) BASELINE config 3 (DTU full size) and 8 reference views on one GPU: value, e2e and the K-A roofline there
@@ -789,7 +800,8 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 kernels + tf32-operand convs (torch default cudnn.allow_tf32)" if tf32 else "f32 (convs 3xTF32-compensated / cuDNN fp32)",
+            "dtype": "f32 kernels + tf32-operand convs (torch default cudnn.allow_tf32; outside the 1e-3 parity bound)" if tf32
+                     else "f32 (PatchMatch kernels fp32; every conv on the tensor cores with the error-compensated 3xTF32 split, fp32-accurate)",
             "data": "synthetic",
             "repeats": {"n": len(dev_runs), "statistic": "median", "value_min": maps / max(dev_runs), "value_max": maps / min(dev_runs),
                         "e2e_min": maps / max(e2e_runs), "e2e_max": maps / min(e2e_runs),
@@ -798,11 +810,13 @@ def main() -> None:
                        "parallelism": f"{world} x (1 process/GPU, reference views sharded by rank, no data-path collective)",
                        "weights": weights, "cuda_graph": eng.use_graph, "requests_in_flight": eng.n_slots,
                        "l2": "flushed before every timed round of <= requests_in_flight concurrent steps (256 MiB write, outside the events)",
-                       "convs": ("every conv fp32-accurate: native kernels 3xTF32, cuDNN fp32 (--no-tf32)" if not tf32 else
+                       "convs": ("every conv (FeatureNet, Refinement, offset convs) on the native channels-last tensor-core kernel, 3xTF32 "
+                                 "error-compensated split = fp32-accurate; no cuDNN conv in the step. Parity of THIS mode: "
+                                 "tests/test_gpu_bench_mode.py (depth rel-L1 vs the fp32 oracle ~1e-5)" if not tf32 else
                                  "native channels-last tensor-core convs (TF32 operands, fp32 accumulate) for FeatureNet's memory-bound layers, "
                                  "its top-down path, Refinement and the stage-1 offset conv; cuDNN (TF32 allowed, torch's default) for the "
                                  "FLOP-bound FeatureNet layers and the stage-2/3 offset convs; every PatchMatch kernel is full fp32. "
-                                 "Parity of THIS mode: tests/test_gpu_bench_mode.py"),
+                                 "This mode is OUTSIDE the 1e-3 parity bound (tests/test_gpu_bench_mode.py)"),
                        "numa": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_seconds / args.steps,

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libpmb200.so")
 SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in ("pm_kernels.cu", "pm_backward.cu", "pm_conv.cu", "pm_geo.cu", "pm_mapio.cpp")]
 HEADERS = [
     os.path.join(_PKG_DIR, "csrc", "pm_math.cuh"),
+    os.path.join(_PKG_DIR, "csrc", "pm_warpcorr4.cuh"),
     os.path.join(_PKG_DIR, "csrc", "pm_geo_math.cuh"),
     os.path.join(_REPO_DIR, "include", "patchmatch_b200.h"),
 ]
@@ -104,6 +105,7 @@ _PMAP = POINTER(MapInfo)
 _SIGNATURES = {
     "pmb200_abi_version": (c_int, []),
     "pmb200_last_error": (c_char_p, []),
+    "pmb200_set_tuning": (c_int, [c_char_p, c_int]),
     "pmb200_relative_projection": (c_int, [c_void_p, c_int64, _PPF, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "pmb200_pack_nhwc": (c_int, [_PPF, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pmb200_photometric_confidence": (c_int, [c_void_p] * 2 + [c_int] * 6 + [c_void_p]),

@@ -109,6 +109,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
+// high part of the 3xTF32 activation split: the value with its 13 low mantissa bits cleared
+__device__ __forceinline__ uint32_t split_hi(float f) { return __float_as_uint(f) & 0xffffe000u; }
+
 // Stage the halo tile of output tile `tile` into `buf` ([rh][rw][ps]): the CTA's threads stride over the
 // tile's copy chunks (16-byte channel vectors when VEC, else single floats: Cin % 4 != 0).  Out-of-image pixels and
 // (STUFF) the odd positions of a zero-stuffed input are written as zeros by the copy engine itself (src-size 0);
@@ -318,11 +321,15 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const __gri
                     for (int j = 0; j < NT; ++j) mma_tf32(acc[m][j], ah, bh[j][0], bh[j][1]);
                 } else {
                     uint32_t al[4];
-                    ah[0] = to_tf32(lo.x); ah[1] = to_tf32(hi.x); ah[2] = to_tf32(lo.y); ah[3] = to_tf32(hi.y);
-                    al[0] = to_tf32(lo.x - __uint_as_float(ah[0]));
-                    al[1] = to_tf32(hi.x - __uint_as_float(ah[1]));
-                    al[2] = to_tf32(lo.y - __uint_as_float(ah[2]));
-                    al[3] = to_tf32(hi.y - __uint_as_float(ah[3]));
+                    // split without conversion instructions: a_hi = the TF32 the tensor core would read anyway (low 13 mantissa
+                    // bits cleared), a_lo = a - a_hi, exact in fp32 (Sterbenz) and handed over as raw bits -- the hardware keeps
+                    // its 11 leading bits, so a_hi + tf32(a_lo) carries >= 22 bits of a.  cvt.rna here was ~10 issue slots per
+                    // register on sm_100 (profiles/r1_run17_conv_ncu.md); this is one LOP3 and one FADD.
+                    ah[0] = split_hi(lo.x); ah[1] = split_hi(hi.x); ah[2] = split_hi(lo.y); ah[3] = split_hi(hi.y);
+                    al[0] = __float_as_uint(lo.x - __uint_as_float(ah[0]));
+                    al[1] = __float_as_uint(hi.x - __uint_as_float(ah[1]));
+                    al[2] = __float_as_uint(lo.y - __uint_as_float(ah[2]));
+                    al[3] = __float_as_uint(hi.y - __uint_as_float(ah[3]));
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {  // small terms first
                         mma_tf32(acc[m][j], al, bh[j][0], bh[j][1]);
@@ -559,8 +566,8 @@ __global__ void __launch_bounds__(128) conv_nhwc_mmat_kernel(const __grid_consta
 #pragma unroll
                                 for (int j = 0; j < MTL; ++j) mma_tf32(acc[m][j][h], ah[j], b0, b1);
                             } else {
-                                const uint32_t bh0 = to_tf32(b.x), bh1 = to_tf32(b.y);
-                                const uint32_t bl0 = to_tf32(b.x - __uint_as_float(bh0)), bl1 = to_tf32(b.y - __uint_as_float(bh1));
+                                const uint32_t bh0 = split_hi(b.x), bh1 = split_hi(b.y);
+                                const uint32_t bl0 = __float_as_uint(b.x - __uint_as_float(bh0)), bl1 = __float_as_uint(b.y - __uint_as_float(bh1));
 #pragma unroll
                                 for (int j = 0; j < MTL; ++j) {  // small terms first
                                     mma_tf32(acc[m][j][h], al[j], bh0, bh1);

@@ -2,11 +2,13 @@
 // (backward kernels: pm_backward.cu; per-element formulas shared with the CPU formula tests: pm_math.cuh).
 //
 // Kernel map (DESIGN.md has the byte/flop budgets and the measured numbers):
-//   warp_corr3_kernel<C,G,EPI,DC,PIPE,MINB>  K-A, third generation (default): homography warp + bilinear gather +
-//                                  group-wise correlation + view-weighted aggregation + (eval) 1x1x1 head epilogue
+//   wc4::warp_corr4_kernel<C,G,EPI,NW,MINB>  K-A, fourth generation (default, pm_warpcorr4.cuh): homography warp + bilinear
+//                                  gather + group-wise correlation + view-weighted aggregation + (eval) 1x1x1 head epilogue
+//                                  as a persistent producer/consumer pipeline over TMA-staged shared-memory windows
 //                                  pmb200_warp_corr / _score / _view_weights
-//   warp_corr2_kernel, warp_corr_kernel      K-A generations 2 and 1, kept selectable (PMB200_KA_GEN=2,
-//                                  PMB200_WARP_CORR_V1=1) for A/B measurements; warp_corr_generic_kernel: any C % G == 0
+//   warp_corr3_kernel<C,G,EPI,DC,PIPE,MINB>  K-A, third generation: register/L1 gather; taken for shapes generation 4
+//                                  declines and selectable for A/B measurements (pmb200_set_tuning("ka_gen", 3));
+//                                  warp_corr_generic_kernel: any C % G == 0
 //   aggregate_views_kernel / aggregate_score_kernel   weighted view average of stored similarities (+ head)
 //   offset_corr_kernel<C,G,HEAD>   K-A': reference self-correlation at the learned evaluation neighbours (+ head)
 //   init_propagate_kernel<NPAD>    K-C: hypothesis init + neighbour gather + warp-shuffle bitonic sort
@@ -218,400 +220,10 @@ constexpr int kEpiAgg = 1;     // view-weighted average                 out [B,G
 constexpr int kEpiScore = 2;   // view-weighted average -> MLP          out [B,D,H,W]      (SimilarityNet head, eval mode)
 constexpr int kEpiViewW = 3;   // per-view -> MLP -> max_d -> sigmoid   out [B,V,H,W]      (PixelwiseNet, eval mode)
 
-template <int C, int G, int EPI>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_corr_kernel(const WarpCorrParams p, const MlpParams mlp) {
-    using M = LaneMap<C, G>;
-    constexpr bool kWeighted = (EPI == kEpiAgg || EPI == kEpiScore);
-    constexpr bool kHead = (EPI == kEpiScore || EPI == kEpiViewW);
-    __shared__ float4 s_w[kWarpsPerBlock][M::EPW];
-    __shared__ int s_key[kWarpsPerBlock][M::EPW];
-    // group values of one warp pass, [hypothesis][pixel][group]: the transpose that brings the G
-    // groups of one (pixel, hypothesis) into one thread for the MLP epilogue
-    __shared__ float s_sim[kHead ? kWarpsPerBlock : 1][kHead ? M::EPW * G : 1];
+#include "pm_warpcorr4.cuh"  // K-A generation 4 (default): persistent, warp-specialised, TMA-staged shared-memory windows
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int HW = p.H * p.W;
-    const int n0 = (blockIdx.x * kWarpsPerBlock + warp) * M::PPW;
-    if (n0 >= HW) return;  // no block-level barrier below, whole warps may leave
-    const int b = blockIdx.z, d0 = blockIdx.y * kChunk;
-    const int pi = lane / M::LPP, li = lane % M::LPP;
-    const int n = n0 + pi;
-    const bool live = n < HW;
-    const int nc = live ? n : HW - 1;
-    const int g0 = li * M::GPL;
+constexpr int kWarps2 = 4;  // warps per CTA of the third-generation kernel
 
-    float r[8];
-    load_reference<C, G>(p.ref, (size_t)b * HW + nc, li, r);
-
-    float acc[kChunk][M::GPL];
-#pragma unroll
-    for (int i = 0; i < kChunk; ++i)
-#pragma unroll
-        for (int g = 0; g < M::GPL; ++g) acc[i][g] = 0.0f;
-    float wsum = 1e-5f;  // reference models/patchmatch.py:192
-
-    for (int v = 0; v < p.V; ++v) {
-        float rt[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) rt[i] = __ldg(p.rt + ((size_t)v * p.B + b) * 12 + i);
-
-        // phase 1: one footprint per (pixel, hypothesis) of this warp pass
-        for (int e = lane; e < M::EPW; e += 32) {
-            const int epi = e % M::PPW, edj = e / M::PPW;
-            const int en = n0 + epi, ed = d0 + edj;
-            pm::Cell c;
-            c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
-            c.key = pm::kKeyNone;
-            if (en < HW && ed < p.D) {
-                const float x = (float)(en % p.W), y = (float)(en / p.W);
-                const float dep = __ldg(p.depth + ((size_t)b * p.D + ed) * HW + en);
-                const pm::Ray ray = pm::pixel_ray(rt, x, y);
-                float u, w;
-                pm::project(ray, rt, dep, p.W, p.H, p.sx, p.sy, &u, &w);
-                c = pm::zero_pad_cell(u, w, p.Hs, p.Ws);
-            }
-            s_w[warp][e] = make_float4(c.w00, c.w01, c.w10, c.w11);
-            s_key[warp][e] = c.key;
-        }
-        __syncwarp();
-
-        float wv = 1.0f;
-        if (kWeighted) {
-            wv = __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc);
-            wsum += wv;
-        }
-        const float4 *sv =
-            reinterpret_cast<const float4 *>(p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C) + li * 2;
-
-        // phase 2
-        int pkey = pm::kKeyNone;
-        float T[4][M::GPL];
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int g = 0; g < M::GPL; ++g) T[t][g] = 0.0f;
-#pragma unroll
-        for (int dj = 0; dj < kChunk; ++dj) {
-            const float4 w = s_w[warp][dj * M::PPW + pi];
-            const int key = s_key[warp][dj * M::PPW + pi];
-            float sim[M::GPL];
-#pragma unroll
-            for (int g = 0; g < M::GPL; ++g) sim[g] = 0.0f;
-            if (key != pm::kKeyNone) {
-                if (key != pkey) {
-                    gather_dot<C, G>(sv, key, p.Ws, r, T);
-                    pkey = key;
-                }
-#pragma unroll
-                for (int g = 0; g < M::GPL; ++g)
-                    sim[g] = w.x * T[0][g] + w.y * T[1][g] + w.z * T[2][g] + w.w * T[3][g];
-            }
-            if (kWeighted) {
-#pragma unroll
-                for (int g = 0; g < M::GPL; ++g) acc[dj][g] = fmaf(sim[g], wv, acc[dj][g]);
-            } else if (EPI == kEpiSims) {
-                if (live && d0 + dj < p.D) {
-#pragma unroll
-                    for (int g = 0; g < M::GPL; ++g)
-                        p.out[((((size_t)v * p.B + b) * G + g0 + g) * p.D + d0 + dj) * HW + n] = sim[g];
-                }
-            } else {  // kEpiViewW: stage the per-view similarity for the head
-#pragma unroll
-                for (int g = 0; g < M::GPL; ++g) s_sim[warp][(dj * M::PPW + pi) * G + g0 + g] = sim[g];
-            }
-        }
-        __syncwarp();  // footprints consumed / similarities staged
-
-        if (EPI == kEpiViewW) {
-            // PixelwiseNet (reference models/patchmatch.py:702): sigmoid(MLP(sim)) maximised over hypotheses.
-            // sigmoid is monotonic, so max first, one sigmoid per pixel, then an atomic max across chunks.
-            float best = -INFINITY;
-            for (int e = lane; e < M::EPW; e += 32) {
-                float x[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) x[g] = s_sim[warp][e * G + g];
-                const float y = mlp_eval<G>(mlp, x);
-                if (d0 + e / M::PPW < p.D) best = fmaxf(best, y);
-            }
-#pragma unroll
-            for (int s = M::PPW; s < 32; s <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, s));
-            const int en = n0 + lane;  // lanes 0..PPW-1 own one pixel each
-            if (lane < M::PPW && en < HW) {
-                const float sg = 1.0f / (1.0f + expf(-best));
-                atomicMax(reinterpret_cast<int *>(p.out + ((size_t)b * p.V + v) * HW + en), __float_as_int(sg));
-            }
-            __syncwarp();
-        }
-    }
-
-    if (EPI == kEpiAgg) {
-        if (live) {
-#pragma unroll
-            for (int dj = 0; dj < kChunk; ++dj) {
-                if (d0 + dj < p.D) {
-#pragma unroll
-                    for (int g = 0; g < M::GPL; ++g)
-                        p.out[(((size_t)b * G + g0 + g) * p.D + d0 + dj) * HW + n] = acc[dj][g] / wsum;
-                }
-            }
-        }
-    } else if (EPI == kEpiScore) {
-#pragma unroll
-        for (int dj = 0; dj < kChunk; ++dj)
-#pragma unroll
-            for (int g = 0; g < M::GPL; ++g) s_sim[warp][(dj * M::PPW + pi) * G + g0 + g] = acc[dj][g] / wsum;
-        __syncwarp();
-        for (int e = lane; e < M::EPW; e += 32) {
-            float x[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) x[g] = s_sim[warp][e * G + g];
-            const float y = mlp_eval<G>(mlp, x);
-            const int en = n0 + e % M::PPW, ed = d0 + e / M::PPW;
-            if (en < HW && ed < p.D) p.out[(((size_t)b * p.D + ed) * HW + en) * p.ostride] = y;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K-A, second generation: footprint compaction.
-//
-// The first-generation kernel above re-gathers whenever ANY pixel of the warp changes source cell and
-// runs the blend once per lane-group.  Measured on the 640x512 cascade only 19-31 % of the (pixel,
-// hypothesis, view) footprints differ from the previous hypothesis of the same pixel, but with 8-16
-// pixels per warp "any pixel changed" is true 70 % of the time, so the reuse did not turn into saved
-// issue slots.  Here each warp pass is split differently:
-//   phase 1  (one footprint per lane)   projection + footprint; "new cell" flags are compacted with a
-//            ballot/popc prefix into a dense list of UNIQUE cells; every footprint learns the slot of its
-//            cell through a shuffle prefix-max along the hypothesis axis;
-//   phase 2a (C/8 lanes per unique cell) gather the 4 taps, dot with the pixel's reference vector
-//            (staged in shared memory), store T[tap][group] of that slot in shared memory;
-//   phase 2b (one footprint per lane)   sim[g] = sum_t w_t * T[slot][t][g]; accumulate over views.
-// Gather work is now proportional to the number of unique cells, the blend runs on all 32 lanes for 32
-// different footprints, and the G group values of a footprint end up in one thread, which is exactly
-// what the MLP epilogue needs (no transpose).
-// ------------------------------------------------------------------------------------------
-constexpr int kWarps2 = 4;
-
-// DC = hypothesis rows per warp pass (PPW * DC must be a multiple of 32), U2A = unique cells gathered per
-// lane group and phase-2a iteration (2 doubles the loads in flight per warp).
-template <int C, int G, int EPI, int DC, int U2A>
-__global__ void __launch_bounds__(kWarps2 * 32) warp_corr2_kernel(const WarpCorrParams p, const MlpParams mlp,
-                                                                  float *__restrict__ sims_out) {
-    using M = LaneMap<C, G>;
-    constexpr int EPW = M::PPW * DC;   // footprints per warp pass
-    static_assert(EPW % 32 == 0, "PPW * DC must be a multiple of the warp size");
-    constexpr int NE = EPW / 32;       // footprints per lane (1, 2, 4)
-    constexpr int RPK = 32 / M::PPW;   // hypothesis rows covered by one k (8, 4, 2)
-    constexpr int TS = 4 * G + 4;      // floats per slot in s_T (padded: conflict-free LDS.128 across slots)
-    constexpr bool kWeighted = (EPI == kEpiAgg || EPI == kEpiScore);
-    __shared__ __align__(16) float s_ref[kWarps2][M::PPW * C];
-    __shared__ int2 s_u[kWarps2][EPW];
-    __shared__ __align__(16) float s_T[kWarps2][EPW * TS];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int HW = p.H * p.W;
-    const int n0 = (blockIdx.x * kWarps2 + warp) * M::PPW;
-    if (n0 >= HW) return;  // warp-level barriers only below
-    const int b = blockIdx.z, d0 = blockIdx.y * DC;
-    const unsigned full = 0xffffffffu;
-
-    // reference vectors of this warp's pixels -> shared memory, pre-scaled by 1/(C/G) (exact)
-    {
-        constexpr int V4 = C / 4;
-        constexpr float sc = 1.0f / (float)M::CPG;
-        const float4 *rp = reinterpret_cast<const float4 *>(p.ref + (size_t)b * HW * C);
-#pragma unroll
-        for (int i = lane; i < M::PPW * V4; i += 32) {
-            const int px = i / V4;
-            const int nn = min(n0 + px, HW - 1);
-            float4 q = __ldg(rp + (size_t)nn * V4 + (i % V4));
-            q.x *= sc; q.y *= sc; q.z *= sc; q.w *= sc;
-            reinterpret_cast<float4 *>(s_ref[warp])[i] = q;
-        }
-    }
-
-    const int pi = lane % M::PPW;          // pixel of all of this lane's footprints
-    const int row0 = lane / M::PPW;        // hypothesis row of footprint k is row0 + k * RPK
-    const int n = n0 + pi;
-    const bool live = n < HW;
-    const int nc = live ? n : HW - 1;
-    const float px_x = (float)(nc % p.W), px_y = (float)(nc / p.W);
-    float dep[NE];
-    bool ev[NE];
-#pragma unroll
-    for (int k = 0; k < NE; ++k) {
-        const int d = d0 + row0 + k * RPK;
-        ev[k] = live && d < p.D;
-        dep[k] = ev[k] ? __ldg(p.depth + ((size_t)b * p.D + d) * HW + n) : 1.0f;
-    }
-    float acc[NE][G];
-#pragma unroll
-    for (int k = 0; k < NE; ++k)
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[k][g] = 0.0f;
-    float wsum = 1e-5f;  // reference models/patchmatch.py:192
-    const int li = lane % M::LPP, grp = lane / M::LPP;
-    __syncwarp();
-
-    for (int v = 0; v < p.V; ++v) {
-        float rt[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) rt[i] = __ldg(p.rt + ((size_t)v * p.B + b) * 12 + i);
-        const pm::Ray ray = pm::pixel_ray(rt, px_x, px_y);
-
-        // ---- phase 1 ----
-        float4 w[NE];
-        int key[NE], slot[NE];
-        int nu = 0;
-#pragma unroll
-        for (int k = 0; k < NE; ++k) {
-            pm::Cell c;
-            c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
-            c.key = pm::kKeyNone;
-            if (ev[k]) {
-                float uu, vv;
-                pm::project(ray, rt, dep[k], p.W, p.H, p.sx, p.sy, &uu, &vv);
-                c = pm::zero_pad_cell(uu, vv, p.Hs, p.Ws);
-            }
-            w[k] = make_float4(c.w00, c.w01, c.w10, c.w11);
-            key[k] = c.key;
-            // key of the previous hypothesis row of the same pixel
-            int pk = __shfl_up_sync(full, key[k], M::PPW);
-            if (k > 0) {
-                const int ck = __shfl_sync(full, key[k > 0 ? k - 1 : 0], 32 - M::PPW + pi);
-                if (lane < M::PPW) pk = ck;
-            } else if (lane < M::PPW) {
-                pk = pm::kKeyNone;
-            }
-            const bool isnew = key[k] != pm::kKeyNone && key[k] != pk;
-            const unsigned m = __ballot_sync(full, isnew);
-            int sl = isnew ? nu + __popc(m & ((1u << lane) - 1u)) : -1;
-            if (isnew) s_u[warp][sl] = make_int2(key[k], pi);
-            nu += __popc(m);
-            // slot of the latest new cell at or before this row (prefix max along rows)
-#pragma unroll
-            for (int off = M::PPW; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(full, sl, off);
-                if (lane >= off) sl = max(sl, t);
-            }
-            if (k > 0) {
-                const int cs = __shfl_sync(full, slot[k > 0 ? k - 1 : 0], 32 - M::PPW + pi);
-                sl = max(sl, cs);
-            }
-            slot[k] = sl;
-        }
-        __syncwarp();
-
-        float wv = 1.0f;
-        if (kWeighted) {
-            wv = __ldg(p.vw + ((size_t)b * p.V + v) * HW + nc);
-            wsum += wv;
-        }
-
-        // ---- phase 2a: one unique cell per lane group ----
-        const float4 *sv =
-            reinterpret_cast<const float4 *>(p.src + ((size_t)v * p.B + b) * p.Hs * p.Ws * C) + li * 2;
-        for (int base = 0; base < nu; base += M::PPW * U2A) {
-            int2 u[U2A];
-            bool on[U2A];
-#pragma unroll
-            for (int j = 0; j < U2A; ++j) {
-                const int s = base + j * M::PPW + grp;
-                on[j] = s < nu;
-                u[j] = on[j] ? s_u[warp][s] : make_int2(0, 0);
-            }
-            float T[U2A][4][M::GPL];
-#pragma unroll
-            for (int j = 0; j < U2A; ++j) {
-                if (on[j]) {
-                    float r[8];
-                    const float4 *rr = reinterpret_cast<const float4 *>(s_ref[warp] + u[j].y * C) + li * 2;
-                    const float4 r0 = rr[0], r1 = rr[1];
-                    r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
-                    r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-                    gather_dot<C, G>(sv, u[j].x, p.Ws, r, T[j]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < U2A; ++j) {
-                if (on[j]) {
-                    float *tp = s_T[warp] + (base + j * M::PPW + grp) * TS + li * M::GPL;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if constexpr (M::GPL == 1) tp[t * G] = T[j][t][0];
-                        else *reinterpret_cast<float2 *>(tp + t * G) = make_float2(T[j][t][0], T[j][t][1]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- phase 2b: one footprint per lane ----
-        float best = -INFINITY;  // kEpiViewW only
-#pragma unroll
-        for (int k = 0; k < NE; ++k) {
-            float sim[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) sim[g] = 0.0f;
-            if (key[k] != pm::kKeyNone) {
-                const float4 *tp = reinterpret_cast<const float4 *>(s_T[warp] + slot[k] * TS);
-#pragma unroll
-                for (int q = 0; q < G / 4; ++q) {
-                    const float4 t0 = tp[q], t1 = tp[G / 4 + q], t2 = tp[2 * (G / 4) + q], t3 = tp[3 * (G / 4) + q];
-                    sim[4 * q + 0] = w[k].x * t0.x + w[k].y * t1.x + w[k].z * t2.x + w[k].w * t3.x;
-                    sim[4 * q + 1] = w[k].x * t0.y + w[k].y * t1.y + w[k].z * t2.y + w[k].w * t3.y;
-                    sim[4 * q + 2] = w[k].x * t0.z + w[k].y * t1.z + w[k].z * t2.z + w[k].w * t3.z;
-                    sim[4 * q + 3] = w[k].x * t0.w + w[k].y * t1.w + w[k].z * t2.w + w[k].w * t3.w;
-                }
-            }
-            if (kWeighted) {
-#pragma unroll
-                for (int g = 0; g < G; ++g) acc[k][g] = fmaf(sim[g], wv, acc[k][g]);
-            } else {
-                const int d = d0 + row0 + k * RPK;
-                if ((EPI == kEpiSims || sims_out != nullptr) && ev[k]) {
-                    float *o = (EPI == kEpiSims ? p.out : sims_out) + ((((size_t)v * p.B + b) * G) * p.D + d) * HW + n;
-#pragma unroll
-                    for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = sim[g];
-                }
-                if (EPI == kEpiViewW && ev[k]) best = fmaxf(best, mlp_eval<G>(mlp, sim));
-            }
-        }
-        if (EPI == kEpiViewW) {
-            // PixelwiseNet (reference models/patchmatch.py:702): max over hypotheses of sigmoid(MLP(sim)); sigmoid is
-            // monotonic -> max first, one sigmoid per pixel, atomic max across hypothesis chunks
-#pragma unroll
-            for (int off = M::PPW; off < 32; off <<= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
-            if (lane < M::PPW && live && best > -INFINITY) {
-                const float sg = 1.0f / (1.0f + expf(-best));
-                atomicMax(reinterpret_cast<int *>(p.out + ((size_t)b * p.V + v) * HW + n), __float_as_int(sg));
-            }
-        }
-        __syncwarp();  // s_u / s_T are rewritten by the next view
-    }
-
-    if (EPI == kEpiAgg) {
-#pragma unroll
-        for (int k = 0; k < NE; ++k) {
-            const int d = d0 + row0 + k * RPK;
-            if (ev[k]) {
-                float *o = p.out + (((size_t)b * G) * p.D + d) * HW + n;
-#pragma unroll
-                for (int g = 0; g < G; ++g) o[(size_t)g * p.D * HW] = acc[k][g] / wsum;
-            }
-        }
-    } else if (EPI == kEpiScore) {
-#pragma unroll
-        for (int k = 0; k < NE; ++k) {
-            const int d = d0 + row0 + k * RPK;
-            float x[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) x[g] = acc[k][g] / wsum;
-            const float y = mlp_eval<G>(mlp, x);
-            if (ev[k]) p.out[(((size_t)b * p.D + d) * HW + n) * p.ostride] = y;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // K-A, third generation.  Same three phases as the second, with the profile-driven changes
@@ -1517,28 +1129,19 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
 #else
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// PMB200_WARP_CORR_V1=1 selects the first-generation K-A kernel (kept for A/B measurements)
-int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return (e && e[0]) ? atoi(e) : dflt;
-}
+// ------------------------------------------------------------------------------------------
+// Launch-configuration knobs.  Defaults are the values measured best on B200 (profiles/); a measurement tool
+// (tools/kbench.py) changes them through pmb200_set_tuning().  Nothing in the launch path reads the environment.
+// ------------------------------------------------------------------------------------------
+enum Tune { kTuneKaGen, kTuneKa3Dc, kTuneKa3DcVw, kTuneKa3Pipe, kTuneKa3MinB, kTuneKa4Nw, kTuneKa4Ctas, kTuneKa4Cap, kTuneKa4Grid,
+            kTuneKbTp, kTuneKbDy, kTuneCount };
+const char *const kTuneNames[kTuneCount] = {"ka_gen", "ka3_dc", "ka3_dc_vw", "ka3_pipe", "ka3_minb", "ka4_nw", "ka4_ctas", "ka4_cap",
+                                            "ka4_grid", "kb_tp", "kb_dy"};
+const int kTuneDefaults[kTuneCount] = {4, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0};
+int g_tune[kTuneCount] = {4, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0};
+inline int tune(Tune t) { return __atomic_load_n(&g_tune[t], __ATOMIC_RELAXED); }
 
-bool use_v1() {
-    const char *e = getenv("PMB200_WARP_CORR_V1");  // read per call so tests/benchmarks can toggle it
-    return e && e[0] == '1';
-}
-
-template <int C, int G, int EPI, int DC, int U2A>
-void launch_wc2(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
-    const int HW = p.H * p.W;
-    constexpr int pix_per_block = kWarps2 * LaneMap<C, G>::PPW;
-    dim3 grid((HW + pix_per_block - 1) / pix_per_block, (p.D + DC - 1) / DC, p.B);
-    warp_corr2_kernel<C, G, EPI, DC, U2A><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
-}
-
-// Second-generation K-A launch.  Rows per warp pass (DC) and gather unroll (U2A) default to the values
-// measured best on B200 (profiles/); PMB200_KA_DC / PMB200_KA_U2A override them for the score epilogue
-// only (tuning sweeps, tools/kbench.py).
+// Third-generation K-A launch (kept for shapes generation 4 does not take and for A/B measurements).
 template <int C, int G, int EPI, int DC>
 void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
     const int HW = p.H * p.W;
@@ -1547,18 +1150,11 @@ void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
     // measured on B200 (profiles/r1_run5_kbench.json): the two-deep gather pipeline pays at 8 pixels per warp
     // (C = 32), is neutral at 4 and loses to the higher occupancy of the plain loop at 16
     constexpr int kPipeDefault = LaneMap<C, G>::PPW == 8 ? 1 : 0;
-    const int pipe = env_int("PMB200_KA_PIPE", kPipeDefault);
-    if constexpr (EPI == kEpiScore) {  // occupancy variant for tuning sweeps: 8 resident CTAs (<= 64 registers)
-        if (!pipe && env_int("PMB200_KA_MINB", 6) == 8) {
-            warp_corr3_kernel<C, G, EPI, DC, 0, 8><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
-            return;
-        }
-    }
+    const int pipe = tune(kTuneKa3Pipe) < 0 ? kPipeDefault : tune(kTuneKa3Pipe);
     if constexpr (EPI == kEpiScore && LaneMap<C, G>::PPW == 8) {
-        // sweep candidate (PMB200_KA_MINB=5): the pipelined stage-2 kernel holds 128 registers -> 4 resident CTAs per SM,
-        // 592 on the chip, and its 1280-CTA grid at 128x160 is 2.16 waves; capped at 96 registers (276 bytes of spills)
-        // 5 CTAs fit (shared memory allows exactly 5) -> 1.73 waves.  Not the default until measured.
-        if (pipe && env_int("PMB200_KA_MINB", 4) == 5) {
+        // sweep candidate (ka3_minb = 5): the pipelined stage-2 kernel holds 128 registers -> 4 resident CTAs per SM; capped
+        // at 96 registers 5 fit
+        if (pipe && tune(kTuneKa3MinB) == 5) {
             warp_corr3_kernel<C, G, EPI, DC, 1, 5><<<grid, kWarps2 * 32, 0, st>>>(p, m, sims_out);
             return;
         }
@@ -1574,14 +1170,12 @@ void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
     }
 }
 
-// Third-generation launch: rows per warp pass chosen per lane map (more rows = more reuse along the
-// hypothesis axis, fewer = less shared memory / registers per warp); PMB200_KA_DC overrides (score epilogue).
 template <int C, int G, int EPI>
 void launch_wc3_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
     constexpr int PPW = LaneMap<C, G>::PPW;
     constexpr int kDefault = PPW == 4 ? 16 : (PPW == 8 ? 8 : 4);
-    if constexpr (EPI == kEpiScore || EPI == kEpiViewW) {  // tuning sweeps (tools/kbench.py); unset = the measured defaults below
-        const int d = env_int(EPI == kEpiScore ? "PMB200_KA_DC" : "PMB200_KA_DC_VW", 0);
+    if constexpr (EPI == kEpiScore || EPI == kEpiViewW) {
+        const int d = tune(EPI == kEpiScore ? kTuneKa3Dc : kTuneKa3DcVw);
 #define PMB200_TRY3(DD)                                                                                  \
     if (d == DD) {                                                                                       \
         if constexpr ((PPW * DD) % 32 == 0 && PPW * DD * (4 * G + 4) * 4 * kWarps2 <= 40 * 1024) {       \
@@ -1589,36 +1183,123 @@ void launch_wc3_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_ou
             return;                                                                                      \
         }                                                                                                \
     }
-        PMB200_TRY3(2) PMB200_TRY3(4) PMB200_TRY3(8) PMB200_TRY3(16)
+        PMB200_TRY3(4) PMB200_TRY3(8) PMB200_TRY3(16)
 #undef PMB200_TRY3
     }
     launch_wc3<C, G, EPI, (EPI == kEpiScore ? kDefault : (PPW == 4 ? 8 : kDefault))>(p, m, sims_out, st);
 }
 
-template <int C, int G, int EPI>
-void launch_wc2_auto(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
-    if (env_int("PMB200_KA_GEN", 3) == 3) {
-        launch_wc3_auto<C, G, EPI>(p, m, sims_out, st);
-        return;
+// ------------------------------------------------------------------------------------------
+// Fourth-generation K-A launch: tensor map of the reference pack, ring-slot size from the shared-memory budget,
+// persistent grid from the occupancy.
+// ------------------------------------------------------------------------------------------
+struct DeviceFacts {
+    int sms = 0, smem_optin = 0;
+};
+const DeviceFacts &device_facts() {
+    static thread_local int cached_dev = -1;
+    static thread_local DeviceFacts f;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&f.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cached_dev = dev;
     }
-    constexpr int PPW = LaneMap<C, G>::PPW;
-    if constexpr (EPI == kEpiScore) {
-        const int dc = env_int("PMB200_KA_DC", 0), u2 = env_int("PMB200_KA_U2A", 0);
-        if (dc != 0 || u2 != 0) {
-            const int d = dc ? dc : 8, u = u2 ? u2 : 1;
-#define PMB200_TRY(DD, UU)                                                       \
-    if (d == DD && u == UU) {                                                    \
-        if constexpr ((PPW * DD) % 32 == 0 && PPW * DD * (4 * G + 4) * 4 * kWarps2 <= 40 * 1024) { \
-            launch_wc2<C, G, EPI, DD, UU>(p, m, sims_out, st);                   \
-            return;                                                              \
-        }                                                                        \
-    }
-            PMB200_TRY(2, 1) PMB200_TRY(2, 2) PMB200_TRY(4, 1) PMB200_TRY(4, 2)
-            PMB200_TRY(8, 1) PMB200_TRY(8, 2) PMB200_TRY(16, 1) PMB200_TRY(16, 2)
-#undef PMB200_TRY
+    return f;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+    }();
+    return fn;
+}
+
+// [B][H][W][C] fp32 channels-last tensor, box {C, 8, box_rows, 1}, no swizzle, zero fill outside
+bool make_ref_map(CUtensorMap *tm, const float *ref, int B, int H, int W, int C, int box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)C, 8u, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ref), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool wc4_accepts(const WarpCorrParams &p) {
+    return p.Ws < (1 << wc4::kXBits) && p.Hs < (1 << 15) && p.V <= 32 && (reinterpret_cast<uintptr_t>(p.ref) & 15u) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.src) & 15u) == 0;
+}
+
+template <int C, int G, int EPI, int NW, int MINB>
+bool launch_wc4_nw(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    using L = wc4::Layout<C, G, NW>;
+    const DeviceFacts &dev = device_facts();
+    auto kern = wc4::warp_corr4_kernel<C, G, EPI, NW, MINB>;
+    // ring-slot size: what is left of the per-CTA share of shared memory when `ctas` CTAs are to be resident
+    const int ctas = tune(kTuneKa4Ctas) > 0 ? tune(kTuneKa4Ctas) : MINB;
+    const int share = (dev.smem_optin + 1024) / ctas - 1024;  // 1 KB per CTA is reserved by the runtime
+    int cap = (share - L::fixed_bytes) / (wc4::kStages * C * 4);
+    if (tune(kTuneKa4Cap) > 0) cap = tune(kTuneKa4Cap);
+    const int cap_max = (dev.smem_optin - L::fixed_bytes) / (wc4::kStages * C * 4);
+    if (cap > cap_max) cap = cap_max;
+    if (cap > 1024) cap = 1024;
+    if (cap < 16) return false;
+    const int smem = L::fixed_bytes + wc4::kStages * cap * C * 4;
+    static thread_local int attr_smem = 0;  // per instantiation and host thread
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
         }
+        attr_smem = smem;
     }
-    launch_wc2<C, G, EPI, 8, 1>(p, m, sims_out, st);
+    static thread_local int occ_smem = -1, occ = 0;
+    if (occ_smem != smem) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NW + 1) * 32, smem) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            return false;
+        }
+        occ_smem = smem;
+    }
+    CUtensorMap ref_map;
+    if (!make_ref_map(&ref_map, p.ref, p.B, p.H, p.W, C, NW)) return false;
+    wc4::Params4 q;
+    q.p = p;
+    q.ntx = (p.W + wc4::kTW - 1) / wc4::kTW;
+    q.nty = (p.H + NW - 1) / NW;
+    q.nd = (p.D + wc4::kDItem - 1) / wc4::kDItem;
+    const long long items = (long long)q.ntx * q.nty * q.nd * p.B;
+    if (items > 0x7fffffffLL) return false;
+    q.nitems = (int)items;
+    q.cap = cap;
+    long long grid = (long long)dev.sms * occ;
+    if (tune(kTuneKa4Grid) > 0) grid = tune(kTuneKa4Grid);
+    if (grid > items) grid = items;
+    kern<<<(unsigned)grid, (NW + 1) * 32, smem, st>>>(q, m, sims_out, ref_map);
+    return true;
+}
+
+template <int C, int G, int EPI>
+bool launch_wc4(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    if (!wc4_accepts(p)) return false;
+    const int nw = tune(kTuneKa4Nw) > 0 ? tune(kTuneKa4Nw) : 4;
+    if (nw == 8) return launch_wc4_nw<C, G, EPI, 8, 2>(p, m, sims_out, st);
+    return launch_wc4_nw<C, G, EPI, 4, 3>(p, m, sims_out, st);
+}
+
+// K-A dispatch: generation 4 unless the knob or the shape says otherwise
+template <int C, int G, int EPI>
+void launch_ka(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cudaStream_t st) {
+    if (tune(kTuneKaGen) != 3 && launch_wc4<C, G, EPI>(p, m, sims_out, st)) return;
+    launch_wc3_auto<C, G, EPI>(p, m, sims_out, st);
 }
 
 }  // namespace
@@ -1634,6 +1315,20 @@ int pmb200_internal_fail(int code, const char *msg) { return fail(code, msg); }
 int pmb200_internal_launch_status(const char *what) { return launch_status(what); }
 
 int pmb200_abi_version(void) { return PMB200_ABI_VERSION; }
+
+int pmb200_set_tuning(const char *key, int value) {
+    if (!key) return fail(PMB200_EINVAL, "set_tuning: null key");
+    if (strcmp(key, "reset") == 0) {
+        for (int i = 0; i < kTuneCount; ++i) __atomic_store_n(&g_tune[i], kTuneDefaults[i], __ATOMIC_RELAXED);
+        return 0;
+    }
+    for (int i = 0; i < kTuneCount; ++i)
+        if (strcmp(key, kTuneNames[i]) == 0) {
+            __atomic_store_n(&g_tune[i], value, __ATOMIC_RELAXED);
+            return 0;
+        }
+    return fail(PMB200_EINVAL, "set_tuning: unknown key");
+}
 
 const char *pmb200_last_error(void) { return g_err; }
 
@@ -1719,19 +1414,11 @@ int pmb200_warp_corr(const float *ref_nhwc, const float *src_nhwc, const float *
     const int HW = H * W;
     cudaStream_t st = as_stream(stream);
     const bool fused = view_weights != nullptr;
-    const int nchunk = (D + kChunk - 1) / kChunk;
-    if (nchunk > 65535) return fail(PMB200_EINVAL, "warp_corr: too many hypotheses");
+    if ((D + 3) / 4 > 65535) return fail(PMB200_EINVAL, "warp_corr: too many hypotheses");
 #define PMB200_LAUNCH_WC(CC, GG)                                                                   \
     do {                                                                                           \
-        if (use_v1()) {                                                                            \
-            dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
-                      nchunk, B);                                                                  \
-            if (fused) warp_corr_kernel<CC, GG, kEpiAgg><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());   \
-            else warp_corr_kernel<CC, GG, kEpiSims><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, MlpParams());       \
-        } else {                                                                                   \
-            if (fused) launch_wc2_auto<CC, GG, kEpiAgg>(p, MlpParams(), nullptr, st);                 \
-            else launch_wc2_auto<CC, GG, kEpiSims>(p, MlpParams(), nullptr, st);                      \
-        }                                                                                          \
+        if (fused) launch_ka<CC, GG, kEpiAgg>(p, MlpParams(), nullptr, st);                        \
+        else launch_ka<CC, GG, kEpiSims>(p, MlpParams(), nullptr, st);                             \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_WC(64, 8);
     else if (C == 32 && G == 8) PMB200_LAUNCH_WC(32, 8);
@@ -1766,23 +1453,15 @@ int warp_corr_head(const char *what, int epi, const float *ref_nhwc, const float
     const MlpParams m = to_device_layout(head_host);
     const int HW = H * W;
     cudaStream_t st = as_stream(stream);
-    const int nchunk = (D + kChunk - 1) / kChunk;
-    if (nchunk > 65535) return fail(PMB200_EINVAL, "warp_corr head: too many hypotheses");
+    if ((D + 3) / 4 > 65535) return fail(PMB200_EINVAL, "warp_corr head: too many hypotheses");
     if (epi == kEpiViewW) {  // atomic max target starts at 0 (weights are sigmoids, > 0)
         cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * V * HW * sizeof(float), st);
         if (e != cudaSuccess) return fail((int)e, "warp_corr_view_weights: memset failed");
     }
 #define PMB200_LAUNCH_WH(CC, GG)                                                                   \
     do {                                                                                           \
-        if (use_v1() && sims_out == nullptr) {                                                     \
-            dim3 grid((HW + kWarpsPerBlock * LaneMap<CC, GG>::PPW - 1) / (kWarpsPerBlock * LaneMap<CC, GG>::PPW), \
-                      nchunk, B);                                                                  \
-            if (epi == kEpiScore) warp_corr_kernel<CC, GG, kEpiScore><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m); \
-            else warp_corr_kernel<CC, GG, kEpiViewW><<<grid, kWarpsPerBlock * 32, 0, st>>>(p, m);  \
-        } else {                                                                                   \
-            if (epi == kEpiScore) launch_wc2_auto<CC, GG, kEpiScore>(p, m, nullptr, st);              \
-            else launch_wc2_auto<CC, GG, kEpiViewW>(p, m, sims_out, st);                              \
-        }                                                                                          \
+        if (epi == kEpiScore) launch_ka<CC, GG, kEpiScore>(p, m, nullptr, st);                     \
+        else launch_ka<CC, GG, kEpiViewW>(p, m, sims_out, st);                                     \
     } while (0)
     if (C == 64 && G == 8) PMB200_LAUNCH_WH(64, 8);
     else if (C == 32 && G == 8) PMB200_LAUNCH_WH(32, 8);
@@ -1961,8 +1640,8 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
         TP = 8;
         DY = D < 32 ? D : 32;
     }
-    {   // measurement aid (tools/kbench.py): PMB200_KB_TP / PMB200_KB_DY override the block shape
-        const int etp = env_int("PMB200_KB_TP", 0), edy = env_int("PMB200_KB_DY", 0);
+    {   // measurement aid (tools/kbench.py): kb_tp / kb_dy override the block shape
+        const int etp = tune(kTuneKbTp), edy = tune(kTuneKbDy);
         if (etp > 0 && edy > 0 && etp * edy <= 256 && smem_for(etp) <= 48 * 1024) {
             TP = etp;
             DY = edy < D ? edy : D;

@@ -66,6 +66,13 @@ def _rowmajor_4x4(m: Tensor, name: str) -> Tensor:
     return m
 
 
+def set_tuning(key: str, value: int = 0) -> None:
+    """Measurement aid (tools/kbench.py, A/B tests): override a launch-configuration knob of the library for this process;
+    `set_tuning("reset")` restores every default.  Keys: include/patchmatch_b200.h, pmb200_set_tuning.  Results never depend
+    on these knobs, only launch shapes do."""
+    _native.check(_native.lib().pmb200_set_tuning(key.encode(), int(value)), "set_tuning")
+
+
 def relative_projection(ref_proj: Tensor, src_projs: Sequence[Tensor]) -> Tensor:
     """[V,B,12] rotation/translation of src_proj @ inv(ref_proj); reference module.py:148-150."""
     B = ref_proj.shape[0]
@@ -169,7 +176,13 @@ def conv_prefers_native(cin: int, cout: int, ks: int) -> bool:
     head, the stage-1 offset conv: 1.2-3.7x faster than the library) -- while the FLOP-heavy 16..64-channel 3x3 / 5x5
     layers stay with cuDNN, whose tcgen05 implicit-GEMM kernels reach 100-150 TFLOP/s there against ~50 for the
     legacy mma.sync path this kernel issues (measured peak of that path: ~245 TFLOP/s TF32)."""
-    return NATIVE_CONVS and (NATIVE_CONVS_ALL or ks == 1 or cin * cout * ks * ks <= 3200)
+    if not NATIVE_CONVS:
+        return False
+    # fp32-accurate mode (cudnn.allow_tf32 off): the library's fp32 kernels for the FLOP-bound layers do not use the tensor
+    # cores at all (value_fp32 of profiles/r2_run1_bench.json: 2.62 ms per forward against 0.755), the native 3xTF32 kernel
+    # does -> every conv native.  The parity configuration and the bench default are this mode (the depth maps of the TF32
+    # mode are 2.6e-3 .. 3.3e-3 off the fp32 reference, outside north_star's 1e-3: tests/test_gpu_bench_mode.py).
+    return NATIVE_CONVS_ALL or conv_precision() == 3 or ks == 1 or cin * cout * ks * ks <= 3200
 
 
 def _round_kcin(cin: int) -> int:

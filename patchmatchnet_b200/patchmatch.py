@@ -47,7 +47,8 @@ def _offset_conv(conv: nn.Conv2d, x: Tensor, native: bool) -> Tensor:
     """propa_conv / eval_conv (reference patchmatch.py:288-311, called at :486 / :498).  `native`: the channels-last
     tensor-core conv of csrc/pm_conv.cu (its channels-last output is what the fused kernels consume in place); the
     fragment-ordered filter is cached off the module (TorchScript would try to type the attribute)."""
-    if not native or not ops.conv_prefers_native(conv.in_channels, conv.out_channels, conv.kernel_size[0]):
+    if (not native or max(conv.in_channels, conv.out_channels) > 64
+            or not ops.conv_prefers_native(conv.in_channels, conv.out_channels, conv.kernel_size[0])):
         return conv(x)
     srcs = (conv.weight, conv.bias)
     prec = ops.conv_precision()
@@ -252,11 +253,16 @@ class PatchMatch(nn.Module):
             self._head_pw = self.evaluation.pixel_wise_net.folded_tensor()
             self._head_sim = self.evaluation.similarity_net.folded_tensor()
         self._conv_precision = ops.conv_precision()
-        self._native_propa = ops.conv_prefers_native(self.propa_conv.in_channels, self.propa_conv.out_channels, 3)
-        self._native_eval = ops.conv_prefers_native(self.eval_conv.in_channels, self.eval_conv.out_channels, 3)
+        # the native conv takes 1..64 channels; wider layers (a valid reference configuration, e.g. num_feature=128)
+        # stay with the library conv instead of failing in eval()
+        fits = lambda conv: max(conv.in_channels, conv.out_channels) <= 64
+        self._native_propa = fits(self.propa_conv) and ops.conv_prefers_native(self.propa_conv.in_channels, self.propa_conv.out_channels, 3)
+        self._native_eval = fits(self.eval_conv) and ops.conv_prefers_native(self.eval_conv.in_channels, self.eval_conv.out_channels, 3)
         with torch.no_grad():
-            self._off_propa_frag = ops.pack_conv_filter(self.propa_conv.weight, self._conv_precision).cpu()
-            self._off_eval_frag = ops.pack_conv_filter(self.eval_conv.weight, self._conv_precision).cpu()
+            if self._native_propa:
+                self._off_propa_frag = ops.pack_conv_filter(self.propa_conv.weight, self._conv_precision).cpu()
+            if self._native_eval:
+                self._off_eval_frag = ops.pack_conv_filter(self.eval_conv.weight, self._conv_precision).cpu()
 
     def train(self, mode: bool = True):
         super().train(mode)

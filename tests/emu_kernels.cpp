@@ -45,9 +45,59 @@ int run_wc3_epi(const WarpCorrParams &p, const MlpParams &m, float *sims_out, in
     return -2;
 }
 
+// K-A, fourth generation: persistent producer / consumer pipeline (pm_warpcorr4.cuh).  The TMA engine is emulated by
+// immediate copies that complete their mbarrier transactions; the producer warp and the consumer warps are fibers like any
+// other thread, an mbarrier wait yields until the phase flips.
+template <int C, int G, int EPI, int NW>
+int run_wc4(const WarpCorrParams &p, const MlpParams &m, float *sims_out, int cap, int grid) {
+    using L = wc4::Layout<C, G, NW>;
+    wc4::Params4 q;
+    q.p = p;
+    q.ntx = (p.W + wc4::kTW - 1) / wc4::kTW;
+    q.nty = (p.H + NW - 1) / NW;
+    q.nd = (p.D + wc4::kDItem - 1) / wc4::kDItem;
+    q.nitems = q.ntx * q.nty * q.nd * p.B;
+    q.cap = cap;
+    const wc4::TensorMap tm{p.ref, p.B, p.H, p.W, C, NW};
+    const size_t smem = (size_t)L::fixed_bytes + (size_t)wc4::kStages * cap * C * 4;
+    if (grid < 1 || grid > q.nitems) grid = q.nitems;
+    emu::launch(dim3(grid), dim3((NW + 1) * 32), smem, [&] { wc4::warp_corr4_kernel<C, G, EPI, NW, 1>(q, m, sims_out, tm); });
+    return 0;
+}
+
+template <int C, int G>
+int run_wc4_epi(const WarpCorrParams &p, const MlpParams &m, float *sims_out, int epi, int nw, int cap, int grid) {
+#define EMU_TRY4(EE, NN) \
+    if (epi == EE && nw == NN) return run_wc4<C, G, EE, NN>(p, m, sims_out, cap, grid);
+    EMU_TRY4(kEpiSims, 4) EMU_TRY4(kEpiAgg, 4) EMU_TRY4(kEpiScore, 4) EMU_TRY4(kEpiViewW, 4)
+    EMU_TRY4(kEpiSims, 8) EMU_TRY4(kEpiAgg, 8) EMU_TRY4(kEpiScore, 8) EMU_TRY4(kEpiViewW, 8)
+#undef EMU_TRY4
+    return -2;
+}
+
 }  // namespace
 
 extern "C" {
+
+// K-A, fourth generation.  Same epilogue numbering as emu_warp_corr3; nw = consumer warps (tile rows), cap = texels per
+// window slot (small values force the global-memory fallback of the gather), grid = persistent CTAs (fewer than items
+// makes every CTA walk several items through the rings).
+int emu_warp_corr4(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth, const float *vw,
+                   const pmb200_mlp *head, float *out, float *sims_out, int ostride, int V, int B, int C, int G, int H, int W,
+                   int Hs, int Ws, int D, int epi, int nw, int cap, int grid) {
+    WarpCorrParams p;
+    p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = vw; p.out = out;
+    p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
+    p.sx = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 1.0f;
+    p.sy = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 1.0f;
+    p.ostride = ostride < 1 ? 1 : ostride;
+    MlpParams m{};
+    if (head) m = to_device_layout(head);
+    if (C == 64 && G == 8) return run_wc4_epi<64, 8>(p, m, sims_out, epi, nw, cap, grid);
+    if (C == 32 && G == 8) return run_wc4_epi<32, 8>(p, m, sims_out, epi, nw, cap, grid);
+    if (C == 16 && G == 4) return run_wc4_epi<16, 4>(p, m, sims_out, epi, nw, cap, grid);
+    return -2;
+}
 
 // K-A, third generation.  epi: 0 per-view sims [V,B,G,D,H,W], 1 weighted average [B,G,D,H,W], 2 score [B,D,H,W]*ostride,
 // 3 view weights [B,V,H,W] (out must be zero-filled; sims_out optional).  Returns -2 for a combination that is not built.

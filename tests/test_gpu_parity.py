@@ -185,30 +185,37 @@ def test_warp_corr_matches_oracle(C, G, H, W, D, B, V):
     assert maxabs(got_a, want_f) <= 2e-5 * max(1.0, scale)
 
 
-def test_warp_corr_generations_agree(monkeypatch):
-    """The kernel generations kept for A/B measurements (first: PMB200_WARP_CORR_V1=1, second: PMB200_KA_GEN=2,
-    third: default, with/without the two-deep gather pipeline) are schedules of the same arithmetic; the third
-    uses a reciprocal instead of two divisions in the projection, hence the 1e-4 (not 1e-6) agreement bound."""
-    from patchmatchnet_b200.patchmatch import SimilarityNet
+def test_warp_corr_generations_agree():
+    """Generation 4 (default: persistent pipeline over TMA-staged windows; 4 or 8 consumer warps, a window slot too small
+    for most boxes so that cells take the global path, a grid of 5 CTAs so that every CTA walks many items through its
+    rings) and generation 3 (register / L1 gather, with and without the two-deep pipeline) are schedules of the same
+    arithmetic with different summation orders of the channel dot products: 1e-4 agreement."""
+    from patchmatchnet_b200.patchmatch import PixelwiseNet, SimilarityNet
 
-    variants = [dict(PMB200_WARP_CORR_V1="1"), dict(PMB200_KA_GEN="2"), dict(PMB200_KA_GEN="3", PMB200_KA_PIPE="0"),
-                dict(PMB200_KA_GEN="3", PMB200_KA_PIPE="1"), dict(PMB200_KA_GEN="3", PMB200_KA_DC="8", PMB200_KA_PIPE="1")]
-    for (C, G, H, W, D, B, V) in [(64, 8, 13, 21, 20, 2, 3), (32, 8, 19, 27, 16, 1, 2), (16, 4, 22, 35, 8, 2, 4)]:
-        ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=77)
-        rt = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs])
-        ref_n, src_n = nhwc(ref.to(DEV)), torch.stack([nhwc(s.to(DEV)) for s in srcs])
-        head = _random_head(SimilarityNet, G, 5).to(DEV)
-        outs = []
-        for env in variants:
-            for k in ("PMB200_WARP_CORR_V1", "PMB200_KA_GEN", "PMB200_KA_PIPE", "PMB200_KA_DC"):
-                monkeypatch.delenv(k, raising=False)
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
-            outs.append((ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G), ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV)),
-                         ops.warp_corr_score(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV), head.folded())))
-        for other in outs[1:]:
-            for a, b in zip(outs[0], other):
-                assert maxabs(a, b) <= 1e-4 * max(1.0, float(a.abs().max()))
+    variants = [dict(ka_gen=3, ka3_pipe=0), dict(ka_gen=3, ka3_pipe=1), dict(ka_gen=3, ka3_dc=8, ka3_pipe=1),
+                dict(ka_gen=4), dict(ka_gen=4, ka4_nw=8), dict(ka_gen=4, ka4_nw=4, ka4_cap=24, ka4_grid=5),
+                dict(ka_gen=4, ka4_nw=8, ka4_cap=40, ka4_grid=3)]
+    try:
+        for (C, G, H, W, D, B, V) in [(64, 8, 13, 21, 20, 2, 3), (32, 8, 19, 27, 16, 1, 2), (16, 4, 22, 35, 8, 2, 4), (32, 8, 64, 80, 16, 1, 4)]:
+            ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, seed=77)
+            rt = ops.relative_projection(ref_proj.to(DEV), [m.to(DEV) for m in src_projs])
+            ref_n, src_n = nhwc(ref.to(DEV)), torch.stack([nhwc(s.to(DEV)) for s in srcs])
+            head = _random_head(SimilarityNet, G, 5).to(DEV)
+            pw = _random_head(PixelwiseNet, G, 6).to(DEV)
+            outs = []
+            for knobs in variants:
+                ops.set_tuning("reset")
+                for k, v in knobs.items():
+                    ops.set_tuning(k, v)
+                vwo, sims = ops.warp_corr_view_weights(ref_n, src_n, rt, depth.to(DEV), G, pw.folded(), keep_sims=True)
+                outs.append((ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G), ops.warp_corr(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV)),
+                             ops.warp_corr_score(ref_n, src_n, rt, depth.to(DEV), G, vw.to(DEV), head.folded()), vwo, sims))
+            torch.cuda.synchronize()
+            for other in outs[1:]:
+                for a, b in zip(outs[0], other):
+                    assert maxabs(a, b) <= 1e-4 * max(1.0, float(a.abs().max()))
+    finally:
+        ops.set_tuning("reset")
 
 
 def test_warp_corr_source_map_of_other_size():

@@ -18,6 +18,7 @@ from patchmatchnet_b200 import ops, synthetic  # noqa: E402
 
 dev = "cuda:0"
 torch.backends.cudnn.benchmark = True
+torch.backends.cudnn.allow_tf32 = os.environ.get("PM_TF32", "0") == "1"  # default: the fp32-accurate mode bench.py times
 H, W = int(os.environ.get("KB_H", 512)), int(os.environ.get("KB_W", 640))
 net, _ = bench.build_net()
 net = net.to(dev)
@@ -68,11 +69,21 @@ def timeit(fn, iters=12):
 
 
 out = {"shape": f"{W}x{H}", "rows": []}
-variants = ([dict(PMB200_WARP_CORR_V1="1"), dict(PMB200_KA_GEN="2")]
-            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE=str(pp)) for d, pp in itertools.product((0, 4, 8, 16), (0, 1))]
-            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE="0", PMB200_KA_MINB="8") for d in (0, 4, 8, 16)]
-            # C32 only (8 pixels per warp): pipelined gather capped at 96 registers -> 5 resident CTAs instead of 4
-            + [dict(PMB200_KA_GEN="3", PMB200_KA_DC=str(d), PMB200_KA_PIPE="1", PMB200_KA_MINB="5") for d in (0, 8, 16)])
+
+
+def with_knobs(knobs, fn):
+    ops.set_tuning("reset")
+    for kk, vv in knobs.items():
+        ops.set_tuning(kk, vv)
+    try:
+        return timeit(fn)
+    finally:
+        ops.set_tuning("reset")
+
+
+# K-A: generation 4 (consumer warps x resident CTAs the ring is sized for) against generation 3 (rows per pass x pipeline)
+ka_variants = ([dict(ka_gen=4, ka4_nw=nw, ka4_ctas=c) for nw, c in ((4, 2), (4, 3), (4, 4), (4, 5), (8, 1), (8, 2), (8, 3))]
+               + [dict(ka_gen=3)] + [dict(ka_gen=3, ka3_dc=d, ka3_pipe=pp) for d, pp in itertools.product((4, 8, 16), (0, 1))])
 for (n, a, k) in calls:
     desc = n
     if n.startswith("warp_corr"):
@@ -87,23 +98,12 @@ for (n, a, k) in calls:
     row = {"call": desc, "default_us": timeit(lambda: origs[n](*a, **k))}
     if n == "adaptive_eval" and os.environ.get("KB_SWEEP_EVAL", "1") == "1":
         for tp, dy in ((32, 8), (32, 4), (16, 16), (16, 8), (8, 32), (8, 16), (64, 4), (32, 2)):
-            os.environ["PMB200_KB_TP"], os.environ["PMB200_KB_DY"] = str(tp), str(dy)
-            row[f"TP={tp},DY={dy}"] = timeit(lambda: origs[n](*a, **k))
-            os.environ.pop("PMB200_KB_TP", None)
-            os.environ.pop("PMB200_KB_DY", None)
-    if n == "warp_corr_view_weights" and os.environ.get("KB_SWEEP_KA", "1") == "1":
-        for dc, pp in itertools.product((8, 16), (0, 1)):  # rows per warp pass / gather pipeline of the view-weights epilogue
-            os.environ["PMB200_KA_DC_VW"], os.environ["PMB200_KA_PIPE"] = str(dc), str(pp)
-            row[f"DC_VW={dc},PIPE={pp}"] = timeit(lambda: origs[n](*a, **k))
-            os.environ.pop("PMB200_KA_DC_VW", None)
-            os.environ.pop("PMB200_KA_PIPE", None)
-    if n == "warp_corr_score" and os.environ.get("KB_SWEEP_KA", "1") == "1":
-        for v in variants:
-            for kk, vv in v.items():
-                os.environ[kk] = vv
-            tag = ",".join(f"{kk[7:]}={vv}" for kk, vv in v.items())
-            row[tag] = timeit(lambda: origs[n](*a, **k))
-            for kk in v:
-                os.environ.pop(kk, None)
+            row[f"TP={tp},DY={dy}"] = with_knobs(dict(kb_tp=tp, kb_dy=dy), lambda: origs[n](*a, **k))
+    if n in ("warp_corr_score", "warp_corr_view_weights") and os.environ.get("KB_SWEEP_KA", "1") == "1":
+        for v in ka_variants:
+            if n == "warp_corr_view_weights" and "ka3_dc" in v:
+                v = {("ka3_dc_vw" if kk == "ka3_dc" else kk): vv for kk, vv in v.items()}
+            tag = ",".join(f"{kk}={vv}" for kk, vv in v.items())
+            row[tag] = with_knobs(v, lambda: origs[n](*a, **k))
     out["rows"].append(row)
 print(json.dumps(out, indent=1))

@@ -19,6 +19,7 @@ ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
 dev = "cuda:0"
 torch.backends.cudnn.benchmark = True
+torch.backends.cudnn.allow_tf32 = os.environ.get("PM_TF32", "0") == "1"  # default: the fp32-accurate mode bench.py times
 net, _ = bench.build_net()
 net = net.to(dev)
 inp = synthetic.make_inputs(a.batch, a.views, a.height, a.width, seed=0)
