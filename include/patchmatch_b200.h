@@ -46,11 +46,30 @@ const char *pmb200_last_error(void);
 /* Measurement aid (tools/kbench.py, A/B tests): override a launch-configuration knob of the library for this process.
  * Keys: "ka_gen" (3 | 4: generation of the fused warp+correlation kernel), "ka3_dc", "ka3_dc_vw", "ka3_pipe", "ka3_minb"
  * (generation-3 rows per pass / gather pipeline / resident CTAs), "ka4_nw" (4 | 8 consumer warps = tile rows), "ka4_ctas"
- * (resident CTAs per SM the window ring is sized for), "ka4_cap" (texels per ring slot), "ka4_grid" (persistent CTAs),
+ * (resident CTAs per SM the window ring is sized for), "ka4_cap" (texels per ring slot), "ka4_stages" (ring depth 2..4), "ka4_grid" (persistent CTAs),
  * "kb_tp", "kb_dy" (block shape of the adaptive-evaluation kernel); 0 = the built-in default.  "reset" restores every
  * default.  Results never depend on these knobs, only launch shapes do.  Returns 0, or PMB200_EINVAL for an unknown key.
  * The reference has no counterpart (its launch shapes are ATen's). */
 int pmb200_set_tuning(const char *key, int value);
+
+/* ------------------------------------------------------------------------------------
+ * K-D5: channels-last convolution on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), fp32-accurate (3xTF32 split).
+ * Replaces, for the FLOP-bound layers in the fp32-accurate mode, the nn.Conv2d calls of reference models/net.py:9-70 (FeatureNet
+ * conv2..10), models/patchmatch.py:288-311 (stage-2/3 offset convs), models/net.py:73-122 (Refinement).
+ *   x_nhwc      [N,H,W,Cin] fp32, 16-byte aligned, Cin in {8,16,32,64}
+ *   filter_tc5  pmb200_conv2d_tc5_filter_floats(Cin,Cout,KS) floats: [tap ky*KS+kx][hi, lo][Cin/32 blocks (1 if Cin <= 32)]
+ *               [Npad = Cout rounded up to 16 rows][min(Cin,32) channels], every [Npad][row bytes] tile stored in the tensor
+ *               core's K-major shared-memory swizzle for that row size (16-byte chunk j of row r sits at chunk
+ *               j ^ (r % 8) for 128-byte rows, j ^ ((r / 2) % 4) for 64-byte rows, j ^ ((r / 4) % 2) for 32-byte rows);
+ *               hi = weight rounded to TF32, lo = (weight - hi) rounded to TF32; rows >= Cout are zero
+ *   y_nhwc      [N,Ho,Wo,y_channel_stride]; channels y_channel_offset .. +Cout are written
+ * Ho = (H + 2 pad - dil (KS-1) - 1) / stride + 1.  bias may be NULL.  relu != 0 applies max(.,0).
+ * pmb200_conv2d_tc5_supported: 1 when (Cin, Cout, KS, stride) is served (KS in {1,3,5}, stride in {1,2}, Cout <= 64). */
+int pmb200_conv2d_tc5_supported(int Cin, int Cout, int KS, int stride);
+int pmb200_conv2d_tc5_filter_floats(int Cin, int Cout, int KS);
+int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float *bias, float *y_nhwc, int N, int H, int W, int Cin,
+                      int Cout, int KS, int stride, int pad, int dil, int relu, int y_channel_stride, int y_channel_offset,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Relative projections for every (source view, batch element):

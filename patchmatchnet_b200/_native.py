@@ -17,7 +17,7 @@ from typing import Optional
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libpmb200.so")
-SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in ("pm_kernels.cu", "pm_backward.cu", "pm_conv.cu", "pm_geo.cu", "pm_mapio.cpp")]
+SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in ("pm_kernels.cu", "pm_backward.cu", "pm_conv.cu", "pm_conv5.cu", "pm_geo.cu", "pm_mapio.cpp")]
 HEADERS = [
     os.path.join(_PKG_DIR, "csrc", "pm_math.cuh"),
     os.path.join(_PKG_DIR, "csrc", "pm_warpcorr4.cuh"),
@@ -112,6 +112,9 @@ _SIGNATURES = {
     "pmb200_upsample2x_add_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "pmb200_conv2d_filter_floats": (c_int, [c_int] * 4),
     "pmb200_conv2d_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 15 + [c_void_p]),
+    "pmb200_conv2d_tc5_supported": (c_int, [c_int] * 4),
+    "pmb200_conv2d_tc5_filter_floats": (c_int, [c_int] * 3),
+    "pmb200_conv2d_tc5": (c_int, [c_void_p] * 4 + [c_int] * 13 + [c_void_p]),
     "pmb200_geometric_filter": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_double, c_float, c_float, c_int] + [c_void_p] * 5),
     "pmb200_map_probe": (c_int, [c_char_p, c_int, _PMAP]),
     "pmb200_map_read": (c_int, [c_char_p, c_int, c_void_p, c_int64, _PMAP]),

@@ -1,0 +1,395 @@
+// pm_conv5.cu -- K-D5: channels-last 2-D convolution as an implicit GEMM on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA), fp32-accurate through the error-compensated
+// 3xTF32 split.  Serves the FLOP-bound layers of the cascade in the fp32-accurate (timed, parity) mode: FeatureNet conv2..10
+// (reference models/net.py:9-70), the stage-2/3 offset convs (models/patchmatch.py:288-311), Refinement's 16->8 conv
+// (models/net.py:73-122).  The memory-bound layers and everything with a fused epilogue stay on pm_conv.cu (mma.sync).
+//
+// GEMM view: D[128 output pixels, Cout] = sum over filter taps of A_tap[128, Cin] . W_tap[Cin, Cout].
+//   * A_tap is ONE TMA box per tap: tensor map over the channels-last input {Cin, W, H, N}, box {<=32 channels, 16*s, 8*s, 1}
+//     with element strides {1, s, s, 1} (s = conv stride), placed at (x0*s + kx*dil - pad, y0*s + ky*dil - pad): the
+//     padding border and the map edge come back as zeros from the copy engine, the 128 pixels of the 16 x 8 output tile
+//     land as 128 rows of a K-major operand in the shared-memory swizzle (32 / 64 / 128 B = row bytes) tcgen05 reads.
+//   * W_tap (hi and lo parts, Cout padded to a multiple of 16) is pre-packed by the host IN that shared-memory image
+//     (ops.pack_conv_filter_tc5) and fetched with one bulk copy per tap.
+//   * 3xTF32: four "worker" warps split every landed A tile in place into A_hi (13 low mantissa bits cleared -- what the
+//     tensor core would read anyway) and A_lo = A - A_hi (exact), then the MMA warp issues per 8-channel slice
+//     A_lo.W_hi, A_hi.W_lo, A_hi.W_hi into the same fp32 TMEM accumulator: >= 21 bits of every product.
+//   * Epilogue: tcgen05.ld (32 lanes x 32 bit, 16 columns at a time) -> bias, ReLU -> channels-last stores (channel slice
+//     of a wider tensor allowed).
+// Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = split + epilogue.
+// Persistent CTAs walk tiles blockIdx.x, +gridDim.x, ...; an S-deep ring of (A, A_lo, W_hi, W_lo) stages decouples the roles;
+// every mbarrier wait is bounded (a pipeline bug traps instead of hanging the GPU).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/patchmatch_b200.h"
+
+extern "C" int pmb200_internal_fail(int code, const char *msg);
+extern "C" int pmb200_internal_launch_status(const char *what);
+
+namespace {
+
+constexpr int kTW = 16, kTH = 8;  // output tile: 128 pixels = the M of one UMMA
+constexpr int kThreads = 192;
+
+struct Conv5Params {
+    const float *wpack;  // [tap][hi|lo][kblock][Npad rows][RB bytes], swizzled image
+    const float *bias;
+    float *y;
+    int N, H, W, Ho, Wo, Cin, Cout, Npad, KS, S, pad, dil, relu, ycs, yco;
+    int tiles_x, tiles_y, total_tiles;
+    int RB;        // row bytes of one K block: min(Cin, 32) * 4
+    int KB;        // K blocks: Cin / 32 (1 when Cin <= 32)
+    int stages;
+    int a_bytes;   // 128 * RB * KB
+    int w_bytes;   // Npad * RB * KB (one of hi / lo)
+    int stage_bytes;
+    uint32_t idesc;
+    uint32_t layout_type;  // UMMA smem-descriptor swizzle code: 2 = 128B, 4 = 64B, 6 = 32B
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(b)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin)
+        if (mbar_try_wait(b, parity)) return;
+    __trap();
+}
+__device__ __forceinline__ void tma_box_4d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<unsigned long long>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {  // arrives on `bar` once every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile in the 32/64/128-byte swizzle: rows of RB bytes, 8-row groups 8*RB apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t RB, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);              // start address
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major): 1
+    d |= (uint64_t)(((8 * RB) >> 4) & 0x3fff) << 32;    // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ unsigned char smem_raw[];
+    // the swizzled operand tiles need 1024-byte alignment: align the dynamic segment by hand (the launch adds the slack)
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // [0, 256): barriers + TMEM address; stages start at 1024
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);  // [stages]  TMA landed
+    uint64_t *split = full + 8;                            // [stages]  A_hi / A_lo written
+    uint64_t *empty = split + 8;                           // [stages]  MMAs that read the stage have completed
+    uint64_t *acc_full = empty + 8;                        // tile accumulated
+    uint64_t *acc_empty = acc_full + 1;                    // epilogue has read the accumulator
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
+    unsigned char *stage0 = smem + 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: Npad fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int T = p.KS * p.KS;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            int s = 0;
+            uint32_t par = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n = tile / per_img, tt = tile - n * per_img;
+                const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+                const int x_in0 = tx * kTW * p.S - p.pad, y_in0 = ty * kTH * p.S - p.pad;
+                for (int t = 0; t < T; ++t) {
+                    mbar_wait(&empty[s], par ^ 1u);
+                    unsigned char *st = stage0 + (size_t)s * p.stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(p.a_bytes + 2 * p.w_bytes));
+                    const int ky = t / p.KS, kx = t - ky * p.KS;
+                    for (int kb = 0; kb < p.KB; ++kb)
+                        tma_box_4d(st + (size_t)kb * 128 * p.RB, &xmap, kb * 32, x_in0 + kx * p.dil, y_in0 + ky * p.dil, n, &full[s]);
+                    bulk_g2s(st + 2 * (size_t)p.a_bytes, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)t * 2 * p.w_bytes,
+                             (uint32_t)(2 * p.w_bytes), &full[s]);
+                    if (++s == p.stages) { s = 0; par ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------- MMA issuer -------------------------------------------------
+        int s = 0;
+        uint32_t par = 0, acc_par = 0;
+        const int kslices = p.Cin / 8;
+        const int per_row = p.RB / 32;  // 8-channel slices per operand row
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(acc_empty, acc_par ^ 1u);  // the epilogue of the previous tile has drained the accumulator
+            tc_fence_after();
+            for (int t = 0; t < T; ++t) {
+                mbar_wait(&split[s], par);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(stage0 + (size_t)s * p.stage_bytes);
+                    const uint32_t a_lo = a_hi + p.a_bytes, w_hi = a_lo + p.a_bytes, w_lo = w_hi + p.w_bytes;
+                    for (int k = 0; k < kslices; ++k) {
+                        const uint32_t kb = k / per_row, kin = (k % per_row) * 32;
+                        const uint32_t ao = kb * 128 * p.RB + kin, wo = kb * p.Npad * p.RB + kin;
+                        const uint64_t dah = make_desc(a_hi + ao, p.RB, p.layout_type), dal = make_desc(a_lo + ao, p.RB, p.layout_type);
+                        const uint64_t dwh = make_desc(w_hi + wo, p.RB, p.layout_type), dwl = make_desc(w_lo + wo, p.RB, p.layout_type);
+                        tc_mma_tf32(tmem, dal, dwh, p.idesc, (t | k) != 0);  // small terms first
+                        tc_mma_tf32(tmem, dah, dwl, p.idesc, 1);
+                        tc_mma_tf32(tmem, dah, dwh, p.idesc, 1);
+                    }
+                    tc_commit(&empty[s]);                    // stage free once these MMAs have read it
+                    if (t == T - 1) tc_commit(acc_full);     // accumulator complete
+                }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; par ^= 1u; }
+            }
+            acc_par ^= 1u;
+        }
+    } else {
+        // ------------------------------------------- split (3xTF32) + epilogue -------------------------------------------
+        const int wt = threadIdx.x - 64;     // 0..127: operand row handled in the split, accumulator lane in the epilogue
+        const int quad = warp & 3;           // TMEM lane quadrant this warp may read: lanes 32*quad .. 32*quad+31
+        const int row = quad * 32 + lane;    // accumulator row = pixel of the tile
+        int s = 0;
+        uint32_t par = 0, acc_par = 0;
+        const int chunks = p.RB / 16;        // 16-byte chunks per operand row of one K block
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int t = 0; t < T; ++t) {
+                mbar_wait(&full[s], par);
+                unsigned char *a = stage0 + (size_t)s * p.stage_bytes;
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    unsigned char *rowp = a + (size_t)kb * 128 * p.RB + (size_t)wt * p.RB;
+                    for (int j = 0; j < chunks; ++j) {
+                        const int c = (j + wt) & (chunks - 1);  // rotated: the 8 lanes of a quarter-warp hit different banks
+                        float4 *q = reinterpret_cast<float4 *>(rowp + c * 16);
+                        const float4 v = *q;
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                        *q = h;
+                        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(q) + p.a_bytes) = l;
+                    }
+                }
+                proxy_fence_async();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+                if (++s == p.stages) { s = 0; par ^= 1u; }
+            }
+            // ---- epilogue of this tile ----
+            mbar_wait(acc_full, acc_par);
+            tc_fence_after();
+            const int n = tile / per_img, tt = tile - n * per_img;
+            const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+            const int oy = ty * kTH + row / kTW, ox = tx * kTW + row % kTW;
+            const bool inside = oy < p.Ho && ox < p.Wo;
+            float *dst = p.y + (((size_t)n * p.Ho + (inside ? oy : 0)) * p.Wo + (inside ? ox : 0)) * p.ycs + p.yco;
+            const bool vec4 = ((p.ycs | p.yco) & 3) == 0;
+            for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+                if (c0 + 16 >= p.Npad) {  // last read of the accumulator: hand it back before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
+                if (!inside) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int co = c0 + i;
+                    float o = v[i] + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.0f);
+                    v[i] = p.relu ? fmaxf(o, 0.0f) : o;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const int co = c0 + i;
+                    if (co + 3 < p.Cout && vec4) {
+                        *reinterpret_cast<float4 *>(dst + co) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (co + e < p.Cout) dst[co + e] = v[i + e];
+                    }
+                }
+            }
+            acc_par ^= 1u;
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+    }();
+    return fn;
+}
+
+int npad_of(int cout) { return (cout + 15) / 16 * 16; }
+
+}  // namespace
+
+extern "C" {
+
+// 1 when pmb200_conv2d_tc5 takes this layer
+int pmb200_conv2d_tc5_supported(int Cin, int Cout, int KS, int stride) {
+    const bool cin_ok = Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64;
+    return (cin_ok && Cout >= 1 && Cout <= 64 && (KS == 1 || KS == 3 || KS == 5) && (stride == 1 || stride == 2)) ? 1 : 0;
+}
+
+// floats of the packed filter: [tap][hi|lo][Cin/32 blocks][Npad rows][min(Cin,32)] (ops.pack_conv_filter_tc5)
+int pmb200_conv2d_tc5_filter_floats(int Cin, int Cout, int KS) {
+    if (!pmb200_conv2d_tc5_supported(Cin, Cout, KS, 1)) return -1;
+    return KS * KS * 2 * npad_of(Cout) * Cin;
+}
+
+int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float *bias, float *y_nhwc, int N, int H, int W, int Cin,
+                      int Cout, int KS, int stride, int pad, int dil, int relu, int y_channel_stride, int y_channel_offset,
+                      void *stream) {
+    if (!x_nhwc || !filter_tc5 || !y_nhwc) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5: null pointer");
+    if (!pmb200_conv2d_tc5_supported(Cin, Cout, KS, stride))
+        return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5: Cin in {8,16,32,64}, Cout <= 64, KS in {1,3,5}, stride 1 or 2");
+    if (N < 1 || H < 1 || W < 1 || pad < 0 || dil < 1) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5: bad size");
+    if ((reinterpret_cast<uintptr_t>(x_nhwc) & 15u) || (reinterpret_cast<uintptr_t>(filter_tc5) & 15u))
+        return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5: input and filter must be 16-byte aligned");
+    const int Ho = (H + 2 * pad - dil * (KS - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (KS - 1) - 1) / stride + 1;
+    if (Ho < 1 || Wo < 1) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5: empty output");
+    if (y_channel_stride < Cout + y_channel_offset || y_channel_offset < 0)
+        return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5: output channel slice out of range");
+    auto enc = encoder();
+    if (!enc) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5: cuTensorMapEncodeTiled unavailable");
+
+    Conv5Params p;
+    p.wpack = filter_tc5; p.bias = bias; p.y = y_nhwc;
+    p.N = N; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.Npad = npad_of(Cout);
+    p.KS = KS; p.S = stride; p.pad = pad; p.dil = dil; p.relu = relu; p.ycs = y_channel_stride; p.yco = y_channel_offset;
+    p.tiles_x = (Wo + kTW - 1) / kTW; p.tiles_y = (Ho + kTH - 1) / kTH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
+    if (tiles > 0x7fffffffLL) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5: too many tiles");
+    p.total_tiles = (int)tiles;
+    const int cblk = Cin < 32 ? Cin : 32;
+    p.RB = cblk * 4;
+    p.KB = Cin / cblk;
+    p.a_bytes = 128 * p.RB * p.KB;
+    p.w_bytes = p.Npad * p.RB * p.KB;
+    p.stage_bytes = 2 * p.a_bytes + 2 * p.w_bytes;  // multiples of 1024 except tiny layers: keep every stage 1024-aligned
+    p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+    p.layout_type = p.RB == 128 ? 2u : (p.RB == 64 ? 4u : 6u);
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);  // F32 += TF32 . TF32, K-major both
+    p.tmem_cols = p.Npad <= 32 ? 32u : 64u;
+
+    int dev = 0, sms = 0, smem_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // two CTAs per SM when the ring allows at least 3 stages each, else one CTA with as many stages as fit (<= 8)
+    int ctas = 2;
+    int stages = ((smem_optin + 1024) / 2 - 1024 - 2048) / p.stage_bytes;
+    if (stages < 3) {
+        ctas = 1;
+        stages = (smem_optin - 2048) / p.stage_bytes;
+    }
+    if (stages > 8) stages = 8;
+    if (stages < 2) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5: a ring of two stages does not fit in shared memory");
+    p.stages = stages;
+    const int smem = 1024 + stages * p.stage_bytes + 1024;  // + slack for the 1024-byte alignment of the dynamic segment
+    static thread_local int attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(conv5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            cudaGetLastError();
+            return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5: shared-memory opt-in failed");
+        }
+        attr_smem = smem;
+    }
+    CUtensorMap xmap;
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)cblk, (cuuint32_t)(kTW * stride), (cuuint32_t)(kTH * stride), 1u};
+    const cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+    const CUtensorMapSwizzle sw = p.RB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.RB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x_nhwc), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5: tensor map rejected (alignment / size)");
+    long long grid = (long long)sms * ctas;
+    if (grid > tiles) grid = tiles;
+    conv5_kernel<<<(unsigned)grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, xmap);
+    return pmb200_internal_launch_status("conv2d_tc5");
+}
+
+}  // extern "C"

@@ -1134,11 +1134,12 @@ cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 // (tools/kbench.py) changes them through pmb200_set_tuning().  Nothing in the launch path reads the environment.
 // ------------------------------------------------------------------------------------------
 enum Tune { kTuneKaGen, kTuneKa3Dc, kTuneKa3DcVw, kTuneKa3Pipe, kTuneKa3MinB, kTuneKa4Nw, kTuneKa4Ctas, kTuneKa4Cap, kTuneKa4Grid,
-            kTuneKbTp, kTuneKbDy, kTuneCount };
+            kTuneKa4Stages, kTuneKbTp, kTuneKbDy, kTuneCount };
 const char *const kTuneNames[kTuneCount] = {"ka_gen", "ka3_dc", "ka3_dc_vw", "ka3_pipe", "ka3_minb", "ka4_nw", "ka4_ctas", "ka4_cap",
-                                            "ka4_grid", "kb_tp", "kb_dy"};
-const int kTuneDefaults[kTuneCount] = {4, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0};
-int g_tune[kTuneCount] = {4, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0};
+                                            "ka4_grid", "ka4_stages", "kb_tp", "kb_dy"};
+// ka_gen: 3 until generation 4 beats it on hardware at the bench sizes (profiles/r2_run2_kbench.json: 42 vs 34-40 us at stage 2)
+const int kTuneDefaults[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
+int g_tune[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
 inline int tune(Tune t) { return __atomic_load_n(&g_tune[t], __ATOMIC_RELAXED); }
 
 // Third-generation K-A launch (kept for shapes generation 4 does not take and for A/B measurements).
@@ -1243,16 +1244,19 @@ bool launch_wc4_nw(const WarpCorrParams &p, const MlpParams &m, float *sims_out,
     using L = wc4::Layout<C, G, NW>;
     const DeviceFacts &dev = device_facts();
     auto kern = wc4::warp_corr4_kernel<C, G, EPI, NW, MINB>;
-    // ring-slot size: what is left of the per-CTA share of shared memory when `ctas` CTAs are to be resident
+    // ring: `stages` slots of `cap` texels out of what is left of the per-CTA share of shared memory when `ctas` CTAs are to
+    // be resident
     const int ctas = tune(kTuneKa4Ctas) > 0 ? tune(kTuneKa4Ctas) : MINB;
+    int stages = tune(kTuneKa4Stages) > 0 ? tune(kTuneKa4Stages) : 3;
+    stages = stages < 2 ? 2 : (stages > wc4::kMaxStages ? wc4::kMaxStages : stages);
     const int share = (dev.smem_optin + 1024) / ctas - 1024;  // 1 KB per CTA is reserved by the runtime
-    int cap = (share - L::fixed_bytes) / (wc4::kStages * C * 4);
+    int cap = (share - L::fixed_bytes) / (stages * C * 4);
     if (tune(kTuneKa4Cap) > 0) cap = tune(kTuneKa4Cap);
-    const int cap_max = (dev.smem_optin - L::fixed_bytes) / (wc4::kStages * C * 4);
+    const int cap_max = (dev.smem_optin - L::fixed_bytes) / (stages * C * 4);
     if (cap > cap_max) cap = cap_max;
     if (cap > 1024) cap = 1024;
     if (cap < 16) return false;
-    const int smem = L::fixed_bytes + wc4::kStages * cap * C * 4;
+    const int smem = L::fixed_bytes + stages * cap * C * 4;
     static thread_local int attr_smem = 0;  // per instantiation and host thread
     if (smem > attr_smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -1280,6 +1284,7 @@ bool launch_wc4_nw(const WarpCorrParams &p, const MlpParams &m, float *sims_out,
     if (items > 0x7fffffffLL) return false;
     q.nitems = (int)items;
     q.cap = cap;
+    q.stages = stages;
     long long grid = (long long)dev.sms * occ;
     if (tune(kTuneKa4Grid) > 0) grid = tune(kTuneKa4Grid);
     if (grid > items) grid = items;

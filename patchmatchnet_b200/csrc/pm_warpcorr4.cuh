@@ -59,6 +59,7 @@ inline void mbar_wait(MBar *b, unsigned parity) {  // returns once the phase wit
         emu::yield();
     }
 }
+inline void mbar_wait_backoff(MBar *b, unsigned parity) { mbar_wait(b, parity); }
 inline void bulk_row_g2s(float *dst, const float *src, unsigned bytes, MBar *b) {
     assert(bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
     memcpy(dst, src, bytes);
@@ -111,6 +112,15 @@ __device__ __forceinline__ void mbar_wait(MBar *b, unsigned parity) {
         if (mbar_try_wait(b, parity)) return;
     __trap();
 }
+// the producer's waits: it is ahead of the consumers most of the time; sleeping between polls keeps its spinning out of the
+// issue slots the consumer warps of the same SM sub-partition need
+__device__ __forceinline__ void mbar_wait_backoff(MBar *b, unsigned parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        if (mbar_try_wait(b, parity)) return;
+        __nanosleep(100);
+    }
+    __trap();
+}
 // one row of a source window: `bytes` contiguous bytes (multiple of 16, 16-byte aligned on both sides)  -> SASS UBLKCP
 __device__ __forceinline__ void bulk_row_g2s(float *dst, const float *src, unsigned bytes, MBar *b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -136,7 +146,7 @@ constexpr int kTW = 8;        // tile width in reference pixels = pixels per con
 constexpr int kRows = 4;      // hypothesis rows per warp pass (32 lanes / 8 pixels)
 constexpr int kNE = 2;        // consecutive hypotheses per lane
 constexpr int kDItem = kRows * kNE;  // hypotheses per item (8)
-constexpr int kStages = 2;    // source-window ring depth
+constexpr int kMaxStages = 4;  // source-window ring depth is a launch parameter (2..4)
 constexpr int kMaxRows = 64;  // window rows a producer warp will stage (2 bulk copies per lane)
 
 // Footprint key of this generation: x0 | y0 << 14 | dx << 29 | dy << 30 (source maps up to 16383 x 32767).
@@ -169,7 +179,6 @@ __device__ __forceinline__ int footprint(float u, float v, int rows, int cols, f
 }
 
 struct alignas(16) WinInfo {  // written by the producer before it arms the window's barrier
-    float rt[12];
     int x0, y0, w, h;  // staged box in source texels; h == 0: nothing staged (every cell takes the global path)
 };
 
@@ -190,23 +199,26 @@ struct Layout {
     static constexpr int TABLE = 4 * TA;                  // floats per warp (32 slots)
     static constexpr int PIX = kTW * NW;                  // reference pixels per item
     // dynamic shared memory carve-up (bytes), every block 128-byte aligned
-    static constexpr int oBars = 0;                                            // MBar[2*kStages + 4]
-    static constexpr int oWin = 256;                                           // WinInfo[kStages]
-    static constexpr int oItem = oWin + 64 * kStages;                          // ItemInfo[2]
-    static constexpr int oDepth = oItem + 128;                                 // float[2][kDItem * PIX]
+    static constexpr int oBars = 0;                                            // MBar[2*kMaxStages + 4]
+    static constexpr int oWin = 384;                                           // WinInfo[kMaxStages]
+    static constexpr int oItem = oWin + 16 * kMaxStages;                       // ItemInfo[2]
+    static constexpr int oRt = oItem + 64;                                     // float[2][PMB200_MAX_VIEWS * 12]
+    static constexpr int oDepth = oRt + 2 * PMB200_MAX_VIEWS * 12 * 4;         // float[2][kDItem * PIX]
     static constexpr int oVw = oDepth + 2 * kDItem * PIX * 4;                  // float[2][PMB200_MAX_VIEWS * PIX]
     static constexpr int oCell = oVw + 2 * PMB200_MAX_VIEWS * PIX * 4;         // int2[NW][kNE * 32]
     static constexpr int oTable = oCell + NW * kNE * 32 * 8;                   // float[NW][TABLE]
     static constexpr int oRef = (oTable + NW * TABLE * 4 + 127) / 128 * 128;   // float[2][PIX * C]
-    static constexpr int oWinData = oRef + 2 * PIX * C * 4;                    // float[kStages][cap * C]
+    static constexpr int oWinData = oRef + 2 * PIX * C * 4;                    // float[stages][cap * C]
     static constexpr int fixed_bytes = oWinData;
-    static_assert(sizeof(MBar) * (2 * kStages + 4) <= oWin && sizeof(WinInfo) == 64 && sizeof(ItemInfo) == 16, "barrier / info blocks");
+    static_assert(sizeof(MBar) * (2 * kMaxStages + 4) <= oWin && sizeof(WinInfo) == 16 && sizeof(ItemInfo) == 16, "barrier / info blocks");
+    static_assert(oDepth % 128 == 0, "blocks stay 128-byte aligned");
 };
 
 struct Params4 {
     WarpCorrParams p;
     int ntx, nty, nd, nitems;
-    int cap;  // texels per window slot
+    int cap;     // texels per window slot
+    int stages;  // window ring depth, 2..kMaxStages
 };
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -285,9 +297,10 @@ warp_corr4_kernel(const Params4 q, const MlpParams mlp, float *__restrict__ sims
     extern __shared__ __align__(128) char smem[];
 #endif
     MBar *bars = reinterpret_cast<MBar *>(smem + L::oBars);
-    MBar *win_full = bars, *win_empty = bars + kStages, *item_full = bars + 2 * kStages, *item_empty = bars + 2 * kStages + 2;
+    MBar *win_full = bars, *win_empty = bars + kMaxStages, *item_full = bars + 2 * kMaxStages, *item_empty = bars + 2 * kMaxStages + 2;
     WinInfo *s_win = reinterpret_cast<WinInfo *>(smem + L::oWin);
     ItemInfo *s_item = reinterpret_cast<ItemInfo *>(smem + L::oItem);
+    float *s_rt = reinterpret_cast<float *>(smem + L::oRt);
     float *s_depth = reinterpret_cast<float *>(smem + L::oDepth);
     float *s_vw = reinterpret_cast<float *>(smem + L::oVw);
     float *s_ref = reinterpret_cast<float *>(smem + L::oRef);
@@ -299,7 +312,7 @@ warp_corr4_kernel(const Params4 q, const MlpParams mlp, float *__restrict__ sims
     const unsigned full = 0xffffffffu;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&win_full[s], 1);
             mbar_init(&win_empty[s], NW);
         }
@@ -313,39 +326,65 @@ warp_corr4_kernel(const Params4 q, const MlpParams mlp, float *__restrict__ sims
 
     if (warp == NW) {
         // ===================================================== producer =====================================================
-        unsigned wcount = 0;  // windows issued so far (ring position)
-        int i = 0;
-        for (int it = blockIdx.x; it < q.nitems; it += gridDim.x, ++i) {
-            const int is = i & 1;
-            mbar_wait(&item_empty[is], ((unsigned)(i >> 1) & 1u) ^ 1u);  // consumers are done with item i-2
+        // Software pipeline: the hypotheses / view weights of item i+1 are fetched into registers while the windows of item i
+        // are being issued, so the global-load latency of the per-item data never sits in front of a TMA request.
+        constexpr int ND = kDItem * PIX / 32;            // hypotheses per lane
+        constexpr int NV = PMB200_MAX_VIEWS * PIX / 32;  // view weights per lane (at most)
+        float dreg[ND], vreg[kWeighted ? NV : 1];
+        auto decode = [&](int it, int &b, int &d0, int &tx0, int &ty0) {
             int rem = it;
             const int tx = rem % q.ntx; rem /= q.ntx;
             const int ty = rem % q.nty; rem /= q.nty;
             const int dc = rem % q.nd;
-            const int b = rem / q.nd;
-            const int tx0 = tx * kTW, ty0 = ty * NW, d0 = dc * kDItem;
-            // hypotheses of the tile -> shared memory, and their range
+            b = rem / q.nd; d0 = dc * kDItem; tx0 = tx * kTW; ty0 = ty * NW;
+        };
+        auto prefetch = [&](int it) {
+            int b, d0, tx0, ty0;
+            decode(it, b, d0, tx0, ty0);
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                const int idx = lane + 32 * j, dl = idx / PIX, pix = idx % PIX;
+                const int y = ty0 + pix / kTW, x = tx0 + pix % kTW, d = d0 + dl;
+                // NaN marks "no hypothesis here" (outside the map / past D): excluded from the range, stored as 1.0
+                dreg[j] = (y < p.H && x < p.W && d < p.D) ? __ldg(p.depth + ((size_t)b * p.D + d) * HW + (size_t)y * p.W + x)
+                                                          : __int_as_float(0x7fc00000);
+            }
+            if (kWeighted) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const int idx = lane + 32 * j, v = idx / PIX, pix = idx % PIX;
+                    const int y = ty0 + pix / kTW, x = tx0 + pix % kTW;
+                    vreg[j] = (v < p.V && y < p.H && x < p.W) ? __ldg(p.vw + ((size_t)b * p.V + v) * HW + (size_t)y * p.W + x) : 0.0f;
+                }
+            }
+        };
+        int ws = 0;
+        unsigned wpar = 0;  // ring position of the next window: slot and phase parity
+        int i = 0;
+        if ((int)blockIdx.x < q.nitems) prefetch(blockIdx.x);
+        for (int it = blockIdx.x; it < q.nitems; it += gridDim.x, ++i) {
+            const int is = i & 1;
+            int b, d0, tx0, ty0;
+            decode(it, b, d0, tx0, ty0);
+            mbar_wait_backoff(&item_empty[is], ((unsigned)(i >> 1) & 1u) ^ 1u);  // consumers are done with item i-2
+            // per-item data -> shared memory; range of the tile's hypotheses
             float dlo = INFINITY, dhi = -INFINITY;
             float *sd = s_depth + is * (kDItem * PIX);
-            for (int idx = lane; idx < kDItem * PIX; idx += 32) {
-                const int dl = idx / PIX, pix = idx % PIX;
-                const int y = ty0 + pix / kTW, x = tx0 + pix % kTW, d = d0 + dl;
-                float val = 1.0f;
-                if (y < p.H && x < p.W && d < p.D) {
-                    val = __ldg(p.depth + ((size_t)b * p.D + d) * HW + (size_t)y * p.W + x);
-                    dlo = fminf(dlo, val);
-                    dhi = fmaxf(dhi, val);
-                }
-                sd[idx] = val;
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                const float val = dreg[j];
+                const bool has = val == val;
+                if (has) { dlo = fminf(dlo, val); dhi = fmaxf(dhi, val); }
+                sd[lane + 32 * j] = has ? val : 1.0f;
             }
             if (kWeighted) {
                 float *sv = s_vw + is * (PMB200_MAX_VIEWS * PIX);
-                for (int idx = lane; idx < p.V * PIX; idx += 32) {
-                    const int v = idx / PIX, pix = idx % PIX;
-                    const int y = ty0 + pix / kTW, x = tx0 + pix % kTW;
-                    sv[idx] = (y < p.H && x < p.W) ? __ldg(p.vw + ((size_t)b * p.V + v) * HW + (size_t)y * p.W + x) : 0.0f;
-                }
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    if (lane + 32 * j < p.V * PIX) sv[lane + 32 * j] = vreg[j];
             }
+            for (int idx = lane; idx < p.V * 12; idx += 32)  // the item's relative projections, read by every consumer lane
+                s_rt[is * (PMB200_MAX_VIEWS * 12) + idx] = __ldg(p.rt + ((size_t)(idx / 12) * p.B + b) * 12 + idx % 12);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 dlo = fminf(dlo, __shfl_xor_sync(full, dlo, off));
@@ -394,21 +433,22 @@ warp_corr4_kernel(const Params4 q, const MlpParams mlp, float *__restrict__ sims
                     }
                 }
             }
-            for (int v = 0; v < p.V; ++v, ++wcount) {
-                const int s = (int)(wcount % kStages);
-                mbar_wait(&win_empty[s], ((wcount / kStages) & 1u) ^ 1u);
+            if (it + (int)gridDim.x < q.nitems) prefetch(it + gridDim.x);  // in flight while this item's windows are issued
+            for (int v = 0; v < p.V; ++v) {
+                mbar_wait_backoff(&win_empty[ws], wpar ^ 1u);
                 const int x0 = __shfl_sync(full, bx0, v), y0 = __shfl_sync(full, by0, v);
                 const int w = __shfl_sync(full, bw, v), h = __shfl_sync(full, bh, v);
-                if (lane < 12) s_win[s].rt[lane] = __ldg(p.rt + ((size_t)v * p.B + b) * 12 + lane);
-                if (lane == 0) { s_win[s].x0 = x0; s_win[s].y0 = y0; s_win[s].w = w; s_win[s].h = h; }
-                __syncwarp();
                 const unsigned row_bytes = (unsigned)(w * C * 4);
-                if (lane == 0) mbar_arrive_expect_tx(&win_full[s], row_bytes * (unsigned)h);
+                if (lane == 0) {
+                    s_win[ws] = WinInfo{x0, y0, w, h};
+                    mbar_arrive_expect_tx(&win_full[ws], row_bytes * (unsigned)h);
+                }
                 __syncwarp();
                 const float *src_v = p.src + (((size_t)v * p.B + b) * p.Hs) * (size_t)p.Ws * C;
-                float *dst = s_data + (size_t)s * q.cap * C;
+                float *dst = s_data + (size_t)ws * q.cap * C;
                 for (int r = lane; r < h; r += 32)
-                    bulk_row_g2s(dst + (size_t)r * w * C, src_v + ((size_t)(y0 + r) * p.Ws + x0) * C, row_bytes, &win_full[s]);
+                    bulk_row_g2s(dst + (size_t)r * w * C, src_v + ((size_t)(y0 + r) * p.Ws + x0) * C, row_bytes, &win_full[ws]);
+                if (++ws == q.stages) { ws = 0; wpar ^= 1u; }
             }
         }
         return;
@@ -420,7 +460,8 @@ warp_corr4_kernel(const Params4 q, const MlpParams mlp, float *__restrict__ sims
     const int pi = lane & 7, r = lane >> 3;
     const unsigned below = (1u << lane) - 1u;
     const unsigned pmask = 0x01010101u << pi;  // the lanes of my pixel
-    unsigned wcount = 0;
+    int ws = 0;
+    unsigned wpar = 0;  // ring position of the next window: slot and phase parity
     int i = 0;
     for (int it = blockIdx.x; it < q.nitems; it += gridDim.x, ++i) {
         const int is = i & 1;
@@ -447,14 +488,15 @@ warp_corr4_kernel(const Params4 q, const MlpParams mlp, float *__restrict__ sims
         float wsum = 1e-5f;  // reference models/patchmatch.py:192
         const float *ref_tile = s_ref + is * (PIX * C) + warp * (kTW * C);
 
-        for (int v = 0; v < p.V; ++v, ++wcount) {
-            const int s = (int)(wcount % kStages);
-            mbar_wait(&win_full[s], (wcount / kStages) & 1u);
-            const WinInfo *wi = &s_win[s];
+        for (int v = 0; v < p.V; ++v) {
+            const int s = ws;
             float rt[12];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) rt[k] = wi->rt[k];
-            const int wx0 = wi->x0, wy0 = wi->y0, ww = wi->w, wh = wi->h;
+            for (int k = 0; k < 12; ++k) rt[k] = s_rt[is * (PMB200_MAX_VIEWS * 12) + v * 12 + k];
+            mbar_wait(&win_full[s], wpar);
+            if (++ws == q.stages) { ws = 0; wpar ^= 1u; }
+            const WinInfo wi = s_win[s];
+            const int wx0 = wi.x0, wy0 = wi.y0, ww = wi.w, wh = wi.h;
             const float wv = kWeighted ? s_vw[is * (PMB200_MAX_VIEWS * PIX) + v * PIX + warp * kTW + pi] : 1.0f;
             if (kWeighted) wsum += wv;
 

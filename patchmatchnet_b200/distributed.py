@@ -45,7 +45,19 @@ def gather_depth_maps(local: torch.Tensor, num_items: int, group=None) -> torch.
 
 
 class FlatGradAllReduce:
-    """Average gradients across ranks with a single all-reduce over one flat fp32 buffer."""
+    """Gradient averaging across ranks as ONE collective and ZERO copies: every parameter's `.grad` is a view into one flat
+    fp32 buffer, autograd accumulates straight into it, and the step's exchange is a single all-reduce of that buffer
+    (0.89 MB for the 222,632 parameters of the network; reference counterpart: nn.DataParallel's per-step gather of
+    replica gradients, train.py:282).
+
+        reducer = FlatGradAllReduce(net.parameters())      # attaches the gradient views
+        reducer.zero_()                                    # instead of optimizer.zero_grad(): one memset
+        loss.backward(); reducer(); optimizer.step()
+
+    Parameters the graph never reaches (three groups with the default flags) simply keep zeros in their
+    slice: every rank contributes to and receives every slice, so replicas cannot drift apart when a parameter has a
+    gradient on some ranks only.  A parameter whose `.grad` was replaced or set to None behind the reducer's
+    back (e.g. zero_grad(set_to_none=True)) is copied in / re-attached -- correct, just not copy-free."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None) -> None:
         self.params = [p for p in params if p.requires_grad]
@@ -53,24 +65,45 @@ class FlatGradAllReduce:
         self.numel = sum(p.numel() for p in self.params)
         first = self.params[0]
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=first.device)
-
-    def __call__(self) -> int:
-        """Returns the number of parameters that had no gradient on this rank (zero-filled)."""
-        off, missing = 0, 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-                missing += 1
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.div_(dist.get_world_size(self.group))
+        self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
+            self.views.append(self.flat[off:off + n].view_as(p))
             off += n
-        return missing
+        self.never_reached = None  # filled by the first call: parameters whose slice is exactly zero after backward
+        self.attach()
+
+    def attach(self) -> None:
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def zero_(self) -> None:
+        """Start a step: one memset of the flat buffer (and re-attach views somebody dropped)."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+
+    def __call__(self) -> int:
+        """All-reduce (average) in place.  Returns the number of parameters that were not attached to the flat buffer on
+        this rank (0 in the copy-free regime)."""
+        detached = 0
+        for p, v in zip(self.params, self.views):
+            if p.grad is v:
+                continue
+            detached += 1
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+            p.grad = v
+        if self.never_reached is None:  # one-off bookkeeping (host sync): which parameters the graph does not reach
+            self.never_reached = sum(1 for v in self.views if not bool(v.any()))
+        world = dist.get_world_size(self.group)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)  # one kernel
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(world)
+        return detached

@@ -93,6 +93,11 @@ class _PackedConv:
         from . import ops
 
         srcs = [conv.weight] + ([conv.bias] if conv.bias is not None else [])
+        if ops.conv_uses_tc5(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0]):
+            frag, bias = self._cache.get(
+                srcs, lambda: (ops.pack_conv_filter_tc5(conv.weight), None if conv.bias is None else conv.bias.detach().clone()), key="tc5")
+            return ops.conv2d_tc5(x, frag, bias if with_bias else None, conv.out_channels, conv.kernel_size[0], conv.stride[0],
+                                  conv.padding[0], conv.dilation[0], relu=relu)
         prec = ops.conv_precision()
         frag, bias = self._cache.get(
             srcs, lambda: (ops.pack_conv_filter(conv.weight, prec), None if conv.bias is None else conv.bias.detach().clone()), key=prec)
@@ -114,6 +119,7 @@ class _ConvBnReLU2d(nn.Module):
         self.bn = nn.BatchNorm2d(cout)
         self._cache = _FoldCache()
         self._frag_cache = _FoldCache()
+        self._tc5_cache = _FoldCache()
 
     def folded_frag(self):
         """(fragment-ordered folded filter, folded bias) for the native conv."""
@@ -130,11 +136,28 @@ class _ConvBnReLU2d(nn.Module):
 
         return self._frag_cache.get(srcs, make, key=prec)
 
+    def folded_tc5(self):
+        """(filter image for the tcgen05 conv, folded bias)."""
+        from . import ops
+
+        bn = self.bn
+        srcs = [self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def make():
+            w, b = _fold_bn(self.conv.weight, bn)
+            return ops.pack_conv_filter_tc5(w), b.contiguous()
+
+        return self._tc5_cache.get(srcs, make)
+
     def native(self, x: Tensor, out: Tensor = None, out_channel_offset: int = 0) -> Tensor:
         from . import ops
 
-        frag, b = self.folded_frag()
         c = self.conv
+        if ops.conv_uses_tc5(c.in_channels, c.out_channels, c.kernel_size[0], c.stride[0]):
+            frag, b = self.folded_tc5()
+            return ops.conv2d_tc5(x, frag, b, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
+                                  relu=True, out=out, out_channel_offset=out_channel_offset)
+        frag, b = self.folded_frag()
         return ops.conv2d_nhwc(x, frag, b, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
                                relu=True, out=out, out_channel_offset=out_channel_offset)
 

@@ -231,6 +231,91 @@ def pack_conv_filter(weight: Tensor, precision: int, transposed: bool = False) -
     return torch.cat((hi, lo), dim=-1).contiguous().view(-1)
 
 
+# K-D5 (csrc/pm_conv5.cu): tcgen05 / TMEM / TMA implicit-GEMM convolution, fp32-accurate (3xTF32).  Used in the
+# fp32-accurate mode for the layers it serves when TC5_CONVS is on (PMB200_TC5=0 hands them back to the mma.sync kernel).
+TC5_CONVS = os.environ.get("PMB200_TC5", "1") != "0"
+
+
+def conv_uses_tc5(cin: int, cout: int, ks: int, stride: int = 1, transposed: bool = False, fused_add: bool = False) -> bool:
+    """Which convs run on the tcgen05 kernel: the fp32-accurate mode only (its arithmetic IS the 3xTF32 split), no fused
+    transposed / upsample-add epilogue, a shape the kernel takes, and enough multiply-adds per output pixel for the tensor
+    pipe to matter (the 8-channel full-resolution layers are bound by activation traffic and stay on pm_conv.cu).
+    Measured per layer on B200: profiles/r2_run3_convbench.json."""
+    if not (NATIVE_CONVS and TC5_CONVS) or transposed or fused_add or conv_precision() != 3:
+        return False
+    if cin * cout * ks * ks < TC5_MIN_MACS:
+        return False
+    return bool(_native.lib().pmb200_conv2d_tc5_supported(cin, cout, ks, stride))
+
+
+TC5_MIN_MACS = int(os.environ.get("PMB200_TC5_MIN_MACS", "1024"))
+
+
+def pack_conv_filter_tc5(weight: Tensor) -> Tensor:
+    """Conv filter [Cout,Cin,KS,KS] -> the shared-memory image `pmb200_conv2d_tc5` copies per tap (include/patchmatch_b200.h):
+    [tap][hi, lo][Cin/32 blocks][Npad rows][min(Cin,32) channels] with every [Npad][row] tile in the K-major swizzle of the
+    tensor core for its row size; hi = TF32-rounded weight, lo = TF32-rounded remainder.  Pure layout / rounding work on
+    the weight's device (CPU-testable)."""
+    if weight.dim() != 4 or weight.shape[2] != weight.shape[3]:
+        raise RuntimeError(f"pack_conv_filter_tc5: expected [Cout,Cin,KS,KS], got {tuple(weight.shape)}")
+    w = weight.detach().float()
+    cout, cin, ks, _ = w.shape
+    if cin not in (8, 16, 32, 64) or not (1 <= cout <= 64):
+        raise RuntimeError("pack_conv_filter_tc5: Cin in {8,16,32,64}, 1 <= Cout <= 64")
+    npad = (cout + 15) // 16 * 16
+    cblk = min(cin, 32)
+    kb = cin // cblk
+    hi = _tf32_round(w)
+    lo = _tf32_round(w - hi)
+    both = torch.stack((hi, lo))  # [2, Cout, Cin, KS, KS]
+    t = torch.zeros((ks * ks, 2, kb, npad, cblk), dtype=torch.float32, device=w.device)
+    t[:, :, :, :cout] = both.permute(3, 4, 0, 1, 2).reshape(ks * ks, 2, cout, kb, cblk).permute(0, 1, 3, 2, 4)
+    # swizzle: 16-byte chunk j of row r moves to chunk j ^ f(r)
+    chunks = cblk // 4
+    rows = torch.arange(npad, device=w.device)
+    f = {8: rows % 8, 4: (rows // 2) % 4, 2: (rows // 4) % 2}[chunks]
+    j = torch.arange(chunks, device=w.device)
+    src = (j.view(1, chunks) ^ f.view(npad, 1))  # physical chunk p of row r holds logical chunk p ^ f(r)
+    t = t.view(ks * ks, 2, kb, npad, chunks, 4)
+    idx = src.view(1, 1, 1, npad, chunks, 1).expand(ks * ks, 2, kb, npad, chunks, 4)
+    return torch.gather(t, 4, idx).contiguous().view(-1)
+
+
+def conv2d_tc5(x: Tensor, filter_tc5: Tensor, bias: Optional[Tensor], cout: int, ks: int, stride: int = 1, pad: int = 0, dil: int = 1,
+               relu: bool = False, out: Optional[Tensor] = None, out_channel_offset: int = 0) -> Tensor:
+    """Channels-last convolution on the 5th-generation tensor cores (csrc/pm_conv5.cu), fp32-accurate.  Same calling
+    convention as conv2d_nhwc; `filter_tc5` comes from pack_conv_filter_tc5."""
+    if not _on_device(x) or x.dtype != torch.float32 or x.dim() != 4:
+        raise RuntimeError(f"conv2d_tc5: x must be a 4-D CUDA float32 tensor (got {x.dtype} {tuple(x.shape)} on {x.device}); no CPU fallback")
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    N, cin, H, W = x.shape
+    want = _native.lib().pmb200_conv2d_tc5_filter_floats(cin, cout, ks)
+    if want <= 0 or filter_tc5.numel() != want or filter_tc5.dtype != torch.float32 or filter_tc5.device != x.device:
+        raise RuntimeError(f"conv2d_tc5: filter must be {want} float32 values on {x.device} (pack_conv_filter_tc5)")
+    Ho = (H + 2 * pad - dil * (ks - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (ks - 1) - 1) // stride + 1
+    if out is None:
+        out = torch.empty((N, cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        ycs, yco = cout, 0
+    else:
+        if (out.dim() != 4 or out.shape[0] != N or out.shape[2:] != (Ho, Wo) or out.dtype != torch.float32 or out.device != x.device
+                or not out.is_contiguous(memory_format=torch.channels_last)):
+            raise RuntimeError("conv2d_tc5: `out` must be a channels-last CUDA float32 [N,C,Ho,Wo] tensor")
+        ycs, yco = out.shape[1], out_channel_offset
+    b_ptr = None
+    if bias is not None:
+        bias = _require(bias, "bias", 1)
+        if bias.numel() != cout:
+            raise RuntimeError("conv2d_tc5: bias must have Cout elements")
+        b_ptr = bias.data_ptr()
+    with _device_guard(x):
+        rc = _native.lib().pmb200_conv2d_tc5(x.data_ptr(), filter_tc5.data_ptr(), b_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride, pad,
+                                             dil, 1 if relu else 0, ycs, yco, _stream(x))
+    _native.check(rc, "conv2d_tc5")
+    return out
+
+
 def conv_precision() -> int:
     """1 (TF32 operands) when the library would use TF32 for convolutions (torch.backends.cudnn.allow_tf32, torch's
     default), else 3 (3xTF32, fp32-accurate): the native convs honour the same switch as the cuDNN ones they replace."""

@@ -11,12 +11,10 @@ import ctypes
 from patchmatchnet_b200 import _native, ops
 
 
-def _ka_config(C, epi):
-    """rows per warp pass / gather pipeline the launcher picks (launch_wc3_auto, launch_wc3)"""
-    ppw = 32 // (C // 8)
-    default = 16 if ppw == 4 else (8 if ppw == 8 else 4)
-    dc = default if epi == 2 else (8 if ppw == 4 else default)
-    return dc, (1 if ppw == 8 else 0)
+# launch configuration of the fourth-generation fused warp+correlation kernel under the emulator: 4 consumer warps (the
+# launcher's default), a window slot of 96 texels (most boxes fit, some are clipped and take the global path) and 7
+# persistent CTAs, so that every CTA walks several items through its rings
+KA4_NW, KA4_CAP, KA4_GRID, KA4_STAGES = 4, 96, 7, 3
 
 
 class EmulatedLibrary:
@@ -54,8 +52,8 @@ class EmulatedLibrary:
             if epi > 1:
                 return -2
             return self.emu.emu_warp_corr_generic(ref, src, rt, depth, vw, out, V, B, C, G, H, W, Hs, Ws, D)
-        dc, pipe = _ka_config(C, epi)
-        return self.emu.emu_warp_corr3(ref, src, rt, depth, vw, head, out, sims, stride, V, B, C, G, H, W, Hs, Ws, D, epi, dc, pipe)
+        return self.emu.emu_warp_corr4(ref, src, rt, depth, vw, head, out, sims, stride, V, B, C, G, H, W, Hs, Ws, D, epi,
+                                       KA4_NW, KA4_CAP, KA4_GRID, KA4_STAGES)
 
     def pmb200_warp_corr(self, ref, src, rt, depth, vw, out, V, B, C, G, H, W, Hs, Ws, D, stream):
         return self._ka(0 if vw is None else 1, ref, src, rt, depth, vw, None, out, None, 1, V, B, C, G, H, W, Hs, Ws, D)

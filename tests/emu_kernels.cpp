@@ -49,7 +49,7 @@ int run_wc3_epi(const WarpCorrParams &p, const MlpParams &m, float *sims_out, in
 // immediate copies that complete their mbarrier transactions; the producer warp and the consumer warps are fibers like any
 // other thread, an mbarrier wait yields until the phase flips.
 template <int C, int G, int EPI, int NW>
-int run_wc4(const WarpCorrParams &p, const MlpParams &m, float *sims_out, int cap, int grid) {
+int run_wc4(const WarpCorrParams &p, const MlpParams &m, float *sims_out, int cap, int grid, int stages) {
     using L = wc4::Layout<C, G, NW>;
     wc4::Params4 q;
     q.p = p;
@@ -58,17 +58,18 @@ int run_wc4(const WarpCorrParams &p, const MlpParams &m, float *sims_out, int ca
     q.nd = (p.D + wc4::kDItem - 1) / wc4::kDItem;
     q.nitems = q.ntx * q.nty * q.nd * p.B;
     q.cap = cap;
+    q.stages = stages < 2 ? 2 : (stages > wc4::kMaxStages ? wc4::kMaxStages : stages);
     const wc4::TensorMap tm{p.ref, p.B, p.H, p.W, C, NW};
-    const size_t smem = (size_t)L::fixed_bytes + (size_t)wc4::kStages * cap * C * 4;
+    const size_t smem = (size_t)L::fixed_bytes + (size_t)q.stages * cap * C * 4;
     if (grid < 1 || grid > q.nitems) grid = q.nitems;
     emu::launch(dim3(grid), dim3((NW + 1) * 32), smem, [&] { wc4::warp_corr4_kernel<C, G, EPI, NW, 1>(q, m, sims_out, tm); });
     return 0;
 }
 
 template <int C, int G>
-int run_wc4_epi(const WarpCorrParams &p, const MlpParams &m, float *sims_out, int epi, int nw, int cap, int grid) {
+int run_wc4_epi(const WarpCorrParams &p, const MlpParams &m, float *sims_out, int epi, int nw, int cap, int grid, int stages) {
 #define EMU_TRY4(EE, NN) \
-    if (epi == EE && nw == NN) return run_wc4<C, G, EE, NN>(p, m, sims_out, cap, grid);
+    if (epi == EE && nw == NN) return run_wc4<C, G, EE, NN>(p, m, sims_out, cap, grid, stages);
     EMU_TRY4(kEpiSims, 4) EMU_TRY4(kEpiAgg, 4) EMU_TRY4(kEpiScore, 4) EMU_TRY4(kEpiViewW, 4)
     EMU_TRY4(kEpiSims, 8) EMU_TRY4(kEpiAgg, 8) EMU_TRY4(kEpiScore, 8) EMU_TRY4(kEpiViewW, 8)
 #undef EMU_TRY4
@@ -81,10 +82,10 @@ extern "C" {
 
 // K-A, fourth generation.  Same epilogue numbering as emu_warp_corr3; nw = consumer warps (tile rows), cap = texels per
 // window slot (small values force the global-memory fallback of the gather), grid = persistent CTAs (fewer than items
-// makes every CTA walk several items through the rings).
+// makes every CTA walk several items through the rings), stages = depth of the window ring (2..4).
 int emu_warp_corr4(const float *ref_nhwc, const float *src_nhwc, const float *rt, const float *depth, const float *vw,
                    const pmb200_mlp *head, float *out, float *sims_out, int ostride, int V, int B, int C, int G, int H, int W,
-                   int Hs, int Ws, int D, int epi, int nw, int cap, int grid) {
+                   int Hs, int Ws, int D, int epi, int nw, int cap, int grid, int stages) {
     WarpCorrParams p;
     p.ref = ref_nhwc; p.src = src_nhwc; p.rt = rt; p.depth = depth; p.vw = vw; p.out = out;
     p.V = V; p.B = B; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.D = D;
@@ -93,9 +94,9 @@ int emu_warp_corr4(const float *ref_nhwc, const float *src_nhwc, const float *rt
     p.ostride = ostride < 1 ? 1 : ostride;
     MlpParams m{};
     if (head) m = to_device_layout(head);
-    if (C == 64 && G == 8) return run_wc4_epi<64, 8>(p, m, sims_out, epi, nw, cap, grid);
-    if (C == 32 && G == 8) return run_wc4_epi<32, 8>(p, m, sims_out, epi, nw, cap, grid);
-    if (C == 16 && G == 4) return run_wc4_epi<16, 4>(p, m, sims_out, epi, nw, cap, grid);
+    if (C == 64 && G == 8) return run_wc4_epi<64, 8>(p, m, sims_out, epi, nw, cap, grid, stages);
+    if (C == 32 && G == 8) return run_wc4_epi<32, 8>(p, m, sims_out, epi, nw, cap, grid, stages);
+    if (C == 16 && G == 4) return run_wc4_epi<16, 4>(p, m, sims_out, epi, nw, cap, grid, stages);
     return -2;
 }
 

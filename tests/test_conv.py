@@ -194,6 +194,87 @@ def test_gpu_conv_full_size_layers(fp32_library):
         assert _scaled_err(got, want) <= 2e-5, name
 
 
+TC5_LAYERS = sorted(n for n, (cin, cout, ks, S, pad, dil, relu) in LAYERS.items() if cin in (8, 16, 32, 64))
+
+
+def test_tc5_filter_image_matches_the_address_swizzle():
+    """ops.pack_conv_filter_tc5 against the element-by-element definition in include/patchmatch_b200.h: byte offset `off` of
+    the dense [Npad][row bytes] tile moves to off ^ ((off >> 3) & mask), mask 0x70 / 0x30 / 0x10 for 128 / 64 / 32-byte rows
+    (what TMA writes and tcgen05 reads for a K-major operand); hi + lo restores the weight to 2^-22."""
+    torch.manual_seed(0)
+    for (cout, cin, ks) in [(16, 8, 5), (18, 32, 3), (64, 64, 3), (8, 16, 3), (32, 16, 5), (64, 64, 1)]:
+        w = torch.randn(cout, cin, ks, ks)
+        got = ops.pack_conv_filter_tc5(w)
+        npad, cblk = (cout + 15) // 16 * 16, min(cin, 32)
+        kb, RB = cin // cblk, cblk * 4
+        assert got.numel() == ks * ks * 2 * npad * cin
+        hi = ops._tf32_round(w)
+        lo = ops._tf32_round(w - hi)
+        assert float((hi + lo - w).abs().max()) <= 2.0 ** -21 * float(w.abs().max())
+        ref = torch.zeros(ks * ks, 2, kb, npad * RB // 4)
+        mask = {128: 0x70, 64: 0x30, 32: 0x10}[RB]
+        for t in range(ks * ks):
+            ky, kx = divmod(t, ks)
+            for si, ww in enumerate((hi, lo)):
+                for k in range(kb):
+                    blk = ww[:, k * cblk:(k + 1) * cblk, ky, kx]
+                    for n in range(cout):
+                        for c in range(cblk):
+                            off = n * RB + c * 4
+                            ref[t, si, k, (off ^ ((off >> 3) & mask)) // 4] = blk[n, c]
+        assert torch.equal(got, ref.view(-1)), (cout, cin, ks)
+    with pytest.raises(RuntimeError):
+        ops.pack_conv_filter_tc5(torch.zeros(8, 3, 3, 3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TC5_LAYERS)
+def test_gpu_tc5_conv_matches_cudnn_fp32(name, fp32_library):
+    """K-D5 (tcgen05 / TMEM / TMA implicit GEMM, 3xTF32) against cuDNN in full fp32: every layer shape it can take, ragged
+    map sizes (partial tiles on both axes, zero padding from the TMA's out-of-bounds fill), two images, strides 1 and 2,
+    dilation up to 6, output channels that are not a multiple of 16."""
+    cin, cout, ks, S, pad, dil, relu = LAYERS[name]
+    dev = "cuda:0"
+    assert _native.lib().pmb200_conv2d_tc5_supported(cin, cout, ks, S) == 1
+    g = torch.Generator().manual_seed(sum(map(ord, name)) + 1)
+    for (N, H, W) in ((2, 37, 53), (1, 16, 32), (3, 9, 70)):
+        x = torch.randn(N, cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
+        b = torch.randn(cout, generator=g).to(dev)
+        want = _ref_conv(x, w, b, S, pad, dil, relu)
+        got = ops.conv2d_tc5(x, ops.pack_conv_filter_tc5(w), b, cout, ks, S, pad, dil, relu=relu)
+        torch.cuda.synchronize()
+        assert got.shape == want.shape
+        err = _scaled_err(got, want)
+        assert err <= 2e-5, f"{name} {N}x{H}x{W}: scaled max err {err:.3e}"
+        got_nb = ops.conv2d_tc5(x, ops.pack_conv_filter_tc5(w), None, cout, ks, S, pad, dil, relu=False)
+        assert _scaled_err(got_nb, F.conv2d(x, w, None, S, pad, dil)) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_gpu_tc5_conv_full_size_layers_and_channel_slice(fp32_library):
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(12)
+    for name, (H, W) in (("feature.conv2", (512, 640)), ("feature.conv5", (256, 320)), ("feature.conv9", (64, 80)), ("stage3.eval_conv", (64, 80))):
+        cin, cout, ks, S, pad, dil, relu = LAYERS[name]
+        x = torch.randn(5, cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
+        b = torch.randn(cout, generator=g).to(dev)
+        want = _ref_conv(x, w, b, S, pad, dil, relu)
+        got = ops.conv2d_tc5(x, ops.pack_conv_filter_tc5(w), b, cout, ks, S, pad, dil, relu=relu)
+        assert _scaled_err(got, want) <= 2e-5, name
+    # written into channels 8..15 of a wider channels-last tensor; the rest untouched
+    cin, cout = 16, 8
+    x = torch.randn(2, cin, 38, 54, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / 12).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    both = torch.full((2, 16, 38, 54), float("nan"), device=dev).contiguous(memory_format=torch.channels_last)
+    ops.conv2d_tc5(x, ops.pack_conv_filter_tc5(w), b, cout, 3, 1, 1, 1, relu=True, out=both, out_channel_offset=8)
+    torch.cuda.synchronize()
+    assert torch.isnan(both[:, :8]).all()
+    assert _scaled_err(both[:, 8:], F.conv2d(x, w, b, padding=1).relu()) <= 2e-5
+
+
 @pytest.mark.gpu
 def test_gpu_transposed_conv_and_channel_slices(fp32_library):
     dev = "cuda:0"

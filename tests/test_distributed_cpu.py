@@ -44,18 +44,35 @@ def _worker(rank, world, port, out):
         local = mine.sum(dim=1, keepdim=True) * 2.0  # stand-in for the per-view computation
         full = pmd.gather_depth_maps(local, n_items)
         assert torch.equal(full, images.sum(dim=1, keepdim=True) * 2.0)
-        # 2. gradient all-reduce with a never-used parameter (grad is None)
+        # 2. gradient all-reduce: .grad tensors are views of ONE flat buffer, a never-used parameter keeps zeros
         torch.manual_seed(0)
         lin = torch.nn.Linear(4, 3)
         unused = torch.nn.Parameter(torch.ones(5))
-        x = torch.full((2, 4), float(rank + 1))
-        lin(x).sum().backward()
-        ref_w = sum(torch.full((3, 4), float(r + 1)) * 2 for r in range(world)) / world
         reducer = pmd.FlatGradAllReduce(list(lin.parameters()) + [unused])
-        missing = reducer()
-        assert missing == 1 and unused.grad is None
-        assert torch.allclose(lin.weight.grad, ref_w)
-        assert torch.allclose(lin.bias.grad, torch.full((3,), 2.0))
+        assert lin.weight.grad.data_ptr() == reducer.flat.data_ptr()  # first slice of the flat buffer: no copy anywhere
+        ref_w = sum(torch.full((3, 4), float(r + 1)) * 2 for r in range(world)) / world
+        for step in range(2):  # second step: zero_() + accumulate-in-place again
+            reducer.zero_()
+            x = torch.full((2, 4), float(rank + 1))
+            lin(x).sum().backward()
+            assert lin.weight.grad is reducer.views[0], "autograd must accumulate into the view, not replace it"
+            detached = reducer()
+            assert detached == 0 and reducer.never_reached == 1
+            assert torch.allclose(lin.weight.grad, ref_w)
+            assert torch.allclose(lin.bias.grad, torch.full((3,), 2.0))
+            assert unused.grad is reducer.views[2] and float(unused.grad.abs().max()) == 0.0
+        # a gradient on one rank only: every rank still receives the average (replicas cannot drift apart)
+        reducer.zero_()
+        if rank == 0:
+            (unused * 3.0).sum().backward()
+        reducer()
+        assert torch.allclose(unused.grad, torch.full((5,), 3.0 / world))
+        # somebody dropped the views (optimizer.zero_grad(set_to_none=True)): copied in and re-attached
+        for p in list(lin.parameters()) + [unused]:
+            p.grad = None
+        lin(torch.full((2, 4), float(rank + 1))).sum().backward()
+        assert reducer() == 3  # two fresh autograd tensors and one None: copied in / zero-filled, then re-attached
+        assert torch.allclose(lin.weight.grad, ref_w) and lin.weight.grad is reducer.views[0]
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))

@@ -34,7 +34,7 @@ def emu():
     P, I = ctypes.c_void_p, ctypes.c_int
     lib.emu_warp_corr3.argtypes = [P] * 5 + [ctypes.POINTER(_native.MlpStruct), P, P] + [I] * 13
     lib.emu_warp_corr3.restype = I
-    lib.emu_warp_corr4.argtypes = [P] * 5 + [ctypes.POINTER(_native.MlpStruct), P, P] + [I] * 14
+    lib.emu_warp_corr4.argtypes = [P] * 5 + [ctypes.POINTER(_native.MlpStruct), P, P] + [I] * 15
     lib.emu_warp_corr4.restype = I
     lib.emu_adaptive_eval.argtypes = [P] * 5 + [I] + [P] * 5 + [I] * 6 + [ctypes.c_float, I, I, I]
     lib.emu_adaptive_eval.restype = I
@@ -212,7 +212,7 @@ def test_emulated_fused_heads_match_unfused(emu, C, G, H, W, D, B, V):
 # ---- K-A generation 4 (pm_warpcorr4.cuh): persistent producer / consumer pipeline over TMA-staged windows ----------------
 
 
-def _run_ka4(emu, ref, srcs, rt, depth, G, epi, nw, cap, grid, vw=None, head=None, keep_sims=False, ostride=1):
+def _run_ka4(emu, ref, srcs, rt, depth, G, epi, nw, cap, grid, stages=2, vw=None, head=None, keep_sims=False, ostride=1):
     B, C, H, W = ref.shape
     V, D = len(srcs), depth.shape[1]
     Hs, Ws = srcs[0].shape[-2:]
@@ -224,15 +224,15 @@ def _run_ka4(emu, ref, srcs, rt, depth, G, epi, nw, cap, grid, vw=None, head=Non
     depth_c, vw_c = depth.contiguous(), None if vw is None else vw.contiguous()
     out_ptr = out.data_ptr() + 4 * (ostride - 1)
     rc = emu.emu_warp_corr4(_ptr(ref_n), _ptr(src_n), _ptr(rt), _ptr(depth_c), _ptr(vw_c), head, out_ptr, _ptr(sims), ostride,
-                            V, B, C, G, H, W, Hs, Ws, D, epi, nw, cap, grid)
+                            V, B, C, G, H, W, Hs, Ws, D, epi, nw, cap, grid, stages)
     assert rc == 0, rc
     return (out, sims) if keep_sims else out
 
 
-# (consumer warps, texels per window slot, persistent CTAs): a roomy slot with one CTA per item; a slot too small for most
+# (consumer warps, texels per window slot, persistent CTAs, ring depth): a roomy slot with one CTA per item; a slot too small for most
 # boxes (clipped windows -> part of the cells take the global path) with 3 CTAs walking all items through the rings; a
 # slot of 16 texels (nearly everything from global memory) with a single CTA
-KA4_CONFIGS = [(4, 512, 0), (8, 512, 0), (4, 48, 3), (8, 40, 2), (4, 16, 1)]
+KA4_CONFIGS = [(4, 512, 0, 2), (8, 512, 0, 4), (4, 48, 3, 3), (8, 40, 2, 2), (4, 16, 1, 4)]
 
 
 @pytest.mark.parametrize("C,G,H,W,D,B,V", KA_SHAPES)
@@ -243,20 +243,20 @@ def test_emulated_warp_corr4_matches_oracle(emu, C, G, H, W, D, B, V):
     scale = max(1.0, float(want.abs().max()))
     wsum = 1e-5 + vw.sum(1)
     want_f = (want * vw.permute(1, 0, 2, 3)[:, :, None, None]).sum(0) / wsum[:, None, None]
-    for nw, cap, grid in KA4_CONFIGS:
-        got = _run_ka4(emu, ref, srcs, rt, depth, G, 0, nw, cap, grid)
-        assert maxabs(got, want) <= 2e-5 * scale, (nw, cap, grid)
+    for nw, cap, grid, st in KA4_CONFIGS:
+        got = _run_ka4(emu, ref, srcs, rt, depth, G, 0, nw, cap, grid, st)
+        assert maxabs(got, want) <= 2e-5 * scale, (nw, cap, grid, st)
         assert float(got[:, :, :, 0, : max(1, H // 4)].abs().max()) == 0.0  # behind the camera: exactly 0
-        got_f = _run_ka4(emu, ref, srcs, rt, depth, G, 1, nw, cap, grid, vw=vw)
-        assert maxabs(got_f, want_f) <= 2e-5 * scale, (nw, cap, grid)
+        got_f = _run_ka4(emu, ref, srcs, rt, depth, G, 1, nw, cap, grid, st, vw=vw)
+        assert maxabs(got_f, want_f) <= 2e-5 * scale, (nw, cap, grid, st)
 
 
 def test_emulated_warp_corr4_source_map_of_other_size(emu):
     C, G, H, W, D, B, V = 32, 8, 12, 20, 8, 1, 2
     ref, srcs, ref_proj, src_projs, depth, vw = _warp_case(B, V, C, H, W, D, Hs=9, Ws=14, seed=5)
     want = _oracle_sims(ref, srcs, ref_proj, src_projs, depth, G)
-    for nw, cap, grid in KA4_CONFIGS[:3]:
-        got = _run_ka4(emu, ref, srcs, _rt(ref_proj, src_projs), depth, G, 0, nw, cap, grid)
+    for nw, cap, grid, st in KA4_CONFIGS[:3]:
+        got = _run_ka4(emu, ref, srcs, _rt(ref_proj, src_projs), depth, G, 0, nw, cap, grid, st)
         assert maxabs(got, want) <= 5e-5 * max(1.0, float(want.abs().max()))
 
 
@@ -269,8 +269,8 @@ def test_emulated_warp_corr4_equals_generation_3(emu):
     depth = (600.0 + 4.0 * torch.arange(D).view(1, D, 1, 1) + 30.0 * torch.rand(B, 1, H, W)).expand(B, D, H, W).contiguous()
     rt = _rt(ref_proj, src_projs)
     g3 = _run_ka(emu, ref, srcs, rt, depth, G, 0, 8, 1)
-    for nw, cap, grid in ((4, 256, 0), (8, 64, 5)):
-        g4 = _run_ka4(emu, ref, srcs, rt, depth, G, 0, nw, cap, grid)
+    for nw, cap, grid, st in ((4, 256, 0, 2), (8, 64, 5, 3)):
+        g4 = _run_ka4(emu, ref, srcs, rt, depth, G, 0, nw, cap, grid, st)
         assert maxabs(g4, g3) <= 1e-5 * max(1.0, float(g3.abs().max()))
 
 
@@ -288,14 +288,14 @@ def test_emulated_warp_corr4_fused_heads_match_unfused(emu, C, G, H, W, D, B, V)
         want = sim_head(agg)
         pw = _random_head(PixelwiseNet, G, 2)
         want_vw = torch.cat([pw(sims[v]) for v in range(V)], dim=1)
-    for nw, cap, grid in KA4_CONFIGS[:4]:
-        got = _run_ka4(emu, ref, srcs, rt, depth, G, 2, nw, cap, grid, vw=vw, head=sim_head.folded())
-        assert maxabs(got[..., 0], want) <= 2e-5 * max(1.0, float(want.abs().max())), (nw, cap, grid)
-        got_vw, kept = _run_ka4(emu, ref, srcs, rt, depth, G, 3, nw, cap, grid, head=pw.folded(), keep_sims=True)
-        assert maxabs(got_vw, want_vw) <= 1e-5, (nw, cap, grid)
+    for nw, cap, grid, st in KA4_CONFIGS[:4]:
+        got = _run_ka4(emu, ref, srcs, rt, depth, G, 2, nw, cap, grid, st, vw=vw, head=sim_head.folded())
+        assert maxabs(got[..., 0], want) <= 2e-5 * max(1.0, float(want.abs().max())), (nw, cap, grid, st)
+        got_vw, kept = _run_ka4(emu, ref, srcs, rt, depth, G, 3, nw, cap, grid, st, head=pw.folded(), keep_sims=True)
+        assert maxabs(got_vw, want_vw) <= 1e-5, (nw, cap, grid, st)
         assert maxabs(kept, sims) <= 2e-5 * max(1.0, float(sims.abs().max()))
-    nw, cap, grid = KA4_CONFIGS[2]
-    xs = _run_ka4(emu, ref, srcs, rt, depth, G, 2, nw, cap, grid, vw=vw, head=sim_head.folded(), ostride=2)
+    nw, cap, grid, st = KA4_CONFIGS[2]
+    xs = _run_ka4(emu, ref, srcs, rt, depth, G, 2, nw, cap, grid, st, vw=vw, head=sim_head.folded(), ostride=2)
     assert bool((xs[..., 0] == -77.0).all()) and maxabs(xs[..., 1], want) <= 2e-5 * max(1.0, float(want.abs().max()))
 
 

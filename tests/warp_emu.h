@@ -288,6 +288,7 @@ inline int __reduce_add_sync(unsigned mask, int v) {
 template <typename T>
 inline T __ldg(const T *p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline void __nanosleep(unsigned) {}
 inline int __float_as_int(float f) { return emu::from_bits<int>(emu::bits_of(f)); }
 inline float __int_as_float(int i) { return emu::from_bits<float>(emu::bits_of(i)); }
 inline float __fdividef(float a, float b) { return a / b; }

@@ -105,6 +105,14 @@ for (name, N, cin, cout, ks, S, pad, dil, relu, h, w) in LAYERS:
                 row["native_tf32_gbs"] = round(act_bytes / (c * 1e-6) / 1e9, 1)
                 row["native_tf32_tflops"] = round(flops / (c * 1e-6) / 1e12, 2)
                 row["speedup_vs_cudnn_cold"] = round(row["cudnn_tf32_us"]["cold"] / c, 2)
+    if cin in (8, 16, 32, 64):  # K-D5: tcgen05 implicit GEMM, 3xTF32 (fp32-accurate) -- compare with native_p3
+        try:
+            f5 = ops.pack_conv_filter_tc5(wt)
+            c, cmin, wm = timeit(lambda: ops.conv2d_tc5(x, f5, b, cout, ks, S, pad, dil, relu=relu))
+            row["tc5_3xtf32_us"] = {"cold": round(c, 1), "cold_min": round(cmin, 1), "warm": round(wm, 1)}
+            row["tc5_tflops_3x"] = round(3 * flops / (c * 1e-6) / 1e12, 1)
+        except Exception as e:  # noqa: BLE001
+            row["tc5_3xtf32_us"] = f"ERR {e}"
     rows.append(row)
 tot_lib = sum(r["cudnn_tf32_us"]["cold"] for r in rows)
 tot_nat = sum(r["native_p1_mt0_us"]["cold"] for r in rows if isinstance(r.get("native_p1_mt0_us"), dict))

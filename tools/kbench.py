@@ -20,9 +20,10 @@ dev = "cuda:0"
 torch.backends.cudnn.benchmark = True
 torch.backends.cudnn.allow_tf32 = os.environ.get("PM_TF32", "0") == "1"  # default: the fp32-accurate mode bench.py times
 H, W = int(os.environ.get("KB_H", 512)), int(os.environ.get("KB_W", 640))
+BATCH = int(os.environ.get("KB_B", 1))
 net, _ = bench.build_net()
 net = net.to(dev)
-inp = synthetic.make_inputs(1, 5, H, W, seed=0)
+inp = synthetic.make_inputs(BATCH, 5, H, W, seed=0)
 args = lambda: ([i.to(dev) for i in inp["images"]], inp["intrinsics"].to(dev), inp["extrinsics"].to(dev), inp["depth_min"].to(dev), inp["depth_max"].to(dev))
 names = ("warp_corr_score", "warp_corr_view_weights", "aggregate_views_score", "adaptive_eval", "init_propagate", "offset_corr_weight")
 calls = []
@@ -68,7 +69,7 @@ def timeit(fn, iters=12):
     return round(statistics.mean(ts), 2), round(min(ts), 2), round(a.elapsed_time(b) * 1e2, 2)
 
 
-out = {"shape": f"{W}x{H}", "rows": []}
+out = {"shape": f"{W}x{H} B{BATCH}", "rows": []}
 
 
 def with_knobs(knobs, fn):
@@ -82,8 +83,9 @@ def with_knobs(knobs, fn):
 
 
 # K-A: generation 4 (consumer warps x resident CTAs the ring is sized for) against generation 3 (rows per pass x pipeline)
-ka_variants = ([dict(ka_gen=4, ka4_nw=nw, ka4_ctas=c) for nw, c in ((4, 2), (4, 3), (4, 4), (4, 5), (8, 1), (8, 2), (8, 3))]
-               + [dict(ka_gen=3)] + [dict(ka_gen=3, ka3_dc=d, ka3_pipe=pp) for d, pp in itertools.product((4, 8, 16), (0, 1))])
+ka_variants = ([dict(ka_gen=4, ka4_nw=nw, ka4_ctas=c, ka4_stages=st) for nw, c, st in
+                ((4, 2, 2), (4, 2, 3), (4, 2, 4), (4, 3, 2), (4, 3, 3), (4, 4, 2), (8, 1, 4), (8, 2, 2), (8, 2, 3))]
+               + [dict(ka_gen=3)] + [dict(ka_gen=3, ka3_dc=d, ka3_pipe=0) for d in (4, 8, 16)])
 for (n, a, k) in calls:
     desc = n
     if n.startswith("warp_corr"):
