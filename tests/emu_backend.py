@@ -82,6 +82,9 @@ class EmulatedLibrary:
 
     def pmb200_adaptive_eval(self, score0, depth, xnorm, xs, off, off_cl, fw, dmin, dmax, prob, depth_out, B, D, H, W, K, dilation,
                              scale, is_inverse, stream):
+        if xs is not None:  # the fused path: generation 2 (shared-memory neighbourhood), slab small enough to exercise clipping
+            return self.emu.emu_adaptive_eval2(depth, xs, off, off_cl, fw, dmin, dmax, prob, depth_out, B, D, H, W, K, dilation, scale,
+                                               is_inverse, 8, 4, min(D, 4), 8, 120)
         return self.emu.emu_adaptive_eval(score0, depth, xnorm, xs, off, off_cl, fw, dmin, dmax, prob, depth_out, B, D, H, W, K,
                                           dilation, scale, is_inverse, 16, min(D, 16))
 
@@ -102,6 +105,9 @@ class EmulatedLibrary:
                                       B, D, H, W, K, dilation, scale, inverse, stream):
         return self.emu.emu_adaptive_eval_backward(score0, hyp, xnorm, off, fw, dmin, dmax, prob, g_depth, g_prob, d_score0, d_hyp, d_off,
                                                    d_fw, B, D, H, W, K, dilation, scale, inverse)
+
+    def pmb200_conv2d_tc5_supported(self, cin, cout, ks, stride):
+        return 0  # tcgen05 / TMEM has no emulation: the convs take the mma.sync kernel here, K-D5 is checked on the GPU only
 
     def pmb200_conv2d_filter_floats(self, cin, cout, ks, prec):
         return self.conv.emu_conv2d_filter_floats(cin, cout, ks, prec)

@@ -109,6 +109,15 @@ def test_eval_mode_with_grad_enabled_is_differentiable(golden_weights):
     """eval() with autograd on must not take the folded / native inference branches (constants built
     under no_grad, cudnn_convolution_relu has no derivative): every FeatureNet / Refinement parameter gets a gradient,
     as in the reference, which is fully differentiable in eval mode."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # both paths fp32-accurate, so that they can be compared at the end
+    try:
+        _eval_mode_grad_body(golden_weights)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def _eval_mode_grad_body(golden_weights):
     net = _net(golden_weights)
     inp = synthetic.make_inputs(1, 3, 64, 80, seed=2)
     fixed = torch.rand(1, 48, 8, 10, device=DEV)

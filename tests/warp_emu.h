@@ -298,6 +298,7 @@ inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline int atomicMax(int *p, int v) { const int o = *p; *p = std::max(o, v); return o; }
+inline int atomicMin(int *p, int v) { const int o = *p; *p = std::min(o, v); return o; }
 inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
 inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
 inline float4 atomicAdd(float4 *p, float4 v) {  // sm_90+ 128-bit vector atomic (needs a 16-byte aligned address)

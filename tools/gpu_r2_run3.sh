@@ -16,7 +16,7 @@ echo "pytest exit $? at $(( $(date +%s) - t0 )) s" >> gpurun_out/pytest_gpu.log
 grep -h "bench-mode parity" gpurun_out/pytest_gpu.log | cut -c1-300
 tail -6 gpurun_out/pytest_gpu.log | cut -c1-300
 timeout 400 python tools/convbench.py > gpurun_out/convbench.json 2> gpurun_out/convbench.err
-KB_SWEEP_EVAL=0 timeout 500 python tools/kbench.py > gpurun_out/kbench.json 2> gpurun_out/kbench.err
+timeout 500 python tools/kbench.py > gpurun_out/kbench.json 2> gpurun_out/kbench.err
 KB_B=8 KB_SWEEP_EVAL=0 timeout 500 python tools/kbench.py > gpurun_out/kbench_b8.json 2> gpurun_out/kbench_b8.err
 timeout 420 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit $? at $(( $(date +%s) - t0 )) s" >> gpurun_out/bench.err
@@ -40,7 +40,7 @@ for f in ("bench.json","bench_no_tc5.json"):
 for f in ("kbench.json","kbench_b8.json"):
     try:
         for r in json.load(open("gpurun_out/"+f))['rows']:
-            if 'warp_corr' in r['call']:
+            if 'warp_corr' in r['call'] or 'adaptive_eval' in r['call']:
                 print('  ',f,r['call'],'default',r['default_us'])
                 for k,v in r.items():
                     if isinstance(v,list) and k!='default_us': print('        ',k,v)
