@@ -47,7 +47,7 @@ const char *pmb200_last_error(void);
  * Keys: "ka_gen" (3 | 4: generation of the fused warp+correlation kernel), "ka3_dc", "ka3_dc_vw", "ka3_pipe", "ka3_minb"
  * (generation-3 rows per pass / gather pipeline / resident CTAs), "ka4_nw" (4 | 8 consumer warps = tile rows), "ka4_ctas"
  * (resident CTAs per SM the window ring is sized for), "ka4_cap" (texels per ring slot), "ka4_stages" (ring depth 2..4), "ka4_grid" (persistent CTAs),
- * "kb_gen" (1 | 2: generation of the adaptive-evaluation kernel), "kb_tp", "kb_dy" (its block shape); 0 = the built-in default.  "reset" restores every
+ * "kb_tp", "kb_dy" (block shape of the adaptive-evaluation kernel); 0 = the built-in default.  "reset" restores every
  * default.  Results never depend on these knobs, only launch shapes do.  Returns 0, or PMB200_EINVAL for an unknown key.
  * The reference has no counterpart (its launch shapes are ATen's). */
 int pmb200_set_tuning(const char *key, int value);

@@ -1124,194 +1124,6 @@ __global__ void __launch_bounds__(256) adaptive_eval_kernel(const EvalParams p) 
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// K-B, second generation (the fused inference path: interleaved (xnorm, score) buffer).  ncu of the first generation
-// (profiles/r1_run23_ncu.md, r2_run2_ncu.md): long_scoreboard 4.4-6.1 warps per issue slot, issue 34-47 % -- every
-// (pixel, hypothesis) thread gathered its 36 taps from L2.  The taps of a pixel tile live in a small neighbourhood
-// (fixed evaluation offsets +- (dilation - 1) plus the learned offsets), so the block now
-//   1. builds the K footprints of its TX x TY pixel tile once (as before) and reduces their bounding box in the map;
-//   2. stages that box of the (xnorm, score) map for a chunk of DCH hypotheses into shared memory with cp.async
-//      (8-byte elements, any alignment; boxes larger than the slab budget are clipped around their centre);
-//   3. gathers from shared memory (LDS.64, immediate tap offsets from one per-(neighbour, pixel) base index computed in
-//      the prologue); a footprint outside the staged box takes the global path exactly as generation 1 does.
-// Softmax and regression are unchanged.
-// ------------------------------------------------------------------------------------------
-struct Eval2Launch {
-    int TX, TY, DCH, cap;  // pixel tile, hypotheses per staged chunk, float2 elements per hypothesis slab
-};
-
-__device__ __forceinline__ void cp_async8(float2 *smem_dst, const float2 *gmem_src) {
-#if defined(PM_EMU)
-    *smem_dst = *gmem_src;
-#else
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-#if !defined(PM_EMU)
-    asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}
-
-// block (TP = TX*TY pixels, DY hypothesis lanes); dynamic smem: float4 cw[K][TP]; float2 win[DCH][cap]; int ck[K][TP];
-// int co[K][TP]; float cf[K][TP]; float sc[D][TP]; float pr[D][TP]; int box[8]
-template <int KT>
-__global__ void __launch_bounds__(256) adaptive_eval2_kernel(const EvalParams p, const Eval2Launch L) {
-#if defined(PM_EMU)
-    float4 *smem4 = static_cast<float4 *>(emu::dyn_smem());
-#else
-    extern __shared__ float4 smem4[];
-#endif
-    const int TP = blockDim.x, DY = blockDim.y;
-    float4 *cw = smem4;
-    float2 *win = reinterpret_cast<float2 *>(cw + (size_t)KT * TP);
-    int *ck = reinterpret_cast<int *>(win + (size_t)L.DCH * L.cap);
-    int *co = ck + (size_t)KT * TP;
-    float *cf = reinterpret_cast<float *>(co + (size_t)KT * TP);
-    float *sc = cf + (size_t)KT * TP;
-    float *pr = sc + (size_t)p.D * TP;
-    int *box = reinterpret_cast<int *>(pr + (size_t)p.D * TP);  // [0..3] min x, max x, min y, max y; [4..7] x0, y0, w, h
-
-    const int tp = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * TP + tp, nthreads = TP * DY;
-    const int HW = p.H * p.W;
-    const int tiles_x = (p.W + L.TX - 1) / L.TX;
-    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
-    const int px = tile_x * L.TX + tp % L.TX, py = tile_y * L.TY + tp / L.TX;
-    const int b = blockIdx.y;
-    const bool live = px < p.W && py < p.H;
-    const int n = live ? py * p.W + px : 0;
-    const float inv_interval = 1.0f / p.interval_scale;
-
-    if (tid == 0) { box[0] = 1 << 30; box[1] = -1; box[2] = 1 << 30; box[3] = -1; }
-    __syncthreads();
-    int lx0 = 1 << 30, lx1 = -1, ly0 = 1 << 30, ly1 = -1;
-    for (int k = ty; k < KT; k += DY) {
-        int dy = 0, dx = 0;
-        pm::neighbour_offset(true, p.K, p.dilation, k, &dy, &dx);
-        const float2 lo = load_offset(p.offsets, p.off_nhwc, b, k, n, p.K, HW);
-        const pm::Cell c = pm::border_cell((float)px + (float)dx + lo.x, (float)py + (float)dy + lo.y, p.H, p.W);
-        cw[k * TP + tp] = make_float4(c.w00, c.w01, c.w10, c.w11);
-        ck[k * TP + tp] = c.key;
-        cf[k * TP + tp] = __ldg(p.fw + ((size_t)b * p.K + k) * HW + n);
-        if (live) {
-            const int r0 = pm::cell_r0(c.key), y0 = r0 / p.W, x0 = r0 - y0 * p.W;
-            lx0 = min(lx0, x0); lx1 = max(lx1, x0 + pm::cell_dx(c.key));
-            ly0 = min(ly0, y0); ly1 = max(ly1, y0 + pm::cell_dy(c.key));
-        }
-    }
-    if (live) {  // the pixel itself (centre value of every hypothesis) belongs to the box as well
-        lx0 = min(lx0, px); lx1 = max(lx1, px); ly0 = min(ly0, py); ly1 = max(ly1, py);
-    }
-    if (lx1 >= 0) {
-        atomicMin(&box[0], lx0); atomicMax(&box[1], lx1);
-        atomicMin(&box[2], ly0); atomicMax(&box[3], ly1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int x0 = box[0], y0 = box[2], w = box[1] - box[0] + 1, h = box[3] - box[2] + 1;
-        if (box[1] < 0) { x0 = y0 = 0; w = h = 0; }
-        if (w > L.cap) { x0 += (w - L.cap) / 2; w = L.cap; }
-        if (w > 0 && w * h > L.cap) {  // keep the centre rows; the rest takes the global path
-            const int nh = max(1, L.cap / w);
-            y0 += (h - nh) / 2;
-            h = nh;
-        }
-        box[4] = x0; box[5] = y0; box[6] = w; box[7] = h;
-    }
-    __syncthreads();
-    const int wx0 = box[4], wy0 = box[5], ww = box[6], wh = box[7];
-    for (int k = ty; k < KT; k += DY) {
-        const int key = ck[k * TP + tp];
-        const int r0 = pm::cell_r0(key), y0 = r0 / p.W, x0 = r0 - y0 * p.W;
-        const int ox = x0 - wx0, oy = y0 - wy0;
-        const bool in = ox >= 0 && oy >= 0 && ox + pm::cell_dx(key) < ww && oy + pm::cell_dy(key) < wh;
-        co[k * TP + tp] = in ? oy * ww + ox : -1;
-    }
-    const int cx = px - wx0, cy = py - wy0;
-    const int centre = (live && cx >= 0 && cy >= 0 && cx < ww && cy < wh) ? cy * ww + cx : -1;
-
-    for (int dch = 0; dch < p.D; dch += L.DCH) {
-        const int nd = min(L.DCH, p.D - dch);
-        __syncthreads();  // previous chunk fully consumed (also orders the `co` writes before the first gather)
-        const int per = ww * wh;
-        for (int idx = tid; idx < nd * per; idx += nthreads) {
-            const int dl = idx / per, r = idx - dl * per;
-            const int yy = r / ww, xx = r - yy * ww;
-            cp_async8(win + (size_t)dl * L.cap + r, p.xs + ((size_t)b * p.D + dch + dl) * HW + (size_t)(wy0 + yy) * p.W + wx0 + xx);
-        }
-        cp_async_wait_all();
-        __syncthreads();
-        for (int dl = ty; dl < nd; dl += DY) {
-            const int d = dch + dl;
-            const float2 *xsm = p.xs + ((size_t)b * p.D + d) * HW;
-            const float2 *slab = win + (size_t)dl * L.cap;
-            const float xc = centre >= 0 ? slab[centre].x : __ldg(xsm + n).x;
-            float num = 0.0f, den = 0.0f;
-#pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                const float4 w = cw[k * TP + tp];
-                const int key = ck[k * TP + tp], off = co[k * TP + tp];
-                const int ddx = pm::cell_dx(key), ddy = pm::cell_dy(key);
-                float2 v0, v1, v2, v3;
-                if (off >= 0) {
-                    const float2 *q0 = slab + off, *q2 = q0 + ddy * ww;
-                    v0 = q0[0]; v1 = q0[ddx]; v2 = q2[0]; v3 = q2[ddx];
-                } else {
-                    const float2 *q0 = xsm + pm::cell_r0(key), *q2 = q0 + ddy * p.W;
-                    v0 = __ldg(q0); v1 = __ldg(q0 + ddx); v2 = __ldg(q2); v3 = __ldg(q2 + ddx);
-                }
-                const float2 acc = ffma2(v3, make_float2(w.w, w.w), ffma2(v2, make_float2(w.z, w.z),
-                                   ffma2(v1, make_float2(w.y, w.y), make_float2(v0.x * w.x, v0.y * w.x))));
-                const float t = fminf(fabsf(acc.x - xc) * inv_interval, 4.0f);
-                const float sg = __fdividef(1.0f, 1.0f + __expf(2.0f * t - 4.0f));
-                const float wk = sg * cf[k * TP + tp];
-                num = fmaf(acc.y, wk, num);
-                den += wk;
-            }
-            sc[d * TP + tp] = num / den;
-        }
-    }
-    __syncthreads();
-
-    // softmax over the hypotheses of this pixel and depth regression: as generation 1
-    float m = -INFINITY;
-    for (int d = 0; d < p.D; ++d) m = fmaxf(m, sc[d * TP + tp]);
-    for (int d = ty; d < p.D; d += DY) pr[d * TP + tp] = expf(sc[d * TP + tp] - m);
-    __syncthreads();
-    float sum = 0.0f;
-    for (int d = 0; d < p.D; ++d) sum += pr[d * TP + tp];
-    const float lse = logf(sum);
-    __syncthreads();
-    for (int d = ty; d < p.D; d += DY) {
-        const float q = expf(sc[d * TP + tp] - m - lse);  // exp(log_softmax), as the reference writes it
-        pr[d * TP + tp] = q;
-        if (live) p.prob[((size_t)b * p.D + d) * HW + n] = q;
-    }
-    __syncthreads();
-    if (ty == 0 && live) {
-        float out;
-        if (p.is_inverse) {  // reference models/patchmatch.py:227-234
-            float idx = 0.0f;
-            for (int d = 0; d < p.D; ++d) idx = fmaf((float)d, pr[d * TP + tp], idx);
-            const float inv_hi = 1.0f / __ldg(p.depth + ((size_t)b * p.D + (p.D - 1)) * HW + n);
-            const float inv_lo = 1.0f / __ldg(p.depth + ((size_t)b * p.D) * HW + n);
-            out = 1.0f / (inv_lo + idx / (float)(p.D - 1) * (inv_hi - inv_lo));
-        } else {
-            float e = 0.0f;
-            for (int d = 0; d < p.D; ++d) e = fmaf(__ldg(p.depth + ((size_t)b * p.D + d) * HW + n), pr[d * TP + tp], e);
-            out = e;
-        }
-        p.depth_out[(size_t)b * HW + n] = out;
-    }
-}
-
-inline size_t eval2_smem_bytes(int K, int TP, int D, int DCH, int cap) {
-    return (size_t)K * TP * (sizeof(float4) + 2 * sizeof(int) + sizeof(float)) + (size_t)DCH * cap * sizeof(float2) +
-           2 * (size_t)D * TP * sizeof(float) + 8 * sizeof(int);
-}
-
 #if defined(PM_EMU)
 }  // namespace  (the emulation build stops here: launchers and the C ABI below need the CUDA runtime)
 #else
@@ -1322,12 +1134,13 @@ cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 // (tools/kbench.py) changes them through pmb200_set_tuning().  Nothing in the launch path reads the environment.
 // ------------------------------------------------------------------------------------------
 enum Tune { kTuneKaGen, kTuneKa3Dc, kTuneKa3DcVw, kTuneKa3Pipe, kTuneKa3MinB, kTuneKa4Nw, kTuneKa4Ctas, kTuneKa4Cap, kTuneKa4Grid,
-            kTuneKa4Stages, kTuneKbTp, kTuneKbDy, kTuneKbGen, kTuneCount };
+            kTuneKa4Stages, kTuneKbTp, kTuneKbDy, kTuneCount };
 const char *const kTuneNames[kTuneCount] = {"ka_gen", "ka3_dc", "ka3_dc_vw", "ka3_pipe", "ka3_minb", "ka4_nw", "ka4_ctas", "ka4_cap",
-                                            "ka4_grid", "ka4_stages", "kb_tp", "kb_dy", "kb_gen"};
-// ka_gen: 3 until generation 4 beats it on hardware at the bench sizes (profiles/r2_run2_kbench.json: 42 vs 34-40 us at stage 2)
-const int kTuneDefaults[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-int g_tune[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                                            "ka4_grid", "ka4_stages", "kb_tp", "kb_dy"};
+// ka_gen: 3.  Generation 4 (TMA-staged windows) is parity-green on B200 but slower at every bench shape (cold us, gen 3 / gen 4:
+// 47.6 / 91.7, 20.5 / 33.0, 34.3 / 41.0, 37.0 / 49.1 -- profiles/r2_run3_kbench.json; DESIGN.md has the analysis)
+const int kTuneDefaults[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
+int g_tune[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
 inline int tune(Tune t) { return __atomic_load_n(&g_tune[t], __ATOMIC_RELAXED); }
 
 // Third-generation K-A launch (kept for shapes generation 4 does not take and for A/B measurements).
@@ -1336,9 +1149,9 @@ void launch_wc3(const WarpCorrParams &p, const MlpParams &m, float *sims_out, cu
     const int HW = p.H * p.W;
     constexpr int pix_per_block = kWarps2 * LaneMap<C, G>::PPW;
     dim3 grid((HW + pix_per_block - 1) / pix_per_block, (p.D + DC - 1) / DC, p.B);
-    // measured on B200 (profiles/r1_run5_kbench.json): the two-deep gather pipeline pays at 8 pixels per warp
-    // (C = 32), is neutral at 4 and loses to the higher occupancy of the plain loop at 16
-    constexpr int kPipeDefault = LaneMap<C, G>::PPW == 8 ? 1 : 0;
+    // measured on B200 with the round-2 kernels (profiles/r2_run3_kbench.json): the plain gather loop wins at every lane map
+    // (C = 32, 8 rows per pass: 34.3 us against 40.8 with the two-deep pipeline, whose 128 registers cost a resident CTA)
+    constexpr int kPipeDefault = 0;
     const int pipe = tune(kTuneKa3Pipe) < 0 ? kPipeDefault : tune(kTuneKa3Pipe);
     if constexpr (EPI == kEpiScore && LaneMap<C, G>::PPW == 8) {
         // sweep candidate (ka3_minb = 5): the pipelined stage-2 kernel holds 128 registers -> 4 resident CTAs per SM; capped
@@ -1833,48 +1646,11 @@ int pmb200_adaptive_eval(const float *score0, const float *depth_sample, const f
         TP = 8;
         DY = D < 32 ? D : 32;
     }
-    if (!(p.xs && tune(kTuneKbGen) != 1)) {   // measurement aid (tools/kbench.py): kb_tp / kb_dy override the block shape
+    {   // measurement aid (tools/kbench.py): kb_tp / kb_dy override the block shape
         const int etp = tune(kTuneKbTp), edy = tune(kTuneKbDy);
         if (etp > 0 && edy > 0 && etp * edy <= 256 && smem_for(etp) <= 48 * 1024) {
             TP = etp;
             DY = edy < D ? edy : D;
-        }
-    }
-    if (p.xs && tune(kTuneKbGen) != 1) {
-        // generation 2: (xnorm, score) neighbourhood of a 2-D pixel tile staged in shared memory per hypothesis chunk
-        Eval2Launch L;
-        L.TX = 16;
-        L.TY = 4;
-        int dy2 = D < 4 ? D : 4;
-        if ((long long)((W + 15) / 16) * ((H + 3) / 4) * B < 2 * 148) {  // small maps: smaller tiles so that the grid covers the SMs
-            L.TX = 8;
-            L.TY = 4;
-            dy2 = D < 8 ? D : 8;
-        }
-        if (tune(kTuneKbTp) > 0 && tune(kTuneKbDy) > 0) {  // measurement aid: kb_tp = tile width (x4 rows), kb_dy = hypothesis lanes
-            L.TX = tune(kTuneKbTp);
-            dy2 = tune(kTuneKbDy) < D ? tune(kTuneKbDy) : D;
-        }
-        const int tp2 = L.TX * L.TY;
-        const int reach = 2 * (dilation + 2);  // typical halo: fixed offsets +- (dilation - 1), learned offsets, bilinear +1
-        L.cap = (L.TX + reach) * (L.TY + reach);
-        L.DCH = D < 8 ? D : 8;
-        while (L.DCH > 1 && eval2_smem_bytes(K, tp2, D, L.DCH, L.cap) > 96 * 1024) L.DCH /= 2;
-        const size_t smem2 = eval2_smem_bytes(K, tp2, D, L.DCH, L.cap);
-        if (smem2 <= 160 * 1024 && tp2 * dy2 <= 256) {
-            auto kern = K == 9 ? adaptive_eval2_kernel<9> : adaptive_eval2_kernel<17>;
-            static thread_local size_t attr9 = 0, attr17 = 0;
-            size_t &attr = K == 9 ? attr9 : attr17;
-            if (smem2 > 48 * 1024 && smem2 > attr) {
-                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) {
-                    cudaGetLastError();
-                    return fail(PMB200_EUNSUPPORTED, "adaptive_eval: shared-memory opt-in failed");
-                }
-                attr = smem2;
-            }
-            dim3 grid2(((W + L.TX - 1) / L.TX) * ((H + L.TY - 1) / L.TY), B);
-            kern<<<grid2, dim3(tp2, dy2), smem2, as_stream(stream)>>>(p, L);
-            return launch_status("adaptive_eval");
         }
     }
     const size_t smem = smem_for(TP);

@@ -236,19 +236,23 @@ def pack_conv_filter(weight: Tensor, precision: int, transposed: bool = False) -
 TC5_CONVS = os.environ.get("PMB200_TC5", "1") != "0"
 
 
+# (Cin, Cout, KS, stride) of the layers the tcgen05 kernel currently beats the mma.sync kernel's 3xTF32 mode on (cold us on
+# B200, profiles/r2_run3_convbench.json: FeatureNet conv5 77.0 vs 92.7, stage-3 propa_conv 27.3 vs 37.9, stage-3 eval_conv
+# 27.0 vs 40.6, stage-2 propa_conv 19.3 vs 25.5).  On the other layers its per-tap operand reloads and its serial
+# split -> MMA -> epilogue chain per tile still lose (conv1 256 vs 70, conv6/7 80 vs 67); PMB200_TC5=all takes every
+# supported layer (A/B measurements), PMB200_TC5=0 none.
+TC5_LAYERS = {(16, 32, 5, 2), (64, 32, 3, 1), (64, 18, 3, 1), (32, 16, 3, 1)}
+TC5_ALL = os.environ.get("PMB200_TC5", "1") == "all"
+
+
 def conv_uses_tc5(cin: int, cout: int, ks: int, stride: int = 1, transposed: bool = False, fused_add: bool = False) -> bool:
     """Which convs run on the tcgen05 kernel: the fp32-accurate mode only (its arithmetic IS the 3xTF32 split), no fused
-    transposed / upsample-add epilogue, a shape the kernel takes, and enough multiply-adds per output pixel for the tensor
-    pipe to matter (the 8-channel full-resolution layers are bound by activation traffic and stay on pm_conv.cu).
-    Measured per layer on B200: profiles/r2_run3_convbench.json."""
+    transposed / upsample-add epilogue, and a layer on the measured list above."""
     if not (NATIVE_CONVS and TC5_CONVS) or transposed or fused_add or conv_precision() != 3:
         return False
-    if cin * cout * ks * ks < TC5_MIN_MACS:
+    if not TC5_ALL and (cin, cout, ks, stride) not in TC5_LAYERS:
         return False
     return bool(_native.lib().pmb200_conv2d_tc5_supported(cin, cout, ks, stride))
-
-
-TC5_MIN_MACS = int(os.environ.get("PMB200_TC5_MIN_MACS", "1024"))
 
 
 def pack_conv_filter_tc5(weight: Tensor) -> Tensor:

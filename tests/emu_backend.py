@@ -82,9 +82,6 @@ class EmulatedLibrary:
 
     def pmb200_adaptive_eval(self, score0, depth, xnorm, xs, off, off_cl, fw, dmin, dmax, prob, depth_out, B, D, H, W, K, dilation,
                              scale, is_inverse, stream):
-        if xs is not None:  # the fused path: generation 2 (shared-memory neighbourhood), slab small enough to exercise clipping
-            return self.emu.emu_adaptive_eval2(depth, xs, off, off_cl, fw, dmin, dmax, prob, depth_out, B, D, H, W, K, dilation, scale,
-                                               is_inverse, 8, 4, min(D, 4), 8, 120)
         return self.emu.emu_adaptive_eval(score0, depth, xnorm, xs, off, off_cl, fw, dmin, dmax, prob, depth_out, B, D, H, W, K,
                                           dilation, scale, is_inverse, 16, min(D, 16))
 

@@ -141,31 +141,6 @@ int emu_adaptive_eval(const float *score0, const float *depth_sample, const floa
     return 0;
 }
 
-// K-B, second generation (interleaved (xnorm, score) input only): pixel tile TX x TY, DY hypothesis lanes, DCH hypotheses
-// per staged chunk, cap = float2 elements per slab (small values clip the staged box: global fallback of the gather).
-int emu_adaptive_eval2(const float *depth_sample, const float *xnorm_score, const float *offsets, int offsets_channels_last,
-                       const float *feature_weight, const float *depth_min, const float *depth_max, float *prob_out, float *depth_out,
-                       int B, int D, int H, int W, int K, int dilation, float interval_scale, int is_inverse, int TX, int TY, int DY,
-                       int DCH, int cap) {
-    EvalParams p;
-    p.score0 = nullptr; p.depth = depth_sample; p.xnorm = nullptr; p.offsets = offsets; p.fw = feature_weight;
-    p.xs = reinterpret_cast<const float2 *>(xnorm_score);
-    p.off_nhwc = offsets_channels_last ? 1 : 0;
-    p.dmin = depth_min; p.dmax = depth_max; p.prob = prob_out; p.depth_out = depth_out;
-    p.B = B; p.D = D; p.H = H; p.W = W; p.K = K; p.dilation = dilation; p.is_inverse = is_inverse;
-    p.interval_scale = interval_scale;
-    Eval2Launch L;
-    L.TX = TX; L.TY = TY; L.DCH = DCH < D ? DCH : D; L.cap = cap;
-    if (DY > D) DY = D;
-    const int TP = TX * TY;
-    const size_t smem = eval2_smem_bytes(K, TP, D, L.DCH, cap);
-    dim3 grid(((W + TX - 1) / TX) * ((H + TY - 1) / TY), B);
-    if (K == 9) emu::launch(grid, dim3(TP, DY), smem, [&] { adaptive_eval2_kernel<9>(p, L); });
-    else if (K == 17) emu::launch(grid, dim3(TP, DY), smem, [&] { adaptive_eval2_kernel<17>(p, L); });
-    else return -2;
-    return 0;
-}
-
 // K-C.  Same arguments as pmb200_init_propagate; the kernel is picked by hypothesis count exactly as the launcher does.
 int emu_init_propagate(const float *seed_map, const float *offsets, int offsets_channels_last, const float *depth_min,
                        const float *depth_max, float *out, float *xnorm_out, int xnorm_stride, int mode, int B, int H, int W, int Ns,

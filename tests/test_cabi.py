@@ -33,6 +33,25 @@ def test_header_symbols_are_all_exported(lib):
     assert set(names) == set(_native.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
 
 
+def declared_parameter_counts():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    counts = {}
+    for name, params in re.findall(r"\b(pmb200_[a-z_0-9]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        params = params.strip()
+        counts[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return counts
+
+
+def test_ctypes_signatures_have_the_headers_parameter_counts():
+    """A binding with one argument too many only fails when the entry point is first CALLED -- on the GPU box (round 2, run
+    3 lost a GPU call to exactly that).  The declaration in the header is the contract: same number of parameters."""
+    counts = declared_parameter_counts()
+    assert set(counts) == set(_native._SIGNATURES)
+    for name, (_res, args) in _native._SIGNATURES.items():
+        assert len(args) == counts[name], f"{name}: ctypes binding has {len(args)} parameters, the header declares {counts[name]}"
+
+
 def test_library_is_sm100a_only():
     import subprocess
 

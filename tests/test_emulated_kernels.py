@@ -38,8 +38,6 @@ def emu():
     lib.emu_warp_corr4.restype = I
     lib.emu_adaptive_eval.argtypes = [P] * 5 + [I] + [P] * 5 + [I] * 6 + [ctypes.c_float, I, I, I]
     lib.emu_adaptive_eval.restype = I
-    lib.emu_adaptive_eval2.argtypes = [P, P, P, I, P, P, P, P, P] + [I] * 6 + [ctypes.c_float] + [I] * 6
-    lib.emu_adaptive_eval2.restype = I
     lib.emu_init_propagate.argtypes = [P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, ctypes.c_float]
     lib.emu_init_propagate.restype = I
     lib.emu_offset_corr.argtypes = [P, P, I, ctypes.POINTER(_native.MlpStruct), P] + [I] * 7
@@ -330,18 +328,6 @@ def test_emulated_adaptive_eval_matches_oracle(emu, D, K, dil, H, W, B, inverse,
         assert maxabs(prob, want_prob) <= 5e-6
         assert pm_cases.rel_l1(dep, want_depth) <= 1e-6
         assert maxabs(prob.sum(1), torch.ones(B, H, W)) <= 1e-5
-    # generation 2: neighbourhood staged in shared memory.  (tile, hypothesis lanes, hypotheses per chunk, slab capacity): a
-    # roomy slab; a slab smaller than most boxes (clipped -> part of the taps from global memory); chunks of one hypothesis
-    for TX, TY, DY2, DCH, cap in ((16, 4, 4, 8, 4096), (8, 4, 8, 3, 40), (8, 2, 2, 1, 150)):
-        for o, cl in ((off, 0), (off_cl, 1)):
-            prob, dep = torch.full((B, D, H, W), -1.0), torch.full((B, H, W), -1.0)
-            rc = emu.emu_adaptive_eval2(_ptr(depth), _ptr(xs), _ptr(o), cl, _ptr(fw), _ptr(dmin), _ptr(dmax), _ptr(prob), _ptr(dep),
-                                        B, D, H, W, K, dil, scale, 1 if inverse else 0, TX, TY, DY2, DCH, cap)
-            assert rc == 0
-            assert maxabs(prob, want_prob) <= 1e-5, (TX, TY, DY2, DCH, cap)
-            assert pm_cases.rel_l1(dep, want_depth) <= 1e-6
-            assert maxabs(prob.sum(1), torch.ones(B, H, W)) <= 1e-5
-
 
 MODE_RANDOM, MODE_PERTURB, MODE_PASSTHROUGH = 0, 1, 2  # patchmatchnet_b200.ops.MODE_*
 

@@ -99,9 +99,8 @@ for (n, a, k) in calls:
         desc += f" C{a[0].shape[3]} {a[0].shape[1]}x{a[0].shape[2]}"
     row = {"call": desc, "default_us": timeit(lambda: origs[n](*a, **k))}
     if n == "adaptive_eval" and os.environ.get("KB_SWEEP_EVAL", "1") == "1":
-        row["gen1"] = with_knobs(dict(kb_gen=1), lambda: origs[n](*a, **k))
-        for tx, dy in ((16, 4), (16, 2), (8, 8), (8, 4), (32, 2), (32, 1)):  # generation 2: tile width (x 4 rows), hypothesis lanes
-            row[f"gen2 TX={tx},DY={dy}"] = with_knobs(dict(kb_gen=2, kb_tp=tx, kb_dy=dy), lambda: origs[n](*a, **k))
+        for tp, dy in ((32, 8), (32, 4), (16, 16), (16, 8), (8, 32), (8, 16), (64, 4), (32, 2)):
+            row[f"TP={tp},DY={dy}"] = with_knobs(dict(kb_tp=tp, kb_dy=dy), lambda: origs[n](*a, **k))
     if n in ("warp_corr_score", "warp_corr_view_weights") and os.environ.get("KB_SWEEP_KA", "1") == "1":
         for v in ka_variants:
             if n == "warp_corr_view_weights" and "ka3_dc" in v:
