@@ -159,6 +159,18 @@ int pmb200_geometric_filter(const float *ref_depth, const float *confidence, con
                             unsigned char *photo_mask_out, unsigned char *final_mask_out, double *depth_avg_out,
                             void *stream);
 
+/* Point-cloud half of the fusion for one reference view (reference eval.py:273-296): the pixels of final_mask, in row-major
+ * order, back-projected with the averaged depth into the world frame, with their colours, written as the 15-byte vertex
+ * records of the reference's fused.ply (binary little endian: float32 x, y, z, uint8 red, green, blue).
+ *   final_mask  [H*W] bytes (0 / non-0), depth_avg [H*W] float64 (both as pmb200_geometric_filter writes them)
+ *   ref_img_hwc [H*W*3] float32 in [0,1] (the reference's read_image output)
+ *   cam25       25 doubles: inverse(ref_intrinsics) row-major (9) then inverse(ref_extrinsics) row-major (16), the float32
+ *               inverses numpy computes, widened (ops.compose_fusion_camera)
+ *   ply_body_out  capacity H*W*15 bytes; count_out: ONE int, the number of vertices written; block_scratch: ceil(H*W/256) ints
+ * All pointers are device memory.  Three launches on `stream` (count, scan, write); no host synchronisation. */
+int pmb200_fuse_points(const unsigned char *final_mask, const double *depth_avg, const float *ref_img_hwc, const double *cam25,
+                       int H, int W, unsigned char *ply_body_out, int *count_out, int *block_scratch, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Depth / confidence map files either side of the path: PFM and COLMAP .bin, read straight into /
  * written straight from caller-owned host buffers (pinned, so the next step is one cudaMemcpyAsync).  Host code, no

@@ -115,3 +115,28 @@ def fuse_reference_view(ref_depth: np.ndarray, ref_intrinsics: np.ndarray, ref_e
     geo_mask = geo_mask_sum >= geo_mask_thres
     final_mask = np.logical_and(photo_mask, geo_mask)
     return photo_mask, geo_mask_sum, final_mask, depth_est_averaged
+
+
+def fuse_points(final_mask: np.ndarray, depth_est_averaged: np.ndarray, ref_img: np.ndarray, ref_intrinsics: np.ndarray,
+                ref_extrinsics: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """The point-cloud half of filter_depth for one reference view (eval.py:273-281): the pixels of `final_mask`, in row-major
+    order, back-projected with the averaged depth into the world frame (float64 arithmetic on float32 camera inverses), and
+    their colours.  -> (vertices float64 [n,3] -- the reference casts them to float32 when it assembles the PLY array,
+    eval.py:285 -- , colours uint8 [n,3])."""
+    height, width = depth_est_averaged.shape[:2]
+    x, y = np.meshgrid(np.arange(0, width), np.arange(0, height))
+    x, y, depth = x[final_mask], y[final_mask], depth_est_averaged[final_mask]
+    color = ref_img[final_mask]
+    xyz_ref = np.matmul(np.linalg.inv(ref_intrinsics), np.vstack((x, y, np.ones_like(x))) * depth)
+    xyz_world = np.matmul(np.linalg.inv(ref_extrinsics), np.vstack((xyz_ref, np.ones_like(x))))[:3]
+    return xyz_world.transpose((1, 0)), (color * 255).astype(np.uint8)
+
+
+def ply_vertex_body(vertices: np.ndarray, colors: np.ndarray) -> bytes:
+    """The binary little-endian body of the reference's fused.ply (eval.py:283-296): per vertex float32 x, y, z and uint8
+    red, green, blue = 15 bytes, in order."""
+    rec = np.empty(len(vertices), dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+    v = np.asarray(vertices)
+    rec["x"], rec["y"], rec["z"] = v[:, 0].astype(np.float32), v[:, 1].astype(np.float32), v[:, 2].astype(np.float32)
+    rec["red"], rec["green"], rec["blue"] = colors[:, 0], colors[:, 1], colors[:, 2]
+    return rec.tobytes()

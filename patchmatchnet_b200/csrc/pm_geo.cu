@@ -51,7 +51,86 @@ __global__ void __launch_bounds__(256) geometric_filter_kernel(const GeoParams p
     p.depth_avg[n] = r.depth_avg;
 }
 
+// ---- fusion half (reference eval.py:273-296): masked back-projection + colour gather + ORDER-PRESERVING compaction ----------
+// Three small launches: per-block survivor counts, one-block exclusive scan of the counts, write.  A survivor's position is
+// scan[block] + (survivors before it in the block), so the records come out in row-major pixel order exactly as the
+// reference's boolean indexing produces them; each record is the 15-byte PLY vertex (float32 x, y, z, uint8 r, g, b).
+constexpr int kFuseBlock = 256;
+
+__global__ void __launch_bounds__(kFuseBlock) fuse_count_kernel(const unsigned char *mask, int n, int *counts) {
+    const int i = blockIdx.x * kFuseBlock + threadIdx.x;
+    const int c = __syncthreads_count(i < n && mask[i] != 0);
+    if (threadIdx.x == 0) counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024) fuse_scan_kernel(int *counts, int nblocks, int *total) {  // in place: exclusive scan
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? counts[i] : 0;
+        int x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) >= off) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, off);
+                if (threadIdx.x >= off) w += y;
+            }
+            s_warp[threadIdx.x] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int before_warp = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+        const int carry = s_carry;
+        if (i < nblocks) counts[i] = carry + before_warp + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + before_warp + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(kFuseBlock) fuse_write_kernel(const unsigned char *mask, const double *depth_avg, const float *rgb,
+                                                                const double *cam, int W, int n, const int *offsets,
+                                                                unsigned char *body) {
+    __shared__ int s_warp[kFuseBlock / 32];
+    __shared__ double s_cam[pmgeo::kFuseCamDoubles];
+    if (threadIdx.x < pmgeo::kFuseCamDoubles) s_cam[threadIdx.x] = cam[threadIdx.x];
+    const int i = blockIdx.x * kFuseBlock + threadIdx.x;
+    const bool keep = i < n && mask[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (!keep) return;
+    const int rank = offsets[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
+    pmgeo::fuse_point(s_cam, i % W, i / W, depth_avg[i], rgb + (size_t)i * 3, body + (size_t)rank * pmgeo::kPlyVertexBytes);
+}
+
 }  // namespace
+
+extern "C" int pmb200_fuse_points(const unsigned char *final_mask, const double *depth_avg, const float *ref_img_hwc,
+                                  const double *cam25, int H, int W, unsigned char *ply_body_out, int *count_out,
+                                  int *block_scratch, void *stream) {
+    if (!final_mask || !depth_avg || !ref_img_hwc || !cam25 || !ply_body_out || !count_out || !block_scratch)
+        return pmb200_internal_fail(PMB200_EINVAL, "fuse_points: null pointer");
+    if (H < 1 || W < 1 || (long long)H * W >= (1ll << 31)) return pmb200_internal_fail(PMB200_EINVAL, "fuse_points: bad size");
+    const int n = H * W, nblocks = (n + kFuseBlock - 1) / kFuseBlock;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    fuse_count_kernel<<<nblocks, kFuseBlock, 0, st>>>(final_mask, n, block_scratch);
+    fuse_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nblocks, count_out);
+    fuse_write_kernel<<<nblocks, kFuseBlock, 0, st>>>(final_mask, depth_avg, ref_img_hwc, cam25, W, n, block_scratch, ply_body_out);
+    return pmb200_internal_launch_status("fuse_points");
+}
 
 extern "C" int pmb200_geometric_filter(const float *ref_depth, const float *confidence, const float *src_depths,
                                        const double *cams, int V, int H, int W, int Hs, int Ws, double geo_pixel_thres,

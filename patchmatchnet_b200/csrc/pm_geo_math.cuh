@@ -130,4 +130,27 @@ PMG_HD PixelResult filter_pixel(const double *cams, const float *src_depths, int
     return r;
 }
 
+// One fused point (reference eval.py:273-281).  cam: Kref^-1 (9, row-major) | Eref^-1 (16): float32 inverses widened to double,
+// composed on the host the way numpy composes them (ops.compose_fusion_camera).  The reference multiplies (x, y, 1) by the
+// float64 averaged depth first, then applies the two matrices in float64 (BLAS: one fused multiply-add chain per output, k
+// ascending); the result is cast to float32 when the PLY array is assembled.  Colour: float32 image value * 255 in float32,
+// truncated to uint8.
+constexpr int kFuseCamDoubles = 25;
+constexpr int kPlyVertexBytes = 15;
+
+PMG_HD void fuse_point(const double *cam, int x, int y, double depth, const float *rgb, unsigned char *rec) {
+    const double px = (double)x * depth, py = (double)y * depth, pz = depth;
+    const double *K = cam, *E = cam + 9;
+    const double rx = fma(K[2], pz, fma(K[1], py, K[0] * px));
+    const double ry = fma(K[5], pz, fma(K[4], py, K[3] * px));
+    const double rz = fma(K[8], pz, fma(K[7], py, K[6] * px));
+    float out[3];
+    out[0] = (float)fma(E[3], 1.0, fma(E[2], rz, fma(E[1], ry, E[0] * rx)));
+    out[1] = (float)fma(E[7], 1.0, fma(E[6], rz, fma(E[5], ry, E[4] * rx)));
+    out[2] = (float)fma(E[11], 1.0, fma(E[10], rz, fma(E[9], ry, E[8] * rx)));
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(out);
+    for (int i = 0; i < 12; ++i) rec[i] = b[i];
+    for (int c = 0; c < 3; ++c) rec[12 + c] = (unsigned char)mul32(load32(rgb + c), 255.0f);
+}
+
 }  // namespace pmgeo

@@ -166,3 +166,23 @@ def save_map_from_device(path: str, tensor: torch.Tensor, scale: float = 1) -> N
     rc = _native.lib().pmb200_map_write(os.fsencode(path), fmt, host.data_ptr(), h, w, c, -float(-scale) if fmt == PFM else 1.0)
     if rc != 0:
         _raise(rc)
+
+
+def save_ply(path: str, body) -> None:
+    """Write the reference's fused.ply (eval.py:283-296: PlyData([PlyElement.describe(vertex_all, "vertex")]).write -- binary
+    little endian, one `vertex` element with float x, y, z and uchar red, green, blue) from vertex records produced by
+    ops.fuse_points: uint8 [n,15] tensor(s) (a list concatenates the per-reference-view clouds, eval.py:283-284)."""
+    import torch
+
+    parts = list(body) if isinstance(body, (list, tuple)) else [body]
+    parts = [b.detach().cpu().contiguous() for b in parts]
+    for b in parts:
+        if b.dtype != torch.uint8 or b.dim() != 2 or b.shape[1] != 15:
+            raise ValueError("save_ply: vertex records must be uint8 [n,15] tensors (ops.fuse_points)")
+    n = sum(int(b.shape[0]) for b in parts)
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+              "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n" % n)
+    with open(path, "wb") as f:
+        f.write(header.encode("ascii"))
+        for b in parts:
+            f.write(b.numpy().tobytes())

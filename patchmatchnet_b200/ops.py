@@ -681,3 +681,44 @@ def geometric_filter(ref_depth: Tensor, confidence: Tensor, src_depths: Tensor, 
         )
     _native.check(rc, "geometric_filter")
     return photo.bool(), mask_sum, final.bool(), avg
+
+
+def compose_fusion_camera(ref_K, ref_E) -> Tensor:
+    """[25] float64 (CPU): inverse(ref_intrinsics) (9) then inverse(ref_extrinsics) (16), inverted in float32 as numpy does
+    on the reference's float32 camera files (eval.py:278-279) and then widened without rounding."""
+    import numpy as np
+
+    f32 = lambda m: np.asarray(m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else m, dtype=np.float32)
+    return torch.from_numpy(np.concatenate([np.linalg.inv(f32(ref_K)).ravel(), np.linalg.inv(f32(ref_E)).ravel()]).astype(np.float64))
+
+
+def fuse_points(final_mask: Tensor, depth_averaged: Tensor, ref_img: Tensor, cam25: Tensor) -> Tensor:
+    """Point-cloud half of the fusion for one reference view (reference eval.py:273-296): -> uint8 [n,15] CUDA tensor, the
+    binary little-endian PLY vertex records (float32 x, y, z, uint8 r, g, b) of the surviving pixels in row-major order.
+    final_mask bool / uint8 [H,W], depth_averaged float64 [H,W] (as geometric_filter returns them), ref_img float32
+    [H,W,3] in [0,1].  One host synchronisation at the end (the vertex count sizes the result)."""
+    if not _on_device(final_mask) or not _on_device(depth_averaged) or not _on_device(ref_img):
+        raise RuntimeError("fuse_points: the B200 path needs CUDA tensors; there is no CPU fallback")
+    H, W = depth_averaged.shape
+    if depth_averaged.dtype != torch.float64 or tuple(final_mask.shape) != (H, W) or tuple(ref_img.shape) != (H, W, 3) or ref_img.dtype != torch.float32:
+        raise RuntimeError("fuse_points: final_mask [H,W], depth_averaged float64 [H,W], ref_img float32 [H,W,3]")
+    if cam25.shape != (25,) or cam25.dtype != torch.float64:
+        raise RuntimeError("fuse_points: cam25 must be a [25] float64 tensor (compose_fusion_camera)")
+    mask = final_mask.to(torch.uint8).contiguous()
+    depth = depth_averaged.contiguous()
+    img = ref_img.contiguous()
+    cam = cam25.to(depth.device).contiguous()
+    body = torch.empty((H * W, 15), dtype=torch.uint8, device=depth.device)
+    count = torch.zeros(1, dtype=torch.int32, device=depth.device)
+    scratch = torch.empty(((H * W + 255) // 256,), dtype=torch.int32, device=depth.device)
+    with _device_guard(depth):
+        rc = _native.lib().pmb200_fuse_points(mask.data_ptr(), depth.data_ptr(), img.data_ptr(), cam.data_ptr(), H, W, body.data_ptr(),
+                                              count.data_ptr(), scratch.data_ptr(), _stream(depth))
+    _native.check(rc, "fuse_points")
+    return body[: int(count.item())]
+
+
+def split_ply_body(body: Tensor):
+    """uint8 [n,15] vertex records -> (vertices float32 [n,3], colours uint8 [n,3]) on the CPU."""
+    b = body.detach().cpu().contiguous()
+    return b[:, :12].contiguous().view(torch.float32).view(-1, 3), b[:, 12:].contiguous()

@@ -80,6 +80,15 @@ void hm_geometric_filter(const float *ref_depth, const float *confidence, const 
     }
 }
 
+// fusion half: the kernel's per-pixel function applied to the surviving pixels in row-major order; returns the count
+int hm_fuse_points(const unsigned char *mask, const double *depth_avg, const float *rgb, const double *cam25, int H, int W,
+                   unsigned char *body) {
+    int n = 0;
+    for (int i = 0; i < H * W; ++i)
+        if (mask[i]) pmgeo::fuse_point(cam25, i % W, i / W, depth_avg[i], rgb + (size_t)i * 3, body + (size_t)(n++) * pmgeo::kPlyVertexBytes);
+    return n;
+}
+
 void hm_remap_linear(const float *src, int rows, int cols, const float *mx, const float *my, int n, float *out) {
     for (int i = 0; i < n; ++i) out[i] = pmgeo::remap_linear(src, rows, cols, mx[i], my[i]);
 }

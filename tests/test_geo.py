@@ -6,6 +6,7 @@ GPU (-m gpu): the one-launch kernel, through the C ABI, against the oracle and t
 quantities: a pixel whose distance / relative depth difference lies within rounding of its threshold may legitimately flip
 (the kernel's float64 dot products are fused multiply-adds, BLAS's are not), so the bound is a fraction of pixels:
 <= 1e-4 of the pixels per mask, and the averaged depth must agree to 1e-6 relative wherever the masks agree."""
+import ctypes
 import os
 from typing import Tuple
 
@@ -203,3 +204,103 @@ def test_gpu_filter_matches_the_oracle(H, W, n_src, seed):
     got[3][~np.isfinite(want[3])] = 1.0
     w3 = np.where(np.isfinite(want[3]), want[3], 1.0)
     _compare(got, (want[0], want[1], want[2], w3))
+
+
+# ------------------------------------------------------------------------------------------------
+# fusion half (reference eval.py:273-296): masked back-projection, colours, order-preserving compaction, PLY body
+# ------------------------------------------------------------------------------------------------
+
+
+def _fusion_case(H, W, n_src, seed):
+    sc, (photo, msum, final, avg) = _oracle_case(H, W, n_src, seed)
+    rng = np.random.default_rng(seed + 100)
+    img = (rng.integers(0, 256, size=(H, W, 3)).astype(np.float32) / np.float32(255.0)).astype(np.float32)  # read_image: uint8 / 255
+    if n_src < 3:  # fewer source views than geo_mask_thres: nothing would survive -- keep the photometric mask instead
+        final = photo
+    final = np.logical_and(final, np.isfinite(avg))
+    return sc, final, np.where(np.isfinite(avg), avg, 0.0), img
+
+
+def test_fusion_oracle_is_bit_identical_to_the_reference_source():
+    path = "/root/reference/eval.py"
+    if not os.path.exists(path):
+        pytest.skip("/root/reference not present (GPU box)")
+    src = open(path).read().split("\n")
+    snippet = "\n".join(line[8:] for line in src[272:281])  # eval.py:273-281, the body of filter_depth's loop, de-indented
+    assert snippet.lstrip().startswith("height, width = depth_est_averaged.shape[:2]") and "vertex_colors.append" in snippet
+    sc, final, avg, img = _fusion_case(72, 100, 3, 3)
+    ns = dict(np=np, depth_est_averaged=avg, final_mask=final, ref_img=img, ref_intrinsics=sc["ref_K"], ref_extrinsics=sc["ref_E"],
+              vertices=[], vertex_colors=[])
+    exec(snippet, ns)
+    v, c = go.fuse_points(final, avg, img, sc["ref_K"], sc["ref_E"])
+    assert 100 < len(v) < final.size and np.array_equal(ns["vertices"][0], v) and np.array_equal(ns["vertex_colors"][0], c)
+
+
+def _check_body(body, want_v, want_c):
+    """records against the oracle: colours exact; coordinates equal after the cast to float32 up to one float32 ulp on a
+    small share of the values (the kernel's fused multiply-add chain vs BLAS's summation of the same four products)"""
+    body = np.asarray(body, dtype=np.uint8).reshape(-1, 15)
+    assert body.shape[0] == want_v.shape[0]
+    got_v = body[:, :12].copy().view(np.float32).reshape(-1, 3)
+    assert np.array_equal(body[:, 12:], want_c)
+    if body.shape[0] == 0:
+        return
+    w32 = want_v.astype(np.float32)
+    diff = got_v != w32
+    assert diff.mean() <= 0.02, diff.mean()
+    assert np.all(np.abs(got_v - w32) <= np.spacing(np.abs(w32)))
+
+
+def test_kernel_fusion_function_matches_the_oracle(hostmath):
+    for (H, W, n_src, seed) in ((72, 100, 3, 3), (33, 47, 1, 5)):
+        sc, final, avg, img = _fusion_case(H, W, n_src, seed)
+        want_v, want_c = go.fuse_points(final, avg, img, sc["ref_K"], sc["ref_E"])
+        from patchmatchnet_b200 import ops
+
+        cam = ops.compose_fusion_camera(sc["ref_K"], sc["ref_E"]).numpy()
+        body = np.zeros((H * W, 15), dtype=np.uint8)
+        mask8 = final.astype(np.uint8)
+        P = ctypes.c_void_p
+        hostmath.hm_fuse_points.argtypes = [P, P, P, P, ctypes.c_int, ctypes.c_int, P]
+        n = hostmath.hm_fuse_points(mask8.ctypes.data, np.ascontiguousarray(avg).ctypes.data, img.ctypes.data, cam.ctypes.data, H, W, body.ctypes.data)
+        assert n == int(final.sum())
+        _check_body(body[:n], want_v, want_c)
+        assert bytes(body[:n].tobytes())[12:15] == go.ply_vertex_body(want_v, want_c)[12:15]
+
+
+def test_save_ply_layout(tmp_path):
+    from patchmatchnet_b200 import data_io
+
+    v = np.array([[1.5, -2.0, 3.25], [0.0, 1e-3, 7.0]])
+    c = np.array([[255, 0, 7], [1, 2, 3]], dtype=np.uint8)
+    body = torch.from_numpy(np.frombuffer(go.ply_vertex_body(v, c), dtype=np.uint8).reshape(-1, 15).copy())
+    path = str(tmp_path / "fused.ply")
+    data_io.save_ply(path, [body[:1], body[1:]])
+    raw = open(path, "rb").read()
+    head, _, rest = raw.partition(b"end_header\n")
+    assert head.startswith(b"ply\nformat binary_little_endian 1.0\nelement vertex 2\nproperty float x\n") and b"property uchar blue\n" in head
+    assert rest == go.ply_vertex_body(v, c) and len(rest) == 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,n_src,seed", [(72, 100, 3, 3), (33, 47, 1, 5), (512, 640, 4, 7)])
+def test_gpu_fusion_matches_the_oracle(H, W, n_src, seed):
+    from patchmatchnet_b200 import ops
+
+    dev = "cuda:0"
+    sc, final, avg, img = _fusion_case(H, W, n_src, seed)
+    want_v, want_c = go.fuse_points(final, avg, img, sc["ref_K"], sc["ref_E"])
+    body = ops.fuse_points(torch.from_numpy(final).to(dev), torch.from_numpy(avg).to(dev), torch.from_numpy(img).to(dev),
+                           ops.compose_fusion_camera(sc["ref_K"], sc["ref_E"]))
+    assert body.shape == (int(final.sum()), 15)
+    _check_body(body.cpu().numpy(), want_v, want_c)
+    v32, c8 = ops.split_ply_body(body)
+    assert v32.shape == (body.shape[0], 3) and c8.dtype == torch.uint8
+    # nothing survives / everything survives
+    none = ops.fuse_points(torch.zeros(H, W, dtype=torch.bool, device=dev), torch.from_numpy(avg).to(dev), torch.from_numpy(img).to(dev),
+                           ops.compose_fusion_camera(sc["ref_K"], sc["ref_E"]))
+    assert none.shape == (0, 15)
+    every = ops.fuse_points(torch.ones(H, W, dtype=torch.bool, device=dev), torch.from_numpy(avg).to(dev), torch.from_numpy(img).to(dev),
+                            ops.compose_fusion_camera(sc["ref_K"], sc["ref_E"]))
+    wv, wc = go.fuse_points(np.ones((H, W), dtype=bool), avg, img, sc["ref_K"], sc["ref_E"])
+    _check_body(every.cpu().numpy(), wv, wc)
