@@ -16,7 +16,9 @@
 //     A_lo.W_hi, A_hi.W_lo, A_hi.W_hi into the same fp32 TMEM accumulator: >= 21 bits of every product.
 //   * Epilogue: tcgen05.ld (32 lanes x 32 bit, 16 columns at a time) -> bias, ReLU -> channels-last stores (channel slice
 //     of a wider tensor allowed).
-// Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = split + epilogue.
+// Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = 3xTF32 split,
+// warps 6..9 = epilogue.  Two accumulators in TMEM: the epilogue of tile i drains one while the MMAs of tile i+1 fill the
+// other (run 3 measured the single-accumulator version, whose split warps also ran the epilogue, at 1.5 us per filter tap).
 // Persistent CTAs walk tiles blockIdx.x, +gridDim.x, ...; an S-deep ring of (A, A_lo, W_hi, W_lo) stages decouples the roles;
 // every mbarrier wait is bounded (a pipeline bug traps instead of hanging the GPU).
 #include <cuda.h>
@@ -33,7 +35,7 @@ extern "C" int pmb200_internal_launch_status(const char *what);
 namespace {
 
 constexpr int kTW = 16, kTH = 8;  // output tile: 128 pixels = the M of one UMMA
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
 
 struct Conv5Params {
     const float *wpack;  // [tap][hi|lo][kblock][Npad rows][RB bytes], swizzled image
@@ -129,9 +131,9 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);  // [stages]  TMA landed
     uint64_t *split = full + 8;                            // [stages]  A_hi / A_lo written
     uint64_t *empty = split + 8;                           // [stages]  MMAs that read the stage have completed
-    uint64_t *acc_full = empty + 8;                        // tile accumulated
-    uint64_t *acc_empty = acc_full + 1;                    // epilogue has read the accumulator
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
+    uint64_t *acc_full = empty + 8;                        // [2] tile accumulated in TMEM buffer a
+    uint64_t *acc_empty = acc_full + 2;                    // [2] the epilogue has read buffer a
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
     unsigned char *stage0 = smem + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,8 +143,10 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
             mbar_init(&split[s], 4);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: Npad fp32 columns x 128 lanes
@@ -182,12 +186,14 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
         }
     } else if (warp == 1) {
         // ------------------------------------------------- MMA issuer -------------------------------------------------
-        int s = 0;
-        uint32_t par = 0, acc_par = 0;
+        int s = 0, it = 0;
+        uint32_t par = 0;
         const int kslices = p.Cin / 8;
         const int per_row = p.RB / 32;  // 8-channel slices per operand row
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            mbar_wait(acc_empty, acc_par ^ 1u);  // the epilogue of the previous tile has drained the accumulator
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;                                  // accumulator buffer of this tile
+            const uint32_t tacc = tmem + (uint32_t)(ab * p.Npad);
+            mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);  // the epilogue of tile it-2 has drained this buffer
             tc_fence_after();
             for (int t = 0; t < T; ++t) {
                 mbar_wait(&split[s], par);
@@ -200,25 +206,22 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
                         const uint32_t ao = kb * 128 * p.RB + kin, wo = kb * p.Npad * p.RB + kin;
                         const uint64_t dah = make_desc(a_hi + ao, p.RB, p.layout_type), dal = make_desc(a_lo + ao, p.RB, p.layout_type);
                         const uint64_t dwh = make_desc(w_hi + wo, p.RB, p.layout_type), dwl = make_desc(w_lo + wo, p.RB, p.layout_type);
-                        tc_mma_tf32(tmem, dal, dwh, p.idesc, (t | k) != 0);  // small terms first
-                        tc_mma_tf32(tmem, dah, dwl, p.idesc, 1);
-                        tc_mma_tf32(tmem, dah, dwh, p.idesc, 1);
+                        tc_mma_tf32(tacc, dal, dwh, p.idesc, (t | k) != 0);  // small terms first
+                        tc_mma_tf32(tacc, dah, dwl, p.idesc, 1);
+                        tc_mma_tf32(tacc, dah, dwh, p.idesc, 1);
                     }
-                    tc_commit(&empty[s]);                    // stage free once these MMAs have read it
-                    if (t == T - 1) tc_commit(acc_full);     // accumulator complete
+                    tc_commit(&empty[s]);                        // stage free once these MMAs have read it
+                    if (t == T - 1) tc_commit(&acc_full[ab]);    // accumulator complete
                 }
                 __syncwarp();
                 if (++s == p.stages) { s = 0; par ^= 1u; }
             }
-            acc_par ^= 1u;
         }
-    } else {
-        // ------------------------------------------- split (3xTF32) + epilogue -------------------------------------------
-        const int wt = threadIdx.x - 64;     // 0..127: operand row handled in the split, accumulator lane in the epilogue
-        const int quad = warp & 3;           // TMEM lane quadrant this warp may read: lanes 32*quad .. 32*quad+31
-        const int row = quad * 32 + lane;    // accumulator row = pixel of the tile
+    } else if (warp < 6) {
+        // ------------------------------------------------ 3xTF32 split ------------------------------------------------
+        const int wt = threadIdx.x - 64;     // 0..127: operand row handled by this thread
         int s = 0;
-        uint32_t par = 0, acc_par = 0;
+        uint32_t par = 0;
         const int chunks = p.RB / 16;        // 16-byte chunks per operand row of one K block
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             for (int t = 0; t < T; ++t) {
@@ -244,22 +247,29 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
                 if (lane == 0) mbar_arrive(&split[s]);
                 if (++s == p.stages) { s = 0; par ^= 1u; }
             }
-            // ---- epilogue of this tile ----
-            mbar_wait(acc_full, acc_par);
+        }
+    } else {
+        // -------------------------------------------------- epilogue --------------------------------------------------
+        const int quad = warp & 3;           // TMEM lane quadrant this warp may read: lanes 32*quad .. 32*quad+31
+        const int row = quad * 32 + lane;    // accumulator row = pixel of the tile
+        const bool vec4 = ((p.ycs | p.yco) & 3) == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            mbar_wait(&acc_full[ab], ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
             const int n = tile / per_img, tt = tile - n * per_img;
             const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
             const int oy = ty * kTH + row / kTW, ox = tx * kTW + row % kTW;
             const bool inside = oy < p.Ho && ox < p.Wo;
             float *dst = p.y + (((size_t)n * p.Ho + (inside ? oy : 0)) * p.Wo + (inside ? ox : 0)) * p.ycs + p.yco;
-            const bool vec4 = ((p.ycs | p.yco) & 3) == 0;
             for (int c0 = 0; c0 < p.Npad; c0 += 16) {
                 float v[16];
-                tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * p.Npad + c0), v);
                 if (c0 + 16 >= p.Npad) {  // last read of the accumulator: hand it back before the stores
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
+                    if (lane == 0) mbar_arrive(&acc_empty[ab]);
                 }
                 if (!inside) continue;
 #pragma unroll
@@ -280,7 +290,6 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
                     }
                 }
             }
-            acc_par ^= 1u;
         }
     }
     __syncthreads();
@@ -352,7 +361,7 @@ int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float 
     p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
     p.layout_type = p.RB == 128 ? 2u : (p.RB == 64 ? 4u : 6u);
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);  // F32 += TF32 . TF32, K-major both
-    p.tmem_cols = p.Npad <= 32 ? 32u : 64u;
+    p.tmem_cols = 2 * p.Npad <= 32 ? 32u : (2 * p.Npad <= 64 ? 64u : 128u);  // two accumulators of Npad fp32 columns
 
     int dev = 0, sms = 0, smem_optin = 0;
     cudaGetDevice(&dev);
