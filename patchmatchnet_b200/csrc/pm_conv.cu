@@ -454,163 +454,6 @@ __global__ void __launch_bounds__(128 * NSPLIT) conv_nhwc_mma_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// Transposed-operand form (opt-in: PMB200_CONV_T=1 for the layers with 16 / 32 output channels, =2 for every supported
-// layer; not a default until it has been timed).
-//
-// The kernel above makes the 16 PIXELS the MMA's M dimension, so a lane's two 64-bit shared loads deliver (a0,a2) and
-// (a1,a3) and ~3.75 register moves per MMA re-order them into the operand the tensor core wants (tools/sass_lines.py: 135
-// moves for 36 HMMAs in the 8-channel kernel).  Computing D^T = W^T . X^T instead makes the activations the B operand:
-// b0 = (k slot t, pixel g), b1 = (k slot t+4, pixel g) are the ADJACENT channels 2t, 2t+1 of ONE pixel -- one 64-bit load,
-// already in operand order -- and the weights the A operand (16 output channels x 8 k), read from the same fragment-ordered
-// filter buffer: n-tile 2j gives (a0,a2), n-tile 2j+1 gives (a1,a3), interleaved once per (tap, k-slice) and reused by every
-// row and both 8-pixel halves of the warp's tile.  D: c0 (cout g, pixel 2t), c1 (cout g, pixel 2t+1), c2 / c3 cout g+8.
-// With Cout = 8 half of every MMA is padding (twice the MMAs of the form above, on a tensor pipe that runs at 16-20 %).
-// Same staging, same shared-memory layout and bank behaviour (the B loads are exactly the `lo` / `hi` loads above), same
-// launch plan.  No fused upsample-add, one warp group, Cin <= 32, Cout <= 32.
-// ------------------------------------------------------------------------------------------------------------------------
-template <int KCIN, int MTL, int MT, int PREC>
-__global__ void __launch_bounds__(128) conv_nhwc_mmat_kernel(const __grid_constant__ ConvParams p) {
-#if defined(PM_EMU)
-    float *s_in = static_cast<float *>(emu::dyn_smem());
-#else
-    extern __shared__ __align__(16) float s_in[];
-#endif
-    constexpr int KK = KCIN / 8;
-    constexpr int ROWS = 4 * MT;
-    constexpr int THREADS = 128;
-    const int warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-
-    for (int i = threadIdx.x; i < p.nbuf * p.buf_floats / 4; i += THREADS) reinterpret_cast<float4 *>(s_in)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-
-    int tile = blockIdx.x;
-    if (p.nbuf == 2) {
-        if (tile < p.total_tiles) stage_any<THREADS>(p, tile, s_in, ROWS);
-        cp_async_commit();
-    }
-
-    // this lane's two output channels (g, g+8) of every 16-channel tile and their bias
-    float bi0[MTL], bi1[MTL];
-#pragma unroll
-    for (int j = 0; j < MTL; ++j) {
-        const int co = j * 16 + g;
-        bi0[j] = (p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
-        bi1[j] = (p.bias && co + 8 < p.Cout) ? __ldg(p.bias + co + 8) : 0.f;
-    }
-    const int brow = g * p.S * p.ps + 2 * t;  // lane part of the B-fragment address: channels 2t, 2t+1 of pixel g
-    const int bstep8 = 8 * p.S * p.ps;        // the second 8-pixel half of the tile row
-    const int per_img = p.tiles_x * p.tiles_y;
-    using Frag = typename std::conditional<PREC == 1, float2, float4>::type;
-    const int wstep = p.nt_total * 32;        // fragments of one (tap, k-slice)
-
-    for (int it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const float *cur = s_in;
-        if (p.nbuf == 2) {
-            cur = s_in + (size_t)(it & 1) * p.buf_floats;
-            const int next = tile + gridDim.x;
-            if (next < p.total_tiles) stage_any<THREADS>(p, next, s_in + (size_t)((it + 1) & 1) * p.buf_floats, ROWS);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            stage_any<THREADS>(p, tile, s_in, ROWS);
-            cp_async_commit();
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-
-        float acc[MT][MTL][2][4];
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-#pragma unroll
-            for (int j = 0; j < MTL; ++j)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[m][j][h][i] = 0.f;
-
-        const float *bbase = cur + (warp * MT * p.S) * p.rw * p.ps + brow;
-        const Frag *wp = reinterpret_cast<const Frag *>(p.wf) + lane;
-#pragma unroll 1
-        for (int ky = 0; ky < p.KS; ++ky) {
-#pragma unroll 1
-            for (int kx = 0; kx < p.KS; ++kx) {
-                const float *btap = bbase + (ky * p.dil * p.rw + kx * p.dil) * p.ps;
-#pragma unroll
-                for (int kk = 0; kk < KK; ++kk, wp += wstep) {
-                    uint32_t ah[MTL][4], al[MTL][4];
-#pragma unroll
-                    for (int j = 0; j < MTL; ++j) {
-                        const bool second = 2 * j + 1 < p.nt_total;  // output channels 16j+8 .. 16j+15 exist
-                        if constexpr (PREC == 1) {
-                            const float2 f0 = __ldg(wp + (2 * j) * 32);
-                            const float2 f1 = second ? __ldg(wp + (2 * j + 1) * 32) : make_float2(0.f, 0.f);
-                            ah[j][0] = __float_as_uint(f0.x); ah[j][1] = __float_as_uint(f1.x);
-                            ah[j][2] = __float_as_uint(f0.y); ah[j][3] = __float_as_uint(f1.y);
-                            al[j][0] = al[j][1] = al[j][2] = al[j][3] = 0u;
-                        } else {
-                            const float4 f0 = __ldg(wp + (2 * j) * 32);
-                            const float4 f1 = second ? __ldg(wp + (2 * j + 1) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            ah[j][0] = __float_as_uint(f0.x); ah[j][1] = __float_as_uint(f1.x);
-                            ah[j][2] = __float_as_uint(f0.y); ah[j][3] = __float_as_uint(f1.y);
-                            al[j][0] = __float_as_uint(f0.z); al[j][1] = __float_as_uint(f1.z);
-                            al[j][2] = __float_as_uint(f0.w); al[j][3] = __float_as_uint(f1.w);
-                        }
-                    }
-#pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float2 b = *reinterpret_cast<const float2 *>(btap + m * p.S * p.rw * p.ps + h * bstep8 + kk * 8);
-                            if constexpr (PREC == 1) {  // the tensor core ignores the low 13 mantissa bits
-                                const uint32_t b0 = __float_as_uint(b.x), b1 = __float_as_uint(b.y);
-#pragma unroll
-                                for (int j = 0; j < MTL; ++j) mma_tf32(acc[m][j][h], ah[j], b0, b1);
-                            } else {
-                                const uint32_t bh0 = split_hi(b.x), bh1 = split_hi(b.y);
-                                const uint32_t bl0 = __float_as_uint(b.x - __uint_as_float(bh0)), bl1 = __float_as_uint(b.y - __uint_as_float(bh1));
-#pragma unroll
-                                for (int j = 0; j < MTL; ++j) {  // small terms first
-                                    mma_tf32(acc[m][j][h], al[j], bh0, bh1);
-                                    mma_tf32(acc[m][j][h], ah[j], bl0, bl1);
-                                    mma_tf32(acc[m][j][h], ah[j], bh0, bh1);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-
-        // ---- epilogue: bias, ReLU, channels-last store (c0,c1: cout g, pixels 2t, 2t+1; c2,c3: cout g+8) ----
-        const int n = tile / per_img, tt = tile - n * per_img;
-        const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
-        const int ox0 = tx * 16, oy0 = ty * ROWS;
-        const int oyw = oy0 + warp * MT;
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            const int oy = oyw + m;
-            if (oy >= p.Ho) continue;
-            float *const row = p.y + ((size_t)n * p.Ho + oy) * p.Wo * p.ycs + p.yco;
-#pragma unroll
-            for (int j = 0; j < MTL; ++j) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int co = j * 16 + g + (i >> 1) * 8;
-                        const int ox = ox0 + 8 * h + 2 * t + (i & 1);
-                        if (co >= p.Cout || ox >= p.Wo) continue;
-                        float v = acc[m][j][h][i] + ((i >> 1) ? bi1[j] : bi0[j]);
-                        if (p.relu) v = fmaxf(v, 0.f);
-                        row[(size_t)ox * p.ycs + co] = v;
-                    }
-                }
-            }
-        }
-        __syncthreads();  // every warp is done with `cur` before the next iteration's prefetch overwrites it
-    }
-    cp_async_wait<0>();
-}
 
 int conv_fail(int code, const char *msg) { return pmb200_internal_fail(code, msg); }
 
@@ -677,40 +520,6 @@ int launch_conv(const ConvParams &p, const LaunchPlan &plan, cudaStream_t st) {
         return pmb200_internal_fail((int)e, msg);
     }
     return 0;
-}
-
-template <int KCIN, int MTL, int MT, int PREC>
-int launch_conv_t(const ConvParams &p, const LaunchPlan &plan, cudaStream_t st) {
-    auto kern = conv_nhwc_mmat_kernel<KCIN, MTL, MT, PREC>;
-    if (plan.smem > 48 * 1024) {
-        static int granted[64] = {0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || granted[dev] < (int)plan.smem) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-            if (e != cudaSuccess) return pmb200_internal_fail((int)e, "conv2d_nhwc (transposed form): cudaFuncSetAttribute failed");
-            if (dev >= 0 && dev < 64) granted[dev] = (int)plan.smem;
-        }
-    }
-#if defined(PM_EMU)
-    (void)st;
-    emu::launch(dim3((unsigned)plan.ctas), dim3(128), plan.smem, [&] { kern(p); });
-#else
-    kern<<<(unsigned)plan.ctas, 128, plan.smem, st>>>(p);
-#endif
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return pmb200_internal_fail((int)e, "conv2d_nhwc (transposed form): launch failed");
-    return 0;
-}
-
-template <int KCIN>
-int launch_shape_t(const ConvParams &p, const LaunchPlan &plan, int mtl, int mt, int prec, cudaStream_t st) {
-#define PMB200_CT(MTLV, MTV)                                                                    \
-    if (mtl == MTLV && mt == MTV)                                                               \
-        return prec == 1 ? launch_conv_t<KCIN, MTLV, MTV, 1>(p, plan, st) : launch_conv_t<KCIN, MTLV, MTV, 3>(p, plan, st);
-    PMB200_CT(1, 1) PMB200_CT(1, 2) PMB200_CT(1, 4) PMB200_CT(2, 1) PMB200_CT(2, 2) PMB200_CT(2, 4)
-#undef PMB200_CT
-    return pmb200_internal_fail(PMB200_EINVAL, "conv2d_nhwc (transposed form): shape not instantiated");
 }
 
 template <int KCIN, int NT, int MT, int NSPLIT>
@@ -872,21 +681,6 @@ int pmb200_conv2d_nhwc(const float *x, const float *filter_frag, const float *bi
         p.step_c[i] = (128 << i) % p.row_chunks;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    {   // opt-in transposed-operand form (see conv_nhwc_mmat_kernel); same plan, same filter buffer
-        const char *e = getenv("PMB200_CONV_T");
-        // '1': layers with 16 or 32 output channels (full M tiles: 62 instead of 92 static instructions per tap and 16 MMAs
-        // at Cin = Cout = 16; with 8 output channels half of every MMA is padding and the form above is shorter: 28 vs 40);
-        // '2': every layer the kernel supports (tests)
-        const bool full_tiles = nt == 2 || nt == 4;
-        if (e && (e[0] == '2' || (e[0] == '1' && full_tiles)) && !add_up2x && nsplit == 1 && kcin <= 32 && nt <= 4) {
-            const int mtl = (nt + 1) / 2;
-            switch (kcin) {
-                case 8: return launch_shape_t<8>(p, plan, mtl, mt, precision, st);
-                case 16: return launch_shape_t<16>(p, plan, mtl, mt, precision, st);
-                default: return launch_shape_t<32>(p, plan, mtl, mt, precision, st);
-            }
-        }
-    }
     switch (kcin) {
         case 8: return launch_shape<8>(p, plan, ntw, nsplit, mt, precision, st);
         case 16: return launch_shape<16>(p, plan, ntw, nsplit, mt, precision, st);

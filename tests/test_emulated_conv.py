@@ -98,60 +98,6 @@ def test_emulated_persistent_double_buffered_path(emu_conv, name, monkeypatch):
     assert _scaled_err(got, want) <= 2e-5
 
 
-T_LAYERS = sorted(n for n, (cin, cout, *_r) in LAYERS.items() if cin <= 32 and cout <= 32)
-
-
-@pytest.mark.parametrize("name", T_LAYERS)
-def test_emulated_transposed_operand_form(emu_conv, name, monkeypatch):
-    """PMB200_CONV_T (2 = every supported layer): the activations as the MMA's B operand (one 64-bit load per fragment, no re-ordering moves), the
-    weights as its A operand read from the SAME fragment-ordered filter buffer.  Opt-in until timed; same tolerances."""
-    monkeypatch.setenv("PMB200_CONV_T", "2")
-    cin, cout, ks, S, pad, dil, relu = LAYERS[name]
-    g = torch.Generator().manual_seed(sum(map(ord, name)) + 7)
-    N, H, W = 2, 13, 21
-    x = torch.randn(N, cin, H, W, generator=g)
-    w = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
-    b = torch.randn(cout, generator=g)
-    want = _ref_conv(x, w, b, S, pad, dil, relu)
-    for prec, tol in ((3, 2e-5), (1, 3e-3)):
-        frag = ops.pack_conv_filter(w, prec)
-        for mt in ((0, 1, 2, 4) if prec == 3 else (0,)):
-            got = _run(emu_conv, x, frag, b, cout, ks, S, pad, dil, relu=relu, prec=prec, mt=mt)
-            err = _scaled_err(got, want)
-            assert err <= tol, f"{name} precision {prec} rows_per_warp {mt}: scaled max err {err:.3e}"
-    # and it differs from the standard form only by summation order: the two agree far inside the tolerance
-    monkeypatch.delenv("PMB200_CONV_T")
-    std = _run(emu_conv, x, ops.pack_conv_filter(w, 3), b, cout, ks, S, pad, dil, relu=relu, prec=3)
-    monkeypatch.setenv("PMB200_CONV_T", "2")
-    tr = _run(emu_conv, x, ops.pack_conv_filter(w, 3), b, cout, ks, S, pad, dil, relu=relu, prec=3)
-    assert _scaled_err(tr, std) <= 1e-5
-
-
-def test_emulated_transposed_operand_form_slices_stuffing_and_persistence(emu_conv, monkeypatch):
-    monkeypatch.setenv("PMB200_CONV_T", "2")
-    g = torch.Generator().manual_seed(15)
-    low = torch.randn(2, 8, 11, 19, generator=g)
-    img = torch.randn(2, 3, 22, 38, generator=g)
-    wt = torch.randn(8, 8, 3, 3, generator=g) / 8
-    bt = torch.randn(8, generator=g)
-    w0 = torch.randn(8, 3, 3, 3, generator=g) / 5
-    b0 = torch.randn(8, generator=g)
-    want = torch.cat((F.conv_transpose2d(low, wt, bt, stride=2, padding=1, output_padding=1).relu(), F.conv2d(img, w0, b0, padding=1).relu()), dim=1)
-    both = _cl(torch.full((2, 16, 22, 38), float("nan")))
-    _run(emu_conv, low, ops.pack_conv_filter(wt, 3, transposed=True), bt, 8, 3, 1, 1, 1, relu=True, transposed2x=True, out=both, yco=0)
-    assert torch.isnan(both[:, 8:]).all()
-    _run(emu_conv, img, ops.pack_conv_filter(w0, 3), b0, 8, 3, 1, 1, 1, relu=True, out=both, yco=8)
-    assert _scaled_err(both, want) <= 2e-5
-    monkeypatch.setenv("PM_EMU_SMS", "1")  # several tiles per CTA, two halo buffers
-    for name in ("feature.conv1", "feature.conv2", "feature.conv3"):
-        cin, cout, ks, S, pad, dil, relu = LAYERS[name]
-        x = torch.randn(2, cin, 29, 37, generator=g)
-        w = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
-        b = torch.randn(cout, generator=g)
-        got = _run(emu_conv, x, ops.pack_conv_filter(w, 3), b, cout, ks, S, pad, dil, relu=relu, prec=3)
-        assert _scaled_err(got, _ref_conv(x, w, b, S, pad, dil, relu)) <= 2e-5, name
-
-
 def test_emulated_transposed_conv_and_channel_slices(emu_conv):
     g = torch.Generator().manual_seed(5)
     low = torch.randn(2, 8, 11, 19, generator=g)
