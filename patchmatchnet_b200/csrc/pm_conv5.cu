@@ -298,6 +298,233 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// K-D5h: the stride-1 form.  conv5_kernel above re-reads (and re-splits) the input once per filter tap; for stride 1 every
+// tap's A operand is just a SHIFTED view of one halo tile, if that tile is stored so that a shift keeps the tensor core's
+// canonical layout intact.  The no-swizzle K-major layout does: its core matrix is 8 rows x 16 bytes stored contiguously,
+// so with the halo tile kept as channel-chunk PLANES [Cin/4][rows][cols][4 floats] (16 bytes per pixel and plane)
+//   * 8 consecutive pixels of one plane ARE a core matrix (128 contiguous bytes),
+//   * the next 8-row group of the operand = the next output row = + (halo cols * 16) bytes      (descriptor SBO),
+//   * the second half of an 8-channel K slice = the next plane = + (halo rows * cols * 16) bytes (descriptor LBO),
+//   * filter tap (ky, kx) = start address + ((ky*dil) * cols + kx*dil) * 16 bytes -- always 16-byte aligned, no swizzle phase.
+// TMA produces the planes directly: tensor map {4, W, H, Cin/4, N} (dim 3 = channel chunk, stride 16 bytes), one 5-D box
+// {4, cols, rows, Cin/4, 1} per tile, zero fill for the padding.  Output tile: 8 wide x 16 tall.  The halo tile is loaded and
+// split (A_hi / A_lo) ONCE per tile; the filter taps stream through a small ring ([chunk][Npad][4 floats] planes, hi and lo,
+// packed by ops.pack_conv_filter_tc5h).  Roles, accumulators and epilogue as conv5_kernel.
+// ----------------------------------------------------------------------------------------------------------------------
+constexpr int kHTW = 8, kHTH = 16;
+
+struct Conv5hParams {
+    const float *wpack;  // [tap][hi|lo][Cin/4 chunks][Npad][4]
+    const float *bias;
+    float *y;
+    int N, H, W, Ho, Wo, Cin, Cout, Npad, KS, pad, dil, relu, ycs, yco;
+    int tiles_x, tiles_y, total_tiles;
+    int hcols, hrows;     // halo tile: 8 + dil*(KS-1) columns, 16 + dil*(KS-1) rows
+    int plane_bytes;      // hrows * hcols * 16
+    int a_bytes;          // plane_bytes * Cin/4 (one of hi / lo): what one TMA box delivers
+    int a_stride;         // a_bytes rounded up to 128: distance hi -> lo and between halo buffers (2 * a_stride)
+    int hbufs;            // halo buffers: 2 when they fit (load + split of tile i+1 under the MMAs of tile i), else 1
+    int w_bytes;          // Npad * Cin * 4 (one of hi / lo)
+    int wstages;
+    uint32_t idesc, tmem_cols;
+};
+
+__device__ __forceinline__ void tma_box_5d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<unsigned long long>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+// no-swizzle K-major operand: core matrices of 8 rows x 16 bytes; LBO = distance of the K-adjacent core matrix, SBO = distance
+// of the next 8-row group (both in bytes)
+__device__ __forceinline__ uint64_t make_desc_plain(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout type 0 = no swizzle
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t *h_full = reinterpret_cast<uint64_t *>(smem);  // [2] halo tile landed
+    uint64_t *h_split = h_full + 2;                          // [2] A_hi / A_lo written
+    uint64_t *h_empty = h_split + 2;                         // [2] every MMA of the tile has read the halo buffer
+    uint64_t *w_full = h_empty + 2;                          // [8] filter tap landed
+    uint64_t *w_empty = w_full + 8;                          // [8] its MMAs have completed
+    uint64_t *acc_full = w_empty + 8;                        // [2]
+    uint64_t *acc_empty = acc_full + 2;                      // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    unsigned char *halo0 = smem + 256;                                      // [hbufs][hi, lo][a_stride]
+    unsigned char *wring = halo0 + (size_t)p.hbufs * 2 * p.a_stride;        // [wstages][hi, lo][w_bytes]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&h_full[a], 1);
+            mbar_init(&h_split[a], 4);
+            mbar_init(&h_empty[a], 1);
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
+        }
+        for (int s = 0; s < p.wstages; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int T = p.KS * p.KS;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            int it = 0, s = 0;
+            uint32_t wpar = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int hb = it % p.hbufs;
+                const uint32_t hpar = (uint32_t)(it / p.hbufs) & 1u;
+                const int n = tile / per_img, tt = tile - n * per_img;
+                const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+                mbar_wait(&h_empty[hb], hpar ^ 1u);
+                mbar_arrive_expect_tx(&h_full[hb], (uint32_t)p.a_bytes);
+                tma_box_5d(halo0 + (size_t)hb * 2 * p.a_stride, &xmap, 0, tx * kHTW - p.pad, ty * kHTH - p.pad, 0, n, &h_full[hb]);
+                for (int t = 0; t < T; ++t) {
+                    mbar_wait(&w_empty[s], wpar ^ 1u);
+                    mbar_arrive_expect_tx(&w_full[s], (uint32_t)(2 * p.w_bytes));
+                    bulk_g2s(wring + (size_t)s * 2 * p.w_bytes, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)t * 2 * p.w_bytes,
+                             (uint32_t)(2 * p.w_bytes), &w_full[s]);
+                    if (++s == p.wstages) { s = 0; wpar ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------- MMA issuer -------------------------------------------------
+        int it = 0, s = 0;
+        uint32_t wpar = 0;
+        const int kslices = p.Cin / 8;
+        const uint32_t a_lbo = (uint32_t)p.plane_bytes, a_sbo = (uint32_t)p.hcols * 16u;
+        const uint32_t w_lbo = (uint32_t)p.Npad * 16u, w_sbo = 128u;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int hb = it % p.hbufs, ab = it & 1;
+            const uint32_t tacc = tmem + (uint32_t)(ab * p.Npad);
+            mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);
+            mbar_wait(&h_split[hb], (uint32_t)(it / p.hbufs) & 1u);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(halo0 + (size_t)hb * 2 * p.a_stride), a_lo = a_hi + p.a_stride;
+            for (int t = 0; t < T; ++t) {
+                mbar_wait(&w_full[s], wpar);
+                tc_fence_after();
+                if (lane == 0) {
+                    const int ky = t / p.KS, kx = t - ky * p.KS;
+                    const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil) * 16u;
+                    const uint32_t w_hi = smem_u32(wring + (size_t)s * 2 * p.w_bytes), w_lo = w_hi + p.w_bytes;
+                    for (int k = 0; k < kslices; ++k) {
+                        const uint32_t ao = (uint32_t)(2 * k) * a_lbo + shift, wo = (uint32_t)(2 * k) * w_lbo;
+                        const uint64_t dah = make_desc_plain(a_hi + ao, a_lbo, a_sbo), dal = make_desc_plain(a_lo + ao, a_lbo, a_sbo);
+                        const uint64_t dwh = make_desc_plain(w_hi + wo, w_lbo, w_sbo), dwl = make_desc_plain(w_lo + wo, w_lbo, w_sbo);
+                        tc_mma_tf32(tacc, dal, dwh, p.idesc, (t | k) != 0);  // small terms first
+                        tc_mma_tf32(tacc, dah, dwl, p.idesc, 1);
+                        tc_mma_tf32(tacc, dah, dwh, p.idesc, 1);
+                    }
+                    tc_commit(&w_empty[s]);
+                    if (t == T - 1) {
+                        tc_commit(&h_empty[hb]);   // halo buffer free once every MMA of the tile has read it
+                        tc_commit(&acc_full[ab]);
+                    }
+                }
+                __syncwarp();
+                if (++s == p.wstages) { s = 0; wpar ^= 1u; }
+            }
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------ 3xTF32 split ------------------------------------------------
+        const int wt = threadIdx.x - 64;  // 0..127
+        int it = 0;
+        const int n16 = p.a_bytes / 16;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int hb = it % p.hbufs;
+            mbar_wait(&h_full[hb], (uint32_t)(it / p.hbufs) & 1u);
+            float4 *a = reinterpret_cast<float4 *>(halo0 + (size_t)hb * 2 * p.a_stride);
+            float4 *alo = reinterpret_cast<float4 *>(halo0 + (size_t)hb * 2 * p.a_stride + p.a_stride);
+            for (int i = wt; i < n16; i += 128) {  // consecutive threads, consecutive 16-byte elements: conflict-free
+                const float4 v = a[i];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                a[i] = h;
+                alo[i] = l;
+            }
+            proxy_fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_split[hb]);
+        }
+    } else {
+        // -------------------------------------------------- epilogue --------------------------------------------------
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;  // accumulator row m -> output pixel (y0 + m / 8, x0 + m % 8)
+        const bool vec4 = ((p.ycs | p.yco) & 3) == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            mbar_wait(&acc_full[ab], ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
+            const int n = tile / per_img, tt = tile - n * per_img;
+            const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+            const int oy = ty * kHTH + row / kHTW, ox = tx * kHTW + row % kHTW;
+            const bool inside = oy < p.Ho && ox < p.Wo;
+            float *dst = p.y + (((size_t)n * p.Ho + (inside ? oy : 0)) * p.Wo + (inside ? ox : 0)) * p.ycs + p.yco;
+            for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * p.Npad + c0), v);
+                if (c0 + 16 >= p.Npad) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                }
+                if (!inside) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int co = c0 + i;
+                    float o = v[i] + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.0f);
+                    v[i] = p.relu ? fmaxf(o, 0.0f) : o;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const int co = c0 + i;
+                    if (co + 3 < p.Cout && vec4) {
+                        *reinterpret_cast<float4 *>(dst + co) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (co + e < p.Cout) dst[co + e] = v[i + e];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encoder() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
         void *sym = nullptr;
@@ -399,6 +626,82 @@ int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float 
     if (grid > tiles) grid = tiles;
     conv5_kernel<<<(unsigned)grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, xmap);
     return pmb200_internal_launch_status("conv2d_tc5");
+}
+
+// Stride-1 form (K-D5h): one halo tile per 8 x 16 output tile, filter taps as shifted views.  Filter image:
+// [tap][hi, lo][Cin/4 chunks][Npad rows][4 floats] (ops.pack_conv_filter_tc5h), same float count as the per-tap form.
+int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const float *bias, float *y_nhwc, int N, int H, int W, int Cin,
+                       int Cout, int KS, int pad, int dil, int relu, int y_channel_stride, int y_channel_offset, void *stream) {
+    if (!x_nhwc || !filter_tc5h || !y_nhwc) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: null pointer");
+    if (!pmb200_conv2d_tc5_supported(Cin, Cout, KS, 1))
+        return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: Cin in {8,16,32,64}, Cout <= 64, KS in {1,3,5}");
+    if (N < 1 || H < 1 || W < 1 || pad < 0 || dil < 1) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: bad size");
+    if ((reinterpret_cast<uintptr_t>(x_nhwc) & 15u) || (reinterpret_cast<uintptr_t>(filter_tc5h) & 15u))
+        return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: input and filter must be 16-byte aligned");
+    const int Ho = H + 2 * pad - dil * (KS - 1), Wo = W + 2 * pad - dil * (KS - 1);
+    if (Ho < 1 || Wo < 1) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: empty output");
+    if (y_channel_stride < Cout + y_channel_offset || y_channel_offset < 0)
+        return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: output channel slice out of range");
+    auto enc = encoder();
+    if (!enc) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: cuTensorMapEncodeTiled unavailable");
+    Conv5hParams p;
+    p.wpack = filter_tc5h; p.bias = bias; p.y = y_nhwc;
+    p.N = N; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.Npad = npad_of(Cout);
+    p.KS = KS; p.pad = pad; p.dil = dil; p.relu = relu; p.ycs = y_channel_stride; p.yco = y_channel_offset;
+    p.tiles_x = (Wo + kHTW - 1) / kHTW; p.tiles_y = (Ho + kHTH - 1) / kHTH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
+    if (tiles > 0x7fffffffLL) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: too many tiles");
+    p.total_tiles = (int)tiles;
+    p.hcols = kHTW + dil * (KS - 1); p.hrows = kHTH + dil * (KS - 1);
+    if (p.hcols > 256 || p.hrows > 256) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: dilation too large for one TMA box");
+    p.plane_bytes = p.hrows * p.hcols * 16;
+    p.a_bytes = p.plane_bytes * (Cin / 4);
+    p.w_bytes = p.Npad * Cin * 4;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+    p.tmem_cols = 2 * p.Npad <= 32 ? 32u : (2 * p.Npad <= 64 ? 64u : 128u);
+    if ((unsigned)p.plane_bytes >= (1u << 18) || p.hcols * 16 >= (1 << 18))
+        return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: halo tile exceeds the descriptor's 14-bit offsets");
+    int dev = 0, sms = 0, smem_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    p.a_stride = (p.a_bytes + 127) / 128 * 128;
+    const int want_w = KS * KS < 4 ? KS * KS : 4;  // filter stages worth having
+    p.hbufs = (256 + 2 * 2 * p.a_stride + want_w * 2 * p.w_bytes + 128 <= smem_optin) ? 2 : 1;
+    const int fixed = 256 + p.hbufs * 2 * p.a_stride + 128;  // barriers, (hi, lo) halo buffers, alignment slack
+    int wst = (smem_optin - fixed) / (2 * p.w_bytes);
+    if (wst > 8) wst = 8;
+    if (wst > KS * KS) wst = KS * KS;
+    if (wst < 1) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: halo tile + filter ring do not fit in shared memory");
+    int ctas = 1;
+    if (2 * (fixed + want_w * 2 * p.w_bytes + 1024) <= smem_optin + 1024) {  // two CTAs per SM when both keep their filter stages
+        ctas = 2;
+        wst = ((smem_optin + 1024) / 2 - 1024 - fixed) / (2 * p.w_bytes);
+        if (wst > 8) wst = 8;
+        if (wst > KS * KS) wst = KS * KS;
+    }
+    p.wstages = wst;
+    const int smem = fixed + wst * 2 * p.w_bytes;
+    static thread_local int attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(conv5h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            cudaGetLastError();
+            return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: shared-memory opt-in failed");
+        }
+        attr_smem = smem;
+    }
+    CUtensorMap xmap;
+    const cuuint64_t dims[5] = {4u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 4), (cuuint64_t)N};
+    const cuuint64_t strides[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, 16u, (cuuint64_t)H * W * Cin * 4};
+    const cuuint32_t box[5] = {4u, (cuuint32_t)p.hcols, (cuuint32_t)p.hrows, (cuuint32_t)(Cin / 4), 1u};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(x_nhwc), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: tensor map rejected (alignment / size)");
+    long long grid = (long long)sms * ctas;
+    if (grid > tiles) grid = tiles;
+    conv5h_kernel<<<(unsigned)grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, xmap);
+    return pmb200_internal_launch_status("conv2d_tc5h");
 }
 
 }  // extern "C"

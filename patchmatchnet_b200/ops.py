@@ -285,10 +285,31 @@ def pack_conv_filter_tc5(weight: Tensor) -> Tensor:
     return torch.gather(t, 4, idx).contiguous().view(-1)
 
 
+def pack_conv_filter_tc5h(weight: Tensor) -> Tensor:
+    """Conv filter [Cout,Cin,KS,KS] -> the image `pmb200_conv2d_tc5h` streams per tap: [tap][hi, lo][Cin/4 chunks][Npad rows]
+    [4 floats] (no swizzle: 8 rows of one chunk are one core matrix of the no-swizzle K-major tcgen05 layout)."""
+    if weight.dim() != 4 or weight.shape[2] != weight.shape[3]:
+        raise RuntimeError(f"pack_conv_filter_tc5h: expected [Cout,Cin,KS,KS], got {tuple(weight.shape)}")
+    w = weight.detach().float()
+    cout, cin, ks, _ = w.shape
+    if cin not in (8, 16, 32, 64) or not (1 <= cout <= 64):
+        raise RuntimeError("pack_conv_filter_tc5h: Cin in {8,16,32,64}, 1 <= Cout <= 64")
+    npad = (cout + 15) // 16 * 16
+    hi = _tf32_round(w)
+    lo = _tf32_round(w - hi)
+    both = torch.stack((hi, lo))  # [2, Cout, Cin, KS, KS]
+    t = torch.zeros((ks * ks, 2, cin // 4, npad, 4), dtype=torch.float32, device=w.device)
+    t[:, :, :, :cout] = both.permute(3, 4, 0, 1, 2).reshape(ks * ks, 2, cout, cin // 4, 4).permute(0, 1, 3, 2, 4)
+    return t.contiguous().view(-1)
+
+
 def conv2d_tc5(x: Tensor, filter_tc5: Tensor, bias: Optional[Tensor], cout: int, ks: int, stride: int = 1, pad: int = 0, dil: int = 1,
-               relu: bool = False, out: Optional[Tensor] = None, out_channel_offset: int = 0) -> Tensor:
+               relu: bool = False, out: Optional[Tensor] = None, out_channel_offset: int = 0, halo: bool = False) -> Tensor:
     """Channels-last convolution on the 5th-generation tensor cores (csrc/pm_conv5.cu), fp32-accurate.  Same calling
-    convention as conv2d_nhwc; `filter_tc5` comes from pack_conv_filter_tc5."""
+    convention as conv2d_nhwc; `filter_tc5` comes from pack_conv_filter_tc5, or from pack_conv_filter_tc5h with `halo=True`
+    (stride 1 only: the halo-tile form K-D5h)."""
+    if halo and stride != 1:
+        raise RuntimeError("conv2d_tc5: the halo-tile form serves stride 1")
     if not _on_device(x) or x.dtype != torch.float32 or x.dim() != 4:
         raise RuntimeError(f"conv2d_tc5: x must be a 4-D CUDA float32 tensor (got {x.dtype} {tuple(x.shape)} on {x.device}); no CPU fallback")
     if not x.is_contiguous(memory_format=torch.channels_last):
@@ -314,9 +335,13 @@ def conv2d_tc5(x: Tensor, filter_tc5: Tensor, bias: Optional[Tensor], cout: int,
             raise RuntimeError("conv2d_tc5: bias must have Cout elements")
         b_ptr = bias.data_ptr()
     with _device_guard(x):
-        rc = _native.lib().pmb200_conv2d_tc5(x.data_ptr(), filter_tc5.data_ptr(), b_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride, pad,
-                                             dil, 1 if relu else 0, ycs, yco, _stream(x))
-    _native.check(rc, "conv2d_tc5")
+        if halo:
+            rc = _native.lib().pmb200_conv2d_tc5h(x.data_ptr(), filter_tc5.data_ptr(), b_ptr, out.data_ptr(), N, H, W, cin, cout, ks, pad,
+                                                  dil, 1 if relu else 0, ycs, yco, _stream(x))
+        else:
+            rc = _native.lib().pmb200_conv2d_tc5(x.data_ptr(), filter_tc5.data_ptr(), b_ptr, out.data_ptr(), N, H, W, cin, cout, ks, stride,
+                                                 pad, dil, 1 if relu else 0, ycs, yco, _stream(x))
+    _native.check(rc, "conv2d_tc5h" if halo else "conv2d_tc5")
     return out
 
 

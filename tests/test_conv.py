@@ -251,6 +251,42 @@ def test_gpu_tc5_conv_matches_cudnn_fp32(name, fp32_library):
         assert _scaled_err(got_nb, F.conv2d(x, w, None, S, pad, dil)) <= 2e-5
 
 
+TC5H_LAYERS = sorted(n for n in TC5_LAYERS if LAYERS[n][3] == 1)
+
+
+def test_tc5h_filter_image_layout():
+    torch.manual_seed(1)
+    w = torch.randn(18, 32, 3, 3)
+    got = ops.pack_conv_filter_tc5h(w).view(9, 2, 8, 32, 4)
+    hi = ops._tf32_round(w)
+    lo = ops._tf32_round(w - hi)
+    for (t, s_, c, n, e) in ((0, 0, 0, 0, 0), (4, 1, 7, 17, 3), (8, 0, 3, 5, 2)):
+        ky, kx = divmod(t, 3)
+        assert float(got[t, s_, c, n, e]) == float((hi, lo)[s_][n, 4 * c + e, ky, kx])
+    assert float(got[:, :, :, 18:].abs().max()) == 0.0
+    assert ops.pack_conv_filter_tc5h(w).numel() == ops.pack_conv_filter_tc5(w).numel()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TC5H_LAYERS)
+def test_gpu_tc5h_conv_matches_cudnn_fp32(name, fp32_library):
+    """K-D5h (stride-1 halo-tile form: one 5-D TMA box per tile, filter taps as shifted no-swizzle descriptors) against cuDNN
+    fp32 on every stride-1 layer shape, ragged sizes (partial 8 x 16 tiles, zero padding from the TMA fill), dilation up to 6."""
+    cin, cout, ks, S, pad, dil, relu = LAYERS[name]
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(sum(map(ord, name)) + 2)
+    for (N, H, W) in ((2, 37, 53), (1, 16, 8), (3, 9, 70)):
+        x = torch.randn(N, cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).to(dev)
+        b = torch.randn(cout, generator=g).to(dev)
+        want = _ref_conv(x, w, b, S, pad, dil, relu)
+        got = ops.conv2d_tc5(x, ops.pack_conv_filter_tc5h(w), b, cout, ks, 1, pad, dil, relu=relu, halo=True)
+        torch.cuda.synchronize()
+        assert got.shape == want.shape
+        err = _scaled_err(got, want)
+        assert err <= 2e-5, f"{name} {N}x{H}x{W}: scaled max err {err:.3e}"
+
+
 @pytest.mark.gpu
 def test_gpu_tc5_conv_full_size_layers_and_channel_slice(fp32_library):
     dev = "cuda:0"

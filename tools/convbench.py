@@ -113,6 +113,13 @@ for (name, N, cin, cout, ks, S, pad, dil, relu, h, w) in LAYERS:
             row["tc5_tflops_3x"] = round(3 * flops / (c * 1e-6) / 1e12, 1)
         except Exception as e:  # noqa: BLE001
             row["tc5_3xtf32_us"] = f"ERR {e}"
+        if S == 1:  # K-D5h: halo tile once per output tile, taps as shifted descriptors
+            try:
+                f5h = ops.pack_conv_filter_tc5h(wt)
+                c, cmin, wm = timeit(lambda: ops.conv2d_tc5(x, f5h, b, cout, ks, 1, pad, dil, relu=relu, halo=True))
+                row["tc5h_3xtf32_us"] = {"cold": round(c, 1), "cold_min": round(cmin, 1), "warm": round(wm, 1)}
+            except Exception as e:  # noqa: BLE001
+                row["tc5h_3xtf32_us"] = f"ERR {e}"
     rows.append(row)
 tot_lib = sum(r["cudnn_tf32_us"]["cold"] for r in rows)
 tot_nat = sum(r["native_p1_mt0_us"]["cold"] for r in rows if isinstance(r.get("native_p1_mt0_us"), dict))
