@@ -93,11 +93,13 @@ class _PackedConv:
         from . import ops
 
         srcs = [conv.weight] + ([conv.bias] if conv.bias is not None else [])
-        if ops.conv_uses_tc5(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0]):
+        mode = ops.conv_tc5_mode(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0])
+        if mode:
             frag, bias = self._cache.get(
-                srcs, lambda: (ops.pack_conv_filter_tc5(conv.weight), None if conv.bias is None else conv.bias.detach().clone()), key="tc5")
+                srcs, lambda: (ops.pack_conv_filter_tc5_for(conv.weight, mode), None if conv.bias is None else conv.bias.detach().clone()),
+                key="tc5" + mode)
             return ops.conv2d_tc5(x, frag, bias if with_bias else None, conv.out_channels, conv.kernel_size[0], conv.stride[0],
-                                  conv.padding[0], conv.dilation[0], relu=relu)
+                                  conv.padding[0], conv.dilation[0], relu=relu, halo=mode == "halo")
         prec = ops.conv_precision()
         frag, bias = self._cache.get(
             srcs, lambda: (ops.pack_conv_filter(conv.weight, prec), None if conv.bias is None else conv.bias.detach().clone()), key=prec)
@@ -136,8 +138,8 @@ class _ConvBnReLU2d(nn.Module):
 
         return self._frag_cache.get(srcs, make, key=prec)
 
-    def folded_tc5(self):
-        """(filter image for the tcgen05 conv, folded bias)."""
+    def folded_tc5(self, mode: str):
+        """(filter image for the tcgen05 conv in the given form, folded bias)."""
         from . import ops
 
         bn = self.bn
@@ -145,18 +147,19 @@ class _ConvBnReLU2d(nn.Module):
 
         def make():
             w, b = _fold_bn(self.conv.weight, bn)
-            return ops.pack_conv_filter_tc5(w), b.contiguous()
+            return ops.pack_conv_filter_tc5_for(w, mode), b.contiguous()
 
-        return self._tc5_cache.get(srcs, make)
+        return self._tc5_cache.get(srcs, make, key=mode)
 
     def native(self, x: Tensor, out: Tensor = None, out_channel_offset: int = 0) -> Tensor:
         from . import ops
 
         c = self.conv
-        if ops.conv_uses_tc5(c.in_channels, c.out_channels, c.kernel_size[0], c.stride[0]):
-            frag, b = self.folded_tc5()
+        mode = ops.conv_tc5_mode(c.in_channels, c.out_channels, c.kernel_size[0], c.stride[0])
+        if mode:
+            frag, b = self.folded_tc5(mode)
             return ops.conv2d_tc5(x, frag, b, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
-                                  relu=True, out=out, out_channel_offset=out_channel_offset)
+                                  relu=True, out=out, out_channel_offset=out_channel_offset, halo=mode == "halo")
         frag, b = self.folded_frag()
         return ops.conv2d_nhwc(x, frag, b, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
                                relu=True, out=out, out_channel_offset=out_channel_offset)

@@ -243,16 +243,35 @@ TC5_CONVS = os.environ.get("PMB200_TC5", "1") != "0"
 # supported layer (A/B measurements), PMB200_TC5=0 none.
 TC5_LAYERS = {(16, 32, 5, 2), (64, 32, 3, 1), (64, 18, 3, 1), (32, 16, 3, 1)}
 TC5_ALL = os.environ.get("PMB200_TC5", "1") == "all"
+# Stride-1 layers served by the halo-tile form K-D5h (one TMA box + one split per output tile, taps as shifted descriptors).
+# PMB200_TC5H=all: every stride-1 layer the kernel takes (A/B measurements); =0: none.
+TC5H_LAYERS: set = set()
+TC5H_ALL = os.environ.get("PMB200_TC5H", "1") == "all"
+TC5H_OFF = os.environ.get("PMB200_TC5H", "1") == "0"
+
+
+def conv_tc5_mode(cin: int, cout: int, ks: int, stride: int = 1, transposed: bool = False, fused_add: bool = False) -> str:
+    """"" (mma.sync kernel), "halo" (K-D5h) or "tap" (K-D5): which tcgen05 form, if any, runs this conv.  Only in the
+    fp32-accurate mode (the arithmetic of both IS the 3xTF32 split), never with a fused transposed / upsample-add epilogue, and
+    only for layers on the measured lists above."""
+    if not (NATIVE_CONVS and TC5_CONVS) or transposed or fused_add or conv_precision() != 3:
+        return ""
+    if not _native.lib().pmb200_conv2d_tc5_supported(cin, cout, ks, stride):
+        return ""
+    key = (cin, cout, ks, stride)
+    if stride == 1 and not TC5H_OFF and (TC5H_ALL or key in TC5H_LAYERS):
+        return "halo"
+    if TC5_ALL or key in TC5_LAYERS:
+        return "tap"
+    return ""
 
 
 def conv_uses_tc5(cin: int, cout: int, ks: int, stride: int = 1, transposed: bool = False, fused_add: bool = False) -> bool:
-    """Which convs run on the tcgen05 kernel: the fp32-accurate mode only (its arithmetic IS the 3xTF32 split), no fused
-    transposed / upsample-add epilogue, and a layer on the measured list above."""
-    if not (NATIVE_CONVS and TC5_CONVS) or transposed or fused_add or conv_precision() != 3:
-        return False
-    if not TC5_ALL and (cin, cout, ks, stride) not in TC5_LAYERS:
-        return False
-    return bool(_native.lib().pmb200_conv2d_tc5_supported(cin, cout, ks, stride))
+    return conv_tc5_mode(cin, cout, ks, stride, transposed, fused_add) != ""
+
+
+def pack_conv_filter_tc5_for(weight: Tensor, mode: str) -> Tensor:
+    return pack_conv_filter_tc5h(weight) if mode == "halo" else pack_conv_filter_tc5(weight)
 
 
 def pack_conv_filter_tc5(weight: Tensor) -> Tensor:

@@ -51,18 +51,18 @@ def _offset_conv(conv: nn.Conv2d, x: Tensor, native: bool) -> Tensor:
             or not ops.conv_prefers_native(conv.in_channels, conv.out_channels, conv.kernel_size[0])):
         return conv(x)
     srcs = (conv.weight, conv.bias)
-    tc5 = ops.conv_uses_tc5(conv.in_channels, conv.out_channels, conv.kernel_size[0], 1)
-    prec = "tc5" if tc5 else ops.conv_precision()
+    tc5 = ops.conv_tc5_mode(conv.in_channels, conv.out_channels, conv.kernel_size[0], 1)
+    prec = "tc5" + tc5 if tc5 else ops.conv_precision()
     stamp = (prec,) + tuple((t.data_ptr(), t._version, t.device) for t in srcs)
     cached = _FOLD_CACHE.get(conv)
     if cached is None or cached[0] != stamp:
         with torch.no_grad():
-            pack = ops.pack_conv_filter_tc5(conv.weight) if tc5 else ops.pack_conv_filter(conv.weight, prec)
+            pack = ops.pack_conv_filter_tc5_for(conv.weight, tc5) if tc5 else ops.pack_conv_filter(conv.weight, prec)
             cached = (stamp, (pack, conv.bias.detach().clone()))
         _FOLD_CACHE[conv] = cached
     frag, bias = cached[1]
     if tc5:  # tcgen05 implicit GEMM (csrc/pm_conv5.cu); its channels-last output is consumed in place like the other's
-        return ops.conv2d_tc5(x, frag, bias, conv.out_channels, conv.kernel_size[0], 1, conv.padding[0], conv.dilation[0])
+        return ops.conv2d_tc5(x, frag, bias, conv.out_channels, conv.kernel_size[0], 1, conv.padding[0], conv.dilation[0], halo=tc5 == "halo")
     return ops.conv2d_nhwc(x, frag, bias, conv.out_channels, conv.kernel_size[0], 1, conv.padding[0], conv.dilation[0])
 
 
