@@ -307,10 +307,13 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
 //   * the next 8-row group of the operand = the next output row = + (halo cols * 16) bytes      (descriptor SBO),
 //   * the second half of an 8-channel K slice = the next plane = + (halo rows * cols * 16) bytes (descriptor LBO),
 //   * filter tap (ky, kx) = start address + ((ky*dil) * cols + kx*dil) * 16 bytes -- always 16-byte aligned, no swizzle phase.
-// TMA produces the planes directly: tensor map {4, W, H, Cin/4, N} (dim 3 = channel chunk, stride 16 bytes), one 5-D box
-// {4, cols, rows, Cin/4, 1} per tile, zero fill for the padding.  Output tile: 8 wide x 16 tall.  The halo tile is loaded and
-// split (A_hi / A_lo) ONCE per tile; the filter taps stream through a small ring ([chunk][Npad][4 floats] planes, hi and lo,
-// packed by ops.pack_conv_filter_tc5h).  Roles, accumulators and epilogue as conv5_kernel.
+// The halo tile arrives as ONE dense TMA box {Cin, cols, rows, 1} (rows of Cin*4 bytes, zero fill for the padding) in a staging
+// buffer; the four split warps, which touch every element anyway, write A_hi / A_lo TRANSPOSED into the planes (chunk order
+// rotated by pixel: conflict-free reads and writes).  (Run 6 measured the first version, whose 5-D tensor map {4, W, H, Cin/4, N}
+// made the TMA engine gather the planes itself in 16-byte pieces: correct, but 55 us on conv6/7 -- the engine is slow at that
+// granularity.)  Output tile: 8 wide x 16 tall.  Load and split happen ONCE per tile; the filter taps stream through a small
+// ring ([chunk][Npad][4 floats] planes, hi and lo, packed by ops.pack_conv_filter_tc5h).  Roles, accumulators and epilogue as
+// conv5_kernel.
 // ----------------------------------------------------------------------------------------------------------------------
 constexpr int kHTW = 8, kHTH = 16;
 
@@ -322,21 +325,15 @@ struct Conv5hParams {
     int tiles_x, tiles_y, total_tiles;
     int hcols, hrows;     // halo tile: 8 + dil*(KS-1) columns, 16 + dil*(KS-1) rows
     int plane_bytes;      // hrows * hcols * 16
-    int a_bytes;          // plane_bytes * Cin/4 (one of hi / lo): what one TMA box delivers
-    int a_stride;         // a_bytes rounded up to 128: distance hi -> lo and between halo buffers (2 * a_stride)
-    int hbufs;            // halo buffers: 2 when they fit (load + split of tile i+1 under the MMAs of tile i), else 1
+    int a_bytes;          // plane_bytes * Cin/4 (one of hi / lo) = what one TMA box delivers into a staging buffer
+    int a_stride;         // a_bytes rounded up to 128: distance between staging buffers, hi -> lo, plane sets (2 * a_stride)
+    int hbufs;            // plane sets (hi, lo): 2 when they fit (split of tile i+1 under the MMAs of tile i), else 1
+    int sbufs;            // staging buffers: 2 when they fit (TMA of tile i+1 under the split of tile i), else 1
     int w_bytes;          // Npad * Cin * 4 (one of hi / lo)
     int wstages;
     uint32_t idesc, tmem_cols;
 };
 
-__device__ __forceinline__ void tma_box_5d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<unsigned long long>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
 // no-swizzle K-major operand: core matrices of 8 rows x 16 bytes; LBO = distance of the K-adjacent core matrix, SBO = distance
 // of the next 8-row group (both in bytes)
 __device__ __forceinline__ uint64_t make_desc_plain(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -351,21 +348,24 @@ __device__ __forceinline__ uint64_t make_desc_plain(uint32_t addr, uint32_t lbo,
 __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    uint64_t *h_full = reinterpret_cast<uint64_t *>(smem);  // [2] halo tile landed
-    uint64_t *h_split = h_full + 2;                          // [2] A_hi / A_lo written
-    uint64_t *h_empty = h_split + 2;                         // [2] every MMA of the tile has read the halo buffer
+    uint64_t *h_full = reinterpret_cast<uint64_t *>(smem);  // [2] halo tile landed in a staging buffer
+    uint64_t *s_free = h_full + 2;                           // [2] the split has read the staging buffer
+    uint64_t *h_split = s_free + 2;                          // [2] A_hi / A_lo planes written
+    uint64_t *h_empty = h_split + 2;                         // [2] every MMA of the tile has read the plane set
     uint64_t *w_full = h_empty + 2;                          // [8] filter tap landed
     uint64_t *w_empty = w_full + 8;                          // [8] its MMAs have completed
     uint64_t *acc_full = w_empty + 8;                        // [2]
     uint64_t *acc_empty = acc_full + 2;                      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    unsigned char *halo0 = smem + 256;                                      // [hbufs][hi, lo][a_stride]
+    unsigned char *stage0 = smem + 384;                                     // [sbufs][a_stride]  dense [rows][cols][Cin]
+    unsigned char *halo0 = stage0 + (size_t)p.sbufs * p.a_stride;           // [hbufs][hi, lo][a_stride]  planes
     unsigned char *wring = halo0 + (size_t)p.hbufs * 2 * p.a_stride;        // [wstages][hi, lo][w_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int a = 0; a < 2; ++a) {
             mbar_init(&h_full[a], 1);
+            mbar_init(&s_free[a], 4);
             mbar_init(&h_split[a], 4);
             mbar_init(&h_empty[a], 1);
             mbar_init(&acc_full[a], 1);
@@ -396,13 +396,13 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
             int it = 0, s = 0;
             uint32_t wpar = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int hb = it % p.hbufs;
-                const uint32_t hpar = (uint32_t)(it / p.hbufs) & 1u;
+                const int sb = it % p.sbufs;
+                const uint32_t spar = (uint32_t)(it / p.sbufs) & 1u;
                 const int n = tile / per_img, tt = tile - n * per_img;
                 const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
-                mbar_wait(&h_empty[hb], hpar ^ 1u);
-                mbar_arrive_expect_tx(&h_full[hb], (uint32_t)p.a_bytes);
-                tma_box_5d(halo0 + (size_t)hb * 2 * p.a_stride, &xmap, 0, tx * kHTW - p.pad, ty * kHTH - p.pad, 0, n, &h_full[hb]);
+                mbar_wait(&s_free[sb], spar ^ 1u);
+                mbar_arrive_expect_tx(&h_full[sb], (uint32_t)p.a_bytes);
+                tma_box_4d(stage0 + (size_t)sb * p.a_stride, &xmap, 0, tx * kHTW - p.pad, ty * kHTH - p.pad, n, &h_full[sb]);
                 for (int t = 0; t < T; ++t) {
                     mbar_wait(&w_empty[s], wpar ^ 1u);
                     mbar_arrive_expect_tx(&w_full[s], (uint32_t)(2 * p.w_bytes));
@@ -455,25 +455,33 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
         // ------------------------------------------------ 3xTF32 split ------------------------------------------------
         const int wt = threadIdx.x - 64;  // 0..127
         int it = 0;
-        const int n16 = p.a_bytes / 16;
+        const int P = p.hcols * p.hrows, NC = p.Cin / 4;  // pixels of the halo tile, 16-byte channel chunks per pixel
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int hb = it % p.hbufs;
-            mbar_wait(&h_full[hb], (uint32_t)(it / p.hbufs) & 1u);
-            float4 *a = reinterpret_cast<float4 *>(halo0 + (size_t)hb * 2 * p.a_stride);
+            const int sb = it % p.sbufs, hb = it % p.hbufs;
+            mbar_wait(&h_full[sb], (uint32_t)(it / p.sbufs) & 1u);            // dense halo tile landed
+            mbar_wait(&h_empty[hb], ((uint32_t)(it / p.hbufs) & 1u) ^ 1u);    // the MMAs that read this plane set are done
+            const float4 *src = reinterpret_cast<const float4 *>(stage0 + (size_t)sb * p.a_stride);
+            float4 *ahi = reinterpret_cast<float4 *>(halo0 + (size_t)hb * 2 * p.a_stride);
             float4 *alo = reinterpret_cast<float4 *>(halo0 + (size_t)hb * 2 * p.a_stride + p.a_stride);
-            for (int i = wt; i < n16; i += 128) {  // consecutive threads, consecutive 16-byte elements: conflict-free
-                const float4 v = a[i];
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-                a[i] = h;
-                alo[i] = l;
+            for (int px = wt; px < P; px += 128) {
+                for (int j = 0; j < NC; ++j) {
+                    const int c = (j + px) & (NC - 1);  // rotated by pixel: the 8 lanes of a quarter-warp read 8 bank groups
+                    const float4 v = src[px * NC + c];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                    ahi[c * P + px] = h;  // plane c: 16 bytes per pixel; consecutive lanes, consecutive pixels (P is even)
+                    alo[c * P + px] = l;
+                }
             }
             proxy_fence_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h_split[hb]);
+            if (lane == 0) {
+                mbar_arrive(&h_split[hb]);
+                mbar_arrive(&s_free[sb]);
+            }
         }
     } else {
         // -------------------------------------------------- epilogue --------------------------------------------------
@@ -667,8 +675,11 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     p.a_stride = (p.a_bytes + 127) / 128 * 128;
     const int want_w = KS * KS < 4 ? KS * KS : 4;  // filter stages worth having
-    p.hbufs = (256 + 2 * 2 * p.a_stride + want_w * 2 * p.w_bytes + 128 <= smem_optin) ? 2 : 1;
-    const int fixed = 256 + p.hbufs * 2 * p.a_stride + 128;  // barriers, (hi, lo) halo buffers, alignment slack
+    auto need = [&](int sb, int hb) { return 384 + sb * p.a_stride + hb * 2 * p.a_stride + want_w * 2 * p.w_bytes + 128; };
+    p.sbufs = 2; p.hbufs = 2;
+    if (need(2, 2) > smem_optin) p.hbufs = 1;
+    if (need(2, p.hbufs) > smem_optin) p.sbufs = 1;
+    const int fixed = 384 + p.sbufs * p.a_stride + p.hbufs * 2 * p.a_stride + 128;  // barriers, staging, plane sets, alignment slack
     int wst = (smem_optin - fixed) / (2 * p.w_bytes);
     if (wst > 8) wst = 8;
     if (wst > KS * KS) wst = KS * KS;
@@ -691,11 +702,11 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
         attr_smem = smem;
     }
     CUtensorMap xmap;
-    const cuuint64_t dims[5] = {4u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 4), (cuuint64_t)N};
-    const cuuint64_t strides[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, 16u, (cuuint64_t)H * W * Cin * 4};
-    const cuuint32_t box[5] = {4u, (cuuint32_t)p.hcols, (cuuint32_t)p.hrows, (cuuint32_t)(Cin / 4), 1u};
-    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
-    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(x_nhwc), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)Cin, (cuuint32_t)p.hcols, (cuuint32_t)p.hrows, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x_nhwc), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: tensor map rejected (alignment / size)");
     long long grid = (long long)sms * ctas;
