@@ -1,0 +1,26 @@
+"""One layer through the tcgen05 convs (both forms) and the mma.sync 3xTF32 conv, a few launches each: the target of an
+`ncu -k regex:conv5 --set full --import-source on` capture.
+
+    python tools/conv5_probe.py N cin cout ks stride pad dil h w
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from patchmatchnet_b200 import ops  # noqa: E402
+
+N, cin, cout, ks, S, pad, dil, h, w = (int(a) for a in sys.argv[1:10])
+g = torch.Generator().manual_seed(0)
+x = torch.randn(N, cin, h, w, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+wt = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).cuda()
+b = torch.randn(cout, generator=g).cuda()
+f3, f5 = ops.pack_conv_filter(wt, 3), ops.pack_conv_filter_tc5(wt)
+for _ in range(3):
+    ops.conv2d_nhwc(x, f3, b, cout, ks, S, pad, dil, relu=True, precision=3)
+    ops.conv2d_tc5(x, f5, b, cout, ks, S, pad, dil, relu=True)
+    if S == 1:
+        ops.conv2d_tc5(x, ops.pack_conv_filter_tc5h(wt), b, cout, ks, 1, pad, dil, relu=True, halo=True)
+torch.cuda.synchronize()
+print("ok")
