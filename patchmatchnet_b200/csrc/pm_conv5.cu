@@ -312,13 +312,20 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
 // rotated by pixel: conflict-free reads and writes).  (Run 6 measured the first version, whose 5-D tensor map {4, W, H, Cin/4, N}
 // made the TMA engine gather the planes itself in 16-byte pieces: correct, but 55 us on conv6/7 -- the engine is slow at that
 // granularity.)  Output tile: 8 wide x 16 tall.  Load and split happen ONCE per tile; the filter taps stream through a small
-// ring ([chunk][Npad][4 floats] planes, hi and lo, packed by ops.pack_conv_filter_tc5h).  Roles, accumulators and epilogue as
-// conv5_kernel.
+// ring.  Roles and accumulator double buffering as conv5_kernel.
+//
+// MMA economy (tools/umma_rate.cu, profiles/r2_umma_rate.json): one tcgen05.mma with M = 128 costs max(49, N/2) cycles whatever
+// its kind -- below N = 128 the instruction, not the arithmetic, is the unit of cost, and the first version of this kernel
+// (3 MMAs of N = Npad per K slice, ~23 issue-thread instructions each) ran at 146 cycles per MMA, bound by the issuing thread.
+// So (a) the filter tap is stored as ONE operand [chunk][w_hi rows | w_lo rows][4 floats] (ops.pack_conv_filter_tc5h):
+// a_hi x [w_hi | w_lo] is one MMA of N = 2 Npad into columns [0, 2 Npad), a_lo x w_hi one of N = Npad into [0, Npad) -- 2 MMAs
+// per K slice instead of 3, the epilogue adds the two column halves; (b) the issue loop carries descriptors as (lo, hi) words
+// and only adds 16-byte offsets to the low word.
 // ----------------------------------------------------------------------------------------------------------------------
 constexpr int kHTW = 8, kHTH = 16;
 
 struct Conv5hParams {
-    const float *wpack;  // [tap][hi|lo][Cin/4 chunks][Npad][4]
+    const float *wpack;  // [tap][Cin/4 chunks][hi rows Npad | lo rows Npad][4]
     const float *bias;
     float *y;
     int N, H, W, Ho, Wo, Cin, Cout, Npad, KS, pad, dil, relu, ycs, yco;
@@ -331,20 +338,11 @@ struct Conv5hParams {
     int sbufs;            // staging buffers: 2 when they fit (TMA of tile i+1 under the split of tile i), else 1
     int w_bytes;          // Npad * Cin * 4 (one of hi / lo)
     int wstages;
-    uint32_t idesc, tmem_cols;
+    uint32_t idesc, idesc2, tmem_cols;  // idesc: N = Npad, idesc2: N = 2 Npad
 };
 
-// no-swizzle K-major operand: core matrices of 8 rows x 16 bytes; LBO = distance of the K-adjacent core matrix, SBO = distance
-// of the next 8-row group (both in bytes)
-__device__ __forceinline__ uint64_t make_desc_plain(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3fff);
-    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout type 0 = no swizzle
-    return d;
-}
-
+// Operands of this kernel are no-swizzle K-major: core matrices of 8 rows x 16 bytes; descriptor LBO = distance of the
+// K-adjacent core matrix, SBO = distance of the next 8-row group, version bit 46, layout type 0.
 __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -414,41 +412,44 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
         }
     } else if (warp == 1) {
         // ------------------------------------------------- MMA issuer -------------------------------------------------
-        int it = 0, s = 0;
-        uint32_t wpar = 0;
-        const int kslices = p.Cin / 8;
-        const uint32_t a_lbo = (uint32_t)p.plane_bytes, a_sbo = (uint32_t)p.hcols * 16u;
-        const uint32_t w_lbo = (uint32_t)p.Npad * 16u, w_sbo = 128u;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int hb = it % p.hbufs, ab = it & 1;
-            const uint32_t tacc = tmem + (uint32_t)(ab * p.Npad);
-            mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);
-            mbar_wait(&h_split[hb], (uint32_t)(it / p.hbufs) & 1u);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(halo0 + (size_t)hb * 2 * p.a_stride), a_lo = a_hi + p.a_stride;
-            for (int t = 0; t < T; ++t) {
-                mbar_wait(&w_full[s], wpar);
+        if (lane == 0) {
+            int it = 0, s = 0;
+            uint32_t wpar = 0;
+            const int kslices = p.Cin / 8;
+            // descriptors as (lo, hi) words: lo = start address >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version; offsets are added
+            // to lo in 16-byte units (shared-memory addresses stay below 2^18, so the 14-bit field never carries)
+            const uint32_t a_hiword = ((uint32_t)p.hcols) | (1u << 14);           // SBO = hcols * 16 bytes
+            const uint32_t w_hiword = (128u >> 4) | (1u << 14);                   // SBO = 128 bytes
+            const uint32_t a_lbo16 = (uint32_t)p.plane_bytes >> 4, w_lbo16 = 2u * (uint32_t)p.Npad;  // next chunk: plane / 2 Npad rows
+            const uint32_t a_kstep = 2u * a_lbo16, w_kstep = 2u * w_lbo16;        // one K slice = two chunks
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int hb = it % p.hbufs, ab = it & 1;
+                const uint32_t tacc = tmem + (uint32_t)(ab * 2 * p.Npad);
+                mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);
+                mbar_wait(&h_split[hb], (uint32_t)(it / p.hbufs) & 1u);
                 tc_fence_after();
-                if (lane == 0) {
-                    const int ky = t / p.KS, kx = t - ky * p.KS;
-                    const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil) * 16u;
-                    const uint32_t w_hi = smem_u32(wring + (size_t)s * 2 * p.w_bytes), w_lo = w_hi + p.w_bytes;
-                    for (int k = 0; k < kslices; ++k) {
-                        const uint32_t ao = (uint32_t)(2 * k) * a_lbo + shift, wo = (uint32_t)(2 * k) * w_lbo;
-                        const uint64_t dah = make_desc_plain(a_hi + ao, a_lbo, a_sbo), dal = make_desc_plain(a_lo + ao, a_lbo, a_sbo);
-                        const uint64_t dwh = make_desc_plain(w_hi + wo, w_lbo, w_sbo), dwl = make_desc_plain(w_lo + wo, w_lbo, w_sbo);
-                        tc_mma_tf32(tacc, dal, dwh, p.idesc, (t | k) != 0);  // small terms first
-                        tc_mma_tf32(tacc, dah, dwl, p.idesc, 1);
-                        tc_mma_tf32(tacc, dah, dwh, p.idesc, 1);
-                    }
-                    tc_commit(&w_empty[s]);
-                    if (t == T - 1) {
-                        tc_commit(&h_empty[hb]);   // halo buffer free once every MMA of the tile has read it
-                        tc_commit(&acc_full[ab]);
+                const uint32_t ahi_lo = (smem_u32(halo0 + (size_t)hb * 2 * p.a_stride) >> 4) | (a_lbo16 << 16);
+                const uint32_t alo_lo = ahi_lo + ((uint32_t)p.a_stride >> 4);
+                uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrites the accumulator)
+                for (int ky = 0; ky < p.KS; ++ky) {
+                    for (int kx = 0; kx < p.KS; ++kx) {
+                        mbar_wait(&w_full[s], wpar);
+                        tc_fence_after();
+                        const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil);
+                        uint32_t ah = ahi_lo + shift, al = alo_lo + shift;
+                        uint32_t w = (smem_u32(wring + (size_t)s * 2 * p.w_bytes) >> 4) | (w_lbo16 << 16);
+                        for (int k = 0; k < kslices; ++k, ah += a_kstep, al += a_kstep, w += w_kstep) {
+                            const uint64_t dw = ((uint64_t)w_hiword << 32) | w;
+                            tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | ah, dw, p.idesc2, first);  // a_hi x [w_hi | w_lo]
+                            tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | al, dw, p.idesc, 1);       // a_lo x w_hi
+                            first = 1;
+                        }
+                        tc_commit(&w_empty[s]);
+                        if (++s == p.wstages) { s = 0; wpar ^= 1u; }
                     }
                 }
-                __syncwarp();
-                if (++s == p.wstages) { s = 0; wpar ^= 1u; }
+                tc_commit(&h_empty[hb]);   // plane set free once every MMA of the tile has read it
+                tc_commit(&acc_full[ab]);
             }
         }
     } else if (warp < 6) {
@@ -499,8 +500,10 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
             const bool inside = oy < p.Ho && ox < p.Wo;
             float *dst = p.y + (((size_t)n * p.Ho + (inside ? oy : 0)) * p.Wo + (inside ? ox : 0)) * p.ycs + p.yco;
             for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * p.Npad + c0), v);
+                float v[16], u[16];
+                const uint32_t tcol = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 2 * p.Npad + c0);
+                tmem_ld16(tcol, v);                        // a_hi.w_hi + a_lo.w_hi
+                tmem_ld16(tcol + (uint32_t)p.Npad, u);     // a_hi.w_lo
                 if (c0 + 16 >= p.Npad) {
                     tc_fence_before();
                     __syncwarp();
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int co = c0 + i;
-                    float o = v[i] + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.0f);
+                    float o = (v[i] + u[i]) + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.0f);
                     v[i] = p.relu ? fmaxf(o, 0.0f) : o;
                 }
 #pragma unroll
@@ -637,7 +640,7 @@ int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float 
 }
 
 // Stride-1 form (K-D5h): one halo tile per 8 x 16 output tile, filter taps as shifted views.  Filter image:
-// [tap][hi, lo][Cin/4 chunks][Npad rows][4 floats] (ops.pack_conv_filter_tc5h), same float count as the per-tap form.
+// [tap][Cin/4 chunks][hi rows Npad | lo rows Npad][4 floats] (ops.pack_conv_filter_tc5h), same float count as the per-tap form.
 int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const float *bias, float *y_nhwc, int N, int H, int W, int Cin,
                        int Cout, int KS, int pad, int dil, int relu, int y_channel_stride, int y_channel_offset, void *stream) {
     if (!x_nhwc || !filter_tc5h || !y_nhwc) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: null pointer");
@@ -666,7 +669,8 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
     p.a_bytes = p.plane_bytes * (Cin / 4);
     p.w_bytes = p.Npad * Cin * 4;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
-    p.tmem_cols = 2 * p.Npad <= 32 ? 32u : (2 * p.Npad <= 64 ? 64u : 128u);
+    p.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+    p.tmem_cols = 4 * p.Npad <= 64 ? 64u : (4 * p.Npad <= 128 ? 128u : 256u);  // two accumulators of 2 Npad fp32 columns
     if ((unsigned)p.plane_bytes >= (1u << 18) || p.hcols * 16 >= (1 << 18))
         return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: halo tile exceeds the descriptor's 14-bit offsets");
     int dev = 0, sms = 0, smem_optin = 0;

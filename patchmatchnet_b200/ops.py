@@ -305,8 +305,9 @@ def pack_conv_filter_tc5(weight: Tensor) -> Tensor:
 
 
 def pack_conv_filter_tc5h(weight: Tensor) -> Tensor:
-    """Conv filter [Cout,Cin,KS,KS] -> the image `pmb200_conv2d_tc5h` streams per tap: [tap][hi, lo][Cin/4 chunks][Npad rows]
-    [4 floats] (no swizzle: 8 rows of one chunk are one core matrix of the no-swizzle K-major tcgen05 layout)."""
+    """Conv filter [Cout,Cin,KS,KS] -> the image `pmb200_conv2d_tc5h` streams per tap: [tap][Cin/4 chunks][2 Npad rows][4 floats],
+    rows 0..Npad-1 = w_hi, Npad..2Npad-1 = w_lo: ONE tcgen05 operand of N = 2 Npad (a_hi x [w_hi | w_lo] is a single MMA), whose
+    first Npad rows double as the N = Npad operand of a_lo x w_hi.  No swizzle: 8 rows of one chunk are one core matrix."""
     if weight.dim() != 4 or weight.shape[2] != weight.shape[3]:
         raise RuntimeError(f"pack_conv_filter_tc5h: expected [Cout,Cin,KS,KS], got {tuple(weight.shape)}")
     w = weight.detach().float()
@@ -317,8 +318,8 @@ def pack_conv_filter_tc5h(weight: Tensor) -> Tensor:
     hi = _tf32_round(w)
     lo = _tf32_round(w - hi)
     both = torch.stack((hi, lo))  # [2, Cout, Cin, KS, KS]
-    t = torch.zeros((ks * ks, 2, cin // 4, npad, 4), dtype=torch.float32, device=w.device)
-    t[:, :, :, :cout] = both.permute(3, 4, 0, 1, 2).reshape(ks * ks, 2, cout, cin // 4, 4).permute(0, 1, 3, 2, 4)
+    t = torch.zeros((ks * ks, cin // 4, 2, npad, 4), dtype=torch.float32, device=w.device)
+    t[:, :, :, :cout] = both.permute(3, 4, 0, 1, 2).reshape(ks * ks, 2, cout, cin // 4, 4).permute(0, 3, 1, 2, 4)
     return t.contiguous().view(-1)
 
 

@@ -257,12 +257,12 @@ TC5H_LAYERS = sorted(n for n in TC5_LAYERS if LAYERS[n][3] == 1)
 def test_tc5h_filter_image_layout():
     torch.manual_seed(1)
     w = torch.randn(18, 32, 3, 3)
-    got = ops.pack_conv_filter_tc5h(w).view(9, 2, 8, 32, 4)
+    got = ops.pack_conv_filter_tc5h(w).view(9, 8, 2, 32, 4)
     hi = ops._tf32_round(w)
     lo = ops._tf32_round(w - hi)
     for (t, s_, c, n, e) in ((0, 0, 0, 0, 0), (4, 1, 7, 17, 3), (8, 0, 3, 5, 2)):
         ky, kx = divmod(t, 3)
-        assert float(got[t, s_, c, n, e]) == float((hi, lo)[s_][n, 4 * c + e, ky, kx])
+        assert float(got[t, c, s_, n, e]) == float((hi, lo)[s_][n, 4 * c + e, ky, kx])
     assert float(got[:, :, :, 18:].abs().max()) == 0.0
     assert ops.pack_conv_filter_tc5h(w).numel() == ops.pack_conv_filter_tc5(w).numel()
 

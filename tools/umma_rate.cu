@@ -55,7 +55,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128) rate_kernel(int N, int nacc, int reps, int swz, long long *out) {
+__global__ void __launch_bounds__(128) rate_kernel(int N, int M, int nacc, int reps, int swz, long long *out) {
     extern __shared__ unsigned char raw[];
     unsigned char *smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int nacc, int reps, in
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *slot;
     const uint32_t kind_bits = KIND == 0 ? ((2u << 7) | (2u << 10)) : ((1u << 7) | (1u << 10));  // tf32 / bf16 operands
-    const uint32_t idesc = (1u << 4) | kind_bits | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | kind_bits | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     if (threadIdx.x == 0) {
         // plain: core matrices 8 rows x 16 B; K-adjacent core matrix 128*16 B away (A) / N*16 B away (B); next 8 rows 128 B away
         const uint64_t da = swz ? desc_sw128(smem_u32(A)) : desc_plain(smem_u32(A), 128 * 16, 128);
@@ -84,7 +84,14 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int nacc, int reps, in
         uint32_t par = 0;
         for (int warm = 0; warm < 2; ++warm) {
             const long long t0 = clock64();
-            for (int r = 0; r < reps; ++r) tc_mma<KIND>(tmem + (uint32_t)((r % nacc) * N), da, db, idesc, 1);
+            const uint32_t d0 = tmem, d1 = tmem + (uint32_t)((nacc - 1) * N);  // the issue loop carries no address arithmetic
+#pragma unroll 1
+            for (int r = 0; r < reps; r += 8) {
+                tc_mma<KIND>(d0, da, db, idesc, 1); tc_mma<KIND>(d1, da, db, idesc, 1);
+                tc_mma<KIND>(d0, da, db, idesc, 1); tc_mma<KIND>(d1, da, db, idesc, 1);
+                tc_mma<KIND>(d0, da, db, idesc, 1); tc_mma<KIND>(d1, da, db, idesc, 1);
+                tc_mma<KIND>(d0, da, db, idesc, 1); tc_mma<KIND>(d1, da, db, idesc, 1);
+            }
             tc_commit(bar);
             const long long t1 = clock64();
             while (!mbar_try_wait(bar, par)) {}
@@ -110,19 +117,20 @@ int main() {
     for (int kind = 0; kind < 2; ++kind)
         for (int swz = 0; swz < 2; ++swz)
             for (int grid : {1, 148})
-                for (int N : {8, 16, 32, 64, 128, 256})
+                for (int N : {16, 32, 64, 128, 256})
+                  for (int M : {64, 128})
                     for (int nacc : {1, 2}) {
                         if (nacc * N > 512) continue;
                         if (kind == 0)
-                            rate_kernel<0><<<grid, 128, smem>>>(N, nacc, reps, swz, out);
+                            rate_kernel<0><<<grid, 128, smem>>>(N, M, nacc, reps, swz, out);
                         else
-                            rate_kernel<1><<<grid, 128, smem>>>(N, nacc, reps, swz, out);
+                            rate_kernel<1><<<grid, 128, smem>>>(N, M, nacc, reps, swz, out);
                         cudaError_t e = cudaDeviceSynchronize();
                         long long h[2] = {0, 0};
                         cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
-                        printf("%s {\"kind\": \"%s\", \"swizzle128\": %d, \"ctas\": %d, \"N\": %d, \"accumulators\": %d, \"issue_cycles_per_mma\": %.1f, "
+                        printf("%s {\"kind\": \"%s\", \"swizzle128\": %d, \"ctas\": %d, \"M\": %d, \"N\": %d, \"accumulators\": %d, \"issue_cycles_per_mma\": %.1f, "
                                "\"complete_cycles_per_mma\": %.1f, \"err\": \"%s\"}",
-                               first ? "" : ",\n", kind == 0 ? "tf32 K8" : "bf16 K16", swz, grid, N, nacc, (double)h[0] / reps, (double)h[1] / reps,
+                               first ? "" : ",\n", kind == 0 ? "tf32 K8" : "bf16 K16", swz, grid, M, N, nacc, (double)h[0] / reps, (double)h[1] / reps,
                                e == cudaSuccess ? "" : cudaGetErrorString(e));
                         first = false;
                         if (e != cudaSuccess) { printf("]}\n"); return 1; }
