@@ -338,6 +338,7 @@ struct Conv5hParams {
     int sbufs;            // staging buffers: 2 when they fit (TMA of tile i+1 under the split of tile i), else 1
     int w_bytes;          // Npad * Cin * 4 (one of hi / lo)
     int wstages;
+    int w_resident;       // 1: wstages == KS*KS, every tap loaded once per CTA; 0: taps stream through the ring per tile
     uint32_t idesc, idesc2, tmem_cols;  // idesc: N = Npad, idesc2: N = 2 Npad
 };
 
@@ -350,12 +351,12 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
     uint64_t *s_free = h_full + 2;                           // [2] the split has read the staging buffer
     uint64_t *h_split = s_free + 2;                          // [2] A_hi / A_lo planes written
     uint64_t *h_empty = h_split + 2;                         // [2] every MMA of the tile has read the plane set
-    uint64_t *w_full = h_empty + 2;                          // [8] filter tap landed
-    uint64_t *w_empty = w_full + 8;                          // [8] its MMAs have completed
-    uint64_t *acc_full = w_empty + 8;                        // [2]
+    uint64_t *w_full = h_empty + 2;                          // [25] filter tap landed
+    uint64_t *w_empty = w_full + 25;                         // [25] its MMAs have completed
+    uint64_t *acc_full = w_empty + 25;                       // [2]
     uint64_t *acc_empty = acc_full + 2;                      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    unsigned char *stage0 = smem + 384;                                     // [sbufs][a_stride]  dense [rows][cols][Cin]
+    unsigned char *stage0 = smem + 640;                                     // [sbufs][a_stride]  dense [rows][cols][Cin]
     unsigned char *halo0 = stage0 + (size_t)p.sbufs * p.a_stride;           // [hbufs][hi, lo][a_stride]  planes
     unsigned char *wring = halo0 + (size_t)p.hbufs * 2 * p.a_stride;        // [wstages][hi, lo][w_bytes]
 
@@ -391,21 +392,31 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
         if (lane == 0) {
+            auto load_halo = [&](int tile, int use) {  // `use` = how many halo tiles this CTA has requested before
+                const int sb = use % p.sbufs;
+                const int n = tile / per_img, tt = tile - n * per_img;
+                const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+                mbar_wait(&s_free[sb], ((uint32_t)(use / p.sbufs) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&h_full[sb], (uint32_t)p.a_bytes);
+                tma_box_4d(stage0 + (size_t)sb * p.a_stride, &xmap, 0, tx * kHTW - p.pad, ty * kHTH - p.pad, n, &h_full[sb]);
+            };
+            auto load_tap = [&](int t, int s) {
+                mbar_arrive_expect_tx(&w_full[s], (uint32_t)(2 * p.w_bytes));
+                bulk_g2s(wring + (size_t)s * 2 * p.w_bytes, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)t * 2 * p.w_bytes,
+                         (uint32_t)(2 * p.w_bytes), &w_full[s]);
+            };
+            if ((int)blockIdx.x < p.total_tiles) load_halo(blockIdx.x, 0);
+            if (p.w_resident)
+                for (int t = 0; t < T; ++t) load_tap(t, t);  // the whole filter stays in shared memory: loaded once per CTA
             int it = 0, s = 0;
             uint32_t wpar = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int sb = it % p.sbufs;
-                const uint32_t spar = (uint32_t)(it / p.sbufs) & 1u;
-                const int n = tile / per_img, tt = tile - n * per_img;
-                const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
-                mbar_wait(&s_free[sb], spar ^ 1u);
-                mbar_arrive_expect_tx(&h_full[sb], (uint32_t)p.a_bytes);
-                tma_box_4d(stage0 + (size_t)sb * p.a_stride, &xmap, 0, tx * kHTW - p.pad, ty * kHTH - p.pad, n, &h_full[sb]);
+                // the NEXT tile's halo first: its latency (and its split) hide under this tile's MMAs
+                if (tile + (int)gridDim.x < p.total_tiles) load_halo(tile + gridDim.x, it + 1);
+                if (p.w_resident) continue;
                 for (int t = 0; t < T; ++t) {
                     mbar_wait(&w_empty[s], wpar ^ 1u);
-                    mbar_arrive_expect_tx(&w_full[s], (uint32_t)(2 * p.w_bytes));
-                    bulk_g2s(wring + (size_t)s * 2 * p.w_bytes, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)t * 2 * p.w_bytes,
-                             (uint32_t)(2 * p.w_bytes), &w_full[s]);
+                    load_tap(t, s);
                     if (++s == p.wstages) { s = 0; wpar ^= 1u; }
                 }
             }
@@ -444,8 +455,12 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
                             tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | al, dw, p.idesc, 1);       // a_lo x w_hi
                             first = 1;
                         }
-                        tc_commit(&w_empty[s]);
-                        if (++s == p.wstages) { s = 0; wpar ^= 1u; }
+                        if (p.w_resident) {
+                            if (++s == p.wstages) s = 0;  // phase 0 of every w_full completed once and stays complete
+                        } else {
+                            tc_commit(&w_empty[s]);
+                            if (++s == p.wstages) { s = 0; wpar ^= 1u; }
+                        }
                     }
                 }
                 tc_commit(&h_empty[hb]);   // plane set free once every MMA of the tile has read it
@@ -678,23 +693,27 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     p.a_stride = (p.a_bytes + 127) / 128 * 128;
-    const int want_w = KS * KS < 4 ? KS * KS : 4;  // filter stages worth having
-    auto need = [&](int sb, int hb) { return 384 + sb * p.a_stride + hb * 2 * p.a_stride + want_w * 2 * p.w_bytes + 128; };
-    p.sbufs = 2; p.hbufs = 2;
-    if (need(2, 2) > smem_optin) p.hbufs = 1;
-    if (need(2, p.hbufs) > smem_optin) p.sbufs = 1;
-    const int fixed = 384 + p.sbufs * p.a_stride + p.hbufs * 2 * p.a_stride + 128;  // barriers, staging, plane sets, alignment slack
-    int wst = (smem_optin - fixed) / (2 * p.w_bytes);
-    if (wst > 8) wst = 8;
-    if (wst > KS * KS) wst = KS * KS;
-    if (wst < 1) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: halo tile + filter ring do not fit in shared memory");
-    int ctas = 1;
-    if (2 * (fixed + want_w * 2 * p.w_bytes + 1024) <= smem_optin + 1024) {  // two CTAs per SM when both keep their filter stages
-        ctas = 2;
-        wst = ((smem_optin + 1024) / 2 - 1024 - fixed) / (2 * p.w_bytes);
+    // Shared memory: barriers (640 B), staging buffers, plane sets, filter stages, 128 B alignment slack.  Preference order:
+    // whole filter resident with both double buffers; resident with one plane set; else a ring as deep as fits (>= 2 stages
+    // wanted) with the buffers reduced in the order plane sets, staging.  Two CTAs per SM when everything fits twice.
+    const int T = KS * KS;
+    auto fixed_of = [&](int sb, int hb) { return 640 + sb * p.a_stride + hb * 2 * p.a_stride + 128; };
+    p.sbufs = 2; p.hbufs = 2; p.w_resident = 0;
+    int wst = 0;
+    if (fixed_of(2, 2) + T * 2 * p.w_bytes <= smem_optin) { p.w_resident = 1; wst = T; }
+    else if (fixed_of(2, 1) + T * 2 * p.w_bytes <= smem_optin) { p.hbufs = 1; p.w_resident = 1; wst = T; }
+    else {
+        const int want_w = T < 4 ? T : 4;
+        if (fixed_of(2, 2) + want_w * 2 * p.w_bytes > smem_optin) p.hbufs = 1;
+        if (fixed_of(2, p.hbufs) + want_w * 2 * p.w_bytes > smem_optin) p.sbufs = 1;
+        wst = (smem_optin - fixed_of(p.sbufs, p.hbufs)) / (2 * p.w_bytes);
         if (wst > 8) wst = 8;
-        if (wst > KS * KS) wst = KS * KS;
+        if (wst > T) wst = T;
+        if (wst < 1) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: halo tile + filter ring do not fit in shared memory");
     }
+    const int fixed = fixed_of(p.sbufs, p.hbufs);
+    int ctas = 1;
+    if (2 * (fixed + wst * 2 * p.w_bytes + 1024) <= smem_optin + 1024) ctas = 2;
     p.wstages = wst;
     const int smem = fixed + wst * 2 * p.w_bytes;
     static thread_local int attr_smem = 0;
