@@ -237,7 +237,7 @@ TC5_CONVS = os.environ.get("PMB200_TC5", "1") != "0"
 
 
 # (Cin, Cout, KS, stride) of the layers a tcgen05 form beats the mma.sync kernel's 3xTF32 mode on (cold us per launch at the
-# 640x512 sizes, tools/convbench.py, profiles/r2_run10_convbench.json).  Per-tap form K-D5 (the only one for stride 2):
+# 640x512 sizes, tools/convbench.py, profiles/r2_run11_convbench.json).  Per-tap form K-D5 (the only one for stride 2):
 # conv5 73 vs 93; it loses on conv2 (152 vs 90) and ties on conv8 (66 vs 63).  PMB200_TC5=all takes every supported layer
 # (A/B measurements), PMB200_TC5=0 none.
 TC5_LAYERS = {(16, 32, 5, 2)}
