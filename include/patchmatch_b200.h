@@ -70,12 +70,15 @@ int pmb200_conv2d_tc5_filter_floats(int Cin, int Cout, int KS);
 int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float *bias, float *y_nhwc, int N, int H, int W, int Cin,
                       int Cout, int KS, int stride, int pad, int dil, int relu, int y_channel_stride, int y_channel_offset,
                       void *stream);
-/* Stride-1 form of the same convolution (K-D5h): the input halo of an 8 x 16 output tile is fetched ONCE (one 5-D TMA box into
- * channel-chunk planes [Cin/4][rows][cols][4 floats]) and split once; every filter tap is a shifted view of it (no-swizzle
+/* Stride-1 form of the same convolution (K-D5h): the input halo of an 8 x 16 output tile is fetched ONCE (one dense TMA box),
+ * split once into channel-chunk planes [Cin/4][rows][cols][4 floats]; every filter tap is a shifted view of them (no-swizzle
  * K-major tcgen05 operand: 8 consecutive pixels of a plane are one core matrix).  Same arguments minus the stride.
- *   filter_tc5h  same float count as filter_tc5, layout [tap][hi, lo][Cin/4 chunks][Npad rows][4 floats], no swizzle */
+ *   filter_tc5h  same float count as filter_tc5, layout [tap][Cin/4 chunks][w_hi rows Npad | w_lo rows Npad][4 floats] */
 int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const float *bias, float *y_nhwc, int N, int H, int W, int Cin,
                        int Cout, int KS, int pad, int dil, int relu, int y_channel_stride, int y_channel_offset, void *stream);
+/* Debugging aid (not a reference interface): a device buffer of 256 int64 that following K-D5h launches stamp with clock64
+ * for the four roles of CTA 0 ([role][tile 0..15][event 0..3]); NULL switches it off. */
+int pmb200_debug_conv5h_trace(long long *device_buffer_256);
 
 /* ------------------------------------------------------------------------------------
  * Relative projections for every (source view, batch element):

@@ -116,6 +116,7 @@ _SIGNATURES = {
     "pmb200_conv2d_tc5_filter_floats": (c_int, [c_int] * 3),
     "pmb200_conv2d_tc5": (c_int, [c_void_p] * 4 + [c_int] * 12 + [c_void_p]),
     "pmb200_conv2d_tc5h": (c_int, [c_void_p] * 4 + [c_int] * 11 + [c_void_p]),
+    "pmb200_debug_conv5h_trace": (c_int, [c_void_p]),
     "pmb200_geometric_filter": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_double, c_float, c_float, c_int] + [c_void_p] * 5),
     "pmb200_fuse_points": (c_int, [c_void_p] * 4 + [c_int] * 2 + [c_void_p] * 4),
     "pmb200_map_probe": (c_int, [c_char_p, c_int, _PMAP]),

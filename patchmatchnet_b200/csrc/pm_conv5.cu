@@ -92,6 +92,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {  // arrives on `bar` once every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -340,7 +345,12 @@ struct Conv5hParams {
     int wstages;
     int w_resident;       // 1: wstages == KS*KS, every tap loaded once per CTA; 0: taps stream through the ring per tile
     uint32_t idesc, idesc2, tmem_cols;  // idesc: N = Npad, idesc2: N = 2 Npad
+    long long *trace;     // debugging aid (pmb200_debug_conv5h_trace): clock64 stamps of CTA 0's roles, [role][tile 0..15][event 0..3]
 };
+
+__device__ __forceinline__ void stamp(const Conv5hParams &p, int role, int it, int ev) {
+    if (p.trace && blockIdx.x == 0 && it < 16) p.trace[(role * 16 + it) * 4 + ev] = clock64();
+}
 
 // Operands of this kernel are no-swizzle K-major: core matrices of 8 rows x 16 bytes; descriptor LBO = distance of the
 // K-adjacent core matrix, SBO = distance of the next 8-row group, version bit 46, layout type 0.
@@ -397,6 +407,7 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
                 const int n = tile / per_img, tt = tile - n * per_img;
                 const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
                 mbar_wait(&s_free[sb], ((uint32_t)(use / p.sbufs) & 1u) ^ 1u);
+                stamp(p, 0, use, 0);
                 mbar_arrive_expect_tx(&h_full[sb], (uint32_t)p.a_bytes);
                 tma_box_4d(stage0 + (size_t)sb * p.a_stride, &xmap, 0, tx * kHTW - p.pad, ty * kHTH - p.pad, n, &h_full[sb]);
             };
@@ -423,49 +434,60 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
         }
     } else if (warp == 1) {
         // ------------------------------------------------- MMA issuer -------------------------------------------------
-        if (lane == 0) {
-            int it = 0, s = 0;
-            uint32_t wpar = 0;
-            const int kslices = p.Cin / 8;
-            // descriptors as (lo, hi) words: lo = start address >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version; offsets are added
-            // to lo in 16-byte units (shared-memory addresses stay below 2^18, so the 14-bit field never carries)
-            const uint32_t a_hiword = ((uint32_t)p.hcols) | (1u << 14);           // SBO = hcols * 16 bytes
-            const uint32_t w_hiword = (128u >> 4) | (1u << 14);                   // SBO = 128 bytes
-            const uint32_t a_lbo16 = (uint32_t)p.plane_bytes >> 4, w_lbo16 = 2u * (uint32_t)p.Npad;  // next chunk: plane / 2 Npad rows
-            const uint32_t a_kstep = 2u * a_lbo16, w_kstep = 2u * w_lbo16;        // one K slice = two chunks
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int hb = it % p.hbufs, ab = it & 1;
-                const uint32_t tacc = tmem + (uint32_t)(ab * 2 * p.Npad);
-                mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);
-                mbar_wait(&h_split[hb], (uint32_t)(it / p.hbufs) & 1u);
-                tc_fence_after();
-                const uint32_t ahi_lo = (smem_u32(halo0 + (size_t)hb * 2 * p.a_stride) >> 4) | (a_lbo16 << 16);
-                const uint32_t alo_lo = ahi_lo + ((uint32_t)p.a_stride >> 4);
-                uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrites the accumulator)
-                for (int ky = 0; ky < p.KS; ++ky) {
-                    for (int kx = 0; kx < p.KS; ++kx) {
-                        mbar_wait(&w_full[s], wpar);
-                        tc_fence_after();
-                        const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil);
-                        uint32_t ah = ahi_lo + shift, al = alo_lo + shift;
-                        uint32_t w = (smem_u32(wring + (size_t)s * 2 * p.w_bytes) >> 4) | (w_lbo16 << 16);
-                        for (int k = 0; k < kslices; ++k, ah += a_kstep, al += a_kstep, w += w_kstep) {
-                            const uint64_t dw = ((uint64_t)w_hiword << 32) | w;
+        // The WHOLE warp runs the loops, on warp-uniform values only (kernel parameters, blockIdx, loop counters): the
+        // compiler then keeps descriptors and addresses in uniform registers and the tcgen05 instructions issue back to back
+        // from the elected lane.  (Run under `if (lane == 0)` every MMA was wrapped in an R2UR / ELECT / BRA.U.ANY sequence:
+        // 108 cycles per MMA measured by the role trace, twice the tensor pipe's 49.)
+        const bool leader = elect_one();
+        int it = 0, s = 0;
+        uint32_t wpar = 0;
+        const int kslices = p.Cin / 8;
+        // descriptors as (lo, hi) words: lo = start address >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version; offsets are added
+        // to lo in 16-byte units (shared-memory addresses stay below 2^18, so the 14-bit field never carries)
+        const uint32_t a_hiword = ((uint32_t)p.hcols) | (1u << 14);           // SBO = hcols * 16 bytes
+        const uint32_t w_hiword = (128u >> 4) | (1u << 14);                   // SBO = 128 bytes
+        const uint32_t a_lbo16 = (uint32_t)p.plane_bytes >> 4, w_lbo16 = 2u * (uint32_t)p.Npad;  // next chunk: plane / 2 Npad rows
+        const uint32_t a_kstep = 2u * a_lbo16, w_kstep = 2u * w_lbo16;        // one K slice = two chunks
+        const uint32_t halo_u32 = smem_u32(halo0), ring_u32 = smem_u32(wring);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int hb = it % p.hbufs, ab = it & 1;
+            const uint32_t tacc = tmem + (uint32_t)(ab * 2 * p.Npad);
+            mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);
+            if (lane == 0) stamp(p, 1, it, 0);
+            mbar_wait(&h_split[hb], (uint32_t)(it / p.hbufs) & 1u);
+            if (lane == 0) stamp(p, 1, it, 1);
+            tc_fence_after();
+            const uint32_t ahi_lo = ((halo_u32 + (uint32_t)(hb * 2 * p.a_stride)) >> 4) | (a_lbo16 << 16);
+            const uint32_t alo_lo = ahi_lo + ((uint32_t)p.a_stride >> 4);
+            uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrites the accumulator)
+            for (int ky = 0; ky < p.KS; ++ky) {
+                for (int kx = 0; kx < p.KS; ++kx) {
+                    mbar_wait(&w_full[s], wpar);
+                    tc_fence_after();
+                    const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil);
+                    uint32_t ah = ahi_lo + shift, al = alo_lo + shift;
+                    uint32_t w = ((ring_u32 + (uint32_t)(s * 2 * p.w_bytes)) >> 4) | (w_lbo16 << 16);
+                    for (int k = 0; k < kslices; ++k, ah += a_kstep, al += a_kstep, w += w_kstep) {
+                        const uint64_t dw = ((uint64_t)w_hiword << 32) | w;
+                        if (leader) {
                             tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | ah, dw, p.idesc2, first);  // a_hi x [w_hi | w_lo]
                             tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | al, dw, p.idesc, 1);       // a_lo x w_hi
-                            first = 1;
                         }
-                        if (p.w_resident) {
-                            if (++s == p.wstages) s = 0;  // phase 0 of every w_full completed once and stays complete
-                        } else {
-                            tc_commit(&w_empty[s]);
-                            if (++s == p.wstages) { s = 0; wpar ^= 1u; }
-                        }
+                        first = 1;
+                    }
+                    if (p.w_resident) {
+                        if (++s == p.wstages) s = 0;  // phase 0 of every w_full completed once and stays complete
+                    } else {
+                        if (leader) tc_commit(&w_empty[s]);
+                        if (++s == p.wstages) { s = 0; wpar ^= 1u; }
                     }
                 }
+            }
+            if (leader) {
                 tc_commit(&h_empty[hb]);   // plane set free once every MMA of the tile has read it
                 tc_commit(&acc_full[ab]);
             }
+            if (lane == 0) stamp(p, 1, it, 2);
         }
     } else if (warp < 6) {
         // ------------------------------------------------ 3xTF32 split ------------------------------------------------
@@ -475,7 +497,9 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int sb = it % p.sbufs, hb = it % p.hbufs;
             mbar_wait(&h_full[sb], (uint32_t)(it / p.sbufs) & 1u);            // dense halo tile landed
+            if (wt == 0) stamp(p, 2, it, 0);
             mbar_wait(&h_empty[hb], ((uint32_t)(it / p.hbufs) & 1u) ^ 1u);    // the MMAs that read this plane set are done
+            if (wt == 0) stamp(p, 2, it, 1);
             const float4 *src = reinterpret_cast<const float4 *>(stage0 + (size_t)sb * p.a_stride);
             float4 *ahi = reinterpret_cast<float4 *>(halo0 + (size_t)hb * 2 * p.a_stride);
             float4 *alo = reinterpret_cast<float4 *>(halo0 + (size_t)hb * 2 * p.a_stride + p.a_stride);
@@ -498,6 +522,7 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
                 mbar_arrive(&h_split[hb]);
                 mbar_arrive(&s_free[sb]);
             }
+            if (wt == 0) stamp(p, 2, it, 2);
         }
     } else {
         // -------------------------------------------------- epilogue --------------------------------------------------
@@ -508,6 +533,7 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
             mbar_wait(&acc_full[ab], ((uint32_t)it >> 1) & 1u);
+            if (threadIdx.x == 192) stamp(p, 3, it, 0);
             tc_fence_after();
             const int n = tile / per_img, tt = tile - n * per_img;
             const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
@@ -543,6 +569,7 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
                     }
                 }
             }
+            if (threadIdx.x == 192) stamp(p, 3, it, 1);
         }
     }
     __syncthreads();
@@ -550,6 +577,8 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
     }
 }
+
+long long *g_conv5h_trace = nullptr;
 
 PFN_cuTensorMapEncodeTiled_v12000 encoder() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
@@ -654,6 +683,13 @@ int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float 
     return pmb200_internal_launch_status("conv2d_tc5");
 }
 
+// Debugging aid: device buffer of 4 roles x 16 tiles x 4 events (256 int64) that the next K-D5h launches stamp with clock64
+// for CTA 0 (producer / MMA issuer / split / epilogue); nullptr switches it off.  Not part of the reference-facing surface.
+int pmb200_debug_conv5h_trace(long long *device_buffer_256) {
+    g_conv5h_trace = device_buffer_256;
+    return 0;
+}
+
 // Stride-1 form (K-D5h): one halo tile per 8 x 16 output tile, filter taps as shifted views.  Filter image:
 // [tap][Cin/4 chunks][hi rows Npad | lo rows Npad][4 floats] (ops.pack_conv_filter_tc5h), same float count as the per-tap form.
 int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const float *bias, float *y_nhwc, int N, int H, int W, int Cin,
@@ -674,6 +710,7 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
     p.wpack = filter_tc5h; p.bias = bias; p.y = y_nhwc;
     p.N = N; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.Npad = npad_of(Cout);
     p.KS = KS; p.pad = pad; p.dil = dil; p.relu = relu; p.ycs = y_channel_stride; p.yco = y_channel_offset;
+    p.trace = g_conv5h_trace;
     p.tiles_x = (Wo + kHTW - 1) / kHTW; p.tiles_y = (Ho + kHTH - 1) / kHTH;
     const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
     if (tiles > 0x7fffffffLL) return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: too many tiles");

@@ -55,7 +55,8 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128) rate_kernel(int N, int M, int nacc, int reps, int swz, long long *out) {
+__global__ void __launch_bounds__(128) rate_kernel(int N, int M, int nacc, int reps, int swz, long long *out, int a_sbo = 128, int a_lbo = 2048,
+                                                   int a_shift = 0) {
     extern __shared__ unsigned char raw[];
     unsigned char *smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int M, int nacc, int r
     const uint32_t idesc = (1u << 4) | kind_bits | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     if (threadIdx.x == 0) {
         // plain: core matrices 8 rows x 16 B; K-adjacent core matrix 128*16 B away (A) / N*16 B away (B); next 8 rows 128 B away
-        const uint64_t da = swz ? desc_sw128(smem_u32(A)) : desc_plain(smem_u32(A), 128 * 16, 128);
+        const uint64_t da = swz ? desc_sw128(smem_u32(A)) : desc_plain(smem_u32(A) + (uint32_t)a_shift, (uint32_t)a_lbo, (uint32_t)a_sbo);
         const uint64_t db = swz ? desc_sw128(smem_u32(B)) : desc_plain(smem_u32(B), (uint32_t)N * 16, 128);
         uint32_t par = 0;
         for (int warm = 0; warm < 2; ++warm) {
@@ -135,6 +136,18 @@ int main() {
                         first = false;
                         if (e != cudaSuccess) { printf("]}\n"); return 1; }
                     }
+    // the K-D5h A operand: core matrices (8 pixels x 16 B) of a halo tile -- row groups hcols*16 = 160 B apart (not 128 B
+    // aligned), planes 2880 B apart, tap shifts in 16 B steps
+    for (int N : {32, 64, 128})
+        for (int geo = 0; geo < 5; ++geo) {
+            const int sbo = geo == 0 ? 128 : (geo == 3 ? 256 : 160), lbo = geo == 0 ? 2048 : (geo == 3 ? 4096 : 2880), shift = geo == 2 ? 176 : (geo == 4 ? 64 : 0);
+            rate_kernel<0><<<148, 128, smem>>>(N, 128, 1, reps, 0, out, sbo, lbo, shift);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long h[2] = {0, 0};
+            cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+            printf(",\n {\"kind\": \"tf32 K8\", \"a_operand\": {\"sbo\": %d, \"lbo\": %d, \"start_shift\": %d}, \"ctas\": 148, \"M\": 128, \"N\": %d, "
+                   "\"complete_cycles_per_mma\": %.1f, \"err\": \"%s\"}", sbo, lbo, shift, N, (double)h[1] / reps, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
     printf("]}\n");
     return 0;
 }
