@@ -57,11 +57,12 @@ int pmb200_set_tuning(const char *key, int value);
  * Replaces, for the FLOP-bound layers in the fp32-accurate mode, the nn.Conv2d calls of reference models/net.py:9-70 (FeatureNet
  * conv2..10), models/patchmatch.py:288-311 (stage-2/3 offset convs), models/net.py:73-122 (Refinement).
  *   x_nhwc      [N,H,W,Cin] fp32, 16-byte aligned, Cin in {8,16,32,64}
- *   filter_tc5  pmb200_conv2d_tc5_filter_floats(Cin,Cout,KS) floats: [tap ky*KS+kx][hi, lo][Cin/32 blocks (1 if Cin <= 32)]
- *               [Npad = Cout rounded up to 16 rows][min(Cin,32) channels], every [Npad][row bytes] tile stored in the tensor
- *               core's K-major shared-memory swizzle for that row size (16-byte chunk j of row r sits at chunk
+ *   filter_tc5  pmb200_conv2d_tc5_filter_floats(Cin,Cout,KS) floats: [tap ky*KS+kx][Cin/32 blocks (1 if Cin <= 32)]
+ *               [2 Npad rows: w_hi rows then w_lo rows, Npad = Cout rounded up to 16][min(Cin,32) channels]; every
+ *               [2 Npad][row bytes] tile is ONE K-major tcgen05 operand (its first Npad rows double as the N = Npad operand)
+ *               stored in the tensor core's shared-memory swizzle for that row size (16-byte chunk j of row r sits at chunk
  *               j ^ (r % 8) for 128-byte rows, j ^ ((r / 2) % 4) for 64-byte rows, j ^ ((r / 4) % 2) for 32-byte rows);
- *               hi = weight rounded to TF32, lo = (weight - hi) rounded to TF32; rows >= Cout are zero
+ *               w_hi = weight rounded to TF32, w_lo = (weight - w_hi) rounded to TF32; rows >= Cout of each half are zero
  *   y_nhwc      [N,Ho,Wo,y_channel_stride]; channels y_channel_offset .. +Cout are written
  * Ho = (H + 2 pad - dil (KS-1) - 1) / stride + 1.  bias may be NULL.  relu != 0 applies max(.,0).
  * pmb200_conv2d_tc5_supported: 1 when (Cin, Cout, KS, stride) is served (KS in {1,3,5}, stride in {1,2}, Cout <= 64). */

@@ -38,7 +38,7 @@ constexpr int kTW = 16, kTH = 8;  // output tile: 128 pixels = the M of one UMMA
 constexpr int kThreads = 320;
 
 struct Conv5Params {
-    const float *wpack;  // [tap][hi|lo][kblock][Npad rows][RB bytes], swizzled image
+    const float *wpack;  // [tap][kblock][w_hi rows Npad | w_lo rows Npad][RB bytes], swizzled image
     const float *bias;
     float *y;
     int N, H, W, Ho, Wo, Cin, Cout, Npad, KS, S, pad, dil, relu, ycs, yco;
@@ -49,7 +49,7 @@ struct Conv5Params {
     int a_bytes;   // 128 * RB * KB
     int w_bytes;   // Npad * RB * KB (one of hi / lo)
     int stage_bytes;
-    uint32_t idesc;
+    uint32_t idesc, idesc2;  // N = Npad / N = 2 Npad
     uint32_t layout_type;  // UMMA smem-descriptor swizzle code: 2 = 128B, 4 = 64B, 6 = 32B
     uint32_t tmem_cols;
 };
@@ -106,16 +106,9 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// K-major operand tile in the 32/64/128-byte swizzle: rows of RB bytes, 8-row groups 8*RB apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t RB, uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3fff);              // start address
-    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major): 1
-    d |= (uint64_t)(((8 * RB) >> 4) & 0x3fff) << 32;    // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
+// Shared-memory matrix descriptor of a K-major operand tile in the 32/64/128-byte swizzle (rows of RB bytes, 8-row groups
+// 8*RB apart): bits 0-13 start address >> 4, 16-29 leading byte offset (unused when swizzled: 1), 32-45 stride byte offset
+// (8*RB) >> 4, 46 version (Blackwell), 61-63 swizzle code (2 = 128B, 4 = 64B, 6 = 32B).  The kernels build it as two words.
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -191,34 +184,42 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
         }
     } else if (warp == 1) {
         // ------------------------------------------------- MMA issuer -------------------------------------------------
+        // Whole warp on warp-uniform values, tcgen05 instructions from the elected lane (see conv5h_kernel); 2 MMAs per K
+        // slice: a_hi x [w_hi | w_lo] (N = 2 Npad, columns [0, 2 Npad)) and a_lo x w_hi (N = Npad, columns [0, Npad)).
+        const bool leader = elect_one();
         int s = 0, it = 0;
         uint32_t par = 0;
-        const int kslices = p.Cin / 8;
         const int per_row = p.RB / 32;  // 8-channel slices per operand row
+        // descriptor words: lo = start address >> 4 | LBO field 1, hi = SBO (8 rows) >> 4 | version | swizzle code << 29
+        const uint32_t hiword = ((8u * (uint32_t)p.RB) >> 4) | (1u << 14) | (p.layout_type << 29);
+        const uint32_t stage_u32 = smem_u32(stage0);
+        const uint32_t a_kb16 = (128u * (uint32_t)p.RB) >> 4, w_kb16 = (2u * (uint32_t)p.Npad * (uint32_t)p.RB) >> 4;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;                                  // accumulator buffer of this tile
-            const uint32_t tacc = tmem + (uint32_t)(ab * p.Npad);
+            const uint32_t tacc = tmem + (uint32_t)(ab * 2 * p.Npad);
             mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);  // the epilogue of tile it-2 has drained this buffer
             tc_fence_after();
+            uint32_t first = 0;
             for (int t = 0; t < T; ++t) {
                 mbar_wait(&split[s], par);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_hi = smem_u32(stage0 + (size_t)s * p.stage_bytes);
-                    const uint32_t a_lo = a_hi + p.a_bytes, w_hi = a_lo + p.a_bytes, w_lo = w_hi + p.w_bytes;
-                    for (int k = 0; k < kslices; ++k) {
-                        const uint32_t kb = k / per_row, kin = (k % per_row) * 32;
-                        const uint32_t ao = kb * 128 * p.RB + kin, wo = kb * p.Npad * p.RB + kin;
-                        const uint64_t dah = make_desc(a_hi + ao, p.RB, p.layout_type), dal = make_desc(a_lo + ao, p.RB, p.layout_type);
-                        const uint64_t dwh = make_desc(w_hi + wo, p.RB, p.layout_type), dwl = make_desc(w_lo + wo, p.RB, p.layout_type);
-                        tc_mma_tf32(tacc, dal, dwh, p.idesc, (t | k) != 0);  // small terms first
-                        tc_mma_tf32(tacc, dah, dwl, p.idesc, 1);
-                        tc_mma_tf32(tacc, dah, dwh, p.idesc, 1);
+                const uint32_t a_hi = ((stage_u32 + (uint32_t)(s * p.stage_bytes)) >> 4) | (1u << 16);
+                const uint32_t a_lo = a_hi + ((uint32_t)p.a_bytes >> 4), w0 = a_lo + ((uint32_t)p.a_bytes >> 4);
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    for (int kin = 0; kin < per_row; ++kin) {
+                        const uint32_t ao = (uint32_t)kb * a_kb16 + 2u * kin, wo = (uint32_t)kb * w_kb16 + 2u * kin;  // 32 bytes per slice
+                        const uint64_t dw = ((uint64_t)hiword << 32) | (w0 + wo);
+                        if (leader) {
+                            tc_mma_tf32(tacc, ((uint64_t)hiword << 32) | (a_hi + ao), dw, p.idesc2, first);
+                            tc_mma_tf32(tacc, ((uint64_t)hiword << 32) | (a_lo + ao), dw, p.idesc, 1);
+                        }
+                        first = 1;
                     }
+                }
+                if (leader) {
                     tc_commit(&empty[s]);                        // stage free once these MMAs have read it
                     if (t == T - 1) tc_commit(&acc_full[ab]);    // accumulator complete
                 }
-                __syncwarp();
                 if (++s == p.stages) { s = 0; par ^= 1u; }
             }
         }
@@ -269,8 +270,10 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
             const bool inside = oy < p.Ho && ox < p.Wo;
             float *dst = p.y + (((size_t)n * p.Ho + (inside ? oy : 0)) * p.Wo + (inside ? ox : 0)) * p.ycs + p.yco;
             for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * p.Npad + c0), v);
+                float v[16], u[16];
+                const uint32_t tcol = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 2 * p.Npad + c0);
+                tmem_ld16(tcol, v);                        // a_hi.w_hi + a_lo.w_hi
+                tmem_ld16(tcol + (uint32_t)p.Npad, u);     // a_hi.w_lo
                 if (c0 + 16 >= p.Npad) {  // last read of the accumulator: hand it back before the stores
                     tc_fence_before();
                     __syncwarp();
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int co = c0 + i;
-                    float o = v[i] + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.0f);
+                    float o = (v[i] + u[i]) + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.0f);
                     v[i] = p.relu ? fmaxf(o, 0.0f) : o;
                 }
 #pragma unroll
@@ -354,6 +357,19 @@ __device__ __forceinline__ void stamp(const Conv5hParams &p, int role, int it, i
 
 // Operands of this kernel are no-swizzle K-major: core matrices of 8 rows x 16 bytes; descriptor LBO = distance of the
 // K-adjacent core matrix, SBO = distance of the next 8-row group, version bit 46, layout type 0.
+// the MMAs of one filter tap: per 8-channel slice a_hi x [w_hi | w_lo] (N = 2 Npad) and a_lo x w_hi (N = Npad)
+template <int KSL>
+__device__ __forceinline__ void issue_tap(bool leader, uint32_t tacc, uint32_t ah, uint32_t al, uint32_t w, uint32_t a_kstep, uint32_t w_kstep,
+                                          uint32_t a_hiword, uint32_t w_hiword, uint32_t idesc, uint32_t idesc2, uint32_t first) {
+    if (!leader) return;
+#pragma unroll
+    for (int k = 0; k < KSL; ++k) {
+        const uint64_t dw = ((uint64_t)w_hiword << 32) | (w + k * w_kstep);
+        tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | (ah + k * a_kstep), dw, idesc2, k == 0 ? first : 1u);
+        tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | (al + k * a_kstep), dw, idesc, 1);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -462,19 +478,20 @@ __global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, 
             uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrites the accumulator)
             for (int ky = 0; ky < p.KS; ++ky) {
                 for (int kx = 0; kx < p.KS; ++kx) {
-                    mbar_wait(&w_full[s], wpar);
-                    tc_fence_after();
-                    const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil);
-                    uint32_t ah = ahi_lo + shift, al = alo_lo + shift;
-                    uint32_t w = ((ring_u32 + (uint32_t)(s * 2 * p.w_bytes)) >> 4) | (w_lbo16 << 16);
-                    for (int k = 0; k < kslices; ++k, ah += a_kstep, al += a_kstep, w += w_kstep) {
-                        const uint64_t dw = ((uint64_t)w_hiword << 32) | w;
-                        if (leader) {
-                            tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | ah, dw, p.idesc2, first);  // a_hi x [w_hi | w_lo]
-                            tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | al, dw, p.idesc, 1);       // a_lo x w_hi
-                        }
-                        first = 1;
+                    if (!p.w_resident || it == 0) {  // a resident filter is waited for once, during the first tile
+                        mbar_wait(&w_full[s], wpar);
+                        tc_fence_after();
                     }
+                    const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil);
+                    const uint32_t ah = ahi_lo + shift, al = alo_lo + shift;
+                    const uint32_t w = ((ring_u32 + (uint32_t)(s * 2 * p.w_bytes)) >> 4) | (w_lbo16 << 16);
+                    switch (kslices) {  // unrolled: the per-slice descriptor steps become immediates of uniform adds
+                    case 1: issue_tap<1>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
+                    case 2: issue_tap<2>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
+                    case 4: issue_tap<4>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
+                    default: issue_tap<8>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
+                    }
+                    first = 1;
                     if (p.w_resident) {
                         if (++s == p.wstages) s = 0;  // phase 0 of every w_full completed once and stays complete
                     } else {
@@ -604,7 +621,7 @@ int pmb200_conv2d_tc5_supported(int Cin, int Cout, int KS, int stride) {
     return (cin_ok && Cout >= 1 && Cout <= 64 && (KS == 1 || KS == 3 || KS == 5) && (stride == 1 || stride == 2)) ? 1 : 0;
 }
 
-// floats of the packed filter: [tap][hi|lo][Cin/32 blocks][Npad rows][min(Cin,32)] (ops.pack_conv_filter_tc5)
+// floats of the packed filter: [tap][Cin/32 blocks][hi rows Npad | lo rows Npad][min(Cin,32)] (ops.pack_conv_filter_tc5)
 int pmb200_conv2d_tc5_filter_floats(int Cin, int Cout, int KS) {
     if (!pmb200_conv2d_tc5_supported(Cin, Cout, KS, 1)) return -1;
     return KS * KS * 2 * npad_of(Cout) * Cin;
@@ -643,7 +660,8 @@ int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float 
     p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
     p.layout_type = p.RB == 128 ? 2u : (p.RB == 64 ? 4u : 6u);
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);  // F32 += TF32 . TF32, K-major both
-    p.tmem_cols = 2 * p.Npad <= 32 ? 32u : (2 * p.Npad <= 64 ? 64u : 128u);  // two accumulators of Npad fp32 columns
+    p.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+    p.tmem_cols = 4 * p.Npad <= 64 ? 64u : (4 * p.Npad <= 128 ? 128u : 256u);  // two accumulators of 2 Npad fp32 columns
 
     int dev = 0, sms = 0, smem_optin = 0;
     cudaGetDevice(&dev);

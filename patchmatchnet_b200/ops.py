@@ -247,7 +247,7 @@ TC5_ALL = os.environ.get("PMB200_TC5", "1") == "all"
 # output2 27 -> 23, output3 77 -> 53, stage-3 offset convs 39 / 40 -> 17 / 18, stage-2 26 / 27 -> 20 / 22.  It loses where
 # Cin = 8 (conv1 154 vs 70: a K slice per tap, the instruction count is the cost) and on stage 1's 16 -> 18 d6 conv (37 vs 32).
 # PMB200_TC5H=all: every stride-1 layer the kernel takes (A/B measurements); =0: none.
-TC5H_LAYERS = {(16, 16, 3, 1), (32, 32, 3, 1), (64, 64, 3, 1), (64, 32, 1, 1), (64, 16, 1, 1), (32, 64, 1, 1), (16, 64, 1, 1),
+TC5H_LAYERS = {(16, 16, 3, 1), (32, 32, 3, 1), (64, 64, 3, 1), (64, 32, 1, 1), (64, 16, 1, 1),
                (64, 32, 3, 1), (64, 18, 3, 1), (32, 16, 3, 1), (32, 18, 3, 1)}
 TC5H_ALL = os.environ.get("PMB200_TC5H", "1") == "all"
 TC5H_OFF = os.environ.get("PMB200_TC5H", "1") == "0"
@@ -279,9 +279,9 @@ def pack_conv_filter_tc5_for(weight: Tensor, mode: str) -> Tensor:
 
 def pack_conv_filter_tc5(weight: Tensor) -> Tensor:
     """Conv filter [Cout,Cin,KS,KS] -> the shared-memory image `pmb200_conv2d_tc5` copies per tap (include/patchmatch_b200.h):
-    [tap][hi, lo][Cin/32 blocks][Npad rows][min(Cin,32) channels] with every [Npad][row] tile in the K-major swizzle of the
-    tensor core for its row size; hi = TF32-rounded weight, lo = TF32-rounded remainder.  Pure layout / rounding work on
-    the weight's device (CPU-testable)."""
+    [tap][Cin/32 blocks][2 Npad rows][min(Cin,32) channels], rows 0..Npad-1 = w_hi (TF32-rounded weight), Npad..2Npad-1 = w_lo
+    (TF32-rounded remainder) -- ONE K-major tcgen05 operand of N = 2 Npad whose first Npad rows double as the N = Npad operand --
+    in the swizzle of the tensor core for its row size.  Pure layout / rounding work on the weight's device (CPU-testable)."""
     if weight.dim() != 4 or weight.shape[2] != weight.shape[3]:
         raise RuntimeError(f"pack_conv_filter_tc5: expected [Cout,Cin,KS,KS], got {tuple(weight.shape)}")
     w = weight.detach().float()
@@ -294,16 +294,16 @@ def pack_conv_filter_tc5(weight: Tensor) -> Tensor:
     hi = _tf32_round(w)
     lo = _tf32_round(w - hi)
     both = torch.stack((hi, lo))  # [2, Cout, Cin, KS, KS]
-    t = torch.zeros((ks * ks, 2, kb, npad, cblk), dtype=torch.float32, device=w.device)
-    t[:, :, :, :cout] = both.permute(3, 4, 0, 1, 2).reshape(ks * ks, 2, cout, kb, cblk).permute(0, 1, 3, 2, 4)
-    # swizzle: 16-byte chunk j of row r moves to chunk j ^ f(r)
+    t = torch.zeros((ks * ks, kb, 2, npad, cblk), dtype=torch.float32, device=w.device)
+    t[:, :, :, :cout] = both.permute(3, 4, 0, 1, 2).reshape(ks * ks, 2, cout, kb, cblk).permute(0, 3, 1, 2, 4)
+    # swizzle: 16-byte chunk j of row r moves to chunk j ^ f(r); Npad is a multiple of 8, so f(Npad + r) = f(r)
     chunks = cblk // 4
     rows = torch.arange(npad, device=w.device)
     f = {8: rows % 8, 4: (rows // 2) % 4, 2: (rows // 4) % 2}[chunks]
     j = torch.arange(chunks, device=w.device)
     src = (j.view(1, chunks) ^ f.view(npad, 1))  # physical chunk p of row r holds logical chunk p ^ f(r)
-    t = t.view(ks * ks, 2, kb, npad, chunks, 4)
-    idx = src.view(1, 1, 1, npad, chunks, 1).expand(ks * ks, 2, kb, npad, chunks, 4)
+    t = t.view(ks * ks, kb, 2, npad, chunks, 4)
+    idx = src.view(1, 1, 1, npad, chunks, 1).expand(ks * ks, kb, 2, npad, chunks, 4)
     return torch.gather(t, 4, idx).contiguous().view(-1)
 
 

@@ -211,7 +211,7 @@ def test_tc5_filter_image_matches_the_address_swizzle():
         hi = ops._tf32_round(w)
         lo = ops._tf32_round(w - hi)
         assert float((hi + lo - w).abs().max()) <= 2.0 ** -21 * float(w.abs().max())
-        ref = torch.zeros(ks * ks, 2, kb, npad * RB // 4)
+        ref = torch.zeros(ks * ks, kb, 2, npad * RB // 4)
         mask = {128: 0x70, 64: 0x30, 32: 0x10}[RB]
         for t in range(ks * ks):
             ky, kx = divmod(t, ks)
@@ -221,7 +221,7 @@ def test_tc5_filter_image_matches_the_address_swizzle():
                     for n in range(cout):
                         for c in range(cblk):
                             off = n * RB + c * 4
-                            ref[t, si, k, (off ^ ((off >> 3) & mask)) // 4] = blk[n, c]
+                            ref[t, k, si, (off ^ ((off >> 3) & mask)) // 4] = blk[n, c]
         assert torch.equal(got, ref.view(-1)), (cout, cin, ks)
     with pytest.raises(RuntimeError):
         ops.pack_conv_filter_tc5(torch.zeros(8, 3, 3, 3))
