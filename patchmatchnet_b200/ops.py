@@ -237,18 +237,18 @@ TC5_CONVS = os.environ.get("PMB200_TC5", "1") != "0"
 
 
 # (Cin, Cout, KS, stride) of the layers a tcgen05 form beats the mma.sync kernel's 3xTF32 mode on (cold us per launch at the
-# 640x512 sizes, tools/convbench.py, profiles/r2_run11_convbench.json).  Per-tap form K-D5 (the only one for stride 2):
-# conv5 73 vs 93; it loses on conv2 (152 vs 90) and ties on conv8 (66 vs 63).  PMB200_TC5=all takes every supported layer
-# (A/B measurements), PMB200_TC5=0 none.
-TC5_LAYERS = {(16, 32, 5, 2)}
+# 640x512 sizes, tools/convbench.py, profiles/r2_run16_convbench.json).  Per-tap form K-D5 (the only one for stride 2):
+# conv5 70 vs 93, conv8 50 vs 63; it loses on conv2 (137 vs 91: Cin = 8, one K slice per tap).  PMB200_TC5=all takes every
+# supported layer (A/B measurements), PMB200_TC5=0 none.
+TC5_LAYERS = {(16, 32, 5, 2), (32, 64, 5, 2)}
 TC5_ALL = os.environ.get("PMB200_TC5", "1") == "all"
 # Stride-1 layers served by the halo-tile form K-D5h (one TMA box + one split per output tile, taps as shifted descriptors,
-# [w_hi | w_lo] as one operand): mma.sync 3xTF32 -> K-D5h, cold us: conv3/4 58 -> 53, conv6/7 66 -> 39, conv9/10 47 -> 29,
-# output2 27 -> 23, output3 77 -> 53, stage-3 offset convs 39 / 40 -> 17 / 18, stage-2 26 / 27 -> 20 / 22.  It loses where
-# Cin = 8 (conv1 154 vs 70: a K slice per tap, the instruction count is the cost) and on stage 1's 16 -> 18 d6 conv (37 vs 32).
+# [w_hi | w_lo] as one operand): mma.sync 3xTF32 -> K-D5h, cold us: conv3/4 58 -> 36, conv6/7 67 -> 29, conv9/10 47 -> 29,
+# output2 27 -> 25, output3 77 -> 44, stage-3 offset convs 39 / 40 -> 17 / 18, stage-2 25 / 27 -> 18 / 21, stage-1 32 -> 30.
+# It loses where Cin = 8 (conv1 93 vs 70: one K slice per tap, the instruction count is the cost) and ties on Refinement.
 # PMB200_TC5H=all: every stride-1 layer the kernel takes (A/B measurements); =0: none.
 TC5H_LAYERS = {(16, 16, 3, 1), (32, 32, 3, 1), (64, 64, 3, 1), (64, 32, 1, 1), (64, 16, 1, 1),
-               (64, 32, 3, 1), (64, 18, 3, 1), (32, 16, 3, 1), (32, 18, 3, 1)}
+               (64, 32, 3, 1), (64, 18, 3, 1), (32, 16, 3, 1), (32, 18, 3, 1), (16, 18, 3, 1)}
 TC5H_ALL = os.environ.get("PMB200_TC5H", "1") == "all"
 TC5H_OFF = os.environ.get("PMB200_TC5H", "1") == "0"
 
