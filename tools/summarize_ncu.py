@@ -1,6 +1,8 @@
 """Summarise an `ncu --set full` report (.ncu-rep) into a markdown table + a traffic JSON for bench.py.
 
-    python tools/summarize_ncu.py gpurun_out/native_full.ncu-rep "title" profiles/rX_ncu.md [profiles/warp_corr_traffic.json]
+    python tools/summarize_ncu.py gpurun_out/native_full.ncu-rep "title" profiles/rX_ncu.md [profiles/r2_warp_corr_traffic.json]
+
+The traffic JSON carries `mean_dram_bytes_per_launch` over the K-A (warp_corr*) launches of the capture: bench.py's `roofline.traffic`.
 """
 import csv
 import io
@@ -70,7 +72,10 @@ def main():
         traffic.setdefault(name, []).append(round((rd + wr) * 1e6))
     open(out_md, "w").write("\n".join(lines) + "\n")
     if traffic_json:
-        json.dump(traffic, open(traffic_json, "w"), indent=1)
+        ka = [b for name, launches in traffic.items() if "warp_corr" in name for b in launches]
+        out = {"capture": title, "mean_dram_bytes_per_launch": (sum(ka) / len(ka)) if ka else None, "warp_corr_launches": len(ka),
+               "dram_bytes_per_launch_by_kernel": traffic}
+        json.dump(out, open(traffic_json, "w"), indent=1)
     print("\n".join(lines[:12]))
 
 
