@@ -31,6 +31,8 @@
 //
 // tcgen05/TMEM is deliberately not used here: with N <= 64 and K <= 64 per tap the operands are far below the
 // 128xNx8 UMMA tile economy, and the layers are bound by activation traffic, not by MMA issue.
+#include <atomic>
+
 #if !defined(PM_EMU)  // host emulation build (tests/warp_emu.h) brings its own CUDA vocabulary
 #include <cuda_runtime.h>
 #endif
@@ -492,19 +494,22 @@ template <int KCIN, int NT, int MT, int PREC, bool WREG, int NSPLIT>
 int launch_conv(const ConvParams &p, const LaunchPlan &plan, cudaStream_t st) {
     auto kern = conv_nhwc_mma_kernel<KCIN, NT, MT, PREC, WREG, NSPLIT>;
     if (plan.smem > 48 * 1024) {
-        // opt in to > 48 KB of dynamic shared memory once per (instantiation, device); the high-water mark is only ever
-        // raised, so concurrent callers (one host thread per GPU) at worst repeat an idempotent call
-        static int granted[64] = {0};
+        // opt in to the device's maximum dynamic shared memory once per (instantiation, device): always the same value, so
+        // concurrent callers (one host thread per GPU, several streams) can only repeat an idempotent call
+        static std::atomic<unsigned long long> optin_done{0};
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || granted[dev] < (int)plan.smem) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        if (dev < 0 || dev >= 64 || !((optin_done.load(std::memory_order_relaxed) >> dev) & 1ull)) {
+            int optin = 0;
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            if (optin < (int)plan.smem) optin = (int)plan.smem;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (e != cudaSuccess) {
                 char msg[200];
-                snprintf(msg, sizeof(msg), "conv2d_nhwc: cudaFuncSetAttribute(%zu B): %s", plan.smem, cudaGetErrorString(e));
+                snprintf(msg, sizeof(msg), "conv2d_nhwc: cudaFuncSetAttribute(%d B): %s", optin, cudaGetErrorString(e));
                 return pmb200_internal_fail((int)e, msg);
             }
-            if (dev >= 0 && dev < 64) granted[dev] = (int)plan.smem;
+            if (dev >= 0 && dev < 64) optin_done.fetch_or(1ull << dev, std::memory_order_relaxed);
         }
     }
 #if defined(PM_EMU)

@@ -27,6 +27,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/patchmatch_b200.h"
 
 extern "C" int pmb200_internal_fail(int code, const char *msg);
@@ -609,6 +611,20 @@ PFN_cuTensorMapEncodeTiled_v12000 encoder() {
     return fn;
 }
 
+// Opt a kernel in to the device's maximum dynamic shared memory, once per (kernel, device).  Always the SAME value, so
+// concurrent host threads (one per GPU, or several streams of one GPU) can only repeat an idempotent call -- a per-thread or
+// per-size high-water mark let one thread lower the attribute under another thread's larger launch.
+template <typename Kern>
+bool optin_max_smem(Kern kern, std::atomic<unsigned long long> &done, int dev, int smem_optin) {
+    if (dev >= 0 && dev < 64 && ((done.load(std::memory_order_relaxed) >> dev) & 1ull)) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_relaxed);
+    return true;
+}
+
 int npad_of(int cout) { return (cout + 15) / 16 * 16; }
 
 }  // namespace
@@ -678,14 +694,9 @@ int pmb200_conv2d_tc5(const float *x_nhwc, const float *filter_tc5, const float 
     if (stages < 2) return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5: a ring of two stages does not fit in shared memory");
     p.stages = stages;
     const int smem = 1024 + stages * p.stage_bytes + 1024;  // + slack for the 1024-byte alignment of the dynamic segment
-    static thread_local int attr_smem = 0;
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(conv5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            cudaGetLastError();
-            return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5: shared-memory opt-in failed");
-        }
-        attr_smem = smem;
-    }
+    static std::atomic<unsigned long long> optin_done{0};
+    if (!optin_max_smem(conv5_kernel, optin_done, dev, smem_optin))
+        return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5: shared-memory opt-in failed");
     CUtensorMap xmap;
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
@@ -771,14 +782,9 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
     if (2 * (fixed + wst * 2 * p.w_bytes + 1024) <= smem_optin + 1024) ctas = 2;
     p.wstages = wst;
     const int smem = fixed + wst * 2 * p.w_bytes;
-    static thread_local int attr_smem = 0;
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(conv5h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            cudaGetLastError();
-            return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: shared-memory opt-in failed");
-        }
-        attr_smem = smem;
-    }
+    static std::atomic<unsigned long long> optin_done{0};
+    if (!optin_max_smem(conv5h_kernel, optin_done, dev, smem_optin))
+        return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: shared-memory opt-in failed");
     CUtensorMap xmap;
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};

@@ -20,6 +20,8 @@
 // contiguous C*4-byte read split over C/8 lanes as 2 x 16-byte loads (a full 128-byte line per pixel at C=32, two at
 // C=64).  PatchMatch hypotheses of one pixel are sorted and clustered, so consecutive hypotheses mostly land in the
 // same source cell; every generation of K-A exploits that differently (see the comments above each kernel).
+#include <atomic>
+
 #if !defined(PM_EMU)  // host emulation build (tests/warp_emu.h) brings its own CUDA vocabulary
 #include <cuda_runtime.h>
 #endif
@@ -1258,13 +1260,16 @@ bool launch_wc4_nw(const WarpCorrParams &p, const MlpParams &m, float *sims_out,
     if (cap > 1024) cap = 1024;
     if (cap < 16) return false;
     const int smem = L::fixed_bytes + stages * cap * C * 4;
-    static thread_local int attr_smem = 0;  // per instantiation and host thread
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    // opt in once per (instantiation, device) to the device maximum: the same value from every host thread
+    static std::atomic<unsigned long long> optin_done{0};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev < 0 || cur_dev >= 64 || !((optin_done.load(std::memory_order_relaxed) >> cur_dev) & 1ull)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        attr_smem = smem;
+        if (cur_dev >= 0 && cur_dev < 64) optin_done.fetch_or(1ull << cur_dev, std::memory_order_relaxed);
     }
     static thread_local int occ_smem = -1, occ = 0;
     if (occ_smem != smem) {
