@@ -82,6 +82,17 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
 int pmb200_debug_conv5h_trace(long long *device_buffer_256);
 
 /* ------------------------------------------------------------------------------------
+ * K-S: the two full-resolution layers of FeatureNet in one launch, exact fp32 (plain FFMA, weights in the constant bank):
+ *     y = relu(conv1(relu(conv0(x))))   conv0 3 -> 8, conv1 8 -> 8, both 3x3 / pad 1, BatchNorm folded into weight and bias.
+ * Replaces `self.conv1(self.conv0(x))` at reference models/net.py:44 (layers :18-19) in eval mode.
+ *   x_nchw   device [N,3,H,W] contiguous (the caller's image planes are read in place: no layout conversion)
+ *   y_nhwc   device [N,H,W,8], 16-byte aligned
+ *   host_w0  HOST memory [8][3][3][3] (PyTorch layout), host_b0 [8]; host_w1 HOST memory [8][8][3][3], host_b1 [8]:
+ *            copied into the kernel parameter block at launch (so a captured CUDA graph keeps the values it was captured with). */
+int pmb200_conv_stem(const float *x_nchw, const float *host_w0, const float *host_b0, const float *host_w1, const float *host_b1,
+                     float *y_nhwc, int N, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Relative projections for every (source view, batch element):
  *     P = src_proj . inverse(ref_proj);  rt = [P[0,0..2], P[1,0..2], P[2,0..2], P[0..2,3]]
  * Replaces torch.matmul(src_proj, torch.inverse(ref_proj)) at models/module.py:148-150,

@@ -208,6 +208,7 @@ class FeatureNet(nn.Module):
         self.output3 = nn.Conv2d(64, 16, 1, bias=False)
         self._packed = {n: _PackedConv() for n in ("output1", "inner1", "inner2", "output2", "output3")}
         self._composed_cache = _FoldCache()
+        self._stem_cache = _FoldCache()
         self.fuse_top_down = True  # eval mode on CUDA: composed 1x1 heads (see composed_heads); False = layer by layer
 
     def _plain(self, name: str, x: Tensor) -> Tensor:
@@ -259,8 +260,33 @@ class FeatureNet(nn.Module):
         out[1] = ops.conv2d_nhwc(half, w["l1"], w["c1"], 16, 1, add_up2x=t)
         return out
 
+    def stem_weights(self):
+        """BatchNorm-folded (w0, b0, w1, b1) of conv0 / conv1 as HOST tensors: K-S carries them in its kernel parameter block."""
+        srcs = []
+        for m in (self.conv0, self.conv1):
+            srcs += [m.conv.weight, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var]
+
+        def make():
+            w0, b0 = _fold_bn(self.conv0.conv.weight, self.conv0.bn)
+            w1, b1 = _fold_bn(self.conv1.conv.weight, self.conv1.bn)
+            return tuple(t.detach().float().cpu().contiguous() for t in (w0, b0, w1, b1))
+
+        return self._stem_cache.get(srcs, make)
+
+    def _stem(self, x: Tensor) -> Tensor:
+        """conv0 -> conv1.  Eval mode on CUDA in the fp32-accurate mode: ONE exact-fp32 launch reading the NCHW image planes in
+        place (K-S, csrc/pm_stem.cu); otherwise the two layers one after the other."""
+        from . import ops
+
+        if (not self.training and _native_convs(x) and ops.STEM_FUSED and ops.conv_precision() == 3 and x.dim() == 4 and x.shape[1] == 3
+                and x.dtype == torch.float32):
+            return ops.conv_stem(x, *self.stem_weights())
+        if _fast(x) and not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        return self._trunk(x, 0, 1)
+
     def forward(self, x: Tensor) -> Dict[int, Tensor]:
-        half = self._trunk(self._trunk(x, 0, 1), 2, 4)
+        half = self._trunk(self._stem(x), 2, 4)
         quarter = self._trunk(half, 5, 7)
         eighth = self._trunk(quarter, 8, 10)
         if not self.training and _native_convs(x) and self.fuse_top_down:
@@ -441,9 +467,10 @@ class PatchmatchNet(nn.Module):
             x = torch.as_strided(first, (n * b,) + tuple(first.shape[1:]), first.stride())  # views of one buffer: no copy
         else:
             x = torch.cat(images, dim=0)
-        if _fast(x):  # cuDNN NHWC kernels; the pyramid then comes out channels-last, which is the layout
-            x = x.contiguous(memory_format=torch.channels_last)  # the fused PatchMatch kernels read in place
-            self._ref_image_cl = x[:b]  # the reference view, already channels-last: Refinement reads it without a second conversion
+        if _fast(x):  # the pyramid comes out channels-last, the layout the fused PatchMatch kernels read in place.  FeatureNet's
+            # first layers read the NCHW planes themselves (K-S) or convert; only the reference view is needed channels-last
+            # again (by Refinement): convert that one view here, once
+            self._ref_image_cl = first.contiguous(memory_format=torch.channels_last)
         stacked = self.feature(x)
         return [{k: v[i * b:(i + 1) * b] for k, v in stacked.items()} for i in range(n)]
 

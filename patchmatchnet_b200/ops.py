@@ -326,6 +326,30 @@ def pack_conv_filter_tc5h(weight: Tensor) -> Tensor:
     return t.contiguous().view(-1)
 
 
+# K-S (csrc/pm_stem.cu): FeatureNet's conv0 -> conv1 as one exact-fp32 launch; PMB200_STEM=0 keeps the two K-D launches.
+STEM_FUSED = os.environ.get("PMB200_STEM", "1") != "0"
+
+
+def conv_stem(x: Tensor, w0: Tensor, b0: Tensor, w1: Tensor, b1: Tensor) -> Tensor:
+    """relu(conv1(relu(conv0(x)))) of FeatureNet (3 -> 8 -> 8, 3x3, pad 1; reference models/net.py:18-19, :44) in one launch.
+    `x` [N,3,H,W] contiguous NCHW on the device; the BatchNorm-folded weights `w0` [8,3,3,3], `b0` [8], `w1` [8,8,3,3], `b1` [8]
+    are HOST float32 tensors (they travel in the kernel's parameter block).  Returns [N,8,H,W] in channels-last memory."""
+    if not _on_device(x) or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+        raise RuntimeError(f"conv_stem: x must be a CUDA float32 [N,3,H,W] tensor (got {x.dtype} {tuple(x.shape)} on {x.device}); no CPU fallback")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    for name, t, shape in (("w0", w0, (8, 3, 3, 3)), ("b0", b0, (8,)), ("w1", w1, (8, 8, 3, 3)), ("b1", b1, (8,))):
+        if t.device.type != "cpu" or t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous():
+            raise RuntimeError(f"conv_stem: {name} must be a contiguous float32 HOST tensor of shape {shape}")
+    N, _, H, W = x.shape
+    y = torch.empty((N, 8, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    with _device_guard(x):
+        rc = _native.lib().pmb200_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), N, H, W,
+                                            _stream(x))
+    _native.check(rc, "conv_stem")
+    return y
+
+
 def conv2d_tc5(x: Tensor, filter_tc5: Tensor, bias: Optional[Tensor], cout: int, ks: int, stride: int = 1, pad: int = 0, dil: int = 1,
                relu: bool = False, out: Optional[Tensor] = None, out_channel_offset: int = 0, halo: bool = False) -> Tensor:
     """Channels-last convolution on the 5th-generation tensor cores (csrc/pm_conv5.cu), fp32-accurate.  Same calling

@@ -112,6 +112,9 @@ class EmulatedLibrary:
     def pmb200_conv2d_nhwc(self, *args):
         return self.conv.emu_conv2d_nhwc(*args)
 
+    def pmb200_conv_stem(self, *args):
+        return self.conv.emu_conv_stem(*args)
+
 
 def install(monkeypatch, emu, emu_conv):
     facade = EmulatedLibrary(emu, emu_conv)

@@ -15,3 +15,7 @@ extern "C" const char *emu_conv_last_error(void) { return g_conv_err; }
 #define pmb200_conv2d_nhwc emu_conv2d_nhwc
 #define pmb200_conv2d_filter_floats emu_conv2d_filter_floats
 #include "../patchmatchnet_b200/csrc/pm_conv.cu"
+
+// K-S, the fused conv0 -> conv1 stem of FeatureNet (pm_stem.cu): plain fp32 FFMA, nothing to restate under PM_EMU
+#define pmb200_conv_stem emu_conv_stem
+#include "../patchmatchnet_b200/csrc/pm_stem.cu"

@@ -374,3 +374,28 @@ def test_gpu_conv_with_fused_upsample_add(fp32_library):
         assert _scaled_err(got, want) <= 2e-5
     with pytest.raises(RuntimeError, match="add_up2x"):
         ops.conv2d_nhwc(fine, ops.pack_conv_filter(wt, 3), b, cout, 1, precision=3, add_up2x=coarse[:, :, :-1])
+
+
+def test_conv_stem_rejects_what_it_cannot_serve():
+    w0, b0, w1, b1 = torch.zeros(8, 3, 3, 3), torch.zeros(8), torch.zeros(8, 8, 3, 3), torch.zeros(8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.conv_stem(torch.zeros(1, 3, 8, 8), w0, b0, w1, b1)
+
+
+@pytest.mark.gpu
+def test_gpu_conv_stem_matches_cudnn_fp32(fp32_library):
+    """K-S (fused conv0 -> conv1 of FeatureNet, exact fp32 FFMA with the weights in the constant bank) against the two cuDNN
+    fp32 convolutions: ragged sizes and the bench's 5 x 640 x 512; strided-batch input (views of one buffer)."""
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(77)
+    w0, b0 = torch.randn(8, 3, 3, 3, generator=g) / 27 ** 0.5, torch.randn(8, generator=g) * 0.5
+    w1, b1 = torch.randn(8, 8, 3, 3, generator=g) / 72 ** 0.5, torch.randn(8, generator=g) * 0.5
+    for (N, H, W) in ((2, 37, 53), (1, 16, 32), (3, 9, 70), (5, 512, 640)):
+        x = torch.randn(N, 3, H, W, generator=g).to(dev)
+        want = F.relu(F.conv2d(F.relu(F.conv2d(x, w0.to(dev), b0.to(dev), padding=1)), w1.to(dev), b1.to(dev), padding=1))
+        got = ops.conv_stem(x, w0, b0, w1, b1)
+        torch.cuda.synchronize()
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        assert _scaled_err(got, want) <= 2e-6, (N, H, W)
+    with pytest.raises(RuntimeError, match="HOST"):
+        ops.conv_stem(x, w0.to(dev), b0, w1, b1)

@@ -21,7 +21,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def emu_conv():
     src = os.path.join(REPO, "tests", "emu_conv.cpp")
     deps = [src, os.path.join(REPO, "tests", "warp_emu.h"), os.path.join(REPO, "include", "patchmatch_b200.h"),
-            os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_conv.cu")]
+            os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_conv.cu"), os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_stem.cu")]
     out = os.path.join(REPO, "tests", "_emu_conv.so")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -33,6 +33,8 @@ def emu_conv():
     lib.emu_conv2d_filter_floats.argtypes = [I] * 4
     lib.emu_conv2d_filter_floats.restype = I
     lib.emu_conv_last_error.restype = ctypes.c_char_p
+    lib.emu_conv_stem.argtypes = [P] * 6 + [I] * 3 + [P]
+    lib.emu_conv_stem.restype = I
     return lib
 
 
@@ -135,3 +137,30 @@ def test_emulated_planner_rejects_bad_arguments(emu_conv):
     assert emu_conv.emu_conv2d_nhwc(*args(S=3)) == -1
     assert emu_conv.emu_conv2d_nhwc(*args(prec=2)) == -1
     assert emu_conv.emu_conv2d_nhwc(*args(yco=4)) == -1 and b"channel slice" in emu_conv.emu_conv_last_error()
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 45), (1, 16, 32), (1, 37, 70), (3, 5, 9)])
+def test_emulated_stem_matches_two_convs(emu_conv, shape):
+    """K-S (csrc/pm_stem.cu, the kernel's own source under the warp emulator): relu(conv1(relu(conv0(x)))) with folded biases
+    against the two F.conv2d calls, ragged sizes (partial 32 x 16 tiles, image borders inside the conv0 halo), exact fp32
+    arithmetic -> agreement to rounding-order noise."""
+    N, H, W = shape
+    g = torch.Generator().manual_seed(N * 1000 + H * 10 + W)
+    x = torch.randn(N, 3, H, W, generator=g)
+    w0, b0 = torch.randn(8, 3, 3, 3, generator=g) / 27 ** 0.5, torch.randn(8, generator=g) * 0.5
+    w1, b1 = torch.randn(8, 8, 3, 3, generator=g) / 72 ** 0.5, torch.randn(8, generator=g) * 0.5
+    y = torch.full((N, H, W, 8), float("nan"))
+    rc = emu_conv.emu_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), N, H, W, None)
+    assert rc == 0, emu_conv.emu_conv_last_error()
+    want = F.relu(F.conv2d(F.relu(F.conv2d(x.double(), w0.double(), b0.double(), padding=1)), w1.double(), b1.double(), padding=1)).float()
+    got = y.permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    assert _scaled_err(got, want) <= 2e-6
+
+
+def test_emulated_stem_argument_errors(emu_conv):
+    x, y = torch.zeros(1, 3, 4, 4), torch.zeros(1, 4, 4, 8)
+    w0, b0, w1, b1 = torch.zeros(8, 3, 3, 3), torch.zeros(8), torch.zeros(8, 8, 3, 3), torch.zeros(8)
+    assert emu_conv.emu_conv_stem(None, w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), 1, 4, 4, None) == -1
+    assert emu_conv.emu_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), 1, 0, 4, None) == -1
+    assert emu_conv.emu_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr() + 4, 1, 4, 4, None) == -1

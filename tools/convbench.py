@@ -121,7 +121,15 @@ for (name, N, cin, cout, ks, S, pad, dil, relu, h, w) in LAYERS:
             except Exception as e:  # noqa: BLE001
                 row["tc5h_3xtf32_us"] = f"ERR {e}"
     rows.append(row)
+# K-S: conv0 -> conv1 fused (exact fp32) against the two K-D launches it replaces (3xTF32), same 5 x H x W input
+x3 = torch.randn(5, 3, H, W, generator=g).to(dev)
+w0, b0 = torch.randn(8, 3, 3, 3, generator=g) / 27 ** 0.5, torch.randn(8, generator=g)
+w1, b1 = torch.randn(8, 8, 3, 3, generator=g) / 72 ** 0.5, torch.randn(8, generator=g)
+c, cmin, wm = timeit(lambda: ops.conv_stem(x3, w0, b0, w1, b1))
+stem = {"layer": "feature.conv0+conv1 fused (K-S)", "shape": f"N5 3->8->8 k3 {H}x{W}", "stem_us": {"cold": round(c, 1), "cold_min": round(cmin, 1), "warm": round(wm, 1)},
+        "replaces_us_cold": sum(r["native_p3_mt0_us"]["cold"] for r in rows if r["layer"] in ("feature.conv0", "feature.conv1")),
+        "gbs_in_plus_out": round(4 * 5 * H * W * (3 + 8) / (c * 1e-6) / 1e9, 1)}
 tot_lib = sum(r["cudnn_tf32_us"]["cold"] for r in rows)
 tot_nat = sum(r["native_p1_mt0_us"]["cold"] for r in rows if isinstance(r.get("native_p1_mt0_us"), dict))
 print(json.dumps({"gpu": torch.cuda.get_device_name(0), "size": [H, W], "sum_cold_us": {"cudnn_tf32": round(tot_lib, 1), "native_tf32": round(tot_nat, 1)},
-                  "layers": rows}, indent=1))
+                  "layers": rows, "stem": stem}, indent=1))
