@@ -57,14 +57,35 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const __grid_co
     const int y0 = ty * kSTH, x0 = tx * kSTW;
     const int tid = threadIdx.x;
 
-    // ---- image halo (rows y0-2 .., cols x0-2 ..), zero outside the image = conv0's padding
+    // ---- image halo (rows y0-2 .., cols x0-2 ..), zero outside the image = conv0's padding.  One warp per halo row (3 planes x
+    // 20 rows = 60 rows over 8 warps), lanes along the row (32 + 4 columns): no per-element index arithmetic, and the loads of a
+    // warp's rows are all issued before the first store so their latencies overlap.
     const float *xin = p.x + (size_t)n * 3 * p.H * p.W;
-    for (int i = tid; i < 3 * kIH * kIW; i += kStemThreads) {
-        const int ci = i / (kIH * kIW), r = (i - ci * kIH * kIW) / kIW, c = i - ci * kIH * kIW - r * kIW;
-        const int gy = y0 - 2 + r, gx = x0 - 2 + c;
-        float v = 0.0f;
-        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = xin[((size_t)ci * p.H + gy) * p.W + gx];
-        img[ci][r][c] = v;
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int kRowsPerWarp = (3 * kIH + 7) / 8;  // 8
+        float v0[kRowsPerWarp], v1[kRowsPerWarp];
+        const int gx0 = x0 - 2 + lane, gx1 = gx0 + 32;
+        const bool in0 = gx0 >= 0 && gx0 < p.W, in1 = lane < kIW - 32 && gx1 < p.W;
+#pragma unroll
+        for (int k = 0; k < kRowsPerWarp; ++k) {
+            const int row = warp + 8 * k;  // plane * kIH + r
+            const int ci = row / kIH, r = row - ci * kIH;
+            const int gy = y0 - 2 + r;
+            const bool rin = row < 3 * kIH && gy >= 0 && gy < p.H;
+            const float *src = xin + ((size_t)ci * p.H + (rin ? gy : 0)) * p.W;
+            v0[k] = (rin && in0) ? src[gx0] : 0.0f;
+            v1[k] = (rin && in1) ? src[gx1] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kRowsPerWarp; ++k) {
+            const int row = warp + 8 * k;
+            if (row < 3 * kIH) {
+                const int ci = row / kIH, r = row - ci * kIH;
+                img[ci][r][lane] = v0[k];
+                if (lane < kIW - 32) img[ci][r][32 + lane] = v1[k];
+            }
+        }
     }
     __syncthreads();
 
