@@ -14,6 +14,8 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/library.h>
 
+#include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -47,6 +49,25 @@ Tensor offsets_arg(const Tensor &off, int64_t B, int64_t K, int64_t H, int64_t W
     if (off.is_contiguous(at::MemoryFormat::ChannelsLast)) { *channels_last = 1; return off; }
     *channels_last = 0;
     return off.contiguous();
+}
+
+// A scripted module keeps its packed offset-conv filters as CPU tensors (state-dict keys stay the reference's).  Uploading them
+// on every forward is an implicit host sync from pageable memory and makes the scripted model impossible to capture in a CUDA
+// graph, so device copies are cached per (source storage, version, device).  The cache holds the SOURCE tensor too: its address
+// cannot be recycled for other contents while the entry lives.  Bounded (a model has two such filters per stage).
+Tensor device_copy_cached(const Tensor &t, const c10::Device &dev) {
+    if (t.device() == dev) return t.contiguous();
+    struct Entry { Tensor src, copy; };
+    static std::mutex mu;
+    static auto *cache = new std::map<std::tuple<const void *, int64_t, int>, Entry>();  // never destroyed: outlives the CUDA context
+    const auto key = std::make_tuple(static_cast<const void *>(t.data_ptr()), (int64_t)t._version(), (int)dev.index());
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache->find(key);
+    if (it != cache->end() && it->second.src.numel() == t.numel()) return it->second.copy;
+    if (cache->size() >= 64) cache->clear();
+    Entry e{t, t.to(dev).contiguous()};
+    (*cache)[key] = e;
+    return e.copy;
 }
 
 // BatchNorm-folded G->16->8->1 head as the flat float image of `pmb200_mlp` (host memory)
@@ -345,7 +366,7 @@ Tensor conv2d_nhwc(const Tensor &x, const Tensor &filter_frag, const c10::option
     TORCH_CHECK(want > 0 && filter_frag.scalar_type() == at::kFloat && filter_frag.numel() == want,
                 "conv2d_nhwc: filter must be ", want, " float32 values in fragment order for this precision (pack_conv_filter)");
     c10::cuda::CUDAGuard guard(xc.device());
-    const Tensor frag = filter_frag.to(xc.device()).contiguous();
+    const Tensor frag = device_copy_cached(filter_frag, xc.device());
     Tensor b;
     const float *b_ptr = nullptr;
     if (bias.has_value() && bias->defined()) {
