@@ -318,7 +318,8 @@ class LaunchCounter:
 
     NAMES = ("relative_projection", "pack_nhwc", "warp_corr", "aggregate_views", "offset_corr", "init_propagate", "adaptive_eval",
              "warp_corr_score", "warp_corr_view_weights", "offset_corr_weight", "aggregate_views_score",
-             "conv2d_nhwc", "conv2d_tc5", "conv2d_tc5h", "conv_stem", "upsample2x_add_nhwc", "photometric_confidence")
+             "conv2d_nhwc", "conv2d_tc5", "conv2d_tc5h", "conv_stem", "refine_low", "refine_full", "upsample2x_add_nhwc",
+             "photometric_confidence")
 
     def __init__(self):
         from patchmatchnet_b200 import _native

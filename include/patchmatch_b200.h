@@ -47,7 +47,8 @@ const char *pmb200_last_error(void);
  * Keys: "ka_gen" (3 | 4: generation of the fused warp+correlation kernel), "ka3_dc", "ka3_dc_vw", "ka3_pipe", "ka3_minb"
  * (generation-3 rows per pass / gather pipeline / resident CTAs), "ka4_nw" (4 | 8 consumer warps = tile rows), "ka4_ctas"
  * (resident CTAs per SM the window ring is sized for), "ka4_cap" (texels per ring slot), "ka4_stages" (ring depth 2..4), "ka4_grid" (persistent CTAs),
- * "kb_tp", "kb_dy" (block shape of the adaptive-evaluation kernel); 0 = the built-in default.  "reset" restores every
+ * "kb_tp", "kb_dy" (block shape of the adaptive-evaluation kernel), "stem_ppt" (output pixels per thread of the fused
+ * conv0 -> conv1 kernel: 2 or 4); 0 = the built-in default.  "reset" restores every
  * default.  Results never depend on these knobs, only launch shapes do.  Returns 0, or PMB200_EINVAL for an unknown key.
  * The reference has no counterpart (its launch shapes are ATen's). */
 int pmb200_set_tuning(const char *key, int value);
@@ -91,6 +92,22 @@ int pmb200_debug_conv5h_trace(long long *device_buffer_256);
  *            copied into the kernel parameter block at launch (so a captured CUDA graph keeps the values it was captured with). */
 int pmb200_conv_stem(const float *x_nchw, const float *host_w0, const float *host_b0, const float *host_w1, const float *host_b1,
                      float *y_nhwc, int N, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-R: Refinement (reference models/net.py:73-122) in two launches, exact fp32 (plain FFMA, weights in the constant bank).
+ * pmb200_refine_low  (half resolution; :104-110):  d = (depth - depth_min) / (depth_max - depth_min);
+ *                    low = relu(conv2(relu(conv1(d))))   conv1 1 -> 8, conv2 8 -> 8, 3x3 / pad 1, BatchNorm folded.
+ * pmb200_refine_full (full resolution; :103, :112-120):  up = relu(bn(deconv(low))), c0 = relu(conv0(img)),
+ *                    c3 = relu(conv3(cat(up, c0))), res = conv_res(c3), out = (nearest_up2x(d) + res) * span + depth_min.
+ *   depth_half [N,1,h,w], depth_min / depth_max [N], low_nhwc [N,h,w,8] (16-byte aligned), img_nchw [N,3,2h,2w] contiguous,
+ *   depth_out [N,1,2h,2w]: device.   Every host_* argument is HOST memory in PyTorch layout with BatchNorm folded:
+ *   host_w1 [8][1][3][3], host_w2 [8][8][3][3], host_wd [8 in][8 out][3][3] (ConvTranspose2d), host_w0 [8][3][3][3],
+ *   host_w3 [8][16][3][3], host_wr [1][8][3][3] (no bias), biases [8].  They travel in the kernel parameter block. */
+int pmb200_refine_low(const float *depth_half, const float *depth_min, const float *depth_max, const float *host_w1, const float *host_b1,
+                      const float *host_w2, const float *host_b2, float *low_nhwc, int N, int h, int w, void *stream);
+int pmb200_refine_full(const float *low_nhwc, const float *img_nchw, const float *depth_half, const float *depth_min, const float *depth_max,
+                       const float *host_wd, const float *host_bd, const float *host_w0, const float *host_b0, const float *host_w3,
+                       const float *host_b3, const float *host_wr, float *depth_out, int N, int H, int W, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Relative projections for every (source view, batch element):

@@ -1136,13 +1136,13 @@ cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 // (tools/kbench.py) changes them through pmb200_set_tuning().  Nothing in the launch path reads the environment.
 // ------------------------------------------------------------------------------------------
 enum Tune { kTuneKaGen, kTuneKa3Dc, kTuneKa3DcVw, kTuneKa3Pipe, kTuneKa3MinB, kTuneKa4Nw, kTuneKa4Ctas, kTuneKa4Cap, kTuneKa4Grid,
-            kTuneKa4Stages, kTuneKbTp, kTuneKbDy, kTuneCount };
+            kTuneKa4Stages, kTuneKbTp, kTuneKbDy, kTuneStemPpt, kTuneCount };
 const char *const kTuneNames[kTuneCount] = {"ka_gen", "ka3_dc", "ka3_dc_vw", "ka3_pipe", "ka3_minb", "ka4_nw", "ka4_ctas", "ka4_cap",
-                                            "ka4_grid", "ka4_stages", "kb_tp", "kb_dy"};
+                                            "ka4_grid", "ka4_stages", "kb_tp", "kb_dy", "stem_ppt"};
 // ka_gen: 3.  Generation 4 (TMA-staged windows) is parity-green on B200 but slower at every bench shape (cold us, gen 3 / gen 4:
 // 47.6 / 91.7, 20.5 / 33.0, 34.3 / 41.0, 37.0 / 49.1 -- profiles/r2_run3_kbench.json; DESIGN.md has the analysis)
-const int kTuneDefaults[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
-int g_tune[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
+const int kTuneDefaults[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 4};
+int g_tune[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 4};
 inline int tune(Tune t) { return __atomic_load_n(&g_tune[t], __ATOMIC_RELAXED); }
 
 // Third-generation K-A launch (kept for shapes generation 4 does not take and for A/B measurements).
@@ -1324,6 +1324,11 @@ extern "C" {
 // shared with pm_backward.cu (not part of the public header)
 int pmb200_internal_fail(int code, const char *msg) { return fail(code, msg); }
 int pmb200_internal_launch_status(const char *what) { return launch_status(what); }
+int pmb200_internal_tuning(const char *key) {
+    for (int i = 0; i < kTuneCount; ++i)
+        if (strcmp(key, kTuneNames[i]) == 0) return tune((Tune)i);
+    return 0;
+}
 
 int pmb200_abi_version(void) { return PMB200_ABI_VERSION; }
 

@@ -27,6 +27,10 @@
 extern "C" int pmb200_internal_fail(int code, const char *msg);  // pm_kernels.cu: sets pmb200_last_error()
 #if !defined(PM_EMU)
 extern "C" int pmb200_internal_launch_status(const char *what);
+extern "C" int pmb200_internal_tuning(const char *key);  // pm_kernels.cu: current value of a pmb200_set_tuning knob
+#else
+static int g_emu_stem_ppt = 4;
+extern "C" void emu_conv_set_stem_ppt(int v) { g_emu_stem_ppt = v; }
 #endif
 
 namespace {
@@ -34,11 +38,14 @@ namespace {
 constexpr int kSTW = 32, kSTH = 16;                    // output tile
 constexpr int kHW = kSTW + 2, kHH = kSTH + 2;          // conv0 outputs needed by the tile (conv1's halo)
 constexpr int kIW = kSTW + 4, kIH = kSTH + 4;          // image pixels needed by those
-constexpr int kStemThreads = 256;
+// Output pixels per thread (PPT): 2 -> 256 threads per CTA, 4 -> 128.  Every weight reaches the FFMA through a uniform register
+// loaded by LDCU.128 (4 weights per load, no direct constant operand on sm_100); a thread's PPT pixels share the load, so PPT
+// sets the LDCU : FFMA ratio of the conv1 phase (1 : 4 PPT).  pmb200_set_tuning("stem_ppt", 2 | 4) for A/B runs.
 
 struct StemParams {
-    const float *x;  // [N,3,H,W]
+    const float *x;  // [N,CIN0,H,W]
     float *y;        // [N,H,W,8]
+    const float *lo, *hi;  // NORM: per-image [N] range; the input is (x - lo) / (hi - lo) (Refinement's depth normalisation)
     int N, H, W, tiles_x, tiles_y;
     float w0[27 * 8];  // [(ci*9 + ky*3 + kx)][co]
     float b0[8];
@@ -47,8 +54,10 @@ struct StemParams {
 };
 static_assert(sizeof(StemParams) <= 4096, "the weights must fit the kernel parameter block");
 
-__global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const __grid_constant__ StemParams p) {
-    __shared__ float img[3][kIH][kIW];
+template <int CIN0, bool NORM, int PPT>
+__global__ void __launch_bounds__(32 * (kSTH / PPT)) conv_stem_kernel(const __grid_constant__ StemParams p) {
+    constexpr int kStemThreads = 32 * (kSTH / PPT), kWarps = kStemThreads / 32, kRowStep = kSTH / PPT;
+    __shared__ float img[CIN0][kIH][kIW];
     __shared__ float4 mid[2][kHH * kHW];  // conv0 output: plane 0 = channels 0-3, plane 1 = channels 4-7
     const int tile = blockIdx.x;
     const int per_img = p.tiles_x * p.tiles_y;
@@ -60,27 +69,36 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const __grid_co
     // ---- image halo (rows y0-2 .., cols x0-2 ..), zero outside the image = conv0's padding.  One warp per halo row (3 planes x
     // 20 rows = 60 rows over 8 warps), lanes along the row (32 + 4 columns): no per-element index arithmetic, and the loads of a
     // warp's rows are all issued before the first store so their latencies overlap.
-    const float *xin = p.x + (size_t)n * 3 * p.H * p.W;
+    const float *xin = p.x + (size_t)n * CIN0 * p.H * p.W;
+    float nlo = 0.0f, nspan = 1.0f;
+    if (NORM) {
+        nlo = p.lo[n];
+        nspan = p.hi[n] - nlo;
+    }
     {
         const int warp = tid >> 5, lane = tid & 31;
-        constexpr int kRowsPerWarp = (3 * kIH + 7) / 8;  // 8
+        constexpr int kRowsPerWarp = (CIN0 * kIH + kWarps - 1) / kWarps;
         float v0[kRowsPerWarp], v1[kRowsPerWarp];
         const int gx0 = x0 - 2 + lane, gx1 = gx0 + 32;
         const bool in0 = gx0 >= 0 && gx0 < p.W, in1 = lane < kIW - 32 && gx1 < p.W;
 #pragma unroll
         for (int k = 0; k < kRowsPerWarp; ++k) {
-            const int row = warp + 8 * k;  // plane * kIH + r
+            const int row = warp + kWarps * k;  // plane * kIH + r
             const int ci = row / kIH, r = row - ci * kIH;
             const int gy = y0 - 2 + r;
-            const bool rin = row < 3 * kIH && gy >= 0 && gy < p.H;
+            const bool rin = row < CIN0 * kIH && gy >= 0 && gy < p.H;
             const float *src = xin + ((size_t)ci * p.H + (rin ? gy : 0)) * p.W;
             v0[k] = (rin && in0) ? src[gx0] : 0.0f;
             v1[k] = (rin && in1) ? src[gx1] : 0.0f;
+            if (NORM) {  // IEEE division like the reference's (depth - lo) / span; the zero padding stays zero
+                v0[k] = (rin && in0) ? (v0[k] - nlo) / nspan : 0.0f;
+                v1[k] = (rin && in1) ? (v1[k] - nlo) / nspan : 0.0f;
+            }
         }
 #pragma unroll
         for (int k = 0; k < kRowsPerWarp; ++k) {
-            const int row = warp + 8 * k;
-            if (row < 3 * kIH) {
+            const int row = warp + kWarps * k;
+            if (row < CIN0 * kIH) {
                 const int ci = row / kIH, r = row - ci * kIH;
                 img[ci][r][lane] = v0[k];
                 if (lane < kIW - 32) img[ci][r][32 + lane] = v1[k];
@@ -97,7 +115,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const __grid_co
 #pragma unroll
         for (int co = 0; co < 8; ++co) a[co] = p.b0[co];
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+        for (int ci = 0; ci < CIN0; ++ci)
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -114,11 +132,11 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const __grid_co
     }
     __syncthreads();
 
-    // ---- conv1 + ReLU: two output pixels per thread (rows oy and oy + 8 of the tile, same column)
-    const int ox = tid & (kSTW - 1), oy = tid >> 5;  // 32 columns x 8 rows of threads
-    float acc[2][8];
+    // ---- conv1 + ReLU: PPT output pixels per thread (rows oy + kRowStep * q of the tile, same column)
+    const int ox = tid & (kSTW - 1), oy = tid >> 5;  // 32 columns x kRowStep rows of threads
+    float acc[PPT][8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < PPT; ++q)
 #pragma unroll
         for (int co = 0; co < 8; ++co) acc[q][co] = p.b1[co];
 #pragma unroll
@@ -126,8 +144,8 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const __grid_co
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int pos = (oy + 8 * q + ky) * kHW + ox + kx;
+            for (int q = 0; q < PPT; ++q) {
+                const int pos = (oy + kRowStep * q + ky) * kHW + ox + kx;
                 const float4 lo = mid[0][pos], hi = mid[1][pos];
                 const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
@@ -137,14 +155,51 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const __grid_co
             }
         }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int gy = y0 + oy + 8 * q, gx = x0 + ox;
+    for (int q = 0; q < PPT; ++q) {
+        const int gy = y0 + oy + kRowStep * q, gx = x0 + ox;
         if (gy < p.H && gx < p.W) {
             float4 *dst = reinterpret_cast<float4 *>(p.y + (((size_t)n * p.H + gy) * p.W + gx) * 8);
             dst[0] = make_float4(fmaxf(acc[q][0], 0.0f), fmaxf(acc[q][1], 0.0f), fmaxf(acc[q][2], 0.0f), fmaxf(acc[q][3], 0.0f));
             dst[1] = make_float4(fmaxf(acc[q][4], 0.0f), fmaxf(acc[q][5], 0.0f), fmaxf(acc[q][6], 0.0f), fmaxf(acc[q][7], 0.0f));
         }
     }
+}
+
+// fills the parameter block from PyTorch-layout host weights and launches
+template <int CIN0, bool NORM>
+int launch_stem(const char *what, const float *x, const float *lo, const float *hi, const float *host_w0, const float *host_b0,
+                const float *host_w1, const float *host_b1, float *y_nhwc, int N, int H, int W, void *stream) {
+    if (!x || !host_w0 || !host_b0 || !host_w1 || !host_b1 || !y_nhwc || (NORM && (!lo || !hi))) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem / refine_low: null pointer");
+    if (N < 1 || H < 1 || W < 1) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem / refine_low: bad size");
+    if (reinterpret_cast<uintptr_t>(y_nhwc) & 15u) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem / refine_low: output must be 16-byte aligned");
+    StemParams p;
+    p.x = x; p.y = y_nhwc; p.lo = lo; p.hi = hi; p.N = N; p.H = H; p.W = W;
+    p.tiles_x = (W + kSTW - 1) / kSTW; p.tiles_y = (H + kSTH - 1) / kSTH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
+    if (tiles > 0x7fffffffLL) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem / refine_low: too many tiles");
+    for (int i = 0; i < 27 * 8; ++i) p.w0[i] = 0.0f;
+    for (int co = 0; co < 8; ++co) {
+        p.b0[co] = host_b0[co];
+        p.b1[co] = host_b1[co];
+        for (int ci = 0; ci < CIN0; ++ci)
+            for (int t = 0; t < 9; ++t) p.w0[(ci * 9 + t) * 8 + co] = host_w0[(co * CIN0 + ci) * 9 + t];
+        for (int ci = 0; ci < 8; ++ci)
+            for (int t = 0; t < 9; ++t) p.w1[(t * 8 + ci) * 8 + co] = host_w1[(co * 8 + ci) * 9 + t];
+    }
+#if defined(PM_EMU)
+    (void)stream; (void)what;
+    if (g_emu_stem_ppt == 2)
+        emu::launch(dim3((unsigned)tiles), dim3(256), 0, [&] { conv_stem_kernel<CIN0, NORM, 2>(p); });
+    else
+        emu::launch(dim3((unsigned)tiles), dim3(128), 0, [&] { conv_stem_kernel<CIN0, NORM, 4>(p); });
+    return 0;
+#else
+    if (pmb200_internal_tuning("stem_ppt") == 2)
+        conv_stem_kernel<CIN0, NORM, 2><<<(unsigned)tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    else
+        conv_stem_kernel<CIN0, NORM, 4><<<(unsigned)tiles, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return pmb200_internal_launch_status(what);
+#endif
 }
 
 }  // namespace
@@ -159,30 +214,16 @@ extern "C" {
 // affect launches already enqueued or captured in a CUDA graph.
 int pmb200_conv_stem(const float *x_nchw, const float *host_w0, const float *host_b0, const float *host_w1, const float *host_b1,
                      float *y_nhwc, int N, int H, int W, void *stream) {
-    if (!x_nchw || !host_w0 || !host_b0 || !host_w1 || !host_b1 || !y_nhwc) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem: null pointer");
-    if (N < 1 || H < 1 || W < 1) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem: bad size");
-    if (reinterpret_cast<uintptr_t>(y_nhwc) & 15u) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem: output must be 16-byte aligned");
-    StemParams p;
-    p.x = x_nchw; p.y = y_nhwc; p.N = N; p.H = H; p.W = W;
-    p.tiles_x = (W + kSTW - 1) / kSTW; p.tiles_y = (H + kSTH - 1) / kSTH;
-    const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
-    if (tiles > 0x7fffffffLL) return pmb200_internal_fail(PMB200_EINVAL, "conv_stem: too many tiles");
-    for (int co = 0; co < 8; ++co) {
-        p.b0[co] = host_b0[co];
-        p.b1[co] = host_b1[co];
-        for (int ci = 0; ci < 3; ++ci)
-            for (int t = 0; t < 9; ++t) p.w0[(ci * 9 + t) * 8 + co] = host_w0[(co * 3 + ci) * 9 + t];
-        for (int ci = 0; ci < 8; ++ci)
-            for (int t = 0; t < 9; ++t) p.w1[(t * 8 + ci) * 8 + co] = host_w1[(co * 8 + ci) * 9 + t];
-    }
-#if defined(PM_EMU)
-    (void)stream;
-    emu::launch(dim3((unsigned)tiles), dim3(kStemThreads), 0, [&] { conv_stem_kernel(p); });
-    return 0;
-#else
-    conv_stem_kernel<<<(unsigned)tiles, kStemThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    return pmb200_internal_launch_status("conv_stem");
-#endif
+    return launch_stem<3, false>("conv_stem", x_nchw, nullptr, nullptr, host_w0, host_b0, host_w1, host_b1, y_nhwc, N, H, W, stream);
+}
+
+// The half-resolution head of Refinement (reference models/net.py:104-110): d = (depth - depth_min) / (depth_max - depth_min),
+// relu(conv2(relu(conv1(d)))) with conv1 1 -> 8, conv2 8 -> 8, 3x3, pad 1, BatchNorm folded -- the same kernel with one input
+// plane and the normalisation applied as the plane is staged (zero padding applies to the NORMALISED map, as in the reference).
+//   depth_half  device [N,1,h,w] contiguous;  depth_min / depth_max  device [N]
+int pmb200_refine_low(const float *depth_half, const float *depth_min, const float *depth_max, const float *host_w1, const float *host_b1,
+                      const float *host_w2, const float *host_b2, float *low_nhwc, int N, int h, int w, void *stream) {
+    return launch_stem<1, true>("refine_low", depth_half, depth_min, depth_max, host_w1, host_b1, host_w2, host_b2, low_nhwc, N, h, w, stream);
 }
 
 }  // extern "C"

@@ -328,6 +328,7 @@ class Refinement(nn.Module):
         self.res = nn.Conv2d(8, 1, 3, padding=1, bias=False)
         self._cache = _FoldCache()
         self._deconv_frag = _FoldCache()
+        self._host_cache = _FoldCache()
         self._res_packed = _PackedConv()
 
     def _native_tail(self, img: Tensor, d: Tensor) -> Tensor:
@@ -361,7 +362,38 @@ class Refinement(nn.Module):
         w, b = self._cache.get(srcs, lambda: _fold_bn(self.deconv.weight, bn, out_dim=1))
         return F.relu_(F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1))
 
+    def host_weights(self):
+        """BatchNorm-folded weights of the six layers as HOST tensors, in the argument order of ops.refine_low (first four) and
+        ops.refine_full (the rest): K-R carries them in its kernel parameter blocks."""
+        srcs = [self.deconv.weight, self.res.weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var]
+        for m in (self.conv0, self.conv1, self.conv2, self.conv3):
+            srcs += [m.conv.weight, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var]
+
+        def make():
+            host = lambda t: t.detach().float().cpu().contiguous()  # noqa: E731
+            w1, b1 = _fold_bn(self.conv1.conv.weight, self.conv1.bn)
+            w2, b2 = _fold_bn(self.conv2.conv.weight, self.conv2.bn)
+            wd, bd = _fold_bn(self.deconv.weight, self.bn, out_dim=1)
+            w0, b0 = _fold_bn(self.conv0.conv.weight, self.conv0.bn)
+            w3, b3 = _fold_bn(self.conv3.conv.weight, self.conv3.bn)
+            return tuple(host(t) for t in (w1, b1, w2, b2, wd, bd, w0, b0, w3, b3, self.res.weight))
+
+        return self._host_cache.get(srcs, make)
+
+    def _fused(self, img: Tensor, depth_half: Tensor, depth_min: Tensor, depth_max: Tensor) -> Tensor:
+        """Eval mode on CUDA, fp32-accurate mode: the whole module in two exact-fp32 launches (K-R)."""
+        from . import ops
+
+        hw = self.host_weights()
+        low = ops.refine_low(depth_half, depth_min, depth_max, *hw[:4])
+        return ops.refine_full(low, img, depth_half, depth_min, depth_max, *hw[4:])
+
     def forward(self, img: Tensor, depth_half: Tensor, depth_min: Tensor, depth_max: Tensor) -> Tensor:
+        from . import ops
+
+        if (not self.training and _native_convs(img) and ops.REFINE_FUSED and ops.conv_precision() == 3 and img.dtype == torch.float32
+                and img.shape[-2:] == (2 * depth_half.shape[-2], 2 * depth_half.shape[-1]) and self.res.bias is None):
+            return self._fused(img, depth_half.float(), depth_min.float(), depth_max.float())
         B = depth_min.size(0)
         lo = depth_min.view(B, 1, 1, 1)
         span = (depth_max - depth_min).view(B, 1, 1, 1)
@@ -469,8 +501,11 @@ class PatchmatchNet(nn.Module):
             x = torch.cat(images, dim=0)
         if _fast(x):  # the pyramid comes out channels-last, the layout the fused PatchMatch kernels read in place.  FeatureNet's
             # first layers read the NCHW planes themselves (K-S) or convert; only the reference view is needed channels-last
-            # again (by Refinement): convert that one view here, once
-            self._ref_image_cl = first.contiguous(memory_format=torch.channels_last)
+            # again, by Refinement's conv-family path; its fused form (K-R) reads the NCHW planes itself
+            from . import ops
+
+            if not (ops.REFINE_FUSED and ops.NATIVE_CONVS and ops.conv_precision() == 3):
+                self._ref_image_cl = first.contiguous(memory_format=torch.channels_last)
         stacked = self.feature(x)
         return [{k: v[i * b:(i + 1) * b] for k, v in stacked.items()} for i in range(n)]
 
@@ -495,6 +530,7 @@ class PatchmatchNet(nn.Module):
         if self._ref_image_cl is not None:  # same values as ref_image, channels-last memory (eval fast path only)
             ref_image = self._ref_image_cl
             self._ref_image_cl = None
+        # (when Refinement runs fused -- K-R reads the NCHW planes in place -- no channels-last copy was made)
         depth_min = depth_min.float()
         depth_max = depth_max.float()
 

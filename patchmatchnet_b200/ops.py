@@ -350,6 +350,62 @@ def conv_stem(x: Tensor, w0: Tensor, b0: Tensor, w1: Tensor, b1: Tensor) -> Tens
     return y
 
 
+# K-R (csrc/pm_refine.cu + the one-plane form of csrc/pm_stem.cu): Refinement as two exact-fp32 launches; PMB200_REFINE=0 keeps
+# the six conv-family launches and the ATen tail.
+REFINE_FUSED = os.environ.get("PMB200_REFINE", "1") != "0"
+
+
+def _host_weights(name: str, pairs) -> None:
+    for nm, t, shape in pairs:
+        if t.device.type != "cpu" or t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous():
+            raise RuntimeError(f"{name}: {nm} must be a contiguous float32 HOST tensor of shape {shape}")
+
+
+def refine_low(depth_half: Tensor, depth_min: Tensor, depth_max: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+    """relu(conv2(relu(conv1((depth - lo) / span)))) of Refinement at half resolution (reference models/net.py:104-110), one launch.
+    depth_half [N,1,h,w], depth_min / depth_max [N] on the device; BatchNorm-folded HOST weights.  -> [N,8,h,w], channels-last."""
+    if not _on_device(depth_half) or depth_half.dtype != torch.float32 or depth_half.dim() != 4 or depth_half.shape[1] != 1:
+        raise RuntimeError(f"refine_low: depth_half must be a CUDA float32 [N,1,h,w] tensor (got {depth_half.dtype} {tuple(depth_half.shape)} on {depth_half.device}); no CPU fallback")
+    _host_weights("refine_low", (("w1", w1, (8, 1, 3, 3)), ("b1", b1, (8,)), ("w2", w2, (8, 8, 3, 3)), ("b2", b2, (8,))))
+    N, _, h, w = depth_half.shape
+    dh = depth_half if depth_half.is_contiguous() else depth_half.contiguous()
+    lo, hi = _require(depth_min.reshape(-1), "depth_min", 1), _require(depth_max.reshape(-1), "depth_max", 1)
+    if lo.numel() != N or hi.numel() != N:
+        raise RuntimeError("refine_low: depth_min / depth_max must have one value per image")
+    y = torch.empty((N, 8, h, w), dtype=torch.float32, device=dh.device, memory_format=torch.channels_last)
+    with _device_guard(dh):
+        rc = _native.lib().pmb200_refine_low(dh.data_ptr(), lo.data_ptr(), hi.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                             y.data_ptr(), N, h, w, _stream(dh))
+    _native.check(rc, "refine_low")
+    return y
+
+
+def refine_full(low: Tensor, img: Tensor, depth_half: Tensor, depth_min: Tensor, depth_max: Tensor, wd: Tensor, bd: Tensor, w0: Tensor, b0: Tensor,
+                w3: Tensor, b3: Tensor, wr: Tensor) -> Tensor:
+    """The full-resolution half of Refinement (reference models/net.py:103, :112-120) in one launch: transposed conv of `low`,
+    conv0 of the image, conv3 over their concatenation, the residual conv, `(nearest_up2x(d) + res) * span + lo`.
+    low [N,8,h,w] channels-last (refine_low), img [N,3,2h,2w] NCHW, depth_half [N,1,h,w]; HOST weights.  -> depth [N,1,2h,2w]."""
+    if not _on_device(low) or low.dtype != torch.float32 or low.dim() != 4 or low.shape[1] != 8 or not low.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError("refine_full: low must be a channels-last CUDA float32 [N,8,h,w] tensor; no CPU fallback")
+    N, _, h, w = low.shape
+    if not _on_device(img) or img.dtype != torch.float32 or tuple(img.shape) != (N, 3, 2 * h, 2 * w):
+        raise RuntimeError(f"refine_full: img must be a CUDA float32 [{N},3,{2 * h},{2 * w}] tensor, got {tuple(img.shape)}")
+    if tuple(depth_half.shape) != (N, 1, h, w) or depth_half.dtype != torch.float32 or not _on_device(depth_half):
+        raise RuntimeError(f"refine_full: depth_half must be a CUDA float32 [{N},1,{h},{w}] tensor")
+    _host_weights("refine_full", (("wd", wd, (8, 8, 3, 3)), ("bd", bd, (8,)), ("w0", w0, (8, 3, 3, 3)), ("b0", b0, (8,)),
+                                  ("w3", w3, (8, 16, 3, 3)), ("b3", b3, (8,)), ("wr", wr, (1, 8, 3, 3))))
+    img = img if img.is_contiguous() else img.contiguous()
+    dh = depth_half if depth_half.is_contiguous() else depth_half.contiguous()
+    lo, hi = _require(depth_min.reshape(-1), "depth_min", 1), _require(depth_max.reshape(-1), "depth_max", 1)
+    out = torch.empty((N, 1, 2 * h, 2 * w), dtype=torch.float32, device=low.device)
+    with _device_guard(low):
+        rc = _native.lib().pmb200_refine_full(low.data_ptr(), img.data_ptr(), dh.data_ptr(), lo.data_ptr(), hi.data_ptr(), wd.data_ptr(), bd.data_ptr(),
+                                              w0.data_ptr(), b0.data_ptr(), w3.data_ptr(), b3.data_ptr(), wr.data_ptr(), out.data_ptr(), N, 2 * h, 2 * w,
+                                              _stream(low))
+    _native.check(rc, "refine_full")
+    return out
+
+
 def conv2d_tc5(x: Tensor, filter_tc5: Tensor, bias: Optional[Tensor], cout: int, ks: int, stride: int = 1, pad: int = 0, dil: int = 1,
                relu: bool = False, out: Optional[Tensor] = None, out_channel_offset: int = 0, halo: bool = False) -> Tensor:
     """Channels-last convolution on the 5th-generation tensor cores (csrc/pm_conv5.cu), fp32-accurate.  Same calling

@@ -115,6 +115,12 @@ class EmulatedLibrary:
     def pmb200_conv_stem(self, *args):
         return self.conv.emu_conv_stem(*args)
 
+    def pmb200_refine_low(self, *args):
+        return self.conv.emu_refine_low(*args)
+
+    def pmb200_refine_full(self, *args):
+        return self.conv.emu_refine_full(*args)
+
 
 def install(monkeypatch, emu, emu_conv):
     facade = EmulatedLibrary(emu, emu_conv)

@@ -18,4 +18,9 @@ extern "C" const char *emu_conv_last_error(void) { return g_conv_err; }
 
 // K-S, the fused conv0 -> conv1 stem of FeatureNet (pm_stem.cu): plain fp32 FFMA, nothing to restate under PM_EMU
 #define pmb200_conv_stem emu_conv_stem
+#define pmb200_refine_low emu_refine_low
 #include "../patchmatchnet_b200/csrc/pm_stem.cu"
+
+// K-R: the full-resolution half of Refinement (pm_refine.cu)
+#define pmb200_refine_full emu_refine_full
+#include "../patchmatchnet_b200/csrc/pm_refine.cu"

@@ -399,3 +399,33 @@ def test_gpu_conv_stem_matches_cudnn_fp32(fp32_library):
         assert _scaled_err(got, want) <= 2e-6, (N, H, W)
     with pytest.raises(RuntimeError, match="HOST"):
         ops.conv_stem(x, w0.to(dev), b0, w1, b1)
+
+
+@pytest.mark.gpu
+def test_gpu_fused_refinement_matches_the_layerwise_path(fp32_library, monkeypatch):
+    """K-R (two exact-fp32 launches) against the same module run layer by layer on cuDNN fp32 kernels, and against the
+    conv-family path it replaces; bench size and a ragged one."""
+    from patchmatchnet_b200 import net as pm_net
+    from tests.test_emulated_conv import _random_refinement
+
+    dev = "cuda:0"
+    m = _random_refinement(3).to(dev)
+    g = torch.Generator().manual_seed(5)
+    for (N, h, w) in ((1, 256, 320), (2, 21, 37)):
+        img = torch.rand(N, 3, 2 * h, 2 * w, generator=g).to(dev)
+        dmin = torch.tensor([400.0, 425.0][:N], device=dev)
+        dmax = torch.tensor([900.0, 935.0][:N], device=dev)
+        depth = dmin.view(N, 1, 1, 1) + torch.rand(N, 1, h, w, generator=g).to(dev) * (dmax - dmin).view(N, 1, 1, 1)
+        span = (dmax - dmin).view(N, 1, 1, 1)
+        with torch.no_grad():
+            got = m(img, depth, dmin, dmax)
+            monkeypatch.setattr(ops, "REFINE_FUSED", False)
+            family = m(img, depth, dmin, dmax)                 # conv-family launches + ATen tail
+            monkeypatch.setattr(pm_net, "LIBRARY_FAST_PATH", False)
+            want = m(img, depth, dmin, dmax)                   # the reference's own op sequence on cuDNN fp32
+            monkeypatch.setattr(pm_net, "LIBRARY_FAST_PATH", True)
+            monkeypatch.setattr(ops, "REFINE_FUSED", True)
+        torch.cuda.synchronize()
+        assert got.shape == want.shape == (N, 1, 2 * h, 2 * w)
+        assert float(((got - want).abs() / span).max()) <= 5e-6, (N, h, w)
+        assert float(((family - want).abs() / span).max()) <= 5e-5

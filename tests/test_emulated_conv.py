@@ -21,7 +21,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def emu_conv():
     src = os.path.join(REPO, "tests", "emu_conv.cpp")
     deps = [src, os.path.join(REPO, "tests", "warp_emu.h"), os.path.join(REPO, "include", "patchmatch_b200.h"),
-            os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_conv.cu"), os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_stem.cu")]
+            os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_conv.cu"), os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_stem.cu"),
+            os.path.join(REPO, "patchmatchnet_b200", "csrc", "pm_refine.cu")]
     out = os.path.join(REPO, "tests", "_emu_conv.so")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -35,6 +36,12 @@ def emu_conv():
     lib.emu_conv_last_error.restype = ctypes.c_char_p
     lib.emu_conv_stem.argtypes = [P] * 6 + [I] * 3 + [P]
     lib.emu_conv_stem.restype = I
+    lib.emu_refine_low.argtypes = [P] * 8 + [I] * 3 + [P]
+    lib.emu_refine_low.restype = I
+    lib.emu_refine_full.argtypes = [P] * 13 + [I] * 3 + [P]
+    lib.emu_refine_full.restype = I
+    lib.emu_conv_set_stem_ppt.argtypes = [I]
+    lib.emu_conv_set_stem_ppt.restype = None
     return lib
 
 
@@ -139,8 +146,9 @@ def test_emulated_planner_rejects_bad_arguments(emu_conv):
     assert emu_conv.emu_conv2d_nhwc(*args(yco=4)) == -1 and b"channel slice" in emu_conv.emu_conv_last_error()
 
 
+@pytest.mark.parametrize("ppt", [2, 4])
 @pytest.mark.parametrize("shape", [(2, 21, 45), (1, 16, 32), (1, 37, 70), (3, 5, 9)])
-def test_emulated_stem_matches_two_convs(emu_conv, shape):
+def test_emulated_stem_matches_two_convs(emu_conv, shape, ppt):
     """K-S (csrc/pm_stem.cu, the kernel's own source under the warp emulator): relu(conv1(relu(conv0(x)))) with folded biases
     against the two F.conv2d calls, ragged sizes (partial 32 x 16 tiles, image borders inside the conv0 halo), exact fp32
     arithmetic -> agreement to rounding-order noise."""
@@ -150,9 +158,11 @@ def test_emulated_stem_matches_two_convs(emu_conv, shape):
     w0, b0 = torch.randn(8, 3, 3, 3, generator=g) / 27 ** 0.5, torch.randn(8, generator=g) * 0.5
     w1, b1 = torch.randn(8, 8, 3, 3, generator=g) / 72 ** 0.5, torch.randn(8, generator=g) * 0.5
     y = torch.full((N, H, W, 8), float("nan"))
+    emu_conv.emu_conv_set_stem_ppt(ppt)  # output pixels per thread: 256- or 128-thread CTAs
     rc = emu_conv.emu_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), N, H, W, None)
     assert rc == 0, emu_conv.emu_conv_last_error()
     want = F.relu(F.conv2d(F.relu(F.conv2d(x.double(), w0.double(), b0.double(), padding=1)), w1.double(), b1.double(), padding=1)).float()
+    emu_conv.emu_conv_set_stem_ppt(4)
     got = y.permute(0, 3, 1, 2)
     assert torch.isfinite(got).all()
     assert _scaled_err(got, want) <= 2e-6
@@ -164,3 +174,58 @@ def test_emulated_stem_argument_errors(emu_conv):
     assert emu_conv.emu_conv_stem(None, w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), 1, 4, 4, None) == -1
     assert emu_conv.emu_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), 1, 0, 4, None) == -1
     assert emu_conv.emu_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr() + 4, 1, 4, 4, None) == -1
+
+
+def _random_refinement(seed):
+    from patchmatchnet_b200.net import Refinement
+
+    torch.manual_seed(seed)
+    m = Refinement().eval()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.3)
+                mod.running_mean.normal_(0, 0.3)
+                mod.running_var.uniform_(0.5, 1.5)
+    return m
+
+
+@pytest.mark.parametrize("shape", [(2, 10, 22), (1, 8, 16), (1, 13, 35), (2, 3, 5)])
+def test_emulated_refinement_matches_the_module(emu_conv, shape):
+    """K-R (pm_stem.cu one-plane form + pm_refine.cu, the kernels' own source under the warp emulator) against the Refinement
+    module's reference op sequence in float64 (reference models/net.py:73-122): transposed conv by output parity, halo
+    recompute across tile borders, image borders inside every halo, the residual tail; ragged sizes, two images."""
+    N, h, w = shape
+    m = _random_refinement(N * 100 + h)
+    g = torch.Generator().manual_seed(h * 7 + w)
+    img = torch.rand(N, 3, 2 * h, 2 * w, generator=g)
+    dmin = torch.tensor([400.0, 425.0][:N])
+    dmax = torch.tensor([900.0, 935.0][:N])
+    depth = dmin.view(N, 1, 1, 1) + torch.rand(N, 1, h, w, generator=g) * (dmax - dmin).view(N, 1, 1, 1)
+    with torch.no_grad():
+        want = m.double()(img.double(), depth.double(), dmin.double(), dmax.double()).float()
+        m.float()
+        hw = m.host_weights()
+    low = torch.full((N, h, w, 8), float("nan"))
+    rc = emu_conv.emu_refine_low(depth.data_ptr(), dmin.data_ptr(), dmax.data_ptr(), *(t.data_ptr() for t in hw[:4]), low.data_ptr(), N, h, w, None)
+    assert rc == 0, emu_conv.emu_conv_last_error()
+    assert torch.isfinite(low).all()
+    out = torch.full((N, 1, 2 * h, 2 * w), float("nan"))
+    rc = emu_conv.emu_refine_full(low.data_ptr(), img.data_ptr(), depth.data_ptr(), dmin.data_ptr(), dmax.data_ptr(), *(t.data_ptr() for t in hw[4:]),
+                                  out.data_ptr(), N, 2 * h, 2 * w, None)
+    assert rc == 0, emu_conv.emu_conv_last_error()
+    assert torch.isfinite(out).all()
+    # depths are ~400..935 and the residual is O(span): compare on the normalised scale
+    span = (dmax - dmin).view(N, 1, 1, 1)
+    assert float(((out - want).abs() / span).max()) <= 2e-6
+
+
+def test_emulated_refinement_argument_errors(emu_conv):
+    z = torch.zeros(1, 4, 4, 8)
+    hw = _random_refinement(0).host_weights()
+    img, depth, lo, hi, out = torch.zeros(1, 3, 8, 8), torch.zeros(1, 1, 4, 4), torch.zeros(1), torch.ones(1), torch.zeros(1, 1, 8, 8)
+    args = [z.data_ptr(), img.data_ptr(), depth.data_ptr(), lo.data_ptr(), hi.data_ptr(), *(t.data_ptr() for t in hw[4:]), out.data_ptr()]
+    assert emu_conv.emu_refine_full(*args, 1, 7, 8, None) == -1 and b"even" in emu_conv.emu_conv_last_error()
+    assert emu_conv.emu_refine_full(None, *args[1:], 1, 8, 8, None) == -1
+    assert emu_conv.emu_refine_low(depth.data_ptr(), None, hi.data_ptr(), *(t.data_ptr() for t in hw[:4]), z.data_ptr(), 1, 4, 4, None) == -1

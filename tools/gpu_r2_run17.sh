@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 t0=$(date +%s)
 python -c "import __graft_entry__ as g; g.build(); print('build ok')" > gpurun_out/build.log 2>&1
-timeout 240 python -m pytest tests/test_conv.py -m gpu -x -q --tb=short -p no:cacheprovider -k "stem" > gpurun_out/pytest_stem.log 2>&1
+timeout 240 python -m pytest tests/test_conv.py -m gpu -x -q --tb=short -p no:cacheprovider -k "stem or refinement" > gpurun_out/pytest_stem.log 2>&1
 echo "pytest stem exit $? at $(( $(date +%s) - t0 )) s" >> gpurun_out/pytest_stem.log
 tail -4 gpurun_out/pytest_stem.log | cut -c1-300
 timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
@@ -13,11 +13,11 @@ echo "pytest exit $? at $(( $(date +%s) - t0 )) s" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log | cut -c1-300
 timeout 400 python tools/convbench.py > gpurun_out/convbench.json 2> gpurun_out/convbench.err
 timeout 400 python bench.py --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-PMB200_STEM=0 timeout 300 python bench.py --no-sub --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_stem_off.json 2> gpurun_out/bench_stem_off.err
+PMB200_REFINE=0 timeout 300 python bench.py --no-sub --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_stem_off.json 2> gpurun_out/bench_stem_off.err
 python - <<'PY'
 import json
 try:
-    j=json.load(open("gpurun_out/convbench.json")); print('stem', j['stem'])
+    j=json.load(open("gpurun_out/convbench.json")); print('stem', j['stem']); print('refinement', j['refinement'])
 except Exception as e: print('convbench ERR',e, open("gpurun_out/convbench.err").read()[-500:])
 for f in ("bench_default.json","bench_stem_off.json"):
     try:
