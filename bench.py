@@ -523,8 +523,9 @@ class Workload:
         self.shape = (B, N, H, W)
         self.eng = DepthEngine(net, B, N, H, W, device=str(dev), use_graph=use_graph, n_slots=slots)
         host = synthetic.make_inputs(B, N, H, W, seed=rank)
+        views = torch.stack(host["images"]).pin_memory()  # the request's views as adjacent slices of ONE pinned buffer: one upload
         self.host_pinned = dict(
-            images=[im.pin_memory() for im in host["images"]],
+            images=[views[i] for i in range(views.shape[0])],
             intrinsics=host["intrinsics"].pin_memory(), extrinsics=host["extrinsics"].pin_memory(),
             depth_min=host["depth_min"].pin_memory(), depth_max=host["depth_max"].pin_memory(),
         )

@@ -1141,8 +1141,9 @@ const char *const kTuneNames[kTuneCount] = {"ka_gen", "ka3_dc", "ka3_dc_vw", "ka
                                             "ka4_grid", "ka4_stages", "kb_tp", "kb_dy", "stem_ppt"};
 // ka_gen: 3.  Generation 4 (TMA-staged windows) is parity-green on B200 but slower at every bench shape (cold us, gen 3 / gen 4:
 // 47.6 / 91.7, 20.5 / 33.0, 34.3 / 41.0, 37.0 / 49.1 -- profiles/r2_run3_kbench.json; DESIGN.md has the analysis)
-const int kTuneDefaults[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 4};
-int g_tune[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 4};
+// stem_ppt: 2 (run 19, cold / warm us: 74.4 / 70.9 with 2 pixels per thread, 75.6 / 74.4 with 4: the LDCU : FFMA ratio is not the limiter)
+const int kTuneDefaults[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 2};
+int g_tune[kTuneCount] = {3, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 2};
 inline int tune(Tune t) { return __atomic_load_n(&g_tune[t], __ATOMIC_RELAXED); }
 
 // Third-generation K-A launch (kept for shapes generation 4 does not take and for A/B measurements).

@@ -29,7 +29,7 @@ extern "C" int pmb200_internal_fail(int code, const char *msg);  // pm_kernels.c
 extern "C" int pmb200_internal_launch_status(const char *what);
 extern "C" int pmb200_internal_tuning(const char *key);  // pm_kernels.cu: current value of a pmb200_set_tuning knob
 #else
-static int g_emu_stem_ppt = 4;
+static int g_emu_stem_ppt = 2;
 extern "C" void emu_conv_set_stem_ppt(int v) { g_emu_stem_ppt = v; }
 #endif
 
@@ -194,7 +194,7 @@ int launch_stem(const char *what, const float *x, const float *lo, const float *
         emu::launch(dim3((unsigned)tiles), dim3(128), 0, [&] { conv_stem_kernel<CIN0, NORM, 4>(p); });
     return 0;
 #else
-    if (pmb200_internal_tuning("stem_ppt") == 2)
+    if (pmb200_internal_tuning("stem_ppt") != 4)
         conv_stem_kernel<CIN0, NORM, 2><<<(unsigned)tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     else
         conv_stem_kernel<CIN0, NORM, 4><<<(unsigned)tiles, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -47,25 +47,51 @@ class DepthEngine:
         self.n_slots = max(1, int(n_slots))
         self._slots = []
         for _ in range(self.n_slots):
-            self._slots.append(
-                dict(
-                    images=torch.zeros(N, B, 3, H, W, device=dev),
-                    intrinsics=torch.zeros(B, N, 3, 3, device=dev),
-                    extrinsics=torch.zeros(B, N, 4, 4, device=dev),
-                    depth_min=torch.ones(B, device=dev),
-                    depth_max=torch.full((B,), 2.0, device=dev),
-                    stream=torch.cuda.Stream(device=dev),
-                    host_depth=torch.empty(B, 1, H, W).pin_memory(),
-                    host_conf=torch.empty(B, H, W).pin_memory(),
-                    graph=None,
-                    outs=None,
-                )
+            slot = self._input_block(dev)
+            slot.update(
+                stream=torch.cuda.Stream(device=dev),
+                host_depth=torch.empty(B, 1, H, W).pin_memory(),
+                host_conf=torch.empty(B, H, W).pin_memory(),
+                graph=None,
+                outs=None,
             )
+            self._slots.append(slot)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.compute_stream = self._slots[0]["stream"]
         self.use_graph = use_graph
         self._warmup = warmup
         self._ready = False
+
+    def _input_block(self, dev, pinned_pack: bool = False) -> Dict[str, Tensor]:
+        """Device tensors for one request's inputs.  The cameras and the depth range live in ONE flat `params` buffer (the
+        named entries are views into it): a request's small inputs then move with one copy instead of four -- the serving
+        loop is a few dozen driver calls per request, and at > 1000 requests/s those calls, not the bytes, are the budget."""
+        B, N, H, W = self.shape
+        n_i, n_e = B * N * 9, B * N * 16
+        params = torch.zeros(n_i + n_e + 2 * B, device=dev)
+        params[n_i + n_e:n_i + n_e + B] = 1.0
+        params[n_i + n_e + B:] = 2.0
+        blk = dict(
+            images=torch.zeros(N, B, 3, H, W, device=dev),
+            params=params,
+            intrinsics=params[:n_i].view(B, N, 3, 3),
+            extrinsics=params[n_i:n_i + n_e].view(B, N, 4, 4),
+            depth_min=params[n_i + n_e:n_i + n_e + B],
+            depth_max=params[n_i + n_e + B:],
+        )
+        if pinned_pack:
+            blk["host_params"] = torch.zeros(params.numel()).pin_memory()
+        return blk
+
+    def _pack_params(self, host_pack: Tensor, req: Dict[str, object]) -> int:
+        """Write a request's cameras and depth range into the pinned pack (plain host copies); returns the bytes."""
+        B, N, _, _ = self.shape
+        n_i, n_e = B * N * 9, B * N * 16
+        host_pack[:n_i].copy_(req["intrinsics"].reshape(-1))
+        host_pack[n_i:n_i + n_e].copy_(req["extrinsics"].reshape(-1))
+        host_pack[n_i + n_e:n_i + n_e + B].copy_(req["depth_min"].reshape(-1))
+        host_pack[n_i + n_e + B:].copy_(req["depth_max"].reshape(-1))
+        return 4 * host_pack.numel()
 
     # ------------------------------------------------------------------
     def _forward(self, slot: Dict[str, Tensor]) -> Tuple[Tensor, Tensor]:
@@ -163,63 +189,76 @@ class DepthEngine:
     def _staging(self):
         """Device staging buffers for uploads (2 per slot): the PCIe copy of a request overlaps the compute of the
         slot's previous request, then a device-to-device copy (20 MB at HBM speed) moves it into the slot's
-        graph-captured input buffers."""
+        graph-captured input buffers.  Each carries a pinned host pack for the request's small inputs and the events
+        the loop re-records (no per-request event construction)."""
         if getattr(self, "_stage", None) is None:
             self._stage = []
             for _ in range(2 * self.n_slots):
-                ref = self._slots[0]
-                self._stage.append({k: torch.empty_like(ref[k]) for k in ("images", "intrinsics", "extrinsics", "depth_min", "depth_max")})
+                blk = self._input_block(self.device, pinned_pack=True)
+                blk["uploaded"] = torch.cuda.Event()
+                blk["free"] = torch.cuda.Event()
+                blk["used"] = False
+                self._stage.append(blk)
+            for slot in self._slots:
+                slot["drained"] = torch.cuda.Event()
         return self._stage
 
     def infer_stream(self, requests: Sequence[Dict[str, object]], on_result=None) -> Tuple[int, int]:
         """Pipelined serving loop over pinned-host requests.  Request i is uploaded (copy stream) into a staging
         buffer while earlier requests compute, then slot i % n_slots copies it into its static inputs, replays its
         CUDA graph on its own stream and reads the results back to the slot's pinned host buffers.  Every request
-        pays its host->device and device->host copies.  Returns (h2d_bytes, d2h_bytes) per request."""
+        pays its host->device and device->host copies.  Returns (h2d_bytes, d2h_bytes) per request.
+        Driver calls per request: one image upload when the request's views are adjacent slices of one pinned buffer (else one
+        per view), one upload of the packed cameras + depth range, two device-to-device copies, the graph launch, two result
+        downloads, three event records."""
+        from .net import _adjacent_views
+
         if not self._ready:
             self._first_use(requests[0])
         S = self.n_slots
         stage = self._staging()
         NS = len(stage)
-        keys = ("images", "intrinsics", "extrinsics", "depth_min", "depth_max")
         h2d = d2h = 0
-        stage_free = [None] * NS  # recorded on a slot stream once the staging buffer has been copied out
-        drained = [None] * S      # recorded on the slot stream once its outputs are in pinned host memory
+        used = [False] * S  # slot has a result in flight from this call
+        for buf in stage:
+            buf["used"] = False
         with torch.cuda.device(self.device):
             for i, req in enumerate(requests):
                 k, j = i % S, i % NS
                 slot, buf = self._slots[k], stage[j]
-                if stage_free[j] is not None:
-                    self.copy_stream.wait_event(stage_free[j])
+                if buf["used"]:
+                    self.copy_stream.wait_event(buf["free"])  # the slot that consumed this staging buffer has copied it out
+                    buf["uploaded"].synchronize()             # ... and its pinned pack has long been read by the copy engine
+                h2d = self._pack_params(buf["host_params"], req)
+                images = req["images"]
                 with torch.cuda.stream(self.copy_stream):
-                    h2d = 0
-                    for v, im in enumerate(req["images"]):
-                        buf["images"][v].copy_(im, non_blocking=True)
-                        h2d += im.numel() * im.element_size()
-                    for kk in keys[1:]:
-                        src = req[kk]
-                        buf[kk].copy_(src.reshape(buf[kk].shape), non_blocking=True)
-                        h2d += src.numel() * src.element_size()
-                    uploaded = torch.cuda.Event()
-                    uploaded.record(self.copy_stream)
-                if on_result is not None and drained[k] is not None:
-                    drained[k].synchronize()  # hand the slot's previous result to the caller before it is overwritten
+                    first = images[0]
+                    if len(images) == buf["images"].shape[0] and _adjacent_views(images):
+                        stacked = torch.as_strided(first, (len(images),) + tuple(first.shape), (first.numel(),) + tuple(first.stride()))
+                        buf["images"].copy_(stacked, non_blocking=True)
+                        h2d += stacked.numel() * stacked.element_size()
+                    else:
+                        for v, im in enumerate(images):
+                            buf["images"][v].copy_(im, non_blocking=True)
+                            h2d += im.numel() * im.element_size()
+                    buf["params"].copy_(buf["host_params"], non_blocking=True)
+                    buf["uploaded"].record(self.copy_stream)
+                buf["used"] = True
+                if on_result is not None and used[k]:
+                    slot["drained"].synchronize()  # hand the slot's previous result to the caller before it is overwritten
                     on_result(i - S, slot["host_depth"], slot["host_conf"])
                 st = slot["stream"]
                 with torch.cuda.stream(st):
-                    st.wait_event(uploaded)
-                    for kk in keys:
-                        slot[kk].copy_(buf[kk], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    stage_free[j] = ev
+                    st.wait_event(buf["uploaded"])
+                    slot["images"].copy_(buf["images"], non_blocking=True)
+                    slot["params"].copy_(buf["params"], non_blocking=True)
+                    buf["free"].record(st)
                     depth, conf = self.run_slot(k)
                     slot["host_depth"].copy_(depth, non_blocking=True)
                     slot["host_conf"].copy_(conf, non_blocking=True)
                     d2h = depth.numel() * 4 + conf.numel() * 4
-                    done = torch.cuda.Event()
-                    done.record(st)
-                    drained[k] = done
+                    slot["drained"].record(st)
+                    used[k] = True
             for k in range(S):
                 self._slots[k]["stream"].synchronize()
             if on_result is not None:

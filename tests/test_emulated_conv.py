@@ -162,7 +162,7 @@ def test_emulated_stem_matches_two_convs(emu_conv, shape, ppt):
     rc = emu_conv.emu_conv_stem(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), y.data_ptr(), N, H, W, None)
     assert rc == 0, emu_conv.emu_conv_last_error()
     want = F.relu(F.conv2d(F.relu(F.conv2d(x.double(), w0.double(), b0.double(), padding=1)), w1.double(), b1.double(), padding=1)).float()
-    emu_conv.emu_conv_set_stem_ppt(4)
+    emu_conv.emu_conv_set_stem_ppt(2)
     got = y.permute(0, 3, 1, 2)
     assert torch.isfinite(got).all()
     assert _scaled_err(got, want) <= 2e-6
