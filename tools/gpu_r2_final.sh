@@ -20,7 +20,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 3 --repeats 1 --no-sub --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 echo "ncu lists done at $(( $(date +%s) - t0 )) s"
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:"warp_corr|adaptive_eval|conv5" -o gpurun_out/native_full -f python tools/profile_forward.py > gpurun_out/ncu_full.log 2>&1
+    -k regex:"warp_corr|adaptive_eval|conv5|conv_stem|refine_full" -o gpurun_out/native_full -f python tools/profile_forward.py > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $? at $(( $(date +%s) - t0 )) s"
 python - <<'PY'
 import json
