@@ -329,9 +329,8 @@ __global__ void __launch_bounds__(kThreads) conv5_kernel(const Conv5Params p, co
 // (3 MMAs of N = Npad per K slice, ~23 issue-thread instructions each) ran at 146 cycles per MMA, bound by the issuing thread.
 // So (a) the filter tap is stored as ONE operand [chunk][w_hi rows | w_lo rows][4 floats] (ops.pack_conv_filter_tc5h):
 // a_hi x [w_hi | w_lo] is one MMA of N = 2 Npad into columns [0, 2 Npad), a_lo x w_hi one of N = Npad into [0, Npad) -- 2 MMAs
-// per K slice instead of 3; (b) the issue loop carries descriptors as (lo, hi) words and only adds 16-byte offsets to the low
-// word; (c) the two MMAs of a slice are issued by TWO warps into disjoint accumulator columns (the epilogue adds the three column
-// groups): one issuing thread could not keep the tensor pipe busy.
+// per K slice instead of 3, the epilogue adds the two column halves; (b) the issue loop carries descriptors as (lo, hi) words
+// and only adds 16-byte offsets to the low word.
 // ----------------------------------------------------------------------------------------------------------------------
 constexpr int kHTW = 8, kHTH = 16;
 
@@ -360,21 +359,20 @@ __device__ __forceinline__ void stamp(const Conv5hParams &p, int role, int it, i
 
 // Operands of this kernel are no-swizzle K-major: core matrices of 8 rows x 16 bytes; descriptor LBO = distance of the
 // K-adjacent core matrix, SBO = distance of the next 8-row group, version bit 46, layout type 0.
-// One issuer's MMAs of one filter tap: per 8-channel slice ONE tcgen05.mma of its A stream (a_hi planes with the N = 2 Npad
-// operand [w_hi | w_lo], or a_lo planes with the N = Npad operand w_hi) into ITS OWN accumulator columns.
+// the MMAs of one filter tap: per 8-channel slice a_hi x [w_hi | w_lo] (N = 2 Npad) and a_lo x w_hi (N = Npad)
 template <int KSL>
-__device__ __forceinline__ void issue_tap(bool leader, uint32_t tacc, uint32_t a, uint32_t w, uint32_t a_kstep, uint32_t w_kstep,
-                                          uint32_t a_hiword, uint32_t w_hiword, uint32_t idesc, uint32_t first) {
+__device__ __forceinline__ void issue_tap(bool leader, uint32_t tacc, uint32_t ah, uint32_t al, uint32_t w, uint32_t a_kstep, uint32_t w_kstep,
+                                          uint32_t a_hiword, uint32_t w_hiword, uint32_t idesc, uint32_t idesc2, uint32_t first) {
     if (!leader) return;
 #pragma unroll
-    for (int k = 0; k < KSL; ++k)
-        tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | (a + k * a_kstep), ((uint64_t)w_hiword << 32) | (w + k * w_kstep), idesc,
-                    k == 0 ? first : 1u);
+    for (int k = 0; k < KSL; ++k) {
+        const uint64_t dw = ((uint64_t)w_hiword << 32) | (w + k * w_kstep);
+        tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | (ah + k * a_kstep), dw, idesc2, k == 0 ? first : 1u);
+        tc_mma_tf32(tacc, ((uint64_t)a_hiword << 32) | (al + k * a_kstep), dw, idesc, 1);
+    }
 }
 
-constexpr int kHThreads = 352;  // conv5_kernel's ten warps + a second MMA issuer (warp 10)
-
-__global__ void __launch_bounds__(kHThreads) conv5h_kernel(const Conv5hParams p, const __grid_constant__ CUtensorMap xmap) {
+__global__ void __launch_bounds__(kThreads) conv5h_kernel(const Conv5hParams p, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t *h_full = reinterpret_cast<uint64_t *>(smem);  // [2] halo tile landed in a staging buffer
@@ -396,13 +394,13 @@ __global__ void __launch_bounds__(kHThreads) conv5h_kernel(const Conv5hParams p,
             mbar_init(&h_full[a], 1);
             mbar_init(&s_free[a], 4);
             mbar_init(&h_split[a], 4);
-            mbar_init(&h_empty[a], 2);   // both MMA issuers commit
-            mbar_init(&acc_full[a], 2);
+            mbar_init(&h_empty[a], 1);
+            mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);
         }
         for (int s = 0; s < p.wstages; ++s) {
             mbar_init(&w_full[s], 1);
-            mbar_init(&w_empty[s], 2);
+            mbar_init(&w_empty[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -452,19 +450,13 @@ __global__ void __launch_bounds__(kHThreads) conv5h_kernel(const Conv5hParams p,
                 }
             }
         }
-    } else if (warp == 1 || warp == 10) {
-        // ------------------------------------------------ MMA issuers ------------------------------------------------
-        // TWO issuing warps, each with its own A stream and its own accumulator columns: warp 1 issues a_hi x [w_hi | w_lo]
-        // (N = 2 Npad, columns [0, 2 Npad) of the tile's accumulator set), warp 10 issues a_lo x w_hi (N = Npad, columns
-        // [2 Npad, 3 Npad)); the epilogue adds the three column groups.  No ordering is needed between the two streams
-        // (disjoint columns), every completion barrier simply counts two commits.  Why: one issuing thread needs ~80 cycles
-        // per MMA (role trace) against the tensor pipe's 49 -- the issue loop, not the pipe, bounded the kernel.
-        // Each WHOLE warp runs the loops on warp-uniform values only (kernel parameters, blockIdx, loop counters): the
-        // compiler keeps descriptors and addresses in uniform registers and the tcgen05 instructions issue back to back
+    } else if (warp == 1) {
+        // ------------------------------------------------- MMA issuer -------------------------------------------------
+        // The WHOLE warp runs the loops, on warp-uniform values only (kernel parameters, blockIdx, loop counters): the
+        // compiler then keeps descriptors and addresses in uniform registers and the tcgen05 instructions issue back to back
         // from the elected lane.  (Run under `if (lane == 0)` every MMA was wrapped in an R2UR / ELECT / BRA.U.ANY sequence:
-        // 108 cycles per MMA.)
+        // 108 cycles per MMA measured by the role trace, twice the tensor pipe's 49.)
         const bool leader = elect_one();
-        const bool lo_stream = warp == 10;
         int it = 0, s = 0;
         uint32_t wpar = 0;
         const int kslices = p.Cin / 8;
@@ -474,32 +466,32 @@ __global__ void __launch_bounds__(kHThreads) conv5h_kernel(const Conv5hParams p,
         const uint32_t w_hiword = (128u >> 4) | (1u << 14);                   // SBO = 128 bytes
         const uint32_t a_lbo16 = (uint32_t)p.plane_bytes >> 4, w_lbo16 = 2u * (uint32_t)p.Npad;  // next chunk: plane / 2 Npad rows
         const uint32_t a_kstep = 2u * a_lbo16, w_kstep = 2u * w_lbo16;        // one K slice = two chunks
-        const uint32_t halo_u32 = smem_u32(halo0) + (lo_stream ? (uint32_t)p.a_stride : 0u), ring_u32 = smem_u32(wring);
-        const uint32_t idesc = lo_stream ? p.idesc : p.idesc2;
-        const uint32_t col0 = lo_stream ? 2u * (uint32_t)p.Npad : 0u;
+        const uint32_t halo_u32 = smem_u32(halo0), ring_u32 = smem_u32(wring);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int hb = it % p.hbufs, ab = it & 1;
-            const uint32_t tacc = tmem + (uint32_t)(ab * 3 * p.Npad) + col0;
+            const uint32_t tacc = tmem + (uint32_t)(ab * 2 * p.Npad);
             mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);
-            if (lane == 0 && !lo_stream) stamp(p, 1, it, 0);
+            if (lane == 0) stamp(p, 1, it, 0);
             mbar_wait(&h_split[hb], (uint32_t)(it / p.hbufs) & 1u);
-            if (lane == 0 && !lo_stream) stamp(p, 1, it, 1);
+            if (lane == 0) stamp(p, 1, it, 1);
             tc_fence_after();
-            const uint32_t a_lo = ((halo_u32 + (uint32_t)(hb * 2 * p.a_stride)) >> 4) | (a_lbo16 << 16);
-            uint32_t first = 0;  // 0 for this stream's very first MMA of the tile (overwrites its accumulator columns)
+            const uint32_t ahi_lo = ((halo_u32 + (uint32_t)(hb * 2 * p.a_stride)) >> 4) | (a_lbo16 << 16);
+            const uint32_t alo_lo = ahi_lo + ((uint32_t)p.a_stride >> 4);
+            uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrites the accumulator)
             for (int ky = 0; ky < p.KS; ++ky) {
                 for (int kx = 0; kx < p.KS; ++kx) {
                     if (!p.w_resident || it == 0) {  // a resident filter is waited for once, during the first tile
                         mbar_wait(&w_full[s], wpar);
                         tc_fence_after();
                     }
-                    const uint32_t a = a_lo + (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil);
+                    const uint32_t shift = (uint32_t)((ky * p.dil) * p.hcols + kx * p.dil);
+                    const uint32_t ah = ahi_lo + shift, al = alo_lo + shift;
                     const uint32_t w = ((ring_u32 + (uint32_t)(s * 2 * p.w_bytes)) >> 4) | (w_lbo16 << 16);
                     switch (kslices) {  // unrolled: the per-slice descriptor steps become immediates of uniform adds
-                    case 1: issue_tap<1>(leader, tacc, a, w, a_kstep, w_kstep, a_hiword, w_hiword, idesc, first); break;
-                    case 2: issue_tap<2>(leader, tacc, a, w, a_kstep, w_kstep, a_hiword, w_hiword, idesc, first); break;
-                    case 4: issue_tap<4>(leader, tacc, a, w, a_kstep, w_kstep, a_hiword, w_hiword, idesc, first); break;
-                    default: issue_tap<8>(leader, tacc, a, w, a_kstep, w_kstep, a_hiword, w_hiword, idesc, first); break;
+                    case 1: issue_tap<1>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
+                    case 2: issue_tap<2>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
+                    case 4: issue_tap<4>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
+                    default: issue_tap<8>(leader, tacc, ah, al, w, a_kstep, w_kstep, a_hiword, w_hiword, p.idesc, p.idesc2, first); break;
                     }
                     first = 1;
                     if (p.w_resident) {
@@ -511,10 +503,10 @@ __global__ void __launch_bounds__(kHThreads) conv5h_kernel(const Conv5hParams p,
                 }
             }
             if (leader) {
-                tc_commit(&h_empty[hb]);   // plane set free once every MMA of the tile (both streams) has read it
+                tc_commit(&h_empty[hb]);   // plane set free once every MMA of the tile has read it
                 tc_commit(&acc_full[ab]);
             }
-            if (lane == 0 && !lo_stream) stamp(p, 1, it, 2);
+            if (lane == 0) stamp(p, 1, it, 2);
         }
     } else if (warp < 6) {
         // ------------------------------------------------ 3xTF32 split ------------------------------------------------
@@ -568,13 +560,10 @@ __global__ void __launch_bounds__(kHThreads) conv5h_kernel(const Conv5hParams p,
             const bool inside = oy < p.Ho && ox < p.Wo;
             float *dst = p.y + (((size_t)n * p.Ho + (inside ? oy : 0)) * p.Wo + (inside ? ox : 0)) * p.ycs + p.yco;
             for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-                float v[16], u[16], t3[16];
-                const uint32_t tcol = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 3 * p.Npad + c0);
-                tmem_ld16(tcol, v);                            // a_hi.w_hi
-                tmem_ld16(tcol + (uint32_t)p.Npad, u);         // a_hi.w_lo
-                tmem_ld16(tcol + 2u * (uint32_t)p.Npad, t3);   // a_lo.w_hi
-#pragma unroll
-                for (int i = 0; i < 16; ++i) u[i] += t3[i];    // the two small terms first
+                float v[16], u[16];
+                const uint32_t tcol = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 2 * p.Npad + c0);
+                tmem_ld16(tcol, v);                        // a_hi.w_hi + a_lo.w_hi
+                tmem_ld16(tcol + (uint32_t)p.Npad, u);     // a_hi.w_lo
                 if (c0 + 16 >= p.Npad) {
                     tc_fence_before();
                     __syncwarp();
@@ -762,7 +751,7 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
     p.w_bytes = p.Npad * Cin * 4;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
     p.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * p.Npad >> 3) << 17) | ((128u >> 4) << 24);
-    p.tmem_cols = 6 * p.Npad <= 128 ? 128u : (6 * p.Npad <= 256 ? 256u : 512u);  // two accumulator sets of 3 Npad fp32 columns
+    p.tmem_cols = 4 * p.Npad <= 64 ? 64u : (4 * p.Npad <= 128 ? 128u : 256u);  // two accumulators of 2 Npad fp32 columns
     if ((unsigned)p.plane_bytes >= (1u << 18) || p.hcols * 16 >= (1 << 18))
         return pmb200_internal_fail(PMB200_EUNSUPPORTED, "conv2d_tc5h: halo tile exceeds the descriptor's 14-bit offsets");
     int dev = 0, sms = 0, smem_optin = 0;
@@ -790,7 +779,7 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
     }
     const int fixed = fixed_of(p.sbufs, p.hbufs);
     int ctas = 1;
-    if (2 * (fixed + wst * 2 * p.w_bytes + 1024) <= smem_optin + 1024 && p.tmem_cols <= 256u) ctas = 2;  // 512 TMEM columns per SM
+    if (2 * (fixed + wst * 2 * p.w_bytes + 1024) <= smem_optin + 1024) ctas = 2;
     p.wstages = wst;
     const int smem = fixed + wst * 2 * p.w_bytes;
     static std::atomic<unsigned long long> optin_done{0};
@@ -806,7 +795,7 @@ int pmb200_conv2d_tc5h(const float *x_nhwc, const float *filter_tc5h, const floa
         return pmb200_internal_fail(PMB200_EINVAL, "conv2d_tc5h: tensor map rejected (alignment / size)");
     long long grid = (long long)sms * ctas;
     if (grid > tiles) grid = tiles;
-    conv5h_kernel<<<(unsigned)grid, kHThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, xmap);
+    conv5h_kernel<<<(unsigned)grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, xmap);
     return pmb200_internal_launch_status("conv2d_tc5h");
 }
 
