@@ -428,6 +428,75 @@ def time_warp_corr_in_step(net, dev_inputs, peak_gbs, flush, steps=10, warmup=3)
     return [_ka_row(n, a, k, ts, peak_gbs) for (n, a, k, ts) in per_call]
 
 
+def time_eval_propagate_in_step(net, dev_inputs, peak_gbs, flush, steps=10, warmup=2):
+    """K-B (adaptive evaluation) and K-C (initialisation / propagation) launches timed live inside eager steps, like K-A's:
+    one row per launch of a step with SURVEY.md 8(d)'s algorithmic bytes -- K-B 4*B*H*W*(3D + 3K + 1), K-C 4*B*H*W*(Ns + 2Kp + (Ns + Kp)).
+    Best effort: any surprise returns None and leaves the bench line as it is."""
+    import inspect
+
+    from patchmatchnet_b200 import ops
+
+    names = ("adaptive_eval", "init_propagate")
+    origs = {n: getattr(ops, n) for n in names}
+    sigs = {n: inspect.signature(origs[n]) for n in names}
+    record = []
+
+    def make_spy(n):
+        def spy(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = origs[n](*a, **k)
+            e1.record()
+            try:
+                b = sigs[n].bind(*a, **k).arguments
+                if n == "adaptive_eval":
+                    B, D, H, W = b["depth_sample"].shape
+                    K = b["offsets"].shape[1] // 2
+                    shape, alg = f"D{D} K{K} {H}x{W} B{B}", 4 * B * H * W * (3 * D + 3 * K + 1)
+                else:
+                    seed = b["seed_map"]
+                    B, H, W = seed.shape[0], seed.shape[-2], seed.shape[-1]
+                    Ns, Kp = int(b["Ns"]), int(b["Kp"])
+                    shape, alg = f"Ns{Ns} Kp{Kp} {H}x{W} B{B}", 4 * B * H * W * (Ns + 2 * Kp + (Ns + Kp))
+                record.append((n, shape, alg, e0, e1))
+            except Exception:  # noqa: BLE001
+                pass
+            return out
+        return spy
+
+    per_call = []
+    try:
+        for n in names:
+            setattr(ops, n, make_spy(n))
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                record.clear()
+                flush()
+                torch.cuda._sleep(60_000_000)  # park the GPU so that the whole step is queued before it starts (see K-A's)
+                torch.manual_seed(0)
+                net(*dev_inputs())
+                torch.cuda.synchronize()
+                if it >= warmup:
+                    for i, (n, shape, alg, e0, e1) in enumerate(record):
+                        if len(per_call) <= i:
+                            per_call.append((n, shape, alg, []))
+                        per_call[i][3].append(e0.elapsed_time(e1) * 1e-3)
+    except Exception:  # noqa: BLE001
+        return None
+    finally:
+        for n in names:
+            setattr(ops, n, origs[n])
+    rows = []
+    for n, shape, alg, ts in per_call:
+        med = statistics.median(ts)
+        kept = [x for x in ts if x <= 5.0 * med] or ts
+        t = statistics.mean(kept)
+        rows.append({"entry": n, "kernel": "K-B" if n == "adaptive_eval" else "K-C", "shape": shape, "us": 1e6 * t, "us_min": 1e6 * min(kept),
+                     "algorithmic_bytes": alg, "achieved_gbs": alg / t / 1e9, "frac": alg / t / 1e9 / peak_gbs,
+                     "samples": len(kept), "dropped_host_stall_samples": len(ts) - len(kept)})
+    return rows or None
+
+
 def time_warp_corr_isolated(net, dev_inputs, peak_gbs, flush, iters=10):
     """The same launches re-run one at a time with L2 flushed before EACH launch (cold inputs from HBM)."""
     from patchmatchnet_b200 import ops
@@ -746,9 +815,14 @@ def main() -> None:
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     roofline, detail, detail_cold, cpu_baseline, gpu_eager, latency, sub = None, None, None, None, None, None, {}
+    detail_kb_kc = None
     if rank == 0:
         roofline, detail = ka_roofline(net, wl, peak_gbs, peak_src, flush, steps=max(5, args.steps // 2))
         detail_cold = time_warp_corr_isolated(net, wl.dev_inputs, peak_gbs, flush)
+        try:
+            detail_kb_kc = time_eval_propagate_in_step(net, wl.dev_inputs, peak_gbs, flush, steps=max(5, args.steps // 2))
+        except Exception:  # noqa: BLE001
+            detail_kb_kc = None
         latency = single_request_latency(wl, flush, stream)
     if world == 1 and not args.no_sub:
         # (1) the same workload under torch's default flags (TF32 operands in the convs), as round 1 timed it: own net so that
@@ -836,6 +910,7 @@ def main() -> None:
             "native_kernels_per_step": {k: v // max(1, forwards_counted) for k, v in sorted(lc.by_name.items())},
             "clocks": clocks,
             "roofline": roofline, "roofline_detail": detail, "roofline_detail_cold_isolated": detail_cold,
+            "roofline_detail_eval_propagate": detail_kb_kc,
             "cpu_baseline": cpu_baseline,
             "gpu_eager_reference": gpu_eager,
         }
