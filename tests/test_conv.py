@@ -382,6 +382,44 @@ def test_conv_stem_rejects_what_it_cannot_serve():
         ops.conv_stem(torch.zeros(1, 3, 8, 8), w0, b0, w1, b1)
 
 
+def test_fused_refinement_wrappers_reject_cpu_tensors_and_device_weights():
+    """ops.refine_low / ops.refine_full: no CPU fallback for the maps, and the weights must be HOST tensors (they travel in the
+    kernel parameter block)."""
+    from patchmatchnet_b200.net import Refinement
+
+    hw = Refinement().eval().host_weights()
+    assert [tuple(t.shape) for t in hw] == [(8, 1, 3, 3), (8,), (8, 8, 3, 3), (8,), (8, 8, 3, 3), (8,), (8, 3, 3, 3), (8,), (8, 16, 3, 3), (8,), (1, 8, 3, 3)]
+    assert all(t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous() for t in hw)
+    depth, lo, hi = torch.zeros(1, 1, 4, 4), torch.zeros(1), torch.ones(1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.refine_low(depth, lo, hi, *hw[:4])
+    low = torch.zeros(1, 8, 4, 4).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.refine_full(low, torch.zeros(1, 3, 8, 8), depth, lo, hi, *hw[4:])
+
+
+def test_refinement_host_weights_fold_batchnorm_like_the_module():
+    """Refinement.host_weights(): conv + eval-mode BatchNorm folded (transposed conv over its OUTPUT channel) reproduce the
+    module's own layers on random inputs."""
+    from tests.test_emulated_conv import _random_refinement
+
+    m = _random_refinement(11)
+    w1, b1, w2, b2, wd, bd, w0, b0, w3, b3, wr = m.host_weights()
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        x1 = torch.randn(1, 1, 6, 7, generator=g)
+        assert torch.allclose(F.relu(F.conv2d(x1, w1, b1, padding=1)), m.conv1(x1), atol=1e-5)
+        x8 = torch.randn(1, 8, 6, 7, generator=g)
+        assert torch.allclose(F.relu(F.conv2d(x8, w2, b2, padding=1)), m.conv2(x8), atol=1e-5)
+        up = F.relu(F.conv_transpose2d(x8, wd, bd, stride=2, padding=1, output_padding=1))
+        assert torch.allclose(up, F.relu(m.bn(m.deconv(x8))), atol=1e-5)
+        x3 = torch.randn(1, 3, 6, 7, generator=g)
+        assert torch.allclose(F.relu(F.conv2d(x3, w0, b0, padding=1)), m.conv0(x3), atol=1e-5)
+        x16 = torch.randn(1, 16, 6, 7, generator=g)
+        assert torch.allclose(F.relu(F.conv2d(x16, w3, b3, padding=1)), m.conv3(x16), atol=1e-5)
+        assert torch.equal(wr, m.res.weight)
+
+
 @pytest.mark.gpu
 def test_gpu_conv_stem_matches_cudnn_fp32(fp32_library):
     """K-S (fused conv0 -> conv1 of FeatureNet, exact fp32 FFMA with the weights in the constant bank) against the two cuDNN
