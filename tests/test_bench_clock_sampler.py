@@ -57,3 +57,21 @@ def test_falls_back_without_nvml_and_without_nvidia_smi(monkeypatch):
     s.mark_end()
     out = s.stop()
     assert out["sm_mhz"] is None and out["reasons"]
+
+
+def test_roofline_row_uses_survey_bytes_and_drops_host_stall_samples():
+    """bench._ka_row: algorithmic bytes = V * 4*B*H*W*(2C + D + G*D), mean launch time over the samples, and a
+    sample that timed a host stall (far above the median) is dropped and counted instead of poisoning the mean."""
+    import torch
+
+    import bench
+
+    B, H, W, C, V, D, G = 1, 64, 80, 64, 4, 32, 8
+    ref, src, rt, depth = torch.zeros(B, H, W, C), torch.zeros(V, B, H, W, C), torch.zeros(V, B, 12), torch.zeros(B, D, H, W)
+    times = [20e-6] * 9 + [60e-3]  # nine clean samples and one 60 ms host stall (run 17 of round 2 saw exactly this)
+    row = bench._ka_row("warp_corr_score", (ref, src, rt, depth, G), {}, times, 6581.6)
+    assert row["algorithmic_bytes"] == V * 4 * B * H * W * (2 * C + D + G * D) == 34078720
+    assert row["dropped_host_stall_samples"] == 1 and row["samples"] == 9
+    assert abs(row["us"] - 20.0) < 1e-6 and abs(row["frac"] - 34078720 / 20e-6 / 1e9 / 6581.6) < 1e-9
+    clean = bench._ka_row("warp_corr_score", (ref, src, rt, depth, G), {}, [20e-6, 22e-6, 21e-6], 6581.6)
+    assert clean["dropped_host_stall_samples"] == 0 and clean["samples"] == 3
